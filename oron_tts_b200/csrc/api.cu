@@ -1,0 +1,338 @@
+// C ABI (include/oron_b200.h) for the tensor-core and row-wise kernels: argument checks,
+// TMA descriptor construction and launches. No device memory is allocated here.
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/oron_b200.h"
+#include "attn_tcgen05.cuh"
+#include "gemm_tcgen05.cuh"
+#include "host_util.h"
+#include "rowwise.cuh"
+
+using namespace oron;
+
+namespace oron {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(int(e), "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+}  // namespace oron
+
+// ---------------------------------------------------------------------------
+// TMA descriptors
+// ---------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), SWIZZLE_128B, box = (64, box1, 1); OOB reads give zeros.
+static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                          uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box1, int rank) {
+  PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
+  if (!enc) return fail(ORON_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(ORON_ERR_BAD_ARG, "TMA base not 16-byte aligned");
+  if ((stride1_elems * 2) % 16 != 0 || (rank == 3 && (stride2_elems * 2) % 16 != 0))
+    return fail(ORON_ERR_BAD_ARG, "TMA strides must be multiples of 16 bytes (ld %llu)", (unsigned long long)stride1_elems);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {64, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ORON_ERR_BAD_ARG, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// GEMM
+// ---------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int max_ctas, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(int(e), "gemm smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles_m = ((a.rows_per_batch + GEMM_BM - 1) / GEMM_BM) * a.nbatch;
+  const int tiles_n = (a.N + BN - 1) / BN;
+  int grid = tiles_m * tiles_n;
+  const int cap = max_ctas > 0 ? max_ctas : num_sms();
+  if (grid > cap) grid = cap;
+  if (grid <= 0) return 0;
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, a);
+  return check_launch("gemm_bf16_tcgen05");
+}
+
+extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
+  if (!d || !d->A || !d->W || !d->out) return fail(ORON_ERR_BAD_ARG, "gemm: null pointer");
+  if (d->rows_per_batch <= 0 || d->nbatch <= 0 || d->N <= 0 || d->w_cols <= 0)
+    return fail(ORON_ERR_BAD_ARG, "gemm: bad shape");
+  const int taps = d->taps > 0 ? d->taps : 1;
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows_per_batch = d->rows_per_batch;
+  a.nbatch = d->nbatch;
+  a.N = d->N;
+  if (taps == 1) {
+    a.num_kb = (d->w_cols + GEMM_BK - 1) / GEMM_BK;
+    a.cpb = a.num_kb;
+    a.pad = 0;
+    a.grouped = 0;
+  } else {
+    if (d->cin_blocks <= 0 || d->w_cols != taps * d->cin_blocks * GEMM_BK)
+      return fail(ORON_ERR_BAD_ARG, "conv-gemm: w_cols must equal taps*cin_blocks*64");
+    if (d->grouped && (d->block_n != 64 || d->cin_blocks != 1))
+      return fail(ORON_ERR_BAD_ARG, "grouped conv-gemm needs block_n == 64 and 64-channel groups");
+    a.num_kb = taps * d->cin_blocks;
+    a.cpb = d->cin_blocks;
+    a.pad = d->pad;
+    a.grouped = d->grouped ? 1 : 0;
+  }
+  a.act = d->act;
+  a.bias = d->bias;
+  a.out = d->out;
+  a.ldo = d->ldo;
+  a.out2 = d->out2;
+  a.ldo2 = d->ldo2;
+  a.addend = d->addend;
+  a.ld_add = d->ld_add;
+  a.gate = d->gate;
+  a.gate_ld = d->gate_ld;
+  a.gate_nb = d->gate_nb > 0 ? d->gate_nb : 1;
+  a.gate_step_stride = d->gate_step_stride;
+  a.step_ptr = d->step_ptr;
+  a.rope_cos = d->rope_cos;
+  a.rope_sin = d->rope_sin;
+  a.rope_cols = d->rope_cols;
+  a.seq_lens = d->seq_lens;
+  a.row_valid = d->row_valid;
+  a.mask_rows = d->mask_rows;
+
+  const int epi = d->epilogue;
+  // per-epilogue operand checks (vectorised epilogues assume 32-column granularity)
+  const bool vec_epi = epi == EPI_QKV_ROPE || epi == EPI_GATE_RESID || epi == EPI_EMBED_DUAL ||
+                       epi == EPI_MISH_MASK_BF16 || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID;
+  if (vec_epi && (d->N % 32 != 0)) return fail(ORON_ERR_BAD_ARG, "gemm: epilogue %d needs N %% 32 == 0", epi);
+  if (epi == EPI_QKV_ROPE && (!d->bias || !d->rope_cos || !d->rope_sin || d->N % 64 != 0 || d->block_n < 128))
+    return fail(ORON_ERR_BAD_ARG, "gemm: QKV_ROPE needs bias, rope tables, N %% 64 == 0, block_n >= 128");
+  if (epi == EPI_GATE_RESID && !d->gate) return fail(ORON_ERR_BAD_ARG, "gemm: GATE_RESID needs gate");
+  if ((epi == EPI_EMBED_DUAL || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID) && !d->addend)
+    return fail(ORON_ERR_BAD_ARG, "gemm: epilogue %d needs addend", epi);
+  if (epi == EPI_EMBED_DUAL && !d->out2) return fail(ORON_ERR_BAD_ARG, "gemm: EMBED_DUAL needs out2");
+  if ((d->ldo % 8) != 0 && epi != EPI_F32) return fail(ORON_ERR_BAD_ARG, "gemm: ldo must be a multiple of 8");
+  if (epi == EPI_F32 && (d->ldo % 4) != 0) return fail(ORON_ERR_BAD_ARG, "gemm: f32 ldo must be a multiple of 4");
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, d->A, uint64_t(d->a_cols), uint64_t(d->rows_per_batch), uint64_t(d->nbatch),
+                          uint64_t(d->lda), uint64_t(d->lda) * uint64_t(d->rows_per_batch), GEMM_BM, 3);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, d->W, uint64_t(d->w_cols), uint64_t(d->N), 1, uint64_t(d->ldw), 0, uint32_t(d->block_n), 2);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+#define ORON_GEMM_CASE(BN_, EPI_) \
+  if (d->block_n == BN_ && epi == EPI_) return launch_gemm<BN_, EPI_>(ta, tb, a, d->max_ctas, st);
+  ORON_GEMM_CASE(128, EPI_BF16)
+  ORON_GEMM_CASE(256, EPI_BF16)
+  ORON_GEMM_CASE(64, EPI_BF16)
+  ORON_GEMM_CASE(128, EPI_F32)
+  ORON_GEMM_CASE(256, EPI_F32)
+  ORON_GEMM_CASE(64, EPI_F32)
+  ORON_GEMM_CASE(128, EPI_QKV_ROPE)
+  ORON_GEMM_CASE(256, EPI_QKV_ROPE)
+  ORON_GEMM_CASE(128, EPI_GATE_RESID)
+  ORON_GEMM_CASE(256, EPI_GATE_RESID)
+  ORON_GEMM_CASE(64, EPI_GATE_RESID)
+  ORON_GEMM_CASE(128, EPI_EMBED_DUAL)
+  ORON_GEMM_CASE(64, EPI_MISH_MASK_BF16)
+  ORON_GEMM_CASE(64, EPI_MISH_MASK_RESID)
+  ORON_GEMM_CASE(128, EPI_SCALE_RESID)
+  ORON_GEMM_CASE(64, EPI_SCALE_RESID)
+#undef ORON_GEMM_CASE
+  return fail(ORON_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d epilogue=%d", d->block_n, epi);
+}
+
+// ---------------------------------------------------------------------------
+// attention
+// ---------------------------------------------------------------------------
+extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
+                                   int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
+                                   oron_stream_t stream) {
+  if (!qkv || !out || nbatch <= 0 || rows_per_batch <= 0 || heads <= 0)
+    return fail(ORON_ERR_BAD_ARG, "attention: bad argument");
+  if (ldo % 8 != 0) return fail(ORON_ERR_BAD_ARG, "attention: ldo must be a multiple of 8");
+  CUtensorMap tq;
+  int rc = make_tmap_bf16(&tq, qkv, uint64_t(3 * heads * ATT_D), uint64_t(rows_per_batch), uint64_t(nbatch),
+                          uint64_t(ld_qkv), uint64_t(ld_qkv) * uint64_t(rows_per_batch), ATT_TILE, 3);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATT_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(int(e), "attention smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  AttnArgs a;
+  a.rows_per_batch = rows_per_batch;
+  a.nbatch = nbatch;
+  a.heads = heads;
+  a.seq_lens = seq_lens;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.ldo = ldo;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((rows_per_batch + ATT_TILE - 1) / ATT_TILE, heads, nbatch);
+  attn_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, a);
+  return check_launch("attn_fwd_tcgen05");
+}
+
+// ---------------------------------------------------------------------------
+// row-wise kernels
+// ---------------------------------------------------------------------------
+extern "C" int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_batch, int32_t nbatch, int32_t C,
+                                float eps, const float* scale, const float* shift, int64_t mod_ld, int32_t mod_nb,
+                                int64_t step_stride, const int32_t* step_ptr, int32_t add_one, void* out_bf16,
+                                float* out_f32, int64_t ldo, oron_stream_t stream) {
+  if (!x || !scale || (!out_bf16 && !out_f32)) return fail(ORON_ERR_BAD_ARG, "ln_modulate: null pointer");
+  if (ldx % 4 != 0 || ldo % 4 != 0) return fail(ORON_ERR_BAD_ARG, "ln_modulate: ld must be a multiple of 4");
+  LnArgs a;
+  a.x = x; a.ldx = ldx; a.rows_per_batch = rows_per_batch; a.nbatch = nbatch; a.C = C; a.eps = eps;
+  a.scale = scale; a.shift = shift; a.mod_ld = mod_ld; a.mod_nb = mod_nb > 0 ? mod_nb : 1;
+  a.step_stride = step_stride; a.step_ptr = step_ptr; a.add_one = add_one;
+  a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.ldo = ldo;
+  const long long rows = (long long)rows_per_batch * nbatch;
+  const int blocks = int((rows + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 1024) ln_modulate_kernel<1024><<<blocks, 256, 0, st>>>(a);
+  else if (C == 512) ln_modulate_kernel<512><<<blocks, 256, 0, st>>>(a);
+  else if (C == 256) ln_modulate_kernel<256><<<blocks, 256, 0, st>>>(a);
+  else if (C == 128) ln_modulate_kernel<128><<<blocks, 256, 0, st>>>(a);
+  else if (C == 768) ln_modulate_kernel<768><<<blocks, 256, 0, st>>>(a);
+  else return fail(ORON_ERR_UNSUPPORTED, "ln_modulate: C=%d not supported (128/256/512/768/1024)", C);
+  return check_launch("ln_modulate");
+}
+
+extern "C" int oron_cfg_euler_step(float* x, const float* v, int64_t ldv, int32_t nb, int32_t rows_per_batch,
+                                   int32_t n_mels, int32_t has_uncond, float cfg, const float* dt, int32_t* step_ptr,
+                                   void* xb_bf16, int64_t ldxb, float* traj, float* v_out, oron_stream_t stream) {
+  if (!x || !v || !dt || !step_ptr || !xb_bf16) return fail(ORON_ERR_BAD_ARG, "cfg_euler_step: null pointer");
+  EulerArgs a;
+  a.x = x; a.v = v; a.ldv = ldv; a.nb = nb; a.rows_per_batch = rows_per_batch; a.n_mels = n_mels;
+  a.has_uncond = has_uncond; a.cfg = cfg; a.dt = dt; a.step_ptr = step_ptr;
+  a.xb = reinterpret_cast<__nv_bfloat16*>(xb_bf16); a.ldxb = ldxb; a.traj = traj; a.v_out = v_out;
+  const long long total = (long long)nb * rows_per_batch * n_mels;
+  int blocks = int((total + 255) / 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cfg_euler_kernel<<<blocks, 256, 0, st>>>(a);
+  int rc = check_launch("cfg_euler");
+  if (rc) return rc;
+  step_advance_kernel<<<1, 1, 0, st>>>(step_ptr);
+  return check_launch("step_advance");
+}
+
+extern "C" int oron_cast_rows_bf16(const float* x, int64_t ldx, int64_t rows, int32_t C, void* out_bf16, int64_t ldo,
+                                   int32_t reps, oron_stream_t stream) {
+  if (!x || !out_bf16 || rows <= 0 || C <= 0) return fail(ORON_ERR_BAD_ARG, "cast_rows_bf16: bad argument");
+  const long long total = rows * C;
+  int blocks = int((total + 255) / 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  cast_rows_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, ldx, rows, C, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, reps > 0 ? reps : 1);
+  return check_launch("cast_rows_bf16");
+}
+
+extern "C" int oron_time_sinusoid(const float* t, int32_t n, void* out_bf16, int64_t ldo, oron_stream_t stream) {
+  if (!t || !out_bf16 || n <= 0) return fail(ORON_ERR_BAD_ARG, "time_sinusoid: bad argument");
+  time_sinusoid_kernel<<<n, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      t, n, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo);
+  return check_launch("time_sinusoid");
+}
+
+extern "C" int oron_text_embed_front(const int32_t* ids, const uint8_t* drop, const float* table,
+                                     const float* pos_table, int32_t rows_per_batch, int32_t nb, int32_t C, float* x,
+                                     int64_t ldx, uint8_t* row_valid, oron_stream_t stream) {
+  if (!ids || !drop || !table || !pos_table || !x || !row_valid)
+    return fail(ORON_ERR_BAD_ARG, "text_embed_front: null pointer");
+  const long long rows = (long long)rows_per_batch * nb;
+  text_embed_front_kernel<<<unsigned(rows), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      ids, drop, table, pos_table, rows_per_batch, nb, C, x, ldx, row_valid);
+  return check_launch("text_embed_front");
+}
+
+extern "C" int oron_dwconv7_ln(const float* x, int64_t ldx, int32_t rows_per_batch, int32_t nbatch, int32_t C,
+                               const int32_t* seq_lens, const float* w, const float* wb, const float* ln_w,
+                               const float* ln_b, float eps, void* out_bf16, int64_t ldo, oron_stream_t stream) {
+  if (!x || !w || !wb || !ln_w || !ln_b || !out_bf16) return fail(ORON_ERR_BAD_ARG, "dwconv7_ln: null pointer");
+  DwLnArgs a;
+  a.x = x; a.ldx = ldx; a.rows_per_batch = rows_per_batch; a.nbatch = nbatch; a.seq_lens = seq_lens;
+  a.w = w; a.wb = wb; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.ldo = ldo;
+  const long long rows = (long long)rows_per_batch * nbatch;
+  const int blocks = int((rows + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 512) dwconv7_ln_kernel<512><<<blocks, 256, 0, st>>>(a);
+  else if (C == 256) dwconv7_ln_kernel<256><<<blocks, 256, 0, st>>>(a);
+  else if (C == 128) dwconv7_ln_kernel<128><<<blocks, 256, 0, st>>>(a);
+  else if (C == 64) dwconv7_ln_kernel<64><<<blocks, 256, 0, st>>>(a);
+  else if (C == 32) dwconv7_ln_kernel<32><<<blocks, 256, 0, st>>>(a);
+  else return fail(ORON_ERR_UNSUPPORTED, "dwconv7_ln: C=%d not supported", C);
+  return check_launch("dwconv7_ln");
+}
+
+extern "C" int oron_grn(void* h_bf16, int64_t ldh, int32_t rows_per_batch, int32_t nb, int32_t C,
+                        const int32_t* seq_lens, const float* gamma, const float* beta, float* gx2,
+                        oron_stream_t stream) {
+  if (!h_bf16 || !gamma || !beta || !gx2) return fail(ORON_ERR_BAD_ARG, "grn: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(gx2, 0, sizeof(float) * size_t(nb) * C, st);
+  if (e != cudaSuccess) return fail(int(e), "grn memset: %s", cudaGetErrorString(e));
+  const int rpb = 32;
+  dim3 grid((rows_per_batch + rpb - 1) / rpb, nb);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(h_bf16);
+  grn_sumsq_kernel<<<grid, 256, 0, st>>>(h, ldh, rows_per_batch, nb, seq_lens, C, rpb, gx2);
+  int rc = check_launch("grn_sumsq");
+  if (rc) return rc;
+  grn_apply_kernel<<<grid, 256, 0, st>>>(h, ldh, rows_per_batch, nb, C, rpb, gx2, gamma, beta);
+  return check_launch("grn_apply");
+}
+
+extern "C" int oron_abi_version(void) { return ORON_ABI_VERSION; }
+extern "C" const char* oron_last_error(void) { return g_err; }
+extern "C" uint64_t oron_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,299 @@
+// HBM/L2-bound row-wise kernels of the DiT / TextEmbedding / Vocos path.
+// Layout everywhere: activations are [nbatch * rows_per_batch, C] row-major ("frame-major").
+#pragma once
+#include "ptx.cuh"
+
+namespace oron {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm (eps, biased variance, fp32 statistics) fused with either
+//   AdaLN modulation  y = LN(x) * (1 + scale[b]) + shift[b]   (modules.py:218, :234, :341)
+//   affine            y = LN(x) * weight + bias               (modules.py:169 / Vocos norms)
+// One warp per row; C = 32 * VPL * 4 ... handled generically with float4 lanes.
+// mod vectors live in a per-step table: ptr + step*step_stride + (b % mod_nb)*mod_ld.
+// ---------------------------------------------------------------------------
+struct LnArgs {
+  const float* x;        // [rows, ldx]
+  long long ldx;
+  int rows_per_batch, nbatch, C;
+  float eps;
+  const float* scale;    // modulation: (1+scale) ; affine: weight (add_one = 0)
+  const float* shift;    // modulation shift / affine bias (nullptr -> 0)
+  long long mod_ld;      // batch stride of scale/shift (0 for affine)
+  int mod_nb;
+  long long step_stride;
+  const int* step_ptr;
+  int add_one;
+  __nv_bfloat16* out_bf16;  // [rows, ldo] or nullptr
+  float* out_f32;           // [rows, ldo] or nullptr
+  long long ldo;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnArgs a) {
+  constexpr int V4 = C / 128;  // float4 per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)a.rows_per_batch * a.nbatch;
+  if (warp >= rows) return;
+  const int b = warp / a.rows_per_batch;
+  const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)warp * a.ldx);
+  float4 v[V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + a.eps);
+  const long long step = a.step_ptr ? (long long)__ldg(a.step_ptr) : 0ll;
+  const long long moff = step * a.step_stride + (long long)(b % a.mod_nb) * a.mod_ld;
+  const float4* sc = reinterpret_cast<const float4*>(a.scale + moff);
+  const float4* sh = a.shift ? reinterpret_cast<const float4*>(a.shift + moff) : nullptr;
+  const float one = a.add_one ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const float4 g = __ldg(sc + lane + 32 * i);
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sh) h = __ldg(sh + lane + 32 * i);
+    float4 y;
+    y.x = v[i].x * rstd * (one + g.x) + h.x;
+    y.y = v[i].y * rstd * (one + g.y) + h.y;
+    y.z = v[i].z * rstd * (one + g.z) + h.z;
+    y.w = v[i].w * rstd * (one + g.w) + h.w;
+    if (a.out_bf16) {
+      uint2 p = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+      reinterpret_cast<uint2*>(a.out_bf16 + (long long)warp * a.ldo)[lane + 32 * i] = p;
+    }
+    if (a.out_f32) reinterpret_cast<float4*>(a.out_f32 + (long long)warp * a.ldo)[lane + 32 * i] = y;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CFG combine + Euler update (flow.py:266-267, 295-299), one launch per ODE step:
+//   v = v_c + (v_c - v_u) * cfg ;  x += v * dt[step]
+// also refreshes the bf16 GEMM operand of the next step (both CFG halves) and the trajectory
+// slot, then (last thread) advances the device-side step counter.
+// ---------------------------------------------------------------------------
+struct EulerArgs {
+  float* x;              // [nb*rows_per_batch, n_mels] fp32 ODE state (in place)
+  const float* v;        // [(cfg?2:1)*nb*rows_per_batch, ldv] fp32 velocity (cond rows first)
+  long long ldv;
+  int nb, rows_per_batch, n_mels;
+  int has_uncond;
+  float cfg;
+  const float* dt;       // [steps]
+  int* step_ptr;         // read, then incremented by one
+  __nv_bfloat16* xb;     // [(cfg?2:1)*nb*rows_per_batch, ldxb] bf16 copy for the input projection
+  long long ldxb;
+  float* traj;           // [steps+1, nb*rows_per_batch, n_mels] or nullptr; slot step+1 is written
+  float* v_out;          // optional [nb*rows_per_batch, n_mels]: the guided velocity (parity checks)
+};
+
+__global__ void __launch_bounds__(256) cfg_euler_kernel(const EulerArgs a) {
+  const long long rows = (long long)a.nb * a.rows_per_batch;
+  const long long total = rows * a.n_mels;
+  const int step = *a.step_ptr;
+  const float dt = a.dt[step];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / a.n_mels;
+    const int c = int(i - row * a.n_mels);
+    const float vc = a.v[row * a.ldv + c];
+    float vv = vc;
+    if (a.has_uncond) {
+      const float vu = a.v[(rows + row) * a.ldv + c];
+      vv = vc + (vc - vu) * a.cfg;
+    }
+    const float xn = a.x[i] + vv * dt;
+    a.x[i] = xn;
+    if (a.v_out) a.v_out[i] = vv;
+    if (a.traj) a.traj[(long long)(step + 1) * total + i] = xn;
+    const __nv_bfloat16 xh = __float2bfloat16(xn);
+    a.xb[row * a.ldxb + c] = xh;
+    if (a.has_uncond) a.xb[(rows + row) * a.ldxb + c] = xh;
+  }
+}
+__global__ void step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
+
+// fp32 [rows, C] -> bf16 [rows, ldo] (cols >= C untouched), optionally replicated `reps` times
+__global__ void __launch_bounds__(256)
+cast_rows_bf16_kernel(const float* x, long long ldx, long long rows, int C, __nv_bfloat16* out,
+                      long long ldo, int reps) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C;
+    const int c = int(i - row * C);
+    const __nv_bfloat16 h = __float2bfloat16(x[row * ldx + c]);
+    for (int r = 0; r < reps; ++r) out[(r * rows + row) * ldo + c] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Timestep features (modules.py:39-45): [sin(1000 t f_j) | cos(1000 t f_j)], f_j = exp(-j ln(1e4)/127)
+// -> bf16 [n, 256]
+// ---------------------------------------------------------------------------
+__global__ void time_sinusoid_kernel(const float* t, int n, __nv_bfloat16* out, long long ldo) {
+  const int i = blockIdx.x;
+  const int j = threadIdx.x;  // 0..127
+  if (i >= n) return;
+  const float emb = expf(float(j) * (-9.210340371976184f / 127.0f));
+  const float e = 1000.0f * t[i] * emb;
+  out[(long long)i * ldo + j] = __float2bfloat16(sinf(e));
+  out[(long long)i * ldo + 128 + j] = __float2bfloat16(cosf(e));
+}
+
+// ---------------------------------------------------------------------------
+// TextEmbedding front (encoder.py:68-91): ids(+1, 0 = filler) -> emb + sinusoidal abs-pos, fillers zeroed.
+//   ids:   [nb, rows_per_batch] int32, already shifted by +1 and cropped/padded with 0
+//   drop:  per batch element flag: look up row 0 for every position (text dropped) but keep the
+//          filler mask of the *original* ids (encoder.py:77-80)
+// outputs fp32 x [rows, C] and row_valid (1 = real token) consumed by the ConvNeXt epilogues.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+text_embed_front_kernel(const int* ids, const unsigned char* drop, const float* table,
+                        const float* pos_table, int rows_per_batch, int nb, int C, float* x,
+                        long long ldx, unsigned char* row_valid) {
+  const long long row = blockIdx.x;
+  const int b = int(row / rows_per_batch);
+  const int t = int(row - (long long)b * rows_per_batch);
+  const int id = ids[row];
+  const bool filler = (id == 0);
+  if (threadIdx.x == 0) row_valid[row] = filler ? 0 : 1;
+  const int look = drop[b] ? 0 : id;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // pos_table = precompute_freqs_cis(C, 8192) built on the host exactly as modules.py:191-196
+    const float v = filler ? 0.f : table[(long long)look * C + c] + pos_table[(long long)t * C + c];
+    x[row * ldx + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Depthwise conv1d k=7 pad=3 over frames (per channel) fused with the LayerNorm that follows it
+// in every ConvNeXt block of the path (modules.py:178-180; Vocos ConvNeXtBlock dwconv+norm).
+// One warp per output frame; the 7 input rows are L1/L2 hits shared with neighbouring warps.
+//   w: [C, 7] (Conv1d weight [C,1,7]), zero padding at sequence ends: rows outside [0,len) read 0.
+// ---------------------------------------------------------------------------
+struct DwLnArgs {
+  const float* x;       // [rows, ldx]
+  long long ldx;
+  int rows_per_batch, nbatch;
+  const int* seq_lens;  // conv sees zeros for t >= len (nullptr -> rows_per_batch)
+  const float* w;       // [C,7]
+  const float* wb;      // [C]
+  const float* ln_w;    // [C]
+  const float* ln_b;    // [C]
+  float eps;
+  __nv_bfloat16* out;   // [rows, ldo]
+  long long ldo;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const DwLnArgs a) {
+  constexpr int VPL = C / 32;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)a.rows_per_batch * a.nbatch;
+  if (warp >= rows) return;
+  const int b = warp / a.rows_per_batch;
+  const int t = warp - b * a.rows_per_batch;
+  const int len = a.seq_lens ? a.seq_lens[b] : a.rows_per_batch;
+  float y[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) y[i] = __ldg(a.wb + lane + 32 * i);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int tt = t + k - 3;
+    if (tt < 0 || tt >= len) continue;
+    const float* xr = a.x + ((long long)b * a.rows_per_batch + tt) * a.ldx;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      y[i] += __ldg(a.w + c * 7 + k) * xr[c];
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += y[i];
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { y[i] -= mean; ss += y[i] * y[i]; }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + a.eps);
+  __nv_bfloat16* o = a.out + (long long)warp * a.ldo;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    o[c] = __float2bfloat16(y[i] * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GRN (modules.py:153-156): gx[b,c] = ||h[b,:,c]||_2 over the frames of the sequence,
+// nx = gx / (mean_c gx + 1e-6), y = gamma * (h * nx) + beta + h.   Two kernels:
+//   grn_sumsq : partial sums of squares per (b, c) accumulated with atomics into gx2 (pre-zeroed)
+//   grn_apply : every block re-derives mean_c from gx2 (C <= 2048) and rewrites h in place (bf16)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grn_sumsq_kernel(const __nv_bfloat16* h, long long ldh, int rows_per_batch, int nb, const int* seq_lens,
+                 int C, int rows_per_block, float* gx2) {
+  const int b = blockIdx.y;
+  const int len = seq_lens ? seq_lens[b] : rows_per_batch;
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(t0 + rows_per_block, len);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int t = t0; t < t1; ++t) {
+      const float v = __bfloat162float(h[((long long)b * rows_per_batch + t) * ldh + c]);
+      s += v * v;
+    }
+    if (t1 > t0) atomicAdd(gx2 + (long long)b * C + c, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+grn_apply_kernel(__nv_bfloat16* h, long long ldh, int rows_per_batch, int nb, int C, int rows_per_block,
+                 const float* gx2, const float* gamma, const float* beta) {
+  __shared__ float red[8];
+  __shared__ float s_mean;
+  const int b = blockIdx.y;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += sqrtf(gx2[(long long)b * C + c]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+    s_mean = tot / float(C);
+  }
+  __syncthreads();
+  const float inv = 1.0f / (s_mean + 1e-6f);
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(t0 + rows_per_block, rows_per_batch);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float nx = sqrtf(gx2[(long long)b * C + c]) * inv;
+    const float g = gamma[c], be = beta[c];
+    for (int t = t0; t < t1; ++t) {
+      __nv_bfloat16* p = h + ((long long)b * rows_per_batch + t) * ldh + c;
+      const float v = __bfloat162float(*p);
+      *p = __float2bfloat16(g * (v * nx) + be + v);
+    }
+  }
+}
+
+}  // namespace oron

@@ -1,0 +1,406 @@
+"""Kernel-level numerics: every C-ABI entry point against the plain PyTorch op it replaces,
+on the same seeded inputs (bf16 operands are rounded identically on both sides; the torch side
+accumulates in fp32). These call through liboron_b200.so — no fallback exists."""
+
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from oron_tts_b200 import _lib
+
+    _lib.lib()
+    return _lib
+
+
+def _rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "M,N,K,bn",
+    [
+        (128, 128, 64, 128),
+        (256, 256, 256, 128),
+        (2816, 1024, 1024, 128),
+        (2816, 3072, 1024, 256),
+        (300, 1026, 512, 128),  # ragged M and N
+        (32, 4096, 1024, 256),  # tiny M (modulation table shape)
+        (1406, 1024, 4096, 64),
+        (2816, 1024, 128, 128),
+    ],
+)
+def test_gemm_bf16_plain(L, M, N, K, bn):
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g)
+    ldo = (N + 7) // 8 * 8
+    out = torch.full((M, ldo), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, W, out, epilogue=L.EPI_BF16, bias=bias, block_n=bn, n=N)
+    ref = A.float() @ W.float().t() + bias
+    torch.cuda.synchronize()
+    assert torch.isfinite(out[:, :N].float()).all()
+    assert _rel(out[:, :N], ref) < 6e-3
+    assert float((out[:, :N].float() - ref).abs().max()) < 0.06 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("act", ["gelu_tanh", "gelu_erf", "silu"])
+def test_gemm_activation_epilogues(L, act):
+    M, N, K = 512, 512, 256
+    g = torch.Generator(device=DEV).manual_seed(11)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K) * 2)
+    bias = torch.randn(N, device=DEV, generator=g)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    code = {"gelu_tanh": L.ACT_GELU_TANH, "gelu_erf": L.ACT_GELU_ERF, "silu": L.ACT_SILU}[act]
+    L.gemm(A, W, out, epilogue=L.EPI_BF16, bias=bias, act=code)
+    pre = A.float() @ W.float().t() + bias
+    ref = {"gelu_tanh": lambda x: F.gelu(x, approximate="tanh"), "gelu_erf": F.gelu, "silu": F.silu}[act](pre)
+    assert _rel(out, ref) < 6e-3
+
+
+def test_gemm_f32_addend_and_tail(L):
+    M, N, K = 1406, 100, 1024
+    g = torch.Generator(device=DEV).manual_seed(5)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    L.gemm(A, W, out, epilogue=L.EPI_F32, bias=bias)
+    ref = A.float() @ W.float().t() + bias
+    assert _rel(out, ref) < 1e-4
+    add = torch.randn(M, 128, device=DEV, generator=g)
+    out2 = torch.zeros(M, 128, device=DEV)
+    L.gemm(A, W, out2, epilogue=L.EPI_F32, bias=bias, addend=add, n=N)
+    assert _rel(out2[:, :N], ref + add[:, :N]) < 1e-4
+    assert float(out2[:, N:].abs().max()) == 0.0
+
+
+def test_gemm_qkv_rope(L):
+    nb, T, D, H = 2, 384, 1024, 16
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(3)
+    A = _bf(torch.randn(M, D, device=DEV, generator=g))
+    W = _bf(torch.randn(3 * D, D, device=DEV, generator=g) / math.sqrt(D))
+    bias = torch.randn(3 * D, device=DEV, generator=g) * 0.1
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=DEV).float() / 64))
+    ang = torch.outer(torch.arange(T, device=DEV).float(), inv_freq)  # [T, 32]
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    for bn in (128, 256):
+        out = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+        L.gemm(A, W, out, epilogue=L.EPI_QKV_ROPE, bias=bias, rows_per_batch=T, nbatch=nb, block_n=bn,
+               rope_cos=cos, rope_sin=sin, rope_cols=2 * D)
+        pre = (A.float() @ W.float().t() + bias).view(nb, T, 3, H, 64)
+        q, k, v = pre[:, :, 0], pre[:, :, 1], pre[:, :, 2]
+        c = torch.cat([cos, cos], -1)[None, :, None, :]
+        s = torch.cat([sin, sin], -1)[None, :, None, :]
+
+        def rot(x):
+            return torch.cat([-x[..., 32:], x[..., :32]], -1)
+
+        ref = torch.stack([q * c + rot(q) * s, k * c + rot(k) * s, v], 2).reshape(M, 3 * D)
+        assert _rel(out, ref) < 6e-3, bn
+
+
+def test_gemm_gate_residual_masked(L):
+    nb, T, D = 2, 256, 1024
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(9)
+    A = _bf(torch.randn(M, D, device=DEV, generator=g))
+    W = _bf(torch.randn(D, D, device=DEV, generator=g) / math.sqrt(D))
+    bias = torch.randn(D, device=DEV, generator=g) * 0.1
+    steps = 3
+    table = torch.randn(steps, 1, 6 * D, device=DEV, generator=g)  # shared by all batch elements
+    step = torch.tensor([2], device=DEV, dtype=torch.int32)
+    lens = torch.tensor([256, 100], device=DEV, dtype=torch.int32)
+    x0 = torch.randn(M, D, device=DEV, generator=g)
+    x = x0.clone()
+    gate_view = table.view(-1)[2 * D:]  # chunk 2 (gate_msa) of step 0
+    L.gemm(A, W, x, epilogue=L.EPI_GATE_RESID, bias=bias, rows_per_batch=T, nbatch=nb, gate=gate_view, gate_ld=0,
+           gate_nb=1, gate_step_stride=6 * D, step_ptr=step, seq_lens=lens, mask_rows=True)
+    gate = table[2, 0, 2 * D:3 * D]
+    upd = gate * (A.float() @ W.float().t() + bias)
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).reshape(M, 1)
+    ref = x0 + torch.where(mask, upd, torch.zeros_like(upd))
+    assert _rel(x, ref) < 2e-3
+    assert torch.equal(x[~mask.squeeze(1)], x0[~mask.squeeze(1)])
+
+
+def test_conv_gemm_grouped_k31_mish(L):
+    """ConvPositionEmbedding conv (modules.py:120-141) as implicit GEMM, both epilogues."""
+    nb, T, D, G, KS = 2, 256, 1024, 16, 31
+    lens = torch.tensor([256, 131], device=DEV, dtype=torch.int32)
+    g = torch.Generator(device=DEV).manual_seed(21)
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None])  # [nb, T]
+    x = torch.randn(nb, T, D, device=DEV, generator=g) * mask[..., None]
+    w = torch.randn(D, D // G, KS, device=DEV, generator=g) / math.sqrt(D // G * KS)
+    bias = torch.randn(D, device=DEV, generator=g) * 0.1
+    xb = _bf(x).reshape(nb * T, D).contiguous()
+    wb = _bf(w)
+    # tap-major weight [D, 31*64]
+    W2 = wb.permute(0, 2, 1).reshape(D, KS * (D // G)).contiguous()
+    out = torch.empty(nb * T, D, device=DEV, dtype=torch.bfloat16)
+    L.gemm(xb, W2, out, epilogue=L.EPI_MISH_MASK_BF16, bias=bias, rows_per_batch=T, nbatch=nb, taps=KS, cin_blocks=1,
+           pad=KS // 2, grouped=True, block_n=64, seq_lens=lens)
+    ref = F.conv1d(xb.float().view(nb, T, D).transpose(1, 2), wb.float(), bias, padding=KS // 2, groups=G)
+    ref = F.mish(ref.masked_fill(~mask[:, None, :], 0.0)).masked_fill(~mask[:, None, :], 0.0)
+    ref = ref.transpose(1, 2).reshape(nb * T, D)
+    assert _rel(out, ref) < 8e-3
+    add = torch.randn(nb * T, D, device=DEV, generator=g)
+    out2 = torch.empty(nb * T, D, device=DEV)
+    L.gemm(xb, W2, out2, epilogue=L.EPI_MISH_MASK_RESID, bias=bias, rows_per_batch=T, nbatch=nb, taps=KS,
+           cin_blocks=1, pad=KS // 2, grouped=True, block_n=64, seq_lens=lens, addend=add)
+    assert _rel(out2, ref + add) < 3e-3
+
+
+def test_conv_gemm_dense_k7(L):
+    """Vocos embed Conv1d(100 -> 512, k=7, pad=3) as a dense implicit GEMM (channels padded to 128)."""
+    nb, T, Cin, Cout, KS = 2, 200, 100, 512, 7
+    g = torch.Generator(device=DEV).manual_seed(22)
+    x = torch.randn(nb, T, Cin, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, KS, device=DEV, generator=g) / math.sqrt(Cin * KS)
+    bias = torch.randn(Cout, device=DEV, generator=g) * 0.1
+    xb = torch.zeros(nb * T, 128, device=DEV, dtype=torch.bfloat16)
+    xb[:, :Cin] = _bf(x).reshape(nb * T, Cin)
+    W2 = torch.zeros(Cout, KS, 128, device=DEV, dtype=torch.bfloat16)
+    W2[:, :, :Cin] = _bf(w).permute(0, 2, 1)
+    W2 = W2.reshape(Cout, KS * 128)
+    out = torch.empty(nb * T, Cout, device=DEV)
+    L.gemm(xb, W2, out, epilogue=L.EPI_F32, bias=bias, rows_per_batch=T, nbatch=nb, taps=KS, cin_blocks=2, pad=3,
+           block_n=128)
+    ref = F.conv1d(_bf(x).float().transpose(1, 2), _bf(w).float(), bias, padding=3).transpose(1, 2).reshape(nb * T, Cout)
+    assert _rel(out, ref) < 1e-4
+
+
+def test_gemm_embed_dual_and_scale_resid(L):
+    nb, T, D, K = 2, 256, 1024, 128
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(31)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(D, K, device=DEV, generator=g) / math.sqrt(K))
+    add = torch.randn(M, D, device=DEV, generator=g)
+    lens = torch.tensor([200, 256], device=DEV, dtype=torch.int32)
+    o32 = torch.empty(M, D, device=DEV)
+    o16 = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, W, o32, epilogue=L.EPI_EMBED_DUAL, rows_per_batch=T, nbatch=nb, addend=add, seq_lens=lens, out2=o16)
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).reshape(M, 1)
+    ref = torch.where(mask, A.float() @ W.float().t() + add, torch.zeros(M, D, device=DEV))
+    assert _rel(o32, ref) < 1e-4
+    assert _rel(o16, ref) < 4e-3
+    # SCALE_RESID with explicit row mask and per-column scale
+    rv = (torch.rand(M, device=DEV, generator=g) > 0.3).to(torch.uint8)
+    colscale = torch.randn(D, device=DEV, generator=g)
+    bias = torch.randn(D, device=DEV, generator=g)
+    o = torch.empty(M, D, device=DEV)
+    L.gemm(A, W, o, epilogue=L.EPI_SCALE_RESID, bias=bias, rows_per_batch=T, nbatch=nb, addend=add, gate=colscale,
+           row_valid=rv)
+    ref2 = torch.where(rv.bool()[:, None], add + colscale * (A.float() @ W.float().t() + bias), torch.zeros_like(add))
+    assert _rel(o, ref2) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nb,T,H,lens", [(1, 128, 2, None), (2, 384, 4, [384, 130]), (2, 1408, 16, [1406, 1406]),
+                                         (3, 200, 8, [200, 1, 77])])
+def test_attention(L, nb, T, H, lens):
+    g = torch.Generator(device=DEV).manual_seed(T + H)
+    qkv = _bf(torch.randn(nb * T, 3 * H * 64, device=DEV, generator=g))
+    out = torch.zeros(nb * T, H * 64, device=DEV, dtype=torch.bfloat16)
+    lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32) if lens is not None else None
+    L.attention(qkv, out, nbatch=nb, rows_per_batch=T, heads=H, seq_lens=lens_t, scale=0.125)
+    x = qkv.float().view(nb, T, 3, H, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    ll = lens if lens is not None else [T] * nb
+    mask = torch.arange(T, device=DEV)[None, :] < torch.tensor(ll, device=DEV)[:, None]
+    ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask[:, None, None, :])
+    ref = ref.transpose(1, 2).reshape(nb, T, H * 64)
+    o = out.view(nb, T, H * 64)
+    for b in range(nb):
+        assert _rel(o[b, : ll[b]], ref[b, : ll[b]]) < 1e-2, b
+
+
+# ------------------------------------------------------------------------------------------
+# row-wise kernels
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [512, 1024])
+def test_ln_modulate(L, C):
+    nb, T = 2, 300
+    g = torch.Generator(device=DEV).manual_seed(C)
+    x = torch.randn(nb * T, C, device=DEV, generator=g) * 3 + 1
+    table = torch.randn(4, nb, 6 * C, device=DEV, generator=g)
+    step = torch.tensor([3], device=DEV, dtype=torch.int32)
+    out = torch.empty(nb * T, C, device=DEV, dtype=torch.bfloat16)
+    flat = table.view(-1)
+    L.ln_modulate(x, rows_per_batch=T, nbatch=nb, eps=1e-6, scale=flat[C:], shift=flat, mod_ld=6 * C, mod_nb=nb,
+                  step_stride=nb * 6 * C, step_ptr=step, add_one=True, out_bf16=out)
+    shift, scale = table[3, :, :C], table[3, :, C:2 * C]
+    ref = F.layer_norm(x.view(nb, T, C), (C,), eps=1e-6) * (1 + scale[:, None]) + shift[:, None]
+    assert _rel(out.view(nb, T, C), ref) < 4e-3
+    w, b = torch.randn(C, device=DEV, generator=g), torch.randn(C, device=DEV, generator=g)
+    o32 = torch.empty(nb * T, C, device=DEV)
+    L.ln_modulate(x, rows_per_batch=T, nbatch=nb, eps=1e-6, scale=w, shift=b, add_one=False, out_f32=o32)
+    assert _rel(o32, F.layer_norm(x, (C,), w, b, eps=1e-6)) < 1e-5
+
+
+def test_cfg_euler_step(L):
+    nb, T, n_mels, steps = 2, 130, 100, 4
+    rows = nb * T
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x0 = torch.randn(rows, n_mels, device=DEV, generator=g)
+    v = torch.randn(2 * rows, 128, device=DEV, generator=g)
+    dt = torch.rand(steps, device=DEV, generator=g)
+    step = torch.tensor([1], device=DEV, dtype=torch.int32)
+    xb = torch.zeros(2 * rows, 128, device=DEV, dtype=torch.bfloat16)
+    traj = torch.zeros(steps + 1, rows, n_mels, device=DEV)
+    vout = torch.empty(rows, n_mels, device=DEV)
+    x = x0.clone()
+    L.cfg_euler_step(x, v, nb=nb, rows_per_batch=T, n_mels=n_mels, has_uncond=True, cfg=2.0, dt=dt, step_ptr=step,
+                     xb=xb, traj=traj, v_out=vout)
+    vc, vu = v[:rows, :n_mels], v[rows:, :n_mels]
+    vg = vc + (vc - vu) * 2.0
+    ref = x0 + vg * dt[1]
+    assert torch.allclose(x, ref, atol=1e-6)
+    assert torch.allclose(vout, vg, atol=1e-6)
+    assert torch.equal(traj[2], x)
+    assert int(step.item()) == 2
+    assert torch.equal(xb[:rows, :n_mels], x.to(torch.bfloat16)) and torch.equal(xb[rows:, :n_mels], x.to(torch.bfloat16))
+    assert float(xb[:, n_mels:].abs().max()) == 0.0
+
+
+def test_time_sinusoid(L):
+    t = torch.linspace(0, 1, 9, device=DEV)
+    out = torch.empty(9, 256, device=DEV, dtype=torch.bfloat16)
+    L.time_sinusoid(t, out)
+    emb = torch.exp(torch.arange(128, device=DEV).float() * -(math.log(10000) / 127))
+    e = 1000.0 * t[:, None] * emb[None]
+    ref = torch.cat([e.sin(), e.cos()], -1)
+    assert float((out.float() - ref).abs().max()) < 1e-2
+
+
+def test_text_front_dwconv_grn(L):
+    nb, T, C = 2, 140, 512
+    g = torch.Generator(device=DEV).manual_seed(4)
+    ids = torch.randint(1, 66, (nb, T), device=DEV, generator=g, dtype=torch.int32)
+    ids[0, 100:] = 0
+    ids[1, 10:20] = 0
+    drop = torch.tensor([0, 1], device=DEV, dtype=torch.uint8)
+    table = torch.randn(66, C, device=DEV, generator=g)
+    pos = torch.randn(T, C, device=DEV, generator=g)
+    x = torch.empty(nb * T, C, device=DEV)
+    rv = torch.empty(nb * T, device=DEV, dtype=torch.uint8)
+    L.text_embed_front(ids.view(-1), drop, table, pos, rows_per_batch=T, nb=nb, x=x, row_valid=rv)
+    look = ids.clone().long()
+    look[1] = 0
+    ref = table[look] + pos[None]
+    ref = ref.masked_fill((ids == 0)[..., None], 0.0)
+    assert torch.equal(x.view(nb, T, C), ref)
+    assert torch.equal(rv.view(nb, T).bool(), ids != 0)
+    # dwconv7 + LN
+    lens = torch.tensor([140, 90], device=DEV, dtype=torch.int32)
+    w = torch.randn(C, 1, 7, device=DEV, generator=g) * 0.3
+    wb, lw, lb = (torch.randn(C, device=DEV, generator=g) for _ in range(3))
+    out = torch.empty(nb * T, C, device=DEV, dtype=torch.bfloat16)
+    L.dwconv7_ln(x, rows_per_batch=T, nbatch=nb, seq_lens=lens, w=w.view(C, 7).contiguous(), wb=wb, ln_w=lw, ln_b=lb,
+                 eps=1e-6, out=out)
+    m = (torch.arange(T, device=DEV)[None, :] < lens[:, None])
+    xin = x.view(nb, T, C) * m[..., None]
+    y = F.conv1d(xin.transpose(1, 2), w, wb, padding=3, groups=C).transpose(1, 2)
+    refln = F.layer_norm(y, (C,), lw, lb, eps=1e-6)
+    o = out.view(nb, T, C).float()
+    for b in range(nb):
+        assert _rel(o[b, : lens[b]], refln[b, : lens[b]]) < 4e-3
+    # GRN over valid frames only
+    C2 = 1024
+    h = _bf(torch.randn(nb * T, C2, device=DEV, generator=g))
+    gamma, beta = torch.randn(C2, device=DEV, generator=g), torch.randn(C2, device=DEV, generator=g)
+    gx2 = torch.empty(nb, C2, device=DEV)
+    h2 = h.clone()
+    L.grn(h2, rows_per_batch=T, nb=nb, seq_lens=lens, gamma=gamma, beta=beta, gx2=gx2)
+    for b in range(nb):
+        hb = h.view(nb, T, C2)[b, : lens[b]].float()[None]
+        gx = torch.norm(hb, p=2, dim=1, keepdim=True)
+        nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
+        refg = gamma * (hb * nx) + beta + hb
+        assert _rel(h2.view(nb, T, C2)[b, : lens[b]], refg[0]) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------
+# audio
+# ------------------------------------------------------------------------------------------
+def _mel_fb(n_freqs=513, n_mels=100, sr=24000):
+    import torchaudio
+
+    return torchaudio.functional.melscale_fbanks(n_freqs, 0.0, sr / 2, n_mels, sr, norm=None, mel_scale="htk")
+
+
+@pytest.mark.parametrize("nb,S", [(1, 48000), (3, 120000), (2, 7777)])
+def test_logmel(L, nb, S):
+    import torchaudio
+
+    g = torch.Generator(device=DEV).manual_seed(S)
+    wav = (torch.rand(nb, S, device=DEV, generator=g) * 2 - 1) * 0.3
+    wav[0] += 0.5 * torch.sin(torch.arange(S, device=DEV) * (2 * math.pi * 220 / 24000))
+    window = torch.hann_window(1024, device=DEV)
+    fb = _mel_fb().to(DEV).contiguous()
+    T = 1 + S // 256
+    out = torch.empty(nb, 100, T, device=DEV)
+    L.logmel(wav, window, fb, out, clip=1e-5)
+    tr = torchaudio.transforms.MelSpectrogram(sample_rate=24000, n_fft=1024, hop_length=256, win_length=1024,
+                                              n_mels=100, center=True, power=1).to(DEV)
+    ref = torch.log(torch.clamp(tr(wav), min=1e-5))
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) < 2e-3
+    assert _rel(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("nb,T,mode", [(1, 37, 0), (2, 300, 0), (2, 64, 1)])
+def test_istft_head(L, nb, T, mode):
+    g = torch.Generator(device=DEV).manual_seed(T)
+    ld = 1056
+    h = torch.randn(nb * T, ld, device=DEV, generator=g)
+    window = torch.hann_window(1024, device=DEV)
+    out = torch.empty(nb, (T - 1) * 256, device=DEV)
+    L.istft_head(h, window, out, rows_per_batch=T, nb=nb, n_frames=T, mode=mode)
+    hv = h.view(nb, T, ld)
+    if mode == 0:
+        mag = torch.clip(torch.exp(hv[..., :513]), max=1e2)
+        p = hv[..., 513:1026]
+        spec = (mag * (torch.cos(p) + 1j * torch.sin(p))).transpose(1, 2)
+        ref = torch.istft(spec, 1024, 256, 1024, window, center=True, normalized=False)
+    else:
+        ri = hv[..., :1026].reshape(nb, T, 513, 2)
+        spec = torch.complex(ri[..., 0], ri[..., 1]).transpose(1, 2)
+        ref = torch.istft(spec, 1024, 256, 1024, window, normalized=True, onesided=True)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 1e-5
+
+
+def test_peak_normalize(L):
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.randn(3, 50001, device=DEV, generator=g) * 0.2
+    x[1] = 0.0
+    out = torch.empty_like(x)
+    scratch = torch.empty(3, device=DEV)
+    L.peak_normalize(x, out, scratch)
+    for b in range(3):
+        mx = x[b].abs().max()
+        ref = x[b] if mx < 1e-8 else torch.clamp(x[b] / (mx + 1e-7), -1.0, 1.0)
+        assert torch.allclose(out[b], ref, atol=1e-7)
