@@ -63,7 +63,9 @@ enum oron_act { ORON_ACT_NONE = 0, ORON_ACT_GELU_TANH = 1, ORON_ACT_GELU_ERF = 2
  *   taps == 1: plain GEMM, K = w_cols.
  *   taps  > 1: W is laid out [N, taps * cin_blocks * 64] (tap-major); A rows are shifted by
  *              (tap - pad) with zero fill outside [0, rows_per_batch) of each batch element;
- *              grouped != 0: A column block = the 64-channel group of the output tile (block_n == 64).
+ *              grouped = G > 0 (a multiple of 64, == cin_blocks*64, block_n == 64): grouped conv whose
+ *              groups are G channels wide; narrower groups are packed block-diagonally into 64-wide
+ *              blocks by the caller (zero weights across groups).
  */
 typedef struct oron_gemm_desc {
   const void* A;

@@ -173,7 +173,7 @@ def gemm(
     taps: int = 1,
     cin_blocks: int = 0,
     pad: int = 0,
-    grouped: bool = False,
+    grouped: int = 0,
     block_n: int = 128,
     out2: torch.Tensor | None = None,
     addend: torch.Tensor | None = None,
@@ -201,7 +201,7 @@ def gemm(
     d.rows_per_batch = int(rows_per_batch if rows_per_batch is not None else A.shape[0])
     d.nbatch = int(nbatch)
     d.N = int(n if n is not None else W.shape[0])
-    d.taps, d.cin_blocks, d.pad, d.grouped = int(taps), int(cin_blocks), int(pad), int(bool(grouped))
+    d.taps, d.cin_blocks, d.pad, d.grouped = int(taps), int(cin_blocks), int(pad), int(grouped)
     d.block_n, d.epilogue, d.act = int(block_n), int(epilogue), int(act)
     d.bias = _ptr(bias, torch.float32, "bias")
     d.out = _ptr(out, None, "out")

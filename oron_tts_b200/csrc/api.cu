@@ -118,12 +118,12 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   } else {
     if (d->cin_blocks <= 0 || d->w_cols != taps * d->cin_blocks * GEMM_BK)
       return fail(ORON_ERR_BAD_ARG, "conv-gemm: w_cols must equal taps*cin_blocks*64");
-    if (d->grouped && (d->block_n != 64 || d->cin_blocks != 1))
-      return fail(ORON_ERR_BAD_ARG, "grouped conv-gemm needs block_n == 64 and 64-channel groups");
+    if (d->grouped && (d->block_n != 64 || d->grouped != d->cin_blocks * GEMM_BK))
+      return fail(ORON_ERR_BAD_ARG, "grouped conv-gemm needs block_n == 64 and grouped == cin_blocks*64");
     a.num_kb = taps * d->cin_blocks;
     a.cpb = d->cin_blocks;
     a.pad = d->pad;
-    a.grouped = d->grouped ? 1 : 0;
+    a.grouped = d->grouped;
   }
   a.act = d->act;
   a.bias = d->bias;

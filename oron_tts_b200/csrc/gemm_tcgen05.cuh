@@ -34,7 +34,8 @@ struct GemmArgs {
   // implicit-GEMM addressing of A (plain GEMM: cpb = num_kb, pad = 0, grouped = 0)
   int cpb;             // k-blocks per tap
   int pad;             // rows of left padding (taps centred)
-  int grouped;         // 1: A column block = n-tile origin (group-aligned), 0: (kb % cpb) * 64
+  int grouped;         // 0: dense. else group size in channels (multiple of 64): A column origin =
+                       //    (n0 / grouped) * grouped, so an output tile only reads its own group's inputs
   // epilogue operands
   int act;
   const float* bias;           // [N] or nullptr
@@ -136,7 +137,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          const int a_col = (args.grouped ? n0 : 0) + (kb % args.cpb) * GEMM_BK;
+          const int a_col = (args.grouped ? (n0 / args.grouped) * args.grouped : 0) + (kb % args.cpb) * GEMM_BK;
           const int a_row = t0 + kb / args.cpb - args.pad;
           tma_load_3d(sa, &tmA, full_bar(stage), a_col, a_row, b);
           tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0);

@@ -158,7 +158,7 @@ def test_conv_gemm_grouped_k31_mish(L):
     W2 = wb.permute(0, 2, 1).reshape(D, KS * (D // G)).contiguous()
     out = torch.empty(nb * T, D, device=DEV, dtype=torch.bfloat16)
     L.gemm(xb, W2, out, epilogue=L.EPI_MISH_MASK_BF16, bias=bias, rows_per_batch=T, nbatch=nb, taps=KS, cin_blocks=1,
-           pad=KS // 2, grouped=True, block_n=64, seq_lens=lens)
+           pad=KS // 2, grouped=64, block_n=64, seq_lens=lens)
     ref = F.conv1d(xb.float().view(nb, T, D).transpose(1, 2), wb.float(), bias, padding=KS // 2, groups=G)
     ref = F.mish(ref.masked_fill(~mask[:, None, :], 0.0)).masked_fill(~mask[:, None, :], 0.0)
     ref = ref.transpose(1, 2).reshape(nb * T, D)
@@ -166,7 +166,7 @@ def test_conv_gemm_grouped_k31_mish(L):
     add = torch.randn(nb * T, D, device=DEV, generator=g)
     out2 = torch.empty(nb * T, D, device=DEV)
     L.gemm(xb, W2, out2, epilogue=L.EPI_MISH_MASK_RESID, bias=bias, rows_per_batch=T, nbatch=nb, taps=KS,
-           cin_blocks=1, pad=KS // 2, grouped=True, block_n=64, seq_lens=lens, addend=add)
+           cin_blocks=1, pad=KS // 2, grouped=64, block_n=64, seq_lens=lens, addend=add)
     assert _rel(out2, ref + add) < 3e-3
 
 
