@@ -1,0 +1,383 @@
+"""Host-side driver of the DiT forward / Euler-ODE step on the sm_100a kernels.
+
+Data layout in HBM: every activation of the DiT is a frame-major matrix
+[nb' * Tpad, C] where nb' = B (no CFG) or 2B ([conditional ; unconditional] halves, dit.py:200-215)
+and Tpad = ceil(max_duration / 128) * 128, so that 128-row GEMM / attention tiles never straddle two
+sequences. Frames t >= duration[b] are padding: zeroed where the reference masks them, ignored
+otherwise. The fp32 residual stream, the bf16 GEMM operands and the per-step modulation table all
+live in one workspace that is reused by every ODE step, which is what makes the whole step
+CUDA-graph replayable (the only per-step state is a device-side step counter).
+
+Everything that is arithmetic runs in liboron_b200.so; torch is used for allocation, the seeded
+noise draw (flow.py:270-283 semantics depend on torch.randn) and tiny integer/index preparation.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+TILE = 128
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def pick_block_n(rows: int, n: int) -> int:
+    """Tile width that minimises the number of 148-SM waves (ties -> wider tile, less smem traffic)."""
+    best, best_cost = 128, None
+    tiles_m = (rows + TILE - 1) // TILE
+    for bn in (256, 128):
+        if n % bn and bn == 256 and n < 256:
+            continue
+        tiles = tiles_m * ((n + bn - 1) // bn)
+        waves = (tiles + 147) // 148
+        cost = waves * bn  # time ~ waves * (tile work ~ bn)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+# ------------------------------------------------------------------------------------------------
+# packed weights
+# ------------------------------------------------------------------------------------------------
+class DiTWeights:
+    """bf16 / fp32 device copies of a DiT state dict in the layouts the kernels consume.
+
+    Lives outside ``state_dict()``: rebuilt whenever the owning module's parameters
+    change (load_state_dict / .to()).  ``sd`` uses keys relative to the DiT module
+    (e.g. ``transformer_blocks.0.attn.to_q.weight``).
+    """
+
+    def __init__(self, sd: dict, device: torch.device):
+        def bf(t):
+            return t.detach().to(device=device, dtype=BF16).contiguous()
+
+        def f32(t):
+            return t.detach().to(device=device, dtype=F32).contiguous()
+
+        self.device = device
+        self.dim = D = sd["proj_out.weight"].shape[1]
+        self.n_mels = n_mels = sd["proj_out.weight"].shape[0]
+        self.text_dim = C = sd["text_embed.text_embed.weight"].shape[1]
+        self.depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("transformer_blocks."))
+        tb = [int(k.split(".")[2]) for k in sd if k.startswith("text_embed.text_blocks.")]
+        self.conv_layers = (1 + max(tb)) if tb else 0
+        self.dim_head = 2 * sd["rotary_embed.inv_freq"].shape[0]
+        self.heads = D // self.dim_head
+        if self.dim_head != 64:
+            raise NotImplementedError("the sm_100a attention kernel is specialised for head_dim 64")
+        if D % 128 or C % 32:
+            raise NotImplementedError("dim must be a multiple of 128 and text_dim a multiple of 32")
+        self.inv_freq = f32(sd["rotary_embed.inv_freq"])
+
+        # timestep MLP (modules.py:54-58)
+        self.t0_w, self.t0_b = bf(sd["time_embed.time_mlp.0.weight"]), f32(sd["time_embed.time_mlp.0.bias"])
+        self.t2_w, self.t2_b = bf(sd["time_embed.time_mlp.2.weight"]), f32(sd["time_embed.time_mlp.2.bias"])
+
+        # all AdaLN projections stacked: one GEMM produces the whole modulation table
+        ws = [sd[f"transformer_blocks.{i}.attn_norm.linear.weight"] for i in range(self.depth)]
+        bs = [sd[f"transformer_blocks.{i}.attn_norm.linear.bias"] for i in range(self.depth)]
+        ws.append(sd["norm_out.linear.weight"])
+        bs.append(sd["norm_out.linear.bias"])
+        self.ada_w = bf(torch.cat(ws, 0))
+        self.ada_b = f32(torch.cat(bs, 0))
+        self.ada_n = self.ada_w.shape[0]  # depth*6D + 2D
+
+        # text embedding (encoder.py)
+        self.text_table = f32(sd["text_embed.text_embed.weight"])
+        self.text_blocks = []
+        for i in range(self.conv_layers):
+            p = f"text_embed.text_blocks.{i}."
+            self.text_blocks.append(dict(
+                dw_w=f32(sd[p + "dwconv.weight"]).view(C, 7).contiguous(), dw_b=f32(sd[p + "dwconv.bias"]),
+                ln_w=f32(sd[p + "norm.weight"]), ln_b=f32(sd[p + "norm.bias"]),
+                w1=bf(sd[p + "pwconv1.weight"]), b1=f32(sd[p + "pwconv1.bias"]),
+                gamma=f32(sd[p + "grn.gamma"]).view(-1).contiguous(), beta=f32(sd[p + "grn.beta"]).view(-1).contiguous(),
+                w2=bf(sd[p + "pwconv2.weight"]), b2=f32(sd[p + "pwconv2.bias"]),
+            ))
+
+        # input projection split by source (dit.py:53): x | cond | text
+        W = sd["input_embed.proj.weight"].detach().to(device=device, dtype=F32)
+        self.kx = _rup(n_mels, 64)
+        wx = torch.zeros(D, self.kx, device=device, dtype=F32)
+        wx[:, :n_mels] = W[:, :n_mels]
+        self.wx = wx.to(BF16).contiguous()
+        self.kct = _rup(n_mels + C, 64)
+        wct = torch.zeros(D, self.kct, device=device, dtype=F32)
+        wct[:, : n_mels + C] = W[:, n_mels:]
+        self.wct = wct.to(BF16).contiguous()
+        self.in_b = f32(sd["input_embed.proj.bias"])
+
+        # ConvPositionEmbedding (modules.py:120-124): grouped k=31 convs as tap-major implicit-GEMM weights,
+        # narrow groups packed block-diagonally into 64-channel blocks
+        self.conv_pos = []
+        for idx in (0, 2):
+            w = sd[f"input_embed.conv_pos_embed.conv1d.{idx}.weight"].detach().to(device=device, dtype=F32)
+            cg, ks = w.shape[1], w.shape[2]
+            gsz = max(64, cg)
+            if gsz % 64:
+                raise NotImplementedError("conv_pos group width must divide or be a multiple of 64")
+            o = torch.arange(D, device=device)
+            off = (o // cg) * cg - (o // gsz) * gsz
+            w2 = torch.zeros(D, gsz, ks, device=device, dtype=F32)
+            w2[o[:, None], off[:, None] + torch.arange(cg, device=device)[None, :], :] = w
+            w2 = w2.permute(0, 2, 1).reshape(D, ks * gsz)
+            self.conv_pos.append(dict(w=w2.to(BF16).contiguous(), b=f32(sd[f"input_embed.conv_pos_embed.conv1d.{idx}.bias"]),
+                                      taps=ks, gsz=gsz))
+
+        # transformer blocks
+        self.blocks = []
+        for i in range(self.depth):
+            p = f"transformer_blocks.{i}."
+            self.blocks.append(dict(
+                wqkv=bf(torch.cat([sd[p + "attn.to_q.weight"], sd[p + "attn.to_k.weight"], sd[p + "attn.to_v.weight"]], 0)),
+                bqkv=f32(torch.cat([sd[p + "attn.to_q.bias"], sd[p + "attn.to_k.bias"], sd[p + "attn.to_v.bias"]], 0)),
+                wo=bf(sd[p + "attn.to_out.0.weight"]), bo=f32(sd[p + "attn.to_out.0.bias"]),
+                w1=bf(sd[p + "ff.ff.0.weight"]), b1=f32(sd[p + "ff.ff.0.bias"]),
+                w2=bf(sd[p + "ff.ff.3.weight"]), b2=f32(sd[p + "ff.ff.3.bias"]),
+            ))
+        self.ff_dim = self.blocks[0]["w1"].shape[0]
+        self.wp, self.bp = bf(sd["proj_out.weight"]), f32(sd["proj_out.bias"])
+
+        # host-built constant tables, bit-identical to the reference buffers
+        self._pos_table = None
+        self._rope = {}
+
+    def pos_table(self, length: int) -> torch.Tensor:
+        """precompute_freqs_cis(text_dim, 8192) (modules.py:191-196), built on CPU like the reference buffer."""
+        if self._pos_table is None or self._pos_table.shape[0] < length:
+            n = max(8192, length)
+            C = self.text_dim
+            freqs = 1.0 / (10000 ** (torch.arange(0, C, 2)[: (C // 2)].float() / C))
+            ang = torch.outer(torch.arange(n), freqs).float()
+            self._pos_table = torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(self.device).contiguous()
+        return self._pos_table
+
+    def rope(self, length: int):
+        """cos/sin [length, 32] of RotaryEmbedding._build_cache (modules.py:80-89), computed on device as there."""
+        if length not in self._rope:
+            t = torch.arange(length, device=self.device).float()
+            ang = torch.outer(t, self.inv_freq)
+            self._rope[length] = (ang.cos().contiguous(), ang.sin().contiguous())
+        return self._rope[length]
+
+
+# ------------------------------------------------------------------------------------------------
+# per-shape workspace
+# ------------------------------------------------------------------------------------------------
+class Workspace:
+    def __init__(self, w: DiTWeights, nb: int, nbp: int, tpad: int, steps: int, keep_traj: bool):
+        dev = w.device
+        D, C, M = w.dim, w.text_dim, w.n_mels
+        R, Rb = nbp * tpad, nb * tpad
+        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
+        self.nb, self.nbp, self.tpad, self.steps = nb, nbp, tpad, steps
+        self.ids = z(R, dt=torch.int32)
+        self.drop = z(nbp, dt=torch.uint8)
+        self.row_valid = z(R, dt=torch.uint8)
+        self.seq_lens = z(nbp, dt=torch.int32)
+        self.xt = z(R, C)
+        self.xt_n = z(R, C, dt=BF16)
+        self.xt_h = z(R, 2 * C, dt=BF16)
+        self.gx2 = z(nbp, 2 * C)
+        self.a_ct = z(R, w.kct, dt=BF16)
+        self.cond = z(Rb, M)
+        self.c0 = z(R, D)
+        self.x = z(Rb, M)
+        self.xb = z(R, w.kx, dt=BF16)
+        self.h0 = z(R, D)
+        self.h0b = z(R, D, dt=BF16)
+        self.c1 = z(R, D, dt=BF16)
+        self.xres = z(R, D)
+        self.nrm = z(R, D, dt=BF16)
+        self.qkv = z(R, 3 * D, dt=BF16)
+        self.ao = z(R, D, dt=BF16)
+        self.hid = z(R, w.ff_dim, dt=BF16)
+        self.v = z(R, M)
+        self.vg = z(Rb, M)
+        self.step = z(1, dt=torch.int32)
+        self.tvals = z(steps)
+        self.dt = z(steps)
+        self.tfeat = z(steps, 256, dt=BF16)
+        self.th = z(steps, D, dt=BF16)
+        self.ts = z(steps, D, dt=BF16)
+        self.table = z(steps, w.ada_n)
+        self.traj = z(steps + 1, Rb, M) if keep_traj else None
+        self.graph = None
+        self.graph_key = None
+
+
+@dataclass
+class Branch:
+    drop_audio: bool
+    drop_text: bool
+
+
+class DiTEngine:
+    """Runs DiT.forward (dit.py:165-234) and the CFG Euler loop (flow.py:244-299) on the CUDA kernels."""
+
+    def __init__(self, weights: DiTWeights):
+        self.w = weights
+        self._ws: dict = {}
+        self.use_graph = True
+
+    # -------------------------------------------------------------------------------------------
+    def workspace(self, nb: int, nbp: int, tpad: int, steps: int, keep_traj: bool) -> Workspace:
+        key = (nb, nbp, tpad, steps, keep_traj)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 8:
+                self._ws.clear()
+            ws = Workspace(self.w, nb, nbp, tpad, steps, keep_traj)
+            self._ws[key] = ws
+        return ws
+
+    # -------------------------------------------------------------------------------------------
+    def load_sequences(self, ws: Workspace, *, text: torch.Tensor, durations: list[int], seq_len: int,
+                       branches: list[Branch]) -> None:
+        """Token ids (+1 shift, crop / 0-pad to seq_len: encoder.py:68-74), drop flags and lengths."""
+        nb, tpad = ws.nb, ws.tpad
+        ids = (text.to(torch.int64) + 1)[:, :seq_len]
+        ids2 = torch.zeros(nb, tpad, device=self.w.device, dtype=torch.int32)
+        ids2[:, : ids.shape[1]] = ids.to(torch.int32)
+        ws.ids.view(ws.nbp, tpad).copy_(ids2.repeat(len(branches), 1))
+        drop = [int(br.drop_text) for br in branches for _ in range(nb)]
+        ws.drop.copy_(torch.tensor(drop, dtype=torch.uint8), non_blocking=False)
+        ws.seq_lens.copy_(torch.tensor(durations * len(branches), dtype=torch.int32))
+
+    def text_embed(self, ws: Workspace) -> None:
+        """TextEmbedding.forward for all branches at once -> ws.xt (fp32 [R, text_dim])."""
+        w = self.w
+        L.text_embed_front(ws.ids, ws.drop, w.text_table, w.pos_table(ws.tpad), rows_per_batch=ws.tpad, nb=ws.nbp,
+                           x=ws.xt, row_valid=ws.row_valid)
+        for blk in w.text_blocks:
+            L.dwconv7_ln(ws.xt, rows_per_batch=ws.tpad, nbatch=ws.nbp, seq_lens=ws.seq_lens, w=blk["dw_w"],
+                         wb=blk["dw_b"], ln_w=blk["ln_w"], ln_b=blk["ln_b"], eps=1e-6, out=ws.xt_n)
+            L.gemm(ws.xt_n, blk["w1"], ws.xt_h, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_ERF,
+                   rows_per_batch=ws.tpad, nbatch=ws.nbp, block_n=128)
+            L.grn(ws.xt_h, rows_per_batch=ws.tpad, nb=ws.nbp, seq_lens=ws.seq_lens, gamma=blk["gamma"],
+                  beta=blk["beta"], gx2=ws.gx2)
+            L.gemm(ws.xt_h, blk["w2"], ws.xt, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=ws.tpad,
+                   nbatch=ws.nbp, addend=ws.xt, row_valid=ws.row_valid,
+                   block_n=128 if w.text_dim % 128 == 0 else 64)
+
+    def static_embed(self, ws: Workspace, cond: torch.Tensor, branches: list[Branch]) -> None:
+        """C0 = [cond | text_embed] @ W[:, n_mels:]^T + b — the step-invariant part of InputEmbedding.proj."""
+        w = self.w
+        nb, tpad, M = ws.nb, ws.tpad, w.n_mels
+        Rb = nb * tpad
+        T = cond.shape[1]
+        ws.cond.view(nb, tpad, M)[:, :T].copy_(cond)
+        if T < tpad:
+            ws.cond.view(nb, tpad, M)[:, T:].zero_()
+        for i, br in enumerate(branches):
+            dst = ws.a_ct[i * Rb:(i + 1) * Rb]
+            if br.drop_audio:
+                dst[:, :M].zero_()
+            else:
+                L.cast_rows_bf16(ws.cond, dst[:, :M])
+        L.cast_rows_bf16(ws.xt, ws.a_ct[:, M:M + w.text_dim])
+        L.gemm(ws.a_ct, w.wct, ws.c0, epilogue=L.EPI_F32, bias=w.in_b, rows_per_batch=ws.tpad, nbatch=ws.nbp,
+               block_n=pick_block_n(ws.nbp * ws.tpad, w.dim))
+
+    def modulation_table(self, ws: Workspace, times: torch.Tensor) -> None:
+        """time_embed -> SiLU -> every AdaLN projection, for all rows of `times` (fp32 [n <= ws.steps])."""
+        w = self.w
+        n = times.numel()
+        ws.tvals[:n].copy_(times)
+        L.time_sinusoid(ws.tvals[:n], ws.tfeat[:n])
+        L.gemm(ws.tfeat[:n], w.t0_w, ws.th[:n], epilogue=L.EPI_BF16, bias=w.t0_b, act=L.ACT_SILU)
+        L.gemm(ws.th[:n], w.t2_w, ws.ts[:n], epilogue=L.EPI_BF16, bias=w.t2_b, act=L.ACT_SILU)
+        L.gemm(ws.ts[:n], w.ada_w, ws.table[:n], epilogue=L.EPI_F32, bias=w.ada_b, block_n=256)
+
+    # -------------------------------------------------------------------------------------------
+    def velocity(self, ws: Workspace, *, mod_nb: int, use_step: bool) -> None:
+        """One DiT forward from ws.xb (bf16 copy of the ODE state) to ws.v (fp32 velocity, all branches)."""
+        w = self.w
+        D, tpad, nbp = w.dim, ws.tpad, ws.nbp
+        R = nbp * tpad
+        cos, sin = w.rope(tpad)
+        tab = ws.table.view(-1)
+        step_ptr = ws.step if use_step else None
+        # modulation rows: per ODE step one row shared by every sequence (mod_nb == 1), or one row per
+        # batch element (generic DiT.forward with per-sample times)
+        sstride = w.ada_n if use_step else 0
+        mld = 0 if mod_nb == 1 else w.ada_n
+        common = dict(rows_per_batch=tpad, nbatch=nbp)
+        bn_d = pick_block_n(R, D)
+
+        L.gemm(ws.xb, w.wx, ws.h0, epilogue=L.EPI_EMBED_DUAL, addend=ws.c0, seq_lens=ws.seq_lens, out2=ws.h0b,
+               block_n=128, **common)
+        c1, c2 = w.conv_pos
+        L.gemm(ws.h0b, c1["w"], ws.c1, epilogue=L.EPI_MISH_MASK_BF16, bias=c1["b"], taps=c1["taps"],
+               cin_blocks=c1["gsz"] // 64, pad=c1["taps"] // 2, grouped=c1["gsz"], block_n=64, seq_lens=ws.seq_lens,
+               **common)
+        L.gemm(ws.c1, c2["w"], ws.xres, epilogue=L.EPI_MISH_MASK_RESID, bias=c2["b"], taps=c2["taps"],
+               cin_blocks=c2["gsz"] // 64, pad=c2["taps"] // 2, grouped=c2["gsz"], block_n=64, seq_lens=ws.seq_lens,
+               addend=ws.h0, **common)
+
+        for i, blk in enumerate(w.blocks):
+            o = i * 6 * D  # (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) — modules.py:215-217
+            L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
+                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
+            L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
+                   rope_cols=2 * D, block_n=pick_block_n(R, 3 * D), **common)
+            L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
+                        scale=1.0 / math.sqrt(w.dim_head))
+            L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
+                   gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
+                   mask_rows=True, block_n=bn_d, **common)
+            L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
+                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
+            L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
+                   block_n=pick_block_n(R, w.ff_dim), **common)
+            L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
+                   gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
+                   block_n=bn_d, **common)
+        o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
+        L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o:], shift=tab[o + D:], mod_ld=mld, mod_nb=mod_nb,
+                      step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
+        L.gemm(ws.nrm, w.wp, ws.v, epilogue=L.EPI_F32, bias=w.bp, block_n=128, **common)
+
+    def euler(self, ws: Workspace, *, cfg: float, has_uncond: bool) -> None:
+        L.cfg_euler_step(ws.x, ws.v, nb=ws.nb, rows_per_batch=ws.tpad, n_mels=self.w.n_mels, has_uncond=has_uncond,
+                         cfg=cfg, dt=ws.dt, step_ptr=ws.step, xb=ws.xb, traj=ws.traj, v_out=ws.vg)
+
+    # -------------------------------------------------------------------------------------------
+    def run_ode(self, ws: Workspace, *, steps: int, cfg: float, has_uncond: bool) -> None:
+        """`steps` x (DiT forward + CFG/Euler update). The step is captured once into a CUDA graph."""
+
+        def one_step():
+            self.velocity(ws, mod_nb=1, use_step=True)
+            self.euler(ws, cfg=cfg, has_uncond=has_uncond)
+
+        if not self.use_graph:
+            for _ in range(steps):
+                one_step()
+            return
+        key = (cfg, has_uncond)
+        if ws.graph is None or ws.graph_key != key:
+            # warm-up outside capture (sets kernel attributes, builds tables), then rewind the state it touched
+            x_save, xb_save = ws.x.clone(), ws.xb.clone()
+            one_step()
+            ws.x.copy_(x_save)
+            ws.xb.copy_(xb_save)
+            ws.step.zero_()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one_step()
+            ws.x.copy_(x_save)
+            ws.xb.copy_(xb_save)
+            ws.step.zero_()
+            ws.graph, ws.graph_key = g, key
+        for _ in range(steps):
+            ws.graph.replay()

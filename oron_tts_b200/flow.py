@@ -1,0 +1,159 @@
+"""CFM sampler (Euler ODE + classifier-free guidance + sway schedule) on the sm_100a engine.
+
+Drop-in for src/models/flow.py:49-306: same constructor, ``sample`` signature, return value
+(``(mel [B, T, n_mels], trajectory list of steps+1 tensors)``) and ValueError messages. The ODE loop
+itself is one CUDA graph replayed ``steps`` times: text embedding, the step-invariant part of the
+input projection and all AdaLN modulation vectors are hoisted out of the loop, and the conditional /
+unconditional passes are batched in every kernel.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .dit import DiT
+from .engine import Branch, TILE, _rup
+
+
+def _lens_to_mask(lens: torch.Tensor, length: int | None = None) -> torch.Tensor:
+    """Boolean [B, N] prefix mask from lengths (flow.py:22-27)."""
+    n = int(lens.amax().item()) if length is None else length
+    return torch.arange(n, device=lens.device)[None, :] < lens[:, None]
+
+
+class CFM(nn.Module):
+    def __init__(self, backbone: DiT, sigma: float = 0.0, audio_drop_prob: float = 0.3, cond_drop_prob: float = 0.2,
+                 frac_lengths_mask: tuple[float, float] = (0.7, 1.0), n_mels: int = 100) -> None:
+        super().__init__()
+        self.backbone = backbone
+        self.sigma = sigma
+        self.audio_drop_prob = audio_drop_prob
+        self.cond_drop_prob = cond_drop_prob
+        self.frac_lengths_mask = frac_lengths_mask
+        self.n_mels = n_mels
+
+    # ---- training objective (flow.py:69-159) -----------------------------------------------------
+    def forward(self, inp: torch.Tensor, text_ids: torch.Tensor, *, lens: torch.Tensor | None = None) -> torch.Tensor:
+        """OT-CFM loss. Only the deterministic eval-mode objective (flow.py:113-128, 136-138) is available:
+        autograd through the sm_100a kernels (the training step) is not built yet."""
+        if self.training:
+            raise NotImplementedError(
+                "oron_tts_b200 implements the inference hot path; the OT-CFM training step (backward kernels, "
+                "NCCL gradient all-reduce) is scheduled after it. Call .eval() for the deterministic validation loss.")
+        if inp.ndim == 3 and inp.shape[1] == self.n_mels:
+            inp = inp.transpose(1, 2)
+        B, T, dev = inp.shape[0], inp.shape[1], inp.device
+        if lens is None:
+            lens = torch.full((B,), T, device=dev, dtype=torch.long)
+        mask = _lens_to_mask(lens, length=T)
+        mid = sum(self.frac_lengths_mask) / 2
+        span = (torch.full((B,), mid, device=dev).float() * lens).long()
+        start = ((lens - span) // 2).clamp(min=0)
+        pos = torch.arange(T, device=dev)
+        span_mask = (pos[None, :] >= start[:, None]) & (pos[None, :] < (start + span)[:, None]) & mask
+        time = torch.full((B,), 0.5, dtype=inp.dtype, device=dev)
+        x1 = inp
+        cond = torch.where(span_mask[..., None], torch.zeros_like(x1), x1)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        x0 = torch.randn(x1.shape, generator=gen, device=dev, dtype=inp.dtype)
+        t = time[:, None, None]
+        phi = (1 - t) * x0 + t * x1
+        pred = self.backbone(x=phi, cond=cond, text=text_ids, time=time, mask=mask)
+        return F.mse_loss(pred, x1 - x0, reduction="none")[span_mask].mean()
+
+    # ---- sampling (flow.py:161-306) -----------------------------------------------------------------
+    @torch.inference_mode()
+    def sample(self, cond: torch.Tensor, text_ids: torch.Tensor, duration: torch.Tensor | int, *,
+               lens: torch.Tensor | None = None, steps: int = 32, cfg_strength: float = 1.0,
+               sway_sampling_coef: float | None = None, seed: int | None = None, max_duration: int = 65536,
+               y0: torch.Tensor | None = None) -> tuple[torch.Tensor, list[torch.Tensor]]:
+        """``y0`` (extra, optional): inject the initial noise [B, max_dur, n_mels] instead of drawing it —
+        needed for cross-device parity because CPU and CUDA generators produce different streams."""
+        if steps < 1:
+            raise ValueError(f"steps must be >= 1, got {steps}")
+        if cfg_strength < 0:
+            raise ValueError(f"cfg_strength must be >= 0, got {cfg_strength}")
+        self.eval()
+        batch, cond_seq_len, device = cond.shape[0], cond.shape[1], cond.device
+        if not cond.is_cuda:
+            raise RuntimeError("CFM.sample runs only on a CUDA device (oron_tts_b200 has no CPU fallback)")
+
+        if lens is None:
+            lens = torch.full((batch,), cond_seq_len, device=device, dtype=torch.long)
+        else:
+            lens = lens.to(device=device, dtype=torch.long)
+        if lens.numel() != batch:
+            raise ValueError(f"lens must have {batch} values, got {lens.numel()}")
+        if isinstance(duration, int):
+            duration = torch.full((batch,), duration, device=device, dtype=torch.long)
+        else:
+            duration = duration.to(device=device, dtype=torch.long)
+        if duration.numel() != batch:
+            raise ValueError(f"duration must have {batch} values, got {duration.numel()}")
+        # one host sync for all the reference's checks (flow.py:219-230)
+        host = torch.stack([duration, lens]).tolist()
+        dur_h, lens_h = host[0], host[1]
+        if any(d <= 0 for d in dur_h):
+            raise ValueError("duration values must be > 0")
+        if any(v < 0 for v in lens_h):
+            raise ValueError("lens values must be >= 0")
+        if any(v > d for v, d in zip(lens_h, dur_h)):
+            raise ValueError("conditioning lens must be <= duration for every sample")
+        if any(d > max_duration for d in dur_h):
+            raise ValueError(f"duration exceeds max_duration={max_duration}")
+        max_dur = max(dur_h)
+        if cond_seq_len > max_dur:
+            raise ValueError("conditioning sequence length must be <= max duration")
+
+        cond = cond.to(torch.float32)
+        cond_mask = _lens_to_mask(lens)
+        cond = F.pad(cond, (0, 0, 0, max_dur - cond_seq_len), value=0.0)
+        cond_mask = F.pad(cond_mask, (0, max_dur - cond_mask.shape[-1]), value=False)
+        cond_mask_3d = cond_mask.unsqueeze(-1)
+        step_cond = torch.where(cond_mask_3d, cond, torch.zeros_like(cond))
+
+        eng = self.backbone.engine()
+        w = eng.w
+        use_cfg = cfg_strength >= 1e-5
+        branches = [Branch(False, False), Branch(True, True)] if use_cfg else [Branch(False, False)]
+        tpad = _rup(max_dur, TILE)
+        ws = eng.workspace(batch, batch * len(branches), tpad, steps, True)
+
+        # initial noise: per-sample sequential draws from one generator, zero padded (flow.py:270-283)
+        if y0 is None:
+            generator = None
+            if seed is not None:
+                generator = torch.Generator(device=device).manual_seed(seed)
+            ys = [torch.randn(d, self.n_mels, device=device, dtype=step_cond.dtype, generator=generator) for d in dur_h]
+            y0 = torch.nn.utils.rnn.pad_sequence(ys, padding_value=0.0, batch_first=True)
+        else:
+            y0 = y0.to(device=device, dtype=torch.float32)
+
+        # sway-sampled schedule (flow.py:286-288)
+        t = torch.linspace(0, 1, steps + 1, device=device, dtype=step_cond.dtype)
+        if sway_sampling_coef is not None:
+            t = t + sway_sampling_coef * (torch.cos(torch.pi / 2 * t) - 1 + t)
+        ws.dt.copy_(t[1:] - t[:-1])
+
+        try:
+            eng.load_sequences(ws, text=text_ids, durations=dur_h, seq_len=max_dur, branches=branches)
+            eng.text_embed(ws)
+            eng.static_embed(ws, step_cond, branches)
+            eng.modulation_table(ws, t[:-1])
+            xv = ws.x.view(batch, tpad, self.n_mels)
+            xv.zero_()
+            xv[:, :max_dur].copy_(y0)
+            from . import _lib as L
+            L.cast_rows_bf16(ws.x, ws.xb[:, : self.n_mels], reps=len(branches))
+            ws.traj[0].copy_(ws.x)
+            ws.step.zero_()
+            eng.run_ode(ws, steps=steps, cfg=float(cfg_strength), has_uncond=use_cfg)
+        finally:
+            self.backbone.clear_cache()
+
+        tr = ws.traj.view(steps + 1, batch, tpad, self.n_mels)[:, :, :max_dur]
+        trajectory = [tr[i].clone() for i in range(steps + 1)]
+        out = torch.where(cond_mask_3d, cond, trajectory[-1])
+        return out, trajectory
