@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Headline benchmark: target-audio-seconds per second at 32 NFE, Base DiT (BASELINE.json config 2:
+5 s synthetic reference mel + 10 s target, CFG 2.0, sway -1, bf16 tensor-core arithmetic, fp32 state).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+  python bench.py --impl reference --gpus N ...             # the reference's CPU algorithm (oracle port)
+
+A "step" is one utterance through the hot path: CFM.sample (32 x [DiT forward on cond+uncond] + CFG/Euler)
+followed by the Vocos decode of the target region. `value` = whole-job target-audio seconds / device time
+with inputs resident in HBM; `e2e` = the same through F5TTS.synthesize with the reference waveform in pinned
+host memory and the result copied back to the host. Multi-GPU: independent utterances per rank, no data-path
+collective (weak scaling); only the timing barrier / max-over-ranks uses NCCL.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import torch  # noqa: E402
+
+METRIC = "target_audio_seconds_per_second_32nfe_base_dit"
+UNIT = "audio-s/s"
+REF_SAMPLES, REF_LEN, TGT_LEN, STEPS_NFE, CFG, SWAY = 120000, 469, 937, 32, 2.0, -1.0
+T_TOTAL = REF_LEN + TGT_LEN
+AUDIO_S = (TGT_LEN - 1) * 256 / 24000.0  # seconds of waveform the vocoder emits for the target region
+BENCH_TEXT = ("Өнөөдөр цаг агаар сайхан байна, бид хамтдаа уул руу алхаж, голын эрэг дээр амарч, "
+              "орой нь гэртээ харина.")
+BENCH_REF_TEXT = "Энэ бол жишээ өгүүлбэр бөгөөд дуу хоолойг дуурайхад ашиглагдана."
+
+
+def algorithmic_flops_per_nfe(T: int, D: int = 1024, depth: int = 22, nb: int = 2) -> dict:
+    """per row 22*(8D^2 + 16D^2) GEMM + attention 4*T*D per layer (rows = nb*T)."""
+    rows = nb * T
+    gemm = rows * depth * 24 * D * D
+    attn = rows * depth * 4 * T * D
+    io = rows * (2 * 128 * D + 2 * 2 * D * 64 * 31 + 2 * D * 100)
+    return dict(gemm=gemm, attn=attn, other=io, total=gemm + attn + io)
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 200 ms during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.2)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_workload(device, seed: int):
+    """Synthetic config-2 inputs + random-init Base model (zero-init tensors re-randomised)."""
+    import weights as GW
+
+    from oron_tts_b200.f5tts import F5TTS, _stretch_text_to_len
+    from oron_tts_b200.vocos import Vocos
+
+    model = F5TTS.from_config(GW.CONFIGS["base"])
+    model.load_state_dict(GW.fill_state_dict(model.state_dict(), GW.SEEDS["base"]), strict=True)
+    model = model.to(device).eval()
+    voc = Vocos()
+    voc.load_state_dict(GW.fill_state_dict(voc.state_dict(), 4321), strict=True)
+    voc = voc.to(device).eval()
+    model.set_vocoder(voc)
+    g = torch.Generator().manual_seed(seed)
+    ref_mel = torch.randn(1, REF_LEN, 100, generator=g) * 1.5 - 3.0
+    ref_ids = torch.randint(11, 65, (60,), generator=g).tolist()
+    tgt_ids = torch.randint(11, 65, (120,), generator=g).tolist()
+    full = torch.tensor([_stretch_text_to_len(ref_ids, REF_LEN) + _stretch_text_to_len(tgt_ids, TGT_LEN)])
+    ref_wav = ((torch.rand(REF_SAMPLES, generator=g) * 2 - 1) * 0.3).pin_memory()
+    return model, voc, ref_mel.to(device), full.to(device), ref_wav
+
+
+def run_ours(args) -> dict:
+    import torch.distributed as dist
+
+    from oron_tts_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()
+    model, voc, ref_mel, ids, ref_wav = build_workload(dev, seed=100 + rank)
+    cfm = model.cfm
+    dur = torch.tensor([T_TOTAL], device=dev)
+    lens = torch.tensor([REF_LEN], device=dev)
+
+    def step_device(seed):
+        mel, _ = cfm.sample(ref_mel, ids, dur, lens=lens, steps=STEPS_NFE, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=seed)
+        return voc.decode(mel[:, REF_LEN:, :].transpose(1, 2))
+
+    def step_e2e(seed):
+        return model.synthesize(BENCH_TEXT, lang="mn", ref_audio_path=ref_wav, ref_text=BENCH_REF_TEXT, n_steps=STEPS_NFE,
+                                cfg_strength=CFG, sway_sampling_coef=SWAY, target_duration_s=10.0, seed=seed, device=str(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for i in range(k):
+            out = fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for i in range(args.warmup):
+        wav = step_device(1000 + i)
+    eng = cfm.backbone.engine()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0, r0 = L.launch_count(), eng.replayed_launches
+    ms, wav = timed(step_device, args.steps)
+    launches = (L.launch_count() - n0) + (eng.replayed_launches - r0)
+    assert wav.shape[-1] == (TGT_LEN - 1) * 256 and bool(torch.isfinite(wav).all())
+    # end to end through the public API, host buffers in, host waveform out
+    for i in range(min(args.warmup, 2)):
+        step_e2e(2000 + i)
+    ms_e2e, wav_host = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert not wav_host.is_cuda and wav_host.numel() == (TGT_LEN - 1) * 256
+
+    value = world * args.steps * AUDIO_S / (ms / 1e3)
+    value_e2e = world * args.steps * AUDIO_S / (ms_e2e / 1e3)
+    out = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 3), "ms_per_nfe": round(ms / args.steps / STEPS_NFE, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cfg2: Base DiT (dim 1024, depth 22), 469 ref + 937 target frames, 32 NFE, CFG 2.0, sway -1, "
+                               "+ Vocos decode of the target; 1 utterance per GPU per step",
+                   "l2": "weights (856 MB bf16) exceed the 126 MB L2 and are re-streamed every NFE; no explicit flush",
+                   "parallelism": f"utterance-sharded x{world} (no data-path collective)"},
+        "e2e": {"value": round(value_e2e, 3), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 3),
+                "h2d_bytes_per_step": int(ref_wav.numel() * 4 + T_TOTAL * 8 + 16),
+                "d2h_bytes_per_step": int(wav_host.numel() * 4 + 16)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if rank == 0:
+        out["roofline"] = roofline(eng, cfm, ref_mel, ids, dur, lens)
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(nfe=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else {}
+
+
+def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
+    """Dominant kernel = gemm_bf16_tcgen05 (all Linear / conv launches of an NFE). achieved = algorithmic GEMM
+    FLOPs of one NFE / summed CUDA-event time of its GEMM launches, measured on one eager (ungraphed) step."""
+    from oron_tts_b200 import _lib as L
+
+    peaks = {}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        peaks = json.load(open(p))
+    peak, which = (peaks["bf16_tflops_sustained"], "measured (sustained cuBLAS bf16)") if "bf16_tflops_sustained" in peaks \
+        else (1400.0, "fallback (B200_PROFILING.md sustained)")
+    ws = next(iter(eng._ws.values())) if len(eng._ws) == 1 else max(eng._ws.values(), key=lambda w: w.steps * w.tpad)
+    records = []
+    orig = {name: getattr(L, name) for name in ("gemm", "attention", "ln_modulate", "cfg_euler_step")}
+
+    def wrap(name):
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig[name](*a, **k)
+            e1.record()
+            records.append((name, e0, e1))
+        return f
+
+    try:
+        for name in orig:
+            setattr(L, name, wrap(name))
+        ws.step.zero_()
+        for _ in range(3):  # warm
+            eng.velocity(ws, mod_nb=1, use_step=True)
+        records.clear()
+        reps = 5
+        for _ in range(reps):
+            eng.velocity(ws, mod_nb=1, use_step=True)
+        torch.cuda.synchronize()
+    finally:
+        for name, fn in orig.items():
+            setattr(L, name, fn)
+    t = {}
+    for name, e0, e1 in records:
+        t[name] = t.get(name, 0.0) + e0.elapsed_time(e1) / reps
+    fl = algorithmic_flops_per_nfe(T_TOTAL)
+    gemm_flops = fl["gemm"] + fl["other"]
+    achieved = gemm_flops / (t["gemm"] * 1e-3) / 1e12
+    total = sum(t.values())
+    return {
+        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+        "frac": round(achieved / peak, 4), "peak_source": which, "traffic": None,
+        "flops_per_nfe": fl, "eager_ms_per_nfe": {k: round(v, 4) for k, v in t.items()},
+        "share_of_step": {k: round(v / total, 4) for k, v in t.items()},
+        "attention_tflops": round(fl["attn"] / (t["attention"] * 1e-3) / 1e12, 1),
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_baseline(nfe: int = 1) -> dict:
+    """The reference algorithm on the host cores (oracle port, fp32, all torch threads): `nfe` CFG NFE steps of
+    config 2 timed and extrapolated to 32 (the DiT forward is >99% of an utterance on CPU)."""
+    import weights as GW
+
+    from oracle import dit_oracle as DO
+    from oron_tts_b200.f5tts import F5TTS
+
+    with torch.device("meta"):
+        proto = F5TTS.from_config(GW.CONFIGS["base"]).state_dict()
+    sd = GW.fill_state_dict({k: torch.empty(v.shape) for k, v in proto.items()}, GW.SEEDS["base"])
+    sd["cfm.backbone.rotary_embed.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
+    g = torch.Generator().manual_seed(100)
+    x = torch.randn(1, T_TOTAL, 100, generator=g)
+    cond = torch.zeros(1, T_TOTAL, 100)
+    cond[:, :REF_LEN] = torch.randn(1, REF_LEN, 100, generator=g) * 1.5 - 3.0
+    ids = torch.randint(11, 65, (1, T_TOTAL), generator=g)
+    mask = torch.ones(1, T_TOTAL, dtype=torch.bool)
+    cache: dict = {}
+    with torch.inference_mode():
+        DO.dit_forward(sd, x[:, :256], cond[:, :256], ids[:, :256], torch.tensor([0.1]), mask[:, :256], cfg_infer=True)  # warm
+        t0 = time.perf_counter()
+        for i in range(nfe):
+            DO.dit_forward(sd, x, cond, ids, torch.tensor([0.1 * (i + 1)]), mask, cfg_infer=True, text_cache=cache)
+        dt = (time.perf_counter() - t0) / nfe
+    return {"value": round(AUDIO_S / (dt * STEPS_NFE), 5), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "s_per_nfe": round(dt, 3), "host_cpus": os.cpu_count(),
+            "sample": f"{nfe} CFG NFE of cfg2 (T=1406, rows 2812) on the oracle port, x32 extrapolated to one utterance"}
+
+
+def run_reference(args) -> dict:
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return {}
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    for _ in range(max(0, min(args.warmup, 1) - 1)):
+        cpu_baseline(1)
+    cb = cpu_baseline(max(1, min(args.steps, 3)))
+    return {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(cb["s_per_nfe"] * STEPS_NFE * 1e3, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: Base DiT, 469 ref + 937 target frames, 32 NFE, CFG 2.0 (CPU, oracle port of the reference)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    res = run_reference(a) if a.impl == "reference" else run_ours(a)
+    if res:
+        print(json.dumps(res, ensure_ascii=False), flush=True)

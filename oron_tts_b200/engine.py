@@ -213,6 +213,7 @@ class Workspace:
         self.traj = z(steps + 1, Rb, M) if keep_traj else None
         self.graph = None
         self.graph_key = None
+        self.graph_launches = 0
 
 
 @dataclass
@@ -228,6 +229,7 @@ class DiTEngine:
         self.w = weights
         self._ws: dict = {}
         self.use_graph = True
+        self.replayed_launches = 0  # kernels executed through CUDA-graph replays (not seen by oron_launch_count)
 
     # -------------------------------------------------------------------------------------------
     def workspace(self, nb: int, nbp: int, tpad: int, steps: int, keep_traj: bool) -> Workspace:
@@ -373,11 +375,14 @@ class DiTEngine:
             ws.step.zero_()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
             with torch.cuda.graph(g):
                 one_step()
+            ws.graph_launches = L.launch_count() - n0  # kernels replayed per ODE step
             ws.x.copy_(x_save)
             ws.xb.copy_(xb_save)
             ws.step.zero_()
             ws.graph, ws.graph_key = g, key
         for _ in range(steps):
             ws.graph.replay()
+        self.replayed_launches += steps * ws.graph_launches

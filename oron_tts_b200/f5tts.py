@@ -216,8 +216,13 @@ class F5TTS(nn.Module):
             if not ref_text:
                 _log.warning("ref_audio_path was provided without ref_text; duration will fall back to the ref-free "
                              "estimate and the reference region will use filler text.")
-            wav, _ = ap.load_audio(ref_audio_path)
-            wav = ap.normalize_audio(wav).to(device)
+            if isinstance(ref_audio_path, torch.Tensor):
+                # extension over the reference: an in-memory 24 kHz mono waveform (e.g. pinned host memory)
+                wav = ref_audio_path.reshape(-1)
+                wav = ap.normalize_audio(wav.to(device, non_blocking=True))
+            else:
+                wav, _ = ap.load_audio(ref_audio_path)
+                wav = ap.normalize_audio(wav).to(device)
             ref_mel_raw = ap.mel_spectrogram(wav)  # [n_mels, T_ref]
         plan = self.prepare_segment(text, lang, ref_mel_raw, ref_text, speed, target_duration_s)
         ref_len, total = plan["ref_len"], plan["T_total"]

@@ -217,12 +217,12 @@ def test_logmel_vs_golden():
             wav = 0.5 * torch.sin(2 * torch.pi * 220 * torch.arange(S) / 24000)
         mel = ap.mel_spectrogram(wav.to(DEV))
         assert mel.shape == case["mel"].shape
-        # fp32 FFT round-off only matters where the mel energy is near the 1e-5 clip (pure sine): compare where
-        # the reference is above the floor, and bound the rest absolutely
+        # log-mel: relative L2; linear mel: absolute error relative to the loudest bin (fp32 FFT round-off is
+        # relative to the frame's peak, so near-silent bins of a pure tone only agree in the linear domain)
         ref = case["mel"]
         assert _rel(mel, ref) < 1e-3
-        loud = ref > -9.0
-        assert float((mel.cpu() - ref)[loud].abs().max()) < 5e-3
+        lin, lin_ref = mel.cpu().exp(), ref.exp()
+        assert float((lin - lin_ref).abs().max() / lin_ref.max()) < 1e-5
         if case["norm"] is not None:
             out = ap.normalize_audio((wav * 0.37).to(DEV))
             assert torch.allclose(out.cpu(), case["norm"], atol=1e-7)
