@@ -178,7 +178,12 @@ class Workspace:
         dev = w.device
         D, C, M = w.dim, w.text_dim, w.n_mels
         R, Rb = nbp * tpad, nb * tpad
-        z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
+
+        def z(*s, dt=F32):
+            # plain (non-inference) tensors: the workspace outlives the inference_mode block that creates it
+            with torch.inference_mode(False):
+                return torch.zeros(*s, device=dev, dtype=dt)
+
         self.nb, self.nbp, self.tpad, self.steps = nb, nbp, tpad, steps
         self.ids = z(R, dt=torch.int32)
         self.drop = z(nbp, dt=torch.uint8)
