@@ -103,6 +103,7 @@ typedef struct oron_gemm_desc {
   const uint8_t* row_valid;  /* [rows] or NULL */
   int32_t mask_rows;
   int32_t max_ctas;          /* 0 = one CTA per SM */
+  int32_t two_sm;            /* 1: 2-SM (cta_group::2) kernel, 256 x block_n tile per SM pair */
 } oron_gemm_desc;
 
 int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);

@@ -79,6 +79,7 @@ class GemmDesc(ctypes.Structure):
         ("row_valid", c_void_p),
         ("mask_rows", c_int32),
         ("max_ctas", c_int32),
+        ("two_sm", c_int32),
     ]
 
 
@@ -189,6 +190,7 @@ def gemm(
     row_valid: torch.Tensor | None = None,
     mask_rows: bool = False,
     max_ctas: int = 0,
+    two_sm: bool = False,
 ) -> None:
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16."""
     d = GemmDesc()
@@ -220,6 +222,7 @@ def gemm(
     d.row_valid = _ptr(row_valid, torch.uint8, "row_valid")
     d.mask_rows = int(bool(mask_rows))
     d.max_ctas = int(max_ctas)
+    d.two_sm = int(bool(two_sm))
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16
     if out.dtype != want:

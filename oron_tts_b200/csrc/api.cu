@@ -100,6 +100,27 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   return check_launch("gemm_bf16_tcgen05");
 }
 
+
+template <int BN, int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int max_ctas, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm2_bf16_tcgen05_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(int(e), "gemm2 smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles_m = ((a.rows_per_batch + GEMM_BM - 1) / GEMM_BM) * a.nbatch;
+  const int tiles = ((tiles_m + 1) / 2) * ((a.N + BN - 1) / BN);
+  int pairs = tiles;
+  const int cap = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
+  if (pairs > cap) pairs = cap;
+  if (pairs <= 0) return 0;
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, a);
+  return check_launch("gemm2_bf16_tcgen05");
+}
+
 extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   if (!d || !d->A || !d->W || !d->out) return fail(ORON_ERR_BAD_ARG, "gemm: null pointer");
   if (d->rows_per_batch <= 0 || d->nbatch <= 0 || d->N <= 0 || d->w_cols <= 0)
@@ -163,10 +184,26 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   int rc = make_tmap_bf16(&ta, d->A, uint64_t(d->a_cols), uint64_t(d->rows_per_batch), uint64_t(d->nbatch),
                           uint64_t(d->lda), uint64_t(d->lda) * uint64_t(d->rows_per_batch), GEMM_BM, 3);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, d->W, uint64_t(d->w_cols), uint64_t(d->N), 1, uint64_t(d->ldw), 0, uint32_t(d->block_n), 2);
+  const bool two_sm = d->two_sm != 0;
+  rc = make_tmap_bf16(&tb, d->W, uint64_t(d->w_cols), uint64_t(d->N), 1, uint64_t(d->ldw), 0,
+                      uint32_t(two_sm ? d->block_n / 2 : d->block_n), 2);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
+#define ORON_GEMM2_CASE(BN_, EPI_) \
+  if (two_sm && d->block_n == BN_ && epi == EPI_) return launch_gemm2<BN_, EPI_>(ta, tb, a, d->max_ctas, st);
+  ORON_GEMM2_CASE(128, EPI_BF16)
+  ORON_GEMM2_CASE(256, EPI_BF16)
+  ORON_GEMM2_CASE(128, EPI_F32)
+  ORON_GEMM2_CASE(256, EPI_F32)
+  ORON_GEMM2_CASE(128, EPI_QKV_ROPE)
+  ORON_GEMM2_CASE(256, EPI_QKV_ROPE)
+  ORON_GEMM2_CASE(128, EPI_GATE_RESID)
+  ORON_GEMM2_CASE(256, EPI_GATE_RESID)
+  ORON_GEMM2_CASE(128, EPI_EMBED_DUAL)
+  ORON_GEMM2_CASE(128, EPI_SCALE_RESID)
+#undef ORON_GEMM2_CASE
+  if (two_sm) return fail(ORON_ERR_UNSUPPORTED, "gemm: no 2-SM kernel for block_n=%d epilogue=%d", d->block_n, epi);
 #define ORON_GEMM_CASE(BN_, EPI_) \
   if (d->block_n == BN_ && epi == EPI_) return launch_gemm<BN_, EPI_>(ta, tb, a, d->max_ctas, st);
   ORON_GEMM_CASE(128, EPI_BF16)

@@ -215,6 +215,72 @@ def test_gemm_embed_dual_and_scale_resid(L):
     assert _rel(o, ref2) < 1e-4
 
 
+
+# ------------------------------------------------------------------------------------------
+# 2-SM (cta_group::2) GEMM: same contracts as the 1-SM kernel
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "nb,T,N,K,bn",
+    [(1, 256, 256, 128, 256), (2, 1408, 3072, 1024, 256), (2, 1408, 1024, 4096, 128), (1, 384, 1024, 1024, 128),
+     (3, 200, 1026, 512, 128), (1, 32, 4096, 1024, 256), (2, 1408, 4096, 1024, 256)],
+)
+def test_gemm_two_sm_plain(L, nb, T, N, K, bn):
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g)
+    ldo = (N + 7) // 8 * 8
+    out = torch.full((M, ldo), float("nan"), device=DEV, dtype=torch.bfloat16)
+    L.gemm(A, W, out, epilogue=L.EPI_BF16, bias=bias, block_n=bn, n=N, rows_per_batch=T, nbatch=nb, two_sm=True,
+           act=L.ACT_GELU_TANH)
+    ref = F.gelu(A.float() @ W.float().t() + bias, approximate="tanh")
+    assert torch.isfinite(out[:, :N].float()).all()
+    assert _rel(out[:, :N], ref) < 6e-3
+
+
+def test_gemm_two_sm_fused_epilogues(L):
+    nb, T, D, H = 2, 384, 1024, 16
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(13)
+    A = _bf(torch.randn(M, D, device=DEV, generator=g))
+    W = _bf(torch.randn(3 * D, D, device=DEV, generator=g) / math.sqrt(D))
+    bias = torch.randn(3 * D, device=DEV, generator=g) * 0.1
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=DEV).float() / 64))
+    ang = torch.outer(torch.arange(T, device=DEV).float(), inv_freq)
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    pre = (A.float() @ W.float().t() + bias).view(nb, T, 3, H, 64)
+    c = torch.cat([cos, cos], -1)[None, :, None, :]
+    s = torch.cat([sin, sin], -1)[None, :, None, :]
+    rot = lambda x: torch.cat([-x[..., 32:], x[..., :32]], -1)
+    q, k, v = pre[:, :, 0], pre[:, :, 1], pre[:, :, 2]
+    ref = torch.stack([q * c + rot(q) * s, k * c + rot(k) * s, v], 2).reshape(M, 3 * D)
+    for bn in (128, 256):
+        out = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+        L.gemm(A, W, out, epilogue=L.EPI_QKV_ROPE, bias=bias, rows_per_batch=T, nbatch=nb, block_n=bn, rope_cos=cos,
+               rope_sin=sin, rope_cols=2 * D, two_sm=True)
+        assert _rel(out, ref) < 6e-3, bn
+    # gated residual with row masking
+    Wo = _bf(torch.randn(D, D, device=DEV, generator=g) / math.sqrt(D))
+    bo = torch.randn(D, device=DEV, generator=g) * 0.1
+    gate = torch.randn(D, device=DEV, generator=g)
+    lens = torch.tensor([384, 100], device=DEV, dtype=torch.int32)
+    x0 = torch.randn(M, D, device=DEV, generator=g)
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).reshape(M, 1)
+    upd = gate * (A.float() @ Wo.float().t() + bo)
+    refx = x0 + torch.where(mask, upd, torch.zeros_like(upd))
+    for bn in (128, 256):
+        x = x0.clone()
+        L.gemm(A, Wo, x, epilogue=L.EPI_GATE_RESID, bias=bo, rows_per_batch=T, nbatch=nb, gate=gate, seq_lens=lens,
+               mask_rows=True, block_n=bn, two_sm=True)
+        assert _rel(x, refx) < 2e-3, bn
+    # f32 with ragged N and addend
+    Wp = _bf(torch.randn(100, D, device=DEV, generator=g) / math.sqrt(D))
+    bp = torch.randn(100, device=DEV, generator=g)
+    o = torch.full((M, 100), float("nan"), device=DEV)
+    L.gemm(A, Wp, o, epilogue=L.EPI_F32, bias=bp, rows_per_batch=T, nbatch=nb, block_n=128, two_sm=True)
+    assert _rel(o, A.float() @ Wp.float().t() + bp) < 1e-4
+
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,115 @@
+"""Micro-benchmarks of the hot kernels at BASELINE config-2 shapes (CUDA events, L2-warm and L2-cold).
+Usage: python tools/kernel_bench.py [gemm|attn|ln|all] [--ncu]   (--ncu: one launch per case, for profiling)"""
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from oron_tts_b200 import _lib as L
+
+DEV = "cuda"
+NCU = "--ncu" in sys.argv
+what = next((a for a in sys.argv[1:] if not a.startswith("--")), "all")
+R, D, T = 2816, 1024, 1408
+flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
+
+
+def timeit(fn, reps=20, cold=False):
+    if NCU:
+        fn()
+        torch.cuda.synchronize()
+        return float("nan")
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if cold:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm_cases():
+    g = torch.Generator(device=DEV).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    bias = {n: rnd(n) for n in (1024, 3072, 4096)}
+    A1 = rnd(R, 1024).bfloat16()
+    A4 = rnd(R, 4096).bfloat16()
+    W = {(n, k): (rnd(n, k) / math.sqrt(k)).bfloat16() for n, k in ((3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096))}
+    cos, sin = rnd(T, 32), rnd(T, 32)
+    gate = rnd(6 * 1024)
+    xres = rnd(R, 1024)
+    out = {n: torch.empty(R, n, device=DEV, dtype=torch.bfloat16) for n in (3072, 4096, 1024)}
+    cases = []
+    for bn in (128, 256):
+        cases.append((f"qkv_rope   N=3072 K=1024 bn={bn}", 2 * R * 3072 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(3072, 1024)], out[3072], epilogue=L.EPI_QKV_ROPE, bias=bias[3072], rows_per_batch=T,
+                                           nbatch=2, block_n=bn, rope_cos=cos, rope_sin=sin, rope_cols=2048)))
+        cases.append((f"plain bf16 N=3072 K=1024 bn={bn}", 2 * R * 3072 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(3072, 1024)], out[3072], epilogue=L.EPI_BF16, bias=bias[3072], rows_per_batch=T,
+                                           nbatch=2, block_n=bn)))
+        cases.append((f"ffn1 gelu  N=4096 K=1024 bn={bn}", 2 * R * 4096 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(4096, 1024)], out[4096], epilogue=L.EPI_BF16, bias=bias[4096], act=L.ACT_GELU_TANH,
+                                           rows_per_batch=T, nbatch=2, block_n=bn)))
+        cases.append((f"outproj    N=1024 K=1024 bn={bn}", 2 * R * 1024 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(1024, 1024)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                           rows_per_batch=T, nbatch=2, block_n=bn)))
+        cases.append((f"ffn2       N=1024 K=4096 bn={bn}", 2 * R * 1024 * 4096,
+                      lambda bn=bn: L.gemm(A4, W[(1024, 4096)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                           rows_per_batch=T, nbatch=2, block_n=bn)))
+    for bn in (128, 256):
+        cases.append((f"2SM qkv_rope   N=3072 K=1024 bn={bn}", 2 * R * 3072 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(3072, 1024)], out[3072], epilogue=L.EPI_QKV_ROPE, bias=bias[3072], rows_per_batch=T,
+                                           nbatch=2, block_n=bn, rope_cos=cos, rope_sin=sin, rope_cols=2048, two_sm=True)))
+        cases.append((f"2SM ffn1 gelu  N=4096 K=1024 bn={bn}", 2 * R * 4096 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(4096, 1024)], out[4096], epilogue=L.EPI_BF16, bias=bias[4096], act=L.ACT_GELU_TANH,
+                                           rows_per_batch=T, nbatch=2, block_n=bn, two_sm=True)))
+        cases.append((f"2SM outproj    N=1024 K=1024 bn={bn}", 2 * R * 1024 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(1024, 1024)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                           rows_per_batch=T, nbatch=2, block_n=bn, two_sm=True)))
+        cases.append((f"2SM ffn2       N=1024 K=4096 bn={bn}", 2 * R * 1024 * 4096,
+                      lambda bn=bn: L.gemm(A4, W[(1024, 4096)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                           rows_per_batch=T, nbatch=2, block_n=bn, two_sm=True)))
+    cases.append(("outproj    N=1024 K=1024 bn=64", 2 * R * 1024 * 1024,
+                  lambda: L.gemm(A1, W[(1024, 1024)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                 rows_per_batch=T, nbatch=2, block_n=64)))
+    cases.append(("ffn2       N=1024 K=4096 bn=64", 2 * R * 1024 * 4096,
+                  lambda: L.gemm(A4, W[(1024, 4096)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                 rows_per_batch=T, nbatch=2, block_n=64)))
+    return cases
+
+
+def run(cases):
+    for name, flops, fn in cases:
+        w, c = timeit(fn), timeit(fn, cold=True)
+        print(f"{name:40s} warm {w:8.1f} us {flops / w / 1e6:8.1f} TFLOP/s | cold {c:8.1f} us {flops / c / 1e6:8.1f} TFLOP/s", flush=True)
+
+
+if what in ("gemm", "all"):
+    run(gemm_cases())
+if what in ("attn", "all"):
+    g = torch.Generator(device=DEV).manual_seed(1)
+    qkv = torch.randn(R, 3072, device=DEV, generator=g).bfloat16()
+    o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
+    lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
+    run([("attention T=1406 H=16 nb=2", 4 * 2 * 16 * 1406 * 1406 * 64,
+          lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125))])
+if what in ("ln", "all"):
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(R, 1024, device=DEV, generator=g)
+    tab = torch.randn(6 * 1024, device=DEV, generator=g)
+    o = torch.empty(R, 1024, device=DEV, dtype=torch.bfloat16)
+    fn = lambda: L.ln_modulate(x, rows_per_batch=T, nbatch=2, eps=1e-6, scale=tab[1024:], shift=tab, add_one=True, out_bf16=o)
+    w, c = timeit(fn), timeit(fn, cold=True)
+    byt = R * 1024 * 6
+    print(f"ln_modulate R=2816 C=1024: warm {w:.1f} us ({byt / w / 1e3:.0f} GB/s) cold {c:.1f} us ({byt / c / 1e3:.0f} GB/s)")
