@@ -104,6 +104,7 @@ typedef struct oron_gemm_desc {
   int32_t mask_rows;
   int32_t max_ctas;          /* 0 = one CTA per SM */
   int32_t two_sm;            /* 1: 2-SM (cta_group::2) kernel, 256 x block_n tile per SM pair */
+  void* debug_stamps;        /* NULL, or int64 [grid, 16] device buffer for per-CTA clock64 stamps (profiling aid) */
 } oron_gemm_desc;
 
 int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);

@@ -80,6 +80,7 @@ class GemmDesc(ctypes.Structure):
         ("mask_rows", c_int32),
         ("max_ctas", c_int32),
         ("two_sm", c_int32),
+        ("debug_stamps", c_void_p),
     ]
 
 
@@ -191,6 +192,7 @@ def gemm(
     mask_rows: bool = False,
     max_ctas: int = 0,
     two_sm: bool = False,
+    debug_stamps: torch.Tensor | None = None,
 ) -> None:
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16."""
     d = GemmDesc()
@@ -223,6 +225,7 @@ def gemm(
     d.mask_rows = int(bool(mask_rows))
     d.max_ctas = int(max_ctas)
     d.two_sm = int(bool(two_sm))
+    d.debug_stamps = _ptr(debug_stamps, torch.int64, "debug_stamps")
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16
     if out.dtype != want:

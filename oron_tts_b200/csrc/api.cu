@@ -165,6 +165,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   a.seq_lens = d->seq_lens;
   a.row_valid = d->row_valid;
   a.mask_rows = d->mask_rows;
+  a.dbg = reinterpret_cast<long long*>(d->debug_stamps);
 
   const int epi = d->epilogue;
   // per-epilogue operand checks (vectorised epilogues assume 32-column granularity)

@@ -56,85 +56,152 @@ struct GemmArgs {
   const int* seq_lens;         // [nbatch] valid rows per batch element or nullptr (all valid)
   const unsigned char* row_valid;  // [rows] explicit per-row validity (overrides seq_lens) or nullptr
   int mask_rows;               // EPI_GATE_RESID: skip rows t >= seq_len
+  long long* dbg;              // optional [grid, 16] clock64 stamps (tools/kernel_bench.py --trace); nullptr in production
 };
+
+#define ORON_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each owning half of the BN columns
 
+constexpr int EPI_STAGE_LD = 36;                                  // floats per staged row (pad -> conflict-free v4)
+constexpr int EPI_STAGE_BYTES_PER_WARP = 32 * EPI_STAGE_LD * 4;   // 4608
+constexpr int EPI_STAGE_BYTES = GEMM_EPI_WARPS * EPI_STAGE_BYTES_PER_WARP;
+
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 };
 
-// Drains columns [cbeg, cbeg + HN) of one 128-row accumulator tile (TMEM address `trow` = this warp's lane
-// quarter, column 0 of the tile) through the fused epilogue. Thread = one output row t of batch element b.
+// ---------------------------------------------------------------------------------------------------
+// Epilogue. tcgen05.ld hands every thread one accumulator ROW (TMEM lane == row), so writing straight from
+// those registers makes each warp-wide global access touch 32 different cache lines (measured: 7.7k-21k
+// cycles per 128x256 tile, the dominant cost of the v1 kernel — profiles/r01_gemm_trace_v1.txt). Each
+// epilogue warp therefore transposes 32x32 fp32 blocks through a private, padded smem staging buffer and
+// runs the fused op in the "coalesced domain": lane l owns columns 4*(l&7)..+3 of row 4*it + (l>>3), so every
+// global load/store of the warp covers 4 rows x 128 contiguous bytes.
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void stage_store_row(uint32_t stage, int lane, const uint32_t (&r)[32]) {
+  const uint32_t base = stage + uint32_t(lane) * (EPI_STAGE_LD * 4);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + 16u * j), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                 "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                 : "memory");
+}
+__device__ __forceinline__ float4 stage_load4(uint32_t stage, int row, int c4) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(stage + uint32_t(row * EPI_STAGE_LD + c4) * 4u)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldg4_guard(const float* p, int col, int n) {
+  // p points at column `col`; columns >= n read as 0
+  if (col + 4 <= n) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < n) v.x = __ldg(p);
+  if (col + 1 < n) v.y = __ldg(p + 1);
+  if (col + 2 < n) v.z = __ldg(p + 2);
+  return v;
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v, int col, int n) {
+  if (col + 4 <= n) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    if (col < n) p[0] = __float2bfloat16(v.x);
+    if (col + 1 < n) p[1] = __float2bfloat16(v.y);
+    if (col + 2 < n) p[2] = __float2bfloat16(v.z);
+  }
+}
+__device__ __forceinline__ void st_f32x4(float* p, float4 v, int col, int n) {
+  if (col + 4 <= n) {
+    *reinterpret_cast<float4*>(p) = v;
+  } else {
+    if (col < n) p[0] = v.x;
+    if (col + 1 < n) p[1] = v.y;
+    if (col + 2 < n) p[2] = v.z;
+  }
+}
+template <typename F>
+__device__ __forceinline__ float4 map4(float4 v, F f) {
+  return make_float4(f(v.x), f(v.y), f(v.z), f(v.w));
+}
+
+// Drains columns [cbeg, cbeg + HN) of one 128-row accumulator tile. `trow`: TMEM address of this warp's lane
+// quarter at column 0 of the tile; `t_base`: row (inside batch element b) of the warp's first lane, or
+// >= rows_per_batch for a phantom tile; `stage`: this warp's staging buffer (shared-window address).
 template <int BN, int EPI, int HN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const uint32_t trow, const int b,
-                                                   const int t, const int n0, const int cbeg) {
-  const bool in_range = t < args.rows_per_batch;
+                                                   const int t_base, const int n0, const int cbeg,
+                                                   const uint32_t stage, const int lane) {
+  const int rsub = lane >> 3;        // row inside a 4-row group
+  const int c4 = (lane & 7) * 4;     // first of the 4 columns this lane owns inside a 32-column chunk
   const int seq_len = args.seq_lens ? args.seq_lens[b] : args.rows_per_batch;
-  const long long grow = (long long)b * args.rows_per_batch + t;
-  bool valid = in_range && (t < seq_len);
-  if (args.row_valid != nullptr) valid = in_range && (args.row_valid[in_range ? grow : 0] != 0);
+  const long long row0 = (long long)b * args.rows_per_batch + t_base;
+  const int N = args.N;
 
   if constexpr (EPI == EPI_QKV_ROPE) {
-    // BN is a multiple of 64: each 64-column group is one head.
-    float cs[32], sn[32];
-    if (in_range) {
-      const float4* c4 = reinterpret_cast<const float4*>(args.rope_cos + (long long)t * 32);
-      const float4* s4 = reinterpret_cast<const float4*>(args.rope_sin + (long long)t * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
-        cs[4 * i] = c.x; cs[4 * i + 1] = c.y; cs[4 * i + 2] = c.z; cs[4 * i + 3] = c.w;
-        sn[4 * i] = s.x; sn[4 * i + 1] = s.y; sn[4 * i + 2] = s.z; sn[4 * i + 3] = s.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { cs[i] = 1.f; sn[i] = 0.f; }
-    }
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo;
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + HN; c0 += 64) {
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32(trow + c0, ra);
-      tmem_ld_32x32(trow + c0 + 32, rb);
+    for (int c0 = cbeg; c0 < cbeg + HN; c0 += 64) {   // one 64-wide head at a time
+      uint32_t r[32];
+      const int col = n0 + c0 + c4;                     // this lane's columns in the first half of the head
+      const bool live = (n0 + c0) < N;                  // warp-uniform
+      tmem_ld_32x32(trow + c0, r);
       tmem_wait_ld();
-      const int col = n0 + c0;
-      if (in_range && col < args.N) {
-        const bool rot = col < args.rope_cols;
-        uint32_t pa[16], pb[16];
+      float4 xa[8];
+      if (live) {
+        stage_store_row(stage, lane, r);
+        __syncwarp();
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col));
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float x1a = __uint_as_float(ra[i]) + __ldg(args.bias + col + i);
-          float x1b = __uint_as_float(ra[i + 1]) + __ldg(args.bias + col + i + 1);
-          float x2a = __uint_as_float(rb[i]) + __ldg(args.bias + col + 32 + i);
-          float x2b = __uint_as_float(rb[i + 1]) + __ldg(args.bias + col + 32 + i + 1);
-          if (rot) {
-            // rotate_half: out[i] = x[i] cos - x[i+32] sin ; out[i+32] = x[i+32] cos + x[i] sin
-            const float o1a = x1a * cs[i] - x2a * sn[i];
-            const float o2a = x2a * cs[i] + x1a * sn[i];
-            const float o1b = x1b * cs[i + 1] - x2b * sn[i + 1];
-            const float o2b = x2b * cs[i + 1] + x1b * sn[i + 1];
-            x1a = o1a; x2a = o2a; x1b = o1b; x2b = o2b;
-          }
-          pa[i / 2] = pack_bf16x2(x1a, x1b);
-          pb[i / 2] = pack_bf16x2(x2a, x2b);
+        for (int it = 0; it < 8; ++it) {
+          const float4 v = stage_load4(stage, 4 * it + rsub, c4);
+          xa[it] = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
         }
-        uint4* o4 = reinterpret_cast<uint4*>(out + col);
+        __syncwarp();
+      }
+      tmem_ld_32x32(trow + c0 + 32, r);
+      tmem_wait_ld();
+      if (live) {
+        stage_store_row(stage, lane, r);
+        __syncwarp();
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col + 32));
+        const bool rot = (n0 + c0) < args.rope_cols;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o4[i] = make_uint4(pa[4 * i], pa[4 * i + 1], pa[4 * i + 2], pa[4 * i + 3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o4[4 + i] = make_uint4(pb[4 * i], pb[4 * i + 1], pb[4 * i + 2], pb[4 * i + 3]);
+        for (int it = 0; it < 8; ++it) {
+          const int rr = 4 * it + rsub;
+          const int t = t_base + rr;
+          const float4 v = stage_load4(stage, rr, c4);
+          float4 x1 = xa[it];
+          float4 x2 = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+          if (t < args.rows_per_batch) {
+            if (rot) {
+              // rotate_half: out[i] = x[i] cos - x[i+32] sin ; out[i+32] = x[i+32] cos + x[i] sin
+              const float4 c = __ldg(reinterpret_cast<const float4*>(args.rope_cos + (long long)t * 32 + c4));
+              const float4 s = __ldg(reinterpret_cast<const float4*>(args.rope_sin + (long long)t * 32 + c4));
+              const float4 o1 = make_float4(x1.x * c.x - x2.x * s.x, x1.y * c.y - x2.y * s.y, x1.z * c.z - x2.z * s.z,
+                                            x1.w * c.w - x2.w * s.w);
+              const float4 o2 = make_float4(x2.x * c.x + x1.x * s.x, x2.y * c.y + x1.y * s.y, x2.z * c.z + x1.z * s.z,
+                                            x2.w * c.w + x1.w * s.w);
+              x1 = o1; x2 = o2;
+            }
+            __nv_bfloat16* o = out + (row0 + rr) * args.ldo + col;
+            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x1.x, x1.y), pack_bf16x2(x1.z, x1.w));
+            *reinterpret_cast<uint2*>(o + 32) = make_uint2(pack_bf16x2(x2.x, x2.y), pack_bf16x2(x2.z, x2.w));
+          }
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -143,133 +210,72 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
       uint32_t r[32];
       tmem_ld_32x32(trow + c0, r);
       tmem_wait_ld();
-      const int col = n0 + c0;
-      if (!in_range || col >= args.N) continue;
-      const bool full = (col + 32 <= args.N);
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float bv = 0.f;
-        if (args.bias != nullptr && (full || col + i < args.N)) bv = __ldg(args.bias + col + i);
-        v[i] = __uint_as_float(r[i]) + bv;
-      }
-
-      if constexpr (EPI == EPI_BF16) {
-        if (args.act == ACT_GELU_TANH) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_f(v[i]);
-        } else if (args.act == ACT_GELU_ERF) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
-        } else if (args.act == ACT_SILU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-        }
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col;
-        if (full) {
-          uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                               pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col + i < args.N) o[i] = __float2bfloat16(v[i]);
-        }
-      } else if constexpr (EPI == EPI_F32) {
-        float* o = reinterpret_cast<float*>(args.out) + grow * args.ldo + col;
-        const float* ad = args.addend ? args.addend + grow * args.ld_add + col : nullptr;
-        if (full) {
-          float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 w = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            if (ad) {
-              const float4 a = *reinterpret_cast<const float4*>(ad + 4 * i);
-              w.x += a.x; w.y += a.y; w.z += a.z; w.w += a.w;
-            }
-            o4[i] = w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col + i < args.N) o[i] = v[i] + (ad ? ad[i] : 0.f);
-        }
-      } else if constexpr (EPI == EPI_GATE_RESID) {
-        if (args.mask_rows && !valid) continue;
-        float* o = reinterpret_cast<float*>(args.out) + grow * args.ldo + col;
+      if (n0 + c0 >= N) continue;  // warp-uniform
+      stage_store_row(stage, lane, r);
+      __syncwarp();
+      const int col = n0 + c0 + c4;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (args.bias != nullptr) b4 = ldg4_guard(args.bias + col, col, N);
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if constexpr (EPI == EPI_GATE_RESID) {
         const long long step = args.step_ptr ? (long long)__ldg(args.step_ptr) : 0ll;
-        const float* g = args.gate + step * args.gate_step_stride +
-                         (long long)(b % args.gate_nb) * args.gate_ld + col;
-        float4* o4 = reinterpret_cast<float4*>(o);
-        const float4* g4 = reinterpret_cast<const float4*>(g);
+        g4 = __ldg(reinterpret_cast<const float4*>(args.gate + step * args.gate_step_stride +
+                                                   (long long)(b % args.gate_nb) * args.gate_ld + col));
+      }
+      if constexpr (EPI == EPI_SCALE_RESID) {
+        if (args.gate != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(args.gate + col));
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 x = o4[i];
-          const float4 gg = __ldg(g4 + i);
-          x.x += gg.x * v[4 * i]; x.y += gg.y * v[4 * i + 1];
-          x.z += gg.z * v[4 * i + 2]; x.w += gg.w * v[4 * i + 3];
-          o4[i] = x;
-        }
-      } else if constexpr (EPI == EPI_EMBED_DUAL) {
-        float* o = reinterpret_cast<float*>(args.out) + grow * args.ldo + col;
-        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col;
-        const float* ad = args.addend + grow * args.ld_add + col;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 a = *reinterpret_cast<const float4*>(ad + 4 * i);
-          v[4 * i] = valid ? v[4 * i] + a.x : 0.f;
-          v[4 * i + 1] = valid ? v[4 * i + 1] + a.y : 0.f;
-          v[4 * i + 2] = valid ? v[4 * i + 2] + a.z : 0.f;
-          v[4 * i + 3] = valid ? v[4 * i + 3] + a.w : 0.f;
-          reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        uint4* o4 = reinterpret_cast<uint4*>(o2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-      } else if constexpr (EPI == EPI_MISH_MASK_BF16) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = valid ? mish_f(v[i]) : 0.f;
-        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-      } else if constexpr (EPI == EPI_MISH_MASK_RESID) {
-        float* o = reinterpret_cast<float*>(args.out) + grow * args.ldo + col;
-        const float* ad = args.addend + grow * args.ld_add + col;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 a = *reinterpret_cast<const float4*>(ad + 4 * i);
-          float4 w;
-          w.x = (valid ? mish_f(v[4 * i]) : 0.f) + a.x;
-          w.y = (valid ? mish_f(v[4 * i + 1]) : 0.f) + a.y;
-          w.z = (valid ? mish_f(v[4 * i + 2]) : 0.f) + a.z;
-          w.w = (valid ? mish_f(v[4 * i + 3]) : 0.f) + a.w;
-          reinterpret_cast<float4*>(o)[i] = w;
-        }
-      } else if constexpr (EPI == EPI_SCALE_RESID) {
-        float* o = reinterpret_cast<float*>(args.out) + grow * args.ldo + col;
-        const float* ad = args.addend + grow * args.ld_add + col;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sc = args.gate ? __ldg(args.gate + col + i) : 1.f;
-          v[i] = valid ? ad[i] + sc * v[i] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        if (args.out2 != nullptr) {
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                               pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+      for (int it = 0; it < 8; ++it) {
+        const int rr = 4 * it + rsub;
+        const int t = t_base + rr;
+        if (t >= args.rows_per_batch) continue;
+        const long long grow = row0 + rr;
+        bool valid = t < seq_len;
+        if (args.row_valid != nullptr) valid = args.row_valid[grow] != 0;
+        float4 v = stage_load4(stage, rr, c4);
+        v = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+
+        if constexpr (EPI == EPI_BF16) {
+          if (args.act == ACT_GELU_TANH) v = map4(v, gelu_tanh_f);
+          else if (args.act == ACT_GELU_ERF) v = map4(v, gelu_erf_f);
+          else if (args.act == ACT_SILU) v = map4(v, silu_f);
+          st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
+        } else if constexpr (EPI == EPI_F32) {
+          if (args.addend != nullptr) {
+            const float4 a = ldg4_guard(args.addend + grow * args.ld_add + col, col, N);
+            v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+          }
+          st_f32x4(reinterpret_cast<float*>(args.out) + grow * args.ldo + col, v, col, N);
+        } else if constexpr (EPI == EPI_GATE_RESID) {
+          if (args.mask_rows && !valid) continue;
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col);
+          float4 x = *o;
+          x.x += g4.x * v.x; x.y += g4.y * v.y; x.z += g4.z * v.z; x.w += g4.w * v.w;
+          *o = x;
+        } else if constexpr (EPI == EPI_EMBED_DUAL) {
+          const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+          v = valid ? make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = v;
+          st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col, v, col, N);
+        } else if constexpr (EPI == EPI_MISH_MASK_BF16) {
+          v = valid ? map4(v, mish_f) : make_float4(0.f, 0.f, 0.f, 0.f);
+          st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
+        } else if constexpr (EPI == EPI_MISH_MASK_RESID) {
+          const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+          v = valid ? map4(v, mish_f) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) =
+              make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+        } else if constexpr (EPI == EPI_SCALE_RESID) {
+          const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+          v = valid ? make_float4(a.x + g4.x * v.x, a.y + g4.y * v.y, a.z + g4.z * v.z, a.w + g4.w * v.w)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = v;
+          if (args.out2 != nullptr)
+            st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col, v, col, N);
         }
       }
+      __syncwarp();
     }
   }
 }
@@ -389,7 +395,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int m_tile = tile % tiles_m;
       const int n_tile = tile / tiles_m;
       const int b = m_tile / tiles_m_pb;
-      const int t = (m_tile % tiles_m_pb) * GEMM_BM + q * 32 + lane;  // row inside the batch element
+      const int t_base = (m_tile % tiles_m_pb) * GEMM_BM + q * 32;  // first row of this warp inside the batch element
       const int n0 = n_tile * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
@@ -397,7 +403,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_after();
 
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t, n0, cbeg);
+      gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t_base, n0, cbeg,
+                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane);
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -429,9 +436,9 @@ struct Gemm2Cfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? 5 : 7;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + EPI_STAGE_BYTES;
 };
 
 template <int BN, int EPI>
@@ -485,6 +492,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) ORON_STAMP(0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -505,6 +513,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const int a_row = t0 + kb / args.cpb - args.pad;
           tma_load_3d_2sm(sa, &tmA, full_bar(stage), a_col, a_row, b);
           tma_load_2d_2sm(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0 + rank * (BN / 2));
+          if (kb == 0 && tile == pair_id) ORON_STAMP(1);
+          if (kb == num_kb - 1 && tile == pair_id) ORON_STAMP(2);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -524,6 +534,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 23);
           tc_fence_after();
+          if (kb == 0 && it == 0) ORON_STAMP(3);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
@@ -532,7 +543,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int k = 0; k < GEMM_BK / 16; ++k)
             umma_bf16_ss_2sm(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(empty_bar(stage), 3);
-          if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(as), 3);
+          if (kb == num_kb - 1) { umma_commit_2sm(tfull_bar(as), 3); if (it < 2) ORON_STAMP(4 + it); }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -550,19 +561,23 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const uint32_t aphase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(as), aphase, 24);
       tc_fence_after();
+      if (threadIdx.x == 64 && it < 2) ORON_STAMP(6 + 2 * it);
       const int b = m_tile < tiles_m ? m_tile / tiles_m_pb : 0;
       // phantom tile: push the row index out of range so nothing is stored
-      const int t = m_tile < tiles_m ? (m_tile % tiles_m_pb) * GEMM_BM + q * 32 + lane : args.rows_per_batch;
+      const int t_base = m_tile < tiles_m ? (m_tile % tiles_m_pb) * GEMM_BM + q * 32 : args.rows_per_batch;
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t, n_tile * BN, cbeg);
+      gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t_base, n_tile * BN, cbeg,
+                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+      if (threadIdx.x == 64 && it < 2) ORON_STAMP(7 + 2 * it);
     }
   }
 
   tc_fence_before();
   cluster_sync_all();
+  if (threadIdx.x == 0) ORON_STAMP(10);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
