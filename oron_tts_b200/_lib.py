@@ -14,7 +14,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_uint
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboron_b200.so")
+LIB_PATH = os.environ.get("ORON_LIB_PATH") or os.path.join(_HERE, "liboron_b200.so")
 
 # ---- enums (include/oron_b200.h) -------------------------------------------------------------
 EPI_BF16, EPI_F32, EPI_QKV_ROPE, EPI_GATE_RESID = 0, 1, 2, 3

@@ -99,6 +99,9 @@ __device__ __forceinline__ void stage_store_row(uint32_t stage, int lane, const 
 }
 __device__ __forceinline__ float4 stage_load4(uint32_t stage, int row, int c4) {
   float4 v;
+#ifdef ORON_EXP_NOLDS
+  return make_float4(float(row), float(c4), 1.f, 2.f);
+#endif
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "r"(stage + uint32_t(row * EPI_STAGE_LD + c4) * 4u)
@@ -115,6 +118,9 @@ __device__ __forceinline__ float4 ldg4_guard(const float* p, int col, int n) {
   return v;
 }
 __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v, int col, int n) {
+#ifdef ORON_EXP_NOSTORE
+  if (v.x != 123456.789f) return;
+#endif
   if (col + 4 <= n) {
     *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   } else {
@@ -137,22 +143,188 @@ __device__ __forceinline__ float4 map4(float4 v, F f) {
   return make_float4(f(v.x), f(v.y), f(v.z), f(v.w));
 }
 
+template <int ACT>
+__device__ __forceinline__ float4 act4(float4 v) {
+  if constexpr (ACT == ACT_GELU_TANH) return map4(v, gelu_tanh_f);
+  if constexpr (ACT == ACT_GELU_ERF) return map4(v, gelu_erf_f);
+  if constexpr (ACT == ACT_SILU) return map4(v, silu_f);
+  return v;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 fma4(float4 g, float4 v, float4 a) {
+  return make_float4(fmaf(g.x, v.x, a.x), fmaf(g.y, v.y, a.y), fmaf(g.z, v.z, a.z), fmaf(g.w, v.w, a.w));
+}
+__device__ __forceinline__ uint2 pack4(float4 v) { return make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
+
+// Fast path of one staged 32x32 block: every row and column of the block is in range, so the 8 row-groups are
+// loaded up front (ILP) and written with unguarded vector accesses. The epilogue is instruction-latency bound
+// (2 warps per scheduler), so straight-line code with independent chains matters more than instruction count.
+template <int EPI, int ACT>
+__device__ __forceinline__ void epi_block_fast(const GemmArgs& args, const float* sp /*stage + rsub*LD + c4*/,
+                                               const long long grow0 /*row0 + rsub*/, const int col, const float4 b4,
+                                               const float4 g4, const int t0 /*t_base + rsub*/, const int seq_len) {
+  float4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) v[it] = add4(*reinterpret_cast<const float4*>(sp + it * 4 * EPI_STAGE_LD), b4);
+  if constexpr (EPI == EPI_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow0 * args.ldo + col;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) = pack4(act4<ACT>(v[it]));
+  } else if constexpr (EPI == EPI_F32) {
+    float* o = reinterpret_cast<float*>(args.out) + grow0 * args.ldo + col;
+    if (args.addend != nullptr) {
+      const float* a = args.addend + grow0 * args.ld_add + col;
+      float4 x[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) x[it] = __ldg(reinterpret_cast<const float4*>(a + (long long)it * 4 * args.ld_add));
+#pragma unroll
+      for (int it = 0; it < 8; ++it) v[it] = add4(v[it], x[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = v[it];
+  } else if constexpr (EPI == EPI_GATE_RESID) {
+    float* o = reinterpret_cast<float*>(args.out) + grow0 * args.ldo + col;
+    float4 x[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(o + (long long)it * 4 * args.ldo);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if (args.mask_rows && (t0 + 4 * it >= seq_len)) continue;
+      *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = fma4(g4, v[it], x[it]);
+    }
+  } else {
+    // epilogues with an addend and a validity mask
+    const float* a = args.addend + grow0 * args.ld_add + col;
+    float4 x[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(a + (long long)it * 4 * args.ld_add);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const long long grow = grow0 + 4 * it;
+      bool valid = (t0 + 4 * it) < seq_len;
+      if (args.row_valid != nullptr) valid = args.row_valid[grow] != 0;
+      float4 w;
+      if constexpr (EPI == EPI_EMBED_DUAL) {
+        w = valid ? add4(v[it], x[it]) : zero;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = w;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col) = pack4(w);
+      } else if constexpr (EPI == EPI_MISH_MASK_BF16) {
+        w = valid ? map4(v[it], mish_f) : zero;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col) = pack4(w);
+      } else if constexpr (EPI == EPI_MISH_MASK_RESID) {
+        w = add4(valid ? map4(v[it], mish_f) : zero, x[it]);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = w;
+      } else if constexpr (EPI == EPI_SCALE_RESID) {
+        w = valid ? fma4(g4, v[it], x[it]) : zero;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = w;
+        if (args.out2 != nullptr)
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col) = pack4(w);
+      }
+    }
+  }
+}
+
+// Guarded path (ragged rows / columns): one row-group at a time with per-element bounds checks.
+template <int EPI>
+__device__ __forceinline__ void epi_block_slow(const GemmArgs& args, const uint32_t stage, const int rsub, const int c4,
+                                               const long long row0, const int t_base, const int col, const float4 b4,
+                                               const float4 g4, const int seq_len) {
+  const int N = args.N;
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int rr = 4 * it + rsub;
+    const int t = t_base + rr;
+    if (t >= args.rows_per_batch) continue;
+    const long long grow = row0 + rr;
+    bool valid = t < seq_len;
+    if (args.row_valid != nullptr) valid = args.row_valid[grow] != 0;
+    float4 v = add4(stage_load4(stage, rr, c4), b4);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (EPI == EPI_BF16) {
+      if (args.act == ACT_GELU_TANH) v = map4(v, gelu_tanh_f);
+      else if (args.act == ACT_GELU_ERF) v = map4(v, gelu_erf_f);
+      else if (args.act == ACT_SILU) v = map4(v, silu_f);
+      st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
+    } else if constexpr (EPI == EPI_F32) {
+      if (args.addend != nullptr) v = add4(v, ldg4_guard(args.addend + grow * args.ld_add + col, col, N));
+      st_f32x4(reinterpret_cast<float*>(args.out) + grow * args.ldo + col, v, col, N);
+    } else if constexpr (EPI == EPI_GATE_RESID) {
+      if (args.mask_rows && !valid) continue;
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col);
+      *o = fma4(g4, v, *o);
+    } else if constexpr (EPI == EPI_EMBED_DUAL) {
+      const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+      v = valid ? add4(v, a) : zero;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = v;
+      st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col, v, col, N);
+    } else if constexpr (EPI == EPI_MISH_MASK_BF16) {
+      v = valid ? map4(v, mish_f) : zero;
+      st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
+    } else if constexpr (EPI == EPI_MISH_MASK_RESID) {
+      const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+      v = valid ? map4(v, mish_f) : zero;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = add4(v, a);
+    } else if constexpr (EPI == EPI_SCALE_RESID) {
+      const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+      v = valid ? fma4(g4, v, a) : zero;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = v;
+      if (args.out2 != nullptr) st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col, v, col, N);
+    }
+  }
+}
+
 // Drains columns [cbeg, cbeg + HN) of one 128-row accumulator tile. `trow`: TMEM address of this warp's lane
 // quarter at column 0 of the tile; `t_base`: row (inside batch element b) of the warp's first lane, or
 // >= rows_per_batch for a phantom tile; `stage`: this warp's staging buffer (shared-window address).
+// Per-column operands (bias, gate / column scale) are fetched for the whole column range BEFORE the caller's
+// accumulator-ready wait would expose their latency: see gemm_epilogue_prefetch.
+template <int HN>
+struct EpiCols {
+  float4 b4[HN / 32];
+  float4 g4[HN / 32];
+};
+
+template <int BN, int EPI, int HN>
+__device__ __forceinline__ void gemm_epilogue_prefetch(const GemmArgs& args, const int b, const int n0, const int cbeg,
+                                                       const int lane, EpiCols<HN>& pc) {
+  const int c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int j = 0; j < HN / 32; ++j) {
+    const int col = n0 + cbeg + 32 * j + c4;
+    pc.b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pc.g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (col < args.N) {
+      if (args.bias != nullptr) pc.b4[j] = ldg4_guard(args.bias + col, col, args.N);
+      if constexpr (EPI == EPI_GATE_RESID) {
+        const long long step = args.step_ptr ? (long long)__ldg(args.step_ptr) : 0ll;
+        pc.g4[j] = __ldg(reinterpret_cast<const float4*>(args.gate + step * args.gate_step_stride +
+                                                        (long long)(b % args.gate_nb) * args.gate_ld + col));
+      }
+      if constexpr (EPI == EPI_SCALE_RESID) {
+        if (args.gate != nullptr) pc.g4[j] = __ldg(reinterpret_cast<const float4*>(args.gate + col));
+      }
+    }
+  }
+}
+
 template <int BN, int EPI, int HN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const uint32_t trow, const int b,
                                                    const int t_base, const int n0, const int cbeg,
-                                                   const uint32_t stage, const int lane) {
+                                                   const uint32_t stage, const int lane, const EpiCols<HN>& pc) {
   const int rsub = lane >> 3;        // row inside a 4-row group
   const int c4 = (lane & 7) * 4;     // first of the 4 columns this lane owns inside a 32-column chunk
   const int seq_len = args.seq_lens ? args.seq_lens[b] : args.rows_per_batch;
   const long long row0 = (long long)b * args.rows_per_batch + t_base;
   const int N = args.N;
+  const bool rows_full = t_base + 32 <= args.rows_per_batch;  // warp-uniform
+  const float* sp = reinterpret_cast<const float*>(__cvta_shared_to_generic(stage)) + rsub * EPI_STAGE_LD + c4;
 
   if constexpr (EPI == EPI_QKV_ROPE) {
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + HN; c0 += 64) {   // one 64-wide head at a time
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out);
+#pragma unroll
+    for (int j = 0; j < HN / 64; ++j) {   // one 64-wide head at a time
+      const int c0 = cbeg + 64 * j;
       uint32_t r[32];
       const int col = n0 + c0 + c4;                     // this lane's columns in the first half of the head
       const bool live = (n0 + c0) < N;                  // warp-uniform
@@ -162,12 +334,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
       if (live) {
         stage_store_row(stage, lane, r);
         __syncwarp();
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col));
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float4 v = stage_load4(stage, 4 * it + rsub, c4);
-          xa[it] = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
-        }
+        for (int it = 0; it < 8; ++it) xa[it] = add4(*reinterpret_cast<const float4*>(sp + it * 4 * EPI_STAGE_LD), pc.b4[2 * j]);
         __syncwarp();
       }
       tmem_ld_32x32(trow + c0 + 32, r);
@@ -175,38 +343,45 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
       if (live) {
         stage_store_row(stage, lane, r);
         __syncwarp();
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col + 32));
         const bool rot = (n0 + c0) < args.rope_cols;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(args.out);
+        float4 xb[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) xb[it] = add4(*reinterpret_cast<const float4*>(sp + it * 4 * EPI_STAGE_LD), pc.b4[2 * j + 1]);
+        if (rot) {
+          // rotate_half: out[i] = x[i] cos - x[i+32] sin ; out[i+32] = x[i+32] cos + x[i] sin
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {   // two batches of 4 row-groups keep the cos/sin registers bounded
+            float4 cs[4], sn[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = min(t_base + 4 * (4 * h + i) + rsub, args.rows_per_batch - 1);
+              cs[i] = __ldg(reinterpret_cast<const float4*>(args.rope_cos + (long long)t * 32 + c4));
+              sn[i] = __ldg(reinterpret_cast<const float4*>(args.rope_sin + (long long)t * 32 + c4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int it = 4 * h + i;
+              const float4 x1 = xa[it], x2 = xb[it], c = cs[i], s_ = sn[i];
+              xa[it] = make_float4(x1.x * c.x - x2.x * s_.x, x1.y * c.y - x2.y * s_.y, x1.z * c.z - x2.z * s_.z, x1.w * c.w - x2.w * s_.w);
+              xb[it] = make_float4(x2.x * c.x + x1.x * s_.x, x2.y * c.y + x1.y * s_.y, x2.z * c.z + x1.z * s_.z, x2.w * c.w + x1.w * s_.w);
+            }
+          }
+        }
+        __nv_bfloat16* o = out + (row0 + rsub) * args.ldo + col;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int rr = 4 * it + rsub;
-          const int t = t_base + rr;
-          const float4 v = stage_load4(stage, rr, c4);
-          float4 x1 = xa[it];
-          float4 x2 = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
-          if (t < args.rows_per_batch) {
-            if (rot) {
-              // rotate_half: out[i] = x[i] cos - x[i+32] sin ; out[i+32] = x[i+32] cos + x[i] sin
-              const float4 c = __ldg(reinterpret_cast<const float4*>(args.rope_cos + (long long)t * 32 + c4));
-              const float4 s = __ldg(reinterpret_cast<const float4*>(args.rope_sin + (long long)t * 32 + c4));
-              const float4 o1 = make_float4(x1.x * c.x - x2.x * s.x, x1.y * c.y - x2.y * s.y, x1.z * c.z - x2.z * s.z,
-                                            x1.w * c.w - x2.w * s.w);
-              const float4 o2 = make_float4(x2.x * c.x + x1.x * s.x, x2.y * c.y + x1.y * s.y, x2.z * c.z + x1.z * s.z,
-                                            x2.w * c.w + x1.w * s.w);
-              x1 = o1; x2 = o2;
-            }
-            __nv_bfloat16* o = out + (row0 + rr) * args.ldo + col;
-            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(x1.x, x1.y), pack_bf16x2(x1.z, x1.w));
-            *reinterpret_cast<uint2*>(o + 32) = make_uint2(pack_bf16x2(x2.x, x2.y), pack_bf16x2(x2.z, x2.w));
+          if (rows_full || (t_base + 4 * it + rsub) < args.rows_per_batch) {
+            *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) = pack4(xa[it]);
+            *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo + 32) = pack4(xb[it]);
           }
         }
         __syncwarp();
       }
     }
   } else {
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + HN; c0 += 32) {
+#pragma unroll
+    for (int j = 0; j < HN / 32; ++j) {
+      const int c0 = cbeg + 32 * j;
       uint32_t r[32];
       tmem_ld_32x32(trow + c0, r);
       tmem_wait_ld();
@@ -214,66 +389,19 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
       stage_store_row(stage, lane, r);
       __syncwarp();
       const int col = n0 + c0 + c4;
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (args.bias != nullptr) b4 = ldg4_guard(args.bias + col, col, N);
-      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if constexpr (EPI == EPI_GATE_RESID) {
-        const long long step = args.step_ptr ? (long long)__ldg(args.step_ptr) : 0ll;
-        g4 = __ldg(reinterpret_cast<const float4*>(args.gate + step * args.gate_step_stride +
-                                                   (long long)(b % args.gate_nb) * args.gate_ld + col));
-      }
-      if constexpr (EPI == EPI_SCALE_RESID) {
-        if (args.gate != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(args.gate + col));
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = 4 * it + rsub;
-        const int t = t_base + rr;
-        if (t >= args.rows_per_batch) continue;
-        const long long grow = row0 + rr;
-        bool valid = t < seq_len;
-        if (args.row_valid != nullptr) valid = args.row_valid[grow] != 0;
-        float4 v = stage_load4(stage, rr, c4);
-        v = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
-
+      if (rows_full && (n0 + c0 + 32 <= N)) {
         if constexpr (EPI == EPI_BF16) {
-          if (args.act == ACT_GELU_TANH) v = map4(v, gelu_tanh_f);
-          else if (args.act == ACT_GELU_ERF) v = map4(v, gelu_erf_f);
-          else if (args.act == ACT_SILU) v = map4(v, silu_f);
-          st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
-        } else if constexpr (EPI == EPI_F32) {
-          if (args.addend != nullptr) {
-            const float4 a = ldg4_guard(args.addend + grow * args.ld_add + col, col, N);
-            v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+          switch (args.act) {  // hoisted out of the row loop: one straight-line body per activation
+            case ACT_GELU_TANH: epi_block_fast<EPI, ACT_GELU_TANH>(args, sp, row0 + rsub, col, pc.b4[j], pc.g4[j], t_base + rsub, seq_len); break;
+            case ACT_GELU_ERF: epi_block_fast<EPI, ACT_GELU_ERF>(args, sp, row0 + rsub, col, pc.b4[j], pc.g4[j], t_base + rsub, seq_len); break;
+            case ACT_SILU: epi_block_fast<EPI, ACT_SILU>(args, sp, row0 + rsub, col, pc.b4[j], pc.g4[j], t_base + rsub, seq_len); break;
+            default: epi_block_fast<EPI, ACT_NONE>(args, sp, row0 + rsub, col, pc.b4[j], pc.g4[j], t_base + rsub, seq_len); break;
           }
-          st_f32x4(reinterpret_cast<float*>(args.out) + grow * args.ldo + col, v, col, N);
-        } else if constexpr (EPI == EPI_GATE_RESID) {
-          if (args.mask_rows && !valid) continue;
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col);
-          float4 x = *o;
-          x.x += g4.x * v.x; x.y += g4.y * v.y; x.z += g4.z * v.z; x.w += g4.w * v.w;
-          *o = x;
-        } else if constexpr (EPI == EPI_EMBED_DUAL) {
-          const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
-          v = valid ? make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = v;
-          st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col, v, col, N);
-        } else if constexpr (EPI == EPI_MISH_MASK_BF16) {
-          v = valid ? map4(v, mish_f) : make_float4(0.f, 0.f, 0.f, 0.f);
-          st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
-        } else if constexpr (EPI == EPI_MISH_MASK_RESID) {
-          const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
-          v = valid ? map4(v, mish_f) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) =
-              make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
-        } else if constexpr (EPI == EPI_SCALE_RESID) {
-          const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
-          v = valid ? make_float4(a.x + g4.x * v.x, a.y + g4.y * v.y, a.z + g4.z * v.z, a.w + g4.w * v.w)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = v;
-          if (args.out2 != nullptr)
-            st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col, v, col, N);
+        } else {
+          epi_block_fast<EPI, ACT_NONE>(args, sp, row0 + rsub, col, pc.b4[j], pc.g4[j], t_base + rsub, seq_len);
         }
+      } else {
+        epi_block_slow<EPI>(args, stage, rsub, c4, row0, t_base, col, pc.b4[j], pc.g4[j], seq_len);
       }
       __syncwarp();
     }
@@ -399,12 +527,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int n0 = n_tile * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
+      EpiCols<HN> pc;
+      gemm_epilogue_prefetch<BN, EPI, HN>(args, b, n0, cbeg, lane, pc);
       mbar_wait(tfull_bar(as), aphase, 4);
       tc_fence_after();
 
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
       gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t_base, n0, cbeg,
-                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane);
+                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane, pc);
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -559,15 +689,17 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int n_tile = tile / tiles_mp;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
+      const int b = m_tile < tiles_m ? m_tile / tiles_m_pb : 0;
+      EpiCols<HN> pc;
+      gemm_epilogue_prefetch<BN, EPI, HN>(args, b, n_tile * BN, cbeg, lane, pc);
       mbar_wait(tfull_bar(as), aphase, 24);
       tc_fence_after();
       if (threadIdx.x == 64 && it < 2) ORON_STAMP(6 + 2 * it);
-      const int b = m_tile < tiles_m ? m_tile / tiles_m_pb : 0;
       // phantom tile: push the row index out of range so nothing is stored
       const int t_base = m_tile < tiles_m ? (m_tile % tiles_m_pb) * GEMM_BM + q * 32 : args.rows_per_batch;
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
       gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t_base, n_tile * BN, cbeg,
-                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane);
+                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane, pc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));
