@@ -319,7 +319,8 @@ class DiTEngine:
         sstride = w.ada_n if use_step else 0
         mld = 0 if mod_nb == 1 else w.ada_n
         common = dict(rows_per_batch=tpad, nbatch=nbp)
-        bn_d = pick_block_n(R, D)
+        # transformer GEMMs run on the 2-SM kernel: 256 x 256 tile per SM pair (256 x 128 for narrow models)
+        bn_big = 256 if D % 256 == 0 else 128
 
         L.gemm(ws.xb, w.wx, ws.h0, epilogue=L.EPI_EMBED_DUAL, addend=ws.c0, seq_lens=ws.seq_lens, out2=ws.h0b,
                block_n=128, **common)
@@ -336,19 +337,19 @@ class DiTEngine:
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
-                   rope_cols=2 * D, block_n=pick_block_n(R, 3 * D), **common)
+                   rope_cols=2 * D, block_n=bn_big, two_sm=True, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
                         scale=1.0 / math.sqrt(w.dim_head))
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
-                   mask_rows=True, block_n=bn_d, **common)
+                   mask_rows=True, block_n=bn_big, two_sm=True, **common)
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
-                   block_n=pick_block_n(R, w.ff_dim), **common)
+                   block_n=bn_big, two_sm=True, **common)
             L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                   block_n=bn_d, **common)
+                   block_n=bn_big, two_sm=True, **common)
         o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
         L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o:], shift=tab[o + D:], mod_ld=mld, mod_nb=mod_nb,
                       step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
