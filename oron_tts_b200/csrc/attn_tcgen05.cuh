@@ -1,10 +1,18 @@
 // Non-causal multi-head attention with per-sequence key lengths (replaces the reference's
 // F.scaled_dot_product_attention + key-padding mask, src/models/modules.py:271-278).
-// One CTA = one (batch element, head, 128-query tile). head_dim = 64.
-//   S = Q K^T      : tcgen05.mma M=128 N=128 K=64, accumulator in TMEM cols [0,128)
-//   P = softmax    : 128 softmax threads, one query row each (TMEM lane == row => no shuffles)
-//   O_j = P V_j    : tcgen05.mma M=128 N=64 K=128 (V tile as MN-major B operand), TMEM cols [128,192)
-//   O += O_j       : running output kept in registers (64 fp32 per row), rescaled online.
+// One CTA = one (batch element, head, 128-query tile); two CTAs per SM. head_dim = 64.
+//
+//   S = Q K^T   : tcgen05.mma M=128 N=128 K=64 -> TMEM cols [0,128)
+//   P = softmax : 128 softmax threads, one query row each (TMEM lane == row => no shuffles), two passes over
+//                 TMEM (row max, then exp2 + bf16 pack into a SW128 K-major smem tile)
+//   O += P V    : tcgen05.mma M=128 N=64 K=128 accumulating IN TMEM (cols [128,192)), V tile as MN-major B.
+//
+// The kernel is MUFU (exp2) bound, so everything else is kept off the softmax threads:
+//   * O stays in TMEM for the whole KV loop. The running maximum is only raised when a tile exceeds it by
+//     more than 2^8 ("lazy rescale": p <= 256 is exact enough in bf16/fp32); only then O is read back,
+//     scaled and stored again — a warp-uniform, rare branch.
+//   * S is released to the MMA thread as soon as the last TMEM read of pass 2 has landed, so Q K^T of the
+//     next tile runs under the exp/pack/store tail of this one.
 // q/k/v are read straight out of the fused QKV activation [rows, 3*H*64] with one 3-D TMA map.
 #pragma once
 #include "ptx.cuh"
@@ -28,6 +36,69 @@ constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB
 // smem: Q | K0 K1 | V0 V1 | P(2 slabs) | barriers
 constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128;
 constexpr int ATT_TMEM_COLS = 256;
+constexpr float ATT_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+        "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// exp2 + pack + swizzled store of one 32-key chunk of a P row. MASKED: keys >= n_valid contribute 0.
+template <bool MASKED>
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&v)[32], const float c, const float mc, const int c0,
+                                               const int n_valid, const uint32_t prow, const uint32_t sw) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
+    float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
+    float p2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), c, -mc));
+    float p3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), c, -mc));
+    if (MASKED) {
+      if (c0 + i >= n_valid) p0 = 0.f;
+      if (c0 + i + 1 >= n_valid) p1 = 0.f;
+      if (c0 + i + 2 >= n_valid) p2 = 0.f;
+      if (c0 + i + 3 >= n_valid) p3 = 0.f;
+    }
+    s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+    pk[i / 2] = pack_bf16x2(p0, p1);
+    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  const uint32_t slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
+  const uint32_t chunk0 = uint32_t(c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group inside its slab row
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t addr = slab + (((chunk0 + g) ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]), "r"(pk[4 * g + 1]),
+                 "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
+                 : "memory");
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+  for (int i = 4; i < 32; i += 4) {
+    m0 = fmaxf(m0, __uint_as_float(v[i]));
+    m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+    m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+    m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) {
@@ -54,16 +125,18 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (3 + s); };
-  const uint32_t s_full = bar_base + 8u * 5;
-  const uint32_t p_full = bar_base + 8u * 6;
-  const uint32_t o_full = bar_base + 8u * 7;
-  const uint32_t tmem_slot = bar_base + 8u * 8;
+  const uint32_t s_full = bar_base + 8u * 5;   // MMA -> softmax: S(j) is in TMEM
+  const uint32_t s_free = bar_base + 8u * 6;   // softmax -> MMA: S(j) has been read (128 arrivals)
+  const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (128 arrivals)
+  const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes P(j) V(j)
+  const uint32_t tmem_slot = bar_base + 8u * 9;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -111,109 +184,101 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       issue_S(0);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
-        mbar_wait(p_full, j & 1u, 14);  // P(j) in smem, S(j) and O(j-1) drained by the softmax threads
-        tc_fence_after();
         if (j + 1 < n_kv) {
+          mbar_wait(s_free, j & 1u, 14);  // S(j) fully read: the S columns may be overwritten
           mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1u, 15);
           tc_fence_after();
           issue_S(j + 1);
         }
+        mbar_wait(p_full, j & 1u, 16);  // P(j) in smem (and O rescaled if the running max moved)
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t pdesc =
               make_smem_desc_sw128(sP + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t vdesc = make_smem_desc_sw128(sV(s) + kk * 2048, 1024, 1024);
-          umma_bf16_ss(tmem_O, pdesc, vdesc, idesc_o, kk != 0);
+          umma_bf16_ss(tmem_O, pdesc, vdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(kv_empty(s));
       }
     }
   } else {
-    // ===================== softmax / output threads =====================
+    // ===================== softmax threads =====================
     const int q = warp & 3;
     const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const float c = args.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+    float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8
+    float l_run = 0.f;
     const uint32_t prow = sP + r * 128;
     const uint32_t sw = uint32_t(r & 7);
 
     for (int j = 0; j < n_kv; ++j) {
       const int n_valid = min(ATT_TILE, len - j * ATT_TILE);
-      mbar_wait(s_full, j & 1u, 16);
+      const bool full_tile = n_valid == ATT_TILE;  // CTA-uniform
+      mbar_wait(s_full, j & 1u, 17);
       tc_fence_after();
-      // pass 1: row maximum over the valid keys of this tile
+      // ---- pass 1: row maximum over the valid keys ----
       float mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_S + lane_off + c0, v);
         tmem_wait_ld();
-        if (c0 + 32 <= n_valid) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        if (full_tile || c0 + 32 <= n_valid) {
+          mx = fmaxf(mx, max32(v));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx((m_run - m_new) * c);  // m_run = -inf on the first tile -> 0
+      // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
+      const float mxc = mx * c;
+      const bool need = mxc > mc + ATT_RESCALE_LOG2;
       if (j > 0) {
-        // fold in O(j-1) = P(j-1) V(j-1), which was computed against m_run
-        mbar_wait(o_full, (j - 1) & 1u, 17);
+        // P(j-1) V(j-1) must have been folded into O before P is overwritten / O is rescaled
+        mbar_wait(o_full, (j - 1) & 1u, 18);
         tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2_approx(mc - mxc) : 1.0f;
+          l_run *= f;
 #pragma unroll
-        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_O + lane_off + c0, v);
-          tmem_wait_ld();
+          for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_O + lane_off + c0, v);
+            tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c0 + i] = (o_acc[c0 + i] + __uint_as_float(v[i])) * alpha;
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x32(tmem_O + lane_off + c0, v);
+          }
+          tmem_wait_st();
         }
       }
-      l_run *= alpha;
-      m_run = m_new;
-      const float mc = m_new * c;
-      // pass 2: P = exp2(S*c - m*c) -> bf16 -> smem (SW128 K-major, two 64-key slabs)
+      if (need) mc = mxc;
+      // ---- pass 2: P = exp2(S*c - m) -> bf16 -> smem (SW128 K-major, two 64-key slabs) ----
       float lsum = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_S + lane_off + c0, v);
         tmem_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(__uint_as_float(v[i]) * c - mc);
-          float p1 = ex2_approx(__uint_as_float(v[i + 1]) * c - mc);
-          if (c0 + i >= n_valid) p0 = 0.f;
-          if (c0 + i + 1 >= n_valid) p1 = 0.f;
-          lsum += p0 + p1;
-          pk[i / 2] = pack_bf16x2(p0, p1);
+        if (c0 == ATT_TILE - 32) {
+          // last read of S(j): let the MMA thread start Q K^T of the next tile under the rest of this pass
+          tc_fence_before();
+          mbar_arrive(s_free);
         }
-        const uint32_t slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
-        const uint32_t chunk0 = uint32_t(c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t addr = slab + (((chunk0 + g) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]),
-                       "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
-                       : "memory");
-        }
+        lsum += full_tile ? softmax_chunk<false>(v, c, mc, c0, n_valid, prow, sw)
+                          : softmax_chunk<true>(v, c, mc, c0, n_valid, prow, sw);
       }
       l_run += lsum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // last tile's PV
-    mbar_wait(o_full, (n_kv - 1) & 1u, 18);
+    // ---- epilogue: O / l ----
+    mbar_wait(o_full, (n_kv - 1) & 1u, 19);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int t = q0 + r;
@@ -227,8 +292,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2)
-          pk[i / 2] = pack_bf16x2((o_acc[c0 + i] + __uint_as_float(v[i])) * inv_l,
-                                  (o_acc[c0 + i + 1] + __uint_as_float(v[i + 1])) * inv_l);
+          pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
         uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
         for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
