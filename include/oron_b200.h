@@ -104,6 +104,7 @@ typedef struct oron_gemm_desc {
   int32_t mask_rows;
   int32_t max_ctas;          /* 0 = one CTA per SM */
   int32_t two_sm;            /* 1: 2-SM (cta_group::2) kernel, 256 x block_n tile per SM pair */
+  int32_t f16_from_col;      /* QKV_ROPE: columns >= this (> 0) are stored as IEEE f16, not bf16 (the V operand of attention) */
   void* debug_stamps;        /* NULL, or int64 [grid, 16] device buffer for per-CTA clock64 stamps (profiling aid) */
 } oron_gemm_desc;
 
@@ -113,7 +114,9 @@ int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);
  * softmax(Q K^T * scale + key_padding_mask) V over the fused QKV activation; head_dim 64.
  * Replaces F.scaled_dot_product_attention + mask (modules.py:271-278). RoPE is already applied
  * by the QKV GEMM epilogue.
- *   qkv: bf16 [nbatch*rows_per_batch, ld_qkv], q | k | v at column offsets 0 | H*64 | 2*H*64.
+ *   qkv: 16-bit [nbatch*rows_per_batch, ld_qkv], q | k | v at column offsets 0 | H*64 | 2*H*64;
+ *        q and k are bf16, v is IEEE f16 (written so by the QKV GEMM with f16_from_col = 2*H*64): the
+ *        probabilities come out of the packed f16x2 exp2 unit and P*V runs as an f16 x f16 MMA.
  *   out: bf16 [nbatch*rows_per_batch, ldo], head h at columns [64h, 64h+64). Query tiles that lie
  *        entirely beyond seq_lens[b] are not written.
  */
@@ -199,6 +202,9 @@ int oron_istft_head(const float* h, int64_t ldh, int32_t rows_per_batch, int32_t
  * scratch: f32 [nb]. */
 int oron_peak_normalize(const float* x, int64_t ldx, int32_t nb, int32_t n, float* out, int64_t ldo,
                         float* scratch, oron_stream_t stream);
+
+/* Profiling aid: int64 [n_ctas, 16] device buffer that receives per-CTA clock64 stamps of the attention kernel; NULL disables. */
+void oron_debug_set_attention_stamps(void* buf);
 
 int oron_abi_version(void);
 const char* oron_last_error(void);

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "oron_logmel",
     "oron_istft_head",
     "oron_peak_normalize",
+    "oron_debug_set_attention_stamps",
     "oron_abi_version",
     "oron_last_error",
     "oron_launch_count",
@@ -80,6 +81,7 @@ class GemmDesc(ctypes.Structure):
         ("mask_rows", c_int32),
         ("max_ctas", c_int32),
         ("two_sm", c_int32),
+        ("f16_from_col", c_int32),
         ("debug_stamps", c_void_p),
     ]
 
@@ -101,6 +103,8 @@ def lib() -> ctypes.CDLL:
     L.oron_last_error.restype = c_char_p
     L.oron_launch_count.restype = c_uint64
     L.oron_abi_version.restype = c_int32
+    L.oron_debug_set_attention_stamps.argtypes = [c_void_p]
+    L.oron_debug_set_attention_stamps.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                       c_void_p, c_float, c_void_p]
@@ -193,6 +197,7 @@ def gemm(
     max_ctas: int = 0,
     two_sm: bool = False,
     debug_stamps: torch.Tensor | None = None,
+    f16_from_col: int = 0,
 ) -> None:
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16."""
     d = GemmDesc()
@@ -225,6 +230,7 @@ def gemm(
     d.mask_rows = int(bool(mask_rows))
     d.max_ctas = int(max_ctas)
     d.two_sm = int(bool(two_sm))
+    d.f16_from_col = int(f16_from_col)
     d.debug_stamps = _ptr(debug_stamps, torch.int64, "debug_stamps")
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16

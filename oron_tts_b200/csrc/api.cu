@@ -162,6 +162,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   a.rope_cos = d->rope_cos;
   a.rope_sin = d->rope_sin;
   a.rope_cols = d->rope_cols;
+  a.f16_from_col = d->f16_from_col > 0 ? d->f16_from_col : 0x7fffffff;
   a.seq_lens = d->seq_lens;
   a.row_valid = d->row_valid;
   a.mask_rows = d->mask_rows;
@@ -230,6 +231,9 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
 // ---------------------------------------------------------------------------
 // attention
 // ---------------------------------------------------------------------------
+static long long* g_attn_dbg = nullptr;
+// profiling aid (tools/attn_trace.py): int64 [n_ctas, 16] device buffer receiving per-CTA clock64 stamps, or NULL
+extern "C" void oron_debug_set_attention_stamps(void* buf) { g_attn_dbg = reinterpret_cast<long long*>(buf); }
 extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                                    int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
                                    oron_stream_t stream) {
@@ -255,6 +259,7 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
+  a.dbg = g_attn_dbg;
   dim3 grid((rows_per_batch + ATT_TILE - 1) / ATT_TILE, heads, nbatch);
   attn_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, a);
   return check_launch("attn_fwd_tcgen05");

@@ -4,8 +4,12 @@
 //
 //   S = Q K^T   : tcgen05.mma M=128 N=128 K=64 -> TMEM cols [0,128)
 //   P = softmax : 128 softmax threads, one query row each (TMEM lane == row => no shuffles), two passes over
-//                 TMEM (row max, then exp2 + bf16 pack into a SW128 K-major smem tile)
-//   O += P V    : tcgen05.mma M=128 N=64 K=128 accumulating IN TMEM (cols [128,192)), V tile as MN-major B.
+//                 TMEM (row max, then packed f16x2 exp2 — two probabilities per MUFU op — stored as an f16
+//                 SW128 K-major smem tile)
+//   O += P V    : tcgen05.mma (f16 x f16) M=128 N=64 K=128 accumulating IN TMEM (cols [128,192)), V tile as
+//                 MN-major B; V is written as f16 by the QKV GEMM epilogue.
+//   l += P 1    : the softmax denominator comes from the tensor core too: P times a constant all-ones tile
+//                 (M=128 N=16) into TMEM cols [192,208) — no row sums on the CUDA cores.
 //
 // The kernel is MUFU (exp2) bound, so everything else is kept off the softmax threads:
 //   * O stays in TMEM for the whole KV loop. The running maximum is only raised when a tile exceeds it by
@@ -15,6 +19,8 @@
 //     next tile runs under the exp/pack/store tail of this one.
 // q/k/v are read straight out of the fused QKV activation [rows, 3*H*64] with one 3-D TMA map.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace oron {
@@ -27,6 +33,7 @@ struct AttnArgs {
   __nv_bfloat16* out;   // [nbatch*rows_per_batch, ldo], head h at columns [h*64, h*64+64)
   long long ldo;
   float scale_log2;     // softmax scale * log2(e)
+  long long* dbg;       // optional [grid, 16] clock64 stamps (tools/attn_trace.py); nullptr in production
 };
 
 constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 softmax
@@ -34,9 +41,12 @@ constexpr int ATT_TILE = 128;
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB
 // smem: Q | K0 K1 | V0 V1 | P(2 slabs) | barriers
-constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128;
+constexpr int ATT_ONES_BYTES = 512;  // [16 x 16] f16 ones, no-swizzle K-major core matrices
+constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_ONES_BYTES;
 constexpr int ATT_TMEM_COLS = 256;
+#define ATT_STAMP(slot) do { if (args.dbg) args.dbg[(long long)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
+constexpr float ATT_P_EXP_BIAS = 7.0f;    // probabilities are scaled by 2^7 (<= 2^15 in f16); cancels in O / l
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -53,28 +63,43 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 
-// exp2 + pack + swizzled store of one 32-key chunk of a P row. MASKED: keys >= n_valid contribute 0.
+// exp2 + swizzled store of one 32-key chunk of a P row: x = s*c - (m*c - 7) is packed to f16x2 and both
+// exponentials come out of ONE MUFU op, already in the f16 format the P*V MMA consumes.
+// MASKED: keys >= n_valid get probability 0.
 template <bool MASKED>
-__device__ __forceinline__ float softmax_chunk(const uint32_t (&v)[32], const float c, const float mc, const int c0,
-                                               const int n_valid, const uint32_t prow, const uint32_t sw) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int c0,
+                                              const int n_valid, const uint32_t prow, const uint32_t sw) {
   uint32_t pk[16];
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
-    float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
-    float p2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), c, -mc));
-    float p3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), c, -mc));
+  for (int i = 0; i < 32; i += 2) {
+    const float x0 = fmaf(__uint_as_float(v[i]), c, -mcb);
+    const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -mcb);
+    __half2 h = __floats2half2_rn(x0, x1);
+    uint32_t p = ex2_f16x2(*reinterpret_cast<uint32_t*>(&h));
     if (MASKED) {
-      if (c0 + i >= n_valid) p0 = 0.f;
-      if (c0 + i + 1 >= n_valid) p1 = 0.f;
-      if (c0 + i + 2 >= n_valid) p2 = 0.f;
-      if (c0 + i + 3 >= n_valid) p3 = 0.f;
+      if (c0 + i >= n_valid) p &= 0xFFFF0000u;
+      if (c0 + i + 1 >= n_valid) p &= 0x0000FFFFu;
     }
-    s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-    pk[i / 2] = pack_bf16x2(p0, p1);
-    pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+    pk[i / 2] = p;
   }
   const uint32_t slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
   const uint32_t chunk0 = uint32_t(c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group inside its slab row
@@ -85,7 +110,6 @@ __device__ __forceinline__ float softmax_chunk(const uint32_t (&v)[32], const fl
                  "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
                  : "memory");
   }
-  return (s0 + s1) + (s2 + s3);
 }
 
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
@@ -130,6 +154,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (128 arrivals)
   const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes P(j) V(j)
   const uint32_t tmem_slot = bar_base + 8u * 9;
+  const uint32_t sOnes = bar_base + 128;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -145,6 +170,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
+  if (threadIdx.x >= 64) {  // constant all-ones B operand of the denominator MMA (f16 1.0 = 0x3C00)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sOnes + 4u * (threadIdx.x - 64)), "r"(0x3C003C00u) : "memory");
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,6 +181,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_L = tmem_base + 192;
+  if (threadIdx.x == 0) ATT_STAMP(0);
 
   const int HD = args.heads * ATT_D;
   if (warp == 0) {
@@ -169,7 +200,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major
+      constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);  // f16 P x f16 V, B = V is MN-major
+      constexpr uint32_t idesc_l = make_idesc_f16(128, 16, 0, 0);  // f16 P x ones
+      const uint64_t onesdesc = make_smem_desc_noswz(sOnes, 128, 256);
       const uint64_t qdesc = make_smem_desc_sw128(sQ, 16, 1024);
       auto issue_S = [&](int j) {
         const uint64_t kdesc = make_smem_desc_sw128(sK(j & 1), 16, 1024);
@@ -198,6 +231,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
               make_smem_desc_sw128(sP + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t vdesc = make_smem_desc_sw128(sV(s) + kk * 2048, 1024, 1024);
           umma_bf16_ss(tmem_O, pdesc, vdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_L, pdesc, onesdesc, idesc_l, (j | kk) != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(kv_empty(s));
@@ -210,7 +244,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const float c = args.scale_log2;
     float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8
-    float l_run = 0.f;
     const uint32_t prow = sP + r * 128;
     const uint32_t sw = uint32_t(r & 7);
 
@@ -219,6 +252,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       const bool full_tile = n_valid == ATT_TILE;  // CTA-uniform
       mbar_wait(s_full, j & 1u, 17);
       tc_fence_after();
+      const bool tr = threadIdx.x == 64 && (j == 2 || j == 3);
+      if (tr) ATT_STAMP(1 + 6 * (j - 2));
       // ---- pass 1: row maximum over the valid keys ----
       float mx = -INFINITY;
 #pragma unroll
@@ -237,13 +272,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const float mxc = mx * c;
       const bool need = mxc > mc + ATT_RESCALE_LOG2;
+      if (tr) ATT_STAMP(2 + 6 * (j - 2));
       if (j > 0) {
         // P(j-1) V(j-1) must have been folded into O before P is overwritten / O is rescaled
         mbar_wait(o_full, (j - 1) & 1u, 18);
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
           const float f = need ? ex2_approx(mc - mxc) : 1.0f;
-          l_run *= f;
 #pragma unroll
           for (int c0 = 0; c0 < ATT_D; c0 += 32) {
             uint32_t v[32];
@@ -253,12 +288,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
             tmem_st_32x32(tmem_O + lane_off + c0, v);
           }
+          {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_L + lane_off, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x16(tmem_L + lane_off, v);
+          }
           tmem_wait_st();
         }
       }
       if (need) mc = mxc;
-      // ---- pass 2: P = exp2(S*c - m) -> bf16 -> smem (SW128 K-major, two 64-key slabs) ----
-      float lsum = 0.f;
+      if (tr) ATT_STAMP(3 + 6 * (j - 2));
+      // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
+      const float mcb = mc - ATT_P_EXP_BIAS;
 #pragma unroll
       for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
         uint32_t v[32];
@@ -269,18 +313,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           tc_fence_before();
           mbar_arrive(s_free);
         }
-        lsum += full_tile ? softmax_chunk<false>(v, c, mc, c0, n_valid, prow, sw)
-                          : softmax_chunk<true>(v, c, mc, c0, n_valid, prow, sw);
+        if (full_tile) softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw);
+        else softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
       }
-      l_run += lsum;
+      if (tr) ATT_STAMP(4 + 6 * (j - 2));
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
+      if (tr) ATT_STAMP(5 + 6 * (j - 2));
     }
     // ---- epilogue: O / l ----
     mbar_wait(o_full, (n_kv - 1) & 1u, 19);
     tc_fence_after();
-    const float inv_l = 1.0f / l_run;
+    float inv_l;
+    {
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_L + lane_off, v);
+      tmem_wait_ld();
+      inv_l = 1.0f / __uint_as_float(v[0]);
+    }
     const int t = q0 + r;
     __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D;
 #pragma unroll
@@ -299,9 +350,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 64) ATT_STAMP(14);
   }
 
   __syncthreads();
+  if (threadIdx.x == 0) ATT_STAMP(15);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);

@@ -8,6 +8,8 @@
 // k-block `kb` is fetched at row offset (kb / cpb - pad) and, for grouped convs, at the
 // column block of the output group; TMA zero-fills rows outside [0, rows_per_batch).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace oron {
@@ -53,6 +55,7 @@ struct GemmArgs {
   const float* rope_cos;       // f32 [rows_per_batch, 32]
   const float* rope_sin;
   int rope_cols;               // columns [0, rope_cols) are rotated (q and k)
+  int f16_from_col;            // EPI_QKV_ROPE: columns >= this are stored as IEEE f16 instead of bf16 (V for attention)
   const int* seq_lens;         // [nbatch] valid rows per batch element or nullptr (all valid)
   const unsigned char* row_valid;  // [rows] explicit per-row validity (overrides seq_lens) or nullptr
   int mask_rows;               // EPI_GATE_RESID: skip rows t >= seq_len
@@ -155,6 +158,10 @@ __device__ __forceinline__ float4 fma4(float4 g, float4 v, float4 a) {
   return make_float4(fmaf(g.x, v.x, a.x), fmaf(g.y, v.y, a.y), fmaf(g.z, v.z, a.z), fmaf(g.w, v.w, a.w));
 }
 __device__ __forceinline__ uint2 pack4(float4 v) { return make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
+__device__ __forceinline__ uint2 pack4_f16(float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
 
 // Fast path of one staged 32x32 block: every row and column of the block is in range, so the 8 row-groups are
 // loaded up front (ILP) and written with unguarded vector accesses. The epilogue is instruction-latency bound
@@ -344,6 +351,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
         stage_store_row(stage, lane, r);
         __syncwarp();
         const bool rot = (n0 + c0) < args.rope_cols;
+        const bool as_f16 = (n0 + c0) >= args.f16_from_col;  // warp-uniform
         float4 xb[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) xb[it] = add4(*reinterpret_cast<const float4*>(sp + it * 4 * EPI_STAGE_LD), pc.b4[2 * j + 1]);
@@ -371,8 +379,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           if (rows_full || (t_base + 4 * it + rsub) < args.rows_per_batch) {
-            *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) = pack4(xa[it]);
-            *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo + 32) = pack4(xb[it]);
+            *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) = as_f16 ? pack4_f16(xa[it]) : pack4(xa[it]);
+            *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo + 32) = as_f16 ? pack4_f16(xb[it]) : pack4(xb[it]);
           }
         }
         __syncwarp();

@@ -337,7 +337,7 @@ class DiTEngine:
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
-                   rope_cols=2 * D, block_n=bn_big, two_sm=True, **common)
+                   rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
                         scale=1.0 / math.sqrt(w.dim_head))
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],

@@ -106,7 +106,8 @@ def test_gemm_qkv_rope(L):
     for bn in (128, 256):
         out = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
         L.gemm(A, W, out, epilogue=L.EPI_QKV_ROPE, bias=bias, rows_per_batch=T, nbatch=nb, block_n=bn,
-               rope_cos=cos, rope_sin=sin, rope_cols=2 * D)
+               rope_cos=cos, rope_sin=sin, rope_cols=2 * D, f16_from_col=2 * D)
+        out = torch.cat([out[:, :2 * D].float(), out[:, 2 * D:].contiguous().view(torch.float16).float()], 1)
         pre = (A.float() @ W.float().t() + bias).view(nb, T, 3, H, 64)
         q, k, v = pre[:, :, 0], pre[:, :, 1], pre[:, :, 2]
         c = torch.cat([cos, cos], -1)[None, :, None, :]
@@ -289,11 +290,15 @@ def test_gemm_two_sm_fused_epilogues(L):
 def test_attention(L, nb, T, H, lens):
     g = torch.Generator(device=DEV).manual_seed(T + H)
     qkv = _bf(torch.randn(nb * T, 3 * H * 64, device=DEV, generator=g))
+    # the V third is IEEE f16 (bit-cast into the bf16-typed buffer), as the QKV GEMM epilogue writes it
+    v16 = torch.randn(nb * T, H * 64, device=DEV, generator=g).half()
+    qkv[:, 2 * H * 64:] = v16.view(torch.bfloat16)
     out = torch.zeros(nb * T, H * 64, device=DEV, dtype=torch.bfloat16)
     lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32) if lens is not None else None
     L.attention(qkv, out, nbatch=nb, rows_per_batch=T, heads=H, seq_lens=lens_t, scale=0.125)
     x = qkv.float().view(nb, T, 3, H, 64)
-    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    q, k = (x[:, :, i].transpose(1, 2) for i in range(2))
+    v = v16.float().view(nb, T, H, 64).transpose(1, 2)
     ll = lens if lens is not None else [T] * nb
     mask = torch.arange(T, device=DEV)[None, :] < torch.tensor(ll, device=DEV)[:, None]
     ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask[:, None, None, :])

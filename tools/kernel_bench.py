@@ -100,6 +100,7 @@ if what in ("gemm", "all"):
 if what in ("attn", "all"):
     g = torch.Generator(device=DEV).manual_seed(1)
     qkv = torch.randn(R, 3072, device=DEV, generator=g).bfloat16()
+    qkv[:, 2048:] = torch.randn(R, 1024, device=DEV, generator=g).half().view(torch.bfloat16)
     o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
     lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
     run([("attention T=1406 H=16 nb=2", 4 * 2 * 16 * 1406 * 1406 * 64,
