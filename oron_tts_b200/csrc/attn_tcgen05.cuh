@@ -46,6 +46,10 @@ constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_ONES_BYTES;
 constexpr int ATT_TMEM_COLS = 256;
 #define ATT_STAMP(slot) do { if (args.dbg) args.dbg[(long long)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
+#ifndef ATT_STAGGER_NS
+#define ATT_STAGGER_NS 700
+#endif
+constexpr unsigned ATT_STAGGER_WAVE = 148;  // CTAs are dealt round-robin over the SMs: lin and lin+148 are co-resident
 constexpr float ATT_P_EXP_BIAS = 7.0f;    // probabilities are scaled by 2^7 (<= 2^15 in f16); cancels in O / l
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -246,6 +250,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8
     const uint32_t prow = sP + r * 128;
     const uint32_t sw = uint32_t(r & 7);
+    // Two CTAs share an SM and would otherwise run in lockstep (same start, same period), hitting the MUFU
+    // pipe at the same time and idling it together. Start every second wave of CTAs half a tile late so that
+    // one CTA's exp phase overlaps the other's max / wait phases.
+    {
+      const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      if ((lin / ATT_STAGGER_WAVE) & 1u) __nanosleep(ATT_STAGGER_NS);
+    }
 
     for (int j = 0; j < n_kv; ++j) {
       const int n_valid = min(ATT_TILE, len - j * ATT_TILE);
