@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/oron_b200.h"
@@ -30,6 +31,14 @@ int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(int(e), "%s: %s", what, cudaGetErrorString(e));
   return 0;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORON_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 int num_sms() {
   static int sms = 0;
@@ -96,7 +105,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   const int cap = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > cap) grid = cap;
   if (grid <= 0) return 0;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, a);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta, tb, a);
+  if (le != cudaSuccess) return fail(int(le), "gemm launch: %s", cudaGetErrorString(le));
   return check_launch("gemm_bf16_tcgen05");
 }
 
@@ -117,7 +127,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   const int cap = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
   if (pairs > cap) pairs = cap;
   if (pairs <= 0) return 0;
-  kern<<<2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, a);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta, tb, a);
+  if (le != cudaSuccess) return fail(int(le), "gemm2 launch: %s", cudaGetErrorString(le));
   return check_launch("gemm2_bf16_tcgen05");
 }
 
@@ -261,7 +272,9 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   a.scale_log2 = scale * 1.4426950408889634f;
   a.dbg = g_attn_dbg;
   dim3 grid((rows_per_batch + ATT_TILE - 1) / ATT_TILE, heads, nbatch);
-  attn_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, a);
+  cudaError_t le = launch_pdl(attn_fwd_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES,
+                              reinterpret_cast<cudaStream_t>(stream), tq, a);
+  if (le != cudaSuccess) return fail(int(le), "attention launch: %s", cudaGetErrorString(le));
   return check_launch("attn_fwd_tcgen05");
 }
 
@@ -282,11 +295,11 @@ extern "C" int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_ba
   const long long rows = (long long)rows_per_batch * nbatch;
   const int blocks = int((rows + 7) / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (C == 1024) ln_modulate_kernel<1024><<<blocks, 256, 0, st>>>(a);
-  else if (C == 512) ln_modulate_kernel<512><<<blocks, 256, 0, st>>>(a);
-  else if (C == 256) ln_modulate_kernel<256><<<blocks, 256, 0, st>>>(a);
-  else if (C == 128) ln_modulate_kernel<128><<<blocks, 256, 0, st>>>(a);
-  else if (C == 768) ln_modulate_kernel<768><<<blocks, 256, 0, st>>>(a);
+  if (C == 1024) launch_pdl(ln_modulate_kernel<1024>, dim3(blocks), dim3(256), 0, st, a);
+  else if (C == 512) launch_pdl(ln_modulate_kernel<512>, dim3(blocks), dim3(256), 0, st, a);
+  else if (C == 256) launch_pdl(ln_modulate_kernel<256>, dim3(blocks), dim3(256), 0, st, a);
+  else if (C == 128) launch_pdl(ln_modulate_kernel<128>, dim3(blocks), dim3(256), 0, st, a);
+  else if (C == 768) launch_pdl(ln_modulate_kernel<768>, dim3(blocks), dim3(256), 0, st, a);
   else return fail(ORON_ERR_UNSUPPORTED, "ln_modulate: C=%d not supported (128/256/512/768/1024)", C);
   return check_launch("ln_modulate");
 }
@@ -303,10 +316,10 @@ extern "C" int oron_cfg_euler_step(float* x, const float* v, int64_t ldv, int32_
   int blocks = int((total + 255) / 256);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cfg_euler_kernel<<<blocks, 256, 0, st>>>(a);
+  launch_pdl(cfg_euler_kernel, dim3(blocks), dim3(256), 0, st, a);
   int rc = check_launch("cfg_euler");
   if (rc) return rc;
-  step_advance_kernel<<<1, 1, 0, st>>>(step_ptr);
+  launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, st, step_ptr);
   return check_launch("step_advance");
 }
 

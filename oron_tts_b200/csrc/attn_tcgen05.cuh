@@ -135,6 +135,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = q_tile * ATT_TILE;
   const int len = args.seq_lens ? min(args.seq_lens[b], args.rows_per_batch) : args.rows_per_batch;
@@ -186,6 +187,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
   const uint32_t tmem_L = tmem_base + 192;
+  pdl_wait();  // the QKV activations of the previous kernel are visible from here on
   if (threadIdx.x == 0) ATT_STAMP(0);
 
   const int HD = args.heads * ATT_D;

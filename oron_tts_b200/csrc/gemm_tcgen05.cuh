@@ -458,11 +458,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
@@ -625,11 +627,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish_2sm();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   if (threadIdx.x == 0) ORON_STAMP(0);
 
   if (warp == 0) {

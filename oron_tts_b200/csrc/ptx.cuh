@@ -32,6 +32,14 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start while its
+// predecessor is still running; it must not touch the predecessor's outputs before pdl_wait().
+// Both are no-ops for ordinary launches.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -38,6 +38,8 @@ struct LnArgs {
 template <int C>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnArgs a) {
   constexpr int V4 = C / 128;  // float4 per lane
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)a.rows_per_batch * a.nbatch;
@@ -104,6 +106,8 @@ struct EulerArgs {
 };
 
 __global__ void __launch_bounds__(256) cfg_euler_kernel(const EulerArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long rows = (long long)a.nb * a.rows_per_batch;
   const long long total = rows * a.n_mels;
   const int step = *a.step_ptr;
@@ -127,7 +131,11 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const EulerArgs a) {
     if (a.has_uncond) a.xb[(rows + row) * a.ldxb + c] = xh;
   }
 }
-__global__ void step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void step_advance_kernel(int* step_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step_ptr += 1;
+}
 
 // fp32 [rows, C] -> bf16 [rows, ldo] (cols >= C untouched), optionally replicated `reps` times
 __global__ void __launch_bounds__(256)
