@@ -201,7 +201,7 @@ def run_ours(args) -> dict:
 
 def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
     """Dominant kernel = gemm_bf16_tcgen05 (all Linear / conv launches of an NFE). achieved = algorithmic GEMM
-    FLOPs of one NFE / summed CUDA-event time of its GEMM launches, measured on one eager (ungraphed) step."""
+    FLOPs of one NFE / CUDA-event time of a graph replaying exactly those launches."""
     from oron_tts_b200 import _lib as L
 
     peaks = {}
@@ -211,39 +211,44 @@ def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
     peak, which = (peaks["bf16_tflops_sustained"], "measured (sustained cuBLAS bf16)") if "bf16_tflops_sustained" in peaks \
         else (1400.0, "fallback (B200_PROFILING.md sustained)")
     ws = next(iter(eng._ws.values())) if len(eng._ws) == 1 else max(eng._ws.values(), key=lambda w: w.steps * w.tpad)
-    records = []
-    orig = {name: getattr(L, name) for name in ("gemm", "attention", "ln_modulate", "cfg_euler_step")}
+    kinds = ("gemm", "attention", "ln_modulate")
+    orig = {name: getattr(L, name) for name in kinds}
+    t, launches = {}, {}
+    ws.step.zero_()
+    for kind in kinds:
+        # one CUDA graph holding ONLY this kernel family's launches of one NFE (same operands, same order, back to
+        # back as in the real step): replay time / launches = average launch duration under the timed conditions.
+        # Bracketing every launch with its own event pair instead costs several microseconds of bubble per kernel.
+        count = [0]
 
-    def wrap(name):
-        def f(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            orig[name](*a, **k)
-            e1.record()
-            records.append((name, e0, e1))
-        return f
+        def counted(*a, _f=orig[kind], **k):
+            count[0] += 1
+            return _f(*a, **k)
 
-    try:
-        for name in orig:
-            setattr(L, name, wrap(name))
-        ws.step.zero_()
-        for _ in range(2):  # warm
-            eng.velocity(ws, mod_nb=1, use_step=True)
-        torch.cuda.synchronize()
-        records.clear()
-        reps = 3
-        for _ in range(reps):
-            # a long spin kernel first: the host enqueues the whole NFE (one Python/ctypes call per kernel) while the
-            # GPU is still busy, so the events bracket device execution, not host launch latency
-            torch.cuda._sleep(int(4.0e7))
-            eng.velocity(ws, mod_nb=1, use_step=True)
+        try:
+            for name in kinds:
+                setattr(L, name, counted if name == kind else (lambda *a, **k: None))
+            eng.velocity(ws, mod_nb=1, use_step=True)  # warm (attributes, tables)
             torch.cuda.synchronize()
-    finally:
-        for name, fn in orig.items():
-            setattr(L, name, fn)
-    t = {}
-    for name, e0, e1 in records:
-        t[name] = t.get(name, 0.0) + e0.elapsed_time(e1) / reps
+            count[0] = 0
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.velocity(ws, mod_nb=1, use_step=True)
+        finally:
+            for name, fn in orig.items():
+                setattr(L, name, fn)
+        launches[kind] = count[0]
+        for _ in range(2):
+            g.replay()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t[kind] = e0.elapsed_time(e1) / reps
     fl = algorithmic_flops_per_nfe(T_TOTAL)
     gemm_flops = fl["gemm"] + fl["other"]
     achieved = gemm_flops / (t["gemm"] * 1e-3) / 1e12
@@ -252,7 +257,8 @@ def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
         "bound": "tensor", "kernel": "gemm2_bf16_tcgen05_kernel (all Linear/conv launches of one NFE)", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
         "frac": round(achieved / peak, 4), "peak_source": which, "traffic": None,
         "flops_per_nfe": fl, "kernel_ms_per_nfe": {k: round(v, 4) for k, v in t.items()},
-        "share_of_step": {k: round(v / total, 4) for k, v in t.items()},
+        "share_of_step": {k: round(v / total, 4) for k, v in t.items()}, "launches_per_nfe": launches,
+        "avg_launch_us": {k: round(1e3 * v / max(launches[k], 1), 2) for k, v in t.items()},
         "attention_tflops": round(fl["attn"] / (t["attention"] * 1e-3) / 1e12, 1),
     }
 

@@ -86,24 +86,44 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
-// exp2 + swizzled store of one 32-key chunk of a P row: x = s*c - (m*c - 7) is packed to f16x2 and both
-// exponentials come out of ONE MUFU op, already in the f16 format the P*V MMA consumes.
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 magic constant,
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 7.5e-5 — f16 resolution is 4.9e-4), and
+// n added straight into the exponent field. Valid for -125 <= x < 2^22.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.0551716573536396f, f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// exp2 + swizzled store of one 32-key chunk of a P row. The exp2 unit (MUFU) is the kernel's bottleneck
+// (~13 cycles per warp instruction), so every second pair of probabilities is evaluated with exp2_poly on the
+// otherwise idle FMA/ALU pipes instead. x = s*c - (m*c - 7); results are packed to the f16 P tile.
 // MASKED: keys >= n_valid get probability 0.
 template <bool MASKED>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int c0,
                                               const int n_valid, const uint32_t prow, const uint32_t sw) {
   uint32_t pk[16];
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
+  for (int i = 0; i < 32; i += 4) {
     const float x0 = fmaf(__uint_as_float(v[i]), c, -mcb);
     const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -mcb);
-    __half2 h = __floats2half2_rn(x0, x1);
-    uint32_t p = ex2_f16x2(*reinterpret_cast<uint32_t*>(&h));
+    const float x2 = fmaf(__uint_as_float(v[i + 2]), c, -mcb);
+    const float x3 = fmaf(__uint_as_float(v[i + 3]), c, -mcb);
+    float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+    float p2 = exp2_poly(x2), p3 = exp2_poly(x3);
     if (MASKED) {
-      if (c0 + i >= n_valid) p &= 0xFFFF0000u;
-      if (c0 + i + 1 >= n_valid) p &= 0x0000FFFFu;
+      if (c0 + i >= n_valid) p0 = 0.f;
+      if (c0 + i + 1 >= n_valid) p1 = 0.f;
+      if (c0 + i + 2 >= n_valid) p2 = 0.f;
+      if (c0 + i + 3 >= n_valid) p3 = 0.f;
     }
-    pk[i / 2] = p;
+    __half2 a = __floats2half2_rn(p0, p1), b = __floats2half2_rn(p2, p3);
+    pk[i / 2] = *reinterpret_cast<uint32_t*>(&a);
+    pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&b);
   }
   const uint32_t slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
   const uint32_t chunk0 = uint32_t(c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group inside its slab row
