@@ -99,9 +99,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-// exp2 + swizzled store of one 32-key chunk of a P row. The exp2 unit (MUFU) is the kernel's bottleneck
-// (~13 cycles per warp instruction), so every second pair of probabilities is evaluated with exp2_poly on the
-// otherwise idle FMA/ALU pipes instead. x = s*c - (m*c - 7); results are packed to the f16 P tile.
+// exp2 + swizzled store of one 32-key chunk of a P row. x = s*c - (m*c - 7); results are packed to the f16 P tile.
 // MASKED: keys >= n_valid get probability 0.
 template <bool MASKED>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int c0,
@@ -113,8 +111,11 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const flo
     const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -mcb);
     const float x2 = fmaf(__uint_as_float(v[i + 2]), c, -mcb);
     const float x3 = fmaf(__uint_as_float(v[i + 3]), c, -mcb);
+    // all four through the exp2 unit: replacing half of them by exp2_poly (FMA pipe) was measured SLOWER
+    // (pass 2: 1.7k -> 2.4k cycles per tile): with one softmax warp per scheduler the loop is bound by the
+    // instruction count, not by MUFU throughput.
     float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-    float p2 = exp2_poly(x2), p3 = exp2_poly(x3);
+    float p2 = ex2_approx(x2), p3 = ex2_approx(x3);
     if (MASKED) {
       if (c0 + i >= n_valid) p0 = 0.f;
       if (c0 + i + 1 >= n_valid) p1 = 0.f;
@@ -228,10 +229,18 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);  // f16 P x f16 V, B = V is MN-major
       constexpr uint32_t idesc_l = make_idesc_f16(128, 16, 0, 0);  // f16 P x ones
+      // all shared-memory descriptors are loop invariant (two K/V stages): build them once so that the single
+      // issuing thread spends its time on tcgen05.mma, not on address arithmetic
       const uint64_t onesdesc = make_smem_desc_noswz(sOnes, 128, 256);
       const uint64_t qdesc = make_smem_desc_sw128(sQ, 16, 1024);
+      const uint64_t kdesc0 = make_smem_desc_sw128(sK(0), 16, 1024);
+      const uint64_t kdesc1 = make_smem_desc_sw128(sK(1), 16, 1024);
+      const uint64_t vdesc0 = make_smem_desc_sw128(sV(0), 1024, 1024);
+      const uint64_t vdesc1 = make_smem_desc_sw128(sV(1), 1024, 1024);
+      const uint64_t pdesc0 = make_smem_desc_sw128(sP, 16, 1024);
+      const uint64_t pdesc1 = make_smem_desc_sw128(sP + ATT_TILE_BYTES, 16, 1024);
       auto issue_S = [&](int j) {
-        const uint64_t kdesc = make_smem_desc_sw128(sK(j & 1), 16, 1024);
+        const uint64_t kdesc = (j & 1) ? kdesc1 : kdesc0;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_S, qdesc + uint64_t(2 * k), kdesc + uint64_t(2 * k), idesc_s, k != 0);
@@ -251,13 +260,14 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         }
         mbar_wait(p_full, j & 1u, 16);  // P(j) in smem (and O rescaled if the running max moved)
         tc_fence_after();
+        const uint64_t vdesc = s ? vdesc1 : vdesc0;
+        const uint32_t acc0 = j != 0 ? 1u : 0u;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t pdesc =
-              make_smem_desc_sw128(sP + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024);
-          const uint64_t vdesc = make_smem_desc_sw128(sV(s) + kk * 2048, 1024, 1024);
-          umma_bf16_ss(tmem_O, pdesc, vdesc, idesc_o, (j | kk) != 0 ? 1u : 0u);
-          umma_bf16_ss(tmem_L, pdesc, onesdesc, idesc_l, (j | kk) != 0 ? 1u : 0u);
+          // P: 16 keys = 32 bytes inside the 128 B swizzle span (>>4 = 2); V: 16 key rows = 2048 bytes (>>4 = 128)
+          const uint64_t pdesc = (kk < 4 ? pdesc0 : pdesc1) + uint64_t(2 * (kk & 3));
+          umma_bf16_ss(tmem_O, pdesc, vdesc + uint64_t(128 * kk), idesc_o, kk != 0 ? 1u : acc0);
+          umma_bf16_ss(tmem_L, pdesc, onesdesc, idesc_l, kk != 0 ? 1u : acc0);
         }
         umma_commit(o_full);
         umma_commit(kv_empty(s));
@@ -287,19 +297,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       tc_fence_after();
       const bool tr = threadIdx.x == 64 && (j == 2 || j == 3);
       if (tr) ATT_STAMP(1 + 6 * (j - 2));
-      // ---- pass 1: row maximum over the valid keys ----
+      // ---- pass 1: row maximum over the valid keys (the last 32-key chunk stays in registers for pass 2) ----
       float mx = -INFINITY;
+      uint32_t vlast[32];
 #pragma unroll
       for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + c0, v);
+        if (c0 < ATT_TILE - 32) {
+          tmem_ld_32x32(tmem_S + lane_off + c0, v);
+        } else {
+          tmem_ld_32x32(tmem_S + lane_off + c0, vlast);
+        }
         tmem_wait_ld();
+        const uint32_t(&u)[32] = (c0 < ATT_TILE - 32) ? v : vlast;
         if (full_tile || c0 + 32 <= n_valid) {
-          mx = fmaxf(mx, max32(v));
+          mx = fmaxf(mx, max32(u));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(u[i]));
         }
       }
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
@@ -337,18 +353,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
       const float mcb = mc - ATT_P_EXP_BIAS;
 #pragma unroll
-      for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
+      for (int c0 = 0; c0 < ATT_TILE - 32; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_S + lane_off + c0, v);
         tmem_wait_ld();
-        if (c0 == ATT_TILE - 32) {
-          // last read of S(j): let the MMA thread start Q K^T of the next tile under the rest of this pass
+        if (c0 == ATT_TILE - 64) {
+          // last TMEM read of S(j) (the final chunk is still in registers from pass 1): let the MMA thread start
+          // Q K^T of the next tile under the remaining half of this pass
           tc_fence_before();
           mbar_arrive(s_free);
         }
         if (full_tile) softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw);
         else softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
       }
+      if (full_tile) softmax_chunk<false>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
+      else softmax_chunk<true>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
       if (tr) ATT_STAMP(4 + 6 * (j - 2));
       fence_proxy_async_smem();
       tc_fence_before();
