@@ -179,7 +179,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const uint32_t s_free = bar_base + 8u * 6;   // softmax -> MMA: S(j) has been read (128 arrivals)
   const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (128 arrivals)
   const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes P(j) V(j)
-  const uint32_t tmem_slot = bar_base + 8u * 9;
+  const uint32_t p0_free = bar_base + 8u * 9;  // MMA -> softmax: P V has consumed the first 64-key slab of P(j)
+  const uint32_t tmem_slot = bar_base + 8u * 10;
   const uint32_t sOnes = bar_base + 128;
 
   if (threadIdx.x == 0) {
@@ -190,6 +191,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     mbar_init(s_free, 128);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
+    mbar_init(p0_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -268,6 +270,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           const uint64_t pdesc = (kk < 4 ? pdesc0 : pdesc1) + uint64_t(2 * (kk & 3));
           umma_bf16_ss(tmem_O, pdesc, vdesc + uint64_t(128 * kk), idesc_o, kk != 0 ? 1u : acc0);
           umma_bf16_ss(tmem_L, pdesc, onesdesc, idesc_l, kk != 0 ? 1u : acc0);
+          // the accumulating MMAs form a latency-bound dependent chain (~130 cycles each): hand the first P slab
+          // back to the softmax threads as soon as its four k-steps have retired
+          if (kk == 3) umma_commit(p0_free);
         }
         umma_commit(o_full);
         umma_commit(kv_empty(s));
@@ -322,32 +327,33 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       const float mxc = mx * c;
       const bool need = mxc > mc + ATT_RESCALE_LOG2;
       if (tr) ATT_STAMP(2 + 6 * (j - 2));
-      if (j > 0) {
-        // P(j-1) V(j-1) must have been folded into O before P is overwritten / O is rescaled
+      bool o_done = (j == 0);
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // rare: P(j-1) V(j-1) must be folded into O before O and l are rescaled
         mbar_wait(o_full, (j - 1) & 1u, 18);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          const float f = need ? ex2_approx(mc - mxc) : 1.0f;
+        o_done = true;
+        const float f = need ? ex2_approx(mc - mxc) : 1.0f;
 #pragma unroll
-          for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_O + lane_off + c0, v);
-            tmem_wait_ld();
+        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_O + lane_off + c0, v);
+          tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st_32x32(tmem_O + lane_off + c0, v);
-          }
-          {
-            uint32_t v[16];
-            tmem_ld_32x16(tmem_L + lane_off, v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st_32x16(tmem_L + lane_off, v);
-          }
-          tmem_wait_st();
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st_32x32(tmem_O + lane_off + c0, v);
         }
+        {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_L + lane_off, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st_32x16(tmem_L + lane_off, v);
+        }
+        tmem_wait_st();
       }
+      if (j > 0 && !o_done) mbar_wait(p0_free, (j - 1) & 1u, 20);  // first P slab may be overwritten
       if (need) mc = mxc;
       if (tr) ATT_STAMP(3 + 6 * (j - 2));
       // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
@@ -362,6 +368,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           // Q K^T of the next tile under the remaining half of this pass
           tc_fence_before();
           mbar_arrive(s_free);
+        }
+        if (c0 == 64 && !o_done) {
+          mbar_wait(o_full, (j - 1) & 1u, 18);  // second P slab: all of P(j-1) V(j-1) has retired
+          o_done = true;
         }
         if (full_tile) softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw);
         else softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
