@@ -8,8 +8,10 @@
 //                 SW128 K-major smem tile)
 //   O += P V    : tcgen05.mma (f16 x f16) M=128 N=64 K=128 accumulating IN TMEM (cols [128,192)), V tile as
 //                 MN-major B; V is written as f16 by the QKV GEMM epilogue.
-//   l += P 1    : the softmax denominator comes from the tensor core too: P times a constant all-ones tile
-//                 (M=128 N=16) into TMEM cols [192,208) — no row sums on the CUDA cores.
+//   l           : row sums of the (fp32) probabilities on the CUDA cores. A tensor-core version (P times an
+//                 all-ones tile, M=128 N=16) was measured slower: every tcgen05.mma of the dependent accumulate
+//                 chain costs ~65 cycles to issue and ~110 to retire whatever its N, and that chain
+//                 (p_full -> P V -> o_full) is the per-tile critical loop.
 //
 // The kernel is MUFU (exp2) bound, so everything else is kept off the softmax threads:
 //   * O stays in TMEM for the whole KV loop. The running maximum is only raised when a tile exceeds it by
@@ -102,9 +104,10 @@ __device__ __forceinline__ float exp2_poly(float x) {
 // exp2 + swizzled store of one 32-key chunk of a P row. x = s*c - (m*c - 7); results are packed to the f16 P tile.
 // MASKED: keys >= n_valid get probability 0.
 template <bool MASKED>
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int c0,
-                                              const int n_valid, const uint32_t prow, const uint32_t sw) {
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int c0,
+                                               const int n_valid, const uint32_t prow, const uint32_t sw) {
   uint32_t pk[16];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float x0 = fmaf(__uint_as_float(v[i]), c, -mcb);
@@ -122,6 +125,7 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const flo
       if (c0 + i + 2 >= n_valid) p2 = 0.f;
       if (c0 + i + 3 >= n_valid) p3 = 0.f;
     }
+    s0 += p0; s1 += p1; s2 += p2; s3 += p3;
     __half2 a = __floats2half2_rn(p0, p1), b = __floats2half2_rn(p2, p3);
     pk[i / 2] = *reinterpret_cast<uint32_t*>(&a);
     pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&b);
@@ -135,6 +139,7 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const flo
                  "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
                  : "memory");
   }
+  return (s0 + s1) + (s2 + s3);
 }
 
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
@@ -181,7 +186,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes P(j) V(j)
   const uint32_t p0_free = bar_base + 8u * 9;  // MMA -> softmax: P V has consumed the first 64-key slab of P(j)
   const uint32_t tmem_slot = bar_base + 8u * 10;
-  const uint32_t sOnes = bar_base + 128;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -198,10 +202,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 64) {  // constant all-ones B operand of the denominator MMA (f16 1.0 = 0x3C00)
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sOnes + 4u * (threadIdx.x - 64)), "r"(0x3C003C00u) : "memory");
-    fence_proxy_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -209,7 +209,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
-  const uint32_t tmem_L = tmem_base + 192;
   pdl_wait();  // the QKV activations of the previous kernel are visible from here on
   if (threadIdx.x == 0) ATT_STAMP(0);
 
@@ -230,10 +229,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_f16(128, 64, 0, 1);  // f16 P x f16 V, B = V is MN-major
-      constexpr uint32_t idesc_l = make_idesc_f16(128, 16, 0, 0);  // f16 P x ones
       // all shared-memory descriptors are loop invariant (two K/V stages): build them once so that the single
       // issuing thread spends its time on tcgen05.mma, not on address arithmetic
-      const uint64_t onesdesc = make_smem_desc_noswz(sOnes, 128, 256);
       const uint64_t qdesc = make_smem_desc_sw128(sQ, 16, 1024);
       const uint64_t kdesc0 = make_smem_desc_sw128(sK(0), 16, 1024);
       const uint64_t kdesc1 = make_smem_desc_sw128(sK(1), 16, 1024);
@@ -262,6 +259,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         }
         mbar_wait(p_full, j & 1u, 16);  // P(j) in smem (and O rescaled if the running max moved)
         tc_fence_after();
+        if (j == 2) ATT_STAMP(12);
         const uint64_t vdesc = s ? vdesc1 : vdesc0;
         const uint32_t acc0 = j != 0 ? 1u : 0u;
 #pragma unroll
@@ -269,13 +267,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           // P: 16 keys = 32 bytes inside the 128 B swizzle span (>>4 = 2); V: 16 key rows = 2048 bytes (>>4 = 128)
           const uint64_t pdesc = (kk < 4 ? pdesc0 : pdesc1) + uint64_t(2 * (kk & 3));
           umma_bf16_ss(tmem_O, pdesc, vdesc + uint64_t(128 * kk), idesc_o, kk != 0 ? 1u : acc0);
-          umma_bf16_ss(tmem_L, pdesc, onesdesc, idesc_l, kk != 0 ? 1u : acc0);
           // the accumulating MMAs form a latency-bound dependent chain (~130 cycles each): hand the first P slab
           // back to the softmax threads as soon as its four k-steps have retired
           if (kk == 3) umma_commit(p0_free);
         }
         umma_commit(o_full);
         umma_commit(kv_empty(s));
+        if (j == 2) ATT_STAMP(13);
       }
     }
   } else {
@@ -285,6 +283,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const float c = args.scale_log2;
     float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8
+    float l_run = 0.f;     // softmax denominator in the same (stale-max, 2^7-biased) scale as O
     const uint32_t prow = sP + r * 128;
     const uint32_t sw = uint32_t(r & 7);
     // Two CTAs share an SM and would otherwise run in lockstep (same start, same period), hitting the MUFU
@@ -343,14 +342,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
           tmem_st_32x32(tmem_O + lane_off + c0, v);
         }
-        {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem_L + lane_off, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-          tmem_st_32x16(tmem_L + lane_off, v);
-        }
+        l_run *= f;
         tmem_wait_st();
       }
       if (j > 0 && !o_done) mbar_wait(p0_free, (j - 1) & 1u, 20);  // first P slab may be overwritten
@@ -372,12 +364,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         if (c0 == 64 && !o_done) {
           mbar_wait(o_full, (j - 1) & 1u, 18);  // second P slab: all of P(j-1) V(j-1) has retired
           o_done = true;
+          if (threadIdx.x == 64 && j == 3) ATT_STAMP(6);
         }
-        if (full_tile) softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw);
-        else softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
+        l_run += full_tile ? softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw)
+                           : softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
       }
-      if (full_tile) softmax_chunk<false>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
-      else softmax_chunk<true>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
+      l_run += full_tile ? softmax_chunk<false>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw)
+                         : softmax_chunk<true>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
       if (tr) ATT_STAMP(4 + 6 * (j - 2));
       fence_proxy_async_smem();
       tc_fence_before();
@@ -387,13 +380,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     // ---- epilogue: O / l ----
     mbar_wait(o_full, (n_kv - 1) & 1u, 19);
     tc_fence_after();
-    float inv_l;
-    {
-      uint32_t v[16];
-      tmem_ld_32x16(tmem_L + lane_off, v);
-      tmem_wait_ld();
-      inv_l = 1.0f / __uint_as_float(v[0]);
-    }
+    const float inv_l = 1.0f / l_run;
     const int t = q0 + r;
     __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D;
 #pragma unroll

@@ -21,7 +21,7 @@ fn(); torch.cuda.synchronize()
 L.lib().oron_debug_set_attention_stamps(None)
 d = dbg.cpu()
 names = {1: "t2 s_full", 2: "t2 pass1", 3: "t2 o_wait", 4: "t2 pass2", 5: "t2 arrive", 7: "t3 s_full", 8: "t3 pass1", 9: "t3 o_wait", 10: "t3 pass2",
-         11: "t3 arrive", 14: "softmax end", 15: "cta end"}
+         11: "t3 arrive", 6: "t3 o_full(2) seen", 12: "mma: p_full(2)", 13: "mma: PV(2) issued", 14: "softmax end", 15: "cta end"}
 starts = d[:, 0]
 print("global start spread (cycles are per-SM clocks; only relative values inside a CTA are meaningful)")
 for cta in (0, 1, 100, 300, 351):
