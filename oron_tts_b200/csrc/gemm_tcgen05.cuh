@@ -633,28 +633,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  // Everything above overlapped the previous kernel's tail. The weights (B operand) do not depend on the previous
-  // kernel either, so the TMA producer thread first fills the pipeline with weight tiles (hiding their HBM latency:
-  // the 856 MB of weights never stay in L2 across an NFE) and only then waits for the upstream activations.
-  if (threadIdx.x != 0) pdl_wait();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   if (threadIdx.x == 0) ORON_STAMP(0);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // weight tiles of the first k-blocks of the first tile, issued before the PDL wait
-      int prefilled = 0;
-      if (pair_id < num_tiles) {
-        const int n0 = (pair_id / tiles_mp) * BN;
-        prefilled = num_kb < kStages ? num_kb : kStages;
-        for (int kb = 0; kb < prefilled; ++kb) {
-          if (leader) mbar_arrive_expect_tx(full_bar(kb), 2 * Cfg::kStageBytes);
-          tma_load_2d_2sm(smem_base + kb * Cfg::kStageBytes + Cfg::kABytes, &tmB, full_bar(kb), kb * GEMM_BK,
-                          n0 + rank * (BN / 2));
-        }
-      }
-      pdl_wait();
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
         const int m_tile = 2 * (tile % tiles_mp) + rank;
         const int n_tile = tile / tiles_mp;
@@ -662,17 +647,14 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         const int t0 = (m_tile % tiles_m_pb) * GEMM_BM;
         const int n0 = n_tile * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const bool pre = (tile == pair_id) && (kb < prefilled);  // B already in flight, barrier already armed
-          if (!pre) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, 21);
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          }
+          mbar_wait(empty_bar(stage), phase ^ 1u, 21);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const int a_col = (args.grouped ? (n0 / args.grouped) * args.grouped : 0) + (kb % args.cpb) * GEMM_BK;
           const int a_row = t0 + kb / args.cpb - args.pad;
           tma_load_3d_2sm(sa, &tmA, full_bar(stage), a_col, a_row, b);
-          if (!pre) tma_load_2d_2sm(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0 + rank * (BN / 2));
+          tma_load_2d_2sm(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0 + rank * (BN / 2));
           if (kb == 0 && tile == pair_id) ORON_STAMP(1);
           if (kb == num_kb - 1 && tile == pair_id) ORON_STAMP(2);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
