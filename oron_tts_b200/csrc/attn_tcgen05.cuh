@@ -3,22 +3,23 @@
 // One CTA = one (batch element, head, 128-query tile); two CTAs per SM. head_dim = 64.
 //
 //   S = Q K^T   : tcgen05.mma M=128 N=128 K=64 -> TMEM cols [0,128)
-//   P = softmax : 128 softmax threads, one query row each (TMEM lane == row => no shuffles), two passes over
-//                 TMEM (row max, then packed f16x2 exp2 — two probabilities per MUFU op — stored as an f16
-//                 SW128 K-major smem tile)
+//   P = softmax : 256 softmax threads = two per query row (TMEM lane == row => no shuffles); warps 2..5 own the
+//                 first 64 keys of a tile, warps 6..9 the last 64. Each thread reads its 64 scores ONCE into
+//                 registers, the two halves exchange their row maxima through 512 B of smem, and the
+//                 probabilities (exp2, f16) go to the 64-key SW128 slab of P that belongs to the half.
 //   O += P V    : tcgen05.mma (f16 x f16) M=128 N=64 K=128 accumulating IN TMEM (cols [128,192)), V tile as
 //                 MN-major B; V is written as f16 by the QKV GEMM epilogue.
-//   l           : row sums of the (fp32) probabilities on the CUDA cores. A tensor-core version (P times an
-//                 all-ones tile, M=128 N=16) was measured slower: every tcgen05.mma of the dependent accumulate
-//                 chain costs ~65 cycles to issue and ~110 to retire whatever its N, and that chain
-//                 (p_full -> P V -> o_full) is the per-tile critical loop.
 //
-// The kernel is MUFU (exp2) bound, so everything else is kept off the softmax threads:
-//   * O stays in TMEM for the whole KV loop. The running maximum is only raised when a tile exceeds it by
-//     more than 2^8 ("lazy rescale": p <= 256 is exact enough in bf16/fp32); only then O is read back,
-//     scaled and stored again — a warp-uniform, rare branch.
-//   * S is released to the MMA thread as soon as the last TMEM read of pass 2 has landed, so Q K^T of the
-//     next tile runs under the exp/pack/store tail of this one.
+// What the per-CTA clock64 traces (tools/attn_trace.py, profiles/r01_attn_trace_*.txt) showed, in order:
+//   * O and its rescaling belong on the tensor core / in TMEM: the running maximum is only raised when a tile
+//     exceeds it by more than 2^8 ("lazy rescale"); only then O is read back, scaled and stored (warp-uniform,
+//     rare). Probabilities carry a 2^7 bias so they use the f16 range; it cancels in O / l.
+//   * every tcgen05.mma of a dependent accumulate chain costs ~65-80 cycles to issue and ~110 to retire
+//     whatever its N, so the chain p_full -> P V -> o_full is a per-tile critical loop: the first P slab is
+//     handed back after four k-steps (p0_free), and a tensor-core row sum (P x ones) was dropped again.
+//   * one softmax warp per scheduler is instruction-latency bound (IPC ~0.3); replacing exp2 by a polynomial
+//     on the FMA pipe made it slower. Hence two warps per row quarter, a single pass over TMEM, and S released
+//     to the MMA thread right after that read so Q K^T of the next tile runs under the whole exp phase.
 // q/k/v are read straight out of the fused QKV activation [rows, 3*H*64] with one 3-D TMA map.
 #pragma once
 #include <cuda_fp16.h>
@@ -38,20 +39,17 @@ struct AttnArgs {
   long long* dbg;       // optional [grid, 16] clock64 stamps (tools/attn_trace.py); nullptr in production
 };
 
-constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 softmax
+constexpr int ATT_THREADS = 320;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..9 softmax
+constexpr int ATT_SOFTMAX_THREADS = 256;
 constexpr int ATT_TILE = 128;
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB
-// smem: Q | K0 K1 | V0 V1 | P(2 slabs) | barriers
-constexpr int ATT_ONES_BYTES = 512;  // [16 x 16] f16 ones, no-swizzle K-major core matrices
-constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_ONES_BYTES;
+constexpr int ATT_XCH_BYTES = 512;                    // row-max / row-sum exchange between the two key halves
+// smem: Q | K0 K1 | V0 V1 | P(2 slabs) | barriers | exchange
+constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_XCH_BYTES;
 constexpr int ATT_TMEM_COLS = 256;
 #define ATT_STAMP(slot) do { if (args.dbg) args.dbg[(long long)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
-#ifndef ATT_STAGGER_NS
-#define ATT_STAGGER_NS 700
-#endif
-constexpr unsigned ATT_STAGGER_WAVE = 148;  // CTAs are dealt round-robin over the SMs: lin and lin+148 are co-resident
 constexpr float ATT_P_EXP_BIAS = 7.0f;    // probabilities are scaled by 2^7 (<= 2^15 in f16); cancels in O / l
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -69,28 +67,8 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 magic constant,
-// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 7.5e-5 — f16 resolution is 4.9e-4), and
-// n added straight into the exponent field. Valid for -125 <= x < 2^22.
+// 2^x on the FMA/ALU pipes (kept for reference; measured slower than MUFU here, see header).
 __device__ __forceinline__ float exp2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float t = x + 12582912.0f;
@@ -101,40 +79,36 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-// exp2 + swizzled store of one 32-key chunk of a P row. x = s*c - (m*c - 7); results are packed to the f16 P tile.
-// MASKED: keys >= n_valid get probability 0.
+// exp2 + swizzled store of one 32-key chunk of a P row; returns the chunk's row sum (fp32).
+// x = s*c - (m*c - 7); results are packed to the f16 P tile. `cslab`: key offset inside the 64-key slab (0 / 32),
+// `kglob`: key offset inside the tile (for masking). MASKED: keys >= n_valid get probability 0.
 template <bool MASKED>
-__device__ __forceinline__ float softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int c0,
-                                               const int n_valid, const uint32_t prow, const uint32_t sw) {
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&v)[32], const float c, const float mcb, const int cslab,
+                                               const int kglob, const int n_valid, const uint32_t prow_slab,
+                                               const uint32_t sw) {
   uint32_t pk[16];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    const float x0 = fmaf(__uint_as_float(v[i]), c, -mcb);
-    const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -mcb);
-    const float x2 = fmaf(__uint_as_float(v[i + 2]), c, -mcb);
-    const float x3 = fmaf(__uint_as_float(v[i + 3]), c, -mcb);
-    // all four through the exp2 unit: replacing half of them by exp2_poly (FMA pipe) was measured SLOWER
-    // (pass 2: 1.7k -> 2.4k cycles per tile): with one softmax warp per scheduler the loop is bound by the
-    // instruction count, not by MUFU throughput.
-    float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-    float p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+    float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c, -mcb));
+    float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mcb));
+    float p2 = ex2_approx(fmaf(__uint_as_float(v[i + 2]), c, -mcb));
+    float p3 = ex2_approx(fmaf(__uint_as_float(v[i + 3]), c, -mcb));
     if (MASKED) {
-      if (c0 + i >= n_valid) p0 = 0.f;
-      if (c0 + i + 1 >= n_valid) p1 = 0.f;
-      if (c0 + i + 2 >= n_valid) p2 = 0.f;
-      if (c0 + i + 3 >= n_valid) p3 = 0.f;
+      if (kglob + i >= n_valid) p0 = 0.f;
+      if (kglob + i + 1 >= n_valid) p1 = 0.f;
+      if (kglob + i + 2 >= n_valid) p2 = 0.f;
+      if (kglob + i + 3 >= n_valid) p3 = 0.f;
     }
     s0 += p0; s1 += p1; s2 += p2; s3 += p3;
     __half2 a = __floats2half2_rn(p0, p1), b = __floats2half2_rn(p2, p3);
     pk[i / 2] = *reinterpret_cast<uint32_t*>(&a);
     pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&b);
   }
-  const uint32_t slab = prow + (c0 >> 6) * ATT_TILE_BYTES;
-  const uint32_t chunk0 = uint32_t(c0 & 63) >> 3;  // first 16-byte chunk of this 32-key group inside its slab row
+  const uint32_t chunk0 = uint32_t(cslab) >> 3;  // first 16-byte chunk of this 32-key group inside its slab row
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint32_t addr = slab + (((chunk0 + g) ^ sw) << 4);
+    const uint32_t addr = prow_slab + (((chunk0 + g) ^ sw) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]), "r"(pk[4 * g + 1]),
                  "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
                  : "memory");
@@ -152,6 +126,16 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
     m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], int k0, int n_valid) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (k0 + i < n_valid) m = fmaxf(m, __uint_as_float(v[i]));
+  return m;
+}
+__device__ __forceinline__ void softmax_bar_sync() {  // named barrier 1: the 256 softmax threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -181,19 +165,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (3 + s); };
   const uint32_t s_full = bar_base + 8u * 5;   // MMA -> softmax: S(j) is in TMEM
-  const uint32_t s_free = bar_base + 8u * 6;   // softmax -> MMA: S(j) has been read (128 arrivals)
-  const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (128 arrivals)
-  const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes P(j) V(j)
+  const uint32_t s_free = bar_base + 8u * 6;   // softmax -> MMA: S(j) has been read (256 arrivals)
+  const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (256 arrivals)
+  const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes all of P(j) V(j)
   const uint32_t p0_free = bar_base + 8u * 9;  // MMA -> softmax: P V has consumed the first 64-key slab of P(j)
   const uint32_t tmem_slot = bar_base + 8u * 10;
+  const uint32_t sXch = bar_base + 128;        // [2 halves][128 rows] bf16 row maxima (reused for f32 sums at the end)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, ATT_SOFTMAX_THREADS);
+    mbar_init(p_full, ATT_SOFTMAX_THREADS);
     mbar_init(o_full, 1);
     mbar_init(p0_free, 1);
     fence_mbar_init();
@@ -252,7 +237,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         if (j + 1 < n_kv) {
-          mbar_wait(s_free, j & 1u, 14);  // S(j) fully read: the S columns may be overwritten
+          mbar_wait(s_free, j & 1u, 14);  // S(j) is in registers: the S columns may be overwritten
           mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1u, 15);
           tc_fence_after();
           issue_S(j + 1);
@@ -267,9 +252,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           // P: 16 keys = 32 bytes inside the 128 B swizzle span (>>4 = 2); V: 16 key rows = 2048 bytes (>>4 = 128)
           const uint64_t pdesc = (kk < 4 ? pdesc0 : pdesc1) + uint64_t(2 * (kk & 3));
           umma_bf16_ss(tmem_O, pdesc, vdesc + uint64_t(128 * kk), idesc_o, kk != 0 ? 1u : acc0);
-          // the accumulating MMAs form a latency-bound dependent chain (~130 cycles each): hand the first P slab
-          // back to the softmax threads as soon as its four k-steps have retired
-          if (kk == 3) umma_commit(p0_free);
+          if (kk == 3) umma_commit(p0_free);  // first P slab back to its softmax warps
         }
         umma_commit(o_full);
         umma_commit(kv_empty(s));
@@ -277,22 +260,19 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       }
     }
   } else {
-    // ===================== softmax threads =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
+    // ===================== softmax threads: two per query row =====================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int half = (warp - 2) >> 2;       // 0: keys [0,64) of every tile, 1: keys [64,128)
+    const int r = q * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const float c = args.scale_log2;
-    float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8
-    float l_run = 0.f;     // softmax denominator in the same (stale-max, 2^7-biased) scale as O
-    const uint32_t prow = sP + r * 128;
+    float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8; identical in both halves
+    float l_run = 0.f;     // this half's share of the softmax denominator (same stale-max, 2^7-biased scale as O)
+    const uint32_t prow_slab = sP + half * ATT_TILE_BYTES + r * 128;
     const uint32_t sw = uint32_t(r & 7);
-    // Two CTAs share an SM and would otherwise run in lockstep (same start, same period), hitting the MUFU
-    // pipe at the same time and idling it together. Start every second wave of CTAs half a tile late so that
-    // one CTA's exp phase overlaps the other's max / wait phases.
-    {
-      const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      if ((lin / ATT_STAGGER_WAVE) & 1u) __nanosleep(ATT_STAGGER_NS);
-    }
+    const uint32_t xch_mine = sXch + uint32_t(half * 128 + r) * 2u;
+    const uint32_t xch_other = sXch + uint32_t((half ^ 1) * 128 + r) * 2u;
+    const int k0 = half * 64;               // first key of this half inside a tile
 
     for (int j = 0; j < n_kv; ++j) {
       const int n_valid = min(ATT_TILE, len - j * ATT_TILE);
@@ -301,99 +281,100 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       tc_fence_after();
       const bool tr = threadIdx.x == 64 && (j == 2 || j == 3);
       if (tr) ATT_STAMP(1 + 6 * (j - 2));
-      // ---- pass 1: row maximum over the valid keys (the last 32-key chunk stays in registers for pass 2) ----
-      float mx = -INFINITY;
-      uint32_t vlast[32];
-#pragma unroll
-      for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
-        uint32_t v[32];
-        if (c0 < ATT_TILE - 32) {
-          tmem_ld_32x32(tmem_S + lane_off + c0, v);
-        } else {
-          tmem_ld_32x32(tmem_S + lane_off + c0, vlast);
-        }
-        tmem_wait_ld();
-        const uint32_t(&u)[32] = (c0 < ATT_TILE - 32) ? v : vlast;
-        if (full_tile || c0 + 32 <= n_valid) {
-          mx = fmaxf(mx, max32(u));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(u[i]));
-        }
+      // ---- single read of this half's 64 scores; S is released right away ----
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(tmem_S + lane_off + k0, va);
+      tmem_ld_32x32(tmem_S + lane_off + k0 + 32, vb);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);
+      float mx = full_tile ? fmaxf(max32(va), max32(vb))
+                           : fmaxf(max32_masked(va, k0, n_valid), max32_masked(vb, k0 + 32, n_valid));
+      // ---- exchange the row maximum with the other key half (bf16-truncated so both sides agree bit for bit) ----
+      {
+        const uint16_t mine = uint16_t(__float_as_uint(mx) >> 16);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(xch_mine), "h"(mine) : "memory");
+        softmax_bar_sync();
+        uint16_t other;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other) : "r"(xch_other) : "memory");
+        softmax_bar_sync();  // the slot may be rewritten for the next tile only after everybody has read it
+        // truncation rounds towards zero: for negative maxima that is an over-estimate, for positive ones an
+        // under-estimate of at most 2^-7 relative — irrelevant next to the 2^8 lazy-rescale slack
+        mx = fmaxf(__uint_as_float(uint32_t(mine) << 16), __uint_as_float(uint32_t(other) << 16));
       }
+      if (tr) ATT_STAMP(2 + 6 * (j - 2));
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const float mxc = mx * c;
       const bool need = mxc > mc + ATT_RESCALE_LOG2;
-      if (tr) ATT_STAMP(2 + 6 * (j - 2));
       bool o_done = (j == 0);
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: P(j-1) V(j-1) must be folded into O before O and l are rescaled
+        // rare: P(j-1) V(j-1) must be folded into O before O is rescaled; each half scales 32 of the 64 columns
         mbar_wait(o_full, (j - 1) & 1u, 18);
         tc_fence_after();
         o_done = true;
         const float f = need ? ex2_approx(mc - mxc) : 1.0f;
-#pragma unroll
-        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_O + lane_off + c0, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-          tmem_st_32x32(tmem_O + lane_off + c0, v);
-        }
-        l_run *= f;
-        tmem_wait_st();
-      }
-      if (j > 0 && !o_done) mbar_wait(p0_free, (j - 1) & 1u, 20);  // first P slab may be overwritten
-      if (need) mc = mxc;
-      if (tr) ATT_STAMP(3 + 6 * (j - 2));
-      // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
-      const float mcb = mc - ATT_P_EXP_BIAS;
-#pragma unroll
-      for (int c0 = 0; c0 < ATT_TILE - 32; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + c0, v);
+        tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
         tmem_wait_ld();
-        if (c0 == ATT_TILE - 64) {
-          // last TMEM read of S(j) (the final chunk is still in registers from pass 1): let the MMA thread start
-          // Q K^T of the next tile under the remaining half of this pass
-          tc_fence_before();
-          mbar_arrive(s_free);
-        }
-        if (c0 == 64 && !o_done) {
-          mbar_wait(o_full, (j - 1) & 1u, 18);  // second P slab: all of P(j-1) V(j-1) has retired
-          o_done = true;
-          if (threadIdx.x == 64 && j == 3) ATT_STAMP(6);
-        }
-        l_run += full_tile ? softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw)
-                           : softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+        tmem_st_32x32(tmem_O + lane_off + half * 32, v);
+        tmem_wait_st();
+        l_run *= f;
       }
-      l_run += full_tile ? softmax_chunk<false>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw)
-                         : softmax_chunk<true>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
+      if (need) mc = mxc;
+      // the half's P slab must have been consumed by P(j-1) V(j-1): slab 0 after four k-steps, slab 1 after all eight
+      if (!o_done) {
+        if (half == 0) mbar_wait(p0_free, (j - 1) & 1u, 20);
+        else mbar_wait(o_full, (j - 1) & 1u, 18);
+      }
+      if (tr) ATT_STAMP(3 + 6 * (j - 2));
+      // ---- P = 2^7 * exp2(S*c - m) -> f16 -> this half's 64-key slab (SW128 K-major) ----
+      const float mcb = mc - ATT_P_EXP_BIAS;
+      if (full_tile) {
+        l_run += softmax_chunk<false>(va, c, mcb, 0, k0, n_valid, prow_slab, sw);
+        l_run += softmax_chunk<false>(vb, c, mcb, 32, k0 + 32, n_valid, prow_slab, sw);
+      } else {
+        l_run += softmax_chunk<true>(va, c, mcb, 0, k0, n_valid, prow_slab, sw);
+        l_run += softmax_chunk<true>(vb, c, mcb, 32, k0 + 32, n_valid, prow_slab, sw);
+      }
       if (tr) ATT_STAMP(4 + 6 * (j - 2));
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
       if (tr) ATT_STAMP(5 + 6 * (j - 2));
     }
-    // ---- epilogue: O / l ----
+    // ---- epilogue: O / (l_half0 + l_half1); each half stores 32 of the 64 output columns ----
     mbar_wait(o_full, (n_kv - 1) & 1u, 19);
     tc_fence_after();
+    {
+      // 128 rows x 2 halves x f32 = 1 KB does not fit the 512 B buffer: exchange in two rounds of 64 rows
+      float l_other = 0.f;
+#pragma unroll
+      for (int round = 0; round < 2; ++round) {
+        const bool mine_now = (r >> 6) == round;
+        const uint32_t slot = sXch + uint32_t(half * 64 + (r & 63)) * 4u;
+        const uint32_t slot_o = sXch + uint32_t((half ^ 1) * 64 + (r & 63)) * 4u;
+        softmax_bar_sync();
+        if (mine_now) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(l_run) : "memory");
+        softmax_bar_sync();
+        if (mine_now) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(slot_o) : "memory");
+      }
+      l_run += l_other;
+    }
     const float inv_l = 1.0f / l_run;
     const int t = q0 + r;
-    __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D;
-#pragma unroll
-    for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+    __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D + half * 32;
+    {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_O + lane_off + c0, v);
+      tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
       tmem_wait_ld();
       if (t < args.rows_per_batch) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2)
           pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+        uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
         for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
