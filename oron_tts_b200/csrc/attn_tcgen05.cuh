@@ -3,12 +3,15 @@
 // One CTA = one (batch element, head, 128-query tile); two CTAs per SM. head_dim = 64.
 //
 //   S = Q K^T   : tcgen05.mma M=128 N=128 K=64 -> TMEM cols [0,128)
-//   P = softmax : 256 softmax threads = two per query row (TMEM lane == row => no shuffles); warps 2..5 own the
-//                 first 64 keys of a tile, warps 6..9 the last 64. Each thread reads its 64 scores ONCE into
-//                 registers, the two halves exchange their row maxima through 512 B of smem, and the
-//                 probabilities (exp2, f16) go to the 64-key SW128 slab of P that belongs to the half.
-//   O += P V    : tcgen05.mma (f16 x f16) M=128 N=64 K=128 accumulating IN TMEM (cols [128,192)), V tile as
-//                 MN-major B; V is written as f16 by the QKV GEMM epilogue.
+//   P = softmax : 256 softmax threads = two per query row (TMEM lane == row => no shuffles); warps 2..5 ("half A")
+//                 own the first 64 keys of every tile, warps 6..9 ("half B") the last 64. The halves are fully
+//                 independent online softmaxes — own running maximum, own denominator, own 64-key SW128 slab
+//                 of P, own accumulator — and are merged once, after the KV loop (flash-decoding style split,
+//                 but inside the CTA, so no extra memory traffic). No per-tile exchange between the halves: a
+//                 per-tile row-max exchange through a named barrier was measured at 1-2.4k cycles per tile.
+//   O_h += P_h V_h : tcgen05.mma (f16 x f16) M=128 N=64 K=64 accumulating IN TMEM (A: cols [128,192),
+//                 B: [192,256)); V tile as MN-major B operand; V is written as f16 by the QKV GEMM epilogue.
+//                 Two accumulators also halve the latency-bound dependent MMA chain.
 //
 // What the per-CTA clock64 traces (tools/attn_trace.py, profiles/r01_attn_trace_*.txt) showed, in order:
 //   * O and its rescaling belong on the tensor core / in TMEM: the running maximum is only raised when a tile
@@ -44,7 +47,7 @@ constexpr int ATT_SOFTMAX_THREADS = 256;
 constexpr int ATT_TILE = 128;
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB
-constexpr int ATT_XCH_BYTES = 512;                    // row-max / row-sum exchange between the two key halves
+constexpr int ATT_XCH_BYTES = 512;                    // (max, sum) exchange between the two key halves, once per CTA
 // smem: Q | K0 K1 | V0 V1 | P(2 slabs) | barriers | exchange
 constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_XCH_BYTES;
 constexpr int ATT_TMEM_COLS = 256;
@@ -66,6 +69,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 
 // 2^x on the FMA/ALU pipes (kept for reference; measured slower than MUFU here, see header).
@@ -166,11 +178,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   auto kv_empty = [&](int s) { return bar_base + 8u * (3 + s); };
   const uint32_t s_full = bar_base + 8u * 5;   // MMA -> softmax: S(j) is in TMEM
   const uint32_t s_free = bar_base + 8u * 6;   // softmax -> MMA: S(j) has been read (256 arrivals)
-  const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (256 arrivals)
-  const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes all of P(j) V(j)
-  const uint32_t p0_free = bar_base + 8u * 9;  // MMA -> softmax: P V has consumed the first 64-key slab of P(j)
-  const uint32_t tmem_slot = bar_base + 8u * 10;
-  const uint32_t sXch = bar_base + 128;        // [2 halves][128 rows] bf16 row maxima (reused for f32 sums at the end)
+  auto p_full = [&](int hf) { return bar_base + 8u * (7 + hf); };   // softmax half -> MMA: its P slab is in smem (128)
+  auto o_full = [&](int hf) { return bar_base + 8u * (9 + hf); };   // MMA -> softmax half: O_h includes P_h(j) V_h(j)
+  const uint32_t tmem_slot = bar_base + 8u * 11;
+  const uint32_t sXch = bar_base + 128;        // half B -> half A: (running max, denominator) of 64 rows at a time
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -178,9 +189,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_full, 1);
     mbar_init(s_free, ATT_SOFTMAX_THREADS);
-    mbar_init(p_full, ATT_SOFTMAX_THREADS);
-    mbar_init(o_full, 1);
-    mbar_init(p0_free, 1);
+    for (int hf = 0; hf < 2; ++hf) { mbar_init(p_full(hf), ATT_SOFTMAX_THREADS / 2); mbar_init(o_full(hf), 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -193,7 +202,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 128;  // half A accumulator; half B at +64
   pdl_wait();  // the QKV activations of the previous kernel are visible from here on
   if (threadIdx.x == 0) ATT_STAMP(0);
 
@@ -242,19 +251,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           tc_fence_after();
           issue_S(j + 1);
         }
-        mbar_wait(p_full, j & 1u, 16);  // P(j) in smem (and O rescaled if the running max moved)
-        tc_fence_after();
-        if (j == 2) ATT_STAMP(12);
         const uint64_t vdesc = s ? vdesc1 : vdesc0;
         const uint32_t acc0 = j != 0 ? 1u : 0u;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // P: 16 keys = 32 bytes inside the 128 B swizzle span (>>4 = 2); V: 16 key rows = 2048 bytes (>>4 = 128)
-          const uint64_t pdesc = (kk < 4 ? pdesc0 : pdesc1) + uint64_t(2 * (kk & 3));
-          umma_bf16_ss(tmem_O, pdesc, vdesc + uint64_t(128 * kk), idesc_o, kk != 0 ? 1u : acc0);
-          if (kk == 3) umma_commit(p0_free);  // first P slab back to its softmax warps
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(p_full(hf), j & 1u, 16);  // this half's P slab is in smem (and its O rescaled if its max moved)
+          tc_fence_after();
+          if (j == 2 && hf == 0) ATT_STAMP(12);
+#pragma unroll
+          for (int kq = 0; kq < 4; ++kq) {
+            const int kk = 4 * hf + kq;
+            // P: 16 keys = 32 bytes inside the 128 B swizzle span (>>4 = 2); V: 16 key rows = 2048 bytes (>>4 = 128)
+            umma_bf16_ss(tmem_O + 64 * hf, (hf ? pdesc1 : pdesc0) + uint64_t(2 * kq), vdesc + uint64_t(128 * kk), idesc_o,
+                         kq != 0 ? 1u : acc0);
+          }
+          umma_commit(o_full(hf));
         }
-        umma_commit(o_full);
         umma_commit(kv_empty(s));
         if (j == 2) ATT_STAMP(13);
       }
@@ -266,117 +278,131 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     const int r = q * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const float c = args.scale_log2;
-    float mc = -INFINITY;  // running max (already multiplied by c), possibly stale by < 2^8; identical in both halves
-    float l_run = 0.f;     // this half's share of the softmax denominator (same stale-max, 2^7-biased scale as O)
+    float mc = -INFINITY;  // this half's running max (already multiplied by c), possibly stale by < 2^8
+    float l_run = 0.f;     // this half's denominator (same stale-max, 2^7-biased scale as its O accumulator)
     const uint32_t prow_slab = sP + half * ATT_TILE_BYTES + r * 128;
     const uint32_t sw = uint32_t(r & 7);
-    const uint32_t xch_mine = sXch + uint32_t(half * 128 + r) * 2u;
-    const uint32_t xch_other = sXch + uint32_t((half ^ 1) * 128 + r) * 2u;
     const int k0 = half * 64;               // first key of this half inside a tile
+    const uint32_t tmem_Oh = tmem_O + 64 * half;
+    const uint32_t my_p_full = p_full(half), my_o_full = o_full(half);
 
     for (int j = 0; j < n_kv; ++j) {
       const int n_valid = min(ATT_TILE, len - j * ATT_TILE);
       const bool full_tile = n_valid == ATT_TILE;  // CTA-uniform
+      const bool any_key = k0 < n_valid;           // half B of a short last tile may own no valid key at all
       mbar_wait(s_full, j & 1u, 17);
       tc_fence_after();
       const bool tr = threadIdx.x == 64 && (j == 2 || j == 3);
       if (tr) ATT_STAMP(1 + 6 * (j - 2));
-      // ---- single read of this half's 64 scores; S is released right away ----
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(tmem_S + lane_off + k0, va);
+      // ---- row maximum over this half's 64 scores (second chunk stays in registers) ----
+      uint32_t vb[32];
+      float mx;
+      {
+        uint32_t va[32];
+        tmem_ld_32x32(tmem_S + lane_off + k0, va);
+        tmem_wait_ld();
+        mx = full_tile ? max32(va) : max32_masked(va, k0, n_valid);
+      }
       tmem_ld_32x32(tmem_S + lane_off + k0 + 32, vb);
       tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(s_free);
-      float mx = full_tile ? fmaxf(max32(va), max32(vb))
-                           : fmaxf(max32_masked(va, k0, n_valid), max32_masked(vb, k0 + 32, n_valid));
-      // ---- exchange the row maximum with the other key half (bf16-truncated so both sides agree bit for bit) ----
-      {
-        const uint16_t mine = uint16_t(__float_as_uint(mx) >> 16);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(xch_mine), "h"(mine) : "memory");
-        softmax_bar_sync();
-        uint16_t other;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other) : "r"(xch_other) : "memory");
-        softmax_bar_sync();  // the slot may be rewritten for the next tile only after everybody has read it
-        // truncation rounds towards zero: for negative maxima that is an over-estimate, for positive ones an
-        // under-estimate of at most 2^-7 relative — irrelevant next to the 2^8 lazy-rescale slack
-        mx = fmaxf(__uint_as_float(uint32_t(mine) << 16), __uint_as_float(uint32_t(other) << 16));
-      }
+      mx = fmaxf(mx, full_tile ? max32(vb) : max32_masked(vb, k0 + 32, n_valid));
       if (tr) ATT_STAMP(2 + 6 * (j - 2));
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const float mxc = mx * c;
-      const bool need = mxc > mc + ATT_RESCALE_LOG2;
+      const bool need = any_key && (mxc > mc + ATT_RESCALE_LOG2);
       bool o_done = (j == 0);
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: P(j-1) V(j-1) must be folded into O before O is rescaled; each half scales 32 of the 64 columns
-        mbar_wait(o_full, (j - 1) & 1u, 18);
+        // rare: P_h(j-1) V_h(j-1) must be folded into O_h before it is rescaled
+        mbar_wait(my_o_full, (j - 1) & 1u, 18);
         tc_fence_after();
         o_done = true;
         const float f = need ? ex2_approx(mc - mxc) : 1.0f;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
-        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-        tmem_st_32x32(tmem_O + lane_off + half * 32, v);
+        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_Oh + lane_off + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st_32x32(tmem_Oh + lane_off + c0, v);
+        }
         tmem_wait_st();
         l_run *= f;
       }
       if (need) mc = mxc;
-      // the half's P slab must have been consumed by P(j-1) V(j-1): slab 0 after four k-steps, slab 1 after all eight
-      if (!o_done) {
-        if (half == 0) mbar_wait(p0_free, (j - 1) & 1u, 20);
-        else mbar_wait(o_full, (j - 1) & 1u, 18);
-      }
+      // this half's P slab must have been consumed by P_h(j-1) V_h(j-1)
+      if (!o_done) mbar_wait(my_o_full, (j - 1) & 1u, 18);
       if (tr) ATT_STAMP(3 + 6 * (j - 2));
       // ---- P = 2^7 * exp2(S*c - m) -> f16 -> this half's 64-key slab (SW128 K-major) ----
-      const float mcb = mc - ATT_P_EXP_BIAS;
-      if (full_tile) {
-        l_run += softmax_chunk<false>(va, c, mcb, 0, k0, n_valid, prow_slab, sw);
-        l_run += softmax_chunk<false>(vb, c, mcb, 32, k0 + 32, n_valid, prow_slab, sw);
-      } else {
-        l_run += softmax_chunk<true>(va, c, mcb, 0, k0, n_valid, prow_slab, sw);
-        l_run += softmax_chunk<true>(vb, c, mcb, 32, k0 + 32, n_valid, prow_slab, sw);
+      // (an all-masked half keeps mc = -inf on its first tile: use 0 so that exp2 sees finite arguments; the
+      //  MASKED path zeroes every probability anyway)
+      const float mcb = (mc == -INFINITY ? 0.f : mc) - ATT_P_EXP_BIAS;
+      if (full_tile) l_run += softmax_chunk<false>(vb, c, mcb, 32, k0 + 32, n_valid, prow_slab, sw);
+      else l_run += softmax_chunk<true>(vb, c, mcb, 32, k0 + 32, n_valid, prow_slab, sw);
+      {
+        uint32_t va[32];
+        tmem_ld_32x32(tmem_S + lane_off + k0, va);  // re-read the first chunk (keeps the live registers at 32 + 16)
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_free);                        // last TMEM read of S(j): Q K^T of the next tile may start
+        if (full_tile) l_run += softmax_chunk<false>(va, c, mcb, 0, k0, n_valid, prow_slab, sw);
+        else l_run += softmax_chunk<true>(va, c, mcb, 0, k0, n_valid, prow_slab, sw);
       }
       if (tr) ATT_STAMP(4 + 6 * (j - 2));
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(my_p_full);
       if (tr) ATT_STAMP(5 + 6 * (j - 2));
     }
-    // ---- epilogue: O / (l_half0 + l_half1); each half stores 32 of the 64 output columns ----
-    mbar_wait(o_full, (n_kv - 1) & 1u, 19);
+    // ---- merge the two halves and write O / l: half B publishes (max, denominator), half A owns output columns
+    //      [0,32), half B [32,64); both read BOTH accumulators for their columns ----
+    mbar_wait(o_full(0), (n_kv - 1) & 1u, 19);
+    mbar_wait(o_full(1), (n_kv - 1) & 1u, 19);
     tc_fence_after();
+    float m_o = 0.f, l_o = 0.f;
     {
-      // 128 rows x 2 halves x f32 = 1 KB does not fit the 512 B buffer: exchange in two rounds of 64 rows
-      float l_other = 0.f;
-#pragma unroll
-      for (int round = 0; round < 2; ++round) {
-        const bool mine_now = (r >> 6) == round;
-        const uint32_t slot = sXch + uint32_t(half * 64 + (r & 63)) * 4u;
-        const uint32_t slot_o = sXch + uint32_t((half ^ 1) * 64 + (r & 63)) * 4u;
+      // 128 rows x 2 halves x (m, l) f32 = 2 KB does not fit the 512 B buffer: four rounds of 32 rows
+#pragma unroll 1
+      for (int round = 0; round < 4; ++round) {
+        const bool mine_now = q == round;
+        const uint32_t slot = sXch + uint32_t(half * 32 + lane) * 8u;
+        const uint32_t slot_o = sXch + uint32_t((half ^ 1) * 32 + lane) * 8u;
         softmax_bar_sync();
-        if (mine_now) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(l_run) : "memory");
+        if (mine_now) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(mc), "f"(l_run) : "memory");
         softmax_bar_sync();
-        if (mine_now) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(slot_o) : "memory");
+        if (mine_now) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(slot_o) : "memory");
       }
-      l_run += l_other;
     }
-    const float inv_l = 1.0f / l_run;
+    // common scale: m = max(m_A, m_B); a half without any valid key has m = -inf, l = 0 and contributes nothing
+    const float m_all = fmaxf(mc, m_o);
+    const float f_me = (mc == -INFINITY) ? 0.f : ex2_approx(mc - m_all);
+    const float f_ot = (m_o == -INFINITY) ? 0.f : ex2_approx(m_o - m_all);
+    const float inv_l = 1.0f / (l_run * f_me + l_o * f_ot);
+    const float fA = (half == 0 ? f_me : f_ot) * inv_l;
+    const float fB = (half == 0 ? f_ot : f_me) * inv_l;
     const int t = q0 + r;
     __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D + half * 32;
-    {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_O + lane_off + half * 32, v);
+#pragma unroll 1
+    for (int cc = 0; cc < 32; cc += 16) {
+      uint32_t va[16], vb2[16];
+      tmem_ld_32x16(tmem_O + lane_off + half * 32 + cc, va);        // O_A, 16 of my 32 output columns
+      tmem_ld_32x16(tmem_O + 64 + lane_off + half * 32 + cc, vb2);  // O_B, same columns
       tmem_wait_ld();
       if (t < args.rows_per_batch) {
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
-        uint4* o4 = reinterpret_cast<uint4*>(orow);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        for (int i = 0; i < 16; i += 2) {
+          // an untouched accumulator (half with no valid key) may hold stale TMEM contents: its factor is 0, so
+          // guard against 0 * inf/nan by selecting instead of multiplying
+          const float a0 = fA != 0.f ? __uint_as_float(va[i]) * fA : 0.f;
+          const float a1 = fA != 0.f ? __uint_as_float(va[i + 1]) * fA : 0.f;
+          const float b0 = fB != 0.f ? __uint_as_float(vb2[i]) * fB : 0.f;
+          const float b1 = fB != 0.f ? __uint_as_float(vb2[i + 1]) * fB : 0.f;
+          pk[i / 2] = pack_bf16x2(a0 + b0, a1 + b1);
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(orow + cc);
+        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
     }
     tc_fence_before();
