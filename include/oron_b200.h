@@ -122,7 +122,14 @@ int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);
  */
 int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                         int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                        oron_stream_t stream);
+                        void* workspace, int64_t workspace_bytes, oron_stream_t stream);
+/*
+ * Optional scratch for oron_attention_bf16 (16-byte aligned, ZERO-FILLED once before its first use; the kernel
+ * leaves it ready for the next call). With it, the (batch, head, query-tile) items of a partially filled last
+ * wave are split along the keys and merged in-kernel, which evens out the exp2-bound work across the SMs.
+ * Returns 0 when the shape needs no split. Passing NULL / 0 is always valid (no split).
+ */
+int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_per_batch, int32_t heads);
 
 /*
  * y = LayerNorm(x) * (add_one + scale) + shift, fp32 statistics, biased variance.

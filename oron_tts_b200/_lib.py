@@ -24,6 +24,7 @@ ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
 EXPORTED_SYMBOLS = (
     "oron_gemm_bf16",
     "oron_attention_bf16",
+    "oron_attention_workspace_bytes",
     "oron_ln_modulate",
     "oron_cfg_euler_step",
     "oron_cast_rows_bf16",
@@ -107,7 +108,9 @@ def lib() -> ctypes.CDLL:
     L.oron_debug_set_attention_stamps.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
-                                      c_void_p, c_float, c_void_p]
+                                      c_void_p, c_float, c_void_p, c_int64, c_void_p]
+    L.oron_attention_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
+    L.oron_attention_workspace_bytes.restype = c_int64
     L.oron_ln_modulate.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
                                    c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                                    c_void_p]
@@ -239,12 +242,21 @@ def gemm(
     _check(lib().oron_gemm_bf16(ctypes.byref(d), _stream()), "oron_gemm_bf16")
 
 
+def attention_workspace(nbatch: int, rows_per_batch: int, heads: int, device) -> torch.Tensor | None:
+    """Zero-filled scratch for `attention` (None when the shape needs no key split)."""
+    n = int(lib().oron_attention_workspace_bytes(nbatch, rows_per_batch, heads))
+    if n == 0:
+        return None
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
 def attention(qkv: torch.Tensor, out: torch.Tensor, *, nbatch: int, rows_per_batch: int, heads: int,
-              seq_lens: torch.Tensor | None, scale: float) -> None:
+              seq_lens: torch.Tensor | None, scale: float, workspace: torch.Tensor | None = None) -> None:
     _check(
         lib().oron_attention_bf16(_ptr(qkv, torch.bfloat16, "qkv"), _ld(qkv), _ptr(out, torch.bfloat16, "out"),
                                   _ld(out), nbatch, rows_per_batch, heads, _ptr(seq_lens, torch.int32, "seq_lens"),
-                                  float(scale), _stream()),
+                                  float(scale), _ptr(workspace, torch.uint8, "workspace"),
+                                  workspace.numel() if workspace is not None else 0, _stream()),
         "oron_attention_bf16",
     )
 

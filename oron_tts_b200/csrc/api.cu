@@ -245,9 +245,43 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
 static long long* g_attn_dbg = nullptr;
 // profiling aid (tools/attn_trace.py): int64 [n_ctas, 16] device buffer receiving per-CTA clock64 stamps, or NULL
 extern "C" void oron_debug_set_attention_stamps(void* buf) { g_attn_dbg = reinterpret_cast<long long*>(buf); }
+// Work plan: items = (batch, head, 128-query tile). Two CTAs fit an SM, so `slots` = 2 * SMs items run concurrently.
+// The kernel is bound by the exp2 unit, i.e. by how evenly exp work is spread: a last, partially filled wave would
+// leave most SMs idle for a whole item (config 2: 352 items on 296 slots -> 2 waves for 1.19 waves of work). The
+// items of that last wave are therefore split along the keys into `parts` CTAs each (<= slots CTAs in total) whose
+// partial results are merged in-kernel by the last finisher.
+struct AttnPlan {
+  int q_tiles, items, n_full, n_tail, parts;
+};
+static AttnPlan attn_plan(int nbatch, int rows_per_batch, int heads, bool have_ws) {
+  AttnPlan p;
+  p.q_tiles = (rows_per_batch + ATT_TILE - 1) / ATT_TILE;
+  p.items = p.q_tiles * heads * nbatch;
+  const int slots = 2 * num_sms();
+  const int kv_tiles = p.q_tiles;
+  p.n_full = (p.items / slots) * slots;
+  p.n_tail = p.items - p.n_full;
+  p.parts = 1;
+  if (have_ws && p.n_tail > 0 && kv_tiles >= 4) {
+    int parts = slots / p.n_tail;
+    if (parts > kv_tiles / 2) parts = kv_tiles / 2;  // at least two key tiles per part
+    if (parts > 8) parts = 8;
+    if (parts >= 2) p.parts = parts;
+  }
+  if (p.parts == 1) { p.n_full = p.items; p.n_tail = 0; }
+  return p;
+}
+
+extern "C" int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_per_batch, int32_t heads) {
+  const AttnPlan p = attn_plan(nbatch, rows_per_batch, heads, true);
+  if (p.parts == 1) return 0;
+  const int64_t units = int64_t(p.n_tail) * p.parts;
+  return units * ATT_TILE * (ATT_D + 2) * 4 + int64_t(p.n_tail) * 4 + 256;
+}
+
 extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                                    int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                                   oron_stream_t stream) {
+                                   void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
   if (!qkv || !out || nbatch <= 0 || rows_per_batch <= 0 || heads <= 0)
     return fail(ORON_ERR_BAD_ARG, "attention: bad argument");
   if (ldo % 8 != 0) return fail(ORON_ERR_BAD_ARG, "attention: ldo must be a multiple of 8");
@@ -262,6 +296,10 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
     if (e != cudaSuccess) return fail(int(e), "attention smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
+  const bool have_ws = workspace != nullptr &&
+                       workspace_bytes >= oron_attention_workspace_bytes(nbatch, rows_per_batch, heads) &&
+                       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+  const AttnPlan p = attn_plan(nbatch, rows_per_batch, heads, have_ws);
   AttnArgs a;
   a.rows_per_batch = rows_per_batch;
   a.nbatch = nbatch;
@@ -271,7 +309,19 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.dbg = g_attn_dbg;
-  dim3 grid((rows_per_batch + ATT_TILE - 1) / ATT_TILE, heads, nbatch);
+  a.q_tiles = p.q_tiles;
+  a.n_full = p.n_full;
+  a.parts = p.parts;
+  a.ws_o = a.ws_ml = nullptr;
+  a.ws_cnt = nullptr;
+  if (p.parts > 1) {
+    const int64_t units = int64_t(p.n_tail) * p.parts;
+    char* w = reinterpret_cast<char*>(workspace);
+    a.ws_o = reinterpret_cast<float*>(w);
+    a.ws_ml = reinterpret_cast<float*>(w + units * ATT_TILE * ATT_D * 4);
+    a.ws_cnt = reinterpret_cast<int*>(w + units * ATT_TILE * (ATT_D + 2) * 4);
+  }
+  dim3 grid(p.n_full + p.n_tail * p.parts);
   cudaError_t le = launch_pdl(attn_fwd_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES,
                               reinterpret_cast<cudaStream_t>(stream), tq, a);
   if (le != cudaSuccess) return fail(int(le), "attention launch: %s", cudaGetErrorString(le));

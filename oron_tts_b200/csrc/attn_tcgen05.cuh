@@ -45,6 +45,15 @@ struct AttnArgs {
   long long ldo;
   float scale_log2;     // softmax scale * log2(e)
   long long* dbg;       // optional [grid, 16] clock64 stamps (tools/attn_trace.py); nullptr in production
+  // work decomposition (see attn_plan in api.cu): items = (batch, head, 128-query tile) in linear order. The first
+  // n_full items run whole, one CTA each; every later ("tail") item is split along the keys into `parts` CTAs whose
+  // partial (O, max, sum) results are merged by whichever of them finishes last.
+  int q_tiles;          // 128-row query tiles per batch element
+  int n_full;
+  int parts;            // >= 1
+  float* ws_o;          // [n_tail_items * parts][128][64] f32 partial numerators
+  float* ws_ml;         // [n_tail_items * parts][128][2] f32 (running max * c, denominator)
+  int* ws_cnt;          // [n_tail_items] arrival counters, zero before the first launch (the kernel re-zeroes them)
 };
 
 constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 softmax
@@ -55,12 +64,8 @@ constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB
 constexpr int ATT_ONES_BYTES = 512;  // [16 x 16] f16 ones, no-swizzle K-major core matrices
 constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_ONES_BYTES;
 constexpr int ATT_TMEM_COLS = 256;
-#define ATT_STAMP(slot) do { if (args.dbg) args.dbg[(long long)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+#define ATT_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
-#ifndef ATT_STAGGER_NS
-#define ATT_STAGGER_NS 700
-#endif
-constexpr unsigned ATT_STAGGER_WAVE = 148;  // CTAs are dealt round-robin over the SMs: lin and lin+148 are co-resident
 constexpr float ATT_P_EXP_BIAS = 7.0f;    // probabilities are scaled by 2^7 (<= 2^15 in f16); cancels in O / l
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -171,15 +176,26 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();
-  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int item = blockIdx.x, part = 0, nparts = 1;
+  if (item >= args.n_full) {
+    const int u = item - args.n_full;
+    item = args.n_full + u / args.parts;
+    part = u % args.parts;
+    nparts = args.parts;
+  }
+  const int q_tile = item % args.q_tiles;
+  const int h = (item / args.q_tiles) % args.heads;
+  const int b = item / (args.q_tiles * args.heads);
   const int q0 = q_tile * ATT_TILE;
   const int len = args.seq_lens ? min(args.seq_lens[b], args.rows_per_batch) : args.rows_per_batch;
-  if (q0 >= len) return;  // whole tile is padding: the out-projection masks these rows
+  if (q0 >= len) return;  // whole tile is padding (all parts of the item agree): the out-projection masks these rows
   if ((smem_base & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[oron] attention: dynamic smem not 1024-byte aligned\n");
     __trap();
   }
   const int n_kv = (len + ATT_TILE - 1) / ATT_TILE;
+  const int j_begin = (part * n_kv) / nparts;                 // this CTA's key tiles: [j_begin, j_begin + n_loc)
+  const int n_loc = ((part + 1) * n_kv) / nparts - j_begin;   // may be 0 when the sequence has fewer tiles than parts
 
   const uint32_t sQ = smem_base;
   auto sK = [&](int s) { return smem_base + (1 + s) * ATT_TILE_BYTES; };
@@ -226,12 +242,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_3d(sQ, &tmQKV, q_full, h * ATT_D, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
+      for (int j = 0; j < n_loc; ++j) {
         const int s = j & 1;
         mbar_wait(kv_empty(s), ((j >> 1) & 1u) ^ 1u, 11);
         mbar_arrive_expect_tx(kv_full(s), 2 * ATT_TILE_BYTES);
-        tma_load_3d(sK(s), &tmQKV, kv_full(s), HD + h * ATT_D, j * ATT_TILE, b);
-        tma_load_3d(sV(s), &tmQKV, kv_full(s), 2 * HD + h * ATT_D, j * ATT_TILE, b);
+        tma_load_3d(sK(s), &tmQKV, kv_full(s), HD + h * ATT_D, (j_begin + j) * ATT_TILE, b);
+        tma_load_3d(sV(s), &tmQKV, kv_full(s), 2 * HD + h * ATT_D, (j_begin + j) * ATT_TILE, b);
       }
     }
   } else if (warp == 1) {
@@ -254,13 +270,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           umma_bf16_ss(tmem_S, qdesc + uint64_t(2 * k), kdesc + uint64_t(2 * k), idesc_s, k != 0);
         umma_commit(s_full);
       };
-      mbar_wait(q_full, 0, 12);
-      mbar_wait(kv_full(0), 0, 13);
-      tc_fence_after();
-      issue_S(0);
-      for (int j = 0; j < n_kv; ++j) {
+      if (n_loc > 0) {
+        mbar_wait(q_full, 0, 12);
+        mbar_wait(kv_full(0), 0, 13);
+        tc_fence_after();
+        issue_S(0);
+      }
+      for (int j = 0; j < n_loc; ++j) {
         const int s = j & 1;
-        if (j + 1 < n_kv) {
+        if (j + 1 < n_loc) {
           mbar_wait(s_free, j & 1u, 14);  // S(j) fully read: the S columns may be overwritten
           mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1u, 15);
           tc_fence_after();
@@ -295,16 +313,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     float l_run = 0.f;     // softmax denominator in the same (stale-max, 2^7-biased) scale as O
     const uint32_t prow = sP + r * 128;
     const uint32_t sw = uint32_t(r & 7);
-    // Two CTAs share an SM and would otherwise run in lockstep (same start, same period), hitting the MUFU
-    // pipe at the same time and idling it together. Start every second wave of CTAs half a tile late so that
-    // one CTA's exp phase overlaps the other's max / wait phases.
-    {
-      const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      if ((lin / ATT_STAGGER_WAVE) & 1u) __nanosleep(ATT_STAGGER_NS);
-    }
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int n_valid = min(ATT_TILE, len - j * ATT_TILE);
+    for (int j = 0; j < n_loc; ++j) {
+      const int n_valid = min(ATT_TILE, len - (j_begin + j) * ATT_TILE);
       const bool full_tile = n_valid == ATT_TILE;  // CTA-uniform
       mbar_wait(s_full, j & 1u, 17);
       tc_fence_after();
@@ -386,25 +396,96 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       mbar_arrive(p_full);
       if (tr) ATT_STAMP(5 + 6 * (j - 2));
     }
-    // ---- epilogue: O / l ----
-    mbar_wait(o_full, (n_kv - 1) & 1u, 19);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
+    // ---- epilogue ----
+    if (n_loc > 0) {
+      mbar_wait(o_full, (n_loc - 1) & 1u, 19);
+      tc_fence_after();
+    }
     const int t = q0 + r;
     __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D;
+    if (nparts == 1) {
+      // whole item: O / l
+      const float inv_l = 1.0f / l_run;
 #pragma unroll
-    for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_O + lane_off + c0, v);
-      tmem_wait_ld();
-      if (t < args.rows_per_batch) {
-        uint32_t pk[16];
+      for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_O + lane_off + c0, v);
+        tmem_wait_ld();
+        if (t < args.rows_per_batch) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+          for (int i = 0; i < 32; i += 2)
+            pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+    } else {
+      // key-split tail item: publish this part's (O, max, sum); the part that arrives last merges all of them.
+      // Nobody waits for anybody (no co-scheduling assumption): ordering is "write, fence, count".
+      const int tail = item - args.n_full;
+      const long long unit = (long long)tail * nparts + part;
+      float* wo = args.ws_o + (unit * ATT_TILE + r) * ATT_D;
+      if (n_loc > 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_O + lane_off + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(wo + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      *reinterpret_cast<float2*>(args.ws_ml + (unit * ATT_TILE + r) * 2) = make_float2(mc, l_run);  // empty part: (-inf, 0)
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t flag = sP;  // the P tile is dead by now: reuse its first word as the "I am last" flag
+      if (threadIdx.x == 64) {
+        const int old = atomicAdd(args.ws_cnt + tail, 1);
+        const int last = (old == nparts - 1) ? 1 : 0;
+        if (last) args.ws_cnt[tail] = 0;  // ready for the next launch (CUDA-graph replays included)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag), "r"(last) : "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t last;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
+      if (last) {
+        __threadfence();
+        const long long u0 = (long long)tail * nparts;
+        float m_all = -INFINITY;
+        for (int p = 0; p < nparts; ++p)
+          m_all = fmaxf(m_all, __ldcg(args.ws_ml + ((u0 + p) * ATT_TILE + r) * 2));
+        float acc[ATT_D];
+#pragma unroll
+        for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
+        float l_all = 0.f;
+        for (int p = 0; p < nparts; ++p) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(args.ws_ml + ((u0 + p) * ATT_TILE + r) * 2));
+          if (ml.y == 0.f) continue;  // empty part (its O slot was never written)
+          const float f = ex2_approx(ml.x - m_all);
+          l_all = fmaf(ml.y, f, l_all);
+          const float4* po = reinterpret_cast<const float4*>(args.ws_o + ((u0 + p) * ATT_TILE + r) * ATT_D);
+#pragma unroll
+          for (int i = 0; i < ATT_D / 4; ++i) {
+            const float4 o = __ldcg(po + i);
+            acc[4 * i] = fmaf(o.x, f, acc[4 * i]);
+            acc[4 * i + 1] = fmaf(o.y, f, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(o.z, f, acc[4 * i + 2]);
+            acc[4 * i + 3] = fmaf(o.w, f, acc[4 * i + 3]);
+          }
+        }
+        if (t < args.rows_per_batch) {
+          const float inv_l = 1.0f / l_all;
+          uint4* o4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+          for (int g = 0; g < ATT_D / 8; ++g)
+            o4[g] = make_uint4(pack_bf16x2(acc[8 * g] * inv_l, acc[8 * g + 1] * inv_l),
+                               pack_bf16x2(acc[8 * g + 2] * inv_l, acc[8 * g + 3] * inv_l),
+                               pack_bf16x2(acc[8 * g + 4] * inv_l, acc[8 * g + 5] * inv_l),
+                               pack_bf16x2(acc[8 * g + 6] * inv_l, acc[8 * g + 7] * inv_l));
+        }
       }
     }
     tc_fence_before();

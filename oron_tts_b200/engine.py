@@ -205,6 +205,8 @@ class Workspace:
         self.nrm = z(R, D, dt=BF16)
         self.qkv = z(R, 3 * D, dt=BF16)
         self.ao = z(R, D, dt=BF16)
+        with torch.inference_mode(False):
+            self.attn_ws = L.attention_workspace(nbp, tpad, w.heads, dev)
         self.hid = z(R, w.ff_dim, dt=BF16)
         self.v = z(R, M)
         self.vg = z(Rb, M)
@@ -339,7 +341,7 @@ class DiTEngine:
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
                    rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
-                        scale=1.0 / math.sqrt(w.dim_head))
+                        scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
                    mask_rows=True, block_n=bn_big, two_sm=True, **common)
