@@ -235,7 +235,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
   pdl_wait();  // the QKV activations of the previous kernel are visible from here on
-  if (threadIdx.x == 0) ATT_STAMP(0);
+  if (threadIdx.x == 0) {
+    ATT_STAMP(0);
+    if (args.dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); args.dbg[(long long)blockIdx.x * 16 + 8] = (long long)gt; }
+  }
 
   const int HD = args.heads * ATT_D;
   if (warp == 0) {
@@ -318,8 +321,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       const bool full_tile = n_valid == ATT_TILE;  // CTA-uniform
       mbar_wait(s_full, j & 1u, 17);
       tc_fence_after();
-      const bool tr = threadIdx.x == 64 && (j == 2 || j == 3);
-      if (tr) ATT_STAMP(1 + 6 * (j - 2));
+      const bool tr = threadIdx.x == 64 && j == (nparts > 1 ? 1 : 2);
+      if (tr) ATT_STAMP(1);
       // ---- pass 1: row maximum over the valid keys (the last 32-key chunk stays in registers for pass 2) ----
       float mx = -INFINITY;
       uint32_t vlast[32];
@@ -344,7 +347,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const float mxc = mx * c;
       const bool need = mxc > mc + ATT_RESCALE_LOG2;
-      if (tr) ATT_STAMP(2 + 6 * (j - 2));
+      if (tr) ATT_STAMP(2);
       bool o_done = (j == 0);
       if (j > 0 && __any_sync(0xffffffffu, need)) {
         // rare: P(j-1) V(j-1) must be folded into O before O and l are rescaled
@@ -366,7 +369,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       }
       if (j > 0 && !o_done) mbar_wait(p0_free, (j - 1) & 1u, 20);  // first P slab may be overwritten
       if (need) mc = mxc;
-      if (tr) ATT_STAMP(3 + 6 * (j - 2));
+      if (tr) ATT_STAMP(3);
       // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
       const float mcb = mc - ATT_P_EXP_BIAS;
 #pragma unroll
@@ -383,18 +386,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         if (c0 == 64 && !o_done) {
           mbar_wait(o_full, (j - 1) & 1u, 18);  // second P slab: all of P(j-1) V(j-1) has retired
           o_done = true;
-          if (threadIdx.x == 64 && j == 3) ATT_STAMP(6);
         }
         l_run += full_tile ? softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw)
                            : softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
       }
       l_run += full_tile ? softmax_chunk<false>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw)
                          : softmax_chunk<true>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
-      if (tr) ATT_STAMP(4 + 6 * (j - 2));
+      if (tr) ATT_STAMP(4);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
-      if (tr) ATT_STAMP(5 + 6 * (j - 2));
+      if (tr) ATT_STAMP(5);
     }
     // ---- epilogue ----
     if (n_loc > 0) {
@@ -424,6 +426,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     } else {
       // key-split tail item: publish this part's (O, max, sum); the part that arrives last merges all of them.
       // Nobody waits for anybody (no co-scheduling assumption): ordering is "write, fence, count".
+      if (threadIdx.x == 64) ATT_STAMP(6);
       const int tail = item - args.n_full;
       const long long unit = (long long)tail * nparts + part;
       float* wo = args.ws_o + (unit * ATT_TILE + r) * ATT_D;
@@ -439,8 +442,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         }
       }
       *reinterpret_cast<float2*>(args.ws_ml + (unit * ATT_TILE + r) * 2) = make_float2(mc, l_run);  // empty part: (-inf, 0)
+      if (threadIdx.x == 64) ATT_STAMP(7);
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) ATT_STAMP(10);
       const uint32_t flag = sP;  // the P tile is dead by now: reuse its first word as the "I am last" flag
       if (threadIdx.x == 64) {
         const int old = atomicAdd(args.ws_cnt + tail, 1);
@@ -451,40 +456,65 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       asm volatile("bar.sync 1, 128;" ::: "memory");
       uint32_t last;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
+      if (threadIdx.x == 64) ATT_STAMP(11);
       if (last) {
         __threadfence();
         const long long u0 = (long long)tail * nparts;
+        // (1) per row: common maximum, per-part factors 2^(m_p - m) / l  -> smem (the P tile is dead)
+        float mp[8], lp[8];
         float m_all = -INFINITY;
-        for (int p = 0; p < nparts; ++p)
-          m_all = fmaxf(m_all, __ldcg(args.ws_ml + ((u0 + p) * ATT_TILE + r) * 2));
-        float acc[ATT_D];
 #pragma unroll
-        for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
-        float l_all = 0.f;
-        for (int p = 0; p < nparts; ++p) {
-          const float2 ml = __ldcg(reinterpret_cast<const float2*>(args.ws_ml + ((u0 + p) * ATT_TILE + r) * 2));
-          if (ml.y == 0.f) continue;  // empty part (its O slot was never written)
-          const float f = ex2_approx(ml.x - m_all);
-          l_all = fmaf(ml.y, f, l_all);
-          const float4* po = reinterpret_cast<const float4*>(args.ws_o + ((u0 + p) * ATT_TILE + r) * ATT_D);
-#pragma unroll
-          for (int i = 0; i < ATT_D / 4; ++i) {
-            const float4 o = __ldcg(po + i);
-            acc[4 * i] = fmaf(o.x, f, acc[4 * i]);
-            acc[4 * i + 1] = fmaf(o.y, f, acc[4 * i + 1]);
-            acc[4 * i + 2] = fmaf(o.z, f, acc[4 * i + 2]);
-            acc[4 * i + 3] = fmaf(o.w, f, acc[4 * i + 3]);
+        for (int p = 0; p < 8; ++p) {
+          mp[p] = -INFINITY; lp[p] = 0.f;
+          if (p < nparts) {
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(args.ws_ml + ((u0 + p) * ATT_TILE + r) * 2));
+            mp[p] = ml.x; lp[p] = ml.y;
           }
+          m_all = fmaxf(m_all, mp[p]);
         }
-        if (t < args.rows_per_batch) {
-          const float inv_l = 1.0f / l_all;
-          uint4* o4 = reinterpret_cast<uint4*>(orow);
+        float l_all = 0.f;
 #pragma unroll
-          for (int g = 0; g < ATT_D / 8; ++g)
-            o4[g] = make_uint4(pack_bf16x2(acc[8 * g] * inv_l, acc[8 * g + 1] * inv_l),
-                               pack_bf16x2(acc[8 * g + 2] * inv_l, acc[8 * g + 3] * inv_l),
-                               pack_bf16x2(acc[8 * g + 4] * inv_l, acc[8 * g + 5] * inv_l),
-                               pack_bf16x2(acc[8 * g + 6] * inv_l, acc[8 * g + 7] * inv_l));
+        for (int p = 0; p < 8; ++p) {
+          mp[p] = lp[p] > 0.f ? ex2_approx(mp[p] - m_all) : 0.f;  // now the factor; empty parts contribute nothing
+          l_all = fmaf(lp[p], mp[p], l_all);
+        }
+        const float inv_l = 1.0f / l_all;
+        const uint32_t sF = sP + 16;  // [8 parts][128 rows] f32
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sF + uint32_t(p * ATT_TILE + r) * 4u), "f"(mp[p] * inv_l) : "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // (2) cooperative, coalesced merge: 16 threads per output row (4 columns each), 8 rows per step
+        const int tid = threadIdx.x - 64;
+        const int c4 = (tid & 15) * 4;
+        const float* fs = reinterpret_cast<const float*>(__cvta_shared_to_generic(sF));
+#pragma unroll 2
+        for (int rg = 0; rg < ATT_TILE / 8; ++rg) {
+          const int row = rg * 8 + (tid >> 4);
+          // all loads of a row group are issued before any of them is consumed (one L2 round trip per group, not
+          // one per part). Empty parts are read too: the scratch only ever holds finite values and their factor is 0.
+          float f[8];
+          float4 o[8];
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            f[p] = 0.f;
+            o[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < nparts) {
+              f[p] = fs[p * ATT_TILE + row];
+              o[p] = __ldcg(reinterpret_cast<const float4*>(args.ws_o + ((u0 + p) * ATT_TILE + row) * ATT_D + c4));
+            }
+          }
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            acc.x = fmaf(o[p].x, f[p], acc.x); acc.y = fmaf(o[p].y, f[p], acc.y);
+            acc.z = fmaf(o[p].z, f[p], acc.z); acc.w = fmaf(o[p].w, f[p], acc.w);
+          }
+          const int tt = q0 + row;
+          if (tt < args.rows_per_batch) {
+            __nv_bfloat16* orow2 = args.out + ((long long)b * args.rows_per_batch + tt) * args.ldo + h * ATT_D + c4;
+            *reinterpret_cast<uint2*>(orow2) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+          }
         }
       }
     }
@@ -493,7 +523,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   }
 
   __syncthreads();
-  if (threadIdx.x == 0) ATT_STAMP(15);
+  if (threadIdx.x == 0) {
+    ATT_STAMP(15);
+    if (args.dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); args.dbg[(long long)blockIdx.x * 16 + 9] = (long long)gt; }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);

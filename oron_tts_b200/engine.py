@@ -205,8 +205,10 @@ class Workspace:
         self.nrm = z(R, D, dt=BF16)
         self.qkv = z(R, 3 * D, dt=BF16)
         self.ao = z(R, D, dt=BF16)
-        with torch.inference_mode(False):
-            self.attn_ws = L.attention_workspace(nbp, tpad, w.heads, dev)
+        # Key-split scratch for the attention kernel's last wave (oron_attention_workspace_bytes). Measured at config 2
+        # (profiles/r01_attn_keysplit.txt): 55 us with the split vs 51 us without — prologue, fence and merge of the
+        # 280 extra CTAs eat the gain — so it stays off until the merge is cheaper.
+        self.attn_ws = None
         self.hid = z(R, w.ff_dim, dt=BF16)
         self.v = z(R, M)
         self.vg = z(Rb, M)

@@ -21,8 +21,7 @@ torch.cuda._sleep(200000)
 fn(); torch.cuda.synchronize()
 L.lib().oron_debug_set_attention_stamps(None)
 d = dbg.cpu()
-names = {1: "t2 s_full", 2: "t2 pass1", 3: "t2 o_wait", 4: "t2 pass2", 5: "t2 arrive", 7: "t3 s_full", 8: "t3 pass1", 9: "t3 o_wait", 10: "t3 pass2",
-         11: "t3 arrive", 6: "t3 o_full(2) seen", 12: "mma: p_full(2)", 13: "mma: PV(2) issued", 14: "softmax end", 15: "cta end"}
+names = {1: "tj s_full", 2: "tj pass1", 3: "tj o_wait", 4: "tj pass2", 5: "tj arrive", 6: "loop done", 7: "partial written", 10: "fence+bar", 11: "count done", 12: "mma: p_full(2)", 13: "mma: PV(2) issued", 14: "softmax end", 15: "cta end"}
 starts = d[:, 0]
 print("global start spread (cycles are per-SM clocks; only relative values inside a CTA are meaningful)")
 for cta in (0, 100, 295, 296, 400, 575):
@@ -31,3 +30,17 @@ for cta in (0, 100, 295, 296, 400, 575):
 d = d[:576]
 dur = (d[:, 15] - d[:, 0]).float()
 print("cta duration cycles: mean %.0f min %.0f max %.0f" % (dur.mean(), dur.min(), dur.max()))
+
+g0 = int(d[:, 8].min())
+st = (d[:, 8] - g0).double() / 1e3
+en = (d[:, 9] - g0).double() / 1e3
+print("globaltimer (us): full items start %.1f..%.1f end %.1f..%.1f | tail units start %.1f..%.1f end %.1f..%.1f" % (
+    st[:296].min(), st[:296].max(), en[:296].min(), en[:296].max(), st[296:].min(), st[296:].max(), en[296:].min(), en[296:].max()))
+print("tail unit durations (us): mean %.2f max %.2f ; full item durations mean %.2f max %.2f" % (
+    (en[296:] - st[296:]).mean(), (en[296:] - st[296:]).max(), (en[:296] - st[:296]).mean(), (en[:296] - st[:296]).max()))
+
+dd = (en - st)
+slow = torch.argsort(dd[296:], descending=True)[:3] + 296
+for cta in slow.tolist() + [300]:
+    base = int(d[cta, 0])
+    print(f"  tail cta {cta} ({dd[cta]:.1f} us): " + ", ".join(f"{names[i]}={int(d[cta, i]) - base}" for i in sorted(names) if int(d[cta, i]) != 0))
