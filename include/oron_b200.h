@@ -105,8 +105,6 @@ typedef struct oron_gemm_desc {
   int32_t max_ctas;          /* 0 = one CTA per SM */
   int32_t two_sm;            /* 1: 2-SM (cta_group::2) kernel, 256 x block_n tile per SM pair */
   int32_t f16_from_col;      /* QKV_ROPE: columns >= this (> 0) are stored as IEEE f16, not bf16 (the V operand of attention) */
-  const void* prefetch;      /* NULL, or a weight slab a later kernel will read: warmed into L2 by idle lanes */
-  int64_t prefetch_bytes;
   void* debug_stamps;        /* NULL, or int64 [grid, 16] device buffer for per-CTA clock64 stamps (profiling aid) */
 } oron_gemm_desc;
 
@@ -124,8 +122,7 @@ int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);
  */
 int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                         int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                        void* workspace, int64_t workspace_bytes, const void* prefetch, int64_t prefetch_bytes,
-                        oron_stream_t stream);
+                        void* workspace, int64_t workspace_bytes, oron_stream_t stream);
 /*
  * Optional scratch for oron_attention_bf16 (16-byte aligned, ZERO-FILLED once before its first use; the kernel
  * leaves it ready for the next call). With it, the (batch, head, query-tile) items of a partially filled last
@@ -138,15 +135,12 @@ int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_per_batch, i
  * y = LayerNorm(x) * (add_one + scale) + shift, fp32 statistics, biased variance.
  * Replaces AdaLayerNorm / AdaLayerNormFinal / DiTBlock.ff_norm modulation (modules.py:218, 234, 341)
  * and affine nn.LayerNorm (modules.py:169; Vocos norms) with add_one = 0, mod_ld = 0.
- * scale/shift address: ptr + step*step_stride + (b % mod_nb)*mod_ld. C in {128, 256, 512, 768, 1024}.
- * prefetch / prefetch_bytes (here, in oron_attention_bf16 and in oron_gemm_desc): optional weight slab of a LATER
- * kernel that this launch warms into L2 with otherwise idle threads (the 856 MB of weights of one NFE never stay in
- * the 126 MB L2); NULL / 0 disables it.
+ * scale/shift address: ptr + step*step_stride + (b % mod_nb)*mod_ld. C in {512, 1024}.
  */
 int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_batch, int32_t nbatch, int32_t C,
                      float eps, const float* scale, const float* shift, int64_t mod_ld, int32_t mod_nb,
                      int64_t step_stride, const int32_t* step_ptr, int32_t add_one, void* out_bf16,
-                     float* out_f32, int64_t ldo, const void* prefetch, int64_t prefetch_bytes, oron_stream_t stream);
+                     float* out_f32, int64_t ldo, oron_stream_t stream);
 
 /*
  * One Euler step with classifier-free guidance (flow.py:266-267, 295-299):

@@ -83,8 +83,6 @@ class GemmDesc(ctypes.Structure):
         ("max_ctas", c_int32),
         ("two_sm", c_int32),
         ("f16_from_col", c_int32),
-        ("prefetch", c_void_p),
-        ("prefetch_bytes", c_int64),
         ("debug_stamps", c_void_p),
     ]
 
@@ -110,12 +108,12 @@ def lib() -> ctypes.CDLL:
     L.oron_debug_set_attention_stamps.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
-                                      c_void_p, c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p]
+                                      c_void_p, c_float, c_void_p, c_int64, c_void_p]
     L.oron_attention_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     L.oron_attention_workspace_bytes.restype = c_int64
     L.oron_ln_modulate.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
                                    c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
-                                   c_void_p, c_int64, c_void_p]
+                                   c_void_p]
     L.oron_cfg_euler_step.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_float,
                                       c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     L.oron_cast_rows_bf16.argtypes = [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p]
@@ -203,7 +201,6 @@ def gemm(
     two_sm: bool = False,
     debug_stamps: torch.Tensor | None = None,
     f16_from_col: int = 0,
-    prefetch: torch.Tensor | None = None,
 ) -> None:
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16."""
     d = GemmDesc()
@@ -237,8 +234,6 @@ def gemm(
     d.max_ctas = int(max_ctas)
     d.two_sm = int(bool(two_sm))
     d.f16_from_col = int(f16_from_col)
-    d.prefetch = _ptr(prefetch, None, "prefetch")
-    d.prefetch_bytes = prefetch.numel() * prefetch.element_size() if prefetch is not None else 0
     d.debug_stamps = _ptr(debug_stamps, torch.int64, "debug_stamps")
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16
@@ -256,14 +251,12 @@ def attention_workspace(nbatch: int, rows_per_batch: int, heads: int, device) ->
 
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, *, nbatch: int, rows_per_batch: int, heads: int,
-              seq_lens: torch.Tensor | None, scale: float, workspace: torch.Tensor | None = None,
-              prefetch: torch.Tensor | None = None) -> None:
+              seq_lens: torch.Tensor | None, scale: float, workspace: torch.Tensor | None = None) -> None:
     _check(
         lib().oron_attention_bf16(_ptr(qkv, torch.bfloat16, "qkv"), _ld(qkv), _ptr(out, torch.bfloat16, "out"),
                                   _ld(out), nbatch, rows_per_batch, heads, _ptr(seq_lens, torch.int32, "seq_lens"),
                                   float(scale), _ptr(workspace, torch.uint8, "workspace"),
-                                  workspace.numel() if workspace is not None else 0, _ptr(prefetch, None, "prefetch"),
-                                  prefetch.numel() * prefetch.element_size() if prefetch is not None else 0, _stream()),
+                                  workspace.numel() if workspace is not None else 0, _stream()),
         "oron_attention_bf16",
     )
 
@@ -271,16 +264,14 @@ def attention(qkv: torch.Tensor, out: torch.Tensor, *, nbatch: int, rows_per_bat
 def ln_modulate(x: torch.Tensor, *, rows_per_batch: int, nbatch: int, eps: float, scale: torch.Tensor,
                 shift: torch.Tensor | None, mod_ld: int = 0, mod_nb: int = 1, step_stride: int = 0,
                 step_ptr: torch.Tensor | None = None, add_one: bool = True,
-                out_bf16: torch.Tensor | None = None, out_f32: torch.Tensor | None = None,
-                prefetch: torch.Tensor | None = None) -> None:
+                out_bf16: torch.Tensor | None = None, out_f32: torch.Tensor | None = None) -> None:
     o = out_bf16 if out_bf16 is not None else out_f32
     _check(
         lib().oron_ln_modulate(_ptr(x, torch.float32, "x"), _ld(x), rows_per_batch, nbatch, x.shape[1], float(eps),
                                _ptr(scale, torch.float32, "scale"), _ptr(shift, torch.float32, "shift"), int(mod_ld),
                                int(mod_nb), int(step_stride), _ptr(step_ptr, torch.int32, "step_ptr"),
                                int(bool(add_one)), _ptr(out_bf16, torch.bfloat16, "out_bf16"),
-                               _ptr(out_f32, torch.float32, "out_f32"), _ld(o), _ptr(prefetch, None, "prefetch"),
-                               prefetch.numel() * prefetch.element_size() if prefetch is not None else 0, _stream()),
+                               _ptr(out_f32, torch.float32, "out_f32"), _ld(o), _stream()),
         "oron_ln_modulate",
     )
 

@@ -178,8 +178,6 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   a.row_valid = d->row_valid;
   a.mask_rows = d->mask_rows;
   a.dbg = reinterpret_cast<long long*>(d->debug_stamps);
-  a.prefetch = d->prefetch;
-  a.prefetch_bytes = d->prefetch_bytes;
 
   const int epi = d->epilogue;
   // per-epilogue operand checks (vectorised epilogues assume 32-column granularity)
@@ -283,8 +281,7 @@ extern "C" int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_p
 
 extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                                    int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                                   void* workspace, int64_t workspace_bytes, const void* prefetch,
-                                   int64_t prefetch_bytes, oron_stream_t stream) {
+                                   void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
   if (!qkv || !out || nbatch <= 0 || rows_per_batch <= 0 || heads <= 0)
     return fail(ORON_ERR_BAD_ARG, "attention: bad argument");
   if (ldo % 8 != 0) return fail(ORON_ERR_BAD_ARG, "attention: ldo must be a multiple of 8");
@@ -315,8 +312,6 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   a.q_tiles = p.q_tiles;
   a.n_full = p.n_full;
   a.parts = p.parts;
-  a.prefetch = prefetch;
-  a.prefetch_bytes = prefetch_bytes;
   a.ws_o = a.ws_ml = nullptr;
   a.ws_cnt = nullptr;
   if (p.parts > 1) {
@@ -339,8 +334,7 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
 extern "C" int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_batch, int32_t nbatch, int32_t C,
                                 float eps, const float* scale, const float* shift, int64_t mod_ld, int32_t mod_nb,
                                 int64_t step_stride, const int32_t* step_ptr, int32_t add_one, void* out_bf16,
-                                float* out_f32, int64_t ldo, const void* prefetch, int64_t prefetch_bytes,
-                                oron_stream_t stream) {
+                                float* out_f32, int64_t ldo, oron_stream_t stream) {
   if (!x || !scale || (!out_bf16 && !out_f32)) return fail(ORON_ERR_BAD_ARG, "ln_modulate: null pointer");
   if (ldx % 4 != 0 || ldo % 4 != 0) return fail(ORON_ERR_BAD_ARG, "ln_modulate: ld must be a multiple of 4");
   LnArgs a;
@@ -348,7 +342,6 @@ extern "C" int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_ba
   a.scale = scale; a.shift = shift; a.mod_ld = mod_ld; a.mod_nb = mod_nb > 0 ? mod_nb : 1;
   a.step_stride = step_stride; a.step_ptr = step_ptr; a.add_one = add_one;
   a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.ldo = ldo;
-  a.prefetch = prefetch; a.prefetch_bytes = prefetch_bytes;
   const long long rows = (long long)rows_per_batch * nbatch;
   const int blocks = int((rows + 7) / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

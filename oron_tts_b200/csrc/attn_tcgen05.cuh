@@ -54,8 +54,6 @@ struct AttnArgs {
   float* ws_o;          // [n_tail_items * parts][128][64] f32 partial numerators
   float* ws_ml;         // [n_tail_items * parts][128][2] f32 (running max * c, denominator)
   int* ws_cnt;          // [n_tail_items] arrival counters, zero before the first launch (the kernel re-zeroes them)
-  const void* prefetch; // optional: weights of the GEMMs that follow, warmed into L2 by the otherwise idle lanes
-  long long prefetch_bytes;
 };
 
 constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 softmax
@@ -178,9 +176,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const int lane = threadIdx.x & 31;
 
   pdl_launch_dependents();
-  if (args.prefetch != nullptr && threadIdx.x < 64 && (threadIdx.x & 31) != 0)  // idle lanes of the TMA / MMA warps
-    l2_prefetch_slab(args.prefetch, args.prefetch_bytes, (long long)blockIdx.x * 62 + (threadIdx.x - 1 - (threadIdx.x >> 5)),
-                     (long long)gridDim.x * 62);
   int item = blockIdx.x, part = 0, nparts = 1;
   if (item >= args.n_full) {
     const int u = item - args.n_full;

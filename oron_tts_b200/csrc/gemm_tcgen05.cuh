@@ -60,8 +60,6 @@ struct GemmArgs {
   const unsigned char* row_valid;  // [rows] explicit per-row validity (overrides seq_lens) or nullptr
   int mask_rows;               // EPI_GATE_RESID: skip rows t >= seq_len
   long long* dbg;              // optional [grid, 16] clock64 stamps (tools/kernel_bench.py --trace); nullptr in production
-  const void* prefetch;        // optional: weights of the NEXT GEMM, warmed into L2 by idle lanes (see l2_prefetch_slab)
-  long long prefetch_bytes;
 };
 
 #define ORON_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -630,8 +628,6 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tmem_relinquish_2sm();
   }
   pdl_launch_dependents();
-  if (args.prefetch != nullptr && warp == 0 && lane != 0)  // idle lanes of the TMA warp
-    l2_prefetch_slab(args.prefetch, args.prefetch_bytes, (long long)blockIdx.x * 31 + (lane - 1), (long long)gridDim.x * 31);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();

@@ -40,18 +40,6 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------
-// L2 prefetch of a weight slab that a LATER kernel will stream with TMA. The 856 MB of bf16 weights of one NFE
-// never survive in the 126 MB L2, so every GEMM would start on cold HBM reads; the kernel that runs just before
-// (LayerNorm, attention, the previous GEMM) has idle memory bandwidth and warms the next weights instead.
-// `worker` / `n_workers`: this thread's index among the threads that share the job (128-byte lines, strided).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void l2_prefetch_slab(const void* base, long long bytes, long long worker, long long n_workers) {
-  const char* p = reinterpret_cast<const char*>(base);
-  for (long long off = worker * 128; off < bytes; off += n_workers * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-}
-
-// ---------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

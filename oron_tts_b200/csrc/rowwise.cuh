@@ -33,17 +33,12 @@ struct LnArgs {
   __nv_bfloat16* out_bf16;  // [rows, ldo] or nullptr
   float* out_f32;           // [rows, ldo] or nullptr
   long long ldo;
-  const void* prefetch;     // optional: weights of the GEMM that follows, warmed into L2 (see l2_prefetch_slab)
-  long long prefetch_bytes;
 };
 
 template <int C>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnArgs a) {
   constexpr int V4 = C / 128;  // float4 per lane
   pdl_launch_dependents();
-  if (a.prefetch != nullptr)  // independent of the previous kernel: issue before the dependency wait
-    l2_prefetch_slab(a.prefetch, a.prefetch_bytes, (long long)blockIdx.x * blockDim.x + threadIdx.x,
-                     (long long)gridDim.x * blockDim.x);
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;

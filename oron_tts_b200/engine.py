@@ -239,9 +239,6 @@ class DiTEngine:
         self._ws: dict = {}
         self.use_graph = True
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (not seen by oron_launch_count)
-        # every kernel warms the weights of the GEMM that follows it into L2 (ORON_PREFETCH=0 disables, for A/B runs)
-        import os
-        self.prefetch_weights = os.environ.get("ORON_PREFETCH", "1") != "0"
 
     # -------------------------------------------------------------------------------------------
     def workspace(self, nb: int, nbp: int, tpad: int, steps: int, keep_traj: bool) -> Workspace:
@@ -341,22 +338,19 @@ class DiTEngine:
 
         for i, blk in enumerate(w.blocks):
             o = i * 6 * D  # (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) — modules.py:215-217
-            pf = self.prefetch_weights
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
-                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm,
-                          prefetch=blk["wqkv"] if pf else None, **common)
+                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
                    rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
-                        scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws, prefetch=blk["wo"] if pf else None)
+                        scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
                    mask_rows=True, block_n=bn_big, two_sm=True, **common)
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
-                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm,
-                          prefetch=blk["w1"] if pf else None, **common)
+                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
-                   block_n=bn_big, two_sm=True, prefetch=blk["w2"] if pf else None, **common)
+                   block_n=bn_big, two_sm=True, **common)
             L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
                    block_n=bn_big, two_sm=True, **common)
