@@ -186,6 +186,9 @@ def run_ours(args) -> dict:
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if rank == 0 and not args.no_secondary:
+        with torch.inference_mode():
+            out["secondary"] = secondary_cfg4(model, voc, dev)
     if rank == 0:
         print("[bench] main legs done: " + json.dumps({k: out[k] for k in ("value", "ms_per_step", "ms_per_nfe", "e2e")}),
               file=sys.stderr, flush=True)
@@ -263,6 +266,45 @@ def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
     }
 
 
+def secondary_cfg4(model, voc, dev) -> dict:
+    """BASELINE config 4 (not the headline): log-mel STFT and Vocos decode on 64 x 30 s clips, inputs resident in HBM.
+    Reports the Vocos real-time factor (decode seconds / audio seconds) and the achieved HBM bandwidth of the fused
+    log-mel kernel against its algorithmic bytes (4 B/sample read + 400 B/frame written)."""
+    nb, S = 64, 720000
+    g = torch.Generator(device=dev).manual_seed(4)
+    wav = (torch.rand(nb, S, device=dev, generator=g) * 2 - 1) * 0.3
+    ap = model._audio_processor
+
+    def timeit(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    ms_mel, mel = timeit(lambda: ap.mel_spectrogram(wav))
+    frames = mel.shape[-1]
+    mel_bytes = nb * S * 4 + nb * 100 * frames * 4
+    ms_voc, w = timeit(lambda: voc.decode(mel), reps=3)
+    audio_s = nb * w.shape[-1] / 24000.0
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        peaks = json.load(open(pth))
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    return {
+        "workload": "cfg4: 64 x 30 s clips (24 kHz, n_fft 1024, hop 256, 100 mels)",
+        "logmel_ms": round(ms_mel, 3), "logmel_gbs": round(mel_bytes / ms_mel / 1e6, 1), "logmel_hbm_frac": round(mel_bytes / ms_mel / 1e6 / hbm, 4),
+        "vocos_ms": round(ms_voc, 3), "vocos_rtf": round(ms_voc / 1e3 / audio_s, 7), "vocos_audio_s_per_s": round(audio_s / (ms_voc / 1e3), 1),
+        "vocos_tflops": round(nb * frames * 27.0e6 / (ms_voc * 1e-3) / 1e12, 1),
+    }
+
+
 # ----------------------------------------------------------------------------------------------------
 def cpu_baseline(nfe: int = 1) -> dict:
     """The reference algorithm on the host cores (oracle port, fp32, all torch threads): `nfe` CFG NFE steps of
@@ -320,6 +362,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-4 (log-mel / Vocos) side measurement")
     a = ap.parse_args()
     res = run_reference(a) if a.impl == "reference" else run_ours(a)
     if res:

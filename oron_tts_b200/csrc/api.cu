@@ -266,6 +266,9 @@ static AttnPlan attn_plan(int nbatch, int rows_per_batch, int heads, bool have_w
     int parts = slots / p.n_tail;
     if (parts > kv_tiles / 2) parts = kv_tiles / 2;  // at least two key tiles per part
     if (parts > 8) parts = 8;
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("ORON_ATT_PARTS"); cap = e ? atoi(e) : 8; }
+    if (parts > cap) parts = cap;
     if (parts >= 2) p.parts = parts;
   }
   if (p.parts == 1) { p.n_full = p.items; p.n_tail = 0; }
