@@ -1,9 +1,15 @@
 // Log-mel STFT front end, Vocos iSTFT head and peak normalisation (n_fft 1024, hop 256).
-// Both transforms run a 1024-point radix-4 Stockham FFT in shared memory and pack TWO real
-// frames into one complex transform (frame A -> real part, frame B -> imaginary part), so the
-// complex spectrum / frame buffers never touch HBM: log-mel reads the waveform once and writes
-// [n_mels, T]; the iSTFT reads the head activations once and writes the waveform once.
+// Both transforms pack TWO real frames into one 1024-point complex FFT (frame A -> real part,
+// frame B -> imaginary part) that a single warp runs in registers (fft_warp.cuh), so a CTA of 8 warps
+// transforms 16 frames between two block barriers and the complex spectra / frame buffers never touch
+// HBM: log-mel reads the waveform once and writes [n_mels, T]; the iSTFT reads the head activations
+// once and writes the waveform once.
+//
+// These kernels are bound by fp32 instruction issue, not by HBM: one packed transform is ~1.2 k
+// instructions per lane against 4 KB (log-mel) / 8.4 KB (iSTFT) of HBM traffic per frame pair
+// ("audio kernels").
 #include "../../include/oron_b200.h"
+#include "fft_warp.cuh"
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -14,249 +20,313 @@ namespace {
 constexpr int NFFT = 1024;
 constexpr int HOP = 256;
 constexpr int NBIN = 513;
-constexpr int FFT_THREADS = 256;
+constexpr int AUD_WARPS = 8;                   // one frame pair per warp; two CTAs per SM overlap load and math phases
+constexpr int AUD_THREADS = AUD_WARPS * 32;
+constexpr int AUD_FR = 2 * AUD_WARPS;          // frames transformed per CTA pass
+constexpr int XB_BYTES = fw::XB_ELEMS * 8;     // per-warp exchange tile
 
-// W[n] = exp(-2 pi i n / 1024)
-__device__ __forceinline__ void fill_twiddles(float2* tw) {
-  for (int n = threadIdx.x; n < NFFT; n += blockDim.x) {
-    float s, c;
-    sincospif(float(n) * (2.0f / NFFT), &s, &c);
-    tw[n] = make_float2(c, -s);
-  }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// In-place-ish 1024-point complex FFT over two smem buffers; 256 threads, 5 radix-4 passes.
-// INVERSE uses conjugated twiddles (no 1/N scaling). Result ends in `a` if the pass count is even,
-// else in `b`: 5 passes -> result in b.  Caller must __syncthreads() before reading.
-template <bool INVERSE>
-__device__ __forceinline__ void fft1024(float2* a, float2* b, const float2* tw) {
-  float2* src = a;
-  float2* dst = b;
-  const int j = threadIdx.x;  // 0..255
-#pragma unroll
-  for (int Ns = 1; Ns < NFFT; Ns <<= 2) {
-    const int k = j & (Ns - 1);
-    float2 v[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = src[j + r * (NFFT / 4)];
-    if (Ns > 1) {
-      const int tstep = k * (NFFT / 4 / Ns);  // angle index for r = 1
-#pragma unroll
-      for (int r = 1; r < 4; ++r) {
-        float2 w = tw[r * tstep];
-        if (INVERSE) w.y = -w.y;
-        v[r] = cmul(v[r], w);
-      }
-    }
-    const float2 a0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-    const float2 a1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-    const float2 a2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-    const float2 d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-    // forward: multiply by -i -> (y, -x); inverse: multiply by +i -> (-y, x)
-    const float2 a3 = INVERSE ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-    const int base = (j / Ns) * Ns * 4 + k;
-    dst[base] = make_float2(a0.x + a2.x, a0.y + a2.y);
-    dst[base + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-    dst[base + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-    dst[base + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
-    __syncthreads();
-    float2* t = src; src = dst; dst = t;
-  }
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // ---------------------------------------------------------------------------
 // log-mel
 // ---------------------------------------------------------------------------
-constexpr int MEL_FR = 32;       // frames per CTA
 constexpr int MEL_MAXBAND = 32;  // widest triangular filter (bins) kept in smem
 constexpr int MEL_MAXM = 128;
-constexpr int MEL_SMEM = 3 * NFFT * 8 + NFFT * 4 + 2 * (NBIN + 3) * 4 + MEL_MAXM * MEL_MAXBAND * 4 +
-                         MEL_FR * (MEL_MAXM + 1) * 4 + 2 * MEL_MAXM * 4;
+constexpr int MAG_LD = 544;      // floats between the two magnitude rows inside a warp tile
+constexpr int MEL_SMEM = AUD_WARPS * XB_BYTES + NFFT * 8 + NFFT * 4 + MEL_MAXBAND * MEL_MAXM * 4 +
+                         AUD_FR * (MEL_MAXM + 1) * 4 + 2 * MEL_MAXM * 4;
 
-__global__ void __launch_bounds__(FFT_THREADS)
-logmel_kernel(const float* __restrict__ wav, long long ld_wav, int n_samples, int n_frames,
+__global__ void __launch_bounds__(AUD_THREADS, 2)
+logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_samples, int n_frames,
               const float* __restrict__ window, const float* __restrict__ fb, int n_mels, float clip,
               float* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  float2* bufA = reinterpret_cast<float2*>(dsm);
-  float2* bufB = bufA + NFFT;
-  float2* tw = bufB + NFFT;
+  float2* xb_all = reinterpret_cast<float2*>(dsm);
+  float2* tw = xb_all + AUD_WARPS * fw::XB_ELEMS;
   float* win = reinterpret_cast<float*>(tw + NFFT);
-  float (*mag)[NBIN + 3] = reinterpret_cast<float (*)[NBIN + 3]>(win + NFFT);
-  float (*fbs)[MEL_MAXBAND] = reinterpret_cast<float (*)[MEL_MAXBAND]>(&mag[2][0]);
-  float (*mel_s)[MEL_MAXM + 1] = reinterpret_cast<float (*)[MEL_MAXM + 1]>(&fbs[MEL_MAXM][0]);
-  int* band_lo = reinterpret_cast<int*>(&mel_s[MEL_FR][0]);
+  float (*fbs)[MEL_MAXM] = reinterpret_cast<float (*)[MEL_MAXM]>(win + NFFT);  // [band bin][filter]
+  float (*mel_s)[MEL_MAXM + 1] = reinterpret_cast<float (*)[MEL_MAXM + 1]>(&fbs[MEL_MAXBAND][0]);
+  int* band_lo = reinterpret_cast<int*>(&mel_s[AUD_FR][0]);
   int* band_n = band_lo + MEL_MAXM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* xb = xb_all + warp * fw::XB_ELEMS;
+  float* magA = reinterpret_cast<float*>(xb);
+  float* magB = magA + MAG_LD;
 
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * MEL_FR;
-  const float* x = wav + (long long)b * ld_wav;
-
-  fill_twiddles(tw);
+  // ---- once per (persistent) CTA: twiddles, window, and the band of every triangular mel filter ----
+  fw::fill_twiddle_table(tw);
   for (int n = threadIdx.x; n < NFFT; n += blockDim.x) win[n] = window[n];
-  // band limits of every mel filter (filters are contiguous triangles)
-  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < NBIN; ++k) {
-      if (fb[(long long)k * n_mels + m] != 0.f) {
-        if (lo < 0) lo = k;
-        hi = k;
-      }
+  for (int m = threadIdx.x; m < MEL_MAXM; m += blockDim.x) { band_lo[m] = NBIN; band_n[m] = -1; }  // band_n holds "hi" for now
+  __syncthreads();
+  for (int i = threadIdx.x; i < NBIN * n_mels; i += blockDim.x) {
+    if (fb[i] != 0.f) {
+      const int k = i / n_mels, m = i - k * n_mels;
+      atomicMin(&band_lo[m], k);
+      atomicMax(&band_n[m], k);
     }
-    if (lo < 0) { lo = 0; hi = -1; }
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < MEL_MAXM; m += blockDim.x) {
+    const bool any = m < n_mels && band_lo[m] <= band_n[m];
+    const int lo = any ? band_lo[m] : 0;
+    const int n = any ? band_n[m] - band_lo[m] + 1 : 0;
     band_lo[m] = lo;
-    band_n[m] = hi - lo + 1;
-    for (int i = 0; i < MEL_MAXBAND; ++i)
-      fbs[m][i] = (i <= hi - lo && i < MEL_MAXBAND) ? fb[(long long)(lo + i) * n_mels + m] : 0.f;
+    band_n[m] = n;
+    for (int i = 0; i < MEL_MAXBAND; ++i) fbs[i][m] = (i < n && n <= MEL_MAXBAND) ? fb[(long long)(lo + i) * n_mels + m] : 0.f;
   }
   __syncthreads();
 
-  const int nfr = min(MEL_FR, n_frames - t0);
-  for (int f = 0; f < nfr; f += 2) {
-    // frame pair (t0+f, t0+f+1): reflect-padded (center=True) windowed samples
-    const bool hasB = (f + 1 < nfr);
-    for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
-      int nA = (t0 + f) * HOP + i - NFFT / 2;
-      if (nA < 0) nA = -nA;
-      if (nA >= n_samples) nA = 2 * (n_samples - 1) - nA;
-      float vb = 0.f;
-      if (hasB) {
-        int nB = (t0 + f + 1) * HOP + i - NFFT / 2;
-        if (nB < 0) nB = -nB;
-        if (nB >= n_samples) nB = 2 * (n_samples - 1) - nB;
-        vb = x[nB] * win[i];
-      }
-      bufA[i] = make_float2(x[nA] * win[i], vb);
-    }
-    __syncthreads();
-    fft1024<false>(bufA, bufB, tw);  // 5 passes: result in bufB (fft1024 ends with a barrier)
-    // split the two real spectra and take magnitudes
-    for (int k = threadIdx.x; k < NBIN; k += blockDim.x) {
-      const float2 z = bufB[k];
-      const float2 zn = bufB[(NFFT - k) & (NFFT - 1)];
-      const float ar = 0.5f * (z.x + zn.x), ai = 0.5f * (z.y - zn.y);
-      const float br = 0.5f * (z.y + zn.y), bi = -0.5f * (z.x - zn.x);
-      mag[0][k] = sqrtf(ar * ar + ai * ai);
-      mag[1][k] = sqrtf(br * br + bi * bi);
-    }
-    __syncthreads();
-    // banded mel projection: threads [0,128) frame A, [128,256) frame B
-    {
-      const int which = threadIdx.x >> 7;
-      const int m = threadIdx.x & 127;
-      if (m < n_mels && (which == 0 || hasB)) {
-        const int lo = band_lo[m], n = band_n[m];
-        float acc = 0.f;
-        if (n <= MEL_MAXBAND) {
-          for (int i = 0; i < n; ++i) acc += fbs[m][i] * mag[which][lo + i];
-        } else {
-          for (int i = 0; i < n; ++i) acc += fb[(long long)(lo + i) * n_mels + m] * mag[which][lo + i];
+  const int chunks_per_clip = (n_frames + AUD_FR - 1) / AUD_FR;
+  for (int chunk = blockIdx.x; chunk < nb * chunks_per_clip; chunk += gridDim.x) {
+    const int b = chunk / chunks_per_clip;
+    const int t0 = (chunk - b * chunks_per_clip) * AUD_FR;
+    const float* x = wav + (long long)b * ld_wav;
+    const int fA = t0 + 2 * warp;
+    if (fA < n_frames) {  // warp-uniform
+      const bool hasB = fA + 1 < n_frames;
+      // frame pair (fA, fA+1): reflect-padded (center=True) windowed samples, lane holds n = lane + 32 n1
+      float2 v[32];
+      const int base = fA * HOP - NFFT / 2 + lane;
+      if (base - lane >= 0 && base - lane + NFFT + HOP <= n_samples) {  // interior: no reflection
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float w = win[lane + 32 * n1];
+          v[n1] = make_float2(x[base + 32 * n1] * w, x[base + HOP + 32 * n1] * w);
         }
-        mel_s[f + which][m] = logf(fmaxf(acc, clip));
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float w = win[lane + 32 * n1];
+          int nA = base + 32 * n1;
+          if (nA < 0) nA = -nA;
+          if (nA >= n_samples) nA = 2 * (n_samples - 1) - nA;
+          float vb = 0.f;
+          if (hasB) {
+            int nB = base + HOP + 32 * n1;
+            if (nB < 0) nB = -nB;
+            if (nB >= n_samples) nB = 2 * (n_samples - 1) - nB;
+            vb = x[nB] * w;
+          }
+          v[n1] = make_float2(x[nA] * w, vb);
+        }
+      }
+      fw::fft1024_warp<false>(v, xb, tw, lane);
+      // split the two real spectra: bin k = lane + 32 k2 needs Z[k] and Z[1024 - k]; the latter sits in lane
+      // (32 - lane) & 31, register 31 - k2 (lane 0: own register (32 - k2) & 31)
+      const int src = (32 - lane) & 31;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const float2 z = v[k2];
+        float2 zp;
+        zp.x = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
+        zp.y = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
+        if (lane == 0) zp = v[(32 - k2) & 31];
+        const float ar = 0.5f * (z.x + zp.x), ai = 0.5f * (z.y - zp.y);
+        const float br = 0.5f * (z.y + zp.y), bi = 0.5f * (zp.x - z.x);
+        magA[lane + 32 * k2] = sqrt_approx(ar * ar + ai * ai);
+        magB[lane + 32 * k2] = sqrt_approx(br * br + bi * bi);
+      }
+      if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
+        magA[512] = fabsf(v[16].x);
+        magB[512] = fabsf(v[16].y);
+      }
+      __syncwarp();
+      // banded mel projection: lane -> filters lane, lane+32, ...
+      for (int m = lane; m < n_mels; m += 32) {
+        const int lo = band_lo[m], n = band_n[m];
+        float accA = 0.f, accB = 0.f;
+        if (n <= MEL_MAXBAND) {
+          for (int i = 0; i < n; ++i) {
+            const float f = fbs[i][m];
+            accA += f * magA[lo + i];
+            accB += f * magB[lo + i];
+          }
+        } else {
+          for (int i = 0; i < n; ++i) {
+            const float f = fb[(long long)(lo + i) * n_mels + m];
+            accA += f * magA[lo + i];
+            accB += f * magB[lo + i];
+          }
+        }
+        mel_s[2 * warp][m] = logf(fmaxf(accA, clip));
+        mel_s[2 * warp + 1][m] = logf(fmaxf(accB, clip));
       }
     }
     __syncthreads();
-  }
-  // out[b, m, t0 + f]: contiguous along frames
-  for (int i = threadIdx.x; i < n_mels * MEL_FR; i += blockDim.x) {
-    const int m = i / MEL_FR, f = i % MEL_FR;
-    if (f < nfr) out[((long long)b * n_mels + m) * n_frames + t0 + f] = mel_s[f][m];
+    // out[b, m, t0 + f]: contiguous along frames
+    const int nfr = min(AUD_FR, n_frames - t0);
+    for (int i = threadIdx.x; i < n_mels * AUD_FR; i += blockDim.x) {
+      const int m = i / AUD_FR, f = i % AUD_FR;
+      if (f < nfr) out[((long long)b * n_mels + m) * n_frames + t0 + f] = mel_s[f][m];
+    }
+    __syncthreads();  // mel_s and the warp tiles are reused by the next chunk
   }
 }
 
 // ---------------------------------------------------------------------------
 // iSTFT head: spectrum from the head activations -> irfft -> window -> overlap-add -> envelope
 // ---------------------------------------------------------------------------
-constexpr int IST_HOPS = 29;             // output hops finished per CTA
-constexpr int IST_FR = IST_HOPS + 3;     // frames transformed per CTA (3-frame halo recomputed)
-constexpr int IST_SMEM = 3 * NFFT * 8 + NFFT * 4 + IST_HOPS * HOP * 4;
+constexpr int IST_HOPS = AUD_FR - 3;     // output hops finished per CTA pass (3-frame halo recomputed)
+constexpr int IST_SMEM = AUD_WARPS * XB_BYTES + NFFT * 8 + NFFT * 4;
 
-__global__ void __launch_bounds__(FFT_THREADS)
-istft_head_kernel(const float* __restrict__ h, long long ldh, int rows_per_batch, int n_frames,
+// exp / cos / sin of the head activations (Vocos ISTFTHead): fast-math units after an explicit
+// two-constant range reduction, absolute error ~1e-6 for |phase| < 1e3.
+__device__ __forceinline__ float2 polar_clip(float logmag, float phase) {
+  const float mg = fminf(__expf(logmag), 100.0f);
+  const float q = rintf(phase * 0.15915494309189535f);
+  float r = fmaf(q, -6.2831854820251465f, phase);   // hi part of 2 pi (fp32)
+  r = fmaf(q, 1.7484555e-7f, r);                    // 2 pi - hi
+  float s, c;
+  __sincosf(r, &s, &c);
+  return make_float2(mg * c, mg * s);
+}
+
+__global__ void __launch_bounds__(AUD_THREADS, 2)
+istft_head_kernel(const float* __restrict__ h, long long ldh, int rows_per_batch, int nb, int n_frames,
                   const float* __restrict__ window, int mode, float* __restrict__ out, long long ld_out) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  float2* bufA = reinterpret_cast<float2*>(dsm);
-  float2* bufB = bufA + NFFT;
-  float2* tw = bufB + NFFT;
+  float2* xb_all = reinterpret_cast<float2*>(dsm);
+  float2* tw = xb_all + AUD_WARPS * fw::XB_ELEMS;
   float* win = reinterpret_cast<float*>(tw + NFFT);
-  float* ola = win + NFFT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* xb = xb_all + warp * fw::XB_ELEMS;
+  float* frames = reinterpret_cast<float*>(xb_all);  // after the FFT: tile w holds frames 2w (floats [0,1024)) and 2w+1
+  constexpr int TILE_F = fw::XB_ELEMS * 2;           // floats per warp tile
+  constexpr int RAW_LD = TILE_F / 2;                 // second raw activation row inside the tile
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(h) & 15) == 0) && ((ldh & 3) == 0);
+  const bool out_vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((ld_out & 3) == 0);
 
-  const int b = blockIdx.y;
-  const int hop0 = blockIdx.x * IST_HOPS;          // first padded-domain hop finished by this CTA
-  const int hop1 = min(hop0 + IST_HOPS, n_frames + 3);
-  const int fr_lo = max(hop0 - 3, 0);
-  const int fr_hi = min(hop1 - 1, n_frames - 1);   // inclusive
-  const long long base_n = (long long)hop0 * HOP;  // padded-domain sample index of ola[0]
-
-  fill_twiddles(tw);
+  fw::fill_twiddle_table(tw);
   for (int n = threadIdx.x; n < NFFT; n += blockDim.x) win[n] = window[n];
-  for (int n = threadIdx.x; n < IST_HOPS * HOP; n += blockDim.x) ola[n] = 0.f;
   __syncthreads();
 
   const float scale = (mode == 1) ? (32.0f / NFFT) : (1.0f / NFFT);  // normalized=True: * sqrt(N)
-  for (int f = fr_lo; f <= fr_hi; f += 2) {
-    const bool hasB = (f + 1 <= fr_hi);
-    const float* ha = h + ((long long)b * rows_per_batch + f) * ldh;
-    const float* hb = ha + ldh;
-    // Hermitian-extend both half spectra and pack Z = A + iB
-    for (int k = threadIdx.x; k < NBIN; k += blockDim.x) {
-      float ar, ai, br = 0.f, bi = 0.f;
-      if (mode == 0) {
-        const float mg = fminf(expf(ha[k]), 100.0f);
-        float s, c;
-        sincosf(ha[NBIN + k], &s, &c);
-        ar = mg * c; ai = mg * s;
-        if (hasB) {
-          const float mg2 = fminf(expf(hb[k]), 100.0f);
-          sincosf(hb[NBIN + k], &s, &c);
-          br = mg2 * c; bi = mg2 * s;
+  const long long out_len = (long long)HOP * (n_frames - 1);
+  const int chunks_per_clip = (n_frames + 3 + IST_HOPS - 1) / IST_HOPS;
+  for (int chunk = blockIdx.x; chunk < nb * chunks_per_clip; chunk += gridDim.x) {
+    const int b = chunk / chunks_per_clip;
+    const int hop0 = (chunk - b * chunks_per_clip) * IST_HOPS;  // first padded-domain hop finished by this pass
+    const int hop1 = min(hop0 + IST_HOPS, n_frames + 3);
+    const int fr_lo = max(hop0 - 3, 0);
+    const int fr_hi = min(hop1 - 1, n_frames - 1);  // inclusive
+    const int f = fr_lo + 2 * warp;
+    if (f <= fr_hi) {  // warp-uniform
+      const bool hasB = f + 1 <= fr_hi;
+      const float* ha = h + ((long long)b * rows_per_batch + f) * ldh;
+      const float* hb = hasB ? ha + ldh : ha;
+      // stage the two activation rows (1026 floats each) in this warp's tile with one batch of async copies:
+      // every byte of the pass is in flight at once instead of trickling through the register file
+      float* rawA = reinterpret_cast<float*>(xb);
+      float* rawB = rawA + RAW_LD;
+      if (vec_ok) {
+#pragma unroll
+        for (int c = lane; c < 256; c += 32) {
+          cp_async16(rawA + 4 * c, ha + 4 * c);
+          cp_async16(rawB + 4 * c, hb + 4 * c);
+        }
+        if (lane < 2) {
+          cp_async4(rawA + 1024 + lane, ha + 1024 + lane);
+          cp_async4(rawB + 1024 + lane, hb + 1024 + lane);
         }
       } else {
-        ar = ha[2 * k]; ai = ha[2 * k + 1];
-        if (hasB) { br = hb[2 * k]; bi = hb[2 * k + 1]; }
-      }
-      if (k == 0 || k == NFFT / 2) { ai = 0.f; bi = 0.f; }  // C2R ignores these imaginary parts
-      // Z[k] = A[k] + i B[k] ; Z[N-k] = conj(A[k]) + i conj(B[k])
-      bufA[k] = make_float2(ar - bi, ai + br);
-      if (k != 0 && k != NFFT / 2) bufA[NFFT - k] = make_float2(ar + bi, br - ai);
-    }
-    __syncthreads();
-    fft1024<true>(bufA, bufB, tw);  // result in bufB: real = frame A, imag = frame B
-    // overlap-add frame A, then frame B (they overlap each other, so two phases)
-    for (int which = 0; which < 2; ++which) {
-      if (which == 1 && !hasB) break;
-      const long long fstart = (long long)(f + which) * HOP - base_n;  // offset of sample 0 in ola
-      for (int i = threadIdx.x; i < NFFT; i += blockDim.x) {
-        const long long p = fstart + i;
-        if (p >= 0 && p < (long long)(hop1 - hop0) * HOP) {
-          const float v = (which == 0 ? bufB[i].x : bufB[i].y) * scale * win[i];
-          ola[p] += v;
+        for (int c = lane; c < 2 * NBIN; c += 32) {
+          cp_async4(rawA + c, ha + c);
+          cp_async4(rawB + c, hb + c);
         }
       }
-      __syncthreads();
+      cp_async_wait_all();
+      __syncwarp();
+      // lower half of Z = A + iB in registers (bin k = lane + 32 n1), mirrored half Z[N-k] = conj(A) + i conj(B)
+      float2 v[32], zc[16];
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int k = lane + 32 * n1;
+        float2 A, B;
+        if (mode == 0) {
+          A = polar_clip(rawA[k], rawA[NBIN + k]);
+          B = polar_clip(rawB[k], rawB[NBIN + k]);
+        } else {
+          A = *reinterpret_cast<const float2*>(rawA + 2 * k);
+          B = *reinterpret_cast<const float2*>(rawB + 2 * k);
+        }
+        if (!hasB) B = make_float2(0.f, 0.f);
+        if (k == 0) { A.y = 0.f; B.y = 0.f; }  // C2R ignores the imaginary part of DC
+        v[n1] = make_float2(A.x - B.y, A.y + B.x);
+        zc[n1] = make_float2(A.x + B.y, B.x - A.y);
+      }
+      // Nyquist bin (k = 512): real parts only, lives in lane 0 register 16
+      float2 nyq = make_float2(0.f, 0.f);
+      if (lane == 0) {
+        if (mode == 0) {
+          nyq.x = polar_clip(rawA[512], rawA[NBIN + 512]).x;
+          nyq.y = hasB ? polar_clip(rawB[512], rawB[NBIN + 512]).x : 0.f;
+        } else {
+          nyq.x = rawA[1024];
+          nyq.y = hasB ? rawB[1024] : 0.f;
+        }
+      }
+      __syncwarp();  // the raw rows are consumed: the tile now belongs to the FFT
+      // upper half: register r in [16,32) of lane L is Z[32 r + L] = mirrored value of bin 1024 - 32 r - L, which
+      // lane (32 - L) & 31 computed as zc[31 - r] (L = 0: own zc[32 - r]; r = 16: the Nyquist bin)
+      const int src = (32 - lane) & 31;
+#pragma unroll
+      for (int r = 16; r < 32; ++r) {
+        float2 g;
+        g.x = __shfl_sync(0xffffffffu, zc[31 - r].x, src);
+        g.y = __shfl_sync(0xffffffffu, zc[31 - r].y, src);
+        if (lane == 0) g = (r == 16) ? nyq : zc[(32 - r) & 15];
+        v[r] = g;
+      }
+      fw::fft1024_warp<true>(v, xb, tw, lane);  // real = frame A, imag = frame B, time index n = lane + 32 k2
+      float* fa = reinterpret_cast<float*>(xb);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const float w = win[lane + 32 * k2] * scale;
+        fa[lane + 32 * k2] = v[k2].x * w;
+        fa[NFFT + lane + 32 * k2] = v[k2].y * w;
+      }
     }
-  }
-  // envelope-normalise and write; output index o = n - 512, valid o in [0, 256*(n_frames-1))
-  const long long out_len = (long long)HOP * (n_frames - 1);
-  for (int i = threadIdx.x; i < (hop1 - hop0) * HOP; i += blockDim.x) {
-    const long long n = base_n + i;
-    const long long o = n - NFFT / 2;
-    if (o < 0 || o >= out_len) continue;
-    // frames covering n: t in [ceil((n-1023)/256), floor(n/256)] intersect [0, n_frames-1]
-    int t_hi = int(n / HOP);
-    int t_lo = t_hi - 3;
-    if (t_lo < 0) t_lo = 0;
-    if (t_hi > n_frames - 1) t_hi = n_frames - 1;
-    float env = 0.f;
-    for (int t = t_lo; t <= t_hi; ++t) {
-      const float w = win[n - (long long)t * HOP];
-      env += w * w;
+    __syncthreads();
+    // overlap-add in ascending frame order, envelope-normalise and write; o = n - 512 in [0, 256*(n_frames-1)).
+    // Four consecutive samples per thread: hop h = hop0 + hrel receives samples [r + 256 (3 - q), +4) of frame h - 3 + q.
+    for (int i4 = threadIdx.x; i4 < (hop1 - hop0) * (HOP / 4); i4 += blockDim.x) {
+      const int hop = hop0 + (i4 >> 6);
+      const int r = (i4 & 63) * 4;
+      const long long o = (long long)hop * HOP + r - NFFT / 2;
+      if (o < 0 || o >= out_len) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = acc;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = hop - 3 + q;
+        if (t >= fr_lo && t <= fr_hi) {
+          const int slot = t - fr_lo, j = r + HOP * (3 - q);
+          const float4 fv = *reinterpret_cast<const float4*>(&frames[(slot >> 1) * TILE_F + (slot & 1) * NFFT + j]);
+          const float4 w = *reinterpret_cast<const float4*>(&win[j]);
+          acc.x += fv.x; acc.y += fv.y; acc.z += fv.z; acc.w += fv.w;
+          env.x += w.x * w.x; env.y += w.y * w.y; env.z += w.z * w.z; env.w += w.w * w.w;
+        }
+      }
+      float* dst = out + (long long)b * ld_out + o;
+      const float4 res = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
+      if (out_vec_ok) {
+        *reinterpret_cast<float4*>(dst) = res;
+      } else {
+        dst[0] = res.x; dst[1] = res.y; dst[2] = res.z; dst[3] = res.w;
+      }
     }
-    out[(long long)b * ld_out + o] = ola[i] / env;
+    __syncthreads();  // warp tiles are reused by the next chunk
   }
 }
 
@@ -294,15 +364,17 @@ extern "C" int oron_logmel(const float* wav, int64_t ld_wav, int32_t nb, int32_t
   if (nb <= 0 || n_mels <= 0 || n_mels > MEL_MAXM) return fail(ORON_ERR_BAD_ARG, "logmel: n_mels must be in [1,128]");
   if (n_samples <= NFFT / 2) return fail(ORON_ERR_BAD_ARG, "logmel: reflect padding needs more than 512 samples");
   const int n_frames = 1 + n_samples / HOP;
-  dim3 grid((n_frames + MEL_FR - 1) / MEL_FR, nb);
+  const long long chunks = (long long)((n_frames + AUD_FR - 1) / AUD_FR) * nb;
+  const long long cap = 2LL * num_sms();  // persistent, two 8-warp CTAs per SM: the table setup is amortised over many chunks
+  dim3 grid((unsigned)(chunks < cap ? chunks : cap));
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_SMEM);
     if (e != cudaSuccess) return fail(int(e), "logmel smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  logmel_kernel<<<grid, FFT_THREADS, MEL_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-      wav, ld_wav, n_samples, n_frames, window, fb, n_mels, clip, out);
+  logmel_kernel<<<grid, AUD_THREADS, MEL_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+      wav, ld_wav, nb, n_samples, n_frames, window, fb, n_mels, clip, out);
   return check_launch("logmel");
 }
 
@@ -311,15 +383,17 @@ extern "C" int oron_istft_head(const float* h, int64_t ldh, int32_t rows_per_bat
   if (!h || !window || !out) return fail(ORON_ERR_BAD_ARG, "istft_head: null pointer");
   if (n_frames < 2 || n_frames > rows_per_batch || nb <= 0) return fail(ORON_ERR_BAD_ARG, "istft_head: bad frame count");
   if (ldh < 2 * NBIN) return fail(ORON_ERR_BAD_ARG, "istft_head: ldh must be >= 1026");
-  dim3 grid((n_frames + 3 + IST_HOPS - 1) / IST_HOPS, nb);
+  const long long chunks = (long long)((n_frames + 3 + IST_HOPS - 1) / IST_HOPS) * nb;
+  const long long cap = 2LL * num_sms();
+  dim3 grid((unsigned)(chunks < cap ? chunks : cap));
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(istft_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IST_SMEM);
     if (e != cudaSuccess) return fail(int(e), "istft smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  istft_head_kernel<<<grid, FFT_THREADS, IST_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-      h, ldh, rows_per_batch, n_frames, window, mode, out, ld_out);
+  istft_head_kernel<<<grid, AUD_THREADS, IST_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, ldh, rows_per_batch, nb, n_frames, window, mode, out, ld_out);
   return check_launch("istft_head");
 }
 
