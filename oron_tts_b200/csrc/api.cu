@@ -215,6 +215,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM2_CASE(256, EPI_GATE_RESID)
   ORON_GEMM2_CASE(128, EPI_EMBED_DUAL)
   ORON_GEMM2_CASE(128, EPI_SCALE_RESID)
+  ORON_GEMM2_CASE(256, EPI_SCALE_RESID)
 #undef ORON_GEMM2_CASE
   if (two_sm) return fail(ORON_ERR_UNSUPPORTED, "gemm: no 2-SM kernel for block_n=%d epilogue=%d", d->block_n, epi);
 #define ORON_GEMM_CASE(BN_, EPI_) \
@@ -234,6 +235,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM_CASE(64, EPI_MISH_MASK_BF16)
   ORON_GEMM_CASE(64, EPI_MISH_MASK_RESID)
   ORON_GEMM_CASE(128, EPI_SCALE_RESID)
+  ORON_GEMM_CASE(256, EPI_SCALE_RESID)
   ORON_GEMM_CASE(64, EPI_SCALE_RESID)
 #undef ORON_GEMM_CASE
   return fail(ORON_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d epilogue=%d", d->block_n, epi);
@@ -416,6 +418,29 @@ extern "C" int oron_dwconv7_ln(const float* x, int64_t ldx, int32_t rows_per_bat
   const long long rows = (long long)rows_per_batch * nbatch;
   const int blocks = int((rows + 7) / 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(wb) |
+                         reinterpret_cast<uintptr_t>(ln_w) | reinterpret_cast<uintptr_t>(ln_b)) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0;
+  if (aligned && (C == 512 || C == 256)) {
+    // runs of consecutive frames per work item: long enough to amortise the 6 halo rows, short enough that the
+    // persistent grid (4 resident CTAs per SM) is balanced
+    static int occ512 = 0, occ256 = 0;
+    if (!occ512) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ512, dwconv7_ln_run_kernel<512>, 128, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ256, dwconv7_ln_run_kernel<256>, 64, 0);
+      if (occ512 < 1) occ512 = 1;
+      if (occ256 < 1) occ256 = 1;
+    }
+    const long long slots = (long long)(C == 512 ? occ512 : occ256) * num_sms();
+    long long run = (rows + slots - 1) / slots;
+    run = run < 16 ? 16 : (run > 64 ? 64 : run);
+    run = (run + 1) & ~1LL;
+    const long long items = ((rows_per_batch + run - 1) / run) * (long long)nbatch;
+    dim3 grid((unsigned)(items < slots ? items : slots));
+    if (C == 512) dwconv7_ln_run_kernel<512><<<grid, 128, 0, st>>>(a, int(run));
+    else dwconv7_ln_run_kernel<256><<<grid, 64, 0, st>>>(a, int(run));
+    return check_launch("dwconv7_ln");
+  }
   if (C == 512) dwconv7_ln_kernel<512><<<blocks, 256, 0, st>>>(a);
   else if (C == 256) dwconv7_ln_kernel<256><<<blocks, 256, 0, st>>>(a);
   else if (C == 128) dwconv7_ln_kernel<128><<<blocks, 256, 0, st>>>(a);

@@ -250,6 +250,127 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const DwLnArgs a) {
   }
 }
 
+// Sliding-window variant (the one the launcher picks when rows are 16-byte aligned): a CTA of C/4 threads owns
+// 4 channels per thread and walks a run of consecutive frames, keeping the 7-row window and the 7 taps of its
+// channels in registers, so every input row is read from HBM once (+6 halo rows per run) and nothing is
+// re-fetched through L1. Rows arrive through a shared-memory ring filled by 16-byte cp.async copies issued
+// DW_AHEAD rows ahead (each thread copies exactly the 16 bytes it later reads, so the ring needs no barrier):
+// ~24 KB in flight per CTA is what covers HBM latency at four CTAs per SM. Two frames per iteration; the
+// LayerNorm statistics cross the C/128 warps through shared memory (mean, then centred variance: the same
+// two-pass arithmetic as the warp-per-row kernel).
+constexpr int DW_AHEAD = 12;            // rows in flight per CTA (even)
+constexpr int DW_RING = DW_AHEAD + 2;   // + the pair consumed in the previous iteration (write-after-read safety)
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int C>
+__global__ void __launch_bounds__(C / 4) dwconv7_ln_run_kernel(const DwLnArgs a, int run) {
+  constexpr int NW = C / 128;
+  __shared__ float red[2][NW][2];
+  __shared__ __align__(16) float4 ring[DW_RING][C / 4];
+  const int c = 4 * threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int runs_per_seq = (a.rows_per_batch + run - 1) / run;
+
+  // taps of channels c..c+3: 28 consecutive floats of w[C,7]
+  float wt[4][7];
+  {
+    const float4* wp = reinterpret_cast<const float4*>(a.w + (long long)c * 7);
+    float raw[28];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const float4 q = __ldg(wp + i);
+      raw[4 * i] = q.x; raw[4 * i + 1] = q.y; raw[4 * i + 2] = q.z; raw[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) wt[j][k] = raw[7 * j + k];
+  }
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(a.wb + c));
+  const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(a.ln_b + c));
+
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // persistent over (sequence, run) items: grid is sized to the resident CTA slots, so there is no partial last wave
+  for (int item = blockIdx.x; item < runs_per_seq * a.nbatch; item += gridDim.x) {
+  const int b = item / runs_per_seq;
+  const int t0 = (item - b * runs_per_seq) * run;
+  const int t1 = min(t0 + run, a.rows_per_batch);
+  const int len = a.seq_lens ? a.seq_lens[b] : a.rows_per_batch;
+  const float* xb = a.x + (long long)b * a.rows_per_batch * a.ldx + c;
+  __nv_bfloat16* ob = a.out + (long long)b * a.rows_per_batch * a.ldo + c;
+  const int t_last = min(len - 1, t1 + 3);  // last row anyone in this run reads
+  auto issue_pair = [&](int q) {  // rows t0 + 2q + 3, +4 -> ring pair slot q % (DW_RING / 2)
+    const int ts = t0 + 2 * q + 3;
+    const int sl = 2 * (q % (DW_RING / 2));
+    if (ts >= 0 && ts <= t_last) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&ring[sl][threadIdx.x])),
+                   "l"(xb + (long long)ts * a.ldx) : "memory");
+    }
+    if (ts + 1 >= 0 && ts + 1 <= t_last) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&ring[sl + 1][threadIdx.x])),
+                   "l"(xb + (long long)(ts + 1) * a.ldx) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int q = 0; q < DW_AHEAD / 2; ++q) issue_pair(q);
+  float4 win[8];  // rows t-3 .. t+4 of the current frame pair; the first six come straight from global memory
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int tt = t0 - 3 + k;
+    win[k] = (tt >= 0 && tt < len) ? *reinterpret_cast<const float4*>(xb + (long long)tt * a.ldx) : zero4;
+  }
+
+  int p = 0;
+  for (int t = t0; t < t1; t += 2, ++p) {
+    cp_async_wait_group<DW_AHEAD / 2 - 1>();
+    {
+      const int sl = 2 * (p % (DW_RING / 2));
+      win[6] = (t + 3 <= t_last) ? ring[sl][threadIdx.x] : zero4;
+      win[7] = (t + 4 <= t_last) ? ring[sl + 1][threadIdx.x] : zero4;
+    }
+    issue_pair(p + DW_AHEAD / 2);  // overwrites the pair read one iteration ago
+    float4 y0 = bias, y1 = bias;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      y0.x += wt[0][k] * win[k].x; y0.y += wt[1][k] * win[k].y; y0.z += wt[2][k] * win[k].z; y0.w += wt[3][k] * win[k].w;
+      y1.x += wt[0][k] * win[k + 1].x; y1.y += wt[1][k] * win[k + 1].y; y1.z += wt[2][k] * win[k + 1].z; y1.w += wt[3][k] * win[k + 1].w;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) win[k] = win[k + 2];
+
+    float s0 = warp_sum(y0.x + y0.y + y0.z + y0.w), s1 = warp_sum(y1.x + y1.y + y1.z + y1.w);
+    if (lane == 0) { red[0][warp][0] = s0; red[0][warp][1] = s1; }
+    __syncthreads();
+    s0 = 0.f; s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { s0 += red[0][i][0]; s1 += red[0][i][1]; }
+    const float m0 = s0 * (1.0f / C), m1 = s1 * (1.0f / C);
+    y0.x -= m0; y0.y -= m0; y0.z -= m0; y0.w -= m0;
+    y1.x -= m1; y1.y -= m1; y1.z -= m1; y1.w -= m1;
+    float q0 = warp_sum(y0.x * y0.x + y0.y * y0.y + y0.z * y0.z + y0.w * y0.w);
+    float q1 = warp_sum(y1.x * y1.x + y1.y * y1.y + y1.z * y1.z + y1.w * y1.w);
+    if (lane == 0) { red[1][warp][0] = q0; red[1][warp][1] = q1; }
+    __syncthreads();
+    q0 = 0.f; q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { q0 += red[1][i][0]; q1 += red[1][i][1]; }
+    const float r0 = rsqrtf(q0 * (1.0f / C) + a.eps), r1 = rsqrtf(q1 * (1.0f / C) + a.eps);
+    uint2 o0, o1;
+    o0.x = pack_bf16x2(y0.x * r0 * g.x + be.x, y0.y * r0 * g.y + be.y);
+    o0.y = pack_bf16x2(y0.z * r0 * g.z + be.z, y0.w * r0 * g.w + be.w);
+    o1.x = pack_bf16x2(y1.x * r1 * g.x + be.x, y1.y * r1 * g.y + be.y);
+    o1.y = pack_bf16x2(y1.z * r1 * g.z + be.z, y1.w * r1 * g.w + be.w);
+    *reinterpret_cast<uint2*>(ob + (long long)t * a.ldo) = o0;
+    if (t + 1 < t1) *reinterpret_cast<uint2*>(ob + (long long)(t + 1) * a.ldo) = o1;
+  }
+  cp_async_wait_group<0>();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // GRN (modules.py:153-156): gx[b,c] = ||h[b,:,c]||_2 over the frames of the sequence,
 // nx = gx / (mean_c gx + 1e-6), y = gamma * (h * nx) + beta + h.   Two kernels:

@@ -145,7 +145,7 @@ class Vocos(nn.Module):
             L.gemm(n, blk["w1"], h, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_ERF, rows_per_batch=T, nbatch=B,
                    block_n=256 if H % 256 == 0 else 128)
             L.gemm(h, blk["w2"], x, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=T, nbatch=B, addend=x,
-                   gate=blk["gamma"], block_n=128)
+                   gate=blk["gamma"], block_n=256 if D % 256 == 0 else 128, two_sm=D % 256 == 0)
         L.ln_modulate(x, rows_per_batch=T, nbatch=B, eps=1e-6, scale=pk["fin_w"], shift=pk["fin_b"], add_one=False,
                       out_bf16=n)
         nh = pk["head_w"].shape[0]

@@ -423,6 +423,30 @@ def test_text_front_dwconv_grn(L):
         assert _rel(h2.view(nb, T, C2)[b, : lens[b]], refg[0]) < 5e-3
 
 
+@pytest.mark.parametrize("nb,T,C,aligned", [(1, 37, 512, True), (3, 301, 512, True), (2, 75, 256, True), (2, 75, 512, False),
+                                            (4, 2813, 512, True)])
+def test_dwconv7_ln_runs(L, nb, T, C, aligned):
+    """Sliding-window kernel (aligned rows) and the warp-per-row fallback (rows offset by one float) against
+    torch conv1d + layer_norm; odd run lengths, ragged seq_lens, several runs per sequence."""
+    g = torch.Generator(device=DEV).manual_seed(40 + T)
+    lens = torch.tensor([T if b % 2 == 0 else max(4, T - 11 * b) for b in range(nb)], device=DEV, dtype=torch.int32)
+    ld = C + (0 if aligned else 4)
+    buf = torch.randn(nb * T * ld + 4, device=DEV, generator=g)
+    x = buf[(0 if aligned else 1):][: nb * T * ld].view(nb * T, ld)[:, :C]
+    w = torch.randn(C, 1, 7, device=DEV, generator=g) * 0.3
+    wb, lw, lb = (torch.randn(C, device=DEV, generator=g) for _ in range(3))
+    out = torch.empty(nb * T, C, device=DEV, dtype=torch.bfloat16)
+    L.dwconv7_ln(x, rows_per_batch=T, nbatch=nb, seq_lens=lens, w=w.view(C, 7).contiguous(), wb=wb, ln_w=lw, ln_b=lb,
+                 eps=1e-6, out=out)
+    m = torch.arange(T, device=DEV)[None, :] < lens[:, None]
+    xin = x.reshape(nb, T, C) * m[..., None]
+    y = F.conv1d(xin.transpose(1, 2), w, wb, padding=3, groups=C).transpose(1, 2)
+    ref = F.layer_norm(y, (C,), lw, lb, eps=1e-6)
+    o = out.view(nb, T, C).float()
+    for b in range(nb):
+        assert _rel(o[b, : lens[b]], ref[b, : lens[b]]) < 4e-3
+
+
 # ------------------------------------------------------------------------------------------
 # audio
 # ------------------------------------------------------------------------------------------

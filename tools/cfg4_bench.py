@@ -90,9 +90,11 @@ def main():
 
         stage("transpose+cast", lambda: L.cast_rows_bf16(mel.transpose(1, 2).reshape(R, 100).float().contiguous(), a0[:, :100]),
               by=R * 100 * 4 * 3 + R * 100 * 2)
-        stage("embed_conv_gemm", lambda: L.gemm(a0, pk["embed_w"], x, epilogue=L.EPI_F32, bias=pk["embed_b"], rows_per_batch=T,
-                                                 nbatch=nb, taps=7, cin_blocks=pk["cin_pad"] // 64, pad=3, block_n=128),
-              fl=2.0 * R * 7 * pk["cin_pad"] * D)
+        for two in (False, True):
+            for bn in (128, 256):
+                stage(f"embed_conv_bn{bn}_2sm{int(two)}", lambda: L.gemm(a0, pk["embed_w"], x, epilogue=L.EPI_F32, bias=pk["embed_b"], rows_per_batch=T,
+                                                                          nbatch=nb, taps=7, cin_blocks=pk["cin_pad"] // 64, pad=3, block_n=bn, two_sm=two),
+                      fl=2.0 * R * 7 * pk["cin_pad"] * D)
         stage("ln_f32", lambda: L.ln_modulate(x, rows_per_batch=T, nbatch=nb, eps=1e-6, scale=pk["norm_w"], shift=pk["norm_b"],
                                               add_one=False, out_f32=x), by=R * D * 8)
         stage("dwconv7_ln", lambda: L.dwconv7_ln(x, rows_per_batch=T, nbatch=nb, seq_lens=None, w=blk["dw_w"], wb=blk["dw_b"],
@@ -102,13 +104,16 @@ def main():
                 stage(f"pw1_gelu_bn{bn}_2sm{int(two)}", lambda: L.gemm(n, blk["w1"], h, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_ERF,
                                                                         rows_per_batch=T, nbatch=nb, block_n=bn, two_sm=two), fl=2.0 * R * D * H)
         for two in (False, True):
-            stage(f"pw2_resid_bn128_2sm{int(two)}", lambda: L.gemm(h, blk["w2"], x, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=T,
-                                                                    nbatch=nb, addend=x, gate=blk["gamma"], block_n=128, two_sm=two), fl=2.0 * R * D * H)
+            for bn in (128, 256):
+                stage(f"pw2_resid_bn{bn}_2sm{int(two)}", lambda: L.gemm(h, blk["w2"], x, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=T,
+                                                                         nbatch=nb, addend=x, gate=blk["gamma"], block_n=bn, two_sm=two), fl=2.0 * R * D * H)
         nh = pk["head_w"].shape[0]
         ldh = (nh + 31) // 32 * 32
         hs = torch.empty(R, ldh, device=dev, dtype=F32)
-        stage("head_gemm", lambda: L.gemm(n, pk["head_w"], hs, epilogue=L.EPI_F32, bias=pk["head_b"], rows_per_batch=T, nbatch=nb,
-                                          block_n=128, n=nh), fl=2.0 * R * D * nh)
+        for two in (False, True):
+            for bn in (128, 256):
+                stage(f"head_gemm_bn{bn}_2sm{int(two)}", lambda: L.gemm(n, pk["head_w"], hs, epilogue=L.EPI_F32, bias=pk["head_b"], rows_per_batch=T,
+                                                                         nbatch=nb, block_n=bn, n=nh, two_sm=two), fl=2.0 * R * D * nh)
         hs.normal_(0, 0.5)
         wv = torch.empty(nb, (T - 1) * 256, device=dev, dtype=F32)
         stage("istft_head", lambda: L.istft_head(hs, pk["window"], wv, rows_per_batch=T, nb=nb, n_frames=T, mode=0),
