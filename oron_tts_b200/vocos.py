@@ -133,8 +133,11 @@ class Vocos(nn.Module):
         a0 = torch.zeros(R, pk["cin_pad"], device=dev, dtype=BF16)
         L.cast_rows_bf16(mel.transpose(1, 2).reshape(R, M).float().contiguous(), a0[:, :M])
         x = torch.empty(R, D, device=dev, dtype=F32)
+        # tile choice (tools/cfg4_bench.py): 256-wide tiles win once there are enough row tiles to fill 148 SMs;
+        # short utterances keep 128-wide tiles for more CTAs
+        big = R >= 8192
         L.gemm(a0, pk["embed_w"], x, epilogue=L.EPI_F32, bias=pk["embed_b"], rows_per_batch=T, nbatch=B, taps=7,
-               cin_blocks=pk["cin_pad"] // 64, pad=3, block_n=128)
+               cin_blocks=pk["cin_pad"] // 64, pad=3, block_n=256 if big else 128)
         L.ln_modulate(x, rows_per_batch=T, nbatch=B, eps=1e-6, scale=pk["norm_w"], shift=pk["norm_b"], add_one=False,
                       out_f32=x)
         n = torch.empty(R, D, device=dev, dtype=BF16)
@@ -145,13 +148,14 @@ class Vocos(nn.Module):
             L.gemm(n, blk["w1"], h, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_ERF, rows_per_batch=T, nbatch=B,
                    block_n=256 if H % 256 == 0 else 128)
             L.gemm(h, blk["w2"], x, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=T, nbatch=B, addend=x,
-                   gate=blk["gamma"], block_n=256 if D % 256 == 0 else 128, two_sm=D % 256 == 0)
+                   gate=blk["gamma"], block_n=256 if big else 128, two_sm=big)
         L.ln_modulate(x, rows_per_batch=T, nbatch=B, eps=1e-6, scale=pk["fin_w"], shift=pk["fin_b"], add_one=False,
                       out_bf16=n)
         nh = pk["head_w"].shape[0]
         ldh = (nh + 31) // 32 * 32
         hs = torch.empty(R, ldh, device=dev, dtype=F32)
-        L.gemm(n, pk["head_w"], hs, epilogue=L.EPI_F32, bias=pk["head_b"], rows_per_batch=T, nbatch=B, block_n=128, n=nh)
+        L.gemm(n, pk["head_w"], hs, epilogue=L.EPI_F32, bias=pk["head_b"], rows_per_batch=T, nbatch=B,
+               block_n=256 if big else 128, n=nh, two_sm=big)
         wav = torch.empty(B, (T - 1) * self.hop_length, device=dev, dtype=F32)
         L.istft_head(hs, pk["window"], wav, rows_per_batch=T, nb=B, n_frames=T, mode=0)
         return wav

@@ -256,3 +256,21 @@ def test_vocos_decode_vs_oracle():
     assert _rel(wav, ref) < 2e-2
     one = voc.decode(mel[0].to(DEV))
     assert one.shape == (1, 149 * 256)
+
+
+def test_vocos_decode_large_batch_tiles():
+    """Batches with >= 8192 frames take the 256-wide / 2-SM tiles (vocos.py `big`); they must agree with the
+    short-utterance tile path clip by clip, and with the CPU oracle."""
+    voc = Vocos()
+    sd = GW.fill_state_dict(voc.state_dict(), 4321)
+    voc.load_state_dict(sd, strict=True)
+    voc = voc.to(DEV).eval()
+    gen = torch.Generator().manual_seed(10)
+    mel = torch.randn(12, 100, 701, generator=gen) * 1.5 - 3.0
+    wav = voc.decode(mel.to(DEV))
+    assert wav.shape == (12, 700 * 256)
+    for b in (0, 5, 11):
+        one = voc.decode(mel[b].to(DEV))
+        assert _rel(wav[b], one[0]) < 2e-3
+    ref = AO.vocos_decode(sd, mel[:1])
+    assert _rel(wav[:1], ref) < 2e-2
