@@ -11,7 +11,8 @@ qkv = torch.randn(R, 3072, device=DEV, generator=g).bfloat16()
 qkv[:, 2048:] = torch.randn(R, 1024, device=DEV, generator=g).half().view(torch.bfloat16)
 o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
 lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
-AWS = L.attention_workspace(2, T, 16, DEV)
+WS = "--ws" in sys.argv  # key-split tail (needs the workspace); default = production path, one CTA per item
+AWS = L.attention_workspace(2, T, 16, DEV) if WS else None
 fn = lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=AWS)
 for _ in range(3): fn()
 torch.cuda.synchronize()
@@ -24,21 +25,25 @@ d = dbg.cpu()
 names = {1: "tj s_full", 2: "tj pass1", 3: "tj o_wait", 4: "tj pass2", 5: "tj arrive", 6: "loop done", 7: "partial written", 10: "fence+bar", 11: "count done", 12: "mma: p_full(2)", 13: "mma: PV(2) issued", 14: "softmax end", 15: "cta end"}
 starts = d[:, 0]
 print("global start spread (cycles are per-SM clocks; only relative values inside a CTA are meaningful)")
-for cta in (0, 100, 295, 296, 400, 575):
+for cta in (0, 100, 200, 295, 296, 320, 351):
     base = int(d[cta, 0])
     print(f"  cta {cta}: " + ", ".join(f"{names[i]}={int(d[cta, i]) - base}" for i in sorted(names) if int(d[cta, i]) != 0))
-d = d[:576]
+NCTA = 576 if WS else 352
+d = d[:NCTA]
 dur = (d[:, 15] - d[:, 0]).float()
 print("cta duration cycles: mean %.0f min %.0f max %.0f" % (dur.mean(), dur.min(), dur.max()))
 
 g0 = int(d[:, 8].min())
 st = (d[:, 8] - g0).double() / 1e3
 en = (d[:, 9] - g0).double() / 1e3
-print("globaltimer (us): full items start %.1f..%.1f end %.1f..%.1f | tail units start %.1f..%.1f end %.1f..%.1f" % (
+if not WS: print("globaltimer (us): full items start %.1f..%.1f end %.1f..%.1f | tail units start %.1f..%.1f end %.1f..%.1f" % (
     st[:296].min(), st[:296].max(), en[:296].min(), en[:296].max(), st[296:].min(), st[296:].max(), en[296:].min(), en[296:].max()))
-print("tail unit durations (us): mean %.2f max %.2f ; full item durations mean %.2f max %.2f" % (
+if not WS: print("tail unit durations (us): mean %.2f max %.2f ; full item durations mean %.2f max %.2f" % (
     (en[296:] - st[296:]).mean(), (en[296:] - st[296:]).max(), (en[:296] - st[:296]).mean(), (en[:296] - st[:296]).max()))
 
+print("kernel span (us): %.1f" % float(en.max() - st.min()))
+print("cta spans (us): mean %.2f min %.2f max %.2f" % (float((en - st).mean()), float((en - st).min()), float((en - st).max())))
+sys.exit(0)
 dd = (en - st)
 slow = torch.argsort(dd[296:], descending=True)[:3] + 296
 for cta in slow.tolist() + [300]:
