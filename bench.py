@@ -194,7 +194,7 @@ def run_ours(args) -> dict:
               file=sys.stderr, flush=True)
         with torch.inference_mode():
             out["roofline"] = roofline(eng, cfm, ref_mel, ids, dur, lens)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # contract: the CPU baseline is reported on rank 0 at N=1 only
             out["cpu_baseline"] = cpu_baseline(nfe=1)
     if world > 1:
         dist.barrier()
@@ -253,12 +253,24 @@ def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
         torch.cuda.synchronize()
         t[kind] = e0.elapsed_time(e1) / reps
     fl = algorithmic_flops_per_nfe(T_TOTAL)
+    # memory-bound family of the NFE: LayerNorm + AdaLN modulation, fp32 row in (4 B/elt) -> bf16 row out (2 B/elt).
+    # Its operands (17 MB per launch) stay L2-resident between the producing GEMM and this kernel, so the figure is
+    # an on-chip bandwidth; the HBM-streaming row-wise kernels are measured at config-4 size in `secondary`.
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    ln_bytes = 6.0 * ws.nbp * ws.tpad * eng.w.dim
+    ln_gbs = ln_bytes * launches["ln_modulate"] / (t["ln_modulate"] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the FFN-up GEMM, from one ncu --set full capture
+        traffic = json.load(open(tp)).get("gemm2_ffn_up_dram_bytes_per_launch")
     gemm_flops = fl["gemm"] + fl["other"]
     achieved = gemm_flops / (t["gemm"] * 1e-3) / 1e12
     total = sum(t.values())
     return {
         "bound": "tensor", "kernel": "gemm2_bf16_tcgen05_kernel (all Linear/conv launches of one NFE)", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-        "frac": round(achieved / peak, 4), "peak_source": which, "traffic": None,
+        "frac": round(achieved / peak, 4), "peak_source": which, "traffic": traffic,
+        "memory_bound": {"ln_modulate": {"bytes_per_launch": int(ln_bytes), "gbs": round(ln_gbs, 1), "frac_of_hbm_peak": round(ln_gbs / hbm, 3),
+                                         "note": "operands L2-resident between kernels"}},
         "flops_per_nfe": fl, "kernel_ms_per_nfe": {k: round(v, 4) for k, v in t.items()},
         "share_of_step": {k: round(v / total, 4) for k, v in t.items()}, "launches_per_nfe": launches,
         "avg_launch_us": {k: round(1e3 * v / max(launches[k], 1), 2) for k, v in t.items()},
@@ -341,6 +353,8 @@ def run_reference(args) -> dict:
     if rank != 0:
         return {}
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # all host threads (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     for _ in range(max(0, min(args.warmup, 1) - 1)):
         cpu_baseline(1)
     cb = cpu_baseline(max(1, min(args.steps, 3)))

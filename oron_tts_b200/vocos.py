@@ -146,7 +146,7 @@ class Vocos(nn.Module):
             L.dwconv7_ln(x, rows_per_batch=T, nbatch=B, seq_lens=None, w=blk["dw_w"], wb=blk["dw_b"], ln_w=blk["ln_w"],
                          ln_b=blk["ln_b"], eps=1e-6, out=n)
             L.gemm(n, blk["w1"], h, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_ERF, rows_per_batch=T, nbatch=B,
-                   block_n=256 if H % 256 == 0 else 128)
+                   block_n=256 if H % 256 == 0 else 128, two_sm=big and H % 256 == 0)
             L.gemm(h, blk["w2"], x, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=T, nbatch=B, addend=x,
                    gate=blk["gamma"], block_n=256 if big else 128, two_sm=big)
         L.ln_modulate(x, rows_per_batch=T, nbatch=B, eps=1e-6, scale=pk["fin_w"], shift=pk["fin_b"], add_one=False,
