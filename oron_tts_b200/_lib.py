@@ -83,6 +83,7 @@ class GemmDesc(ctypes.Structure):
         ("max_ctas", c_int32),
         ("two_sm", c_int32),
         ("f16_from_col", c_int32),
+        ("stream_k", c_int32),
         ("debug_stamps", c_void_p),
     ]
 
@@ -201,6 +202,7 @@ def gemm(
     two_sm: bool = False,
     debug_stamps: torch.Tensor | None = None,
     f16_from_col: int = 0,
+    stream_k: bool = False,
 ) -> None:
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16."""
     d = GemmDesc()
@@ -234,6 +236,7 @@ def gemm(
     d.max_ctas = int(max_ctas)
     d.two_sm = int(bool(two_sm))
     d.f16_from_col = int(f16_from_col)
+    d.stream_k = int(bool(stream_k))
     d.debug_stamps = _ptr(debug_stamps, torch.int64, "debug_stamps")
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16

@@ -123,11 +123,11 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   }
   const int tiles_m = ((a.rows_per_batch + GEMM_BM - 1) / GEMM_BM) * a.nbatch;
   const int tiles = ((tiles_m + 1) / 2) * ((a.N + BN - 1) / BN);
-  int pairs = tiles;
+  long long pairs = a.stream_k ? (long long)tiles * a.num_kb : tiles;  // stream-K: every pair takes an equal share of k-blocks
   const int cap = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
   if (pairs > cap) pairs = cap;
   if (pairs <= 0) return 0;
-  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta, tb, a);
+  cudaError_t le = launch_pdl(kern, dim3(unsigned(2 * pairs)), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta, tb, a);
   if (le != cudaSuccess) return fail(int(le), "gemm2 launch: %s", cudaGetErrorString(le));
   return check_launch("gemm2_bf16_tcgen05");
 }
@@ -177,6 +177,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   a.seq_lens = d->seq_lens;
   a.row_valid = d->row_valid;
   a.mask_rows = d->mask_rows;
+  a.stream_k = d->stream_k != 0 ? 1 : 0;
   a.dbg = reinterpret_cast<long long*>(d->debug_stamps);
 
   const int epi = d->epilogue;
@@ -187,6 +188,8 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   if (epi == EPI_QKV_ROPE && (!d->bias || !d->rope_cos || !d->rope_sin || d->N % 64 != 0 || d->block_n < 128))
     return fail(ORON_ERR_BAD_ARG, "gemm: QKV_ROPE needs bias, rope tables, N %% 64 == 0, block_n >= 128");
   if (epi == EPI_GATE_RESID && !d->gate) return fail(ORON_ERR_BAD_ARG, "gemm: GATE_RESID needs gate");
+  if (d->stream_k && !(d->two_sm && epi == EPI_GATE_RESID && taps == 1))
+    return fail(ORON_ERR_BAD_ARG, "gemm: stream_k needs two_sm, the GATE_RESID epilogue and taps == 1");
   if ((epi == EPI_EMBED_DUAL || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID) && !d->addend)
     return fail(ORON_ERR_BAD_ARG, "gemm: epilogue %d needs addend", epi);
   if (epi == EPI_EMBED_DUAL && !d->out2) return fail(ORON_ERR_BAD_ARG, "gemm: EMBED_DUAL needs out2");

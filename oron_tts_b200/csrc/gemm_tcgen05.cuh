@@ -59,6 +59,7 @@ struct GemmArgs {
   const int* seq_lens;         // [nbatch] valid rows per batch element or nullptr (all valid)
   const unsigned char* row_valid;  // [rows] explicit per-row validity (overrides seq_lens) or nullptr
   int mask_rows;               // EPI_GATE_RESID: skip rows t >= seq_len
+  int stream_k;                // 2-SM EPI_GATE_RESID only: split the K loops evenly over the SM pairs, partial sums land with f32 atomics
   long long* dbg;              // optional [grid, 16] clock64 stamps (tools/kernel_bench.py --trace); nullptr in production
 };
 
@@ -163,6 +164,11 @@ __device__ __forceinline__ uint2 pack4_f16(float4 v) {
   return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
 }
 
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
 // Fast path of one staged 32x32 block: every row and column of the block is in range, so the 8 row-groups are
 // loaded up front (ILP) and written with unguarded vector accesses. The epilogue is instruction-latency bound
 // (2 warps per scheduler), so straight-line code with independent chains matters more than instruction count.
@@ -191,13 +197,22 @@ __device__ __forceinline__ void epi_block_fast(const GemmArgs& args, const float
     for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = v[it];
   } else if constexpr (EPI == EPI_GATE_RESID) {
     float* o = reinterpret_cast<float*>(args.out) + grow0 * args.ldo + col;
-    float4 x[8];
+    if (args.stream_k) {
+      // this CTA holds only part of the K sum: x += gate * partial, fire-and-forget vector reductions
 #pragma unroll
-    for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(o + (long long)it * 4 * args.ldo);
+      for (int it = 0; it < 8; ++it) {
+        if (args.mask_rows && (t0 + 4 * it >= seq_len)) continue;
+        red_add4(o + (long long)it * 4 * args.ldo, mul4(g4, v[it]));
+      }
+    } else {
+      float4 x[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      if (args.mask_rows && (t0 + 4 * it >= seq_len)) continue;
-      *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = fma4(g4, v[it], x[it]);
+      for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(o + (long long)it * 4 * args.ldo);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        if (args.mask_rows && (t0 + 4 * it >= seq_len)) continue;
+        *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = fma4(g4, v[it], x[it]);
+      }
     }
   } else {
     // epilogues with an addend and a validity mask
@@ -259,7 +274,8 @@ __device__ __forceinline__ void epi_block_slow(const GemmArgs& args, const uint3
     } else if constexpr (EPI == EPI_GATE_RESID) {
       if (args.mask_rows && !valid) continue;
       float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col);
-      *o = fma4(g4, v, *o);
+      if (args.stream_k) red_add4(reinterpret_cast<float*>(o), mul4(g4, v));  // host guarantees N % 4 == 0 here
+      else *o = fma4(g4, v, *o);
     } else if constexpr (EPI == EPI_EMBED_DUAL) {
       const float4 a = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
       v = valid ? add4(v, a) : zero;
@@ -294,7 +310,7 @@ struct EpiCols {
 
 template <int BN, int EPI, int HN>
 __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmArgs& args, const int b, const int n0, const int cbeg,
-                                                       const int lane, EpiCols<HN>& pc) {
+                                                       const int lane, EpiCols<HN>& pc, const bool with_bias = true) {
   const int c4 = (lane & 7) * 4;
 #pragma unroll
   for (int j = 0; j < HN / 32; ++j) {
@@ -302,7 +318,7 @@ __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmArgs& args, con
     pc.b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     pc.g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
     if (col < args.N) {
-      if (args.bias != nullptr) pc.b4[j] = ldg4_guard(args.bias + col, col, args.N);
+      if (with_bias && args.bias != nullptr) pc.b4[j] = ldg4_guard(args.bias + col, col, args.N);
       if constexpr (EPI == EPI_GATE_RESID) {
         const long long step = args.step_ptr ? (long long)__ldg(args.step_ptr) : 0ll;
         pc.g4[j] = __ldg(reinterpret_cast<const float4*>(args.gate + step * args.gate_step_stride +
@@ -579,6 +595,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 // The two CTAs' row blocks are consecutive 128-row m-tiles (2*pm, 2*pm+1); they need not be adjacent in
 // memory (each CTA addresses its own (batch, t0) through the 3-D A map).
 // =====================================================================================================
+// Work walker of the 2-SM kernel. Plain: whole tiles, strided over the SM pairs. stream_k: the flat list of
+// (tile, k-block) units is cut into equal contiguous shares, so a pair runs up to two partial tiles ("segments")
+// and every pair is busy for the same time whatever the tile count (44 tiles on 74 pairs for the N=1024 GEMMs).
+struct SegWalk {
+  long long u, u_end;
+  int nkb, step;
+  bool sk;
+  int tile, kb0, kb1;
+  __device__ SegWalk(bool stream_k, int pair_id, int num_pairs, int num_tiles, int num_kb) {
+    sk = stream_k; nkb = num_kb; step = num_pairs;
+    if (sk) {
+      const long long U = (long long)num_tiles * num_kb;
+      u = (U * pair_id) / num_pairs;
+      u_end = (U * (pair_id + 1)) / num_pairs;
+    } else {
+      u = pair_id;
+      u_end = num_tiles;
+    }
+    tile = 0; kb0 = 0; kb1 = 0;
+  }
+  __device__ bool next() {
+    if (u >= u_end) return false;
+    if (sk) {
+      tile = int(u / nkb);
+      kb0 = int(u - (long long)tile * nkb);
+      const long long n = min((long long)(nkb - kb0), u_end - u);
+      kb1 = kb0 + int(n);
+      u += n;
+    } else {
+      tile = int(u); kb0 = 0; kb1 = nkb;
+      u += step;
+    }
+    return true;
+  }
+};
+
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
@@ -617,6 +669,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int tiles_n = (args.N + BN - 1) / BN;
   const int num_tiles = tiles_mp * tiles_n;
   const int num_kb = args.num_kb;
+  const bool sk = (EPI == EPI_GATE_RESID) && args.stream_k != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -648,13 +701,15 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      bool first_seg = true;
+      for (SegWalk w(sk, pair_id, num_pairs, num_tiles, num_kb); w.next(); first_seg = false) {
+        const int tile = w.tile;
         const int m_tile = 2 * (tile % tiles_mp) + rank;
         const int n_tile = tile / tiles_mp;
         const int b = m_tile / tiles_m_pb;  // a phantom m-tile (odd tile count) lands past the last batch element: zero fill
         const int t0 = (m_tile % tiles_m_pb) * GEMM_BM;
         const int n0 = n_tile * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 21);
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -663,8 +718,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const int a_row = t0 + kb / args.cpb - args.pad;
           tma_load_3d_2sm(sa, &tmA, full_bar(stage), a_col, a_row, b);
           tma_load_2d_2sm(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0 + rank * (BN / 2));
-          if (kb == 0 && tile == pair_id) ORON_STAMP(1);
-          if (kb == num_kb - 1 && tile == pair_id) ORON_STAMP(2);
+          if (kb == w.kb0 && first_seg) ORON_STAMP(1);
+          if (kb == w.kb1 - 1 && first_seg) ORON_STAMP(2);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -675,25 +730,25 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+      for (SegWalk w(sk, pair_id, num_pairs, num_tiles, num_kb); w.next(); ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u, 22);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, 23);
           tc_fence_after();
-          if (kb == 0 && it == 0) ORON_STAMP(3);
+          if (kb == w.kb0 && it == 0) ORON_STAMP(3);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16_ss_2sm(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_2sm(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
           umma_commit_2sm(empty_bar(stage), 3);
-          if (kb == num_kb - 1) { umma_commit_2sm(tfull_bar(as), 3); if (it < 2) ORON_STAMP(4 + it); }
+          if (kb == w.kb1 - 1) { umma_commit_2sm(tfull_bar(as), 3); if (it < 2) ORON_STAMP(4 + it); }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -704,14 +759,15 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     constexpr int HN = BN / 2;
     const int cbeg = chalf * HN;
     int it = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+    for (SegWalk w(sk, pair_id, num_pairs, num_tiles, num_kb); w.next(); ++it) {
+      const int tile = w.tile;
       const int m_tile = 2 * (tile % tiles_mp) + rank;
       const int n_tile = tile / tiles_mp;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
       const int b = m_tile < tiles_m ? m_tile / tiles_m_pb : 0;
       EpiCols<HN> pc;
-      gemm_epilogue_prefetch<BN, EPI, HN>(args, b, n_tile * BN, cbeg, lane, pc);
+      gemm_epilogue_prefetch<BN, EPI, HN>(args, b, n_tile * BN, cbeg, lane, pc, w.kb0 == 0);  // the bias rides with the first k-block
       mbar_wait(tfull_bar(as), aphase, 24);
       tc_fence_after();
       if (threadIdx.x == 64 && it < 2) ORON_STAMP(6 + 2 * it);

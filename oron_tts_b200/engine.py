@@ -15,12 +15,18 @@ noise draw (flow.py:270-283 semantics depend on torch.randn) and tiny integer/in
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
 
 from . import _lib as L
 
+# The FFN-down GEMM (N = dim, K = 4 dim) has 44 tiles for 74 SM pairs at config 2; stream-K gives every pair an equal
+# share of k-blocks instead (partial sums land in the fp32 residual stream with vector reductions, so the last bit
+# of a run depends on arrival order): 39.8 -> 33.8 us per call. The out-projection (K = dim) is too short to gain
+# (21.5 -> 23.6 us). ORON_STREAM_K=0 restores whole tiles.
+STREAM_K = os.environ.get("ORON_STREAM_K", "1") != "0"
 BF16 = torch.bfloat16
 F32 = torch.float32
 TILE = 128
@@ -346,14 +352,14 @@ class DiTEngine:
                         scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
-                   mask_rows=True, block_n=bn_big, two_sm=True, **common)
+                   mask_rows=True, block_n=bn_big, two_sm=True, **common)  # K = dim: too short for stream-K to pay
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
                    block_n=bn_big, two_sm=True, **common)
             L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                   block_n=bn_big, two_sm=True, **common)
+                   block_n=bn_big, two_sm=True, stream_k=STREAM_K, **common)
         o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
         L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o:], shift=tab[o + D:], mod_ld=mld, mod_nb=mod_nb,
                       step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)

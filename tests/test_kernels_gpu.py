@@ -271,10 +271,11 @@ def test_gemm_two_sm_fused_epilogues(L):
     upd = gate * (A.float() @ Wo.float().t() + bo)
     refx = x0 + torch.where(mask, upd, torch.zeros_like(upd))
     for bn in (128, 256):
-        x = x0.clone()
-        L.gemm(A, Wo, x, epilogue=L.EPI_GATE_RESID, bias=bo, rows_per_batch=T, nbatch=nb, gate=gate, seq_lens=lens,
-               mask_rows=True, block_n=bn, two_sm=True)
-        assert _rel(x, refx) < 2e-3, bn
+        for sk in (False, True):  # stream-K: equal k-block shares per SM pair, partial sums land with f32 reductions
+            x = x0.clone()
+            L.gemm(A, Wo, x, epilogue=L.EPI_GATE_RESID, bias=bo, rows_per_batch=T, nbatch=nb, gate=gate, seq_lens=lens,
+                   mask_rows=True, block_n=bn, two_sm=True, stream_k=sk)
+            assert _rel(x, refx) < 2e-3, (bn, sk)
     # f32 with ragged N and addend
     Wp = _bf(torch.randn(100, D, device=DEV, generator=g) / math.sqrt(D))
     bp = torch.randn(100, device=DEV, generator=g)
@@ -509,3 +510,27 @@ def test_peak_normalize(L):
         mx = x[b].abs().max()
         ref = x[b] if mx < 1e-8 else torch.clamp(x[b] / (mx + 1e-7), -1.0, 1.0)
         assert torch.allclose(out[b], ref, atol=1e-7)
+
+
+@pytest.mark.parametrize("nb,T,N,K,bn", [(2, 1408, 1024, 4096, 256), (2, 1408, 1024, 1024, 256), (3, 200, 512, 1536, 128),
+                                         (1, 130, 1024, 1024, 256)])
+def test_gemm_stream_k(L, nb, T, N, K, bn):
+    """Stream-K gated residual at the config-2 out-proj / FFN-down shapes, a ragged case with phantom m-tiles and a
+    tiny one (fewer tiles than SM pairs): x += gate * (A W^T + bias), rows beyond seq_len untouched."""
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(M + N + K + 1)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    gate = torch.randn(N, device=DEV, generator=g)
+    lens = torch.tensor([T if b % 2 == 0 else max(1, T - 37) for b in range(nb)], device=DEV, dtype=torch.int32)
+    x0 = torch.randn(M, N, device=DEV, generator=g)
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).reshape(M, 1)
+    upd = gate * (A.float() @ W.float().t() + bias)
+    ref = x0 + torch.where(mask, upd, torch.zeros_like(upd))
+    for _ in range(2):
+        x = x0.clone()
+        L.gemm(A, W, x, epilogue=L.EPI_GATE_RESID, bias=bias, rows_per_batch=T, nbatch=nb, gate=gate, seq_lens=lens,
+               mask_rows=True, block_n=bn, two_sm=True, stream_k=True)
+        assert _rel(x, ref) < 2e-3
+        assert torch.equal(x[~mask.squeeze(1)], x0[~mask.squeeze(1)])

@@ -80,6 +80,13 @@ def gemm_cases():
         cases.append((f"2SM ffn2       N=1024 K=4096 bn={bn}", 2 * R * 1024 * 4096,
                       lambda bn=bn: L.gemm(A4, W[(1024, 4096)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
                                            rows_per_batch=T, nbatch=2, block_n=bn, two_sm=True)))
+    for bn in (128, 256):
+        cases.append((f"2SM outproj SK N=1024 K=1024 bn={bn}", 2 * R * 1024 * 1024,
+                      lambda bn=bn: L.gemm(A1, W[(1024, 1024)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                           rows_per_batch=T, nbatch=2, block_n=bn, two_sm=True, stream_k=True)))
+        cases.append((f"2SM ffn2    SK N=1024 K=4096 bn={bn}", 2 * R * 1024 * 4096,
+                      lambda bn=bn: L.gemm(A4, W[(1024, 4096)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
+                                           rows_per_batch=T, nbatch=2, block_n=bn, two_sm=True, stream_k=True)))
     cases.append(("outproj    N=1024 K=1024 bn=64", 2 * R * 1024 * 1024,
                   lambda: L.gemm(A1, W[(1024, 1024)], xres, epilogue=L.EPI_GATE_RESID, bias=bias[1024], gate=gate,
                                  rows_per_batch=T, nbatch=2, block_n=64)))
