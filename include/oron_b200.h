@@ -126,12 +126,19 @@ int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo,
                         int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
                         void* workspace, int64_t workspace_bytes, oron_stream_t stream);
 /*
- * Optional scratch for oron_attention_bf16 (16-byte aligned, ZERO-FILLED once before its first use; the kernel
- * leaves it ready for the next call). With it, the (batch, head, query-tile) items of a partially filled last
- * wave are split along the keys and merged in-kernel, which evens out the exp2-bound work across the SMs.
- * Returns 0 when the shape needs no split. Passing NULL / 0 is always valid (no split).
+ * Optional workspace of oron_attention_bf16 (16-byte aligned). With it -- and once oron_attention_plan has filled
+ * it for the current sequence lengths -- calls with more (batch, head, query-tile) items than resident CTA slots
+ * (2 per SM) run a balanced persistent schedule: every CTA owns an equal share of the flat (item, key tile) list,
+ * items that straddle two shares are split along the keys, their normalised partial results (f16) are staged in the
+ * workspace and combined by a small merge kernel launched right after. Passing NULL / 0 is always valid (one CTA per
+ * item). The same workspace may be used by any number of calls with the planned shape and lengths.
  */
 int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_per_batch, int32_t heads);
+/* Writes the schedule for these sequence lengths (device array, or NULL = all rows valid) into the workspace; enqueue
+ * it on the same stream before the first oron_attention_bf16 that uses the workspace, and again whenever the lengths
+ * change. An attention call whose workspace holds no plan for its shape traps with a message. */
+int oron_attention_plan(const int32_t* seq_lens, int32_t nbatch, int32_t rows_per_batch, int32_t heads,
+                        void* workspace, int64_t workspace_bytes, oron_stream_t stream);
 
 /*
  * y = LayerNorm(x) * (add_one + scale) + shift, fp32 statistics, biased variance.
@@ -214,6 +221,9 @@ int oron_peak_normalize(const float* x, int64_t ldx, int32_t nb, int32_t n, floa
 
 /* Profiling aid: int64 [n_ctas, 16] device buffer that receives per-CTA clock64 stamps of the attention kernel; NULL disables. */
 void oron_debug_set_attention_stamps(void* buf);
+/* Test aid: attention schedule override. -1 = automatic (default), 0 = one CTA per item, 1 = balanced whenever a
+ * planned workspace is passed (exercises the split / merge path on small shapes). */
+void oron_debug_set_attention_schedule(int32_t mode);
 
 int oron_abi_version(void);
 const char* oron_last_error(void);

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "oron_gemm_bf16",
     "oron_attention_bf16",
     "oron_attention_workspace_bytes",
+    "oron_attention_plan",
     "oron_ln_modulate",
     "oron_cfg_euler_step",
     "oron_cast_rows_bf16",
@@ -36,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "oron_istft_head",
     "oron_peak_normalize",
     "oron_debug_set_attention_stamps",
+    "oron_debug_set_attention_schedule",
     "oron_abi_version",
     "oron_last_error",
     "oron_launch_count",
@@ -107,11 +109,14 @@ def lib() -> ctypes.CDLL:
     L.oron_abi_version.restype = c_int32
     L.oron_debug_set_attention_stamps.argtypes = [c_void_p]
     L.oron_debug_set_attention_stamps.restype = None
+    L.oron_debug_set_attention_schedule.argtypes = [c_int32]
+    L.oron_debug_set_attention_schedule.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                       c_void_p, c_float, c_void_p, c_int64, c_void_p]
     L.oron_attention_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     L.oron_attention_workspace_bytes.restype = c_int64
+    L.oron_attention_plan.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]
     L.oron_ln_modulate.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
                                    c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                                    c_void_p]
@@ -245,12 +250,22 @@ def gemm(
     _check(lib().oron_gemm_bf16(ctypes.byref(d), _stream()), "oron_gemm_bf16")
 
 
-def attention_workspace(nbatch: int, rows_per_batch: int, heads: int, device) -> torch.Tensor | None:
-    """Zero-filled scratch for `attention` (None when the shape needs no key split)."""
+def attention_workspace(nbatch: int, rows_per_batch: int, heads: int, device, seq_lens: torch.Tensor | None = None) -> torch.Tensor:
+    """Workspace for the balanced schedule of `attention`, planned for `seq_lens` (call `attention_plan` again when the
+    lengths change)."""
     n = int(lib().oron_attention_workspace_bytes(nbatch, rows_per_batch, heads))
-    if n == 0:
-        return None
-    return torch.zeros(n, dtype=torch.uint8, device=device)
+    ws = torch.zeros(n, dtype=torch.uint8, device=device)
+    attention_plan(ws, nbatch=nbatch, rows_per_batch=rows_per_batch, heads=heads, seq_lens=seq_lens)
+    return ws
+
+
+def attention_plan(workspace: torch.Tensor, *, nbatch: int, rows_per_batch: int, heads: int,
+                   seq_lens: torch.Tensor | None) -> None:
+    _check(
+        lib().oron_attention_plan(_ptr(seq_lens, torch.int32, "seq_lens"), nbatch, rows_per_batch, heads,
+                                  _ptr(workspace, torch.uint8, "workspace"), workspace.numel(), _stream()),
+        "oron_attention_plan",
+    )
 
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, *, nbatch: int, rows_per_batch: int, heads: int,

@@ -250,41 +250,53 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
 static long long* g_attn_dbg = nullptr;
 // profiling aid (tools/attn_trace.py): int64 [n_ctas, 16] device buffer receiving per-CTA clock64 stamps, or NULL
 extern "C" void oron_debug_set_attention_stamps(void* buf) { g_attn_dbg = reinterpret_cast<long long*>(buf); }
-// Work plan: items = (batch, head, 128-query tile). Two CTAs fit an SM, so `slots` = 2 * SMs items run concurrently.
-// The kernel is bound by the exp2 unit, i.e. by how evenly exp work is spread: a last, partially filled wave would
-// leave most SMs idle for a whole item (config 2: 352 items on 296 slots -> 2 waves for 1.19 waves of work). The
-// items of that last wave are therefore split along the keys into `parts` CTAs each (<= slots CTAs in total) whose
-// partial results are merged in-kernel by the last finisher.
-struct AttnPlan {
-  int q_tiles, items, n_full, n_tail, parts;
+// Work decomposition: items = (batch, head, 128-query tile); two CTAs fit an SM. One CTA per item leaves a partially
+// filled last wave (config 2: 352 items on 296 slots -> 2 waves for 1.19 waves of work) and pays the ~4 us prologue
+// (TMEM allocation, first Q/K/V loads) once per item. The balanced schedule launches exactly the resident slots and
+// gives each CTA an equal share of the flat (item, key tile) list (attn_tcgen05.cuh): it needs a workspace holding
+// the plan (oron_attention_plan, once per set of sequence lengths) and the partial results of the split items.
+static int g_attn_schedule = -1;
+extern "C" void oron_debug_set_attention_schedule(int32_t mode) { g_attn_schedule = mode; }
+static int attn_slots() { return 2 * num_sms(); }
+
+struct AttnWsLayout {
+  int grid, seg_stride;
+  int64_t off_nseg, off_segs, off_merge, off_cnt, off_ml, off_o, bytes;
 };
-static AttnPlan attn_plan(int nbatch, int rows_per_batch, int heads, bool have_ws) {
-  AttnPlan p;
-  p.q_tiles = (rows_per_batch + ATT_TILE - 1) / ATT_TILE;
-  p.items = p.q_tiles * heads * nbatch;
-  const int slots = 2 * num_sms();
-  const int kv_tiles = p.q_tiles;
-  p.n_full = (p.items / slots) * slots;
-  p.n_tail = p.items - p.n_full;
-  p.parts = 1;
-  if (have_ws && p.n_tail > 0 && kv_tiles >= 4) {
-    int parts = slots / p.n_tail;
-    if (parts > kv_tiles / 2) parts = kv_tiles / 2;  // at least two key tiles per part
-    if (parts > 8) parts = 8;
-    static int cap = -1;
-    if (cap < 0) { const char* e = getenv("ORON_ATT_PARTS"); cap = e ? atoi(e) : 8; }
-    if (parts > cap) parts = cap;
-    if (parts >= 2) p.parts = parts;
-  }
-  if (p.parts == 1) { p.n_full = p.items; p.n_tail = 0; }
-  return p;
+static AttnWsLayout attn_ws_layout(int nbatch, int rows_per_batch, int heads) {
+  AttnWsLayout w;
+  w.grid = attn_slots();
+  const int64_t q_tiles = (rows_per_batch + ATT_TILE - 1) / ATT_TILE;
+  const int64_t total_max = int64_t(nbatch) * heads * q_tiles * q_tiles;
+  w.seg_stride = int((total_max + w.grid - 1) / w.grid) + 2;  // whole items in a share <= its units, + the two partial ends
+  auto up = [](int64_t x) { return (x + 255) & ~int64_t(255); };
+  w.off_nseg = up(sizeof(AttnPlanHeader));
+  w.off_segs = up(w.off_nseg + int64_t(w.grid) * 4);
+  w.off_merge = up(w.off_segs + int64_t(w.grid) * w.seg_stride * int64_t(sizeof(AttnSeg)));
+  w.off_cnt = up(w.off_merge + int64_t(w.grid) * int64_t(sizeof(AttnMergeEnt)));
+  w.off_ml = up(w.off_cnt + int64_t(w.grid) * 4);
+  w.off_o = up(w.off_ml + int64_t(2 * w.grid) * ATT_TILE * 2 * 4);
+  w.bytes = up(w.off_o + int64_t(2 * w.grid) * ATT_TILE * ATT_D * 2);
+  return w;
 }
 
 extern "C" int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_per_batch, int32_t heads) {
-  const AttnPlan p = attn_plan(nbatch, rows_per_batch, heads, true);
-  if (p.parts == 1) return 0;
-  const int64_t units = int64_t(p.n_tail) * p.parts;
-  return units * ATT_TILE * (ATT_D + 2) * 4 + int64_t(p.n_tail) * 4 + 256;
+  if (nbatch <= 0 || rows_per_batch <= 0 || heads <= 0) return 0;
+  return attn_ws_layout(nbatch, rows_per_batch, heads).bytes;
+}
+
+extern "C" int oron_attention_plan(const int32_t* seq_lens, int32_t nbatch, int32_t rows_per_batch, int32_t heads,
+                                   void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
+  if (!workspace || nbatch <= 0 || rows_per_batch <= 0 || heads <= 0) return fail(ORON_ERR_BAD_ARG, "attention_plan: bad argument");
+  const AttnWsLayout w = attn_ws_layout(nbatch, rows_per_batch, heads);
+  if (workspace_bytes < w.bytes || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+    return fail(ORON_ERR_BAD_ARG, "attention_plan: workspace too small or not 16-byte aligned");
+  char* p = reinterpret_cast<char*>(workspace);
+  attn_plan_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<AttnPlanHeader*>(p), reinterpret_cast<int*>(p + w.off_nseg), reinterpret_cast<AttnSeg*>(p + w.off_segs),
+      reinterpret_cast<AttnMergeEnt*>(p + w.off_merge), reinterpret_cast<int*>(p + w.off_cnt), seq_lens, nbatch, rows_per_batch,
+      heads, w.grid, w.seg_stride);
+  return check_launch("attn_plan");
 }
 
 extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
@@ -304,11 +316,13 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
     if (e != cudaSuccess) return fail(int(e), "attention smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  const bool have_ws = workspace != nullptr &&
-                       workspace_bytes >= oron_attention_workspace_bytes(nbatch, rows_per_batch, heads) &&
-                       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
-  const AttnPlan p = attn_plan(nbatch, rows_per_batch, heads, have_ws);
+  const AttnWsLayout w = attn_ws_layout(nbatch, rows_per_batch, heads);
+  const bool have_ws = workspace != nullptr && workspace_bytes >= w.bytes && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+  static int env_mode = -2;
+  if (env_mode == -2) { const char* e = getenv("ORON_ATT_BALANCED"); env_mode = e ? atoi(e) : -1; }
+  const int mode = g_attn_schedule >= 0 ? g_attn_schedule : env_mode;
   AttnArgs a;
+  memset(&a, 0, sizeof(a));
   a.rows_per_batch = rows_per_batch;
   a.nbatch = nbatch;
   a.heads = heads;
@@ -317,21 +331,23 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.dbg = g_attn_dbg;
-  a.q_tiles = p.q_tiles;
-  a.n_full = p.n_full;
-  a.parts = p.parts;
-  a.ws_o = a.ws_ml = nullptr;
-  a.ws_cnt = nullptr;
-  if (p.parts > 1) {
-    const int64_t units = int64_t(p.n_tail) * p.parts;
-    char* w = reinterpret_cast<char*>(workspace);
-    a.ws_o = reinterpret_cast<float*>(w);
-    a.ws_ml = reinterpret_cast<float*>(w + units * ATT_TILE * ATT_D * 4);
-    a.ws_cnt = reinterpret_cast<int*>(w + units * ATT_TILE * (ATT_D + 2) * 4);
+  a.q_tiles = (rows_per_batch + ATT_TILE - 1) / ATT_TILE;
+  const long long items = (long long)a.q_tiles * heads * nbatch;
+  // the balanced schedule only pays when there are more items than resident CTA slots
+  const bool balanced = have_ws && (mode == 1 || (mode != 0 && items > attn_slots()));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (balanced) {
+    char* p = reinterpret_cast<char*>(workspace);
+    a.plan_hdr = reinterpret_cast<const AttnPlanHeader*>(p);
+    a.plan_nseg = reinterpret_cast<const int*>(p + w.off_nseg);
+    a.plan_segs = reinterpret_cast<const AttnSeg*>(p + w.off_segs);
+    a.plan_merge = reinterpret_cast<const AttnMergeEnt*>(p + w.off_merge);
+    a.ws_cnt = reinterpret_cast<int*>(p + w.off_cnt);
+    a.ws_ml = reinterpret_cast<float*>(p + w.off_ml);
+    a.ws_o = reinterpret_cast<__half*>(p + w.off_o);
   }
-  dim3 grid(p.n_full + p.n_tail * p.parts);
-  cudaError_t le = launch_pdl(attn_fwd_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES,
-                              reinterpret_cast<cudaStream_t>(stream), tq, a);
+  dim3 grid(balanced ? unsigned(w.grid) : unsigned(items));
+  cudaError_t le = launch_pdl(attn_fwd_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tq, a);
   if (le != cudaSuccess) return fail(int(le), "attention launch: %s", cudaGetErrorString(le));
   return check_launch("attn_fwd_tcgen05");
 }

@@ -36,6 +36,31 @@
 
 namespace oron {
 
+// One contiguous run of key tiles [j0, j1) of one (batch, head, 128-query tile) item.
+struct AttnSeg {
+  int b, h, qt;
+  int j0, j1;
+  int slot;    // -1: the whole item (O / l goes to `out`); else the partial-result slot this segment writes
+  int owner;   // partial segment: the CTA that merges the item (the one holding its first key tiles)
+  int pad;
+};
+// The split item a CTA merges at the end of its run: parts live in slots 2*(cta + p) + (p == 0 ? 1 : 0), p = 0..nparts-1.
+struct AttnMergeEnt {
+  int b, h, qt, nparts;   // nparts == 0: nothing to merge
+};
+// Workspace of the balanced schedule:
+//   AttnPlanHeader | int nseg[grid] | AttnSeg segs[grid][seg_stride] | AttnMergeEnt merge[grid] | int cnt[grid] | ws_ml | ws_o
+// Everything up to `merge` is written by attn_plan_kernel; cnt are the arrival counters of the split items (zeroed
+// by the plan, left zero by every attention call).
+struct AttnPlanHeader {
+  unsigned magic;       // ATT_PLAN_MAGIC once attn_plan_kernel has run
+  int nbatch, rows, heads;
+  int grid;             // CTAs of the balanced launch
+  int seg_stride;       // AttnSeg entries reserved per CTA
+  int pad[10];
+};
+constexpr unsigned ATT_PLAN_MAGIC = 0x0A77B201u;
+
 struct AttnArgs {
   int rows_per_batch;   // Tpad: rows per batch element in qkv / out
   int nbatch;
@@ -45,15 +70,17 @@ struct AttnArgs {
   long long ldo;
   float scale_log2;     // softmax scale * log2(e)
   long long* dbg;       // optional [grid, 16] clock64 stamps (tools/attn_trace.py); nullptr in production
-  // work decomposition (see attn_plan in api.cu): items = (batch, head, 128-query tile) in linear order. The first
-  // n_full items run whole, one CTA each; every later ("tail") item is split along the keys into `parts` CTAs whose
-  // partial (O, max, sum) results are merged by whichever of them finishes last.
-  int q_tiles;          // 128-row query tiles per batch element
-  int n_full;
-  int parts;            // >= 1
-  float* ws_o;          // [n_tail_items * parts][128][64] f32 partial numerators
-  float* ws_ml;         // [n_tail_items * parts][128][2] f32 (running max * c, denominator)
-  int* ws_cnt;          // [n_tail_items] arrival counters, zero before the first launch (the kernel re-zeroes them)
+  int q_tiles;          // 128-row query tiles per batch element (ceil(rows_per_batch / 128))
+  // balanced schedule (plan != nullptr): the grid is the number of resident CTA slots and CTA c owns an equal share of
+  // the flat (item, key tile) list; items that straddle two shares are split along the keys, their normalised partial
+  // results go to the workspace and the CTA holding an item's first key tiles combines them at the end of its run. plan == nullptr: one CTA per item.
+  const AttnPlanHeader* plan_hdr;
+  const int* plan_nseg;
+  const AttnSeg* plan_segs;
+  const AttnMergeEnt* plan_merge;
+  int* ws_cnt;          // [grid] arrival counters of the split items
+  __half* ws_o;         // [2 * grid][128][64] f16: O_p / l_p of a partial segment
+  float* ws_ml;         // [2 * grid][128][2] f32: (running max * c, l_p)
 };
 
 constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 softmax
@@ -61,8 +88,7 @@ constexpr int ATT_TILE = 128;
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_D * 2;  // 16 KB
 // smem: Q | K0 K1 | V0 V1 | P(2 slabs) | barriers
-constexpr int ATT_ONES_BYTES = 512;  // [16 x 16] f16 ones, no-swizzle K-major core matrices
-constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 128 + ATT_ONES_BYTES;
+constexpr int ATT_SMEM_BYTES = 7 * ATT_TILE_BYTES + 256;
 constexpr int ATT_TMEM_COLS = 256;
 #define ATT_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
@@ -168,59 +194,86 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// Cursor over a CTA's segments; every role (TMA, MMA, softmax) runs its own copy and sees the same tile sequence.
+struct SegIt {
+  const AttnSeg* segs;
+  int nseg, s, j;
+  AttnSeg cur;
+  __device__ __forceinline__ void init(const AttnSeg* p, int n) { segs = p; nseg = n; s = 0; cur = p[0]; j = cur.j0; }
+  __device__ __forceinline__ bool valid() const { return s < nseg; }
+  __device__ __forceinline__ bool first() const { return j == cur.j0; }
+  __device__ __forceinline__ bool last() const { return j == cur.j1 - 1; }
+  __device__ __forceinline__ void next() {
+    if (++j == cur.j1 && ++s < nseg) { cur = segs[s]; j = cur.j0; }
+  }
+};
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // one-CTA-per-item mode: the item as a single whole segment, kept after the barriers in dynamic shared memory
+  AttnSeg& own_seg = *reinterpret_cast<AttnSeg*>(smem_raw + 7 * ATT_TILE_BYTES + 128);
 
   pdl_launch_dependents();
-  int item = blockIdx.x, part = 0, nparts = 1;
-  if (item >= args.n_full) {
-    const int u = item - args.n_full;
-    item = args.n_full + u / args.parts;
-    part = u % args.parts;
-    nparts = args.parts;
+  const AttnSeg* segs;
+  int nseg;
+  if (args.plan_hdr != nullptr) {
+    nseg = args.plan_nseg[blockIdx.x];
+    segs = args.plan_segs + (long long)blockIdx.x * args.plan_hdr->seg_stride;
+    const AttnPlanHeader& ph = *args.plan_hdr;
+    if (ph.magic != ATT_PLAN_MAGIC || ph.nbatch != args.nbatch || ph.rows != args.rows_per_batch || ph.heads != args.heads ||
+        ph.grid != int(gridDim.x)) {
+      if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("[oron] attention: the workspace holds no plan for this shape (call oron_attention_plan first)\n");
+      __trap();
+    }
+  } else {
+    const int qt = blockIdx.x % args.q_tiles;
+    const int h = (blockIdx.x / args.q_tiles) % args.heads;
+    const int b = blockIdx.x / (args.q_tiles * args.heads);
+    const int len = args.seq_lens ? min(args.seq_lens[b], args.rows_per_batch) : args.rows_per_batch;
+    const int nt = (len + ATT_TILE - 1) / ATT_TILE;
+    nseg = qt < nt ? 1 : 0;  // a query tile entirely beyond the sequence: the out-projection masks these rows
+    if (threadIdx.x == 0) { own_seg.b = b; own_seg.h = h; own_seg.qt = qt; own_seg.j0 = 0; own_seg.j1 = nt; own_seg.slot = -1; own_seg.owner = -1; own_seg.pad = 0; }
+    segs = &own_seg;
   }
-  const int q_tile = item % args.q_tiles;
-  const int h = (item / args.q_tiles) % args.heads;
-  const int b = item / (args.q_tiles * args.heads);
-  const int q0 = q_tile * ATT_TILE;
-  const int len = args.seq_lens ? min(args.seq_lens[b], args.rows_per_batch) : args.rows_per_batch;
-  if (q0 >= len) return;  // whole tile is padding (all parts of the item agree): the out-projection masks these rows
+  if (nseg == 0) return;  // CTA-uniform, nothing allocated yet
   if ((smem_base & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[oron] attention: dynamic smem not 1024-byte aligned\n");
     __trap();
   }
-  const int n_kv = (len + ATT_TILE - 1) / ATT_TILE;
-  const int j_begin = (part * n_kv) / nparts;                 // this CTA's key tiles: [j_begin, j_begin + n_loc)
-  const int n_loc = ((part + 1) * n_kv) / nparts - j_begin;   // may be 0 when the sequence has fewer tiles than parts
 
   const uint32_t sQ = smem_base;
-  auto sK = [&](int s) { return smem_base + (1 + s) * ATT_TILE_BYTES; };
-  auto sV = [&](int s) { return smem_base + (3 + s) * ATT_TILE_BYTES; };
+  auto sK = [&](int st) { return smem_base + (1 + st) * ATT_TILE_BYTES; };
+  auto sV = [&](int st) { return smem_base + (3 + st) * ATT_TILE_BYTES; };
   const uint32_t sP = smem_base + 5 * ATT_TILE_BYTES;
   const uint32_t bar_base = smem_base + 7 * ATT_TILE_BYTES;
-  const uint32_t q_full = bar_base;
-  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (3 + s); };
-  const uint32_t s_full = bar_base + 8u * 5;   // MMA -> softmax: S(j) is in TMEM
-  const uint32_t s_free = bar_base + 8u * 6;   // softmax -> MMA: S(j) has been read (128 arrivals)
-  const uint32_t p_full = bar_base + 8u * 7;   // softmax -> MMA: P(j) is in smem (128 arrivals)
-  const uint32_t o_full = bar_base + 8u * 8;   // MMA -> softmax: O includes P(j) V(j)
-  const uint32_t p0_free = bar_base + 8u * 9;  // MMA -> softmax: P V has consumed the first 64-key slab of P(j)
+  const uint32_t q_full = bar_base;             // per segment
+  auto kv_full = [&](int st) { return bar_base + 8u * (1 + st); };
+  auto kv_empty = [&](int st) { return bar_base + 8u * (3 + st); };  // MMA -> TMA: P(i) V(i) (and S(i+1)) have retired
+  const uint32_t s_full = bar_base + 8u * 5;    // MMA -> softmax: S(i) is in TMEM
+  const uint32_t s_free = bar_base + 8u * 6;    // softmax -> MMA: S(i) has been read (128 arrivals)
+  const uint32_t p_full = bar_base + 8u * 7;    // softmax -> MMA: P(i) is in smem (128 arrivals)
+  const uint32_t o_full = bar_base + 8u * 8;    // MMA -> softmax: O includes P(i) V(i)
+  const uint32_t p0_free = bar_base + 8u * 9;   // MMA -> softmax: P V has consumed the first 64-key slab of P(i)
   const uint32_t tmem_slot = bar_base + 8u * 10;
+  const uint32_t o_free = bar_base + 8u * 11;   // softmax -> MMA, per segment: O has been read out (128 arrivals)
+  const uint32_t q_empty = bar_base + 8u * 12;  // MMA -> TMA, per segment: the last S of the segment has retired
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    mbar_init(q_empty, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     mbar_init(s_full, 1);
     mbar_init(s_free, 128);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     mbar_init(p0_free, 1);
+    mbar_init(o_free, 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -243,14 +296,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
   const int HD = args.heads * ATT_D;
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQKV, q_full, h * ATT_D, q0, b);
-      for (int j = 0; j < n_loc; ++j) {
-        const int s = j & 1;
-        mbar_wait(kv_empty(s), ((j >> 1) & 1u) ^ 1u, 11);
-        mbar_arrive_expect_tx(kv_full(s), 2 * ATT_TILE_BYTES);
-        tma_load_3d(sK(s), &tmQKV, kv_full(s), HD + h * ATT_D, (j_begin + j) * ATT_TILE, b);
-        tma_load_3d(sV(s), &tmQKV, kv_full(s), 2 * HD + h * ATT_D, (j_begin + j) * ATT_TILE, b);
+      SegIt w;
+      w.init(segs, nseg);
+      int seg = 0;
+      for (int i = 0; w.valid(); w.next(), ++i) {
+        const int st = i & 1;
+        if (w.first()) {
+          if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1u, 11);  // every S of the previous segment has retired
+          ++seg;
+          mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+          tma_load_3d(sQ, &tmQKV, q_full, w.cur.h * ATT_D, w.cur.qt * ATT_TILE, w.cur.b);
+        }
+        mbar_wait(kv_empty(st), ((i >> 1) & 1u) ^ 1u, 11);
+        mbar_arrive_expect_tx(kv_full(st), 2 * ATT_TILE_BYTES);
+        tma_load_3d(sK(st), &tmQKV, kv_full(st), HD + w.cur.h * ATT_D, w.j * ATT_TILE, w.cur.b);
+        tma_load_3d(sV(st), &tmQKV, kv_full(st), 2 * HD + w.cur.h * ATT_D, w.j * ATT_TILE, w.cur.b);
       }
     }
   } else if (warp == 1) {
@@ -266,32 +326,40 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       const uint64_t vdesc1 = make_smem_desc_sw128(sV(1), 1024, 1024);
       const uint64_t pdesc0 = make_smem_desc_sw128(sP, 16, 1024);
       const uint64_t pdesc1 = make_smem_desc_sw128(sP + ATT_TILE_BYTES, 16, 1024);
-      auto issue_S = [&](int j) {
-        const uint64_t kdesc = (j & 1) ? kdesc1 : kdesc0;
+      int seg_q = 0;  // segments whose Q has been consumed by an S issue
+      auto issue_S = [&](bool first_of_seg, bool last_of_seg, int i) {
+        if (first_of_seg) { mbar_wait(q_full, seg_q & 1u, 12); ++seg_q; }
+        mbar_wait(kv_full(i & 1), (i >> 1) & 1u, 13);
+        tc_fence_after();
+        const uint64_t kdesc = (i & 1) ? kdesc1 : kdesc0;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_S, qdesc + uint64_t(2 * k), kdesc + uint64_t(2 * k), idesc_s, k != 0);
         umma_commit(s_full);
+        if (last_of_seg) umma_commit(q_empty);
       };
-      if (n_loc > 0) {
-        mbar_wait(q_full, 0, 12);
-        mbar_wait(kv_full(0), 0, 13);
-        tc_fence_after();
-        issue_S(0);
-      }
-      for (int j = 0; j < n_loc; ++j) {
-        const int s = j & 1;
-        if (j + 1 < n_loc) {
-          mbar_wait(s_free, j & 1u, 14);  // S(j) fully read: the S columns may be overwritten
-          mbar_wait(kv_full((j + 1) & 1), ((j + 1) >> 1) & 1u, 15);
-          tc_fence_after();
-          issue_S(j + 1);
+      SegIt w, wn;            // w: tile whose P V is issued in this iteration; wn: one tile ahead (S(i+1) goes first)
+      w.init(segs, nseg);
+      wn.init(segs, nseg);
+      issue_S(true, wn.last(), 0);
+      wn.next();
+      int seg_o = 0;          // segments whose first P V has been issued
+      for (int i = 0; w.valid(); w.next(), ++i) {
+        if (wn.valid()) {
+          mbar_wait(s_free, i & 1u, 14);  // S(i) fully read: the S columns may be overwritten
+          issue_S(wn.first(), wn.last(), i + 1);
+          wn.next();
         }
-        mbar_wait(p_full, j & 1u, 16);  // P(j) in smem (and O rescaled if the running max moved)
+        mbar_wait(p_full, i & 1u, 16);  // P(i) in smem (and O rescaled if the running max moved)
+        const bool first = w.first();
+        if (first) {
+          if (seg_o > 0) mbar_wait(o_free, (seg_o - 1) & 1u, 17);  // the previous segment's O has been read out
+          ++seg_o;
+        }
         tc_fence_after();
-        if (j == 2) ATT_STAMP(12);
-        const uint64_t vdesc = s ? vdesc1 : vdesc0;
-        const uint32_t acc0 = j != 0 ? 1u : 0u;
+        if (i == 2) ATT_STAMP(12);
+        const uint64_t vdesc = (i & 1) ? vdesc1 : vdesc0;
+        const uint32_t acc0 = first ? 0u : 1u;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           // P: 16 keys = 32 bytes inside the 128 B swizzle span (>>4 = 2); V: 16 key rows = 2048 bytes (>>4 = 128)
@@ -302,8 +370,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           if (kk == 3) umma_commit(p0_free);
         }
         umma_commit(o_full);
-        umma_commit(kv_empty(s));
-        if (j == 2) ATT_STAMP(13);
+        umma_commit(kv_empty(i & 1));
+        if (i == 2) ATT_STAMP(13);
       }
     }
   } else {
@@ -316,13 +384,24 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     float l_run = 0.f;     // softmax denominator in the same (stale-max, 2^7-biased) scale as O
     const uint32_t prow = sP + r * 128;
     const uint32_t sw = uint32_t(r & 7);
-    for (int j = 0; j < n_loc; ++j) {
-      const int n_valid = min(ATT_TILE, len - (j_begin + j) * ATT_TILE);
+    SegIt w;
+    w.init(segs, nseg);
+    int len = 0;
+    for (int i = 0; w.valid(); w.next(), ++i) {
+      const bool first = w.first();
+      if (first) {
+        mc = -INFINITY;
+        l_run = 0.f;
+        len = args.seq_lens ? min(args.seq_lens[w.cur.b], args.rows_per_batch) : args.rows_per_batch;
+      }
+      const int n_valid = min(ATT_TILE, len - w.j * ATT_TILE);
       const bool full_tile = n_valid == ATT_TILE;  // CTA-uniform
-      mbar_wait(s_full, j & 1u, 17);
+      mbar_wait(s_full, i & 1u, 17);
       tc_fence_after();
-      const bool tr = threadIdx.x == 64 && j == (nparts > 1 ? 1 : 2);
+      const bool tr = threadIdx.x == 64 && i == 6;
       if (tr) ATT_STAMP(1);
+      if (threadIdx.x == 64 && i == 7) ATT_STAMP(6);
+      if (threadIdx.x == 64 && i == 8) ATT_STAMP(7);
       // ---- pass 1: row maximum over the valid keys (the last 32-key chunk stays in registers for pass 2) ----
       float mx = -INFINITY;
       uint32_t vlast[32];
@@ -340,18 +419,18 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           mx = fmaxf(mx, max32(u));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < n_valid) mx = fmaxf(mx, __uint_as_float(u[i]));
+          for (int k = 0; k < 32; ++k)
+            if (c0 + k < n_valid) mx = fmaxf(mx, __uint_as_float(u[k]));
         }
       }
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const float mxc = mx * c;
       const bool need = mxc > mc + ATT_RESCALE_LOG2;
       if (tr) ATT_STAMP(2);
-      bool o_done = (j == 0);
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: P(j-1) V(j-1) must be folded into O before O and l are rescaled
-        mbar_wait(o_full, (j - 1) & 1u, 18);
+      bool o_done = (i == 0);
+      if (!first && __any_sync(0xffffffffu, need)) {
+        // rare: P(i-1) V(i-1) must be folded into O before O and l are rescaled
+        mbar_wait(o_full, (i - 1) & 1u, 18);
         tc_fence_after();
         o_done = true;
         const float f = need ? ex2_approx(mc - mxc) : 1.0f;
@@ -361,13 +440,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           tmem_ld_32x32(tmem_O + lane_off + c0, v);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * f);
           tmem_st_32x32(tmem_O + lane_off + c0, v);
         }
         l_run *= f;
         tmem_wait_st();
       }
-      if (j > 0 && !o_done) mbar_wait(p0_free, (j - 1) & 1u, 20);  // first P slab may be overwritten
+      if (!o_done) mbar_wait(p0_free, (i - 1) & 1u, 20);  // first P slab may be overwritten
       if (need) mc = mxc;
       if (tr) ATT_STAMP(3);
       // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
@@ -378,13 +457,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
         tmem_ld_32x32(tmem_S + lane_off + c0, v);
         tmem_wait_ld();
         if (c0 == ATT_TILE - 64) {
-          // last TMEM read of S(j) (the final chunk is still in registers from pass 1): let the MMA thread start
+          // last TMEM read of S(i) (the final chunk is still in registers from pass 1): let the MMA thread start
           // Q K^T of the next tile under the remaining half of this pass
           tc_fence_before();
           mbar_arrive(s_free);
         }
         if (c0 == 64 && !o_done) {
-          mbar_wait(o_full, (j - 1) & 1u, 18);  // second P slab: all of P(j-1) V(j-1) has retired
+          mbar_wait(o_full, (i - 1) & 1u, 18);  // second P slab: all of P(i-1) V(i-1) has retired
           o_done = true;
         }
         l_run += full_tile ? softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw)
@@ -397,124 +476,127 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       tc_fence_before();
       mbar_arrive(p_full);
       if (tr) ATT_STAMP(5);
-    }
-    // ---- epilogue ----
-    if (n_loc > 0) {
-      mbar_wait(o_full, (n_loc - 1) & 1u, 19);
+      if (!w.last()) continue;
+
+      // ---- end of a segment: O / l to the output (whole item) or to the workspace (partial item, f16 + (m, l)) ----
+      mbar_wait(o_full, i & 1u, 19);
       tc_fence_after();
-    }
-    const int t = q0 + r;
-    __nv_bfloat16* orow = args.out + ((long long)b * args.rows_per_batch + t) * args.ldo + h * ATT_D;
-    if (nparts == 1) {
-      // whole item: O / l
       const float inv_l = 1.0f / l_run;
-#pragma unroll
+      const int slot = w.cur.slot;
+      const int t = w.cur.qt * ATT_TILE + r;
+      const bool store = slot >= 0 || t < args.rows_per_batch;
+      // destination row: 64 values, 16 bits each, for both kinds
+      uint4* dst = slot >= 0
+          ? reinterpret_cast<uint4*>(args.ws_o + ((long long)slot * ATT_TILE + r) * ATT_D)
+          : reinterpret_cast<uint4*>(args.out + ((long long)w.cur.b * args.rows_per_batch + t) * args.ldo + w.cur.h * ATT_D);
+#pragma unroll 1
       for (int c0 = 0; c0 < ATT_D; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_O + lane_off + c0, v);
         tmem_wait_ld();
-        if (t < args.rows_per_batch) {
-          uint32_t pk[16];
+        if (c0 == ATT_D - 32) { tc_fence_before(); mbar_arrive(o_free); }  // O is in registers: the next segment may start
+        uint32_t pk[16];
+        if (slot >= 0) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
-          uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) o4[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-        }
-      }
-    } else {
-      // key-split tail item: publish this part's (O, max, sum); the part that arrives last merges all of them.
-      // Nobody waits for anybody (no co-scheduling assumption): ordering is "write, fence, count".
-      if (threadIdx.x == 64) ATT_STAMP(6);
-      const int tail = item - args.n_full;
-      const long long unit = (long long)tail * nparts + part;
-      float* wo = args.ws_o + (unit * ATT_TILE + r) * ATT_D;
-      if (n_loc > 0) {
-#pragma unroll
-        for (int c0 = 0; c0 < ATT_D; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_O + lane_off + c0, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<uint4*>(wo + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-      }
-      *reinterpret_cast<float2*>(args.ws_ml + (unit * ATT_TILE + r) * 2) = make_float2(mc, l_run);  // empty part: (-inf, 0)
-      if (threadIdx.x == 64) ATT_STAMP(7);
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) ATT_STAMP(10);
-      const uint32_t flag = sP;  // the P tile is dead by now: reuse its first word as the "I am last" flag
-      if (threadIdx.x == 64) {
-        const int old = atomicAdd(args.ws_cnt + tail, 1);
-        const int last = (old == nparts - 1) ? 1 : 0;
-        if (last) args.ws_cnt[tail] = 0;  // ready for the next launch (CUDA-graph replays included)
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(flag), "r"(last) : "memory");
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      uint32_t last;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(flag) : "memory");
-      if (threadIdx.x == 64) ATT_STAMP(11);
-      if (last) {
-        __threadfence();
-        const long long u0 = (long long)tail * nparts;
-        // (1) per row: common maximum, per-part factors 2^(m_p - m) / l  -> smem (the P tile is dead)
-        float mp[8], lp[8];
-        float m_all = -INFINITY;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          mp[p] = -INFINITY; lp[p] = 0.f;
-          if (p < nparts) {
-            const float2 ml = __ldcg(reinterpret_cast<const float2*>(args.ws_ml + ((u0 + p) * ATT_TILE + r) * 2));
-            mp[p] = ml.x; lp[p] = ml.y;
+          for (int k = 0; k < 32; k += 2) {
+            const __half2 hh = __floats2half2_rn(__uint_as_float(v[k]) * inv_l, __uint_as_float(v[k + 1]) * inv_l);
+            pk[k / 2] = *reinterpret_cast<const uint32_t*>(&hh);
           }
-          m_all = fmaxf(m_all, mp[p]);
-        }
-        float l_all = 0.f;
+        } else {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          mp[p] = lp[p] > 0.f ? ex2_approx(mp[p] - m_all) : 0.f;  // now the factor; empty parts contribute nothing
-          l_all = fmaf(lp[p], mp[p], l_all);
+          for (int k = 0; k < 32; k += 2)
+            pk[k / 2] = pack_bf16x2(__uint_as_float(v[k]) * inv_l, __uint_as_float(v[k + 1]) * inv_l);
         }
-        const float inv_l = 1.0f / l_all;
-        const uint32_t sF = sP + 16;  // [8 parts][128 rows] f32
+        if (store) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sF + uint32_t(p * ATT_TILE + r) * 4u), "f"(mp[p] * inv_l) : "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        // (2) cooperative, coalesced merge: 16 threads per output row (4 columns each), 8 rows per step
+          for (int g = 0; g < 4; ++g) dst[c0 / 8 + g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      }
+      if (slot >= 0) {
+        *reinterpret_cast<float2*>(args.ws_ml + ((long long)slot * ATT_TILE + r) * 2) = make_float2(mc, l_run);
+        if (w.cur.owner != int(blockIdx.x)) {
+          // a part merged by another CTA: publish it ("write, fence, count"; nobody waits here)
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) atomicAdd(args.ws_cnt + w.cur.owner, 1);
+        }
+      }
+    }
+    // ---- the split item whose first key tiles this CTA computed: combine its parts --------------------------------
+    // Partial items come FIRST in every CTA's run, so by now (>= one whole item later) the other parts have long been
+    // published by CTAs of this same launch; the wait below is a formality with a watchdog, not a scheduling assumption
+    // about other launches.
+    if (args.plan_hdr != nullptr) {
+      const AttnMergeEnt me = args.plan_merge[blockIdx.x];
+      if (me.nparts > 0) {
         const int tid = threadIdx.x - 64;
-        const int c4 = (tid & 15) * 4;
-        const float* fs = reinterpret_cast<const float*>(__cvta_shared_to_generic(sF));
-#pragma unroll 2
-        for (int rg = 0; rg < ATT_TILE / 8; ++rg) {
-          const int row = rg * 8 + (tid >> 4);
-          // all loads of a row group are issued before any of them is consumed (one L2 round trip per group, not
-          // one per part). Empty parts are read too: the scratch only ever holds finite values and their factor is 0.
-          float f[8];
-          float4 o[8];
-#pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            f[p] = 0.f;
-            o[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p < nparts) {
-              f[p] = fs[p * ATT_TILE + row];
-              o[p] = __ldcg(reinterpret_cast<const float4*>(args.ws_o + ((u0 + p) * ATT_TILE + row) * ATT_D + c4));
+        if (tid == 0) {
+          const long long t_start = clock64();
+          volatile int* cnt = args.ws_cnt + blockIdx.x;
+          while (*cnt < me.nparts - 1) {
+            __nanosleep(100);
+            if (clock64() - t_start > 4000000000ll) {
+              printf("[oron] attention: merge wait timed out (cta %d)\n", int(blockIdx.x));
+              __trap();
             }
           }
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          *cnt = 0;  // ready for the next call (CUDA-graph replays included)
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __threadfence();
+        auto slot_of = [&](int p) { return (long long)(2 * (int(blockIdx.x) + p) + (p == 0 ? 1 : 0)); };
+        // per-row weights w_p = l_p 2^(m_p - m) / sum_q l_q 2^(m_q - m)
+        float m_all = -INFINITY;
+        for (int p = 0; p < me.nparts; ++p)
+          m_all = fmaxf(m_all, __ldcg(args.ws_ml + (slot_of(p) * ATT_TILE + r) * 2));
+        float l_all = 0.f;
+        for (int p = 0; p < me.nparts; ++p) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(args.ws_ml + (slot_of(p) * ATT_TILE + r) * 2));
+          l_all = fmaf(ml.y, ex2_approx(ml.x - m_all), l_all);
+        }
+        const float inv_l = 1.0f / l_all;
+        // cooperative, coalesced combine: 8 threads per row (8 columns = 16 bytes of f16 each), 16 rows per step; the
+        // weights of up to 8 parts at a time travel through the (idle) P tile
+        float* fs = reinterpret_cast<float*>(smem_raw + 5 * ATT_TILE_BYTES);  // [8][128]
+        const int c8 = (tid & 7) * 8, rsub = tid >> 3;
+        float acc[8][8];
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            acc.x = fmaf(o[p].x, f[p], acc.x); acc.y = fmaf(o[p].y, f[p], acc.y);
-            acc.z = fmaf(o[p].z, f[p], acc.z); acc.w = fmaf(o[p].w, f[p], acc.w);
+        for (int st = 0; st < 8; ++st)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[st][k] = 0.f;
+        for (int p0 = 0; p0 < me.nparts; p0 += 8) {
+          const int pn = min(8, me.nparts - p0);
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // the previous chunk's weights are consumed
+          for (int pp = 0; pp < pn; ++pp) {
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(args.ws_ml + (slot_of(p0 + pp) * ATT_TILE + r) * 2));
+            fs[pp * ATT_TILE + r] = ml.y * ex2_approx(ml.x - m_all) * inv_l;
           }
-          const int tt = q0 + row;
-          if (tt < args.rows_per_batch) {
-            __nv_bfloat16* orow2 = args.out + ((long long)b * args.rows_per_batch + tt) * args.ldo + h * ATT_D + c4;
-            *reinterpret_cast<uint2*>(orow2) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int pp = 0; pp < pn; ++pp) {
+            const __half* po = args.ws_o + slot_of(p0 + pp) * (ATT_TILE * ATT_D) + c8;
+            uint4 v[8];
+#pragma unroll
+            for (int st = 0; st < 8; ++st) v[st] = __ldcg(reinterpret_cast<const uint4*>(po + (st * 16 + rsub) * ATT_D));
+#pragma unroll
+            for (int st = 0; st < 8; ++st) {
+              const float f = fs[pp * ATT_TILE + st * 16 + rsub];
+              const uint32_t wds[4] = {v[st].x, v[st].y, v[st].z, v[st].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&wds[k]));
+                acc[st][2 * k] = fmaf(fv.x, f, acc[st][2 * k]);
+                acc[st][2 * k + 1] = fmaf(fv.y, f, acc[st][2 * k + 1]);
+              }
+            }
           }
+        }
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          const int tt = me.qt * ATT_TILE + st * 16 + rsub;
+          if (tt < args.rows_per_batch)
+            *reinterpret_cast<uint4*>(args.out + ((long long)me.b * args.rows_per_batch + tt) * args.ldo + me.h * ATT_D + c8) =
+                make_uint4(pack_bf16x2(acc[st][0], acc[st][1]), pack_bf16x2(acc[st][2], acc[st][3]),
+                           pack_bf16x2(acc[st][4], acc[st][5]), pack_bf16x2(acc[st][6], acc[st][7]));
         }
       }
     }
@@ -531,6 +613,103 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Balanced schedule, part 1: the plan. One thread per CTA of the balanced launch cuts its equal share [u0, u1) of
+// the flat (item, key tile) list into segments: the partial item at either end FIRST, whole items after them (so
+// every partial result exists early), and notes for each CTA the split item it has to combine at the end of its run. Runs once per set of sequence lengths (oron_attention_plan), not per call.
+// ------------------------------------------------------------------------------------------------------------
+struct PlanWalk {
+  int heads, nbatch, rows;
+  const int* lens;
+  int b, item, tile, nt;
+  long long item_u0;
+  __device__ int len_of(int bb) const { return lens ? min(lens[bb], rows) : rows; }
+  __device__ static int tiles_of(int l) { return (l + ATT_TILE - 1) / ATT_TILE; }
+  __device__ long long total() const {
+    long long t = 0;
+    for (int bb = 0; bb < nbatch; ++bb) { const long long n = tiles_of(len_of(bb)); t += n * n * heads; }
+    return t;
+  }
+  __device__ void seek(long long u) {
+    long long base = 0;
+    for (b = 0; b < nbatch; ++b) {
+      nt = tiles_of(len_of(b));
+      const long long n = (long long)nt * nt * heads;
+      if (u < base + n) break;
+      base += n;
+    }
+    const long long r = u - base;
+    item = int(r / nt);
+    tile = int(r - (long long)item * nt);
+    item_u0 = u - tile;
+  }
+  __device__ AttnSeg seg(int j0, int j1, int slot) const {
+    AttnSeg s;
+    s.b = b; s.h = item / nt; s.qt = item % nt; s.j0 = j0; s.j1 = j1; s.slot = slot; s.owner = -1; s.pad = 0;
+    return s;
+  }
+};
+
+__global__ void attn_plan_kernel(AttnPlanHeader* hdr, int* nseg_out, AttnSeg* segs_out, AttnMergeEnt* merge, int* cnt,
+                                 const int* seq_lens, int nbatch, int rows, int heads, int grid, int seg_stride) {
+  if (threadIdx.x == 0) {
+    hdr->nbatch = nbatch; hdr->rows = rows; hdr->heads = heads; hdr->grid = grid; hdr->seg_stride = seg_stride;
+  }
+  PlanWalk w;
+  w.heads = heads; w.nbatch = nbatch; w.rows = rows; w.lens = seq_lens;
+  const long long total = w.total();
+  const long long G = min((long long)grid, total);
+  auto start_of = [&](long long cta) { return (total * cta) / G; };
+  auto cta_of = [&](long long u) {
+    long long cc = (u * G) / total;
+    while (cc + 1 < G && start_of(cc + 1) <= u) ++cc;
+    while (cc > 0 && start_of(cc) > u) --cc;
+    return cc;
+  };
+  for (int c = threadIdx.x; c < grid; c += blockDim.x) {
+    int n = 0;
+    AttnSeg* out = segs_out + (long long)c * seg_stride;
+    AttnMergeEnt me;
+    me.b = me.h = me.qt = me.nparts = 0;
+    if (c < G) {
+      const long long u0 = start_of(c), u1 = start_of(c + 1);
+      // partial tail of the item the share starts in: merged by the CTA that holds the item's first tile
+      w.seek(u0);
+      long long a_end = u0;
+      if (w.tile != 0) {
+        a_end = min(u1, w.item_u0 + w.nt);
+        AttnSeg sg = w.seg(w.tile, w.tile + int(a_end - u0), 2 * c);
+        sg.owner = int(cta_of(w.item_u0));
+        out[n++] = sg;
+      }
+      // partial head of the item the share ends in: this CTA merges it
+      long long b_start = u1;
+      if (a_end < u1) {
+        w.seek(u1 - 1);
+        if (w.item_u0 + w.nt > u1) {
+          b_start = w.item_u0;
+          AttnSeg sg = w.seg(0, int(u1 - b_start), 2 * c + 1);
+          sg.owner = c;
+          out[n++] = sg;
+          me.b = w.b; me.h = w.item / w.nt; me.qt = w.item % w.nt;
+          me.nparts = int(cta_of(w.item_u0 + w.nt - 1) - c + 1);
+        }
+      }
+      // whole items in between
+      for (long long u = a_end; u < b_start;) {
+        w.seek(u);
+        if (n < seg_stride) out[n++] = w.seg(0, w.nt, -1);
+        u += w.nt;
+      }
+    }
+    nseg_out[c] = n;
+    merge[c] = me;
+    cnt[c] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); hdr->magic = ATT_PLAN_MAGIC; }
 }
 
 }  // namespace oron

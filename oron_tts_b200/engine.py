@@ -211,10 +211,10 @@ class Workspace:
         self.nrm = z(R, D, dt=BF16)
         self.qkv = z(R, 3 * D, dt=BF16)
         self.ao = z(R, D, dt=BF16)
-        # Key-split scratch for the attention kernel's last wave (oron_attention_workspace_bytes). Measured at config 2
-        # (profiles/r01_attn_keysplit.txt): 55 us with the split vs 51 us without — prologue, fence and merge of the
-        # 280 extra CTAs eat the gain — so it stays off until the merge is cheaper.
-        self.attn_ws = None
+        # Workspace of the balanced attention schedule (plan + partial results of the items split between two CTAs);
+        # planned in `DiTEngine` once the sequence lengths of the call are known (attention_plan).
+        with torch.inference_mode(False):
+            self.attn_ws = torch.zeros(int(L.lib().oron_attention_workspace_bytes(nbp, tpad, w.heads)), dtype=torch.uint8, device=dev)
         self.hid = z(R, w.ff_dim, dt=BF16)
         self.v = z(R, M)
         self.vg = z(Rb, M)
@@ -269,6 +269,8 @@ class DiTEngine:
         drop = [int(br.drop_text) for br in branches for _ in range(nb)]
         ws.drop.copy_(torch.tensor(drop, dtype=torch.uint8), non_blocking=False)
         ws.seq_lens.copy_(torch.tensor(durations * len(branches), dtype=torch.int32))
+        # schedule of the attention kernel for these lengths (once per call, outside the per-NFE graph)
+        L.attention_plan(ws.attn_ws, nbatch=ws.nbp, rows_per_batch=tpad, heads=self.w.heads, seq_lens=ws.seq_lens)
 
     def text_embed(self, ws: Workspace) -> None:
         """TextEmbedding.forward for all branches at once -> ws.xt (fp32 [R, text_dim])."""

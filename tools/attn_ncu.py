@@ -11,7 +11,7 @@ qkv = torch.randn(R, 3072, device=DEV, generator=g).bfloat16()
 qkv[:, 2048:] = torch.randn(R, 1024, device=DEV, generator=g).half().view(torch.bfloat16)
 o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
 lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
-ws = L.attention_workspace(2, T, 16, DEV) if "--ws" in sys.argv else None
+ws = L.attention_workspace(2, T, 16, DEV, seq_lens=lens) if "--ws" in sys.argv else None
 for _ in range(3):
     L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=ws)
 torch.cuda.synchronize()

@@ -12,7 +12,7 @@ qkv[:, 2048:] = torch.randn(R, 1024, device=DEV, generator=g).half().view(torch.
 o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
 lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
 WS = "--ws" in sys.argv  # key-split tail (needs the workspace); default = production path, one CTA per item
-AWS = L.attention_workspace(2, T, 16, DEV) if WS else None
+AWS = L.attention_workspace(2, T, 16, DEV, seq_lens=lens) if WS else None
 fn = lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=AWS)
 for _ in range(3): fn()
 torch.cuda.synchronize()
@@ -22,13 +22,13 @@ torch.cuda._sleep(200000)
 fn(); torch.cuda.synchronize()
 L.lib().oron_debug_set_attention_stamps(None)
 d = dbg.cpu()
-names = {1: "tj s_full", 2: "tj pass1", 3: "tj o_wait", 4: "tj pass2", 5: "tj arrive", 6: "loop done", 7: "partial written", 10: "fence+bar", 11: "count done", 12: "mma: p_full(2)", 13: "mma: PV(2) issued", 14: "softmax end", 15: "cta end"}
+names = {1: "tj s_full", 2: "tj pass1", 3: "tj o_wait", 4: "tj pass2", 5: "tj arrive", 6: "t+1 s_full", 7: "t+2 s_full", 10: "fence+bar", 11: "count done", 12: "mma: p_full(2)", 13: "mma: PV(2) issued", 14: "softmax end", 15: "cta end"}
 starts = d[:, 0]
 print("global start spread (cycles are per-SM clocks; only relative values inside a CTA are meaningful)")
-for cta in (0, 100, 200, 295, 296, 320, 351):
+for cta in (0, 50, 100, 150, 200, 250, 295, 296, 320, 351):
     base = int(d[cta, 0])
     print(f"  cta {cta}: " + ", ".join(f"{names[i]}={int(d[cta, i]) - base}" for i in sorted(names) if int(d[cta, i]) != 0))
-NCTA = 576 if WS else 352
+NCTA = 296 if WS else 352
 d = d[:NCTA]
 dur = (d[:, 15] - d[:, 0]).float()
 print("cta duration cycles: mean %.0f min %.0f max %.0f" % (dur.mean(), dur.min(), dur.max()))

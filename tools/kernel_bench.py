@@ -110,10 +110,10 @@ if what in ("attn", "all"):
     qkv[:, 2048:] = torch.randn(R, 1024, device=DEV, generator=g).half().view(torch.bfloat16)
     o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
     lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
-    AWS = L.attention_workspace(2, T, 16, DEV)
+    AWS = L.attention_workspace(2, T, 16, DEV, seq_lens=lens)
     run([("attention T=1406 H=16 nb=2 (one CTA per item)", 4 * 2 * 16 * 1406 * 1406 * 64,
           lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125)),
-         ("attention T=1406 H=16 nb=2 (key-split tail)", 4 * 2 * 16 * 1406 * 1406 * 64,
+         ("attention T=1406 H=16 nb=2 (balanced schedule)", 4 * 2 * 16 * 1406 * 1406 * 64,
           lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=AWS))])
 if what in ("ln", "all"):
     g = torch.Generator(device=DEV).manual_seed(2)
