@@ -402,19 +402,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       if (tr) ATT_STAMP(1);
       if (threadIdx.x == 64 && i == 7) ATT_STAMP(6);
       if (threadIdx.x == 64 && i == 8) ATT_STAMP(7);
-      // ---- pass 1: row maximum over the valid keys (the last 32-key chunk stays in registers for pass 2) ----
+      // ---- pass 1: row maximum over the valid keys (the last 32-key chunk stays in registers for pass 2).
+      // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is reduced (tcgen05.wait::ld waits
+      // for everything issued so far, so each load is issued right after the wait for its predecessor).
       float mx = -INFINITY;
       uint32_t vlast[32];
-#pragma unroll
-      for (int c0 = 0; c0 < ATT_TILE; c0 += 32) {
-        uint32_t v[32];
-        if (c0 < ATT_TILE - 32) {
-          tmem_ld_32x32(tmem_S + lane_off + c0, v);
-        } else {
-          tmem_ld_32x32(tmem_S + lane_off + c0, vlast);
-        }
-        tmem_wait_ld();
-        const uint32_t(&u)[32] = (c0 < ATT_TILE - 32) ? v : vlast;
+      auto chunk_max = [&](const uint32_t (&u)[32], const int c0) {
         if (full_tile || c0 + 32 <= n_valid) {
           mx = fmaxf(mx, max32(u));
         } else {
@@ -422,6 +415,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
           for (int k = 0; k < 32; ++k)
             if (c0 + k < n_valid) mx = fmaxf(mx, __uint_as_float(u[k]));
         }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tmem_S + lane_off + 0, va);
+        tmem_wait_ld();
+        tmem_ld_32x32(tmem_S + lane_off + 32, vb);
+        chunk_max(va, 0);
+        tmem_wait_ld();
+        tmem_ld_32x32(tmem_S + lane_off + 64, va);
+        chunk_max(vb, 32);
+        tmem_wait_ld();
+        tmem_ld_32x32(tmem_S + lane_off + 96, vlast);
+        chunk_max(va, 64);
+        tmem_wait_ld();
+        chunk_max(vlast, 96);
       }
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const float mxc = mx * c;
@@ -451,26 +459,31 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       if (tr) ATT_STAMP(3);
       // ---- pass 2: P = 2^7 * exp2(S*c - m) -> f16 -> smem (SW128 K-major, two 64-key slabs) ----
       const float mcb = mc - ATT_P_EXP_BIAS;
-#pragma unroll
-      for (int c0 = 0; c0 < ATT_TILE - 32; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_off + c0, v);
+      auto chunk_exp = [&](const uint32_t (&u)[32], const int c0) {
+        l_run += full_tile ? softmax_chunk<false>(u, c, mcb, c0, n_valid, prow, sw)
+                           : softmax_chunk<true>(u, c, mcb, c0, n_valid, prow, sw);
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tmem_S + lane_off + 0, va);
         tmem_wait_ld();
-        if (c0 == ATT_TILE - 64) {
-          // last TMEM read of S(i) (the final chunk is still in registers from pass 1): let the MMA thread start
-          // Q K^T of the next tile under the remaining half of this pass
-          tc_fence_before();
-          mbar_arrive(s_free);
-        }
-        if (c0 == 64 && !o_done) {
+        tmem_ld_32x32(tmem_S + lane_off + 32, vb);
+        chunk_exp(va, 0);
+        tmem_wait_ld();
+        tmem_ld_32x32(tmem_S + lane_off + 64, va);
+        chunk_exp(vb, 32);
+        tmem_wait_ld();
+        // last TMEM read of S(i) (the final chunk is still in registers from pass 1): let the MMA thread start
+        // Q K^T of the next tile under the remaining half of this pass
+        tc_fence_before();
+        mbar_arrive(s_free);
+        if (!o_done) {
           mbar_wait(o_full, (i - 1) & 1u, 18);  // second P slab: all of P(i-1) V(i-1) has retired
           o_done = true;
         }
-        l_run += full_tile ? softmax_chunk<false>(v, c, mcb, c0, n_valid, prow, sw)
-                           : softmax_chunk<true>(v, c, mcb, c0, n_valid, prow, sw);
+        chunk_exp(va, 64);
+        chunk_exp(vlast, 96);
       }
-      l_run += full_tile ? softmax_chunk<false>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw)
-                         : softmax_chunk<true>(vlast, c, mcb, ATT_TILE - 32, n_valid, prow, sw);
       if (tr) ATT_STAMP(4);
       fence_proxy_async_smem();
       tc_fence_before();
