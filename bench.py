@@ -186,9 +186,12 @@ def run_ours(args) -> dict:
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
-    if rank == 0 and not args.no_secondary:
-        with torch.inference_mode():
-            out["secondary"] = secondary_cfg4(model, voc, dev)
+    if not args.no_secondary:
+        cfg3 = secondary_cfg3(cfm, voc, dev, rank, world, args.cfg3_utterances or 32 * world, barrier)
+        if rank == 0:
+            with torch.inference_mode():
+                out["secondary"] = secondary_cfg4(model, voc, dev)
+            out["secondary_cfg3"] = cfg3
     if rank == 0:
         print("[bench] main legs done: " + json.dumps({k: out[k] for k in ("value", "ms_per_step", "ms_per_nfe", "e2e")}),
               file=sys.stderr, flush=True)
@@ -213,7 +216,9 @@ def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
         peaks = json.load(open(p))
     peak, which = (peaks["bf16_tflops_sustained"], "measured (sustained cuBLAS bf16)") if "bf16_tflops_sustained" in peaks \
         else (1400.0, "fallback (B200_PROFILING.md sustained)")
-    ws = next(iter(eng._ws.values())) if len(eng._ws) == 1 else max(eng._ws.values(), key=lambda w: w.steps * w.tpad)
+    # (re)populate the config-2 workspace (the side measurements may have evicted or replaced it) and take it by key
+    cfm.sample(ref_mel, ids, dur, lens=lens, steps=STEPS_NFE, cfg_strength=CFG, sway_sampling_coef=SWAY, seed=1)
+    ws = eng.workspace(1, 2, (T_TOTAL + 127) // 128 * 128, STEPS_NFE, True)
     kinds = ("gemm", "attention", "ln_modulate")
     orig = {name: getattr(L, name) for name in kinds}
     t, launches = {}, {}
@@ -276,6 +281,66 @@ def roofline(eng, cfm, ref_mel, ids, dur, lens) -> dict:
         "avg_launch_us": {k: round(1e3 * v / max(launches[k], 1), 2) for k, v in t.items()},
         "attention_tflops": round(fl["attn"] / (t["attention"] * 1e-3) / 1e12, 1),
     }
+
+
+def secondary_cfg3(cfm, voc, dev, rank, world, n_utt, barrier) -> dict:
+    """BASELINE config 3 (not the headline): Base DiT batched synthesis of mixed-length utterances (durations
+    ~ U(1, 30) s, seed 0 -> T = int(d * 93.75) frames, reference-free, 32 NFE, CFG 2.0), sharded across the ranks by
+    the longest-first cost-model assignment (shard.assign_utterances, no data-path collective) and, inside a rank,
+    packed into length-sorted batches of <= 8192 padded rows (shard.plan_batches). n_utt = 32 per GPU by default, i.e.
+    exactly the named 256-utterance job at 8 GPUs. One untimed pass first (workspaces + CUDA graphs per batch shape)."""
+    import random
+
+    import torch.distributed as dist
+
+    from oron_tts_b200.shard import assign_utterances, imbalance, padding_waste, plan_batches
+
+    rnd = random.Random(0)
+    frames = [int(rnd.uniform(1.0, 30.0) * 93.75) for _ in range(n_utt)]
+    plan = assign_utterances(frames, world)
+    mine = plan[rank]
+    my_frames = [frames[i] for i in mine]
+    batches = plan_batches(my_frames, max_rows=8192)
+    g = torch.Generator().manual_seed(3)
+    ids_all = [torch.randint(11, 65, (max(4, f // 8),), generator=g) for f in frames]
+
+    def one_pass():
+        outs = 0
+        for b in batches:
+            fr = [my_frames[j] for j in b]
+            tmax, B = max(fr), len(b)
+            ids = torch.full((B, tmax), -1, dtype=torch.long)
+            for r, j in enumerate(b):
+                src = ids_all[mine[j]]
+                ids[r, : fr[r]] = src[(torch.arange(fr[r]) * src.numel() // fr[r])]
+            mel, _ = cfm.sample(torch.zeros(B, tmax, 100, device=dev), ids.to(dev), torch.tensor(fr, device=dev),
+                                lens=torch.zeros(B, dtype=torch.long, device=dev), steps=STEPS_NFE, cfg_strength=CFG,
+                                sway_sampling_coef=SWAY, seed=7)
+            for r in range(B):
+                outs += voc.decode(mel[r:r + 1, : fr[r]].transpose(1, 2)).shape[-1]
+        return outs
+
+    one_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    samples = one_pass()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    tot = torch.tensor([float(samples)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    audio_s = float(tot.item()) / 24000.0
+    fl = sum(2 * f * (563.4e6 + 90112.0 * f) for f in frames) * STEPS_NFE
+    return {"workload": f"cfg3: {n_utt} reference-free utterances, durations U(1,30) s (seed 0), 32 NFE, CFG 2.0, + Vocos; "
+                        f"sharded over {world} GPU(s), length-sorted batches of <= 8192 padded rows",
+            "utterances": n_utt, "audio_s": round(audio_s, 1), "ms": round(float(ms.item()), 1),
+            "audio_s_per_s": round(audio_s / (float(ms.item()) / 1e3), 1),
+            "algorithmic_tflops": round(fl / (float(ms.item()) * 1e-3) / 1e12, 1),
+            "rank_imbalance": round(imbalance(frames, plan), 4), "padding_waste_rank0": round(padding_waste(my_frames, batches), 4),
+            "batches_rank0": len(batches)}
 
 
 def secondary_cfg4(model, voc, dev) -> dict:
@@ -376,6 +441,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg3-utterances", type=int, default=0, help="utterances of the config-3 side measurement (default 32 per GPU)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-4 (log-mel / Vocos) side measurement")
     a = ap.parse_args()
     res = run_reference(a) if a.impl == "reference" else run_ours(a)

@@ -249,10 +249,12 @@ class DiTEngine:
     # -------------------------------------------------------------------------------------------
     def workspace(self, nb: int, nbp: int, tpad: int, steps: int, keep_traj: bool) -> Workspace:
         key = (nb, nbp, tpad, steps, keep_traj)
-        ws = self._ws.get(key)
+        ws = self._ws.pop(key, None)
+        if ws is not None:
+            self._ws[key] = ws  # most recently used last
         if ws is None:
-            if len(self._ws) > 8:
-                self._ws.clear()
+            if len(self._ws) >= 24:  # drop the least recently used shape (each holds its buffers and its CUDA graph)
+                self._ws.pop(next(iter(self._ws)))
             ws = Workspace(self.w, nb, nbp, tpad, steps, keep_traj)
             self._ws[key] = ws
         return ws

@@ -188,6 +188,105 @@ class F5TTS(nn.Module):
                                                   seed=None if seed is None else seed + i, **common))
         return _concat_with_pause(waves, self.sample_rate, pause_s)
 
+    # ---- batched inference (extension over the reference) -----------------------------------
+    @torch.inference_mode()
+    def synthesize_batch(self, texts: list[str], lang: str = "mn", ref_audio_path: str | Path | None = None,
+                         ref_text: str | None = None, n_steps: int = 32, cfg_strength: float = 2.0,
+                         sway_sampling_coef: float | None = -1.0, speed: float = 1.0,
+                         target_durations_s: list[float | None] | None = None,
+                         max_chars_per_chunk: int | None = _MAX_CHARS, pause_s: float = _PAUSE_S,
+                         seeds: list[int | None] | None = None, max_rows_per_batch: int = 8192,
+                         device: str = "cuda") -> list[torch.Tensor]:
+        """``[synthesize(t, ...) for t in texts]`` with the segments of all requests packed into length-sorted
+        batches (the reference loops B = 1, f5tts.py:301-320). Every segment keeps the semantics of a B = 1 call:
+        its own seeded noise draw (flow.py:270-283), its own frame counts, GRN / convolutions over its own frames
+        only, so the waveforms equal the one-by-one results up to the order of fp32 partial sums.
+        One shared reference clip (``ref_audio_path`` / ``ref_text``) conditions every request."""
+        lang = validate_language(lang)
+        if n_steps < 1:
+            raise ValueError(f"n_steps must be >= 1, got {n_steps}")
+        if cfg_strength < 0:
+            raise ValueError(f"cfg_strength must be >= 0, got {cfg_strength}")
+        if speed <= 0:
+            raise ValueError(f"speed must be > 0, got {speed}")
+        if max_chars_per_chunk is not None and max_chars_per_chunk < 0:
+            raise ValueError(f"max_chars_per_chunk must be >= 0, got {max_chars_per_chunk}")
+        if pause_s < 0:
+            raise ValueError(f"pause_s must be >= 0, got {pause_s}")
+        n = len(texts)
+        durs = list(target_durations_s) if target_durations_s is not None else [None] * n
+        sds = list(seeds) if seeds is not None else [None] * n
+        if len(durs) != n or len(sds) != n:
+            raise ValueError("target_durations_s and seeds must have one entry per text")
+        if any(d is not None and d <= 0 for d in durs):
+            raise ValueError("target_duration_s must be > 0")
+        from .shard import plan_batches
+
+        self.eval()
+        self.to(device)
+        ap = self._audio_processor
+        ref_mel_raw = None
+        if ref_audio_path is not None:
+            if isinstance(ref_audio_path, torch.Tensor):
+                wav = ap.normalize_audio(ref_audio_path.reshape(-1).to(device, non_blocking=True))
+            else:
+                wav, _ = ap.load_audio(ref_audio_path)
+                wav = ap.normalize_audio(wav).to(device)
+            ref_mel_raw = ap.mel_spectrogram(wav)  # [n_mels, T_ref]
+        limit = max_chars_per_chunk or 0
+        segs: list[dict] = []  # one per (request, chunk)
+        owners: list[list[int]] = []
+        for r, text in enumerate(texts):
+            self._warn_lang_contamination(text, lang)
+            chunks = [c for c in (split_text_for_synthesis(text, limit) if limit > 0 else [text.strip()]) if c]
+            if not chunks:
+                raise ValueError("text must not be empty")
+            weights = [max(1, len(c.replace(" ", ""))) for c in chunks]
+            total_w = sum(weights)
+            mine = []
+            for i, chunk in enumerate(chunks):
+                if len(chunks) == 1:
+                    dur, seed = durs[r], sds[r]
+                else:
+                    dur = None if durs[r] is None else durs[r] * weights[i] / total_w
+                    seed = None if sds[r] is None else sds[r] + i
+                plan = self.prepare_segment(chunk, lang, ref_mel_raw, ref_text, speed, dur)
+                plan["seed"] = seed
+                mine.append(len(segs))
+                segs.append(plan)
+            owners.append(mine)
+
+        ref_len = 0 if ref_mel_raw is None else int(ref_mel_raw.shape[-1])
+        ref_rows = None if ref_mel_raw is None else ref_mel_raw.transpose(0, 1)  # [T_ref, n_mels]
+        vocos = self._get_vocos(device)
+        waves: list[torch.Tensor | None] = [None] * len(segs)
+        frames = [s["T_total"] for s in segs]
+        for batch in plan_batches(frames, max_rows=max_rows_per_batch):
+            tmax = max(frames[i] for i in batch)
+            B = len(batch)
+            ids = torch.full((B, tmax), -1, dtype=torch.long)
+            for j, i in enumerate(batch):
+                ids[j, : frames[i]] = torch.tensor(segs[i]["full_ids"], dtype=torch.long)
+            cond = torch.zeros(B, tmax, self.n_mels, device=device)
+            if ref_rows is not None:
+                cond[:, :ref_len] = ref_rows
+            y0 = torch.zeros(B, tmax, self.n_mels, device=device)
+            for j, i in enumerate(batch):  # the B = 1 noise stream of every segment (flow.py:270-283)
+                g = None
+                if segs[i]["seed"] is not None:
+                    g = torch.Generator(device=device).manual_seed(segs[i]["seed"])
+                y0[j, : frames[i]] = torch.randn(frames[i], self.n_mels, device=device, generator=g)
+            mel, _ = self.cfm.sample(cond=cond, text_ids=ids.to(device),
+                                     duration=torch.tensor([frames[i] for i in batch], device=device, dtype=torch.long),
+                                     lens=torch.full((B,), ref_len, device=device, dtype=torch.long), steps=n_steps,
+                                     cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, y0=y0)
+            for j, i in enumerate(batch):
+                target_mel = mel[j:j + 1, ref_len:frames[i], :].transpose(1, 2)
+                waves[i] = vocos.decode(target_mel).squeeze(0)
+        host = [w.cpu() for w in waves]
+        return [host[m[0]] if len(m) == 1 else _concat_with_pause([host[i] for i in m], self.sample_rate, pause_s)
+                for m in owners]
+
     def prepare_segment(self, text: str, lang: str, ref_mel: torch.Tensor | None, ref_text: str | None, speed: float,
                         target_duration_s: float | None) -> dict:
         """Integer side of one segment: ids, frame counts, stretched text (all host-side, bit-exact contract)."""

@@ -138,6 +138,29 @@ def test_sample_batched_matches_per_utterance():
         assert _rel(mel[b, :d], one[0]) < 2e-3, b
 
 
+def test_synthesize_batch_matches_one_by_one():
+    """F5TTS.synthesize_batch == [synthesize(t) for t in texts]: chunking, seeds (seed + chunk index), frame counts
+    and waveform lengths exact; waveforms equal up to bf16 arithmetic on differently padded batches."""
+    m = model_for("tiny")
+    voc = Vocos()
+    voc.load_state_dict(GW.fill_state_dict(voc.state_dict(), 4321), strict=True)
+    m.set_vocoder(voc.to(DEV).eval())
+    gen = torch.Generator().manual_seed(5)
+    ref = (torch.rand(24000, generator=gen) * 2 - 1) * 0.3
+    texts = ["Сайн байна уу", "Өнөөдөр цаг агаар сайхан байна. Бид хамтдаа уул руу алхаж, голын эрэг дээр амарна.", "Баярлалаа"]
+    kw = dict(lang="mn", ref_audio_path=ref, ref_text="Энэ бол жишээ", n_steps=3, cfg_strength=2.0, max_chars_per_chunk=40,
+              device=DEV)
+    seeds = [11, 22, 33]
+    got = m.synthesize_batch(texts, seeds=seeds, max_rows_per_batch=512, **kw)
+    assert len(got) == len(texts)
+    for t, s, w in zip(texts, seeds, got):
+        one = m.synthesize(t, seed=s, **kw)
+        assert w.shape == one.shape and not w.is_cuda
+        assert _rel(w, one) < 2e-2, t
+    with pytest.raises(ValueError, match="text must not be empty"):
+        m.synthesize_batch(["ok", "   "], **kw)
+
+
 def test_sample_small_config1():
     g = _gold("sample_small.pt")
     cfm = model_for("small").cfm

@@ -46,6 +46,28 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_plan_batches_rows_budget_and_cover():
+    from oron_tts_b200.shard import padding_waste, plan_batches
+
+    import random
+
+    rnd = random.Random(0)
+    frames = [int(rnd.uniform(1, 30) * 93.75) for _ in range(256)]  # BASELINE config 3 lengths
+    plan = plan_batches(frames, max_rows=8192)
+    assert sorted(i for b in plan for i in b) == list(range(256))
+    for b in plan:
+        tpad = (max(frames[i] for i in b) + 127) // 128 * 128
+        assert len(b) == 1 or len(b) * tpad <= 8192
+        assert frames[b[0]] == max(frames[i] for i in b)
+    assert padding_waste(frames, plan) < 1.12
+    assert plan_batches([5000], max_rows=1024) == [[0]]
+    assert plan_batches([], max_rows=1024) == []
+    import pytest
+
+    with pytest.raises(ValueError):
+        plan_batches([0], max_rows=1024)
+
+
 def test_two_rank_plan_agreement_gloo():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
