@@ -68,7 +68,7 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
 }
 
 // bf16 tensor [d2][d1][d0] (d0 contiguous), SWIZZLE_128B, box = (64, box1, 1); OOB reads give zeros.
-static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+int oron::make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                           uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box1, int rank) {
   PFN_cuTensorMapEncodeTiled enc = get_encode_fn();
   if (!enc) return fail(ORON_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");

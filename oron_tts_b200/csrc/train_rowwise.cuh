@@ -1,0 +1,768 @@
+// Row-wise / elementwise kernels of the OT-CFM training step (include/oron_b200_train.h): the backward halves of the
+// HBM-bound forward kernels in rowwise.cuh, the un-fused training variants of two fused forward epilogues, the loss
+// and the optimizer. Layout everywhere: activations are [nbatch * rows_per_batch, C] row-major ("frame-major").
+#pragma once
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace oron {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// derivatives of the activations (forward forms are the ones of the fused GEMM epilogues, ptx.cuh)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k = 0.7978845608028654f, a = 0.044715f;
+  const float x2 = x * x;
+  const float u = k * x * fmaf(a, x2, 1.0f);
+  const float t = tanhf(u);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * fmaf(3.0f * a, x2, 1.0f);
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = 1.0f / (1.0f + __expf(-x));
+  return s * (1.0f + x * (1.0f - s));
+}
+__device__ __forceinline__ float mish_grad(float x) {
+  const float sp = x > 20.0f ? x : log1pf(__expf(x));
+  const float t = tanhf(sp);
+  const float s = 1.0f / (1.0f + __expf(-x));
+  return t + x * (1.0f - t * t) * s;
+}
+__device__ __forceinline__ float act_apply(int act, float x) {
+  switch (act) {
+    case 1: return gelu_tanh_f(x);
+    case 2: return gelu_erf_f(x);
+    case 3: return silu_f(x);
+    case 4: return mish_f(x);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_grad(int act, float x) {
+  switch (act) {
+    case 1: return gelu_tanh_grad(x);
+    case 2: return gelu_erf_grad(x);
+    case 3: return silu_grad(x);
+    case 4: return mish_grad(x);
+    default: return 1.0f;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float ld_as_f32(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_f32<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_f32<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void st_from_f32(T* p, float v);
+template <>
+__device__ __forceinline__ void st_from_f32<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_from_f32<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// out = act(in) / out = dy * act'(pre): two columns per thread
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const TI* in, long long ld_in, long long rows, int C, int act, TO* out,
+                                                      long long ld_out) {
+  const long long half = C / 2;
+  const long long total = rows * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / half;
+    const int c = int(i - r * half) * 2;
+    const TI* p = in + r * ld_in + c;
+    TO* q = out + r * ld_out + c;
+    st_from_f32<TO>(q, act_apply(act, ld_as_f32<TI>(p)));
+    st_from_f32<TO>(q + 1, act_apply(act, ld_as_f32<TI>(p + 1)));
+  }
+}
+template <typename TD, typename TP, typename TO>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld_dy, const TP* pre, long long ld_pre,
+                                                      long long rows, int C, int act, TO* out, long long ld_out) {
+  const long long half = C / 2;
+  const long long total = rows * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / half;
+    const int c = int(i - r * half) * 2;
+    const TD* d = dy + r * ld_dy + c;
+    const TP* p = pre + r * ld_pre + c;
+    TO* q = out + r * ld_out + c;
+    st_from_f32<TO>(q, ld_as_f32<TD>(d) * act_grad(act, ld_as_f32<TP>(p)));
+    st_from_f32<TO>(q + 1, ld_as_f32<TD>(d + 1) * act_grad(act, ld_as_f32<TP>(p + 1)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// transpose with optional row mask and column sums
+// ---------------------------------------------------------------------------------------------------------
+struct TransposeArgs {
+  const __nv_bfloat16* in;
+  long long ld_in;
+  int rows_per_batch, nbatch, C;
+  const int* seq_lens;
+  __nv_bfloat16* out;
+  long long ld_out;
+  float* colsum;
+};
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const TransposeArgs a) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const long long R = (long long)a.rows_per_batch * a.nbatch;
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + 8 * i;
+    const long long row = r0 + r;
+    const int c = c0 + 2 * tx;
+    uint32_t v = 0;
+    if (row < R && c < a.C) {
+      bool ok = true;
+      if (a.seq_lens) {
+        const int b = int(row / a.rows_per_batch);
+        ok = int(row - (long long)b * a.rows_per_batch) < a.seq_lens[b];
+      }
+      if (ok) v = *reinterpret_cast<const uint32_t*>(a.in + row * a.ld_in + c);
+    }
+    *reinterpret_cast<uint32_t*>(&tile[r][2 * tx]) = v;
+  }
+  __syncthreads();
+  if (a.colsum && threadIdx.x < 64 && c0 + int(threadIdx.x) < a.C) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) s += __bfloat162float(tile[r][threadIdx.x]);
+    atomicAdd(a.colsum + c0 + threadIdx.x, s);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = ty + 8 * i;
+    const long long r = r0 + 2 * tx;
+    if (c0 + c < a.C && r < R) {
+      __nv_bfloat162 v;
+      v.x = tile[2 * tx][c];
+      v.y = tile[2 * tx + 1][c];
+      *reinterpret_cast<__nv_bfloat162*>(a.out + (long long)(c0 + c) * a.ld_out + r) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// column sums of per-warp register partials: lane owns columns {2*(lane + 32 i), +1}, i < V2 (C = 64 V2);
+// reduce over the 8 warps of the CTA through shared memory, then one atomicAdd per column.
+// ---------------------------------------------------------------------------------------------------------
+template <int V2>
+__device__ __forceinline__ void cta_colsum_atomic(const float2 (&acc)[V2], float* red, float* dst) {
+  constexpr int C = 64 * V2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < V2; ++i) *reinterpret_cast<float2*>(red + warp * C + 2 * (lane + 32 * i)) = acc[i];
+  __syncthreads();
+  if (dst) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w * C + c];
+      atomicAdd(dst + c, s);
+    }
+  }
+}
+
+constexpr int TR_ROWS = 64;  // rows per CTA of the column-reducing kernels (8 per warp)
+
+struct LnBwdArgs {
+  const float* x;
+  long long ldx;
+  const __nv_bfloat16* dy;
+  long long lddy;
+  int rows_per_batch, nbatch;
+  float eps;
+  const float* scale;
+  long long mod_ld;
+  int add_one;
+  const int* seq_lens;
+  float* dx;
+  long long lddx;
+  int accumulate;
+  float* dscale;
+  float* dshift;
+  long long dmod_ld;
+};
+template <int V2>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  constexpr int C = 64 * V2;
+  __shared__ float red[8 * C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+  float2 mult[V2], ds[V2], dh[V2];
+  const float one = a.add_one ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < V2; ++i) {
+    const float2 s = *reinterpret_cast<const float2*>(a.scale + (long long)b * a.mod_ld + 2 * (lane + 32 * i));
+    mult[i] = make_float2(one + s.x, one + s.y);
+    ds[i] = make_float2(0.f, 0.f);
+    dh[i] = make_float2(0.f, 0.f);
+  }
+  for (int k = 0; k < TR_ROWS / 8; ++k) {
+    const int t = blockIdx.x * TR_ROWS + warp + 8 * k;
+    if (t >= a.rows_per_batch) break;
+    const long long row = (long long)b * a.rows_per_batch + t;
+    float* dxr = a.dx + row * a.lddx;
+    if (t >= len) {
+      if (!a.accumulate) {
+#pragma unroll
+        for (int i = 0; i < V2; ++i) *reinterpret_cast<float2*>(dxr + 2 * (lane + 32 * i)) = make_float2(0.f, 0.f);
+      }
+      continue;
+    }
+    float2 v[V2];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V2; ++i) {
+      v[i] = *reinterpret_cast<const float2*>(a.x + row * a.ldx + 2 * (lane + 32 * i));
+      s += v[i].x + v[i].y;
+    }
+    const float mean = warp_sum_t(s) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V2; ++i) {
+      v[i].x -= mean;
+      v[i].y -= mean;
+      ss += v[i].x * v[i].x + v[i].y * v[i].y;
+    }
+    const float rstd = rsqrtf(warp_sum_t(ss) * (1.0f / C) + a.eps);
+    float2 g[V2];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V2; ++i) {
+      const float2 d = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.dy + row * a.lddy + 2 * (lane + 32 * i)));
+      v[i].x *= rstd;  // xhat
+      v[i].y *= rstd;
+      ds[i].x += d.x * v[i].x;
+      ds[i].y += d.y * v[i].y;
+      dh[i].x += d.x;
+      dh[i].y += d.y;
+      g[i] = make_float2(d.x * mult[i].x, d.y * mult[i].y);
+      s1 += g[i].x + g[i].y;
+      s2 += g[i].x * v[i].x + g[i].y * v[i].y;
+    }
+    const float m1 = warp_sum_t(s1) * (1.0f / C);
+    const float m2 = warp_sum_t(s2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < V2; ++i) {
+      float2 o = make_float2(rstd * (g[i].x - m1 - v[i].x * m2), rstd * (g[i].y - m1 - v[i].y * m2));
+      float2* p = reinterpret_cast<float2*>(dxr + 2 * (lane + 32 * i));
+      if (a.accumulate) {
+        const float2 old = *p;
+        o.x += old.x;
+        o.y += old.y;
+      }
+      *p = o;
+    }
+  }
+  cta_colsum_atomic<V2>(ds, red, a.dscale ? a.dscale + (long long)b * a.dmod_ld : nullptr);
+  cta_colsum_atomic<V2>(dh, red, a.dshift ? a.dshift + (long long)b * a.dmod_ld : nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gated residual (training forward) and its backward
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_resid_kernel(float* x, long long ldx, const __nv_bfloat16* y, long long ldy,
+                                                         int rows_per_batch, int nbatch, int C, const float* gate,
+                                                         long long gate_ld, const int* seq_lens, int mask_rows) {
+  const long long half = C / 2;
+  const long long total = (long long)rows_per_batch * nbatch * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / half;
+    const int c = int(i - row * half) * 2;
+    const int b = int(row / rows_per_batch);
+    if (mask_rows && seq_lens && int(row - (long long)b * rows_per_batch) >= seq_lens[b]) continue;
+    const float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(y + row * ldy + c));
+    const float2 gv = *reinterpret_cast<const float2*>(gate + (long long)b * gate_ld + c);
+    float2* p = reinterpret_cast<float2*>(x + row * ldx + c);
+    float2 xv = *p;
+    xv.x = fmaf(gv.x, yv.x, xv.x);
+    xv.y = fmaf(gv.y, yv.y, xv.y);
+    *p = xv;
+  }
+}
+
+struct GateBwdArgs {
+  const float* dx;
+  long long lddx;
+  const __nv_bfloat16* y;
+  long long ldy;
+  int rows_per_batch, nbatch;
+  const float* gate;
+  long long gate_ld;
+  const int* seq_lens;
+  __nv_bfloat16* dy;
+  long long lddy;
+  float* dgate;
+  long long dgate_ld;
+};
+template <int V2>
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
+  constexpr int C = 64 * V2;
+  __shared__ float red[8 * C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+  float2 gv[V2], dg[V2];
+#pragma unroll
+  for (int i = 0; i < V2; ++i) {
+    gv[i] = *reinterpret_cast<const float2*>(a.gate + (long long)b * a.gate_ld + 2 * (lane + 32 * i));
+    dg[i] = make_float2(0.f, 0.f);
+  }
+  for (int k = 0; k < TR_ROWS / 8; ++k) {
+    const int t = blockIdx.x * TR_ROWS + warp + 8 * k;
+    if (t >= a.rows_per_batch) break;
+    const long long row = (long long)b * a.rows_per_batch + t;
+    uint32_t* out = reinterpret_cast<uint32_t*>(a.dy + row * a.lddy);
+    if (t >= len) {
+#pragma unroll
+      for (int i = 0; i < V2; ++i) out[lane + 32 * i] = 0u;
+      continue;
+    }
+#pragma unroll
+    for (int i = 0; i < V2; ++i) {
+      const float2 d = *reinterpret_cast<const float2*>(a.dx + row * a.lddx + 2 * (lane + 32 * i));
+      const float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.y + row * a.ldy + 2 * (lane + 32 * i)));
+      dg[i].x += d.x * yv.x;
+      dg[i].y += d.y * yv.y;
+      out[lane + 32 * i] = pack_bf16x2(d.x * gv[i].x, d.y * gv[i].y);
+    }
+  }
+  cta_colsum_atomic<V2>(dg, red, a.dgate ? a.dgate + (long long)b * a.dgate_ld : nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// depthwise conv k=7 (f32), forward / data gradient (flip) and weight gradient
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwconv7_kernel(const float* x, long long ldx, int rows_per_batch, int nbatch, int C,
+                                                      const int* seq_lens, const float* w, const float* bias, int flip,
+                                                      float* out, long long ldo, int accumulate) {
+  const long long total = (long long)rows_per_batch * nbatch * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C;
+    const int c = int(i - row * C);
+    const int b = int(row / rows_per_batch);
+    const int t = int(row - (long long)b * rows_per_batch);
+    const int len = seq_lens ? min(seq_lens[b], rows_per_batch) : rows_per_batch;
+    float acc = bias ? bias[c] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int tt = t + k - 3;
+      if (tt >= 0 && tt < len) acc = fmaf(w[c * 7 + (flip ? 6 - k : k)], x[(row + k - 3) * ldx + c], acc);
+    }
+    float* p = out + row * ldo + c;
+    *p = accumulate ? *p + acc : acc;
+  }
+}
+// grid (ceil(rows_per_batch / 64), nbatch, ceil(C / 128)), 128 threads: one channel per thread over 64 rows
+__global__ void __launch_bounds__(128) dwconv7_wgrad_kernel(const float* x, long long ldx, const float* dy, long long lddy,
+                                                            int rows_per_batch, int nbatch, int C, const int* seq_lens,
+                                                            float* dw, float* db) {
+  const int c = blockIdx.z * 128 + threadIdx.x;
+  if (c >= C) return;
+  const int b = blockIdx.y;
+  const int len = seq_lens ? min(seq_lens[b], rows_per_batch) : rows_per_batch;
+  const int t0 = blockIdx.x * 64, t1 = min(t0 + 64, len);
+  if (t1 <= t0) return;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sb = 0.f;
+  const long long base = (long long)b * rows_per_batch;
+  for (int t = t0; t < t1; ++t) {
+    const float d = dy[(base + t) * lddy + c];
+    sb += d;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int tt = t + k - 3;
+      if (tt >= 0 && tt < len) acc[k] = fmaf(d, x[(base + tt) * ldx + c], acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) atomicAdd(dw + c * 7 + k, acc[k]);
+  if (db) atomicAdd(db + c, sb);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GELU(erf) -> GRN backward
+// ---------------------------------------------------------------------------------------------------------
+struct GrnBwdArgs {
+  const __nv_bfloat16* dy;
+  long long lddy;
+  const __nv_bfloat16* pre;
+  long long ldpre;
+  int rows_per_batch, nb;
+  const int* seq_lens;
+  float* A;      // [nb, C]
+  float* dbeta;  // [C]
+  const float* gamma;
+  const float* nx;    // [nb, C]
+  const float* coef;  // [nb, C]
+  __nv_bfloat16* dpre;
+  long long ldo;
+};
+template <int V2>
+__global__ void __launch_bounds__(256) grn_bwd_reduce_kernel(const GrnBwdArgs a) {
+  constexpr int C = 64 * V2;
+  __shared__ float red[8 * C];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+  float2 sa[V2], sb[V2];
+#pragma unroll
+  for (int i = 0; i < V2; ++i) sa[i] = sb[i] = make_float2(0.f, 0.f);
+  for (int k = 0; k < TR_ROWS / 8; ++k) {
+    const int t = blockIdx.x * TR_ROWS + warp + 8 * k;
+    if (t >= len) break;
+    const long long row = (long long)b * a.rows_per_batch + t;
+#pragma unroll
+    for (int i = 0; i < V2; ++i) {
+      const float2 d = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.dy + row * a.lddy + 2 * (lane + 32 * i)));
+      const float2 p = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.pre + row * a.ldpre + 2 * (lane + 32 * i)));
+      // h as the forward saw it: GELU output rounded to bf16
+      const float hx = __bfloat162float(__float2bfloat16(gelu_erf_f(p.x)));
+      const float hy = __bfloat162float(__float2bfloat16(gelu_erf_f(p.y)));
+      sa[i].x += d.x * hx;
+      sa[i].y += d.y * hy;
+      sb[i].x += d.x;
+      sb[i].y += d.y;
+    }
+  }
+  cta_colsum_atomic<V2>(sa, red, a.A + (long long)b * C);
+  cta_colsum_atomic<V2>(sb, red, a.dbeta);
+}
+// one CTA per batch element
+__global__ void __launch_bounds__(256) grn_bwd_coef_kernel(const float* A, const float* gx2, int nb, int C, const float* gamma,
+                                                           float* coef, float* nx, float* dgamma) {
+  __shared__ float red[2][8];
+  __shared__ float s_tot[2];
+  const int b = blockIdx.x;
+  float sg = 0.f, sd = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gx = sqrtf(gx2[(long long)b * C + c]);
+    sg += gx;
+    sd += gamma[c] * A[(long long)b * C + c] * gx;
+  }
+  sg = warp_sum_t(sg);
+  sd = warp_sum_t(sd);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sg; red[1][threadIdx.x >> 5] = sd; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < 8; ++i) { a0 += red[0][i]; a1 += red[1][i]; }
+    s_tot[0] = a0;
+    s_tot[1] = a1;
+  }
+  __syncthreads();
+  const float den = s_tot[0] / float(C) + 1e-6f;
+  const float S = s_tot[1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float gx = sqrtf(gx2[(long long)b * C + c]);
+    const float n = gx / den;
+    const float a = A[(long long)b * C + c];
+    const float dgx = gamma[c] * a / den - S / (float(C) * den * den);
+    nx[(long long)b * C + c] = n;
+    coef[(long long)b * C + c] = gx > 0.f ? dgx / gx : 0.f;
+    atomicAdd(dgamma + c, n * a);
+  }
+}
+__global__ void __launch_bounds__(256) grn_bwd_apply_kernel(const GrnBwdArgs a, int C) {
+  const long long half = C / 2;
+  const long long total = (long long)a.rows_per_batch * a.nb * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / half;
+    const int c = int(i - row * half) * 2;
+    const int b = int(row / a.rows_per_batch);
+    const int t = int(row - (long long)b * a.rows_per_batch);
+    const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+    uint32_t o = 0u;
+    if (t < len) {
+      const float2 d = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.dy + row * a.lddy + c));
+      const float2 p = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.pre + row * a.ldpre + c));
+      const float hx = __bfloat162float(__float2bfloat16(gelu_erf_f(p.x)));
+      const float hy = __bfloat162float(__float2bfloat16(gelu_erf_f(p.y)));
+      const float2 n = *reinterpret_cast<const float2*>(a.nx + (long long)b * C + c);
+      const float2 cf = *reinterpret_cast<const float2*>(a.coef + (long long)b * C + c);
+      const float2 g = *reinterpret_cast<const float2*>(a.gamma + c);
+      const float dhx = d.x * fmaf(g.x, n.x, 1.0f) + cf.x * hx;
+      const float dhy = d.y * fmaf(g.y, n.y, 1.0f) + cf.y * hy;
+      o = pack_bf16x2(dhx * gelu_erf_grad(p.x), dhy * gelu_erf_grad(p.y));
+    }
+    *reinterpret_cast<uint32_t*>(a.dpre + row * a.ldo + c) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// embedding gradient
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) text_embed_bwd_kernel(const int* ids, const uint8_t* drop, const float* dx, long long lddx,
+                                                             int rows_per_batch, int nb, int C, float* dtable) {
+  const long long total = (long long)rows_per_batch * nb * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C;
+    const int c = int(i - row * C);
+    const int id = ids[row];
+    if (id == 0) continue;  // filler / padding rows were zeroed in the forward (encoder.py:86-87)
+    const int b = int(row / rows_per_batch);
+    const int eff = drop[b] ? 0 : id;
+    atomicAdd(dtable + (long long)eff * C + c, dx[row * lddx + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// skinny matmuls (M = nb rows)
+// ---------------------------------------------------------------------------------------------------------
+// grid (ceil(N / 1024), ceil(K / 512)); 256 threads, 2 columns of K per thread
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* dY, long long lddy, int nb, int N, const __nv_bfloat16* W,
+                                                           long long ldw, int K, float* dX, long long lddx) {
+  __shared__ float sdy[8][64];
+  const int k = blockIdx.y * 512 + threadIdx.x * 2;
+  const int n_begin = blockIdx.x * 1024, n_end = min(n_begin + 1024, N);
+  for (int b0 = 0; b0 < nb; b0 += 8) {
+    float2 acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int n0 = n_begin; n0 < n_end; n0 += 64) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 8 * 64; i += 256) {
+        const int j = i >> 6, n = n0 + (i & 63);
+        sdy[j][i & 63] = (b0 + j < nb && n < n_end) ? dY[(long long)(b0 + j) * lddy + n] : 0.f;
+      }
+      __syncthreads();
+      if (k < K) {
+        const int nn = min(64, n_end - n0);
+        for (int n = 0; n < nn; ++n) {
+          const float2 w = bf2_to_f2(*reinterpret_cast<const uint32_t*>(W + (long long)(n0 + n) * ldw + k));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[j].x = fmaf(sdy[j][n], w.x, acc[j].x);
+            acc[j].y = fmaf(sdy[j][n], w.y, acc[j].y);
+          }
+        }
+      }
+    }
+    if (k < K) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b0 + j < nb) {
+          atomicAdd(dX + (long long)(b0 + j) * lddx + k, acc[j].x);
+          if (k + 1 < K) atomicAdd(dX + (long long)(b0 + j) * lddx + k + 1, acc[j].y);
+        }
+    }
+  }
+}
+// grid (ceil(N / 8), ceil(K / 256)); 256 threads: thread = one k, 8 rows of n
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* dY, long long lddy, const float* X, long long ldx, int nb,
+                                                           int N, int K, float* dW, long long lddw, float* db, int accumulate) {
+  __shared__ float sdy[64][8];
+  const int n0 = blockIdx.x * 8;
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < nb * 8; i += 256) {
+    const int b = i >> 3, j = i & 7;
+    sdy[b][j] = (n0 + j < N) ? dY[(long long)b * lddy + n0 + j] : 0.f;
+  }
+  __syncthreads();
+  if (db && blockIdx.y == 0 && threadIdx.x < 8 && n0 + threadIdx.x < N) {
+    float s = 0.f;
+    for (int b = 0; b < nb; ++b) s += sdy[b][threadIdx.x];
+    db[n0 + threadIdx.x] = accumulate ? db[n0 + threadIdx.x] + s : s;
+  }
+  if (k >= K) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int b = 0; b < nb; ++b) {
+    const float xv = X[(long long)b * ldx + k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(sdy[b][j], xv, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (n0 + j < N) {
+      float* p = dW + (long long)(n0 + j) * lddw + k;
+      *p = accumulate ? *p + acc[j] : acc[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grouped conv (k = taps) weight gradient on the CUDA cores: one CTA per (64-channel block, tap, batch element),
+// 4 x 4 register tile per thread over a 64 (co) x 64 (ci) product; only same-group entries are written.
+// ---------------------------------------------------------------------------------------------------------
+struct GconvWgradArgs {
+  const __nv_bfloat16* x;
+  long long ldx;
+  const __nv_bfloat16* dy;
+  long long lddy;
+  int rows_per_batch, nbatch, C, cg, taps;
+  const int* seq_lens;
+  float* dw;
+  float* db;
+};
+__global__ void __launch_bounds__(256) gconv_wgrad_kernel(const GconvWgradArgs a) {
+  __shared__ __align__(16) float sx[32][64];
+  __shared__ __align__(16) float sd[32][64];
+  const int cb = blockIdx.x / a.taps;
+  const int tap = blockIdx.x - cb * a.taps;
+  const int b = blockIdx.y;
+  const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+  const int shift = tap - a.taps / 2;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;  // co = 4 ty + i, ci = 4 tx + j
+  const int cw = min(64, a.C - cb * 64);                   // channels of this block (C may be < 64 * blocks)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float sb = 0.f;  // bias gradient of channel threadIdx.x (< 64), tap 0 only
+  const long long base = (long long)b * a.rows_per_batch;
+  for (int t0 = 0; t0 < len; t0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+      const int r = i >> 5, c = (i & 31) * 2;
+      const int t = t0 + r, ts = t + shift;
+      float2 dv = make_float2(0.f, 0.f), xv = make_float2(0.f, 0.f);
+      if (c < cw) {
+        if (t < len) dv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.dy + (base + t) * a.lddy + cb * 64 + c));
+        if (t < len && ts >= 0 && ts < len) xv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.x + (base + ts) * a.ldx + cb * 64 + c));
+      }
+      *reinterpret_cast<float2*>(&sd[r][c]) = dv;
+      *reinterpret_cast<float2*>(&sx[r][c]) = xv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&sd[r][4 * ty]);
+      const float4 x4 = *reinterpret_cast<const float4*>(&sx[r][4 * tx]);
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dd[i], xx[j], acc[i][j]);
+    }
+    if (tap == 0 && a.db && threadIdx.x < 64) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) sb += sd[r][threadIdx.x];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = 4 * ty + i, ci = 4 * tx + j;
+      if (co < cw && ci < cw && co / a.cg == ci / a.cg)
+        atomicAdd(a.dw + ((long long)(cb * 64 + co) * a.cg + (ci % a.cg)) * a.taps + tap, acc[i][j]);
+    }
+  if (tap == 0 && a.db && threadIdx.x < cw) atomicAdd(a.db + cb * 64 + threadIdx.x, sb);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// masked MSE + gradient; gradient norm; clip + AdamW
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cfm_loss_kernel(const float* pred, long long ldp, const float* flow, const uint8_t* span,
+                                                       const int* count, long long rows, int n_mels, float* loss_sum,
+                                                       __nv_bfloat16* dpred, long long ldd) {
+  __shared__ float red[8];
+  const float k = 2.0f / (fmaxf(float(*count), 1.0f) * float(n_mels));
+  float s = 0.f;
+  const long long total = rows * ldd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / ldd;
+    const int c = int(i - row * ldd);
+    float g = 0.f;
+    if (c < n_mels && span[row]) {
+      const float d = pred[row * ldp + c] - flow[row * n_mels + c];
+      s += d * d;
+      g = d * k;
+    }
+    dpred[i] = __float2bfloat16(g);
+  }
+  s = warp_sum_t(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(loss_sum, t);
+  }
+}
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n, float* out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < int(n - n4 * 4)) {
+    const float v = g[n4 * 4 + threadIdx.x];
+    s += v * v;
+  }
+  s = warp_sum_t(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+struct AdamArgs {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  __nv_bfloat16* pb;
+  long long n;
+  const float* sumsq;
+  float grad_scale, max_norm, lr, beta1, beta2, eps, wd, bc1, bc2;
+  int* skipped;
+};
+__global__ void __launch_bounds__(256) adamw_clip_kernel(const AdamArgs a) {
+  const float norm = sqrtf(*a.sumsq) * a.grad_scale;
+  if (!isfinite(norm)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.skipped) *a.skipped = 1;
+    return;
+  }
+  const float coef = a.grad_scale * fminf(1.0f, a.max_norm / (norm + 1e-6f));
+  const float step = a.lr / a.bc1;
+  const float rs2 = rsqrtf(a.bc2);
+  const float decay = 1.0f - a.lr * a.wd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = a.g[i] * coef;
+    float p = a.p[i] * decay;
+    const float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+    p -= step * m / (sqrtf(v) * rs2 + a.eps);
+    a.m[i] = m;
+    a.v[i] = v;
+    a.p[i] = p;
+    if (a.pb) a.pb[i] = __float2bfloat16(p);
+  }
+}
+__global__ void __launch_bounds__(256) f16_to_bf16_kernel(const __half* in, long long ld_in, long long rows, int C,
+                                                          __nv_bfloat16* out, long long ld_out) {
+  const long long half = C / 2;
+  const long long total = rows * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / half;
+    const int c = int(i - r * half) * 2;
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(in + r * ld_in + c));
+    *reinterpret_cast<uint32_t*>(out + r * ld_out + c) = pack_bf16x2(v.x, v.y);
+  }
+}
+
+}  // namespace oron

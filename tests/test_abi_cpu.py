@@ -35,6 +35,21 @@ def test_header_symbols_exported(built):
     assert built.lib().oron_abi_version() == 1
 
 
+def test_train_header_symbols_exported(built):
+    """include/oron_b200_train.h (the training-step entry points) against the library and its ctypes mirror."""
+    from oron_tts_b200 import _lib_train
+
+    text = open(os.path.join(ROOT, "include", "oron_b200_train.h")).read()
+    declared = set(re.findall(r"^int (oron_[a-z0-9_]+)\s*\(", text, flags=re.M))
+    assert declared == set(_lib_train.TRAIN_SYMBOLS)
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in oron_b200_train.h but not exported"
+    # every prototype has as many parameters as its ctypes argtypes
+    for name, body in re.findall(r"^int (oron_[a-z0-9_]+)\s*\(([^;]*?)\);", text, flags=re.M | re.S):
+        assert len(body.split(",")) == len(_lib_train._ARGTYPES[name]), name
+
+
 def test_gemm_desc_layout_matches_c(built, tmp_path):
     fields = [f[0] for f in built.GemmDesc._fields_]
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){",
