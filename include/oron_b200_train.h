@@ -35,13 +35,15 @@ int oron_ln_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, 
                 float* dshift, int64_t dmod_ld, oron_stream_t stream);
 
 /* Elementwise activation, forward (out = act(in)) and backward (out = dy * act'(pre)); act = oron_act or
- * ORON_ACT_MISH (= 4). in/pre/dy/out are [rows, C] with leading dimensions; *_f32 flags select f32 (1) or bf16 (0). */
+ * ORON_ACT_MISH (= 4). in/pre/dy/out are [rows, C] with leading dimensions; *_f32 flags select f32 (1) or bf16 (0).
+ * With seq_lens != NULL rows t >= seq_lens[row / rows_per_batch] are written as zeros (the masks of
+ * ConvPositionEmbedding, modules.py:136-140). */
 #define ORON_ACT_MISH 4
 int oron_act_fwd(const void* in, int32_t in_f32, int64_t ld_in, int64_t rows, int32_t C, int32_t act, void* out,
-                 int32_t out_f32, int64_t ld_out, oron_stream_t stream);
+                 int32_t out_f32, int64_t ld_out, int32_t rows_per_batch, const int32_t* seq_lens, oron_stream_t stream);
 int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const void* pre, int32_t pre_f32, int64_t ld_pre,
                  int64_t rows, int32_t C, int32_t act, void* out, int32_t out_f32, int64_t ld_out,
-                 oron_stream_t stream);
+                 int32_t rows_per_batch, const int32_t* seq_lens, oron_stream_t stream);
 
 /* Gated residual of DiTBlock (modules.py:338, 343) un-fused for training:
  *   fwd: x[r, :] += gate[b, :] * y[r, :]   (rows t >= seq_lens[b]: y taken as 0 when mask_rows, modules.py:281-282)
@@ -113,6 +115,9 @@ int oron_sumsq(const float* g, int64_t n, float* sumsq, oron_stream_t stream);
 int oron_adamw_clip(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* sumsq,
                     float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float wd,
                     float bc1, float bc2, int32_t* skipped, oron_stream_t stream);
+
+/* x[r, :] = 0 where row_valid[r] == 0: the masked_fill of TextEmbedding (encoder.py:86-87, 95) applied to a gradient. */
+int oron_mask_rows_f32(float* x, int64_t ldx, int64_t rows, int32_t C, const uint8_t* row_valid, oron_stream_t stream);
 
 /* IEEE f16 -> bf16 copy of [rows, C] (the V columns the QKV GEMM writes as f16 for the forward attention kernel). */
 int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, void* out, int64_t ld_out,

@@ -244,3 +244,60 @@ def cfm_sample(sd: SD, cond: Tensor, text_ids: Tensor, duration: Tensor | int, *
     if return_velocity:
         return out, traj, vels
     return out, traj
+
+
+# --------------------------------------------------------------------------------------------
+# CFM.forward (training objective) — src/models/flow.py:69-159. Differentiable (plain torch ops), so
+# torch.autograd over this function is the gradient oracle of the training step.
+# --------------------------------------------------------------------------------------------
+def cfm_eval_draws(x1: Tensor, lens: Tensor, frac_lengths_mask: tuple[float, float] = (0.7, 1.0)) -> dict:
+    """The deterministic eval-mode choices (flow.py:113-128, 136-138): centred span, t = 0.5, seed-0 noise."""
+    B, T, _ = x1.shape
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    mid = sum(frac_lengths_mask) / 2
+    span_len = (torch.full((B,), mid).float() * lens).long()
+    start = ((lens - span_len) // 2).clamp(min=0)
+    pos = torch.arange(T)
+    span = (pos[None, :] >= start[:, None]) & (pos[None, :] < (start + span_len)[:, None]) & mask
+    x0 = torch.randn(x1.shape, generator=torch.Generator().manual_seed(0), dtype=x1.dtype)
+    return dict(x1=x1, x0=x0, time=torch.full((B,), 0.5, dtype=x1.dtype), span=span, drop_audio=False, drop_text=False)
+
+
+def cfm_loss(sd: SD, draws: dict, text: Tensor, lens: Tensor) -> Tensor:
+    x1, x0, time, span = draws["x1"], draws["x0"], draws["time"], draws["span"]
+    T = x1.shape[1]
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    t = time[:, None, None]
+    phi = (1 - t) * x0 + t * x1
+    cond = torch.where(span[..., None], torch.zeros_like(x1), x1)
+    pred = dit_forward(sd, phi, cond, text, time, mask, drop_audio_cond=draws["drop_audio"], drop_text=draws["drop_text"])
+    return F.mse_loss(pred, x1 - x0, reduction="none")[span].mean()
+
+
+def cfm_loss_and_grads(sd: SD, draws: dict, text: Tensor, lens: Tensor) -> tuple[Tensor, dict]:
+    """Loss and d loss / d parameter for every floating-point entry of the state dict (inv_freq excluded)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "inv_freq" not in k}
+    full = dict(sd)
+    full.update(leaves)
+    loss = cfm_loss(full, draws, text, lens)
+    grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(leaves, grads)}
+
+
+def adamw_clip_step(params: dict, grads: dict, state: dict, *, lr: float, step: int, max_norm: float = 1.0,
+                    betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01) -> float:
+    """clip_grad_norm_ + torch.optim.AdamW update restated (trainer.py:76-80, 206-211). In place on `params`;
+    `state` holds exp_avg / exp_avg_sq per key. Returns the pre-clip global norm."""
+    total = math.sqrt(sum(float((g.double() ** 2).sum()) for g in grads.values()))
+    coef = min(1.0, max_norm / (total + 1e-6))
+    b1, b2 = betas
+    for k, p in params.items():
+        g = grads[k] * coef
+        m = state.setdefault(k + ".m", torch.zeros_like(p))
+        v = state.setdefault(k + ".v", torch.zeros_like(p))
+        p.mul_(1 - lr * weight_decay)
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (v.sqrt() / math.sqrt(1 - b2 ** step)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / (1 - b1 ** step))
+    return total

@@ -15,15 +15,15 @@ TRAIN_SYMBOLS = (
     "oron_transpose_bf16", "oron_ln_bwd", "oron_act_fwd", "oron_act_bwd", "oron_gate_resid", "oron_gate_bwd",
     "oron_dwconv7", "oron_dwconv7_wgrad", "oron_grn_bwd_reduce", "oron_grn_bwd_coef", "oron_grn_bwd_apply",
     "oron_text_embed_bwd", "oron_skinny_dgrad", "oron_skinny_wgrad", "oron_gconv_wgrad", "oron_cfm_loss", "oron_sumsq",
-    "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd",
+    "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32",
 )
 
 _P, _I, _L, _F = c_void_p, c_int32, c_int64, c_float
 _ARGTYPES = {
     "oron_transpose_bf16": [_P, _L, _I, _I, _I, _P, _P, _L, _P, _P],
     "oron_ln_bwd": [_P, _L, _P, _L, _I, _I, _I, _F, _P, _L, _I, _P, _P, _L, _I, _P, _P, _L, _P],
-    "oron_act_fwd": [_P, _I, _L, _L, _I, _I, _P, _I, _L, _P],
-    "oron_act_bwd": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P, _I, _L, _P],
+    "oron_act_fwd": [_P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _P],
+    "oron_act_bwd": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _P],
     "oron_gate_resid": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _P],
     "oron_gate_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _L, _P, _L, _P],
     "oron_dwconv7": [_P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _L, _I, _P],
@@ -39,6 +39,7 @@ _ARGTYPES = {
     "oron_sumsq": [_P, _L, _P, _P],
     "oron_adamw_clip": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "oron_f16_to_bf16": [_P, _L, _L, _I, _P, _L, _P],
+    "oron_mask_rows_f32": [_P, _L, _L, _I, _P, _P],
     "oron_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P],
 }
 _bound = False
@@ -80,14 +81,17 @@ def ln_bwd(x: torch.Tensor, dy: torch.Tensor, *, rows_per_batch: int, nbatch: in
            "oron_ln_bwd")
 
 
-def act_fwd(x: torch.Tensor, out: torch.Tensor, act: int) -> None:
+def act_fwd(x: torch.Tensor, out: torch.Tensor, act: int, *, rows_per_batch: int = 0,
+            seq_lens: torch.Tensor | None = None) -> None:
     _check(tlib().oron_act_fwd(_ptr(x), _is32(x), _ld(x), x.shape[0], x.shape[1], act, _ptr(out), _is32(out), _ld(out),
-                               _stream()), "oron_act_fwd")
+                               int(rows_per_batch), _ptr(seq_lens, torch.int32, "seq_lens"), _stream()), "oron_act_fwd")
 
 
-def act_bwd(dy: torch.Tensor, pre: torch.Tensor, out: torch.Tensor, act: int) -> None:
+def act_bwd(dy: torch.Tensor, pre: torch.Tensor, out: torch.Tensor, act: int, *, rows_per_batch: int = 0,
+            seq_lens: torch.Tensor | None = None) -> None:
     _check(tlib().oron_act_bwd(_ptr(dy), _is32(dy), _ld(dy), _ptr(pre), _is32(pre), _ld(pre), dy.shape[0], dy.shape[1], act,
-                               _ptr(out), _is32(out), _ld(out), _stream()), "oron_act_bwd")
+                               _ptr(out), _is32(out), _ld(out), int(rows_per_batch), _ptr(seq_lens, torch.int32, "seq_lens"),
+                               _stream()), "oron_act_bwd")
 
 
 def gate_resid(x: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch: int, gate: torch.Tensor, gate_ld: int,
@@ -182,6 +186,11 @@ def adamw_clip(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
                                   _ptr(pb, BF16, "pb"), p.numel(), _ptr(sumsq_t, F32, "sumsq"), grad_scale, max_norm, lr,
                                   beta1, beta2, eps, wd, bc1, bc2, _ptr(skipped, torch.int32, "skipped"), _stream()),
            "oron_adamw_clip")
+
+
+def mask_rows(x: torch.Tensor, row_valid: torch.Tensor) -> None:
+    _check(tlib().oron_mask_rows_f32(_ptr(x, F32, "x"), _ld(x), x.shape[0], x.shape[1], _ptr(row_valid, torch.uint8, "row_valid"),
+                                     _stream()), "oron_mask_rows_f32")
 
 
 def f16_to_bf16(x: torch.Tensor, out: torch.Tensor) -> None:

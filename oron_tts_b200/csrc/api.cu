@@ -374,7 +374,8 @@ extern "C" int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_ba
   else if (C == 256) launch_pdl(ln_modulate_kernel<256>, dim3(blocks), dim3(256), 0, st, a);
   else if (C == 128) launch_pdl(ln_modulate_kernel<128>, dim3(blocks), dim3(256), 0, st, a);
   else if (C == 768) launch_pdl(ln_modulate_kernel<768>, dim3(blocks), dim3(256), 0, st, a);
-  else return fail(ORON_ERR_UNSUPPORTED, "ln_modulate: C=%d not supported (128/256/512/768/1024)", C);
+  else if (C == 64) launch_pdl(ln_modulate64_kernel, dim3(blocks), dim3(256), 0, st, a);
+  else return fail(ORON_ERR_UNSUPPORTED, "ln_modulate: C=%d not supported (64/128/256/512/768/1024)", C);
   return check_launch("ln_modulate");
 }
 

@@ -84,6 +84,32 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnArgs a) {
   }
 }
 
+// Narrow rows (C = 64: the text embedding of small models): two columns per lane, same arithmetic.
+__global__ void __launch_bounds__(256) ln_modulate64_kernel(const LnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int C = 64;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)a.rows_per_batch * a.nbatch;
+  if (warp >= rows) return;
+  const int b = warp / a.rows_per_batch;
+  float2 v = reinterpret_cast<const float2*>(a.x + (long long)warp * a.ldx)[lane];
+  const float mean = warp_sum(v.x + v.y) * (1.0f / C);
+  v.x -= mean;
+  v.y -= mean;
+  const float rstd = rsqrtf(warp_sum(v.x * v.x + v.y * v.y) * (1.0f / C) + a.eps);
+  const long long step = a.step_ptr ? (long long)__ldg(a.step_ptr) : 0ll;
+  const long long moff = step * a.step_stride + (long long)(b % a.mod_nb) * a.mod_ld;
+  const float2 g = reinterpret_cast<const float2*>(a.scale + moff)[lane];
+  float2 h = make_float2(0.f, 0.f);
+  if (a.shift) h = reinterpret_cast<const float2*>(a.shift + moff)[lane];
+  const float one = a.add_one ? 1.f : 0.f;
+  const float2 y = make_float2(v.x * rstd * (one + g.x) + h.x, v.y * rstd * (one + g.y) + h.y);
+  if (a.out_bf16) reinterpret_cast<uint32_t*>(a.out_bf16 + (long long)warp * a.ldo)[lane] = pack_bf16x2(y.x, y.y);
+  if (a.out_f32) reinterpret_cast<float2*>(a.out_f32 + (long long)warp * a.ldo)[lane] = y;
+}
+
 // ---------------------------------------------------------------------------
 // CFG combine + Euler update (flow.py:266-267, 295-299), one launch per ODE step:
 //   v = v_c + (v_c - v_u) * cfg ;  x += v * dt[step]

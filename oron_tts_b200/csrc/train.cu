@@ -58,41 +58,43 @@ extern "C" int oron_ln_bwd(const float* x, int64_t ldx, const void* dy_bf16, int
 
 template <typename TI, typename TO>
 static void launch_act_fwd(const void* in, int64_t ld_in, int64_t rows, int32_t C, int32_t act, void* out, int64_t ld_out,
-                           cudaStream_t st) {
+                           int rpb, const int* sl, cudaStream_t st) {
   act_fwd_kernel<TI, TO><<<ew_blocks(rows * (C / 2)), 256, 0, st>>>(reinterpret_cast<const TI*>(in), ld_in, rows, C, act,
-                                                                    reinterpret_cast<TO*>(out), ld_out);
+                                                                    reinterpret_cast<TO*>(out), ld_out, rpb, sl);
 }
 extern "C" int oron_act_fwd(const void* in, int32_t in_f32, int64_t ld_in, int64_t rows, int32_t C, int32_t act, void* out,
-                            int32_t out_f32, int64_t ld_out, oron_stream_t stream) {
-  if (!in || !out || (C & 1)) return fail(ORON_ERR_BAD_ARG, "act_fwd: bad argument");
+                            int32_t out_f32, int64_t ld_out, int32_t rows_per_batch, const int32_t* seq_lens,
+                            oron_stream_t stream) {
+  if (!in || !out || (C & 1) || (seq_lens && rows_per_batch <= 0)) return fail(ORON_ERR_BAD_ARG, "act_fwd: bad argument");
   if (rows <= 0) return 0;
   cudaStream_t st = ST(stream);
-  if (in_f32 && out_f32) launch_act_fwd<float, float>(in, ld_in, rows, C, act, out, ld_out, st);
-  else if (in_f32) launch_act_fwd<float, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, st);
-  else if (out_f32) launch_act_fwd<__nv_bfloat16, float>(in, ld_in, rows, C, act, out, ld_out, st);
-  else launch_act_fwd<__nv_bfloat16, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, st);
+  if (in_f32 && out_f32) launch_act_fwd<float, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
+  else if (in_f32) launch_act_fwd<float, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
+  else if (out_f32) launch_act_fwd<__nv_bfloat16, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
+  else launch_act_fwd<__nv_bfloat16, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
   return check_launch("act_fwd");
 }
 template <typename TD, typename TP, typename TO>
 static void launch_act_bwd(const void* dy, int64_t ld_dy, const void* pre, int64_t ld_pre, int64_t rows, int32_t C,
-                           int32_t act, void* out, int64_t ld_out, cudaStream_t st) {
+                           int32_t act, void* out, int64_t ld_out, int rpb, const int* sl, cudaStream_t st) {
   act_bwd_kernel<TD, TP, TO><<<ew_blocks(rows * (C / 2)), 256, 0, st>>>(
       reinterpret_cast<const TD*>(dy), ld_dy, reinterpret_cast<const TP*>(pre), ld_pre, rows, C, act,
-      reinterpret_cast<TO*>(out), ld_out);
+      reinterpret_cast<TO*>(out), ld_out, rpb, sl);
 }
 extern "C" int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const void* pre, int32_t pre_f32, int64_t ld_pre,
                             int64_t rows, int32_t C, int32_t act, void* out, int32_t out_f32, int64_t ld_out,
-                            oron_stream_t stream) {
-  if (!dy || !pre || !out || (C & 1)) return fail(ORON_ERR_BAD_ARG, "act_bwd: bad argument");
+                            int32_t rows_per_batch, const int32_t* seq_lens, oron_stream_t stream) {
+  if (!dy || !pre || !out || (C & 1) || (seq_lens && rows_per_batch <= 0)) return fail(ORON_ERR_BAD_ARG, "act_bwd: bad argument");
   if (rows <= 0) return 0;
   cudaStream_t st = ST(stream);
   using bf = __nv_bfloat16;
   const int key = (dy_f32 ? 4 : 0) | (pre_f32 ? 2 : 0) | (out_f32 ? 1 : 0);
   switch (key) {
-    case 0: launch_act_bwd<bf, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, st); break;
-    case 7: launch_act_bwd<float, float, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, st); break;
-    case 1: launch_act_bwd<bf, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, st); break;
-    case 5: launch_act_bwd<float, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, st); break;
+    case 0: launch_act_bwd<bf, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
+    case 7: launch_act_bwd<float, float, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
+    case 1: launch_act_bwd<bf, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
+    case 4: launch_act_bwd<float, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
+    case 5: launch_act_bwd<float, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
     default: return fail(ORON_ERR_UNSUPPORTED, "act_bwd: dtype combination %d not instantiated", key);
   }
   return check_launch("act_bwd");
@@ -250,6 +252,12 @@ extern "C" int oron_adamw_clip(float* p, const float* g, float* m, float* v, voi
              bc1, bc2, skipped};
   adamw_clip_kernel<<<ew_blocks(n), 256, 0, ST(stream)>>>(a);
   return check_launch("adamw_clip");
+}
+extern "C" int oron_mask_rows_f32(float* x, int64_t ldx, int64_t rows, int32_t C, const uint8_t* row_valid,
+                                  oron_stream_t stream) {
+  if (!x || !row_valid) return fail(ORON_ERR_BAD_ARG, "mask_rows: null pointer");
+  mask_rows_kernel<<<ew_blocks(rows * C), 256, 0, ST(stream)>>>(x, ldx, rows, C, row_valid);
+  return check_launch("mask_rows");
 }
 extern "C" int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, void* out, int64_t ld_out,
                                 oron_stream_t stream) {

@@ -75,7 +75,7 @@ __device__ __forceinline__ void st_from_f32<__nv_bfloat16>(__nv_bfloat16* p, flo
 // out = act(in) / out = dy * act'(pre): two columns per thread
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* in, long long ld_in, long long rows, int C, int act, TO* out,
-                                                      long long ld_out) {
+                                                      long long ld_out, int rows_per_batch, const int* seq_lens) {
   const long long half = C / 2;
   const long long total = rows * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -83,13 +83,19 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* in, long long ld
     const int c = int(i - r * half) * 2;
     const TI* p = in + r * ld_in + c;
     TO* q = out + r * ld_out + c;
+    if (seq_lens != nullptr && int(r % rows_per_batch) >= seq_lens[r / rows_per_batch]) {  // masked row
+      st_from_f32<TO>(q, 0.f);
+      st_from_f32<TO>(q + 1, 0.f);
+      continue;
+    }
     st_from_f32<TO>(q, act_apply(act, ld_as_f32<TI>(p)));
     st_from_f32<TO>(q + 1, act_apply(act, ld_as_f32<TI>(p + 1)));
   }
 }
 template <typename TD, typename TP, typename TO>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld_dy, const TP* pre, long long ld_pre,
-                                                      long long rows, int C, int act, TO* out, long long ld_out) {
+                                                      long long rows, int C, int act, TO* out, long long ld_out,
+                                                      int rows_per_batch, const int* seq_lens) {
   const long long half = C / 2;
   const long long total = rows * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -98,6 +104,11 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld
     const TD* d = dy + r * ld_dy + c;
     const TP* p = pre + r * ld_pre + c;
     TO* q = out + r * ld_out + c;
+    if (seq_lens != nullptr && int(r % rows_per_batch) >= seq_lens[r / rows_per_batch]) {
+      st_from_f32<TO>(q, 0.f);
+      st_from_f32<TO>(q + 1, 0.f);
+      continue;
+    }
     st_from_f32<TO>(q, ld_as_f32<TD>(d) * act_grad(act, ld_as_f32<TP>(p)));
     st_from_f32<TO>(q + 1, ld_as_f32<TD>(d + 1) * act_grad(act, ld_as_f32<TP>(p + 1)));
   }
@@ -751,6 +762,14 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(const AdamArgs a) {
     a.v[i] = v;
     a.p[i] = p;
     if (a.pb) a.pb[i] = __float2bfloat16(p);
+  }
+}
+// x[r, :] = 0 where row_valid[r] == 0 (the masked_fill of TextEmbedding, encoder.py:86-87 / :95, on the gradient)
+__global__ void __launch_bounds__(256) mask_rows_kernel(float* x, long long ldx, long long rows, int C, const uint8_t* row_valid) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    if (!row_valid[r]) x[r * ldx + (i - r * C)] = 0.f;
   }
 }
 __global__ void __launch_bounds__(256) f16_to_bf16_kernel(const __half* in, long long ld_in, long long rows, int C,

@@ -51,6 +51,21 @@ def pick_block_n(rows: int, n: int) -> int:
     return best
 
 
+def pack_conv_pos(w: torch.Tensor, D: int) -> dict:
+    """Grouped Conv1d weight [D, cg, taps] (modules.py:120-124) -> tap-major implicit-GEMM operand [D, taps * gsz] (bf16),
+    gsz = max(64, cg); groups narrower than 64 channels are packed block-diagonally into 64-channel blocks."""
+    cg, ks = w.shape[1], w.shape[2]
+    gsz = max(64, cg)
+    if gsz % 64:
+        raise NotImplementedError("conv_pos group width must divide or be a multiple of 64")
+    device = w.device
+    o = torch.arange(D, device=device)
+    off = (o // cg) * cg - (o // gsz) * gsz
+    w2 = torch.zeros(D, gsz, ks, device=device, dtype=F32)
+    w2[o[:, None], off[:, None] + torch.arange(cg, device=device)[None, :], :] = w.to(F32)
+    return dict(w=w2.permute(0, 2, 1).reshape(D, ks * gsz).to(BF16).contiguous(), gsz=gsz)
+
+
 # ------------------------------------------------------------------------------------------------
 # packed weights
 # ------------------------------------------------------------------------------------------------
@@ -127,17 +142,9 @@ class DiTWeights:
         self.conv_pos = []
         for idx in (0, 2):
             w = sd[f"input_embed.conv_pos_embed.conv1d.{idx}.weight"].detach().to(device=device, dtype=F32)
-            cg, ks = w.shape[1], w.shape[2]
-            gsz = max(64, cg)
-            if gsz % 64:
-                raise NotImplementedError("conv_pos group width must divide or be a multiple of 64")
-            o = torch.arange(D, device=device)
-            off = (o // cg) * cg - (o // gsz) * gsz
-            w2 = torch.zeros(D, gsz, ks, device=device, dtype=F32)
-            w2[o[:, None], off[:, None] + torch.arange(cg, device=device)[None, :], :] = w
-            w2 = w2.permute(0, 2, 1).reshape(D, ks * gsz)
-            self.conv_pos.append(dict(w=w2.to(BF16).contiguous(), b=f32(sd[f"input_embed.conv_pos_embed.conv1d.{idx}.bias"]),
-                                      taps=ks, gsz=gsz))
+            pk = pack_conv_pos(w, D)
+            self.conv_pos.append(dict(w=pk["w"], b=f32(sd[f"input_embed.conv_pos_embed.conv1d.{idx}.bias"]), taps=w.shape[2],
+                                      gsz=pk["gsz"]))
 
         # transformer blocks
         self.blocks = []

@@ -111,3 +111,28 @@ def test_oracle_istft_against_reference_decoder():
     wav = AO.istft_center(spec, normalized=True)
     assert wav.shape == g["wav"].shape
     assert _rel(wav, g["wav"]) < 1e-5
+
+
+def test_oracle_training_loss_grads_and_optimizer():
+    """Gradient oracle (autograd over the oracle's CFM loss) and the clip + AdamW restatement against the fixture
+    recorded from the live reference (tests/golden/make_golden_train.py)."""
+    g = _gold("train_tiny.pt")
+    sd = ref_state_dict("tiny")
+    x1 = g["mel"].transpose(1, 2)
+    draws = DO.cfm_eval_draws(x1, g["lens"])
+    loss, grads = DO.cfm_loss_and_grads(sd, draws, g["text"], g["lens"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])
+    assert set(grads) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        assert _rel(grads[k], ref) < 1e-3 or float((grads[k] - ref).abs().max()) < 1e-7, k
+    params = {k: sd[k].clone() for k in grads}
+    state: dict = {}
+    for step in range(2):
+        full = dict(sd)
+        full.update(params)
+        _, gr = DO.cfm_loss_and_grads(full, draws, g["text"], g["lens"])
+        norm = DO.adamw_clip_step(params, gr, state, lr=g[f"lr_step{step}"], step=step + 1)
+        if step == 0:
+            assert abs(norm - float(g["grad_norm"])) < 1e-4 * norm
+    for k, ref in g["params_after_2_steps"].items():
+        assert float((params[k] - ref).abs().max()) < 2e-6, k

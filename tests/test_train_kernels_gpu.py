@@ -100,6 +100,13 @@ def test_act_fwd_bwd(act, fn):
     xr2 = xb.float().requires_grad_()
     fn(xr2).backward(dyb.float())
     assert _rel(db, xr2.grad) < 6e-3
+    # row mask (rows t >= seq_lens[b] are written as zeros)
+    sl = torch.tensor([100, 150], device=DEV, dtype=torch.int32)
+    m = _mask(2, 150, [100, 150])
+    T.act_fwd(xb, ob, act, rows_per_batch=150, seq_lens=sl)
+    T.act_bwd(dyb, xb, db, act, rows_per_batch=150, seq_lens=sl)
+    assert float(ob[~m].float().abs().max()) == 0.0 and float(db[~m].float().abs().max()) == 0.0
+    assert _rel(db, xr2.grad * m[:, None]) < 6e-3 and _rel(ob, fn(xb.float()) * m[:, None]) < 6e-3
 
 
 def test_gate_resid_and_bwd():
