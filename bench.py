@@ -188,10 +188,12 @@ def run_ours(args) -> dict:
     }
     if not args.no_secondary:
         cfg3 = secondary_cfg3(cfm, voc, dev, rank, world, args.cfg3_utterances or 32 * world, barrier)
+        cfg5 = secondary_cfg5(model, dev, rank, world, barrier)
         if rank == 0:
             with torch.inference_mode():
                 out["secondary"] = secondary_cfg4(model, voc, dev)
             out["secondary_cfg3"] = cfg3
+            out["secondary_cfg5"] = cfg5
     if rank == 0:
         print("[bench] main legs done: " + json.dumps({k: out[k] for k in ("value", "ms_per_step", "ms_per_nfe", "e2e")}),
               file=sys.stderr, flush=True)
@@ -341,6 +343,56 @@ def secondary_cfg3(cfm, voc, dev, rank, world, n_utt, barrier) -> dict:
             "algorithmic_tflops": round(fl / (float(ms.item()) * 1e-3) / 1e12, 1),
             "rank_imbalance": round(imbalance(frames, plan), 4), "padding_waste_rank0": round(padding_waste(my_frames, batches), 4),
             "batches_rank0": len(batches)}
+
+
+def secondary_cfg5(model, dev, rank, world, barrier, steps: int = 3) -> dict:
+    """BASELINE config 5 (not the headline): Base DiT OT-CFM training step -- CFM.forward (random t / span / noise / CFG
+    drops, flow.py:101-138) + backward + NCCL gradient all-reduce + clip + AdamW (trainer.py:191-262) -- on the sm_100a
+    kernels, bf16 tensor-core operands with fp32 master weights / gradients / moments. Per-GPU batch 8 x 1024 frames
+    (runpod.yaml batch_size), data-parallel over the ranks (weak scaling). Algorithmic FLOPs = 3 x forward."""
+    import torch.distributed as dist
+    import weights as GW
+
+    from oron_tts_b200.f5tts import F5TTS
+    from oron_tts_b200.train import TrainEngine
+
+    B, Tn = 8, 1024
+    with torch.device(dev):
+        tm = F5TTS.from_config(GW.CONFIGS["base"])
+    tm.load_state_dict(model.state_dict(), strict=True)  # same seeded weights as the inference legs, separate storage
+    tm = tm.to(dev).train()
+    eng = TrainEngine(tm, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.01, max_grad_norm=1.0)
+    g = torch.Generator(device=dev).manual_seed(500 + rank)
+    mel = torch.randn(B, 100, Tn, device=dev, generator=g) * 1.5 - 3.0
+    text = torch.randint(4, 65, (B, Tn), device=dev, generator=g)
+    lens = torch.full((B,), Tn, device=dev, dtype=torch.long)
+    losses = []
+    for _ in range(2):
+        losses.append(eng.train_step(mel, text, lens, lr=1e-4))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses.append(eng.train_step(mel, text, lens, lr=1e-4))
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    ls = [float(x) for x in losses]
+    assert all(v == v and v < 1e6 for v in ls), ls
+    fwd = B * Tn * (563.4e6 + 90112.0 * Tn)
+    out = {"workload": f"cfg5: Base DiT OT-CFM training step, per-GPU batch {B} x {Tn} frames, bf16 operands / fp32 master+grads, "
+                       f"data-parallel x{world} (NCCL all-reduce of {eng.arena.numel * 4 / 1e9:.2f} GB fp32 gradients per step, "
+                       "per-block buckets overlapped with backward)",
+           "ms_per_step": round(ms, 2), "samples_per_s": round(world * B / (ms / 1e3), 2),
+           "frames_per_s": round(world * B * Tn / (ms / 1e3), 1),
+           "algorithmic_tflops_per_gpu": round(3 * fwd / (ms * 1e-3) / 1e12, 1), "loss_first_last": [round(ls[0], 4), round(ls[-1], 4)],
+           "optimizer_steps_skipped": int(eng.skipped.item())}
+    del eng, tm
+    torch.cuda.empty_cache()
+    return out
 
 
 def secondary_cfg4(model, voc, dev) -> dict:

@@ -95,6 +95,46 @@ class ParamArena:
         return arena[o:o + n].view(prm.shape if shape is None else shape)
 
 
+class GradReducer:
+    """Sum of the flat gradient arena over the data-parallel ranks (trainer.py:70-71 wraps the model in DDP for this).
+    The ranges of the transformer blocks are all-reduced asynchronously as soon as the backward pass reports them final
+    (``block_done``), overlapping NCCL with the backward kernels of the earlier blocks; ``finish`` waits for those and
+    reduces everything outside the block ranges (embeddings, AdaLN projections, output head). The division by the world
+    size is folded into the optimizer kernel. No-op without an initialised process group."""
+
+    def __init__(self, g: torch.Tensor, block_ranges: list[tuple[int, int]], overlap: bool = True):
+        self.g, self.block_ranges, self.overlap = g, block_ranges, overlap
+        self._pending: list = []
+
+    @staticmethod
+    def _world() -> int:
+        import torch.distributed as dist
+
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def block_done(self, i: int) -> None:
+        import torch.distributed as dist
+
+        if self._world() > 1 and self.overlap:
+            lo, hi = self.block_ranges[i]
+            self._pending.append((dist.all_reduce(self.g[lo:hi], op=dist.ReduceOp.SUM, async_op=True), lo, hi))
+
+    def finish(self) -> None:
+        import torch.distributed as dist
+
+        if self._world() == 1:
+            return
+        done = sorted((lo, hi) for _, lo, hi in self._pending)
+        for h, _, _ in self._pending:
+            h.wait()
+        self._pending.clear()
+        cur = 0
+        for lo, hi in done + [(self.g.numel(), self.g.numel())]:  # everything outside the already reduced ranges
+            if lo > cur:
+                dist.all_reduce(self.g[cur:lo], op=dist.ReduceOp.SUM)
+            cur = max(cur, hi)
+
+
 class TrainWeights(DiTWeights):
     """The engine's packed-weight record, as views into the arenas (bf16 operands, f32 biases / row-wise parameters)
     plus the few re-laid-out copies (input projection split, conv-position taps, transposes for the data gradients)
@@ -269,7 +309,7 @@ class TrainEngine:
         self._ws: dict = {}
         self.sumsq = torch.zeros(1, device=p0.device, dtype=F32)
         self.skipped = torch.zeros(1, device=p0.device, dtype=I32)
-        self._pending: list = []
+        self.reducer = GradReducer(self.arena.g, self.arena.block_ranges)
 
     def workspace(self, nb: int, tpad: int) -> TrainWorkspace:
         key = (nb, tpad)
@@ -558,30 +598,10 @@ class TrainEngine:
 
     # ---- data-parallel gradient mean + optimizer ---------------------------------------------------------------
     def _block_done(self, i: int) -> None:
-        """Gradients of transformer block i are final: start their all-reduce while the earlier blocks run backward."""
-        import torch.distributed as dist
-
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and self._overlap:
-            lo, hi = self.arena.block_ranges[i]
-            self._pending.append((dist.all_reduce(self.arena.g[lo:hi], op=dist.ReduceOp.SUM, async_op=True), lo, hi))
-
-    _overlap = True
+        self.reducer.block_done(i)
 
     def reduce_gradients(self) -> None:
-        """Sum of the gradients over the data-parallel ranks (the 1/world factor is folded into the optimizer kernel)."""
-        import torch.distributed as dist
-
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return
-        done = sorted((lo, hi) for _, lo, hi in self._pending)
-        for h, _, _ in self._pending:
-            h.wait()
-        self._pending.clear()
-        cur = 0
-        for lo, hi in done + [(self.arena.numel, self.arena.numel)]:  # everything outside the already reduced block ranges
-            if lo > cur:
-                dist.all_reduce(self.arena.g[cur:lo], op=dist.ReduceOp.SUM)
-            cur = max(cur, hi)
+        self.reducer.finish()
 
     @torch.no_grad()
     def optimizer_step(self, lr: float | None = None) -> None:

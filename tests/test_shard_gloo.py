@@ -89,3 +89,53 @@ def test_two_rank_plan_agreement_gloo():
         merged.update(res)
     assert sorted(merged) == list(range(64))
     assert ms == 11.0  # max over ranks
+
+
+def _reducer_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from oron_tts_b200.f5tts import F5TTS
+    from oron_tts_b200.train import GradReducer, ParamArena
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = F5TTS.from_config({"model": dict(dim=128, depth=3, heads=2, text_dim=64, conv_layers=1)})
+    arena = ParamArena(model)  # CPU arenas: parameters and .grad become views, state_dict unchanged
+    ok = all(p.data_ptr() >= arena.p.data_ptr() and p.grad.data_ptr() >= arena.g.data_ptr() for p in model.parameters())
+    ok = ok and len(arena.block_ranges) == 3 and all(hi > lo for lo, hi in arena.block_ranges)
+    # fused operands are contiguous views: q | k | v weights of a block, and the stacked AdaLN projections
+    o = arena.offsets
+    pre = "cfm.backbone.transformer_blocks.1.attn."
+    ok = ok and o[pre + "to_k.weight"] == o[pre + "to_q.weight"] + 128 * 128 and o[pre + "to_v.weight"] == o[pre + "to_k.weight"] + 128 * 128
+    ok = ok and o["cfm.backbone.norm_out.linear.weight"] == o["cfm.backbone.transformer_blocks.0.attn_norm.linear.weight"] + 3 * 6 * 128 * 128
+    base = torch.arange(arena.numel, dtype=torch.float32)
+    for overlap in (True, False):
+        arena.g.copy_(base * (rank + 1))
+        red = GradReducer(arena.g, arena.block_ranges, overlap=overlap)
+        for i in reversed(range(3)):
+            red.block_done(i)
+        red.finish()
+        ok = ok and torch.equal(arena.g, base * sum(r + 1 for r in range(world)))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_reducer_two_ranks_gloo():
+    """N > 1 host logic of the training step: bucketed (per transformer block) + remainder all-reduce of the flat arena."""
+    import multiprocessing as mp
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
