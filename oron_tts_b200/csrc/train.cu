@@ -49,9 +49,10 @@ extern "C" int oron_ln_bwd(const float* x, int64_t ldx, const void* dy_bf16, int
                            const int32_t* seq_lens, float* dx, int64_t lddx, int32_t accumulate, float* dscale,
                            float* dshift, int64_t dmod_ld, oron_stream_t stream) {
   if (!x || !dy_bf16 || !scale || !dx) return fail(ORON_ERR_BAD_ARG, "ln_bwd: null pointer");
+  const int rpc = tr_rows_for((long long)rows_per_batch * nbatch, num_sms());
   LnBwdArgs a{x, ldx, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), lddy, rows_per_batch, nbatch, eps, scale, mod_ld,
-              add_one, seq_lens, dx, lddx, accumulate, dscale, dshift, dmod_ld};
-  dim3 grid(unsigned((rows_per_batch + TR_ROWS - 1) / TR_ROWS), unsigned(nbatch));
+              add_one, seq_lens, dx, lddx, accumulate, dscale, dshift, dmod_ld, rpc};
+  dim3 grid(unsigned((rows_per_batch + rpc - 1) / rpc), unsigned(nbatch));
   DISPATCH_V2(C, (ln_bwd_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("ln_bwd");
 }
@@ -68,6 +69,13 @@ extern "C" int oron_act_fwd(const void* in, int32_t in_f32, int64_t ld_in, int64
   if (!in || !out || (C & 1) || (seq_lens && rows_per_batch <= 0)) return fail(ORON_ERR_BAD_ARG, "act_fwd: bad argument");
   if (rows <= 0) return 0;
   cudaStream_t st = ST(stream);
+  if (!in_f32 && !out_f32 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    act_fwd_bf16x8_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, rows, C, act,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows_per_batch,
+                                                                    seq_lens);
+    return check_launch("act_fwd");
+  }
   if (in_f32 && out_f32) launch_act_fwd<float, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
   else if (in_f32) launch_act_fwd<float, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
   else if (out_f32) launch_act_fwd<__nv_bfloat16, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
@@ -89,6 +97,13 @@ extern "C" int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const
   cudaStream_t st = ST(stream);
   using bf = __nv_bfloat16;
   const int key = (dy_f32 ? 4 : 0) | (pre_f32 ? 2 : 0) | (out_f32 ? 1 : 0);
+  if (key == 0 && C % 8 == 0 && ld_dy % 8 == 0 && ld_pre % 8 == 0 && ld_out % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    act_bwd_bf16x8_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, st>>>(
+        reinterpret_cast<const bf*>(dy), ld_dy, reinterpret_cast<const bf*>(pre), ld_pre, rows, C, act, reinterpret_cast<bf*>(out),
+        ld_out, rows_per_batch, seq_lens);
+    return check_launch("act_bwd");
+  }
   switch (key) {
     case 0: launch_act_bwd<bf, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
     case 7: launch_act_bwd<float, float, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
@@ -113,9 +128,10 @@ extern "C" int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, 
                              int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
                              void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, oron_stream_t stream) {
   if (!dx || !y_bf16 || !gate || !dy_bf16) return fail(ORON_ERR_BAD_ARG, "gate_bwd: null pointer");
+  const int rpc = tr_rows_for((long long)rows_per_batch * nbatch, num_sms());
   GateBwdArgs a{dx, lddx, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy, rows_per_batch, nbatch, gate, gate_ld,
-                seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld};
-  dim3 grid(unsigned((rows_per_batch + TR_ROWS - 1) / TR_ROWS), unsigned(nbatch));
+                seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld, rpc};
+  dim3 grid(unsigned((rows_per_batch + rpc - 1) / rpc), unsigned(nbatch));
   DISPATCH_V2(C, (gate_bwd_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("gate_bwd");
 }
@@ -155,7 +171,8 @@ extern "C" int oron_grn_bwd_reduce(const void* dy_bf16, int64_t lddy, const void
   a.dbeta = dbeta;
   cudaError_t e = cudaMemsetAsync(A, 0, sizeof(float) * size_t(nb) * C, ST(stream));
   if (e != cudaSuccess) return fail(int(e), "grn_bwd memset: %s", cudaGetErrorString(e));
-  dim3 grid(unsigned((rows_per_batch + TR_ROWS - 1) / TR_ROWS), unsigned(nb));
+  a.rows_per_cta = tr_rows_for((long long)rows_per_batch * nb, num_sms());
+  dim3 grid(unsigned((rows_per_batch + a.rows_per_cta - 1) / a.rows_per_cta), unsigned(nb));
   DISPATCH_V2(C, (grn_bwd_reduce_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("grn_bwd_reduce");
 }

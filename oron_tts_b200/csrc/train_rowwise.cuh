@@ -114,6 +114,55 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld
   }
 }
 
+// bf16 -> bf16 fast paths: 8 columns (16 bytes) per thread
+__global__ void __launch_bounds__(256) act_fwd_bf16x8_kernel(const __nv_bfloat16* in, long long ld_in, long long rows, int C, int act,
+                                                             __nv_bfloat16* out, long long ld_out, int rows_per_batch,
+                                                             const int* seq_lens) {
+  const long long per = C / 8;
+  const long long total = rows * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per;
+    const int c = int(i - r * per) * 8;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (seq_lens == nullptr || int(r % rows_per_batch) < seq_lens[r / rows_per_batch]) {
+      const uint4 v = *reinterpret_cast<const uint4*>(in + r * ld_in + c);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = bf2_to_f2(w[k]);
+        q[k] = pack_bf16x2(act_apply(act, f.x), act_apply(act, f.y));
+      }
+      o = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = o;
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_bf16x8_kernel(const __nv_bfloat16* dy, long long ld_dy, const __nv_bfloat16* pre,
+                                                             long long ld_pre, long long rows, int C, int act, __nv_bfloat16* out,
+                                                             long long ld_out, int rows_per_batch, const int* seq_lens) {
+  const long long per = C / 8;
+  const long long total = rows * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per;
+    const int c = int(i - r * per) * 8;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (seq_lens == nullptr || int(r % rows_per_batch) < seq_lens[r / rows_per_batch]) {
+      const uint4 d = *reinterpret_cast<const uint4*>(dy + r * ld_dy + c);
+      const uint4 p = *reinterpret_cast<const uint4*>(pre + r * ld_pre + c);
+      const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, pw[4] = {p.x, p.y, p.z, p.w};
+      uint32_t q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fd = bf2_to_f2(dw[k]), fp = bf2_to_f2(pw[k]);
+        q[k] = pack_bf16x2(fd.x * act_grad(act, fp.x), fd.y * act_grad(act, fp.y));
+      }
+      o = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // transpose with optional row mask and column sums
 // ---------------------------------------------------------------------------------------------------------
@@ -190,7 +239,13 @@ __device__ __forceinline__ void cta_colsum_atomic(const float2 (&acc)[V2], float
   }
 }
 
-constexpr int TR_ROWS = 64;  // rows per CTA of the column-reducing kernels (8 per warp)
+// rows per CTA of the column-reducing kernels (a multiple of 8: one row per warp per pass), chosen by the host so that
+// the grid covers the SMs several times over; fewer rows per CTA = more parallelism, more atomics
+__host__ __device__ inline int tr_rows_for(long long total_rows, int sms) {
+  long long r = total_rows / (4ll * sms);
+  r = (r / 8) * 8;
+  return int(r < 8 ? 8 : (r > 64 ? 64 : r));
+}
 
 struct LnBwdArgs {
   const float* x;
@@ -209,6 +264,7 @@ struct LnBwdArgs {
   float* dscale;
   float* dshift;
   long long dmod_ld;
+  int rows_per_cta;
 };
 template <int V2>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
@@ -226,8 +282,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     ds[i] = make_float2(0.f, 0.f);
     dh[i] = make_float2(0.f, 0.f);
   }
-  for (int k = 0; k < TR_ROWS / 8; ++k) {
-    const int t = blockIdx.x * TR_ROWS + warp + 8 * k;
+  for (int k = 0; k < a.rows_per_cta / 8; ++k) {
+    const int t = blockIdx.x * a.rows_per_cta + warp + 8 * k;
     if (t >= a.rows_per_batch) break;
     const long long row = (long long)b * a.rows_per_batch + t;
     float* dxr = a.dx + row * a.lddx;
@@ -323,6 +379,7 @@ struct GateBwdArgs {
   long long lddy;
   float* dgate;
   long long dgate_ld;
+  int rows_per_cta;
 };
 template <int V2>
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
@@ -337,8 +394,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
     gv[i] = *reinterpret_cast<const float2*>(a.gate + (long long)b * a.gate_ld + 2 * (lane + 32 * i));
     dg[i] = make_float2(0.f, 0.f);
   }
-  for (int k = 0; k < TR_ROWS / 8; ++k) {
-    const int t = blockIdx.x * TR_ROWS + warp + 8 * k;
+  for (int k = 0; k < a.rows_per_cta / 8; ++k) {
+    const int t = blockIdx.x * a.rows_per_cta + warp + 8 * k;
     if (t >= a.rows_per_batch) break;
     const long long row = (long long)b * a.rows_per_batch + t;
     uint32_t* out = reinterpret_cast<uint32_t*>(a.dy + row * a.lddy);
@@ -426,6 +483,7 @@ struct GrnBwdArgs {
   const float* coef;  // [nb, C]
   __nv_bfloat16* dpre;
   long long ldo;
+  int rows_per_cta;
 };
 template <int V2>
 __global__ void __launch_bounds__(256) grn_bwd_reduce_kernel(const GrnBwdArgs a) {
@@ -437,8 +495,8 @@ __global__ void __launch_bounds__(256) grn_bwd_reduce_kernel(const GrnBwdArgs a)
   float2 sa[V2], sb[V2];
 #pragma unroll
   for (int i = 0; i < V2; ++i) sa[i] = sb[i] = make_float2(0.f, 0.f);
-  for (int k = 0; k < TR_ROWS / 8; ++k) {
-    const int t = blockIdx.x * TR_ROWS + warp + 8 * k;
+  for (int k = 0; k < a.rows_per_cta / 8; ++k) {
+    const int t = blockIdx.x * a.rows_per_cta + warp + 8 * k;
     if (t >= len) break;
     const long long row = (long long)b * a.rows_per_batch + t;
 #pragma unroll
