@@ -123,18 +123,26 @@ int oron_mask_rows_f32(float* x, int64_t ldx, int64_t rows, int32_t C, const uin
 int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, void* out, int64_t ld_out,
                      oron_stream_t stream);
 
+/* oron_attention_bf16 for the training forward: one CTA per (batch, head, query tile) and lse[(b*heads + h)*rows_per_batch
+ * + t] = log2(sum_k exp2(s_tk * scale * log2 e)) of every query row, which oron_attention_bwd takes with have_lse = 1. */
+int oron_attention_fwd_lse(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
+                           int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale, float* lse,
+                           oron_stream_t stream);
+
 /*
  * Backward of oron_attention_bf16 (F.scaled_dot_product_attention + key-padding mask, modules.py:271-278) with
  * the RoPE of q and k (modules.py:96-104) inverted on the way out. head_dim 64; tcgen05 MMAs, TMEM accumulators.
  *   qk:  bf16 [rows, ld_qk]: q | k (post-RoPE, as written by the QKV GEMM) at columns 0 | H*64
  *   v:   bf16 [rows, ld_v]; o: bf16 [rows, ld_o] (forward output); d_o: bf16 [rows, ld_do]
  *   dqkv: bf16 [rows, ld_dqkv]: dq | dk | dv w.r.t. the PRE-RoPE projections; rows t >= seq_lens[b] are zeroed
- *   lse, delta: f32 [nbatch*heads*rows_per_batch] workspaces (log2-domain log-sum-exp, rowsum(dO * O))
+ *   lse, delta: f32 [nbatch*heads*rows_per_batch] workspaces (log2-domain log-sum-exp, rowsum(dO * O));
+ *   have_lse = 1: lse holds the values written by oron_attention_fwd_lse (otherwise a pre-pass recomputes them)
  */
 int oron_attention_bwd(const void* qk, int64_t ld_qk, const void* v, int64_t ld_v, const void* o, int64_t ld_o,
                        const void* d_o, int64_t ld_do, void* dqkv, int64_t ld_dqkv, int32_t nbatch,
                        int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                       const float* rope_cos, const float* rope_sin, float* lse, float* delta, oron_stream_t stream);
+                       const float* rope_cos, const float* rope_sin, float* lse, float* delta, int32_t have_lse,
+                       oron_stream_t stream);
 
 #ifdef __cplusplus
 }

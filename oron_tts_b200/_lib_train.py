@@ -15,7 +15,7 @@ TRAIN_SYMBOLS = (
     "oron_transpose_bf16", "oron_ln_bwd", "oron_act_fwd", "oron_act_bwd", "oron_gate_resid", "oron_gate_bwd",
     "oron_dwconv7", "oron_dwconv7_wgrad", "oron_grn_bwd_reduce", "oron_grn_bwd_coef", "oron_grn_bwd_apply",
     "oron_text_embed_bwd", "oron_skinny_dgrad", "oron_skinny_wgrad", "oron_gconv_wgrad", "oron_cfm_loss", "oron_sumsq",
-    "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32",
+    "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32", "oron_attention_fwd_lse",
 )
 
 _P, _I, _L, _F = c_void_p, c_int32, c_int64, c_float
@@ -40,7 +40,8 @@ _ARGTYPES = {
     "oron_adamw_clip": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "oron_f16_to_bf16": [_P, _L, _L, _I, _P, _L, _P],
     "oron_mask_rows_f32": [_P, _L, _L, _I, _P, _P],
-    "oron_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P],
+    "oron_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _P, _P, _I, _P],
+    "oron_attention_fwd_lse": [_P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P],
 }
 _bound = False
 
@@ -201,9 +202,16 @@ def f16_to_bf16(x: torch.Tensor, out: torch.Tensor) -> None:
 
 def attention_bwd(qk: torch.Tensor, v: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor, dqkv: torch.Tensor, *, nbatch: int,
                   rows_per_batch: int, heads: int, seq_lens: torch.Tensor | None, scale: float, rope_cos: torch.Tensor,
-                  rope_sin: torch.Tensor, lse: torch.Tensor, delta: torch.Tensor) -> None:
+                  rope_sin: torch.Tensor, lse: torch.Tensor, delta: torch.Tensor, have_lse: bool = False) -> None:
     _check(tlib().oron_attention_bwd(_ptr(qk, BF16, "qk"), _ld(qk), _ptr(v, BF16, "v"), _ld(v), _ptr(o, BF16, "o"), _ld(o),
                                      _ptr(d_o, BF16, "d_o"), _ld(d_o), _ptr(dqkv, BF16, "dqkv"), _ld(dqkv), nbatch,
                                      rows_per_batch, heads, _ptr(seq_lens, torch.int32, "seq_lens"), float(scale),
                                      _ptr(rope_cos, F32, "rope_cos"), _ptr(rope_sin, F32, "rope_sin"), _ptr(lse, F32, "lse"),
-                                     _ptr(delta, F32, "delta"), _stream()), "oron_attention_bwd")
+                                     _ptr(delta, F32, "delta"), int(bool(have_lse)), _stream()), "oron_attention_bwd")
+
+
+def attention_fwd_lse(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, *, nbatch: int, rows_per_batch: int, heads: int,
+                      seq_lens: torch.Tensor | None, scale: float) -> None:
+    _check(tlib().oron_attention_fwd_lse(_ptr(qkv, BF16, "qkv"), _ld(qkv), _ptr(out, BF16, "out"), _ld(out), nbatch,
+                                         rows_per_batch, heads, _ptr(seq_lens, torch.int32, "seq_lens"), float(scale),
+                                         _ptr(lse, F32, "lse"), _stream()), "oron_attention_fwd_lse")

@@ -299,9 +299,9 @@ extern "C" int oron_attention_plan(const int32_t* seq_lens, int32_t nbatch, int3
   return check_launch("attn_plan");
 }
 
-extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
-                                   int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                                   void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
+static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch, int32_t rows_per_batch,
+                          int32_t heads, const int32_t* seq_lens, float scale, void* workspace, int64_t workspace_bytes,
+                          float* lse, oron_stream_t stream) {
   if (!qkv || !out || nbatch <= 0 || rows_per_batch <= 0 || heads <= 0)
     return fail(ORON_ERR_BAD_ARG, "attention: bad argument");
   if (ldo % 8 != 0) return fail(ORON_ERR_BAD_ARG, "attention: ldo must be a multiple of 8");
@@ -331,6 +331,7 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   a.ldo = ldo;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.dbg = g_attn_dbg;
+  a.lse = lse;
   a.q_tiles = (rows_per_batch + ATT_TILE - 1) / ATT_TILE;
   const long long items = (long long)a.q_tiles * heads * nbatch;
   // the balanced schedule only pays when there are more items than resident CTA slots
@@ -350,6 +351,20 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
   cudaError_t le = launch_pdl(attn_fwd_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, st, tq, a);
   if (le != cudaSuccess) return fail(int(le), "attention launch: %s", cudaGetErrorString(le));
   return check_launch("attn_fwd_tcgen05");
+}
+
+extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
+                                   int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
+                                   void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
+  return attention_impl(qkv, ld_qkv, out, ldo, nbatch, rows_per_batch, heads, seq_lens, scale, workspace, workspace_bytes, nullptr,
+                        stream);
+}
+// Training forward (include/oron_b200_train.h): one CTA per item, and the log-sum-exp of every row is kept.
+extern "C" int oron_attention_fwd_lse(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
+                                      int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale, float* lse,
+                                      oron_stream_t stream) {
+  if (!lse) return fail(ORON_ERR_BAD_ARG, "attention_fwd_lse: lse is NULL");
+  return attention_impl(qkv, ld_qkv, out, ldo, nbatch, rows_per_batch, heads, seq_lens, scale, nullptr, 0, lse, stream);
 }
 
 // ---------------------------------------------------------------------------

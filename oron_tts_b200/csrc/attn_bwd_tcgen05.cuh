@@ -1,5 +1,7 @@
-// Backward of the varlen non-causal attention (head_dim 64) on tcgen05 / TMEM, first version: correct and
-// un-pipelined (one CTA per (batch, head, 128-row owner tile); MMA and CUDA-core phases alternate).
+// Backward of the varlen non-causal attention (head_dim 64) on tcgen05 / TMEM: one CTA per (batch, head, 128-row owner
+// tile); the operand tiles of the next iteration arrive by TMA while the current one computes, the accumulating MMAs
+// of an iteration stay in flight behind the S / dP MMAs of the next; the S / dP -> CUDA cores -> dS hand-off itself is
+// not yet overlapped across iterations (TMEM holds one S and one dP).
 //
 //   MODE 0 (dQ):    owner = 128 queries. Pre-pass over the key tiles: S = Q K^T -> log2-domain log-sum-exp per row
 //                   (written to `lse` together with delta = rowsum(dO * O)). Main pass per key tile j:
@@ -30,6 +32,7 @@ struct AttnBwdArgs {
   const float* rope_sin;
   float* lse;    // [nbatch * heads * rows_per_batch]
   float* delta;
+  int have_lse;  // 1: `lse` was written by the forward kernel (oron_attention_fwd_lse): MODE 0 skips its pre-pass
 };
 
 constexpr int AB_THREADS = 160;  // warp 0: TMA + MMA issue (+ TMEM alloc); warps 1..4: one thread per owner row
@@ -37,8 +40,9 @@ constexpr int AB_TILE = 128;
 constexpr int AB_D = 64;
 constexpr int AB_TILE_BYTES = AB_TILE * AB_D * 2;  // 16 KB
 constexpr int AB_TMEM_COLS = 512;
-// smem: X1 | X2 | Y1 | Y2 | stageA (2 slabs) | stageB (2 slabs) | barriers + lse/delta staging
-constexpr int AB_SMEM_BYTES = 8 * AB_TILE_BYTES + 64 + 4 * 128 * 4 + 1024;
+// smem: X1 | X2 | Y1[0] Y2[0] | Y1[1] Y2[1] | stageA (2 slabs) | stageB (2 slabs) | barriers + lse/delta staging
+// (the Y tiles of iteration it + 1 are fetched by TMA while iteration it computes)
+constexpr int AB_SMEM_BYTES = 10 * AB_TILE_BYTES + 64 + 4 * 128 * 4 + 1024;
 
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
@@ -95,19 +99,22 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   }
 
   const uint32_t sX1 = smem_base, sX2 = smem_base + AB_TILE_BYTES;
-  const uint32_t sY1 = smem_base + 2 * AB_TILE_BYTES, sY2 = smem_base + 3 * AB_TILE_BYTES;
-  const uint32_t sA = smem_base + 4 * AB_TILE_BYTES, sB = smem_base + 6 * AB_TILE_BYTES;
-  const uint32_t bar_base = smem_base + 8 * AB_TILE_BYTES;
-  const uint32_t bar_x = bar_base, bar_y = bar_base + 8, bar_s = bar_base + 16, bar_p = bar_base + 24,
-                 bar_acc = bar_base + 32, tmem_slot = bar_base + 40;
-  float* s_stat = reinterpret_cast<float*>(smem_gen + 8 * AB_TILE_BYTES + 64);  // [2][2][128]: buffer, {lse, delta}
+  auto sY1 = [&](int st) { return smem_base + (2 + 2 * st) * AB_TILE_BYTES; };
+  auto sY2 = [&](int st) { return smem_base + (3 + 2 * st) * AB_TILE_BYTES; };
+  const uint32_t sA = smem_base + 6 * AB_TILE_BYTES, sB = smem_base + 8 * AB_TILE_BYTES;
+  const uint32_t bar_base = smem_base + 10 * AB_TILE_BYTES;
+  const uint32_t bar_x = bar_base, bar_s = bar_base + 16, bar_p = bar_base + 24, bar_acc = bar_base + 32,
+                 tmem_slot = bar_base + 40;
+  auto bar_y = [&](int st) { return bar_base + 8u + 40u * uint32_t(st); };  // +8 and +48
+  float* s_stat = reinterpret_cast<float*>(smem_gen + 10 * AB_TILE_BYTES + 64);  // [2][2][128]: buffer, {lse, delta}
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_x, 1);
-    mbar_init(bar_y, 1);
+    mbar_init(bar_y(0), 1);
+    mbar_init(bar_y(1), 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_acc, 1);
@@ -124,7 +131,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 320;
 
-  const int n_pre = MODE == 0 ? nt : 0;  // LSE pre-pass iterations
+  const int n_pre = (MODE == 0 && !args.have_lse) ? nt : 0;  // LSE pre-pass iterations
   const int n_it = n_pre + nt;
 
   if (warp == 0) {
@@ -132,8 +139,14 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
       const uint64_t x1desc = make_smem_desc_sw128(sX1, 16, 1024), x2desc = make_smem_desc_sw128(sX2, 16, 1024);
-      const uint64_t y1desc = make_smem_desc_sw128(sY1, 16, 1024), y2desc = make_smem_desc_sw128(sY2, 16, 1024);
-      const uint64_t y1mn = make_smem_desc_sw128(sY1, 1024, 1024), y2mn = make_smem_desc_sw128(sY2, 1024, 1024);
+      uint64_t y1desc[2], y2desc[2], y1mn[2], y2mn[2];
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        y1desc[st] = make_smem_desc_sw128(sY1(st), 16, 1024);
+        y2desc[st] = make_smem_desc_sw128(sY2(st), 16, 1024);
+        y1mn[st] = make_smem_desc_sw128(sY1(st), 1024, 1024);
+        y2mn[st] = make_smem_desc_sw128(sY2(st), 1024, 1024);
+      }
       const uint64_t a0 = make_smem_desc_sw128(sA, 16, 1024), a1 = make_smem_desc_sw128(sA + AB_TILE_BYTES, 16, 1024);
       const uint64_t b0 = make_smem_desc_sw128(sB, 16, 1024), b1 = make_smem_desc_sw128(sB + AB_TILE_BYTES, 16, 1024);
       // owner tiles
@@ -145,28 +158,40 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         tma_load_3d(sX1, &tmQK, bar_x, HD + h * AB_D, tile * AB_TILE, b);  // K
         tma_load_3d(sX2, &tmV, bar_x, h * AB_D, tile * AB_TILE, b);        // V
       }
+      auto fetch = [&](int it) {  // the Y tiles of iteration `it` into buffer it & 1
+        const bool pre = it < n_pre;
+        const int j = pre ? it : it - n_pre;
+        const int st = it & 1;
+        mbar_arrive_expect_tx(bar_y(st), (pre ? 1 : 2) * AB_TILE_BYTES);
+        if (MODE == 0) {
+          tma_load_3d(sY1(st), &tmQK, bar_y(st), HD + h * AB_D, j * AB_TILE, b);  // K_j
+          if (!pre) tma_load_3d(sY2(st), &tmV, bar_y(st), h * AB_D, j * AB_TILE, b);  // V_j
+        } else {
+          tma_load_3d(sY1(st), &tmQK, bar_y(st), h * AB_D, j * AB_TILE, b);   // Q_i
+          tma_load_3d(sY2(st), &tmDO, bar_y(st), h * AB_D, j * AB_TILE, b);   // dO_i
+        }
+      };
+      fetch(0);
       mbar_wait(bar_x, 0, 1);
       int n_acc = 0;
       for (int it = 0; it < n_it; ++it) {
         const bool pre = it < n_pre;
         const int j = pre ? it : it - n_pre;
-        mbar_arrive_expect_tx(bar_y, (pre ? 1 : 2) * AB_TILE_BYTES);
-        if (MODE == 0) {
-          tma_load_3d(sY1, &tmQK, bar_y, HD + h * AB_D, j * AB_TILE, b);  // K_j
-          if (!pre) tma_load_3d(sY2, &tmV, bar_y, h * AB_D, j * AB_TILE, b);  // V_j
-        } else {
-          tma_load_3d(sY1, &tmQK, bar_y, h * AB_D, j * AB_TILE, b);   // Q_i
-          tma_load_3d(sY2, &tmDO, bar_y, h * AB_D, j * AB_TILE, b);   // dO_i
-        }
-        mbar_wait(bar_y, it & 1u, 2);
+        const int st = it & 1;
+        mbar_wait(bar_y(st), (it >> 1) & 1u, 2);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, x1desc + uint64_t(2 * k), y1desc + uint64_t(2 * k), idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, x1desc + uint64_t(2 * k), y1desc[st] + uint64_t(2 * k), idesc_s, k != 0);
         if (!pre) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_dP, x2desc + uint64_t(2 * k), y2desc + uint64_t(2 * k), idesc_s, k != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_dP, x2desc + uint64_t(2 * k), y2desc[st] + uint64_t(2 * k), idesc_s, k != 0);
         }
         umma_commit(bar_s);
+        // the accumulating MMAs of the previous iteration were left in flight behind this iteration's S / dP; they
+        // must have retired before their Y buffer is refilled (the staging tiles are protected by bar_s, whose commit
+        // covers every earlier MMA of this thread)
+        if (it > n_pre) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
+        if (it + 1 < n_it) fetch(it + 1);  // buffer (it + 1) & 1 was last read by the MMAs of iteration it - 1
         mbar_wait(bar_p, it & 1u, 3);  // S (and dP) consumed; staging written
         if (!pre) {
           tc_fence_after();
@@ -174,20 +199,19 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           if (MODE == 0) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)  // dQ += dS K_j
-              umma_bf16_ss(tmem_acc2, (kk < 4 ? a0 : a1) + uint64_t(2 * (kk & 3)), y1mn + uint64_t(128 * kk), idesc_acc,
+              umma_bf16_ss(tmem_acc2, (kk < 4 ? a0 : a1) + uint64_t(2 * (kk & 3)), y1mn[st] + uint64_t(128 * kk), idesc_acc,
                            kk != 0 ? 1u : accf);
           } else {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
-              umma_bf16_ss(tmem_acc1, (kk < 4 ? a0 : a1) + uint64_t(2 * (kk & 3)), y2mn + uint64_t(128 * kk), idesc_acc,
+              umma_bf16_ss(tmem_acc1, (kk < 4 ? a0 : a1) + uint64_t(2 * (kk & 3)), y2mn[st] + uint64_t(128 * kk), idesc_acc,
                            kk != 0 ? 1u : accf);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
-              umma_bf16_ss(tmem_acc2, (kk < 4 ? b0 : b1) + uint64_t(2 * (kk & 3)), y1mn + uint64_t(128 * kk), idesc_acc,
+              umma_bf16_ss(tmem_acc2, (kk < 4 ? b0 : b1) + uint64_t(2 * (kk & 3)), y1mn[st] + uint64_t(128 * kk), idesc_acc,
                            kk != 0 ? 1u : accf);
           }
           umma_commit(bar_acc);
-          mbar_wait(bar_acc, n_acc & 1u, 4);  // operands (Y tiles, staging) free again
           ++n_acc;
         }
       }
@@ -247,9 +271,13 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         tc_fence_before();
         mbar_arrive(bar_p);
       }
-      lse2 = m + log2f(l);
+      if (args.have_lse) {
+        lse2 = t_own < args.rows_per_batch ? args.lse[stat_base + t_own] : 0.f;
+      } else {
+        lse2 = m + log2f(l);
+      }
       if (t_own < args.rows_per_batch) {
-        args.lse[stat_base + t_own] = lse2;
+        if (!args.have_lse) args.lse[stat_base + t_own] = lse2;
         args.delta[stat_base + t_own] = delta;
       }
     }

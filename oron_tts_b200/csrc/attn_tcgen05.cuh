@@ -81,6 +81,8 @@ struct AttnArgs {
   int* ws_cnt;          // [grid] arrival counters of the split items
   __half* ws_o;         // [2 * grid][128][64] f16: O_p / l_p of a partial segment
   float* ws_ml;         // [2 * grid][128][2] f32: (running max * c, l_p)
+  float* lse;           // optional [nbatch * heads * rows_per_batch] f32: log2-domain log-sum-exp of every query row
+                        // (whole items only: the training forward, which saves it for the backward kernels)
 };
 
 constexpr int ATT_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 softmax
@@ -498,6 +500,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArg
       const int slot = w.cur.slot;
       const int t = w.cur.qt * ATT_TILE + r;
       const bool store = slot >= 0 || t < args.rows_per_batch;
+      if (args.lse != nullptr && slot < 0 && t < args.rows_per_batch)  // sum_k 2^(s_k c) = l_run 2^(mc - 7)
+        args.lse[((long long)w.cur.b * args.heads + w.cur.h) * args.rows_per_batch + t] = log2f(l_run) + mc - ATT_P_EXP_BIAS;
       // destination row: 64 values, 16 bits each, for both kinds
       uint4* dst = slot >= 0
           ? reinterpret_cast<uint4*>(args.ws_o + ((long long)slot * ATT_TILE + r) * ATT_D)

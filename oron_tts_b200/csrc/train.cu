@@ -290,7 +290,7 @@ extern "C" int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int
 extern "C" int oron_attention_bwd(const void* qk, int64_t ld_qk, const void* v, int64_t ld_v, const void* o, int64_t ld_o,
                                   const void* d_o, int64_t ld_do, void* dqkv, int64_t ld_dqkv, int32_t nbatch,
                                   int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale,
-                                  const float* rope_cos, const float* rope_sin, float* lse, float* delta,
+                                  const float* rope_cos, const float* rope_sin, float* lse, float* delta, int32_t have_lse,
                                   oron_stream_t stream) {
   if (!qk || !v || !o || !d_o || !dqkv || !rope_cos || !rope_sin || !lse || !delta || nbatch <= 0 || rows_per_batch <= 0 ||
       heads <= 0)
@@ -334,6 +334,7 @@ extern "C" int oron_attention_bwd(const void* qk, int64_t ld_qk, const void* v, 
   a.rope_sin = rope_sin;
   a.lse = lse;
   a.delta = delta;
+  a.have_lse = have_lse ? 1 : 0;
   const unsigned grid = unsigned(a.tiles) * unsigned(heads) * unsigned(nbatch);
   cudaStream_t st = ST(stream);
   attn_bwd_tcgen05_kernel<0><<<grid, AB_THREADS, AB_SMEM_BYTES, st>>>(tqk, tv, tdo, a);

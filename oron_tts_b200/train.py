@@ -283,7 +283,8 @@ class TrainWorkspace:
         self.g_h, self.g_qkv = z(R, H, dt=BF16), z(R, 3 * D, dt=BF16)
         self.vb = z(R, D, dt=BF16)
         self.tA, self.tB = z(wide, R, dt=BF16), z(wide, R, dt=BF16)
-        self.lse, self.delta = z(nb * w.heads * tpad), z(nb * w.heads * tpad)
+        self.lse = [z(nb * w.heads * tpad) for _ in range(nd)]
+        self.delta = z(nb * w.heads * tpad)
         self.dtab = z(nb, w.ada_n)
         self.dts, self.dth, self.dpre2, self.dpre0 = z(nb, D), z(nb, D), z(nb, D), z(nb, D)
         self.dxt, self.dconv = z(R, C), z(R, C)
@@ -478,8 +479,8 @@ class TrainEngine:
             L.ln_modulate(ws.xres, scale=tab[o + D:], shift=tab[o:], out_bf16=ws.nrm1[i], **mod)
             L.gemm(ws.nrm1[i], blk["wqkv"], ws.qkv[i], epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
                    rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
-            L.attention(ws.qkv[i], ws.ao[i], nbatch=nb, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
-                        scale=1.0 / math.sqrt(w.dim_head))
+            T.attention_fwd_lse(ws.qkv[i], ws.ao[i], ws.lse[i], nbatch=nb, rows_per_batch=tpad, heads=w.heads,
+                                seq_lens=ws.seq_lens, scale=1.0 / math.sqrt(w.dim_head))
             L.gemm(ws.ao[i], blk["wo"], ws.y1[i], epilogue=L.EPI_BF16, bias=blk["bo"], block_n=bn_big, two_sm=True, **common)
             T.gate_resid(ws.xres, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True, **common)
             ws.xmid[i].copy_(ws.xres)
@@ -533,7 +534,7 @@ class TrainEngine:
             T.f16_to_bf16(ws.qkv[i][:, 2 * D:], ws.vb)
             T.attention_bwd(ws.qkv[i][:, : 2 * D], ws.vb, ws.ao[i], ws.g_ao, ws.g_qkv, nbatch=nb, rows_per_batch=tpad,
                             heads=w.heads, seq_lens=sl, scale=1.0 / math.sqrt(w.dim_head), rope_cos=cos, rope_sin=sin,
-                            lse=ws.lse, delta=ws.delta)
+                            lse=ws.lse[i], delta=ws.delta, have_lse=True)
             self._linear_bwd(ws, ws.g_qkv, ws.nrm1[i], blk["wqkvT"], a.view(G, p + "attn.to_q.weight", (3 * D, D), 3 * D * D),
                              a.view(G, p + "attn.to_q.bias", (3 * D,), 3 * D), ws.g_d, acc=acc)
             T.ln_bwd(ws.xin[i], ws.g_d, scale=tab[o + D:], accumulate=True, dscale=dtab[o + D:], dshift=dtab[o:], **lnb)

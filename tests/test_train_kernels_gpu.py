@@ -331,3 +331,16 @@ def test_attention_bwd_vs_torch(nb, rpb, H, lens):
     for name, lo in (("dq", 0), ("dk", HD), ("dv", 2 * HD)):
         assert _rel(dqkv[:, lo:lo + HD], ref[:, lo:lo + HD]) < 2e-2, name
     assert float(dqkv[~m].float().abs().max()) == 0.0 if (~m).any() else True
+    # log-sum-exp from the forward kernel (the training path): same gradients without the backward's pre-pass
+    qkv16 = torch.cat([qk, vb.float().to(torch.float16).view(torch.bfloat16)], dim=1).contiguous()
+    out = torch.zeros(R, HD, device=DEV, dtype=BF16)
+    lse_f = torch.zeros(nb * H * rpb, device=DEV)
+    T.attention_fwd_lse(qkv16, out, lse_f, nbatch=nb, rows_per_batch=rpb, heads=H, seq_lens=sl, scale=0.125)
+    assert _rel(out[m], o.detach()[m]) < 2e-2
+    valid = m.view(nb, 1, rpb).expand(nb, H, rpb).reshape(-1)
+    assert float((lse_f - lse)[valid].abs().max()) < 2e-2
+    dqkv2 = torch.full((R, 3 * HD), 9.0, device=DEV, dtype=BF16)
+    T.attention_bwd(qk, vb, out, d_o, dqkv2, nbatch=nb, rows_per_batch=rpb, heads=H, seq_lens=sl, scale=0.125, rope_cos=cos,
+                    rope_sin=sin, lse=lse_f, delta=delta, have_lse=True)
+    for name, lo in (("dq", 0), ("dk", HD), ("dv", 2 * HD)):
+        assert _rel(dqkv2[:, lo:lo + HD], ref[:, lo:lo + HD]) < 2e-2, name
