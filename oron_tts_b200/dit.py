@@ -175,7 +175,8 @@ class DiT(nn.Module):
         CFM.sample fast path hoists them out of the ODE loop instead).
         """
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("training (autograd) through the sm_100a kernels is not implemented yet")
+            raise NotImplementedError("DiT.forward alone builds no autograd graph: train through CFM.forward / F5TTS.forward "
+                                      "(an autograd node over the sm_100a training engine) or oron_tts_b200.train.TrainEngine")
         eng = self.engine()
         w = eng.w
         B, T, _ = x.shape

@@ -36,12 +36,20 @@ class CFM(nn.Module):
 
     # ---- training objective (flow.py:69-159) -----------------------------------------------------
     def forward(self, inp: torch.Tensor, text_ids: torch.Tensor, *, lens: torch.Tensor | None = None) -> torch.Tensor:
-        """OT-CFM loss. Only the deterministic eval-mode objective (flow.py:113-128, 136-138) is available:
-        autograd through the sm_100a kernels (the training step) is not built yet."""
+        """OT-CFM loss (flow.py:69-159). In training mode with autograd enabled the loss is an autograd node backed by
+        the sm_100a training engine (oron_tts_b200/train.py): ``loss.backward()`` delivers the parameter gradients
+        exactly as the reference's autograd graph would. Eval mode: the deterministic validation objective."""
+        if self.training and torch.is_grad_enabled():
+            from .train import OTCFMLoss, TrainEngine
+
+            eng = self.__dict__.get("_train_engine")
+            if eng is None:
+                eng = TrainEngine(self)
+                self.__dict__["_train_engine"] = eng
+            params = [eng.arena.named[k] for k in eng.arena.order]
+            return OTCFMLoss.apply(eng, inp, text_ids, lens, *params)
         if self.training:
-            raise NotImplementedError(
-                "oron_tts_b200 implements the inference hot path; the OT-CFM training step (backward kernels, "
-                "NCCL gradient all-reduce) is scheduled after it. Call .eval() for the deterministic validation loss.")
+            raise RuntimeError("CFM.forward in training mode needs autograd enabled (or call .eval() for the validation loss)")
         if inp.ndim == 3 and inp.shape[1] == self.n_mels:
             inp = inp.transpose(1, 2)
         B, T, dev = inp.shape[0], inp.shape[1], inp.device

@@ -39,7 +39,9 @@ I32 = torch.int32
 class ParamArena:
     ALIGN = 64  # elements; every fused view stays 128-byte aligned for TMA in both f32 and bf16
 
-    def __init__(self, module: torch.nn.Module, prefix: str = "cfm.backbone."):
+    def __init__(self, module: torch.nn.Module, prefix: str | None = None):
+        if prefix is None:  # F5TTS (cfm.backbone.*) or CFM (backbone.*)
+            prefix = "cfm.backbone." if hasattr(module, "cfm") else "backbone."
         named = dict(module.named_parameters())
         keys = [k for k in named if k.startswith(prefix)]
         if len(keys) != len(named):
@@ -302,9 +304,10 @@ class TrainEngine:
         if not p0.is_cuda:
             raise RuntimeError("TrainEngine runs only on a CUDA device (oron_tts_b200 has no CPU fallback)")
         self.model = model
-        self.cfm = model.cfm
+        self.cfm = model.cfm if hasattr(model, "cfm") else model
         self.arena = ParamArena(model)
-        self.w = TrainWeights(self.arena, model.cfm.backbone.rotary_embed.inv_freq)
+        self.w = TrainWeights(self.arena, self.cfm.backbone.rotary_embed.inv_freq)
+        self._seen_version = self.arena.p._version
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         self._ws: dict = {}
@@ -621,6 +624,24 @@ class TrainEngine:
                      lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, wd=self.wd,
                      step=self.step_count, skipped=self.skipped)
         self.w.refresh()
+        self._seen_version = self.arena.p._version
+
+    @torch.no_grad()
+    def sync_params(self) -> None:
+        """Master weights changed outside ``optimizer_step`` (a torch optimizer stepping the parameter views,
+        ``load_state_dict``): refresh the bf16 operands and the re-laid-out copies."""
+        if self.arena.p._version != self._seen_version:
+            self.arena.pb.copy_(self.arena.p)
+            self.w.refresh()
+            self._seen_version = self.arena.p._version
+
+    def detach_grads(self) -> None:
+        """Autograd-bridge mode: ``param.grad`` must not alias the gradient arena (autograd accumulates into it)."""
+        lo = self.arena.g.data_ptr()
+        hi = lo + self.arena.g.numel() * 4
+        for prm in self.arena.named.values():
+            if prm.grad is not None and lo <= prm.grad.data_ptr() < hi:
+                prm.grad = None
 
     def grad_norm(self) -> torch.Tensor:
         """Global L2 norm of the current gradients (trainer.py:171-177), device scalar."""
@@ -633,3 +654,29 @@ class TrainEngine:
         loss = self.loss_and_grad(mel, text_ids, lens, draws=draws, training=training)
         self.optimizer_step(lr)
         return loss
+
+
+class OTCFMLoss(torch.autograd.Function):
+    """``loss = CFM.forward(...)`` as an autograd node, for hosts that drive training the reference's way
+    (``loss.backward(); optimizer.step()``, trainer.py:236-262, DDP / torch.optim included): forward runs the whole
+    forward + backward on the kernels, backward hands the parameter gradients (times the incoming scalar) to autograd.
+    ``TrainEngine.train_step`` is the fast path (no per-tensor gradient copies, fused optimizer)."""
+
+    @staticmethod
+    def forward(ctx, eng: TrainEngine, mel, text_ids, lens, *params):
+        eng.sync_params()
+        eng.detach_grads()
+        loss = eng.loss_and_grad(mel, text_ids, lens, training=True)
+        ctx.eng = eng
+        ctx.keys = [k for k in eng.arena.order]
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        a = ctx.eng.arena
+        grads = []
+        for k in a.order:
+            prm = a.named[k]
+            o, n = a.offsets[k], prm.numel()
+            grads.append(a.g[o:o + n].view(prm.shape) * gout)
+        return (None, None, None, None, *grads)

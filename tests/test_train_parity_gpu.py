@@ -130,3 +130,47 @@ def test_gradients_vs_oracle_random_draws_and_text_drop():
     g1 = eng.arena.g.clone()
     eng.loss_and_grad(x1.transpose(1, 2).to(DEV), text.to(DEV), lens.to(DEV), draws=_to_dev(draws), accumulate=True)
     assert _rel(eng.arena.g, 2 * g1) < 1e-3
+
+
+def test_reference_style_training_loop_through_autograd_bridge():
+    """The reference's loop (trainer.py:236-262): model.train(); loss = model(mel, text, lens); loss.backward();
+    clip_grad_norm_; torch.optim.AdamW.step() -- with the loss an autograd node over the sm_100a engine."""
+    import random
+
+    g = _gold("train_tiny.pt")
+    m = F5TTS.from_config(GW.CONFIGS["tiny"])
+    m.load_state_dict(_state_dict("tiny"), strict=True)
+    m = m.to(DEV).train()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01)
+    mel, text, lens = g["mel"].to(DEV), g["text"].to(DEV), g["lens"].to(DEV)
+    random.seed(0)
+    torch.manual_seed(0)
+    loss = m(mel, text, lens)
+    assert loss.requires_grad and torch.isfinite(loss)
+    (0.5 * loss).backward()
+    eng = m.cfm.__dict__["_train_engine"]
+    a = eng.arena
+    for k, prm in m.named_parameters():
+        key = k[len("cfm."):]
+        o, n = a.offsets[key], prm.numel()
+        assert prm.grad is not None and prm.grad.data_ptr() != a.g[o:o + n].data_ptr()
+        assert torch.allclose(prm.grad.reshape(-1), 0.5 * a.g[o:o + n], rtol=1e-6, atol=0), k
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    losses = [float(loss.detach())]
+    for _ in range(6):  # fixed draws: the loss must go down under the reference optimizer
+        random.seed(0)
+        torch.manual_seed(0)
+        loss = m(mel, text, lens)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss.detach()))
+    eng.sync_params()
+    assert torch.equal(a.pb, a.p.to(torch.bfloat16))  # bf16 operands follow a torch optimizer stepping the views
+    assert losses[-1] < losses[0], losses
+    m.eval()
+    with torch.no_grad():
+        assert torch.isfinite(m(mel, text, lens))
