@@ -307,7 +307,7 @@ class TrainEngine:
         self.cfm = model.cfm if hasattr(model, "cfm") else model
         self.arena = ParamArena(model)
         self.w = TrainWeights(self.arena, self.cfm.backbone.rotary_embed.inv_freq)
-        self._seen_version = self.arena.p._version
+        self._seen_version = self._versions()
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         self._ws: dict = {}
@@ -624,16 +624,22 @@ class TrainEngine:
                      lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, wd=self.wd,
                      step=self.step_count, skipped=self.skipped)
         self.w.refresh()
-        self._seen_version = self.arena.p._version
+        self._seen_version = self._versions()
 
     @torch.no_grad()
     def sync_params(self) -> None:
         """Master weights changed outside ``optimizer_step`` (a torch optimizer stepping the parameter views,
         ``load_state_dict``): refresh the bf16 operands and the re-laid-out copies."""
-        if self.arena.p._version != self._seen_version:
+        v = self._versions()
+        if v != self._seen_version:
             self.arena.pb.copy_(self.arena.p)
             self.w.refresh()
-            self._seen_version = self.arena.p._version
+            self._seen_version = v
+
+    def _versions(self) -> int:
+        # ``param.data = view`` gives every parameter its own version counter: in-place updates by a torch optimizer
+        # bump these, not the arena's
+        return sum(prm._version for prm in self.arena.named.values())
 
     def detach_grads(self) -> None:
         """Autograd-bridge mode: ``param.grad`` must not alias the gradient arena (autograd accumulates into it)."""
