@@ -32,10 +32,12 @@ struct AttnBwdArgs {
   const float* rope_sin;
   float* lse;    // [nbatch * heads * rows_per_batch]
   float* delta;
+  long long* dbg;  // optional [grid, 8] clock64 stamps of the first compute thread (tools/attn_bwd_trace.py)
   int have_lse;  // 1: `lse` was written by the forward kernel (oron_attention_fwd_lse): MODE 0 skips its pre-pass
 };
 
-constexpr int AB_THREADS = 160;  // warp 0: TMA + MMA issue (+ TMEM alloc); warps 1..4: one thread per owner row
+constexpr int AB_THREADS = 288;  // warp 0: TMA + MMA issue (+ TMEM alloc); warps 1..8: two threads per owner row
+                                 // (warp & 3 = TMEM lane quarter, (warp - 1) >> 2 = which 64 of the tile's 128 columns)
 constexpr int AB_TILE = 128;
 constexpr int AB_D = 64;
 constexpr int AB_TILE_BYTES = AB_TILE * AB_D * 2;  // 16 KB
@@ -116,7 +118,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     mbar_init(bar_y(0), 1);
     mbar_init(bar_y(1), 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -218,41 +220,57 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     }
     __syncwarp();
   } else {
-    // ===================== one thread per owner row =====================
+    // ===================== two threads per owner row =====================
     const int q4 = warp & 3;
+    const int half = (warp - 1) >> 2;  // columns [64 * half, 64 * half + 64) of every S / dP tile
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = uint32_t(q4 * 32) << 16;
     const int t_own = tile * AB_TILE + r;
     const bool own_valid = t_own < len;
     const float c = args.scale_log2;
     const long long stat_base = ((long long)b * args.heads + h) * args.rows_per_batch;
+    const bool tr = args.dbg != nullptr && threadIdx.x == 32;
+#define AB_STAMP(slot) do { if (tr) args.dbg[(long long)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+    AB_STAMP(0);
     float lse2 = 0.f, delta = 0.f;
     if (MODE == 0) {
-      if (own_valid) {
-        const uint4* po = reinterpret_cast<const uint4*>(args.o + (row_base + t_own) * args.ld_o + h * AB_D);
-        const uint4* pd = reinterpret_cast<const uint4*>(args.d_o + (row_base + t_own) * args.ld_do + h * AB_D);
+      if (args.have_lse) lse2 = t_own < args.rows_per_batch ? __ldg(args.lse + stat_base + t_own) : 0.f;  // in flight under the delta loads
+      // delta[row] = sum_d dO * O, cooperatively: 8 lanes per row read one 16-byte chunk each (coalesced), shuffle-reduce
+      {
+        const int tid = int(threadIdx.x) - 32;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 a = po[i], d = pd[i];
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+        for (int i = 0; i < 4; ++i) {
+          const int q = i * 256 + tid;
+          const int row = q >> 3, k = q & 7;
+          const int t = tile * AB_TILE + row;
+          float part = 0.f;
+          if (t < len) {
+            const uint4 a = *reinterpret_cast<const uint4*>(args.o + (row_base + t) * args.ld_o + h * AB_D + 8 * k);
+            const uint4 d = *reinterpret_cast<const uint4*>(args.d_o + (row_base + t) * args.ld_do + h * AB_D + 8 * k);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 fa = make_float2(__uint_as_float(aw[k] << 16), __uint_as_float(aw[k] & 0xffff0000u));
-            const float2 fd = make_float2(__uint_as_float(dw[k] << 16), __uint_as_float(dw[k] & 0xffff0000u));
-            delta = fmaf(fa.x, fd.x, delta);
-            delta = fmaf(fa.y, fd.y, delta);
+            for (int e = 0; e < 4; ++e) {
+              part = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(dw[e] << 16), part);
+              part = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(dw[e] & 0xffff0000u), part);
+            }
           }
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+          if (k == 0) s_stat[128 + row] = part;
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        delta = s_stat[128 + r];
       }
       // ---- pre-pass: log-sum-exp of the row (log2 domain) ----
       float m = -INFINITY, l = 0.f;
-      for (int it = 0; it < n_pre; ++it) {
+      for (int it = 0; it < n_pre; ++it) {  // (fallback path, have_lse == 0: the first thread of each row does all 128 columns)
         const int nv = min(AB_TILE, len - it * AB_TILE);
         mbar_wait(bar_s, it & 1u, 5);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < AB_TILE; c0 += 32) {
-          if (c0 >= nv) break;
+          if (c0 >= nv || half != 0) break;
           uint32_t v[32];
           ab_tmem_ld32(tmem_S + lane_off + c0, v);
           tmem_wait_ld();
@@ -271,16 +289,18 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         tc_fence_before();
         mbar_arrive(bar_p);
       }
-      if (args.have_lse) {
-        lse2 = t_own < args.rows_per_batch ? args.lse[stat_base + t_own] : 0.f;
-      } else {
-        lse2 = m + log2f(l);
+      if (!args.have_lse) {
+        if (half == 0) s_stat[r] = m + log2f(l);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        lse2 = s_stat[r];
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // s_stat is reused by nobody in MODE 0, kept for symmetry
       }
-      if (t_own < args.rows_per_batch) {
+      if (half == 0 && t_own < args.rows_per_batch) {
         if (!args.have_lse) args.lse[stat_base + t_own] = lse2;
         args.delta[stat_base + t_own] = delta;
       }
     }
+    AB_STAMP(1);
     // ---- main pass ----
     for (int it = n_pre; it < n_it; ++it) {
       const int j = it - n_pre;
@@ -289,14 +309,16 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       if (MODE == 1) {
         const int tq = j * AB_TILE + r;
         float* sw_ = s_stat + (j & 1) * 256;
-        sw_[r] = tq < args.rows_per_batch ? args.lse[stat_base + tq] : 0.f;
-        sw_[128 + r] = tq < args.rows_per_batch ? args.delta[stat_base + tq] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* src = half == 0 ? args.lse : args.delta;
+        sw_[128 * half + r] = tq < args.rows_per_batch ? src[stat_base + tq] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(bar_s, it & 1u, 6);
       tc_fence_after();
+      if (it == n_pre) AB_STAMP(2);
+      if (it == n_pre + 1) AB_STAMP(3);
 #pragma unroll 1
-      for (int c0 = 0; c0 < AB_TILE; c0 += 32) {
+      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
         uint32_t vs[32], vd[32];
         ab_tmem_ld32(tmem_S + lane_off + c0, vs);
         ab_tmem_ld32(tmem_dP + lane_off + c0, vd);
@@ -329,53 +351,86 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       tc_fence_before();
       mbar_arrive(bar_p);
     }
+    AB_STAMP(4);
     // ---- read the accumulators ----
     mbar_wait(bar_acc, (nt - 1) & 1u, 7);
     tc_fence_after();
-    const bool in_range = t_own < args.rows_per_batch;
-    float cs[32], sn[32];
-    if (own_valid) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        cs[i] = args.rope_cos[(long long)t_own * 32 + i];
-        sn[i] = args.rope_sin[(long long)t_own * 32 + i];
-      }
-    }
-    auto emit = [&](uint32_t tm, int col0, bool rope) {
+    AB_STAMP(5);
+    // Phase A: the accumulator rows go to shared memory as f32 (row = 256 B, 16-byte chunks XOR-swizzled by row & 15)
+    // in the idle staging tiles; phase B: all threads store 16-byte bf16 chunks, 8 lanes per row (coalesced), with the
+    // RoPE rotation of dq / dk applied on the way (cos / sin read coalesced too).
+    auto to_smem = [&](uint32_t tm, uint32_t tile_s) {
       uint32_t lo[32], hi[32];
       ab_tmem_ld32(tm + lane_off, lo);
       ab_tmem_ld32(tm + lane_off + 32, hi);
       tmem_wait_ld();
-      uint32_t out[32];
-      if (own_valid) {
+      const uint32_t rowa = tile_s + uint32_t(r) * 256u;
+      const uint32_t sw = uint32_t(r & 15);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0 = __uint_as_float(lo[i]), a1 = __uint_as_float(lo[i + 1]);
-          float b0 = __uint_as_float(hi[i]), b1 = __uint_as_float(hi[i + 1]);
-          if (rope) {  // transpose of q' = q cos + rotate_half(q) sin
-            const float x0 = a0 * cs[i] + b0 * sn[i], y0 = b0 * cs[i] - a0 * sn[i];
-            const float x1 = a1 * cs[i + 1] + b1 * sn[i + 1], y1 = b1 * cs[i + 1] - a1 * sn[i + 1];
-            a0 = x0; b0 = y0; a1 = x1; b1 = y1;
-          }
-          out[i >> 1] = pack_bf16x2(a0, a1);
-          out[16 + (i >> 1)] = pack_bf16x2(b0, b1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) out[i] = 0u;
-      }
-      if (in_range) {
-        uint4* p = reinterpret_cast<uint4*>(args.dqkv + (row_base + t_own) * args.ld_dqkv + col0 + h * AB_D);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) p[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+      for (int cidx = 0; cidx < 8; ++cidx) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((uint32_t(cidx) ^ sw) << 4)), "r"(lo[4 * cidx]),
+                     "r"(lo[4 * cidx + 1]), "r"(lo[4 * cidx + 2]), "r"(lo[4 * cidx + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((uint32_t(cidx + 8) ^ sw) << 4)), "r"(hi[4 * cidx]),
+                     "r"(hi[4 * cidx + 1]), "r"(hi[4 * cidx + 2]), "r"(hi[4 * cidx + 3]) : "memory");
       }
     };
+    auto ld_chunk = [&](uint32_t tile_s, int row, int cidx, float (&f)[4]) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                   : "r"(tile_s + uint32_t(row) * 256u + ((uint32_t(cidx) ^ uint32_t(row & 15)) << 4)) : "memory");
+      f[0] = __uint_as_float(a0); f[1] = __uint_as_float(a1); f[2] = __uint_as_float(a2); f[3] = __uint_as_float(a3);
+    };
+    // q: task index (row = q >> 3, 16-byte output chunk k = q & 7)
+    auto store_task = [&](uint32_t tile_s, int q, int col0, bool rope) {
+      const int row = q >> 3, k = q & 7;
+      const int t = tile * AB_TILE + row;
+      if (t >= args.rows_per_batch) return;
+      uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+      if (t < len) {
+        float v[8];
+        if (!rope) {
+          float x[4], y[4];
+          ld_chunk(tile_s, row, 2 * k, x);
+          ld_chunk(tile_s, row, 2 * k + 1, y);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { v[e] = x[e]; v[4 + e] = y[e]; }
+        } else {  // transpose of q' = q cos + rotate_half(q) sin: columns c (< 32) and c + 32 mix
+          const int kk = k & 3;
+          float a[8], bb[8];
+          { float x[4], y[4]; ld_chunk(tile_s, row, 2 * kk, x); ld_chunk(tile_s, row, 2 * kk + 1, y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { a[e] = x[e]; a[4 + e] = y[e]; } }
+          { float x[4], y[4]; ld_chunk(tile_s, row, 8 + 2 * kk, x); ld_chunk(tile_s, row, 8 + 2 * kk + 1, y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { bb[e] = x[e]; bb[4 + e] = y[e]; } }
+          const float4* pc = reinterpret_cast<const float4*>(args.rope_cos + (long long)t * 32 + 8 * kk);
+          const float4* ps = reinterpret_cast<const float4*>(args.rope_sin + (long long)t * 32 + 8 * kk);
+          const float4 c0 = __ldg(pc), c1 = __ldg(pc + 1), s0 = __ldg(ps), s1 = __ldg(ps + 1);
+          const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = k < 4 ? a[e] * cs[e] + bb[e] * sn[e] : bb[e] * cs[e] - a[e] * sn[e];
+        }
+        outv = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
+      *reinterpret_cast<uint4*>(args.dqkv + (row_base + t) * args.ld_dqkv + col0 + h * AB_D + 8 * k) = outv;
+    };
+    const int tid = int(threadIdx.x) - 32;
     if (MODE == 0) {
-      emit(tmem_acc2, 0, true);
+      if (half == 0) to_smem(tmem_acc2, sA);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) store_task(sA, i * 256 + tid, 0, true);
     } else {
-      emit(tmem_acc1, 2 * HD, false);
-      emit(tmem_acc2, HD, true);
+      if (half == 0) to_smem(tmem_acc1, sA); else to_smem(tmem_acc2, sB);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        if (half == 0) store_task(sA, i * 128 + (tid & 127), 2 * HD, false);
+        else store_task(sB, i * 128 + (tid & 127), HD, true);
+      }
     }
+    AB_STAMP(6);
     tc_fence_before();
   }
   __syncthreads();
