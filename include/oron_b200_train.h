@@ -144,7 +144,7 @@ int oron_attention_bwd(const void* qk, int64_t ld_qk, const void* v, int64_t ld_
                        const float* rope_cos, const float* rope_sin, float* lse, float* delta, int32_t have_lse,
                        oron_stream_t stream);
 
-/* Profiling aid: int64 [2 * grid, 8] device buffer that receives clock64 stamps of the two attention-backward launches
+/* Profiling aid: int64 [2 * grid, 16] device buffer that receives clock64 stamps of the two attention-backward launches
  * (grid = tiles * heads * nbatch; dQ launch first); NULL disables. */
 void oron_debug_set_attention_bwd_stamps(void* buf);
 

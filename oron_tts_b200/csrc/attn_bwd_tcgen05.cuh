@@ -1,7 +1,7 @@
 // Backward of the varlen non-causal attention (head_dim 64) on tcgen05 / TMEM: one CTA per (batch, head, 128-row owner
-// tile); the operand tiles of the next iteration arrive by TMA while the current one computes, the accumulating MMAs
-// of an iteration stay in flight behind the S / dP MMAs of the next; the S / dP -> CUDA cores -> dS hand-off itself is
-// not yet overlapped across iterations (TMEM holds one S and one dP).
+// tile). Every 128-row operand tile (TMA, double buffered) is consumed as two 64-column sub-tiles with their own
+// S / dP accumulators in TMEM (2 x (64 + 64) columns), so the tensor core computes S / dP of sub-tile n + 1 and the
+// accumulating MMAs of sub-tile n - 1 while the CUDA cores turn S / dP of sub-tile n into dS (and P^T).
 //
 //   MODE 0 (dQ):    owner = 128 queries. Pre-pass over the key tiles: S = Q K^T -> log2-domain log-sum-exp per row
 //                   (written to `lse` together with delta = rowsum(dO * O)). Main pass per key tile j:
@@ -32,7 +32,7 @@ struct AttnBwdArgs {
   const float* rope_sin;
   float* lse;    // [nbatch * heads * rows_per_batch]
   float* delta;
-  long long* dbg;  // optional [grid, 8] clock64 stamps of the first compute thread (tools/attn_bwd_trace.py)
+  long long* dbg;  // optional [grid, 16] clock64 stamps: slots 0-7 first compute thread, 8-15 MMA thread (tools/attn_bwd_trace.py)
   int have_lse;  // 1: `lse` was written by the forward kernel (oron_attention_fwd_lse): MODE 0 skips its pre-pass
 };
 
@@ -44,7 +44,7 @@ constexpr int AB_TILE_BYTES = AB_TILE * AB_D * 2;  // 16 KB
 constexpr int AB_TMEM_COLS = 512;
 // smem: X1 | X2 | Y1[0] Y2[0] | Y1[1] Y2[1] | stageA (2 slabs) | stageB (2 slabs) | barriers + lse/delta staging
 // (the Y tiles of iteration it + 1 are fetched by TMA while iteration it computes)
-constexpr int AB_SMEM_BYTES = 10 * AB_TILE_BYTES + 64 + 4 * 128 * 4 + 1024;
+constexpr int AB_SMEM_BYTES = 10 * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 4 * 128 * 4 + 1024;
 
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
@@ -105,20 +105,23 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   auto sY2 = [&](int st) { return smem_base + (3 + 2 * st) * AB_TILE_BYTES; };
   const uint32_t sA = smem_base + 6 * AB_TILE_BYTES, sB = smem_base + 8 * AB_TILE_BYTES;
   const uint32_t bar_base = smem_base + 10 * AB_TILE_BYTES;
-  const uint32_t bar_x = bar_base, bar_s = bar_base + 16, bar_p = bar_base + 24, bar_acc = bar_base + 32,
-                 tmem_slot = bar_base + 40;
-  auto bar_y = [&](int st) { return bar_base + 8u + 40u * uint32_t(st); };  // +8 and +48
-  float* s_stat = reinterpret_cast<float*>(smem_gen + 10 * AB_TILE_BYTES + 64);  // [2][2][128]: buffer, {lse, delta}
+  // barriers (8 bytes each): x | y0 y1 | s0 s1 | p0 p1 | acc ; then the TMEM slot
+  const uint32_t bar_x = bar_base, bar_acc = bar_base + 56, tmem_slot = bar_base + 64;
+  auto bar_y = [&](int st) { return bar_base + 8u + 8u * uint32_t(st); };
+  auto bar_s = [&](int u) { return bar_base + 24u + 8u * uint32_t(u); };   // MMA -> CUDA cores: S_u / dP_u are in TMEM
+  auto bar_p = [&](int u) { return bar_base + 40u + 8u * uint32_t(u); };   // CUDA cores -> MMA: S_u / dP_u read, slab u written
+  float* s_stat = reinterpret_cast<float*>(smem_gen + 10 * AB_TILE_BYTES + 128);  // [2][2][128]: buffer, {lse, delta}
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_x, 1);
-    mbar_init(bar_y(0), 1);
-    mbar_init(bar_y(1), 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 256);
+    for (int u = 0; u < 2; ++u) {
+      mbar_init(bar_y(u), 1);
+      mbar_init(bar_s(u), 1);
+      mbar_init(bar_p(u), 256);
+    }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -131,26 +134,28 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 320;
+  // TMEM columns: [S_0 | dP_0 | S_1 | dP_1] 64 each, then the two 64-column accumulators
+  auto tmem_S = [&](int u) { return tmem_base + 128u * uint32_t(u); };
+  auto tmem_dP = [&](int u) { return tmem_base + 128u * uint32_t(u) + 64u; };
+  const uint32_t tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 320;
 
-  const int n_pre = (MODE == 0 && !args.have_lse) ? nt : 0;  // LSE pre-pass iterations
-  const int n_it = n_pre + nt;
+  // sub-iterations: n = 2 * (tile index) + (which 64 columns); the optional pre-pass (no lse from the forward) walks
+  // the same sub-tiles with S only
+  const int n_pre = (MODE == 0 && !args.have_lse) ? 2 * nt : 0;
+  const int n_sub = n_pre + 2 * nt;
 
   if (warp == 0) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
       const uint64_t x1desc = make_smem_desc_sw128(sX1, 16, 1024), x2desc = make_smem_desc_sw128(sX2, 16, 1024);
-      uint64_t y1desc[2], y2desc[2], y1mn[2], y2mn[2];
-#pragma unroll
-      for (int st = 0; st < 2; ++st) {
-        y1desc[st] = make_smem_desc_sw128(sY1(st), 16, 1024);
-        y2desc[st] = make_smem_desc_sw128(sY2(st), 16, 1024);
-        y1mn[st] = make_smem_desc_sw128(sY1(st), 1024, 1024);
-        y2mn[st] = make_smem_desc_sw128(sY2(st), 1024, 1024);
-      }
-      const uint64_t a0 = make_smem_desc_sw128(sA, 16, 1024), a1 = make_smem_desc_sw128(sA + AB_TILE_BYTES, 16, 1024);
-      const uint64_t b0 = make_smem_desc_sw128(sB, 16, 1024), b1 = make_smem_desc_sw128(sB + AB_TILE_BYTES, 16, 1024);
+      // every descriptor is base + a small multiple: no arrays (dynamic indexing would put them in local memory and each
+      // tcgen05.mma issue behind a load). Buffer st of the Y tiles is 2 tiles further (>> 4: 2048), staging slab u one
+      // tile further (1024).
+      const uint64_t y1d = make_smem_desc_sw128(sY1(0), 16, 1024), y2d = make_smem_desc_sw128(sY2(0), 16, 1024);
+      const uint64_t y1m = make_smem_desc_sw128(sY1(0), 1024, 1024), y2m = make_smem_desc_sw128(sY2(0), 1024, 1024);
+      const uint64_t ad = make_smem_desc_sw128(sA, 16, 1024), bd = make_smem_desc_sw128(sB, 16, 1024);
+      constexpr uint64_t kBuf = uint64_t(2 * AB_TILE_BYTES) >> 4, kSlab = uint64_t(AB_TILE_BYTES) >> 4;
       // owner tiles
       mbar_arrive_expect_tx(bar_x, 2 * AB_TILE_BYTES);
       if (MODE == 0) {
@@ -160,10 +165,11 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         tma_load_3d(sX1, &tmQK, bar_x, HD + h * AB_D, tile * AB_TILE, b);  // K
         tma_load_3d(sX2, &tmV, bar_x, h * AB_D, tile * AB_TILE, b);        // V
       }
-      auto fetch = [&](int it) {  // the Y tiles of iteration `it` into buffer it & 1
-        const bool pre = it < n_pre;
-        const int j = pre ? it : it - n_pre;
-        const int st = it & 1;
+      const int n_tiles = n_sub / 2;  // operand tiles over both passes
+      auto fetch = [&](int ti) {      // the Y tiles of tile-iteration ti into buffer ti & 1
+        const bool pre = 2 * ti < n_pre;
+        const int j = pre ? ti : ti - n_pre / 2;
+        const int st = ti & 1;
         mbar_arrive_expect_tx(bar_y(st), (pre ? 1 : 2) * AB_TILE_BYTES);
         if (MODE == 0) {
           tma_load_3d(sY1(st), &tmQK, bar_y(st), HD + h * AB_D, j * AB_TILE, b);  // K_j
@@ -173,56 +179,77 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           tma_load_3d(sY2(st), &tmDO, bar_y(st), h * AB_D, j * AB_TILE, b);   // dO_i
         }
       };
+      // S_u / dP_u of sub-iteration n (u = n & 1): the 64 rows [64 u, 64 u + 64) of the Y tiles as the N dimension
+      auto issue_sdp = [&](int n) {
+        const int ti = n >> 1, u = n & 1, st = ti & 1;
+        if (u == 0) {
+          mbar_wait(bar_y(st), (ti >> 1) & 1u, 2);
+          tc_fence_after();
+        }
+        const uint64_t roff = uint64_t(u) * (64u * 128u >> 4);  // 64 rows of 128 bytes
+        // accumulating MMAs into one TMEM tile form a dependent chain (~130 cycles per link against ~65 for independent
+        // instructions): the S and dP chains are interleaved
+        const bool with_dp = n >= n_pre;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16_ss(tmem_S(u), x1desc + uint64_t(2 * k), (y1d + kBuf * uint64_t(st)) + roff + uint64_t(2 * k), idesc_s, k != 0);
+          if (with_dp) umma_bf16_ss(tmem_dP(u), x2desc + uint64_t(2 * k), (y2d + kBuf * uint64_t(st)) + roff + uint64_t(2 * k), idesc_s, k != 0);
+        }
+        umma_commit(bar_s(u));
+      };
       fetch(0);
       mbar_wait(bar_x, 0, 1);
-      int n_acc = 0;
-      for (int it = 0; it < n_it; ++it) {
-        const bool pre = it < n_pre;
-        const int j = pre ? it : it - n_pre;
-        const int st = it & 1;
-        mbar_wait(bar_y(st), (it >> 1) & 1u, 2);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_S, x1desc + uint64_t(2 * k), y1desc[st] + uint64_t(2 * k), idesc_s, k != 0);
-        if (!pre) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_dP, x2desc + uint64_t(2 * k), y2desc[st] + uint64_t(2 * k), idesc_s, k != 0);
+      issue_sdp(0);
+      int n_acc = 0;  // bar_acc phases committed so far (one per main tile)
+#define AB_CSTAMP(slot) do { if (args.dbg != nullptr && n == n_pre + 6) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+      for (int n = 0; n < n_sub; ++n) {
+        const int ti = n >> 1, u = n & 1, st = ti & 1;
+        const bool pre = n < n_pre;
+        AB_CSTAMP(8);
+        // TMEM buffer (n + 1) & 1 was released by the bar_p wait of sub-iteration n - 1 (below, previous turn)
+        AB_CSTAMP(9);
+        if (n + 1 < n_sub) issue_sdp(n + 1);
+        AB_CSTAMP(10);
+        if (u == 0 && ti + 1 < n_tiles) {
+          // buffer (ti + 1) & 1 was last read by the MMAs of tile ti - 1: S / dP (retired: their bar_p waits are behind
+          // us) and, in the main pass, the accumulating MMAs committed to bar_acc
+          if (n_acc > 0) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
+          fetch(ti + 1);
         }
-        umma_commit(bar_s);
-        // the accumulating MMAs of the previous iteration were left in flight behind this iteration's S / dP; they
-        // must have retired before their Y buffer is refilled (the staging tiles are protected by bar_s, whose commit
-        // covers every earlier MMA of this thread)
-        if (it > n_pre) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
-        if (it + 1 < n_it) fetch(it + 1);  // buffer (it + 1) & 1 was last read by the MMAs of iteration it - 1
-        mbar_wait(bar_p, it & 1u, 3);  // S (and dP) consumed; staging written
+        mbar_wait(bar_p(u), (n >> 1) & 1u, 3);  // S_u / dP_u consumed; staging slab u written
+        AB_CSTAMP(11);
         if (!pre) {
           tc_fence_after();
-          const uint32_t accf = j == 0 ? 0u : 1u;
+          const int j = ti - n_pre / 2;
+          const uint32_t accf = (j == 0 && u == 0) ? 0u : 1u;
           if (MODE == 0) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)  // dQ += dS K_j
-              umma_bf16_ss(tmem_acc2, (kk < 4 ? a0 : a1) + uint64_t(2 * (kk & 3)), y1mn[st] + uint64_t(128 * kk), idesc_acc,
-                           kk != 0 ? 1u : accf);
+            for (int k = 0; k < 4; ++k)  // dQ += dS[:, 64 u ..] K_j[64 u .., :]; even / odd k-steps into two accumulators
+                                         // (two interleaved dependent chains instead of one), summed in the epilogue
+              umma_bf16_ss((k & 1) ? tmem_acc1 : tmem_acc2, (ad + kSlab * uint64_t(u)) + uint64_t(2 * k),
+                           (y1m + kBuf * uint64_t(st)) + uint64_t(128 * (4 * u + k)), idesc_acc, k >= 2 ? 1u : accf);
           } else {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
-              umma_bf16_ss(tmem_acc1, (kk < 4 ? a0 : a1) + uint64_t(2 * (kk & 3)), y2mn[st] + uint64_t(128 * kk), idesc_acc,
-                           kk != 0 ? 1u : accf);
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
-              umma_bf16_ss(tmem_acc2, (kk < 4 ? b0 : b1) + uint64_t(2 * (kk & 3)), y1mn[st] + uint64_t(128 * kk), idesc_acc,
-                           kk != 0 ? 1u : accf);
+            for (int k = 0; k < 4; ++k) {  // dV += P^T dO_i and dK += dS^T Q_i, interleaved (independent chains)
+              umma_bf16_ss(tmem_acc1, (ad + kSlab * uint64_t(u)) + uint64_t(2 * k), (y2m + kBuf * uint64_t(st)) + uint64_t(128 * (4 * u + k)), idesc_acc,
+                           k != 0 ? 1u : accf);
+              umma_bf16_ss(tmem_acc2, (bd + kSlab * uint64_t(u)) + uint64_t(2 * k), (y1m + kBuf * uint64_t(st)) + uint64_t(128 * (4 * u + k)), idesc_acc,
+                           k != 0 ? 1u : accf);
+            }
           }
-          umma_commit(bar_acc);
-          ++n_acc;
+          if (u == 1) {
+            umma_commit(bar_acc);
+            ++n_acc;
+          }
         }
+        AB_CSTAMP(12);
       }
     }
     __syncwarp();
   } else {
     // ===================== two threads per owner row =====================
     const int q4 = warp & 3;
-    const int half = (warp - 1) >> 2;  // columns [64 * half, 64 * half + 64) of every S / dP tile
+    const int half = (warp - 1) >> 2;  // columns [32 * half, 32 * half + 32) of every 64-column sub-tile
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = uint32_t(q4 * 32) << 16;
     const int t_own = tile * AB_TILE + r;
@@ -230,7 +257,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     const float c = args.scale_log2;
     const long long stat_base = ((long long)b * args.heads + h) * args.rows_per_batch;
     const bool tr = args.dbg != nullptr && threadIdx.x == 32;
-#define AB_STAMP(slot) do { if (tr) args.dbg[(long long)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+#define AB_STAMP(slot) do { if (tr) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
     AB_STAMP(0);
     float lse2 = 0.f, delta = 0.f;
     if (MODE == 0) {
@@ -262,83 +289,128 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         asm volatile("bar.sync 1, 256;" ::: "memory");
         delta = s_stat[128 + r];
       }
-      // ---- pre-pass: log-sum-exp of the row (log2 domain) ----
+      // ---- pre-pass (no lse from the forward): log-sum-exp of the row, log2 domain; each thread covers its 32 columns of
+      // every sub-tile, the two partial (max, sum) pairs of a row are combined through shared memory ----
       float m = -INFINITY, l = 0.f;
-      for (int it = 0; it < n_pre; ++it) {  // (fallback path, have_lse == 0: the first thread of each row does all 128 columns)
-        const int nv = min(AB_TILE, len - it * AB_TILE);
-        mbar_wait(bar_s, it & 1u, 5);
+      for (int n = 0; n < n_pre; ++n) {
+        const int u = n & 1;
+        const int nv = min(AB_TILE, len - (n >> 1) * AB_TILE);
+        const int c0 = 64 * u + 32 * half;
+        mbar_wait(bar_s(u), (n >> 1) & 1u, 5);
         tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < AB_TILE; c0 += 32) {
-          if (c0 >= nv || half != 0) break;
+        if (c0 < nv) {
           uint32_t v[32];
-          ab_tmem_ld32(tmem_S + lane_off + c0, v);
+          ab_tmem_ld32(tmem_S(u) + lane_off + 32 * half, v);
           tmem_wait_ld();
           float cm = -INFINITY;
 #pragma unroll
           for (int k = 0; k < 32; ++k)
             if (c0 + k < nv) cm = fmaxf(cm, __uint_as_float(v[k]) * c);
           const float mn = fmaxf(m, cm);
-          float s = 0.f;
+          float sum = 0.f;
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (c0 + k < nv) s += ex2_approx(fmaf(__uint_as_float(v[k]), c, -mn));
-          l = l * ex2_approx(m - mn) + s;
+            if (c0 + k < nv) sum += ex2_approx(fmaf(__uint_as_float(v[k]), c, -mn));
+          l = l * ex2_approx(m - mn) + sum;
           m = mn;
         }
         tc_fence_before();
-        mbar_arrive(bar_p);
+        mbar_arrive(bar_p(u));
       }
       if (!args.have_lse) {
-        if (half == 0) s_stat[r] = m + log2f(l);
+        s_stat[256 + 2 * (128 * half + r)] = m;
+        s_stat[256 + 2 * (128 * half + r) + 1] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        lse2 = s_stat[r];
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // s_stat is reused by nobody in MODE 0, kept for symmetry
+        const float m0 = s_stat[256 + 2 * r], l0 = s_stat[256 + 2 * r + 1];
+        const float m1 = s_stat[256 + 2 * (128 + r)], l1 = s_stat[256 + 2 * (128 + r) + 1];
+        const float mm = fmaxf(m0, m1);
+        float ll = 0.f;
+        if (m0 > -INFINITY) ll += l0 * ex2_approx(m0 - mm);
+        if (m1 > -INFINITY) ll += l1 * ex2_approx(m1 - mm);
+        lse2 = mm + log2f(ll);
       }
       if (half == 0 && t_own < args.rows_per_batch) {
         if (!args.have_lse) args.lse[stat_base + t_own] = lse2;
         args.delta[stat_base + t_own] = delta;
       }
     }
+    if (MODE == 0) lse2 -= log2f(args.scale);  // ps = scale * P straight out of the exp2
     AB_STAMP(1);
     // ---- main pass ----
-    for (int it = n_pre; it < n_it; ++it) {
-      const int j = it - n_pre;
+    for (int n = n_pre; n < n_sub; ++n) {
+      const int u = n & 1;
+      const int j = (n - n_pre) >> 1;
       const int nv = min(AB_TILE, len - j * AB_TILE);  // valid columns of this tile (keys in MODE 0, queries in MODE 1)
       const float* st = s_stat + (j & 1) * 256;
-      if (MODE == 1) {
+      if (MODE == 1 && u == 0) {
         const int tq = j * AB_TILE + r;
         float* sw_ = s_stat + (j & 1) * 256;
         const float* src = half == 0 ? args.lse : args.delta;
-        sw_[128 * half + r] = tq < args.rows_per_batch ? src[stat_base + tq] : 0.f;
+        const float sv = tq < args.rows_per_batch ? src[stat_base + tq] : 0.f;
+        sw_[128 * half + r] = half == 0 ? sv : -args.scale * sv;  // (lse, -scale * delta)
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      mbar_wait(bar_s, it & 1u, 6);
+      if (n == n_pre + 6) AB_STAMP(13);
+      mbar_wait(bar_s(u), (n >> 1) & 1u, 6);
       tc_fence_after();
-      if (it == n_pre) AB_STAMP(2);
-      if (it == n_pre + 1) AB_STAMP(3);
-#pragma unroll 1
-      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
+      if (n == n_pre) AB_STAMP(2);
+      if (n == n_pre + 2) AB_STAMP(3);
+      if (n == n_pre + 6) AB_STAMP(14);
+      {
+        const int c0 = 64 * u + 32 * half;  // column inside the 128-wide tile
         uint32_t vs[32], vd[32];
-        ab_tmem_ld32(tmem_S + lane_off + c0, vs);
-        ab_tmem_ld32(tmem_dP + lane_off + c0, vd);
+        ab_tmem_ld32(tmem_S(u) + lane_off + 32 * half, vs);
+        ab_tmem_ld32(tmem_dP(u) + lane_off + 32 * half, vd);
         tmem_wait_ld();
         uint32_t pp[16], pd[16];
+        // MODE 0: the softmax scale is folded into the exponent (lse2 holds lse - log2(scale)): ps = scale * P in one
+        // exp2, dS = ps * (dP - delta). MODE 1: the staged column statistics are (lse, -scale * delta), so that
+        // dS^T = P^T * fma(dP^T, scale, -scale * delta). Full tiles of valid rows skip the masks.
+        const bool fast = own_valid && nv == AB_TILE;  // nv is CTA-uniform
+        if (fast) {
+          if (MODE == 0) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-          const float l0 = MODE == 0 ? lse2 : st[c0 + k], l1 = MODE == 0 ? lse2 : st[c0 + k + 1];
-          const float e0 = MODE == 0 ? delta : st[128 + c0 + k], e1 = MODE == 0 ? delta : st[128 + c0 + k + 1];
-          if (own_valid && c0 + k < nv) {
-            p0 = ex2_approx(fmaf(__uint_as_float(vs[k]), c, -l0));
-            d0 = p0 * (__uint_as_float(vd[k]) - e0) * args.scale;
+            for (int k = 0; k < 32; k += 2) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(vs[k]), c, -lse2));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(vs[k + 1]), c, -lse2));
+              pd[k >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[k]) - delta), p1 * (__uint_as_float(vd[k + 1]) - delta));
+            }
+          } else {
+            const float4* sl = reinterpret_cast<const float4*>(st + c0);
+            const float4* se = reinterpret_cast<const float4*>(st + 128 + c0);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 l4 = sl[k4], e4 = se[k4];
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+              float pv[4], dv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pv[e] = ex2_approx(fmaf(__uint_as_float(vs[4 * k4 + e]), c, -ll[e]));
+                dv[e] = pv[e] * fmaf(__uint_as_float(vd[4 * k4 + e]), args.scale, ee[e]);
+              }
+              pp[2 * k4] = pack_bf16x2(pv[0], pv[1]);
+              pp[2 * k4 + 1] = pack_bf16x2(pv[2], pv[3]);
+              pd[2 * k4] = pack_bf16x2(dv[0], dv[1]);
+              pd[2 * k4 + 1] = pack_bf16x2(dv[2], dv[3]);
+            }
           }
-          if (own_valid && c0 + k + 1 < nv) {
-            p1 = ex2_approx(fmaf(__uint_as_float(vs[k + 1]), c, -l1));
-            d1 = p1 * (__uint_as_float(vd[k + 1]) - e1) * args.scale;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+            const float l0 = MODE == 0 ? lse2 : st[c0 + k], l1 = MODE == 0 ? lse2 : st[c0 + k + 1];
+            const float e0 = MODE == 0 ? delta : st[128 + c0 + k], e1 = MODE == 0 ? delta : st[128 + c0 + k + 1];
+            if (own_valid && c0 + k < nv) {
+              p0 = ex2_approx(fmaf(__uint_as_float(vs[k]), c, -l0));
+              d0 = MODE == 0 ? p0 * (__uint_as_float(vd[k]) - e0) : p0 * fmaf(__uint_as_float(vd[k]), args.scale, e0);
+            }
+            if (own_valid && c0 + k + 1 < nv) {
+              p1 = ex2_approx(fmaf(__uint_as_float(vs[k + 1]), c, -l1));
+              d1 = MODE == 0 ? p1 * (__uint_as_float(vd[k + 1]) - e1) : p1 * fmaf(__uint_as_float(vd[k + 1]), args.scale, e1);
+            }
+            pp[k >> 1] = pack_bf16x2(p0, p1);
+            pd[k >> 1] = pack_bf16x2(d0, d1);
           }
-          pp[k >> 1] = pack_bf16x2(p0, p1);
-          pd[k >> 1] = pack_bf16x2(d0, d1);
         }
         if (MODE == 0) {
           ab_stage_store(sA, r, c0, pd);
@@ -349,7 +421,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive(bar_p(u));
+      if (n == n_pre + 6) AB_STAMP(15);
     }
     AB_STAMP(4);
     // ---- read the accumulators ----
@@ -359,11 +432,22 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     // Phase A: the accumulator rows go to shared memory as f32 (row = 256 B, 16-byte chunks XOR-swizzled by row & 15)
     // in the idle staging tiles; phase B: all threads store 16-byte bf16 chunks, 8 lanes per row (coalesced), with the
     // RoPE rotation of dq / dk applied on the way (cos / sin read coalesced too).
-    auto to_smem = [&](uint32_t tm, uint32_t tile_s) {
+    auto to_smem = [&](uint32_t tm, uint32_t tile_s, uint32_t tm_add) {  // tm_add != 0: a second accumulator to add
       uint32_t lo[32], hi[32];
       ab_tmem_ld32(tm + lane_off, lo);
       ab_tmem_ld32(tm + lane_off + 32, hi);
       tmem_wait_ld();
+      if (tm_add != 0u) {
+        uint32_t lo2[32], hi2[32];
+        ab_tmem_ld32(tm_add + lane_off, lo2);
+        ab_tmem_ld32(tm_add + lane_off + 32, hi2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          lo[i] = __float_as_uint(__uint_as_float(lo[i]) + __uint_as_float(lo2[i]));
+          hi[i] = __float_as_uint(__uint_as_float(hi[i]) + __uint_as_float(hi2[i]));
+        }
+      }
       const uint32_t rowa = tile_s + uint32_t(r) * 256u;
       const uint32_t sw = uint32_t(r & 15);
 #pragma unroll
@@ -417,12 +501,12 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     };
     const int tid = int(threadIdx.x) - 32;
     if (MODE == 0) {
-      if (half == 0) to_smem(tmem_acc2, sA);
+      if (half == 0) to_smem(tmem_acc2, sA, tmem_acc1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) store_task(sA, i * 256 + tid, 0, true);
     } else {
-      if (half == 0) to_smem(tmem_acc1, sA); else to_smem(tmem_acc2, sB);
+      if (half == 0) to_smem(tmem_acc1, sA, 0u); else to_smem(tmem_acc2, sB, 0u);
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {

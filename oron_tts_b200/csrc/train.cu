@@ -288,7 +288,7 @@ extern "C" int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int
 // attention backward
 // ---------------------------------------------------------------------------------------------------------
 static long long* g_attn_bwd_dbg = nullptr;
-// profiling aid (tools/attn_bwd_trace.py): int64 [2 * grid, 8] device buffer (dQ launch first, then dK/dV), or NULL
+// profiling aid (tools/attn_bwd_trace.py): int64 [2 * grid, 16] device buffer (dQ launch first, then dK/dV), or NULL
 extern "C" void oron_debug_set_attention_bwd_stamps(void* buf) { g_attn_bwd_dbg = reinterpret_cast<long long*>(buf); }
 
 extern "C" int oron_attention_bwd(const void* qk, int64_t ld_qk, const void* v, int64_t ld_v, const void* o, int64_t ld_o,
@@ -345,7 +345,7 @@ extern "C" int oron_attention_bwd(const void* qk, int64_t ld_qk, const void* v, 
   attn_bwd_tcgen05_kernel<0><<<grid, AB_THREADS, AB_SMEM_BYTES, st>>>(tqk, tv, tdo, a);
   rc = check_launch("attn_bwd_dq");
   if (rc) return rc;
-  if (a.dbg) a.dbg += (long long)grid * 8;
+  if (a.dbg) a.dbg += (long long)grid * 16;
   attn_bwd_tcgen05_kernel<1><<<grid, AB_THREADS, AB_SMEM_BYTES, st>>>(tqk, tv, tdo, a);
   return check_launch("attn_bwd_dkdv");
 }

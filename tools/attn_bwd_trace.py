@@ -31,7 +31,7 @@ for _ in range(10): run()
 e1.record(); torch.cuda.synchronize()
 print(f"attention backward (dQ + dK/dV): {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per call")
 grid = (rpb // 128) * H * nb
-dbg = torch.zeros(2 * grid, 8, device=DEV, dtype=torch.int64)
+dbg = torch.zeros(2 * grid, 16, device=DEV, dtype=torch.int64)
 T.tlib().oron_debug_set_attention_bwd_stamps.argtypes = [__import__("ctypes").c_void_p]
 T.tlib().oron_debug_set_attention_bwd_stamps(dbg.data_ptr())
 run(); torch.cuda.synchronize()
@@ -43,4 +43,9 @@ for mode in (0, 1):
     print(f"mode {mode}: cycles since the CTA's first stamp (median over CTAs)")
     for k in range(1, 7):
         print(f"   {names[k]:22s} {int((x[:, k] - x[:, 0]).median())}")
-    print(f"   per main iteration     {int(((x[:, 4] - x[:, 3]) / 6).median())}  (iterations 2..7)")
+    med = lambda a, b_: int((x[:, a] - x[:, b_]).median())
+    print(f"   sub-iteration 6 (tile 3, first half), MMA thread: fetch/acc-wait {med(9, 8)}, issue S/dP(n+1) {med(10, 9)}, "
+          f"wait bar_p {med(11, 10)}, issue acc {med(12, 11)}")
+    print(f"   same, compute thread: wait bar_s {med(14, 13)}, tmem ld + math + stores + arrive {med(15, 14)}; "
+          f"compute start relative to the MMA thread's loop top {med(13, 8)}")
+    print(f"   per 128-column tile    {int(((x[:, 4] - x[:, 3]) / 7).median())}  (tiles 1..7)")
