@@ -108,6 +108,13 @@ typedef struct oron_gemm_desc {
   int32_t stream_k;          /* 1 (two_sm + ORON_EPI_GATE_RESID, taps == 1 only): cut the flat (tile, k-block) list into equal shares per SM pair;
                               * partial sums are added to `out` with f32 vector reductions (sum order, hence the last bit, may vary run to run) */
   void* debug_stamps;        /* NULL, or int64 [grid, 16] device buffer for per-CTA clock64 stamps (profiling aid) */
+  /* Backward-pass operand layouts (two_sm = 1, taps = 1, K = w_cols a multiple of 64): the contraction runs over the
+   * ROWS of the operand as stored, so no transposed copy is needed (TMA boxes of 64 x 64, MN-major UMMA descriptors):
+   *   a_mn_major: A points to bf16 [K, lda], columns [0, rows_per_batch) -> D[m, n] = sum_k A[k, m] * ... (nbatch = 1)
+   *   b_mn_major: W points to bf16 [K, ldw], columns [0, N)             -> D[m, n] = sum_k ... * W[k, n]
+   * weight gradient dW = dY^T X: both; data gradient dX = dY W: b_mn_major only. */
+  int32_t a_mn_major;
+  int32_t b_mn_major;
 } oron_gemm_desc;
 
 int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);

@@ -23,6 +23,10 @@ extern "C" {
 int oron_transpose_bf16(const void* in, int64_t ld_in, int32_t rows_per_batch, int32_t nbatch, int32_t C,
                         const int32_t* seq_lens, void* out, int64_t ld_out, float* colsum, oron_stream_t stream);
 
+/* out[c] += sum over rows of in[r, c] (bf16 [rows, ld_in], columns [0, C)): the bias gradient of a Linear from its
+ * output gradient, when the weight gradient is taken straight from the row-major operands (a_mn_major / b_mn_major). */
+int oron_colsum_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, float* out, oron_stream_t stream);
+
 /* Backward of oron_ln_modulate (modules.py:218, 234, 341 and the affine LayerNorms modules.py:169):
  *   y = LN(x) * (add_one + scale[b]) + shift[b]
  *   dx (+)= LN-backward(dy * (add_one + scale)) ; dscale[b or 0] += sum_t dy * xhat ; dshift += sum_t dy

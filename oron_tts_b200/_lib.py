@@ -87,6 +87,8 @@ class GemmDesc(ctypes.Structure):
         ("f16_from_col", c_int32),
         ("stream_k", c_int32),
         ("debug_stamps", c_void_p),
+        ("a_mn_major", c_int32),
+        ("b_mn_major", c_int32),
     ]
 
 
@@ -208,8 +210,22 @@ def gemm(
     debug_stamps: torch.Tensor | None = None,
     f16_from_col: int = 0,
     stream_k: bool = False,
+    a_mn: bool = False,
+    b_mn: bool = False,
+    k: int | None = None,
 ) -> None:
-    """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16."""
+    """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16.
+
+    ``a_mn`` / ``b_mn`` (2-SM kernel): the operand is given as stored for the backward pass, with the contraction over
+    its ROWS -- A as [K, M] (out = A.T @ ...), W as [K, N] (out = ... @ W); pass ``rows_per_batch`` = M and ``n`` = N."""
+    if a_mn or b_mn:
+        kk = int(k if k is not None else (A.shape[0] if a_mn else A.shape[1]))
+        if rows_per_batch is None:
+            rows_per_batch = A.shape[1] if a_mn else A.shape[0]
+        if n is None:
+            n = W.shape[1] if b_mn else W.shape[0]
+        a_cols = kk if a_cols is None else a_cols
+        w_cols = kk
     d = GemmDesc()
     d.A = _ptr(A, torch.bfloat16, "A")
     d.lda = _ld(A)
@@ -243,6 +259,7 @@ def gemm(
     d.f16_from_col = int(f16_from_col)
     d.stream_k = int(bool(stream_k))
     d.debug_stamps = _ptr(debug_stamps, torch.int64, "debug_stamps")
+    d.a_mn_major, d.b_mn_major = int(bool(a_mn)), int(bool(b_mn))
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16
     if out.dtype != want:

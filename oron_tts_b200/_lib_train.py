@@ -15,7 +15,7 @@ TRAIN_SYMBOLS = (
     "oron_transpose_bf16", "oron_ln_bwd", "oron_act_fwd", "oron_act_bwd", "oron_gate_resid", "oron_gate_bwd",
     "oron_dwconv7", "oron_dwconv7_wgrad", "oron_grn_bwd_reduce", "oron_grn_bwd_coef", "oron_grn_bwd_apply",
     "oron_text_embed_bwd", "oron_skinny_dgrad", "oron_skinny_wgrad", "oron_gconv_wgrad", "oron_cfm_loss", "oron_sumsq",
-    "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32", "oron_attention_fwd_lse",
+    "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32", "oron_attention_fwd_lse", "oron_colsum_bf16",
 )
 
 _P, _I, _L, _F = c_void_p, c_int32, c_int64, c_float
@@ -40,6 +40,7 @@ _ARGTYPES = {
     "oron_adamw_clip": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "oron_f16_to_bf16": [_P, _L, _L, _I, _P, _L, _P],
     "oron_mask_rows_f32": [_P, _L, _L, _I, _P, _P],
+    "oron_colsum_bf16": [_P, _L, _L, _I, _P, _P],
     "oron_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _P, _P, _I, _P],
     "oron_attention_fwd_lse": [_P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P],
 }
@@ -187,6 +188,12 @@ def adamw_clip(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
                                   _ptr(pb, BF16, "pb"), p.numel(), _ptr(sumsq_t, F32, "sumsq"), grad_scale, max_norm, lr,
                                   beta1, beta2, eps, wd, bc1, bc2, _ptr(skipped, torch.int32, "skipped"), _stream()),
            "oron_adamw_clip")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out f32 [C] += column sums of x bf16 [rows, C]."""
+    _check(tlib().oron_colsum_bf16(_ptr(x, BF16, "x"), _ld(x), x.shape[0], x.shape[1], _ptr(out, F32, "out"), _stream()),
+           "oron_colsum_bf16")
 
 
 def mask_rows(x: torch.Tensor, row_valid: torch.Tensor) -> None:

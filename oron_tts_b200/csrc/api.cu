@@ -196,13 +196,26 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   if ((d->ldo % 8) != 0 && epi != EPI_F32) return fail(ORON_ERR_BAD_ARG, "gemm: ldo must be a multiple of 8");
   if (epi == EPI_F32 && (d->ldo % 4) != 0) return fail(ORON_ERR_BAD_ARG, "gemm: f32 ldo must be a multiple of 4");
 
-  CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(&ta, d->A, uint64_t(d->a_cols), uint64_t(d->rows_per_batch), uint64_t(d->nbatch),
-                          uint64_t(d->lda), uint64_t(d->lda) * uint64_t(d->rows_per_batch), GEMM_BM, 3);
-  if (rc) return rc;
   const bool two_sm = d->two_sm != 0;
-  rc = make_tmap_bf16(&tb, d->W, uint64_t(d->w_cols), uint64_t(d->N), 1, uint64_t(d->ldw), 0,
-                      uint32_t(two_sm ? d->block_n / 2 : d->block_n), 2);
+  a.a_mn = d->a_mn_major != 0 ? 1 : 0;
+  a.b_mn = d->b_mn_major != 0 ? 1 : 0;
+  if (a.a_mn || a.b_mn) {
+    if (!two_sm || taps != 1 || d->stream_k || d->w_cols % GEMM_BK != 0 || (a.a_mn && d->nbatch != 1))
+      return fail(ORON_ERR_UNSUPPORTED, "gemm: MN-major operands need two_sm, taps == 1, no stream_k, K %% 64 == 0 (and nbatch == 1 for A)");
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  if (a.a_mn)  // source [K, lda], columns [0, M): box = 64 MN x 64 K rows
+    rc = make_tmap_bf16(&ta, d->A, uint64_t(d->rows_per_batch), uint64_t(d->w_cols), 1, uint64_t(d->lda), 0, 64, 2);
+  else
+    rc = make_tmap_bf16(&ta, d->A, uint64_t(d->a_cols), uint64_t(d->rows_per_batch), uint64_t(d->nbatch),
+                        uint64_t(d->lda), uint64_t(d->lda) * uint64_t(d->rows_per_batch), GEMM_BM, 3);
+  if (rc) return rc;
+  if (a.b_mn)  // source [K, ldw], columns [0, N)
+    rc = make_tmap_bf16(&tb, d->W, uint64_t(d->N), uint64_t(d->w_cols), 1, uint64_t(d->ldw), 0, 64, 2);
+  else
+    rc = make_tmap_bf16(&tb, d->W, uint64_t(d->w_cols), uint64_t(d->N), 1, uint64_t(d->ldw), 0,
+                        uint32_t(two_sm ? d->block_n / 2 : d->block_n), 2);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 

@@ -61,6 +61,11 @@ struct GemmArgs {
   int mask_rows;               // EPI_GATE_RESID: skip rows t >= seq_len
   int stream_k;                // 2-SM EPI_GATE_RESID only: split the K loops evenly over the SM pairs, partial sums land with f32 atomics
   long long* dbg;              // optional [grid, 16] clock64 stamps (tools/kernel_bench.py --trace); nullptr in production
+  // 2-SM kernel only: operands whose K dimension runs along the ROWS of the source (the backward-pass GEMMs):
+  //   a_mn: A source is [K, M] row-major (D = Asrc^T ...), b_mn: B source is [K, N] row-major (D = ... Bsrc).
+  // The TMA box is 64 (MN, contiguous) x 64 (K rows); a 128-wide operand tile is two such 8 KB boxes, consumed through
+  // MN-major SW128 descriptors (SBO = 1024: next 8 K rows, LBO = 8192: next 64 MN elements).
+  int a_mn, b_mn;
 };
 
 #define ORON_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -716,8 +721,20 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t sb = sa + Cfg::kABytes;
           const int a_col = (args.grouped ? (n0 / args.grouped) * args.grouped : 0) + (kb % args.cpb) * GEMM_BK;
           const int a_row = t0 + kb / args.cpb - args.pad;
-          tma_load_3d_2sm(sa, &tmA, full_bar(stage), a_col, a_row, b);
-          tma_load_2d_2sm(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0 + rank * (BN / 2));
+          if (args.a_mn) {
+#pragma unroll
+            for (int i = 0; i < GEMM_BM / 64; ++i)
+              tma_load_2d_2sm(sa + i * 8192, &tmA, full_bar(stage), m_tile * GEMM_BM + 64 * i, kb * GEMM_BK);
+          } else {
+            tma_load_3d_2sm(sa, &tmA, full_bar(stage), a_col, a_row, b);
+          }
+          if (args.b_mn) {
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i)
+              tma_load_2d_2sm(sb + i * 8192, &tmB, full_bar(stage), n0 + rank * (BN / 2) + 64 * i, kb * GEMM_BK);
+          } else {
+            tma_load_2d_2sm(sb, &tmB, full_bar(stage), kb * GEMM_BK, n0 + rank * (BN / 2));
+          }
           if (kb == w.kb0 && first_seg) ORON_STAMP(1);
           if (kb == w.kb1 - 1 && first_seg) ORON_STAMP(2);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -726,7 +743,10 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN);
+      const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, args.a_mn, args.b_mn);
+      // K-major: 16 K elements = 32 bytes inside the 128-byte rows; MN-major: 16 K rows = 2048 bytes (>> 4)
+      const uint64_t a_kstep = args.a_mn ? 128u : 2u, b_kstep = args.b_mn ? 128u : 2u;
+      const uint32_t a_lbo = args.a_mn ? 8192u : 16u, b_lbo = args.b_mn ? 8192u : 16u;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -742,11 +762,11 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (kb == w.kb0 && it == 0) ORON_STAMP(3);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+          const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16_ss_2sm(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
+            umma_bf16_ss_2sm(tmem_d, adesc + a_kstep * uint64_t(k), bdesc + b_kstep * uint64_t(k), idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
           umma_commit_2sm(empty_bar(stage), 3);
           if (kb == w.kb1 - 1) { umma_commit_2sm(tfull_bar(as), 3); if (it < 2) ORON_STAMP(4 + it); }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }

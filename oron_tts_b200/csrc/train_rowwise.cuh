@@ -217,6 +217,31 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const TransposeArgs
   }
 }
 
+// out[c] += sum_r in[r, c] (bias gradients). grid (ceil(C / 64), row chunks of 512); 256 threads = 32 column pairs x 8
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* in, long long ld, long long rows, int C, float* out) {
+  __shared__ float2 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * tx;
+  const long long r0 = (long long)blockIdx.y * 512, r1 = min(r0 + 512, rows);
+  float2 acc = make_float2(0.f, 0.f);
+  if (c < C) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(in + r * ld + c));
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float2 s = red[0][tx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s.x += red[i][tx].x; s.y += red[i][tx].y; }
+    atomicAdd(out + c, s.x);
+    if (c + 1 < C) atomicAdd(out + c + 1, s.y);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // column sums of per-warp register partials: lane owns columns {2*(lane + 32 i), +1}, i < V2 (C = 64 V2);
 // reduce over the 8 warps of the CTA through shared memory, then one atomicAdd per column.

@@ -191,14 +191,9 @@ class TrainWeights(DiTWeights):
         H = self.ff_dim
         z = lambda *s: torch.zeros(*s, device=dev, dtype=BF16)  # noqa: E731
         self.wx, self.wct = z(D, self.kx), z(D, self.kct)
-        self.wtextT = z(C, D)
         self.wpT = z(D, _rup(M, 64))
         self.conv_pos = [None, None]
         self.conv_posT = [None, None]
-        for blk in self.blocks:
-            blk.update(wqkvT=z(D, 3 * D), woT=z(D, D), w1T=z(D, H), w2T=z(H, D))
-        for blk in self.text_blocks:
-            blk.update(w1T=z(C, 2 * C), w2T=z(2 * C, C))
         self.refresh()
 
     @torch.no_grad()
@@ -208,7 +203,6 @@ class TrainWeights(DiTWeights):
         W = a.view(a.p, "input_embed.proj.weight")
         self.wx[:, :M].copy_(W[:, :M])
         self.wct[:, :M + C].copy_(W[:, M:])
-        self.wtextT.copy_(W[:, 2 * M:].t())
         self.wpT[:, :M].copy_(a.view(a.p, "proj_out.weight").t())
         for j, idx in enumerate((0, 2)):
             w = a.view(a.p, f"input_embed.conv_pos_embed.conv1d.{idx}.weight")
@@ -224,14 +218,6 @@ class TrainWeights(DiTWeights):
             else:
                 self.conv_pos[j]["w"].copy_(fwd["w"])
                 self.conv_posT[j]["w"].copy_(bwd["w"])
-        for blk in self.blocks:
-            for n in ("wqkv", "wo", "w1", "w2"):
-                src = blk[n]
-                T.transpose(src, blk[n + "T"], rows_per_batch=src.shape[0], nbatch=1)
-        for blk in self.text_blocks:
-            for n in ("w1", "w2"):
-                src = blk[n]
-                T.transpose(src, blk[n + "T"], rows_per_batch=src.shape[0], nbatch=1)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -279,12 +265,10 @@ class TrainWorkspace:
         self.loss_sum = z(1)
         self.dpred = z(R, _rup(M, 64), dt=BF16)
         # backward
-        wide = max(H, 3 * D, 2 * C, w.kct)
         self.dx = z(R, D)
         self.g_d, self.g_ao = z(R, D, dt=BF16), z(R, D, dt=BF16)
         self.g_h, self.g_qkv = z(R, H, dt=BF16), z(R, 3 * D, dt=BF16)
         self.vb = z(R, D, dt=BF16)
-        self.tA, self.tB = z(wide, R, dt=BF16), z(wide, R, dt=BF16)
         self.lse = [z(nb * w.heads * tpad) for _ in range(nd)]
         self.delta = z(nb * w.heads * tpad)
         self.dtab = z(nb, w.ada_n)
@@ -327,31 +311,26 @@ class TrainEngine:
     def _bn(n: int) -> int:
         return 256 if n % 256 == 0 else (128 if n % 128 == 0 or n > 128 else 64)
 
-    def _dgrad(self, ws, dy, wT, out, *, n=None):
-        """out[R, K_in] (bf16) = dy[R, N_out] @ W, with W^T given as [K_in, N_out]."""
-        nn = wT.shape[0] if n is None else n
-        bn = self._bn(nn)
-        L.gemm(dy, wT, out, epilogue=L.EPI_BF16, rows_per_batch=ws.tpad, nbatch=ws.nb, block_n=bn, n=nn,
-               two_sm=bn >= 128 and nn % bn == 0 and self.w.dim % 256 == 0)
+    def _dgrad(self, ws, dy, w, out):
+        """out[R, K_in] (bf16) = dy[R, N_out] @ w, w = the Linear's weight as stored ([N_out, K_in], read MN-major)."""
+        nn = w.shape[1]
+        bn = 256 if nn % 256 == 0 else 128
+        L.gemm(dy, w, out, epilogue=L.EPI_BF16, rows_per_batch=ws.tpad, nbatch=ws.nb, block_n=bn, b_mn=True, two_sm=True)
 
-    def _wgrad(self, dyT, xT, out, *, n=None, accumulate=False):
-        """out[N_out, K_in] (f32, a gradient-arena view) (+)= dyT[N_out, R] @ xT[K_in, R]^T."""
-        rows = dyT.shape[0]
-        nn = xT.shape[0] if n is None else n
-        bn = self._bn(nn)
-        L.gemm(dyT, xT, out, epilogue=L.EPI_F32, rows_per_batch=rows, nbatch=1, block_n=bn, n=nn,
-               addend=out if accumulate else None, two_sm=bn >= 128 and nn % bn == 0 and rows % 256 == 0)
+    def _wgrad(self, dy, x, out, *, accumulate=False):
+        """out[N_out, K_in] (f32, a gradient-arena view) (+)= dy[R, N_out]^T @ x[R, K_in], both operands as stored."""
+        nn = x.shape[1]
+        bn = 256 if nn % 256 == 0 else 128
+        L.gemm(dy, x, out, epilogue=L.EPI_F32, block_n=bn, a_mn=True, b_mn=True, two_sm=True,
+               addend=out if accumulate else None)
 
-    def _linear_bwd(self, ws, dy, x_saved, wT, gw, gb, dx_out, *, acc=False):
-        """Backward of y = x W^T + b for [R, .] activations: bias + weight gradients into the arena, data gradient."""
-        a = self.arena
-        n_out, k_in = dy.shape[1], x_saved.shape[1]
-        T.transpose(dy, ws.tA[:n_out], rows_per_batch=ws.tpad, nbatch=ws.nb, colsum=gb)
-        T.transpose(x_saved, ws.tB[:k_in], rows_per_batch=ws.tpad, nbatch=ws.nb)
-        self._wgrad(ws.tA[:n_out], ws.tB[:k_in], gw, accumulate=acc)
+    def _linear_bwd(self, ws, dy, x_saved, w, gw, gb, dx_out, *, acc=False):
+        """Backward of y = x W^T + b for [R, .] activations: bias and weight gradients into the arena, data gradient.
+        No transposed copies: the tcgen05 GEMM reads the row-major operands MN-major (oron_gemm_desc.a/b_mn_major)."""
+        T.colsum(dy, gb)
+        self._wgrad(dy, x_saved, gw, accumulate=acc)
         if dx_out is not None:
-            self._dgrad(ws, dy, wT, dx_out)
-        del a
+            self._dgrad(ws, dy, w, dx_out)
 
     # ---- objective ---------------------------------------------------------------------------------------
     def draw(self, mel: torch.Tensor, lens: torch.Tensor, training: bool = True) -> dict:
@@ -507,10 +486,10 @@ class TrainEngine:
         ws.dtab.zero_()
         sl = ws.seq_lens
         # -- proj_out (dit.py:234) and the final AdaLN (modules.py:232-234: chunks (scale, shift))
-        T.transpose(ws.dpred[:, :M], ws.tA[:M], colsum=a.view(G, "proj_out.bias"), **common)
-        T.transpose(ws.nrmf, ws.tB[:D], **common)
-        self._wgrad(ws.tA[:M], ws.tB[:D], a.view(G, "proj_out.weight"), accumulate=acc)
-        self._dgrad(ws, ws.dpred, w.wpT, ws.g_d)
+        T.colsum(ws.dpred[:, :M], a.view(G, "proj_out.bias"))
+        self._wgrad(ws.dpred[:, :M], ws.nrmf, a.view(G, "proj_out.weight"), accumulate=acc)
+        # K = n_mels is not a multiple of 64: this one data gradient keeps a (tiny) transposed, zero-padded weight copy
+        L.gemm(ws.dpred, w.wpT, ws.g_d, epilogue=L.EPI_BF16, block_n=256 if D % 256 == 0 else 128, two_sm=True, **common)
         o = w.depth * 6 * D
         lnb = dict(eps=1e-6, mod_ld=an, add_one=True, seq_lens=sl, dx=ws.dx, dmod_ld=an, **common)
         T.ln_bwd(ws.xres, ws.g_d, scale=tab[o:], accumulate=False, dscale=dtab[o:], dshift=dtab[o + D:], **lnb)
@@ -522,23 +501,23 @@ class TrainEngine:
             # FFN branch: x += gate_mlp * (W2 gelu(W1 n + b1) + b2)
             T.gate_bwd(ws.dx, ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=sl, dy=ws.g_d, dgate=dtab[o + 5 * D:],
                        dgate_ld=an, **common)
-            self._linear_bwd(ws, ws.g_d, ws.hid[i], blk["w2T"], a.view(G, p + "ff.ff.3.weight"), a.view(G, p + "ff.ff.3.bias"),
+            self._linear_bwd(ws, ws.g_d, ws.hid[i], blk["w2"], a.view(G, p + "ff.ff.3.weight"), a.view(G, p + "ff.ff.3.bias"),
                              ws.g_h, acc=acc)
             T.act_bwd(ws.g_h, ws.hpre[i], ws.g_h, L.ACT_GELU_TANH)
-            self._linear_bwd(ws, ws.g_h, ws.nrm2[i], blk["w1T"], a.view(G, p + "ff.ff.0.weight"), a.view(G, p + "ff.ff.0.bias"),
+            self._linear_bwd(ws, ws.g_h, ws.nrm2[i], blk["w1"], a.view(G, p + "ff.ff.0.weight"), a.view(G, p + "ff.ff.0.bias"),
                              ws.g_d, acc=acc)
             T.ln_bwd(ws.xmid[i], ws.g_d, scale=tab[o + 4 * D:], accumulate=True, dscale=dtab[o + 4 * D:], dshift=dtab[o + 3 * D:],
                      **lnb)
             # attention branch: x += gate_msa * mask(Wo attn(...) + bo)
             T.gate_bwd(ws.dx, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=sl, dy=ws.g_d, dgate=dtab[o + 2 * D:],
                        dgate_ld=an, **common)
-            self._linear_bwd(ws, ws.g_d, ws.ao[i], blk["woT"], a.view(G, p + "attn.to_out.0.weight"),
+            self._linear_bwd(ws, ws.g_d, ws.ao[i], blk["wo"], a.view(G, p + "attn.to_out.0.weight"),
                              a.view(G, p + "attn.to_out.0.bias"), ws.g_ao, acc=acc)
             T.f16_to_bf16(ws.qkv[i][:, 2 * D:], ws.vb)
             T.attention_bwd(ws.qkv[i][:, : 2 * D], ws.vb, ws.ao[i], ws.g_ao, ws.g_qkv, nbatch=nb, rows_per_batch=tpad,
                             heads=w.heads, seq_lens=sl, scale=1.0 / math.sqrt(w.dim_head), rope_cos=cos, rope_sin=sin,
                             lse=ws.lse[i], delta=ws.delta, have_lse=True)
-            self._linear_bwd(ws, ws.g_qkv, ws.nrm1[i], blk["wqkvT"], a.view(G, p + "attn.to_q.weight", (3 * D, D), 3 * D * D),
+            self._linear_bwd(ws, ws.g_qkv, ws.nrm1[i], blk["wqkv"], a.view(G, p + "attn.to_q.weight", (3 * D, D), 3 * D * D),
                              a.view(G, p + "attn.to_q.bias", (3 * D,), 3 * D), ws.g_d, acc=acc)
             T.ln_bwd(ws.xin[i], ws.g_d, scale=tab[o + D:], accumulate=True, dscale=dtab[o + D:], dshift=dtab[o:], **lnb)
             self._block_done(i)
@@ -558,12 +537,12 @@ class TrainEngine:
         L.gemm(ws.g_ao, t1["w"], ws.dx, epilogue=L.EPI_SCALE_RESID, addend=ws.dx, seq_lens=sl, out2=ws.g_d, **conv(t1))
         # -- InputEmbedding.proj (dit.py:53): h0 = [x | cond | text] W^T + b
         Gw = a.view(G, "input_embed.proj.weight")
-        T.transpose(ws.g_d, ws.tA[:D], colsum=a.view(G, "input_embed.proj.bias"), **common)
-        T.transpose(ws.xb, ws.tB[: w.kx], **common)
-        self._wgrad(ws.tA[:D], ws.tB[: w.kx], Gw[:, :M], n=M, accumulate=acc)
-        T.transpose(ws.a_ct, ws.tB[: w.kct], **common)
-        self._wgrad(ws.tA[:D], ws.tB[: w.kct], Gw[:, M:], n=M + C, accumulate=acc)
-        L.gemm(ws.g_d, w.wtextT, ws.dxt, epilogue=L.EPI_F32, block_n=128 if C % 128 == 0 else 64, **common)
+        T.colsum(ws.g_d, a.view(G, "input_embed.proj.bias"))
+        self._wgrad(ws.g_d, ws.xb[:, :M], Gw[:, :M], accumulate=acc)
+        self._wgrad(ws.g_d, ws.a_ct[:, : M + C], Gw[:, M:], accumulate=acc)
+        # d text_embed = dh0 @ W[:, 2M:] (the text columns of the projection, read in place from the bf16 arena)
+        L.gemm(ws.g_d, a.view(a.pb, "input_embed.proj.weight")[:, 2 * M:], ws.dxt, epilogue=L.EPI_F32,
+               block_n=256 if C % 256 == 0 else 128, b_mn=True, two_sm=True, **common)
         # -- TextEmbedding (encoder.py:68-96)
         tl = ws.text_lens
         for j in reversed(range(w.conv_layers)):
@@ -571,12 +550,12 @@ class TrainEngine:
             p = blk["key"]
             T.mask_rows(ws.dxt, ws.row_valid)
             L.cast_rows_bf16(ws.dxt, ws.g_c)
-            self._linear_bwd(ws, ws.g_c, ws.thg[j], blk["w2T"], a.view(G, p + "pwconv2.weight"), a.view(G, p + "pwconv2.bias"),
+            self._linear_bwd(ws, ws.g_c, ws.thg[j], blk["w2"], a.view(G, p + "pwconv2.weight"), a.view(G, p + "pwconv2.bias"),
                              ws.g_h2, acc=acc)
             T.grn_bwd(ws.g_h2, ws.tpre[j], ws.g_h2, rows_per_batch=tpad, nb=nb, seq_lens=tl, gamma=blk["gamma"], gx2=ws.gx2[j],
                       A=ws.grn_A, nx=ws.grn_nx, coef=ws.grn_coef, dgamma=a.view(G, p + "grn.gamma", (2 * C,)),
                       dbeta=a.view(G, p + "grn.beta", (2 * C,)))
-            self._linear_bwd(ws, ws.g_h2, ws.tn[j], blk["w1T"], a.view(G, p + "pwconv1.weight"), a.view(G, p + "pwconv1.bias"),
+            self._linear_bwd(ws, ws.g_h2, ws.tn[j], blk["w1"], a.view(G, p + "pwconv1.weight"), a.view(G, p + "pwconv1.bias"),
                              ws.g_c, acc=acc)
             T.ln_bwd(ws.conv[j], ws.g_c, eps=1e-6, scale=blk["ln_w"], mod_ld=0, add_one=False, seq_lens=tl, dx=ws.dconv,
                      accumulate=False, dscale=a.view(G, p + "norm.weight"), dshift=a.view(G, p + "norm.bias"), dmod_ld=0, **common)

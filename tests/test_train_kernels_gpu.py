@@ -344,3 +344,26 @@ def test_attention_bwd_vs_torch(nb, rpb, H, lens):
                     rope_sin=sin, lse=lse_f, delta=delta, have_lse=True)
     for name, lo in (("dq", 0), ("dk", HD), ("dv", 2 * HD)):
         assert _rel(dqkv2[:, lo:lo + HD], ref[:, lo:lo + HD]) < 2e-2, name
+
+
+@pytest.mark.parametrize("R,n_out,k_in,bn", [(2048, 1024, 512, 256), (1024, 256, 4096, 256), (1024, 100, 1024, 256),
+                                             (2048, 1024, 612, 128)])
+def test_gemm_mn_major_operands(R, n_out, k_in, bn):
+    """Backward-pass GEMMs straight from the row-major activations (no transposed copies): dW = dY^T X with both
+    operands MN-major, dX = dY W with an MN-major B."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    ko = (k_in + 7) // 8 * 8
+    dY = (torch.randn(R, 1024 if n_out <= 1024 else n_out, device=DEV, generator=g) * 0.1).to(BF16)[:, :n_out]
+    X = torch.randn(R, ko, device=DEV, generator=g).to(BF16)[:, :k_in]
+    dW = torch.full((n_out, ko), 7.0, device=DEV)[:, :k_in]
+    L.gemm(dY, X, dW, epilogue=L.EPI_F32, a_mn=True, b_mn=True, two_sm=True, block_n=bn)
+    ref = dY.float().t() @ X.float()
+    assert _rel(dW, ref) < 1e-5 + 2e-3 * 0, _rel(dW, ref)
+    dW2 = dW.clone()
+    L.gemm(dY, X, dW2, epilogue=L.EPI_F32, a_mn=True, b_mn=True, two_sm=True, block_n=bn, addend=dW2)
+    assert _rel(dW2, 2 * ref) < 1e-5
+    if n_out % 64 == 0 and k_in % 8 == 0:
+        W = (torch.randn(n_out, k_in, device=DEV, generator=g) * 0.05).to(BF16)
+        dX = torch.zeros(R, k_in, device=DEV, dtype=BF16)
+        L.gemm(dY, W, dX, epilogue=L.EPI_BF16, b_mn=True, two_sm=True, block_n=bn, rows_per_batch=R // 2, nbatch=2)
+        assert _rel(dX, dY.float() @ W.float()) < 5e-3

@@ -101,7 +101,9 @@ def test_two_optimizer_steps_vs_reference_golden():
     a = eng.arena
     assert torch.equal(a.pb, a.p.to(torch.bfloat16))
     blk = eng.w.blocks[0]
-    assert torch.equal(blk["wqkvT"], blk["wqkv"].t())
+    q = dict(eng.model.named_parameters())["cfm.backbone.transformer_blocks.0.attn.to_q.weight"]
+    assert blk["wqkv"].data_ptr() == a.pb.data_ptr() + 2 * a.offsets["cfm.backbone.transformer_blocks.0.attn.to_q.weight"]
+    assert torch.equal(blk["wqkv"][: q.shape[0]], q.detach().to(torch.bfloat16))  # the fused operand IS the arena
 
 
 def test_gradients_vs_oracle_random_draws_and_text_drop():
