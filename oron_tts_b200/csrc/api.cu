@@ -111,10 +111,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 }
 
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MNM = 0>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int max_ctas, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm2_bf16_tcgen05_kernel<BN, EPI>;
+  auto kern = gemm2_bf16_tcgen05_kernel<BN, EPI, MNM>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -219,6 +219,19 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
+  if (a.a_mn || a.b_mn) {  // backward-pass layouts: compile-time variants of the 2-SM kernel
+    const int mnm = a.a_mn | (a.b_mn << 1);
+#define ORON_GEMM2_MN_CASE(BN_, EPI_, MNM_) \
+    if (d->block_n == BN_ && epi == EPI_ && mnm == MNM_) return launch_gemm2<BN_, EPI_, MNM_>(ta, tb, a, d->max_ctas, st);
+    ORON_GEMM2_MN_CASE(128, EPI_BF16, 2)
+    ORON_GEMM2_MN_CASE(256, EPI_BF16, 2)
+    ORON_GEMM2_MN_CASE(128, EPI_F32, 2)
+    ORON_GEMM2_MN_CASE(256, EPI_F32, 2)
+    ORON_GEMM2_MN_CASE(128, EPI_F32, 3)
+    ORON_GEMM2_MN_CASE(256, EPI_F32, 3)
+#undef ORON_GEMM2_MN_CASE
+    return fail(ORON_ERR_UNSUPPORTED, "gemm: no MN-major kernel for block_n=%d epilogue=%d a_mn=%d b_mn=%d", d->block_n, epi, a.a_mn, a.b_mn);
+  }
 #define ORON_GEMM2_CASE(BN_, EPI_) \
   if (two_sm && d->block_n == BN_ && epi == EPI_) return launch_gemm2<BN_, EPI_>(ta, tb, a, d->max_ctas, st);
   ORON_GEMM2_CASE(128, EPI_BF16)

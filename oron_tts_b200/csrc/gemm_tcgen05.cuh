@@ -646,7 +646,9 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + EPI_STAGE_BYTES;
 };
 
-template <int BN, int EPI>
+// MNM: bit 0 = A is MN-major, bit 1 = B is MN-major (compile-time: the K-major instantiations used by the inference path keep
+// constant descriptors / instruction descriptor in the single-thread MMA issue loop)
+template <int BN, int EPI, int MNM = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
@@ -721,14 +723,14 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t sb = sa + Cfg::kABytes;
           const int a_col = (args.grouped ? (n0 / args.grouped) * args.grouped : 0) + (kb % args.cpb) * GEMM_BK;
           const int a_row = t0 + kb / args.cpb - args.pad;
-          if (args.a_mn) {
+          if constexpr ((MNM & 1) != 0) {
 #pragma unroll
             for (int i = 0; i < GEMM_BM / 64; ++i)
               tma_load_2d_2sm(sa + i * 8192, &tmA, full_bar(stage), m_tile * GEMM_BM + 64 * i, kb * GEMM_BK);
           } else {
             tma_load_3d_2sm(sa, &tmA, full_bar(stage), a_col, a_row, b);
           }
-          if (args.b_mn) {
+          if constexpr ((MNM & 2) != 0) {
 #pragma unroll
             for (int i = 0; i < BN / 128; ++i)
               tma_load_2d_2sm(sb + i * 8192, &tmB, full_bar(stage), n0 + rank * (BN / 2) + 64 * i, kb * GEMM_BK);
@@ -743,10 +745,10 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, args.a_mn, args.b_mn);
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, MNM & 1, (MNM >> 1) & 1);
       // K-major: 16 K elements = 32 bytes inside the 128-byte rows; MN-major: 16 K rows = 2048 bytes (>> 4)
-      const uint64_t a_kstep = args.a_mn ? 128u : 2u, b_kstep = args.b_mn ? 128u : 2u;
-      const uint32_t a_lbo = args.a_mn ? 8192u : 16u, b_lbo = args.b_mn ? 8192u : 16u;
+      constexpr uint64_t a_kstep = (MNM & 1) ? 128u : 2u, b_kstep = (MNM & 2) ? 128u : 2u;
+      constexpr uint32_t a_lbo = (MNM & 1) ? 8192u : 16u, b_lbo = (MNM & 2) ? 8192u : 16u;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
