@@ -41,23 +41,29 @@ int oron_ln_bwd(const float* x, int64_t ldx, const void* dy_bf16, int64_t lddy, 
 /* Elementwise activation, forward (out = act(in)) and backward (out = dy * act'(pre)); act = oron_act or
  * ORON_ACT_MISH (= 4). in/pre/dy/out are [rows, C] with leading dimensions; *_f32 flags select f32 (1) or bf16 (0).
  * With seq_lens != NULL rows t >= seq_lens[row / rows_per_batch] are written as zeros (the masks of
- * ConvPositionEmbedding, modules.py:136-140). */
+ * ConvPositionEmbedding, modules.py:136-140).
+ * dropout_p > 0: nn.Dropout after the activation (FeedForward, modules.py:297) -- element (r, c) survives iff
+ * hash(dropout_seed, r * C + c) >= p * 2^32 and is scaled by 1 / (1 - p); the backward recomputes the same mask. */
 #define ORON_ACT_MISH 4
 int oron_act_fwd(const void* in, int32_t in_f32, int64_t ld_in, int64_t rows, int32_t C, int32_t act, void* out,
-                 int32_t out_f32, int64_t ld_out, int32_t rows_per_batch, const int32_t* seq_lens, oron_stream_t stream);
+                 int32_t out_f32, int64_t ld_out, int32_t rows_per_batch, const int32_t* seq_lens, float dropout_p,
+                 uint64_t dropout_seed, oron_stream_t stream);
 int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const void* pre, int32_t pre_f32, int64_t ld_pre,
                  int64_t rows, int32_t C, int32_t act, void* out, int32_t out_f32, int64_t ld_out,
-                 int32_t rows_per_batch, const int32_t* seq_lens, oron_stream_t stream);
+                 int32_t rows_per_batch, const int32_t* seq_lens, float dropout_p, uint64_t dropout_seed,
+                 oron_stream_t stream);
 
 /* Gated residual of DiTBlock (modules.py:338, 343) un-fused for training:
  *   fwd: x[r, :] += gate[b, :] * y[r, :]   (rows t >= seq_lens[b]: y taken as 0 when mask_rows, modules.py:281-282)
- *   bwd: dy[r, :] = gate[b, :] * dx[r, :] (bf16; zero rows beyond seq_lens) ; dgate[b, :] += sum_t dx * y */
+ *   bwd: dy[r, :] = gate[b, :] * dx[r, :] (bf16; zero rows beyond seq_lens) ; dgate[b, :] += sum_t dx * y
+ * dropout_p > 0: y is first passed through nn.Dropout (Attention.to_out[1], modules.py:253), same stateless mask as above. */
 int oron_gate_resid(float* x, int64_t ldx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch, int32_t nbatch,
                     int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens, int32_t mask_rows,
-                    oron_stream_t stream);
+                    float dropout_p, uint64_t dropout_seed, oron_stream_t stream);
 int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
                   int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
-                  void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, oron_stream_t stream);
+                  void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, float dropout_p, uint64_t dropout_seed,
+                  oron_stream_t stream);
 
 /* Depthwise Conv1d(k=7, pad=3, groups=C) over frames, un-fused (modules.py:178; backward data path with flip=1):
  *   out[t, c] (+)= bias[c] + sum_k w[c, flip ? 6-k : k] * x[t + k - 3, c], x = 0 outside [0, seq_lens[b]).

@@ -2,7 +2,7 @@
 
 from __future__ import annotations
 
-from ctypes import c_float, c_int32, c_int64, c_void_p
+from ctypes import c_float, c_int32, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -18,14 +18,14 @@ TRAIN_SYMBOLS = (
     "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32", "oron_attention_fwd_lse", "oron_colsum_bf16",
 )
 
-_P, _I, _L, _F = c_void_p, c_int32, c_int64, c_float
+_P, _I, _L, _F, _U = c_void_p, c_int32, c_int64, c_float, c_uint64
 _ARGTYPES = {
     "oron_transpose_bf16": [_P, _L, _I, _I, _I, _P, _P, _L, _P, _P],
     "oron_ln_bwd": [_P, _L, _P, _L, _I, _I, _I, _F, _P, _L, _I, _P, _P, _L, _I, _P, _P, _L, _P],
-    "oron_act_fwd": [_P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _P],
-    "oron_act_bwd": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _P],
-    "oron_gate_resid": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _P],
-    "oron_gate_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _L, _P, _L, _P],
+    "oron_act_fwd": [_P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _F, _U, _P],
+    "oron_act_bwd": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _F, _U, _P],
+    "oron_gate_resid": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _F, _U, _P],
+    "oron_gate_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _L, _P, _L, _F, _U, _P],
     "oron_dwconv7": [_P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _L, _I, _P],
     "oron_dwconv7_wgrad": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P],
     "oron_grn_bwd_reduce": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P],
@@ -84,31 +84,33 @@ def ln_bwd(x: torch.Tensor, dy: torch.Tensor, *, rows_per_batch: int, nbatch: in
 
 
 def act_fwd(x: torch.Tensor, out: torch.Tensor, act: int, *, rows_per_batch: int = 0,
-            seq_lens: torch.Tensor | None = None) -> None:
+            seq_lens: torch.Tensor | None = None, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     _check(tlib().oron_act_fwd(_ptr(x), _is32(x), _ld(x), x.shape[0], x.shape[1], act, _ptr(out), _is32(out), _ld(out),
-                               int(rows_per_batch), _ptr(seq_lens, torch.int32, "seq_lens"), _stream()), "oron_act_fwd")
+                               int(rows_per_batch), _ptr(seq_lens, torch.int32, "seq_lens"), float(dropout_p),
+                               int(dropout_seed), _stream()), "oron_act_fwd")
 
 
 def act_bwd(dy: torch.Tensor, pre: torch.Tensor, out: torch.Tensor, act: int, *, rows_per_batch: int = 0,
-            seq_lens: torch.Tensor | None = None) -> None:
+            seq_lens: torch.Tensor | None = None, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     _check(tlib().oron_act_bwd(_ptr(dy), _is32(dy), _ld(dy), _ptr(pre), _is32(pre), _ld(pre), dy.shape[0], dy.shape[1], act,
                                _ptr(out), _is32(out), _ld(out), int(rows_per_batch), _ptr(seq_lens, torch.int32, "seq_lens"),
-                               _stream()), "oron_act_bwd")
+                               float(dropout_p), int(dropout_seed), _stream()), "oron_act_bwd")
 
 
 def gate_resid(x: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch: int, gate: torch.Tensor, gate_ld: int,
-               seq_lens: torch.Tensor | None, mask_rows: bool) -> None:
+               seq_lens: torch.Tensor | None, mask_rows: bool, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     _check(tlib().oron_gate_resid(_ptr(x, F32, "x"), _ld(x), _ptr(y, BF16, "y"), _ld(y), rows_per_batch, nbatch, x.shape[1],
                                   _ptr(gate, F32, "gate"), int(gate_ld), _ptr(seq_lens, torch.int32, "seq_lens"),
-                                  int(bool(mask_rows)), _stream()), "oron_gate_resid")
+                                  int(bool(mask_rows)), float(dropout_p), int(dropout_seed), _stream()), "oron_gate_resid")
 
 
 def gate_bwd(dx: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch: int, gate: torch.Tensor, gate_ld: int,
-             seq_lens: torch.Tensor | None, dy: torch.Tensor, dgate: torch.Tensor | None, dgate_ld: int) -> None:
+             seq_lens: torch.Tensor | None, dy: torch.Tensor, dgate: torch.Tensor | None, dgate_ld: int,
+             dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     _check(tlib().oron_gate_bwd(_ptr(dx, F32, "dx"), _ld(dx), _ptr(y, BF16, "y"), _ld(y), rows_per_batch, nbatch,
                                 dx.shape[1], _ptr(gate, F32, "gate"), int(gate_ld), _ptr(seq_lens, torch.int32, "seq_lens"),
-                                _ptr(dy, BF16, "dy"), _ld(dy), _ptr(dgate, F32, "dgate"), int(dgate_ld), _stream()),
-           "oron_gate_bwd")
+                                _ptr(dy, BF16, "dy"), _ld(dy), _ptr(dgate, F32, "dgate"), int(dgate_ld), float(dropout_p),
+                                int(dropout_seed), _stream()), "oron_gate_bwd")
 
 
 def dwconv7(x: torch.Tensor, out: torch.Tensor, *, rows_per_batch: int, nbatch: int, seq_lens: torch.Tensor | None,

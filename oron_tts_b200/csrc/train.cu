@@ -12,6 +12,21 @@ using namespace oron;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+static inline DropCfg drop_cfg(float p, uint64_t seed) {
+  DropCfg d;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull;  // splitmix64: nearby seeds (per-layer offsets) give unrelated keys
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  d.key = (unsigned int)(z >> 32) ^ (unsigned int)z;
+  if (!(p > 0.f)) { d.thresh = 0u; d.inv_keep = 1.f; return d; }
+  if (p > 0.999f) p = 0.999f;
+  d.thresh = (unsigned int)((double)p * 4294967296.0);
+  if (d.thresh == 0u) d.thresh = 1u;
+  d.inv_keep = 1.0f / (1.0f - p);
+  return d;
+}
+
 static inline int ew_blocks(long long total, int per_block = 256) {
   long long b = (total + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * 16;
@@ -66,57 +81,60 @@ extern "C" int oron_ln_bwd(const float* x, int64_t ldx, const void* dy_bf16, int
 
 template <typename TI, typename TO>
 static void launch_act_fwd(const void* in, int64_t ld_in, int64_t rows, int32_t C, int32_t act, void* out, int64_t ld_out,
-                           int rpb, const int* sl, cudaStream_t st) {
+                           int rpb, const int* sl, const DropCfg& dc, cudaStream_t st) {
   act_fwd_kernel<TI, TO><<<ew_blocks(rows * (C / 2)), 256, 0, st>>>(reinterpret_cast<const TI*>(in), ld_in, rows, C, act,
-                                                                    reinterpret_cast<TO*>(out), ld_out, rpb, sl);
+                                                                    reinterpret_cast<TO*>(out), ld_out, rpb, sl, dc);
 }
 extern "C" int oron_act_fwd(const void* in, int32_t in_f32, int64_t ld_in, int64_t rows, int32_t C, int32_t act, void* out,
                             int32_t out_f32, int64_t ld_out, int32_t rows_per_batch, const int32_t* seq_lens,
-                            oron_stream_t stream) {
+                            float dropout_p, uint64_t dropout_seed, oron_stream_t stream) {
   if (!in || !out || (C & 1) || (seq_lens && rows_per_batch <= 0)) return fail(ORON_ERR_BAD_ARG, "act_fwd: bad argument");
   if (rows <= 0) return 0;
   cudaStream_t st = ST(stream);
+  const DropCfg dc = drop_cfg(dropout_p, dropout_seed);
   if (!in_f32 && !out_f32 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     act_fwd_bf16x8_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, rows, C, act,
                                                                     reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows_per_batch,
-                                                                    seq_lens);
+                                                                    seq_lens, dc);
     return check_launch("act_fwd");
   }
-  if (in_f32 && out_f32) launch_act_fwd<float, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
-  else if (in_f32) launch_act_fwd<float, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
-  else if (out_f32) launch_act_fwd<__nv_bfloat16, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
-  else launch_act_fwd<__nv_bfloat16, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st);
+  if (in_f32 && out_f32) launch_act_fwd<float, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st);
+  else if (in_f32) launch_act_fwd<float, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st);
+  else if (out_f32) launch_act_fwd<__nv_bfloat16, float>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st);
+  else launch_act_fwd<__nv_bfloat16, __nv_bfloat16>(in, ld_in, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st);
   return check_launch("act_fwd");
 }
 template <typename TD, typename TP, typename TO>
 static void launch_act_bwd(const void* dy, int64_t ld_dy, const void* pre, int64_t ld_pre, int64_t rows, int32_t C,
-                           int32_t act, void* out, int64_t ld_out, int rpb, const int* sl, cudaStream_t st) {
+                           int32_t act, void* out, int64_t ld_out, int rpb, const int* sl, const DropCfg& dc, cudaStream_t st) {
   act_bwd_kernel<TD, TP, TO><<<ew_blocks(rows * (C / 2)), 256, 0, st>>>(
       reinterpret_cast<const TD*>(dy), ld_dy, reinterpret_cast<const TP*>(pre), ld_pre, rows, C, act,
-      reinterpret_cast<TO*>(out), ld_out, rpb, sl);
+      reinterpret_cast<TO*>(out), ld_out, rpb, sl, dc);
 }
 extern "C" int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const void* pre, int32_t pre_f32, int64_t ld_pre,
                             int64_t rows, int32_t C, int32_t act, void* out, int32_t out_f32, int64_t ld_out,
-                            int32_t rows_per_batch, const int32_t* seq_lens, oron_stream_t stream) {
+                            int32_t rows_per_batch, const int32_t* seq_lens, float dropout_p, uint64_t dropout_seed,
+                            oron_stream_t stream) {
   if (!dy || !pre || !out || (C & 1) || (seq_lens && rows_per_batch <= 0)) return fail(ORON_ERR_BAD_ARG, "act_bwd: bad argument");
   if (rows <= 0) return 0;
   cudaStream_t st = ST(stream);
+  const DropCfg dc = drop_cfg(dropout_p, dropout_seed);
   using bf = __nv_bfloat16;
   const int key = (dy_f32 ? 4 : 0) | (pre_f32 ? 2 : 0) | (out_f32 ? 1 : 0);
   if (key == 0 && C % 8 == 0 && ld_dy % 8 == 0 && ld_pre % 8 == 0 && ld_out % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     act_bwd_bf16x8_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, st>>>(
         reinterpret_cast<const bf*>(dy), ld_dy, reinterpret_cast<const bf*>(pre), ld_pre, rows, C, act, reinterpret_cast<bf*>(out),
-        ld_out, rows_per_batch, seq_lens);
+        ld_out, rows_per_batch, seq_lens, dc);
     return check_launch("act_bwd");
   }
   switch (key) {
-    case 0: launch_act_bwd<bf, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
-    case 7: launch_act_bwd<float, float, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
-    case 1: launch_act_bwd<bf, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
-    case 4: launch_act_bwd<float, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
-    case 5: launch_act_bwd<float, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, st); break;
+    case 0: launch_act_bwd<bf, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st); break;
+    case 7: launch_act_bwd<float, float, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st); break;
+    case 1: launch_act_bwd<bf, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st); break;
+    case 4: launch_act_bwd<float, bf, bf>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st); break;
+    case 5: launch_act_bwd<float, bf, float>(dy, ld_dy, pre, ld_pre, rows, C, act, out, ld_out, rows_per_batch, seq_lens, dc, st); break;
     default: return fail(ORON_ERR_UNSUPPORTED, "act_bwd: dtype combination %d not instantiated", key);
   }
   return check_launch("act_bwd");
@@ -124,20 +142,22 @@ extern "C" int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const
 
 extern "C" int oron_gate_resid(float* x, int64_t ldx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
                                int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
-                               int32_t mask_rows, oron_stream_t stream) {
+                               int32_t mask_rows, float dropout_p, uint64_t dropout_seed, oron_stream_t stream) {
   if (!x || !y_bf16 || !gate || (C & 1)) return fail(ORON_ERR_BAD_ARG, "gate_resid: bad argument");
   const long long total = (long long)rows_per_batch * nbatch * (C / 2);
   gate_resid_kernel<<<ew_blocks(total), 256, 0, ST(stream)>>>(x, ldx, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy,
-                                                              rows_per_batch, nbatch, C, gate, gate_ld, seq_lens, mask_rows);
+                                                              rows_per_batch, nbatch, C, gate, gate_ld, seq_lens, mask_rows,
+                                                              drop_cfg(dropout_p, dropout_seed));
   return check_launch("gate_resid");
 }
 extern "C" int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
                              int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
-                             void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, oron_stream_t stream) {
+                             void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, float dropout_p,
+                             uint64_t dropout_seed, oron_stream_t stream) {
   if (!dx || !y_bf16 || !gate || !dy_bf16) return fail(ORON_ERR_BAD_ARG, "gate_bwd: null pointer");
   const int rpc = tr_rows_for((long long)rows_per_batch * nbatch, num_sms());
   GateBwdArgs a{dx, lddx, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy, rows_per_batch, nbatch, gate, gate_ld,
-                seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld, rpc};
+                seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld, rpc, drop_cfg(dropout_p, dropout_seed)};
   dim3 grid(unsigned((rows_per_batch + rpc - 1) / rpc), unsigned(nbatch));
   DISPATCH_V2(C, (gate_bwd_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("gate_bwd");

@@ -59,6 +59,24 @@ __device__ __forceinline__ float act_grad(int act, float x) {
   }
 }
 
+// Dropout (modules.py:253, 297) as a stateless mask: element `idx` of a tensor survives iff hash(seed, idx) >= p * 2^32,
+// survivors are scaled by 1 / (1 - p). Forward and backward recompute the same mask from (seed, idx): nothing is stored.
+struct DropCfg {
+  unsigned int key;     // host-mixed (splitmix64) 32-bit key of the call's seed
+  unsigned int thresh;  // p * 2^32 (0: dropout off)
+  float inv_keep;       // 1 / (1 - p)
+};
+__device__ __forceinline__ float drop_scale(const DropCfg& d, unsigned long long idx) {
+  if (d.thresh == 0u) return 1.0f;
+  unsigned int x = (unsigned int)idx * 0x9E3779B1u + d.key;  // lowbias32 finaliser: two 32-bit multiplies per element
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x >= d.thresh ? d.inv_keep : 0.0f;
+}
+
 template <typename T>
 __device__ __forceinline__ float ld_as_f32(const T* p);
 template <>
@@ -75,7 +93,7 @@ __device__ __forceinline__ void st_from_f32<__nv_bfloat16>(__nv_bfloat16* p, flo
 // out = act(in) / out = dy * act'(pre): two columns per thread
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* in, long long ld_in, long long rows, int C, int act, TO* out,
-                                                      long long ld_out, int rows_per_batch, const int* seq_lens) {
+                                                      long long ld_out, int rows_per_batch, const int* seq_lens, const DropCfg dc) {
   const long long half = C / 2;
   const long long total = rows * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -88,14 +106,15 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* in, long long ld
       st_from_f32<TO>(q + 1, 0.f);
       continue;
     }
-    st_from_f32<TO>(q, act_apply(act, ld_as_f32<TI>(p)));
-    st_from_f32<TO>(q + 1, act_apply(act, ld_as_f32<TI>(p + 1)));
+    const unsigned long long e = (unsigned long long)r * C + c;
+    st_from_f32<TO>(q, act_apply(act, ld_as_f32<TI>(p)) * drop_scale(dc, e));
+    st_from_f32<TO>(q + 1, act_apply(act, ld_as_f32<TI>(p + 1)) * drop_scale(dc, e + 1));
   }
 }
 template <typename TD, typename TP, typename TO>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld_dy, const TP* pre, long long ld_pre,
                                                       long long rows, int C, int act, TO* out, long long ld_out,
-                                                      int rows_per_batch, const int* seq_lens) {
+                                                      int rows_per_batch, const int* seq_lens, const DropCfg dc) {
   const long long half = C / 2;
   const long long total = rows * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -109,15 +128,16 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld
       st_from_f32<TO>(q + 1, 0.f);
       continue;
     }
-    st_from_f32<TO>(q, ld_as_f32<TD>(d) * act_grad(act, ld_as_f32<TP>(p)));
-    st_from_f32<TO>(q + 1, ld_as_f32<TD>(d + 1) * act_grad(act, ld_as_f32<TP>(p + 1)));
+    const unsigned long long e = (unsigned long long)r * C + c;
+    st_from_f32<TO>(q, ld_as_f32<TD>(d) * act_grad(act, ld_as_f32<TP>(p)) * drop_scale(dc, e));
+    st_from_f32<TO>(q + 1, ld_as_f32<TD>(d + 1) * act_grad(act, ld_as_f32<TP>(p + 1)) * drop_scale(dc, e + 1));
   }
 }
 
 // bf16 -> bf16 fast paths: 8 columns (16 bytes) per thread
 __global__ void __launch_bounds__(256) act_fwd_bf16x8_kernel(const __nv_bfloat16* in, long long ld_in, long long rows, int C, int act,
                                                              __nv_bfloat16* out, long long ld_out, int rows_per_batch,
-                                                             const int* seq_lens) {
+                                                             const int* seq_lens, const DropCfg dc) {
   const long long per = C / 8;
   const long long total = rows * per;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -131,7 +151,8 @@ __global__ void __launch_bounds__(256) act_fwd_bf16x8_kernel(const __nv_bfloat16
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = bf2_to_f2(w[k]);
-        q[k] = pack_bf16x2(act_apply(act, f.x), act_apply(act, f.y));
+        const unsigned long long e = (unsigned long long)r * C + c + 2 * k;
+        q[k] = pack_bf16x2(act_apply(act, f.x) * drop_scale(dc, e), act_apply(act, f.y) * drop_scale(dc, e + 1));
       }
       o = make_uint4(q[0], q[1], q[2], q[3]);
     }
@@ -140,7 +161,8 @@ __global__ void __launch_bounds__(256) act_fwd_bf16x8_kernel(const __nv_bfloat16
 }
 __global__ void __launch_bounds__(256) act_bwd_bf16x8_kernel(const __nv_bfloat16* dy, long long ld_dy, const __nv_bfloat16* pre,
                                                              long long ld_pre, long long rows, int C, int act, __nv_bfloat16* out,
-                                                             long long ld_out, int rows_per_batch, const int* seq_lens) {
+                                                             long long ld_out, int rows_per_batch, const int* seq_lens,
+                                                             const DropCfg dc) {
   const long long per = C / 8;
   const long long total = rows * per;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -155,7 +177,8 @@ __global__ void __launch_bounds__(256) act_bwd_bf16x8_kernel(const __nv_bfloat16
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 fd = bf2_to_f2(dw[k]), fp = bf2_to_f2(pw[k]);
-        q[k] = pack_bf16x2(fd.x * act_grad(act, fp.x), fd.y * act_grad(act, fp.y));
+        const unsigned long long e = (unsigned long long)r * C + c + 2 * k;
+        q[k] = pack_bf16x2(fd.x * act_grad(act, fp.x) * drop_scale(dc, e), fd.y * act_grad(act, fp.y) * drop_scale(dc, e + 1));
       }
       o = make_uint4(q[0], q[1], q[2], q[3]);
     }
@@ -373,7 +396,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gate_resid_kernel(float* x, long long ldx, const __nv_bfloat16* y, long long ldy,
                                                          int rows_per_batch, int nbatch, int C, const float* gate,
-                                                         long long gate_ld, const int* seq_lens, int mask_rows) {
+                                                         long long gate_ld, const int* seq_lens, int mask_rows, const DropCfg dc) {
   const long long half = C / 2;
   const long long total = (long long)rows_per_batch * nbatch * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -381,7 +404,10 @@ __global__ void __launch_bounds__(256) gate_resid_kernel(float* x, long long ldx
     const int c = int(i - row * half) * 2;
     const int b = int(row / rows_per_batch);
     if (mask_rows && seq_lens && int(row - (long long)b * rows_per_batch) >= seq_lens[b]) continue;
-    const float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(y + row * ldy + c));
+    float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(y + row * ldy + c));
+    const unsigned long long e = (unsigned long long)row * C + c;
+    yv.x *= drop_scale(dc, e);
+    yv.y *= drop_scale(dc, e + 1);
     const float2 gv = *reinterpret_cast<const float2*>(gate + (long long)b * gate_ld + c);
     float2* p = reinterpret_cast<float2*>(x + row * ldx + c);
     float2 xv = *p;
@@ -405,6 +431,7 @@ struct GateBwdArgs {
   float* dgate;
   long long dgate_ld;
   int rows_per_cta;
+  DropCfg dc;
 };
 template <int V2>
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
@@ -433,9 +460,11 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
     for (int i = 0; i < V2; ++i) {
       const float2 d = *reinterpret_cast<const float2*>(a.dx + row * a.lddx + 2 * (lane + 32 * i));
       const float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.y + row * a.ldy + 2 * (lane + 32 * i)));
-      dg[i].x += d.x * yv.x;
-      dg[i].y += d.y * yv.y;
-      out[lane + 32 * i] = pack_bf16x2(d.x * gv[i].x, d.y * gv[i].y);
+      const unsigned long long e = (unsigned long long)row * C + 2 * (lane + 32 * i);
+      const float k0 = drop_scale(a.dc, e), k1 = drop_scale(a.dc, e + 1);
+      dg[i].x += d.x * yv.x * k0;
+      dg[i].y += d.y * yv.y * k1;
+      out[lane + 32 * i] = pack_bf16x2(d.x * gv[i].x * k0, d.y * gv[i].y * k1);
     }
   }
   cta_colsum_atomic<V2>(dg, red, a.dgate ? a.dgate + (long long)b * a.dgate_ld : nullptr);

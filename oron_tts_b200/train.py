@@ -15,8 +15,10 @@ Design:
     also yields the bias gradients), tcgen05 attention backward, row-wise backward kernels (include/oron_b200_train.h);
   * gradients of each transformer block are all-reduced (async, NCCL stream) as soon as its backward is enqueued.
 
-Dropout (p_dropout, modules.py:253, 297) is not applied: the deterministic objective is what parity is defined on
-(SURVEY §8 a17); train-mode randomness (t, span, noise, CFG drops) is drawn with torch on the device as the reference does.
+Train-mode randomness (t, span, noise, CFG drops) is drawn with torch as the reference does. Dropout (p_dropout,
+modules.py:253, 297) is a stateless mask recomputed by the backward kernels from (seed, element index); the torch
+Philox stream cannot be reproduced, so parity is defined on the deterministic objective and dropout is
+checked statistically (tests/test_train_kernels_gpu.py::test_dropout_masks).
 """
 
 from __future__ import annotations
@@ -298,6 +300,8 @@ class TrainEngine:
         self.sumsq = torch.zeros(1, device=p0.device, dtype=F32)
         self.skipped = torch.zeros(1, device=p0.device, dtype=I32)
         self.reducer = GradReducer(self.arena.g, self.arena.block_ranges)
+        drops = [m.p for m in self.cfm.backbone.modules() if isinstance(m, torch.nn.Dropout)]
+        self.dropout_p = float(drops[0]) if drops else 0.0  # Attention.to_out[1] / FeedForward.ff[2] share p_dropout
 
     def workspace(self, nb: int, tpad: int) -> TrainWorkspace:
         key = (nb, tpad)
@@ -358,7 +362,8 @@ class TrainEngine:
             time = torch.full((B,), 0.5, dtype=x1.dtype, device=dev)
             drop_audio = drop_text = False
             x0 = torch.randn(x1.shape, generator=torch.Generator(device=dev).manual_seed(0), device=dev, dtype=x1.dtype)
-        return dict(x1=x1, x0=x0, time=time, span=span, drop_audio=drop_audio, drop_text=drop_text)
+        dseed = int(torch.randint(0, 2 ** 62, ()).item()) if (training and self.dropout_p > 0) else None
+        return dict(x1=x1, x0=x0, time=time, span=span, drop_audio=drop_audio, drop_text=drop_text, dropout_seed=dseed)
 
     @torch.no_grad()
     def loss_and_grad(self, mel: torch.Tensor, text_ids: torch.Tensor, lens: torch.Tensor | None = None, *,
@@ -378,6 +383,9 @@ class TrainEngine:
         ws = self.workspace(B, tpad)
         if not accumulate:
             self.arena.g.zero_()
+        dseed = d.get("dropout_seed")
+        ws.drop_p = self.dropout_p if dseed is not None else 0.0
+        ws.drop_seed = int(dseed) if dseed is not None else 0
         self._forward(ws, phi, cond, text_ids, time, lens, d["drop_audio"], d["drop_text"])
         # loss + d(pred)
         M = self.w.n_mels
@@ -464,11 +472,12 @@ class TrainEngine:
             T.attention_fwd_lse(ws.qkv[i], ws.ao[i], ws.lse[i], nbatch=nb, rows_per_batch=tpad, heads=w.heads,
                                 seq_lens=ws.seq_lens, scale=1.0 / math.sqrt(w.dim_head))
             L.gemm(ws.ao[i], blk["wo"], ws.y1[i], epilogue=L.EPI_BF16, bias=blk["bo"], block_n=bn_big, two_sm=True, **common)
-            T.gate_resid(ws.xres, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True, **common)
+            T.gate_resid(ws.xres, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True,
+                         dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, **common)
             ws.xmid[i].copy_(ws.xres)
             L.ln_modulate(ws.xres, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], out_bf16=ws.nrm2[i], **mod)
             L.gemm(ws.nrm2[i], blk["w1"], ws.hpre[i], epilogue=L.EPI_BF16, bias=blk["b1"], block_n=bn_big, two_sm=True, **common)
-            T.act_fwd(ws.hpre[i], ws.hid[i], L.ACT_GELU_TANH)
+            T.act_fwd(ws.hpre[i], ws.hid[i], L.ACT_GELU_TANH, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1)
             L.gemm(ws.hid[i], blk["w2"], ws.y2[i], epilogue=L.EPI_BF16, bias=blk["b2"], block_n=bn_big, two_sm=True, **common)
             T.gate_resid(ws.xres, ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=None, mask_rows=False, **common)
         o = w.depth * 6 * D
@@ -503,14 +512,14 @@ class TrainEngine:
                        dgate_ld=an, **common)
             self._linear_bwd(ws, ws.g_d, ws.hid[i], blk["w2"], a.view(G, p + "ff.ff.3.weight"), a.view(G, p + "ff.ff.3.bias"),
                              ws.g_h, acc=acc)
-            T.act_bwd(ws.g_h, ws.hpre[i], ws.g_h, L.ACT_GELU_TANH)
+            T.act_bwd(ws.g_h, ws.hpre[i], ws.g_h, L.ACT_GELU_TANH, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1)
             self._linear_bwd(ws, ws.g_h, ws.nrm2[i], blk["w1"], a.view(G, p + "ff.ff.0.weight"), a.view(G, p + "ff.ff.0.bias"),
                              ws.g_d, acc=acc)
             T.ln_bwd(ws.xmid[i], ws.g_d, scale=tab[o + 4 * D:], accumulate=True, dscale=dtab[o + 4 * D:], dshift=dtab[o + 3 * D:],
                      **lnb)
             # attention branch: x += gate_msa * mask(Wo attn(...) + bo)
             T.gate_bwd(ws.dx, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=sl, dy=ws.g_d, dgate=dtab[o + 2 * D:],
-                       dgate_ld=an, **common)
+                       dgate_ld=an, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, **common)
             self._linear_bwd(ws, ws.g_d, ws.ao[i], blk["wo"], a.view(G, p + "attn.to_out.0.weight"),
                              a.view(G, p + "attn.to_out.0.bias"), ws.g_ao, acc=acc)
             T.f16_to_bf16(ws.qkv[i][:, 2 * D:], ws.vb)

@@ -367,3 +367,47 @@ def test_gemm_mn_major_operands(R, n_out, k_in, bn):
         dX = torch.zeros(R, k_in, device=DEV, dtype=BF16)
         L.gemm(dY, W, dX, epilogue=L.EPI_BF16, b_mn=True, two_sm=True, block_n=bn, rows_per_batch=R // 2, nbatch=2)
         assert _rel(dX, dY.float() @ W.float()) < 5e-3
+
+
+def test_dropout_masks():
+    """nn.Dropout inside the activation / gated-residual kernels: keep rate, 1/(1-p) scaling, and the backward kernels
+    recompute exactly the forward's mask from (seed, element index)."""
+    g = torch.Generator(device=DEV).manual_seed(13)
+    rows, C, p = 512, 1024, 0.3
+    x = (torch.randn(rows, C, device=DEV, generator=g) + 2.0).to(BF16)  # gelu(x) != 0 almost everywhere
+    ref = F.gelu(x.float(), approximate="tanh")
+    out = torch.empty_like(x)
+    T.act_fwd(x, out, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=123)
+    kept = out.float() != 0
+    live = ref.abs() > 1e-3
+    rate = float(kept[live].float().mean())
+    assert abs(rate - (1 - p)) < 5e-3, rate
+    assert _rel(out.float()[kept], (ref / (1 - p))[kept]) < 6e-3
+    out2 = torch.empty_like(x)
+    T.act_fwd(x, out2, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=123)
+    assert torch.equal(out, out2)
+    T.act_fwd(x, out2, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=124)
+    assert float(((out2.float() != 0) != kept)[live].float().mean()) > 0.3  # another seed, another mask
+    dy = torch.ones(rows, C, device=DEV, dtype=BF16)
+    dpre = torch.empty_like(x)
+    T.act_bwd(dy, x, dpre, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=123)
+    assert torch.equal((dpre.float() != 0)[live], kept[live])
+    # gated residual: x += gate * dropout(y); backward dy = gate * dx * mask / (1 - p), dgate = sum dx * dropout(y)
+    nb, rpb, Cg = 2, 128, 256
+    y = (torch.randn(nb * rpb, Cg, device=DEV, generator=g) + 3.0).to(BF16)
+    gate = torch.randn(nb, Cg, device=DEV, generator=g)
+    x0 = torch.zeros(nb * rpb, Cg, device=DEV)
+    T.gate_resid(x0, y, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=Cg, seq_lens=None, mask_rows=False, dropout_p=p,
+                 dropout_seed=7)
+    yd = x0.view(nb, rpb, Cg) / gate[:, None, :]  # = dropout(y)
+    k2 = yd.abs() > 1e-6
+    assert abs(float(k2.float().mean()) - (1 - p)) < 1.5e-2
+    assert _rel(yd[k2], (y.float().view(nb, rpb, Cg) / (1 - p))[k2]) < 1e-3
+    dx = torch.randn(nb * rpb, Cg, device=DEV, generator=g)
+    dyo = torch.empty(nb * rpb, Cg, device=DEV, dtype=BF16)
+    dg = torch.zeros(nb, Cg, device=DEV)
+    T.gate_bwd(dx, y, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=Cg, seq_lens=None, dy=dyo, dgate=dg, dgate_ld=Cg,
+               dropout_p=p, dropout_seed=7)
+    mask = k2.float() / (1 - p)
+    assert _rel(dyo, (gate[:, None, :] * dx.view(nb, rpb, Cg) * mask).reshape(-1, Cg)) < 5e-3
+    assert _rel(dg, (dx.view(nb, rpb, Cg) * y.float().view(nb, rpb, Cg) * mask).sum(1)) < 1e-4
