@@ -25,7 +25,7 @@ _ARGTYPES = {
     "oron_act_fwd": [_P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _F, _U, _P],
     "oron_act_bwd": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _F, _U, _P],
     "oron_gate_resid": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _F, _U, _P],
-    "oron_gate_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _L, _P, _L, _F, _U, _P],
+    "oron_gate_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _L, _P, _L, _P, _F, _U, _P],
     "oron_dwconv7": [_P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _L, _I, _P],
     "oron_dwconv7_wgrad": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P],
     "oron_grn_bwd_reduce": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P],
@@ -106,11 +106,11 @@ def gate_resid(x: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch:
 
 def gate_bwd(dx: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch: int, gate: torch.Tensor, gate_ld: int,
              seq_lens: torch.Tensor | None, dy: torch.Tensor, dgate: torch.Tensor | None, dgate_ld: int,
-             dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
+             dropout_p: float = 0.0, dropout_seed: int = 0, dbias: torch.Tensor | None = None) -> None:
     _check(tlib().oron_gate_bwd(_ptr(dx, F32, "dx"), _ld(dx), _ptr(y, BF16, "y"), _ld(y), rows_per_batch, nbatch,
                                 dx.shape[1], _ptr(gate, F32, "gate"), int(gate_ld), _ptr(seq_lens, torch.int32, "seq_lens"),
-                                _ptr(dy, BF16, "dy"), _ld(dy), _ptr(dgate, F32, "dgate"), int(dgate_ld), float(dropout_p),
-                                int(dropout_seed), _stream()), "oron_gate_bwd")
+                                _ptr(dy, BF16, "dy"), _ld(dy), _ptr(dgate, F32, "dgate"), int(dgate_ld),
+                                _ptr(dbias, F32, "dbias"), float(dropout_p), int(dropout_seed), _stream()), "oron_gate_bwd")
 
 
 def dwconv7(x: torch.Tensor, out: torch.Tensor, *, rows_per_batch: int, nbatch: int, seq_lens: torch.Tensor | None,

@@ -152,12 +152,12 @@ extern "C" int oron_gate_resid(float* x, int64_t ldx, const void* y_bf16, int64_
 }
 extern "C" int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
                              int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
-                             void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, float dropout_p,
+                             void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, float* dbias, float dropout_p,
                              uint64_t dropout_seed, oron_stream_t stream) {
   if (!dx || !y_bf16 || !gate || !dy_bf16) return fail(ORON_ERR_BAD_ARG, "gate_bwd: null pointer");
   const int rpc = tr_rows_for((long long)rows_per_batch * nbatch, num_sms());
   GateBwdArgs a{dx, lddx, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy, rows_per_batch, nbatch, gate, gate_ld,
-                seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld, rpc, drop_cfg(dropout_p, dropout_seed)};
+                seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld, rpc, drop_cfg(dropout_p, dropout_seed), dbias};
   dim3 grid(unsigned((rows_per_batch + rpc - 1) / rpc), unsigned(nbatch));
   DISPATCH_V2(C, (gate_bwd_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("gate_bwd");
@@ -292,9 +292,12 @@ extern "C" int oron_adamw_clip(float* p, const float* g, float* m, float* v, voi
                                float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float wd,
                                float bc1, float bc2, int32_t* skipped, oron_stream_t stream) {
   if (!p || !g || !m || !v || !sumsq || n < 0) return fail(ORON_ERR_BAD_ARG, "adamw_clip: bad argument");
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15) != 0 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) != 0)
+    return fail(ORON_ERR_BAD_ARG, "adamw_clip: arenas must be 16-byte aligned (bf16 copy: 8)");
   AdamArgs a{p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, sumsq, grad_scale, max_norm, lr, beta1, beta2, eps, wd,
              bc1, bc2, skipped};
-  adamw_clip_kernel<<<ew_blocks(n), 256, 0, ST(stream)>>>(a);
+  adamw_clip_kernel<<<ew_blocks(n / 4 + 1), 256, 0, ST(stream)>>>(a);
   return check_launch("adamw_clip");
 }
 extern "C" int oron_mask_rows_f32(float* x, int64_t ldx, int64_t rows, int32_t C, const uint8_t* row_valid,

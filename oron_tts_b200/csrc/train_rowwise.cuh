@@ -432,6 +432,7 @@ struct GateBwdArgs {
   long long dgate_ld;
   int rows_per_cta;
   DropCfg dc;
+  float* dbias;  // optional [C]: += sum over all rows of dy (the bias gradient of the Linear that produced y)
 };
 template <int V2>
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
@@ -440,11 +441,12 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
-  float2 gv[V2], dg[V2];
+  float2 gv[V2], dg[V2], db[V2];
 #pragma unroll
   for (int i = 0; i < V2; ++i) {
     gv[i] = *reinterpret_cast<const float2*>(a.gate + (long long)b * a.gate_ld + 2 * (lane + 32 * i));
     dg[i] = make_float2(0.f, 0.f);
+    db[i] = make_float2(0.f, 0.f);
   }
   for (int k = 0; k < a.rows_per_cta / 8; ++k) {
     const int t = blockIdx.x * a.rows_per_cta + warp + 8 * k;
@@ -464,10 +466,14 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
       const float k0 = drop_scale(a.dc, e), k1 = drop_scale(a.dc, e + 1);
       dg[i].x += d.x * yv.x * k0;
       dg[i].y += d.y * yv.y * k1;
-      out[lane + 32 * i] = pack_bf16x2(d.x * gv[i].x * k0, d.y * gv[i].y * k1);
+      const float o0 = d.x * gv[i].x * k0, o1 = d.y * gv[i].y * k1;
+      db[i].x += o0;
+      db[i].y += o1;
+      out[lane + 32 * i] = pack_bf16x2(o0, o1);
     }
   }
   cta_colsum_atomic<V2>(dg, red, a.dgate ? a.dgate + (long long)b * a.dgate_ld : nullptr);
+  if (a.dbias != nullptr) cta_colsum_atomic<V2>(db, red, a.dbias);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -864,15 +870,35 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(const AdamArgs a) {
   const float step = a.lr / a.bc1;
   const float rs2 = rsqrtf(a.bc2);
   const float decay = 1.0f - a.lr * a.wd;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-    const float g = a.g[i] * coef;
-    float p = a.p[i] * decay;
-    const float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
-    const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+  auto upd = [&](float& p, float gi, float& m, float& v) {
+    const float g = gi * coef;
+    p *= decay;
+    m = a.beta1 * m + (1.0f - a.beta1) * g;
+    v = a.beta2 * v + (1.0f - a.beta2) * g * g;
     p -= step * m / (sqrtf(v) * rs2 + a.eps);
+  };
+  const long long n4 = a.n / 4;  // the arenas are 16-byte aligned and padded: four elements per thread
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(a.p)[i];
+    const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    upd(p.x, g.x, m.x, v.x);
+    upd(p.y, g.y, m.y, v.y);
+    upd(p.z, g.z, m.z, v.z);
+    upd(p.w, g.w, m.w, v.w);
+    reinterpret_cast<float4*>(a.p)[i] = p;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+    if (a.pb) reinterpret_cast<uint2*>(a.pb)[i] = make_uint2(pack_bf16x2(p.x, p.y), pack_bf16x2(p.z, p.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < int(a.n - n4 * 4)) {
+    const long long i = n4 * 4 + threadIdx.x;
+    float p = a.p[i], m = a.m[i], v = a.v[i];
+    upd(p, a.g[i], m, v);
+    a.p[i] = p;
     a.m[i] = m;
     a.v[i] = v;
-    a.p[i] = p;
     if (a.pb) a.pb[i] = __float2bfloat16(p);
   }
 }

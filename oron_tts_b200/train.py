@@ -54,7 +54,7 @@ class ParamArena:
         # stacked AdaLN projections first (one contiguous [depth*6D + 2D, D] operand), then their biases
         order += [f"{bb}transformer_blocks.{i}.attn_norm.linear.weight" for i in range(depth)] + [bb + "norm_out.linear.weight"]
         order += [f"{bb}transformer_blocks.{i}.attn_norm.linear.bias" for i in range(depth)] + [bb + "norm_out.linear.bias"]
-        self.block_ranges: list[tuple[int, int]] = []
+        self.block_ranges: list[list[tuple[int, int]]] = []
         per_block = ["attn.to_q.weight", "attn.to_k.weight", "attn.to_v.weight", "attn.to_q.bias", "attn.to_k.bias",
                      "attn.to_v.bias", "attn.to_out.0.weight", "attn.to_out.0.bias", "ff.ff.0.weight", "ff.ff.0.bias",
                      "ff.ff.3.weight", "ff.ff.3.bias"]
@@ -72,10 +72,13 @@ class ParamArena:
             self.offsets[k] = off
             off += _rup(named[k].numel(), self.ALIGN)
         self.numel = off
-        for i in range(depth):
+        for i in range(depth):  # what is final once block i's backward has run: its own tensors + its AdaLN projection
             first = f"{bb}transformer_blocks.{i}.{per_block[0]}"
             last = f"{bb}transformer_blocks.{i}.{per_block[-1]}"
-            self.block_ranges.append((self.offsets[first], self.offsets[last] + _rup(named[last].numel(), self.ALIGN)))
+            aw, ab = f"{bb}transformer_blocks.{i}.attn_norm.linear.weight", f"{bb}transformer_blocks.{i}.attn_norm.linear.bias"
+            self.block_ranges.append([(self.offsets[first], self.offsets[last] + _rup(named[last].numel(), self.ALIGN)),
+                                      (self.offsets[aw], self.offsets[aw] + _rup(named[aw].numel(), self.ALIGN)),
+                                      (self.offsets[ab], self.offsets[ab] + _rup(named[ab].numel(), self.ALIGN))])
         self.p = torch.zeros(off, device=dev, dtype=F32)
         self.g = torch.zeros(off, device=dev, dtype=F32)
         self.m = torch.zeros(off, device=dev, dtype=F32)
@@ -106,7 +109,7 @@ class GradReducer:
     reduces everything outside the block ranges (embeddings, AdaLN projections, output head). The division by the world
     size is folded into the optimizer kernel. No-op without an initialised process group."""
 
-    def __init__(self, g: torch.Tensor, block_ranges: list[tuple[int, int]], overlap: bool = True):
+    def __init__(self, g: torch.Tensor, block_ranges: list[list[tuple[int, int]]], overlap: bool = True):
         self.g, self.block_ranges, self.overlap = g, block_ranges, overlap
         self._pending: list = []
 
@@ -120,8 +123,8 @@ class GradReducer:
         import torch.distributed as dist
 
         if self._world() > 1 and self.overlap:
-            lo, hi = self.block_ranges[i]
-            self._pending.append((dist.all_reduce(self.g[lo:hi], op=dist.ReduceOp.SUM, async_op=True), lo, hi))
+            for lo, hi in self.block_ranges[i]:
+                self._pending.append((dist.all_reduce(self.g[lo:hi], op=dist.ReduceOp.SUM, async_op=True), lo, hi))
 
     def finish(self) -> None:
         import torch.distributed as dist
@@ -331,7 +334,8 @@ class TrainEngine:
     def _linear_bwd(self, ws, dy, x_saved, w, gw, gb, dx_out, *, acc=False):
         """Backward of y = x W^T + b for [R, .] activations: bias and weight gradients into the arena, data gradient.
         No transposed copies: the tcgen05 GEMM reads the row-major operands MN-major (oron_gemm_desc.a/b_mn_major)."""
-        T.colsum(dy, gb)
+        if gb is not None:  # None: the kernel that produced dy already summed its columns
+            T.colsum(dy, gb)
         self._wgrad(dy, x_saved, gw, accumulate=acc)
         if dx_out is not None:
             self._dgrad(ws, dy, w, dx_out)
@@ -502,6 +506,9 @@ class TrainEngine:
         o = w.depth * 6 * D
         lnb = dict(eps=1e-6, mod_ld=an, add_one=True, seq_lens=sl, dx=ws.dx, dmod_ld=an, **common)
         T.ln_bwd(ws.xres, ws.g_d, scale=tab[o:], accumulate=False, dscale=dtab[o:], dshift=dtab[o + D:], **lnb)
+        gada_w = a.view(G, "transformer_blocks.0.attn_norm.linear.weight", (an, D), an * D)
+        gada_b = a.view(G, "transformer_blocks.0.attn_norm.linear.bias", (an,), an)
+        T.skinny_wgrad(ws.dtab[:, o:], ws.ts32, gada_w[o:], gada_b[o:], accumulate=acc)  # norm_out.linear (modules.py:232)
         cos, sin = w.rope(tpad)
         for i in reversed(range(w.depth)):
             blk = w.blocks[i]
@@ -509,9 +516,8 @@ class TrainEngine:
             o = i * 6 * D
             # FFN branch: x += gate_mlp * (W2 gelu(W1 n + b1) + b2)
             T.gate_bwd(ws.dx, ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=sl, dy=ws.g_d, dgate=dtab[o + 5 * D:],
-                       dgate_ld=an, **common)
-            self._linear_bwd(ws, ws.g_d, ws.hid[i], blk["w2"], a.view(G, p + "ff.ff.3.weight"), a.view(G, p + "ff.ff.3.bias"),
-                             ws.g_h, acc=acc)
+                       dgate_ld=an, dbias=a.view(G, p + "ff.ff.3.bias"), **common)
+            self._linear_bwd(ws, ws.g_d, ws.hid[i], blk["w2"], a.view(G, p + "ff.ff.3.weight"), None, ws.g_h, acc=acc)
             T.act_bwd(ws.g_h, ws.hpre[i], ws.g_h, L.ACT_GELU_TANH, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1)
             self._linear_bwd(ws, ws.g_h, ws.nrm2[i], blk["w1"], a.view(G, p + "ff.ff.0.weight"), a.view(G, p + "ff.ff.0.bias"),
                              ws.g_d, acc=acc)
@@ -519,9 +525,9 @@ class TrainEngine:
                      **lnb)
             # attention branch: x += gate_msa * mask(Wo attn(...) + bo)
             T.gate_bwd(ws.dx, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=sl, dy=ws.g_d, dgate=dtab[o + 2 * D:],
-                       dgate_ld=an, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, **common)
-            self._linear_bwd(ws, ws.g_d, ws.ao[i], blk["wo"], a.view(G, p + "attn.to_out.0.weight"),
-                             a.view(G, p + "attn.to_out.0.bias"), ws.g_ao, acc=acc)
+                       dgate_ld=an, dbias=a.view(G, p + "attn.to_out.0.bias"), dropout_p=ws.drop_p,
+                       dropout_seed=ws.drop_seed + 4 * i, **common)
+            self._linear_bwd(ws, ws.g_d, ws.ao[i], blk["wo"], a.view(G, p + "attn.to_out.0.weight"), None, ws.g_ao, acc=acc)
             T.f16_to_bf16(ws.qkv[i][:, 2 * D:], ws.vb)
             T.attention_bwd(ws.qkv[i][:, : 2 * D], ws.vb, ws.ao[i], ws.g_ao, ws.g_qkv, nbatch=nb, rows_per_batch=tpad,
                             heads=w.heads, seq_lens=sl, scale=1.0 / math.sqrt(w.dim_head), rope_cos=cos, rope_sin=sin,
@@ -529,6 +535,9 @@ class TrainEngine:
             self._linear_bwd(ws, ws.g_qkv, ws.nrm1[i], blk["wqkv"], a.view(G, p + "attn.to_q.weight", (3 * D, D), 3 * D * D),
                              a.view(G, p + "attn.to_q.bias", (3 * D,), 3 * D), ws.g_d, acc=acc)
             T.ln_bwd(ws.xin[i], ws.g_d, scale=tab[o + D:], accumulate=True, dscale=dtab[o + D:], dshift=dtab[o:], **lnb)
+            # this block's six modulation gradients are final: its AdaLN projection (modules.py:214) gets its gradient now,
+            # so that it travels with the block's all-reduce bucket
+            T.skinny_wgrad(ws.dtab[:, o:o + 6 * D], ws.ts32, gada_w[o:o + 6 * D], gada_b[o:o + 6 * D], accumulate=acc)
             self._block_done(i)
         # -- ConvPositionEmbedding (modules.py:131-141) + residual (dit.py:54): xres = h0 + mask * mish(z2)
         c1, c2 = w.conv_pos
@@ -574,9 +583,6 @@ class TrainEngine:
         T.mask_rows(ws.dxt, ws.row_valid)
         T.text_embed_bwd(ws.ids, ws.drop, ws.dxt, a.view(G, "text_embed.text_embed.weight"), rows_per_batch=tpad, nb=nb)
         # -- AdaLN projections (stacked) and the timestep MLP
-        gada_w = a.view(G, "transformer_blocks.0.attn_norm.linear.weight", (an, D), an * D)
-        gada_b = a.view(G, "transformer_blocks.0.attn_norm.linear.bias", (an,), an)
-        T.skinny_wgrad(ws.dtab, ws.ts32, gada_w, gada_b, accumulate=acc)
         ws.dts.zero_()
         T.skinny_dgrad(ws.dtab, w.ada_w, ws.dts)
         T.act_bwd(ws.dts, ws.pre2, ws.dpre2, L.ACT_SILU)

@@ -103,7 +103,7 @@ def _reducer_worker(rank, world, port, q):
     model = F5TTS.from_config({"model": dict(dim=128, depth=3, heads=2, text_dim=64, conv_layers=1)})
     arena = ParamArena(model)  # CPU arenas: parameters and .grad become views, state_dict unchanged
     ok = all(p.data_ptr() >= arena.p.data_ptr() and p.grad.data_ptr() >= arena.g.data_ptr() for p in model.parameters())
-    ok = ok and len(arena.block_ranges) == 3 and all(hi > lo for lo, hi in arena.block_ranges)
+    ok = ok and len(arena.block_ranges) == 3 and all(hi > lo for rs in arena.block_ranges for lo, hi in rs)
     # fused operands are contiguous views: q | k | v weights of a block, and the stacked AdaLN projections
     o = arena.offsets
     pre = "cfm.backbone.transformer_blocks.1.attn."

@@ -125,8 +125,10 @@ def test_gate_resid_and_bwd():
     dx = torch.randn(nb * rpb, C, device=DEV, generator=g)
     dy = torch.empty(nb * rpb, C, device=DEV, dtype=BF16)
     dg = torch.zeros(nb, C, device=DEV)
-    T.gate_bwd(dx, y, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=3 * C, seq_lens=sl, dy=dy, dgate=dg, dgate_ld=C)
+    dbias = torch.zeros(C, device=DEV)
+    T.gate_bwd(dx, y, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=3 * C, seq_lens=sl, dy=dy, dgate=dg, dgate_ld=C, dbias=dbias)
     dxm = dx * m[:, None]
+    assert _rel(dbias, (gate[:, None, :] * dxm.view(nb, rpb, C)).sum((0, 1))) < 1e-5
     assert _rel(dy, (gate[:, None, :] * dxm.view(nb, rpb, C)).reshape(-1, C)) < 4e-3
     assert _rel(dg, (dxm * y.float()).view(nb, rpb, C).sum(1)) < 1e-5
 
