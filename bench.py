@@ -200,7 +200,7 @@ def run_ours(args) -> dict:
         with torch.inference_mode():
             out["roofline"] = roofline(eng, cfm, ref_mel, ids, dur, lens)
         if not args.no_cpu_baseline and world == 1:  # contract: the CPU baseline is reported on rank 0 at N=1 only
-            out["cpu_baseline"] = cpu_baseline(nfe=1)
+            out["cpu_baseline"] = cpu_baseline(nfe=8)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -474,7 +474,7 @@ def run_reference(args) -> dict:
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     for _ in range(max(0, min(args.warmup, 1) - 1)):
         cpu_baseline(1)
-    cb = cpu_baseline(max(1, min(args.steps, 3)))
+    cb = cpu_baseline(max(1, min(args.steps, 8)))
     return {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(cb["s_per_nfe"] * STEPS_NFE * 1e3, 1), "higher_is_better": True,

@@ -54,13 +54,14 @@ int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const void* pre,
                  oron_stream_t stream);
 
 /* Gated residual of DiTBlock (modules.py:338, 343) un-fused for training:
- *   fwd: x[r, :] += gate[b, :] * y[r, :]   (rows t >= seq_lens[b]: y taken as 0 when mask_rows, modules.py:281-282)
+ *   fwd: out[r, :] = x[r, :] + gate[b, :] * y[r, :]   (rows t >= seq_lens[b]: y taken as 0 when mask_rows,
+ *        modules.py:281-282); out may be x (in place) or the next saved residual-stream buffer
  *   bwd: dy[r, :] = gate[b, :] * dx[r, :] (bf16; zero rows beyond seq_lens) ; dgate[b, :] += sum_t dx * y ;
  *        dbias[:] += sum over all rows of dy (optional: the bias gradient of the Linear that produced y)
  * dropout_p > 0: y is first passed through nn.Dropout (Attention.to_out[1], modules.py:253), same stateless mask as above. */
-int oron_gate_resid(float* x, int64_t ldx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch, int32_t nbatch,
+int oron_gate_resid(const float* x, int64_t ldx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch, int32_t nbatch,
                     int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens, int32_t mask_rows,
-                    float dropout_p, uint64_t dropout_seed, oron_stream_t stream);
+                    float dropout_p, uint64_t dropout_seed, float* out, int64_t ldo, oron_stream_t stream);
 int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
                   int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
                   void* dy_bf16, int64_t lddy, float* dgate, int64_t dgate_ld, float* dbias, float dropout_p,

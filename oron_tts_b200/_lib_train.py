@@ -24,7 +24,7 @@ _ARGTYPES = {
     "oron_ln_bwd": [_P, _L, _P, _L, _I, _I, _I, _F, _P, _L, _I, _P, _P, _L, _I, _P, _P, _L, _P],
     "oron_act_fwd": [_P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _F, _U, _P],
     "oron_act_bwd": [_P, _I, _L, _P, _I, _L, _L, _I, _I, _P, _I, _L, _I, _P, _F, _U, _P],
-    "oron_gate_resid": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _F, _U, _P],
+    "oron_gate_resid": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _F, _U, _P, _L, _P],
     "oron_gate_bwd": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _P, _L, _P, _L, _P, _F, _U, _P],
     "oron_dwconv7": [_P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _L, _I, _P],
     "oron_dwconv7_wgrad": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P],
@@ -98,10 +98,14 @@ def act_bwd(dy: torch.Tensor, pre: torch.Tensor, out: torch.Tensor, act: int, *,
 
 
 def gate_resid(x: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch: int, gate: torch.Tensor, gate_ld: int,
-               seq_lens: torch.Tensor | None, mask_rows: bool, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
+               seq_lens: torch.Tensor | None, mask_rows: bool, dropout_p: float = 0.0, dropout_seed: int = 0,
+               out: torch.Tensor | None = None) -> None:
+    """out (default: x, in place) = x + gate[b] * dropout(y)."""
+    o = x if out is None else out
     _check(tlib().oron_gate_resid(_ptr(x, F32, "x"), _ld(x), _ptr(y, BF16, "y"), _ld(y), rows_per_batch, nbatch, x.shape[1],
                                   _ptr(gate, F32, "gate"), int(gate_ld), _ptr(seq_lens, torch.int32, "seq_lens"),
-                                  int(bool(mask_rows)), float(dropout_p), int(dropout_seed), _stream()), "oron_gate_resid")
+                                  int(bool(mask_rows)), float(dropout_p), int(dropout_seed), _ptr(o, F32, "out"), _ld(o),
+                                  _stream()), "oron_gate_resid")
 
 
 def gate_bwd(dx: torch.Tensor, y: torch.Tensor, *, rows_per_batch: int, nbatch: int, gate: torch.Tensor, gate_ld: int,

@@ -140,14 +140,15 @@ extern "C" int oron_act_bwd(const void* dy, int32_t dy_f32, int64_t ld_dy, const
   return check_launch("act_bwd");
 }
 
-extern "C" int oron_gate_resid(float* x, int64_t ldx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
+extern "C" int oron_gate_resid(const float* x, int64_t ldx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,
                                int32_t nbatch, int32_t C, const float* gate, int64_t gate_ld, const int32_t* seq_lens,
-                               int32_t mask_rows, float dropout_p, uint64_t dropout_seed, oron_stream_t stream) {
-  if (!x || !y_bf16 || !gate || (C & 1)) return fail(ORON_ERR_BAD_ARG, "gate_resid: bad argument");
+                               int32_t mask_rows, float dropout_p, uint64_t dropout_seed, float* out, int64_t ldo,
+                               oron_stream_t stream) {
+  if (!x || !y_bf16 || !gate || !out || (C & 1)) return fail(ORON_ERR_BAD_ARG, "gate_resid: bad argument");
   const long long total = (long long)rows_per_batch * nbatch * (C / 2);
   gate_resid_kernel<<<ew_blocks(total), 256, 0, ST(stream)>>>(x, ldx, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy,
                                                               rows_per_batch, nbatch, C, gate, gate_ld, seq_lens, mask_rows,
-                                                              drop_cfg(dropout_p, dropout_seed));
+                                                              drop_cfg(dropout_p, dropout_seed), out, ldo);
   return check_launch("gate_resid");
 }
 extern "C" int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, int64_t ldy, int32_t rows_per_batch,

@@ -394,26 +394,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // gated residual (training forward) and its backward
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gate_resid_kernel(float* x, long long ldx, const __nv_bfloat16* y, long long ldy,
+__global__ void __launch_bounds__(256) gate_resid_kernel(const float* x, long long ldx, const __nv_bfloat16* y, long long ldy,
                                                          int rows_per_batch, int nbatch, int C, const float* gate,
-                                                         long long gate_ld, const int* seq_lens, int mask_rows, const DropCfg dc) {
+                                                         long long gate_ld, const int* seq_lens, int mask_rows, const DropCfg dc,
+                                                         float* out, long long ldo) {
   const long long half = C / 2;
   const long long total = (long long)rows_per_batch * nbatch * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / half;
     const int c = int(i - row * half) * 2;
     const int b = int(row / rows_per_batch);
-    if (mask_rows && seq_lens && int(row - (long long)b * rows_per_batch) >= seq_lens[b]) continue;
-    float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(y + row * ldy + c));
-    const unsigned long long e = (unsigned long long)row * C + c;
-    yv.x *= drop_scale(dc, e);
-    yv.y *= drop_scale(dc, e + 1);
-    const float2 gv = *reinterpret_cast<const float2*>(gate + (long long)b * gate_ld + c);
-    float2* p = reinterpret_cast<float2*>(x + row * ldx + c);
-    float2 xv = *p;
-    xv.x = fmaf(gv.x, yv.x, xv.x);
-    xv.y = fmaf(gv.y, yv.y, xv.y);
-    *p = xv;
+    float2 xv = *reinterpret_cast<const float2*>(x + row * ldx + c);
+    if (!(mask_rows && seq_lens && int(row - (long long)b * rows_per_batch) >= seq_lens[b])) {
+      float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(y + row * ldy + c));
+      const unsigned long long e = (unsigned long long)row * C + c;
+      yv.x *= drop_scale(dc, e);
+      yv.y *= drop_scale(dc, e + 1);
+      const float2 gv = *reinterpret_cast<const float2*>(gate + (long long)b * gate_ld + c);
+      xv.x = fmaf(gv.x, yv.x, xv.x);
+      xv.y = fmaf(gv.y, yv.y, xv.y);
+    }
+    *reinterpret_cast<float2*>(out + row * ldo + c) = xv;
   }
 }
 

@@ -248,9 +248,9 @@ class TrainWorkspace:
         self.c0, self.h0, self.h0b = z(R, D), z(R, D), z(R, D, dt=BF16)
         self.z1, self.c1, self.z2, self.m2 = (z(R, D, dt=BF16) for _ in range(4))
         self.ones = torch.ones(D, device=dev, dtype=F32)
-        self.xres = z(R, D)
         nd = w.depth
-        self.xin = [z(R, D) for _ in range(nd)]
+        self.xin = [z(R, D) for _ in range(nd + 1)]  # residual stream entering block i; [nd] = after the last block
+        self.xres = self.xin[nd]
         self.xmid = [z(R, D) for _ in range(nd)]
         self.nrm1 = [z(R, D, dt=BF16) for _ in range(nd)]
         self.nrm2 = [z(R, D, dt=BF16) for _ in range(nd)]
@@ -450,8 +450,7 @@ class TrainEngine:
         T.act_fwd(ws.z1, ws.c1, T.ACT_MISH, rows_per_batch=tpad, seq_lens=ws.seq_lens)
         L.gemm(ws.c1, c2["w"], ws.z2, epilogue=L.EPI_BF16, bias=c2["b"], **conv(c2))
         T.act_fwd(ws.z2, ws.m2, T.ACT_MISH, rows_per_batch=tpad, seq_lens=ws.seq_lens)
-        ws.xres.copy_(ws.h0)
-        T.gate_resid(ws.xres, ws.m2, gate=ws.ones, gate_ld=0, seq_lens=None, mask_rows=False, **common)
+        T.gate_resid(ws.h0, ws.m2, gate=ws.ones, gate_ld=0, seq_lens=None, mask_rows=False, out=ws.xin[0], **common)
         # -- timestep conditioning (modules.py:39-62) and every AdaLN projection (modules.py:214, 232)
         ws.tvals.copy_(time)
         L.time_sinusoid(ws.tvals, ws.tfeat)
@@ -469,21 +468,21 @@ class TrainEngine:
         mod = dict(mod_ld=an, mod_nb=nb, add_one=True, eps=1e-6, **common)
         for i, blk in enumerate(w.blocks):
             o = i * 6 * D
-            ws.xin[i].copy_(ws.xres)
-            L.ln_modulate(ws.xres, scale=tab[o + D:], shift=tab[o:], out_bf16=ws.nrm1[i], **mod)
+            # the residual stream is never copied: each gated residual writes the next saved buffer
+            L.ln_modulate(ws.xin[i], scale=tab[o + D:], shift=tab[o:], out_bf16=ws.nrm1[i], **mod)
             L.gemm(ws.nrm1[i], blk["wqkv"], ws.qkv[i], epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
                    rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
             T.attention_fwd_lse(ws.qkv[i], ws.ao[i], ws.lse[i], nbatch=nb, rows_per_batch=tpad, heads=w.heads,
                                 seq_lens=ws.seq_lens, scale=1.0 / math.sqrt(w.dim_head))
             L.gemm(ws.ao[i], blk["wo"], ws.y1[i], epilogue=L.EPI_BF16, bias=blk["bo"], block_n=bn_big, two_sm=True, **common)
-            T.gate_resid(ws.xres, ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True,
-                         dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, **common)
-            ws.xmid[i].copy_(ws.xres)
-            L.ln_modulate(ws.xres, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], out_bf16=ws.nrm2[i], **mod)
+            T.gate_resid(ws.xin[i], ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True,
+                         dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, out=ws.xmid[i], **common)
+            L.ln_modulate(ws.xmid[i], scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], out_bf16=ws.nrm2[i], **mod)
             L.gemm(ws.nrm2[i], blk["w1"], ws.hpre[i], epilogue=L.EPI_BF16, bias=blk["b1"], block_n=bn_big, two_sm=True, **common)
             T.act_fwd(ws.hpre[i], ws.hid[i], L.ACT_GELU_TANH, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1)
             L.gemm(ws.hid[i], blk["w2"], ws.y2[i], epilogue=L.EPI_BF16, bias=blk["b2"], block_n=bn_big, two_sm=True, **common)
-            T.gate_resid(ws.xres, ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=None, mask_rows=False, **common)
+            T.gate_resid(ws.xmid[i], ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=None, mask_rows=False,
+                         out=ws.xin[i + 1], **common)
         o = w.depth * 6 * D
         L.ln_modulate(ws.xres, scale=tab[o:], shift=tab[o + D:], out_bf16=ws.nrmf, **mod)
         L.gemm(ws.nrmf, w.wp, ws.v, epilogue=L.EPI_F32, bias=w.bp, block_n=128, **common)

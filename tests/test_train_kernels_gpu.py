@@ -122,6 +122,9 @@ def test_gate_resid_and_bwd():
     T.gate_resid(x1, y, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=3 * C, seq_lens=sl, mask_rows=True)
     ref = x + (gate[:, None, :] * y.float().view(nb, rpb, C)).reshape(-1, C) * m[:, None]
     assert _rel(x1, ref) < 1e-6
+    x2 = torch.empty_like(x)
+    T.gate_resid(x, y, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=3 * C, seq_lens=sl, mask_rows=True, out=x2)
+    assert torch.equal(x2, x1)  # out of place (the training forward writes the next saved residual buffer)
     dx = torch.randn(nb * rpb, C, device=DEV, generator=g)
     dy = torch.empty(nb * rpb, C, device=DEV, dtype=BF16)
     dg = torch.zeros(nb, C, device=DEV)
