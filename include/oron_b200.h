@@ -159,13 +159,16 @@ int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_batch, int32_
                      float* out_f32, int64_t ldo, oron_stream_t stream);
 
 /*
- * One Euler step with classifier-free guidance (flow.py:266-267, 295-299):
+ * One ODE update with classifier-free guidance (flow.py:266-267, 295-299):
  *   v = v_c + (v_c - v_u) * cfg ; x += v * dt[*step_ptr] ; traj[*step_ptr + 1] = x ; ++*step_ptr
- * and refresh of the bf16 operand of the next step's input projection.
+ * and refresh of the bf16 operand of the next evaluation's input projection.
+ * method 0: Euler (the reference). method 1: explicit midpoint rule behind the same call (the device counter then counts
+ * velocity evaluations e, interval i = e / 2): even e writes only the operand x + v * dt[i] / 2, odd e does
+ * x += v * dt[i] and fills trajectory slot i + 1. One launch per evaluation either way (CUDA-graph replayable).
  */
 int oron_cfg_euler_step(float* x, const float* v, int64_t ldv, int32_t nb, int32_t rows_per_batch,
                         int32_t n_mels, int32_t has_uncond, float cfg, const float* dt, int32_t* step_ptr,
-                        void* xb_bf16, int64_t ldxb, float* traj, float* v_out, oron_stream_t stream);
+                        void* xb_bf16, int64_t ldxb, float* traj, float* v_out, int32_t method, oron_stream_t stream);
 
 /* fp32 [rows, C] -> bf16 [reps*rows, ldo] (replicated `reps` times along rows). */
 int oron_cast_rows_bf16(const float* x, int64_t ldx, int64_t rows, int32_t C, void* out_bf16, int64_t ldo,

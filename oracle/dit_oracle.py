@@ -212,7 +212,9 @@ def seeded_noise(durations: list[int], n_mels: int, seed: int | None) -> Tensor:
 @torch.inference_mode()
 def cfm_sample(sd: SD, cond: Tensor, text_ids: Tensor, duration: Tensor | int, *, lens: Tensor | None = None,
                steps: int = 32, cfg_strength: float = 1.0, sway_sampling_coef: float | None = None,
-               seed: int | None = None, y0: Tensor | None = None, return_velocity: bool = False):
+               seed: int | None = None, y0: Tensor | None = None, return_velocity: bool = False, method: str = "euler"):
+    """method "midpoint": explicit midpoint rule on the same schedule (an extension over the reference's Euler loop,
+    flow.py:290-299) -- x_{i+1} = x_i + dt_i v(x_i + dt_i/2 v(x_i, t_i), t_i + dt_i/2)."""
     d = model_dims(sd)
     B, T_ref, _ = cond.shape
     lens = torch.full((B,), T_ref, dtype=torch.long) if lens is None else lens.long()
@@ -229,16 +231,21 @@ def cfm_sample(sd: SD, cond: Tensor, text_ids: Tensor, duration: Tensor | int, *
     cache: dict = {}
     x = y0
     traj, vels = [y0], []
-    for i in range(steps):
-        tb = t[i].expand(B)
+    def velocity(xx: Tensor, tt: Tensor) -> Tensor:
+        tb = tt.expand(B)
         if cfg_strength < 1e-5:
-            v = dit_forward(sd, x, step_cond, text_ids, tb, attn_mask, text_cache=cache)
-        else:
-            both = dit_forward(sd, x, step_cond, text_ids, tb, attn_mask, cfg_infer=True, text_cache=cache)
-            vc, vu = both[:B], both[B:]
-            v = vc + (vc - vu) * cfg_strength
+            return dit_forward(sd, xx, step_cond, text_ids, tb, attn_mask, text_cache=cache)
+        both = dit_forward(sd, xx, step_cond, text_ids, tb, attn_mask, cfg_infer=True, text_cache=cache)
+        vc, vu = both[:B], both[B:]
+        return vc + (vc - vu) * cfg_strength
+
+    for i in range(steps):
+        dt = t[i + 1] - t[i]
+        v = velocity(x, t[i])
+        if method == "midpoint":
+            v = velocity(x + v * (0.5 * dt), 0.5 * (t[i] + t[i + 1]))
         vels.append(v)
-        x = x + v * (t[i + 1] - t[i])
+        x = x + v * dt
         traj.append(x)
     out = torch.where(cond_mask[..., None], cond, x)
     if return_velocity:

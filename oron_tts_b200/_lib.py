@@ -123,7 +123,7 @@ def lib() -> ctypes.CDLL:
                                    c_int64, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
                                    c_void_p]
     L.oron_cfg_euler_step.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_float,
-                                      c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+                                      c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p]
     L.oron_cast_rows_bf16.argtypes = [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p]
     L.oron_time_sinusoid.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_void_p]
     L.oron_text_embed_front.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
@@ -313,13 +313,13 @@ def ln_modulate(x: torch.Tensor, *, rows_per_batch: int, nbatch: int, eps: float
 
 def cfg_euler_step(x: torch.Tensor, v: torch.Tensor, *, nb: int, rows_per_batch: int, n_mels: int,
                    has_uncond: bool, cfg: float, dt: torch.Tensor, step_ptr: torch.Tensor, xb: torch.Tensor,
-                   traj: torch.Tensor | None = None, v_out: torch.Tensor | None = None) -> None:
+                   traj: torch.Tensor | None = None, v_out: torch.Tensor | None = None, method: int = 0) -> None:
     _check(
         lib().oron_cfg_euler_step(_ptr(x, torch.float32, "x"), _ptr(v, torch.float32, "v"), _ld(v), nb,
                                   rows_per_batch, n_mels, int(bool(has_uncond)), float(cfg),
                                   _ptr(dt, torch.float32, "dt"), _ptr(step_ptr, torch.int32, "step_ptr"),
                                   _ptr(xb, torch.bfloat16, "xb"), _ld(xb), _ptr(traj, torch.float32, "traj"),
-                                  _ptr(v_out, torch.float32, "v_out"), _stream()),
+                                  _ptr(v_out, torch.float32, "v_out"), int(method), _stream()),
         "oron_cfg_euler_step",
     )
 

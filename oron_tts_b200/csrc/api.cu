@@ -422,12 +422,14 @@ extern "C" int oron_ln_modulate(const float* x, int64_t ldx, int32_t rows_per_ba
 
 extern "C" int oron_cfg_euler_step(float* x, const float* v, int64_t ldv, int32_t nb, int32_t rows_per_batch,
                                    int32_t n_mels, int32_t has_uncond, float cfg, const float* dt, int32_t* step_ptr,
-                                   void* xb_bf16, int64_t ldxb, float* traj, float* v_out, oron_stream_t stream) {
+                                   void* xb_bf16, int64_t ldxb, float* traj, float* v_out, int32_t method,
+                                   oron_stream_t stream) {
   if (!x || !v || !dt || !step_ptr || !xb_bf16) return fail(ORON_ERR_BAD_ARG, "cfg_euler_step: null pointer");
+  if (method != 0 && method != 1) return fail(ORON_ERR_BAD_ARG, "cfg_euler_step: method must be 0 (Euler) or 1 (midpoint)");
   EulerArgs a;
   a.x = x; a.v = v; a.ldv = ldv; a.nb = nb; a.rows_per_batch = rows_per_batch; a.n_mels = n_mels;
   a.has_uncond = has_uncond; a.cfg = cfg; a.dt = dt; a.step_ptr = step_ptr;
-  a.xb = reinterpret_cast<__nv_bfloat16*>(xb_bf16); a.ldxb = ldxb; a.traj = traj; a.v_out = v_out;
+  a.xb = reinterpret_cast<__nv_bfloat16*>(xb_bf16); a.ldxb = ldxb; a.traj = traj; a.v_out = v_out; a.midpoint = method;
   const long long total = (long long)nb * rows_per_batch * n_mels;
   int blocks = int((total + 255) / 256);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();

@@ -129,6 +129,8 @@ struct EulerArgs {
   long long ldxb;
   float* traj;           // [steps+1, nb*rows_per_batch, n_mels] or nullptr; slot step+1 is written
   float* v_out;          // optional [nb*rows_per_batch, n_mels]: the guided velocity (parity checks)
+  int midpoint;          // 1: explicit midpoint rule. The counter counts EVALUATIONS e: interval i = e >> 1; even e:
+                         // the operand becomes x + v dt_i / 2 (x itself untouched), odd e: x += v dt_i, trajectory slot i + 1
 };
 
 __global__ void __launch_bounds__(256) cfg_euler_kernel(const EulerArgs a) {
@@ -136,8 +138,10 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const EulerArgs a) {
   pdl_wait();
   const long long rows = (long long)a.nb * a.rows_per_batch;
   const long long total = rows * a.n_mels;
-  const int step = *a.step_ptr;
-  const float dt = a.dt[step];
+  const int e = *a.step_ptr;
+  const int step = a.midpoint ? (e >> 1) : e;
+  const bool half_step = a.midpoint && (e & 1) == 0;  // first evaluation of a midpoint interval
+  const float dt = half_step ? 0.5f * a.dt[step] : a.dt[step];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / a.n_mels;
@@ -149,9 +153,11 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const EulerArgs a) {
       vv = vc + (vc - vu) * a.cfg;
     }
     const float xn = a.x[i] + vv * dt;
-    a.x[i] = xn;
+    if (!half_step) {
+      a.x[i] = xn;
+      if (a.traj) a.traj[(long long)(step + 1) * total + i] = xn;
+    }
     if (a.v_out) a.v_out[i] = vv;
-    if (a.traj) a.traj[(long long)(step + 1) * total + i] = xn;
     const __nv_bfloat16 xh = __float2bfloat16(xn);
     a.xb[row * a.ldxb + c] = xh;
     if (a.has_uncond) a.xb[(rows + row) * a.ldxb + c] = xh;

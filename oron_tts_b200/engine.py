@@ -376,23 +376,24 @@ class DiTEngine:
                       step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
         L.gemm(ws.nrm, w.wp, ws.v, epilogue=L.EPI_F32, bias=w.bp, block_n=128, **common)
 
-    def euler(self, ws: Workspace, *, cfg: float, has_uncond: bool) -> None:
+    def euler(self, ws: Workspace, *, cfg: float, has_uncond: bool, method: int = 0) -> None:
         L.cfg_euler_step(ws.x, ws.v, nb=ws.nb, rows_per_batch=ws.tpad, n_mels=self.w.n_mels, has_uncond=has_uncond,
-                         cfg=cfg, dt=ws.dt, step_ptr=ws.step, xb=ws.xb, traj=ws.traj, v_out=ws.vg)
+                         cfg=cfg, dt=ws.dt, step_ptr=ws.step, xb=ws.xb, traj=ws.traj, v_out=ws.vg, method=method)
 
     # -------------------------------------------------------------------------------------------
-    def run_ode(self, ws: Workspace, *, steps: int, cfg: float, has_uncond: bool) -> None:
-        """`steps` x (DiT forward + CFG/Euler update). The step is captured once into a CUDA graph."""
+    def run_ode(self, ws: Workspace, *, steps: int, cfg: float, has_uncond: bool, method: int = 0) -> None:
+        """`steps` x (DiT forward + CFG / ODE update): `steps` counts velocity evaluations (2 per interval for the
+        midpoint rule, method 1). One evaluation is captured once into a CUDA graph and replayed."""
 
         def one_step():
             self.velocity(ws, mod_nb=1, use_step=True)
-            self.euler(ws, cfg=cfg, has_uncond=has_uncond)
+            self.euler(ws, cfg=cfg, has_uncond=has_uncond, method=method)
 
         if not self.use_graph:
             for _ in range(steps):
                 one_step()
             return
-        key = (cfg, has_uncond)
+        key = (cfg, has_uncond, method)
         if ws.graph is None or ws.graph_key != key:
             # warm-up outside capture (sets kernel attributes, builds tables), then rewind the state it touched
             x_save, xb_save = ws.x.clone(), ws.xb.clone()

@@ -76,9 +76,14 @@ class CFM(nn.Module):
     def sample(self, cond: torch.Tensor, text_ids: torch.Tensor, duration: torch.Tensor | int, *,
                lens: torch.Tensor | None = None, steps: int = 32, cfg_strength: float = 1.0,
                sway_sampling_coef: float | None = None, seed: int | None = None, max_duration: int = 65536,
-               y0: torch.Tensor | None = None) -> tuple[torch.Tensor, list[torch.Tensor]]:
+               y0: torch.Tensor | None = None, method: str = "euler") -> tuple[torch.Tensor, list[torch.Tensor]]:
         """``y0`` (extra, optional): inject the initial noise [B, max_dur, n_mels] instead of drawing it —
-        needed for cross-device parity because CPU and CUDA generators produce different streams."""
+        needed for cross-device parity because CPU and CUDA generators produce different streams.
+        ``method`` (extra): "euler" (the reference, flow.py:290-299) or "midpoint" (explicit midpoint rule on the same
+        schedule: two DiT evaluations per step, second-order accurate)."""
+        if method not in ("euler", "midpoint"):
+            raise ValueError(f"method must be 'euler' or 'midpoint', got {method!r}")
+        evals = 2 if method == "midpoint" else 1
         if steps < 1:
             raise ValueError(f"steps must be >= 1, got {steps}")
         if cfg_strength < 0:
@@ -127,7 +132,7 @@ class CFM(nn.Module):
         use_cfg = cfg_strength >= 1e-5
         branches = [Branch(False, False), Branch(True, True)] if use_cfg else [Branch(False, False)]
         tpad = _rup(max_dur, TILE)
-        ws = eng.workspace(batch, batch * len(branches), tpad, steps, True)
+        ws = eng.workspace(batch, batch * len(branches), tpad, steps * evals, True)
 
         # initial noise: per-sample sequential draws from one generator, zero padded (flow.py:270-283)
         if y0 is None:
@@ -143,13 +148,15 @@ class CFM(nn.Module):
         t = torch.linspace(0, 1, steps + 1, device=device, dtype=step_cond.dtype)
         if sway_sampling_coef is not None:
             t = t + sway_sampling_coef * (torch.cos(torch.pi / 2 * t) - 1 + t)
-        ws.dt.copy_(t[1:] - t[:-1])
+        ws.dt[:steps].copy_(t[1:] - t[:-1])
 
         try:
             eng.load_sequences(ws, text=text_ids, durations=dur_h, seq_len=max_dur, branches=branches)
             eng.text_embed(ws)
             eng.static_embed(ws, step_cond, branches)
-            eng.modulation_table(ws, t[:-1])
+            # one modulation row per velocity evaluation: t_i, and t_i + dt_i / 2 for the midpoint rule
+            t_eval = t[:-1] if evals == 1 else torch.stack([t[:-1], 0.5 * (t[:-1] + t[1:])], dim=1).reshape(-1)
+            eng.modulation_table(ws, t_eval)
             xv = ws.x.view(batch, tpad, self.n_mels)
             xv.zero_()
             xv[:, :max_dur].copy_(y0)
@@ -157,11 +164,11 @@ class CFM(nn.Module):
             L.cast_rows_bf16(ws.x, ws.xb[:, : self.n_mels], reps=len(branches))
             ws.traj[0].copy_(ws.x)
             ws.step.zero_()
-            eng.run_ode(ws, steps=steps, cfg=float(cfg_strength), has_uncond=use_cfg)
+            eng.run_ode(ws, steps=steps * evals, cfg=float(cfg_strength), has_uncond=use_cfg, method=evals - 1)
         finally:
             self.backbone.clear_cache()
 
-        tr = ws.traj.view(steps + 1, batch, tpad, self.n_mels)[:, :, :max_dur]
+        tr = ws.traj.view(steps * evals + 1, batch, tpad, self.n_mels)[: steps + 1, :, :max_dur]
         trajectory = [tr[i].clone() for i in range(steps + 1)]
         out = torch.where(cond_mask_3d, cond, trajectory[-1])
         return out, trajectory

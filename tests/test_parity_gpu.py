@@ -161,6 +161,28 @@ def test_synthesize_batch_matches_one_by_one():
         m.synthesize_batch(["ok", "   "], **kw)
 
 
+def test_sample_midpoint_method_vs_oracle():
+    """CFM.sample(method="midpoint"): the explicit midpoint rule (two evaluations per step) against the oracle's
+    restatement, with CFG and the sway schedule; "euler" stays the default and an unknown method raises."""
+    g = _gold("dit_tiny.pt")
+    sd = ref_state_dict("tiny")
+    cfm = model_for("tiny").cfm
+    y0 = g["s1_traj"][0]
+    kw = dict(steps=3, cfg_strength=2.0, sway_sampling_coef=-1.0)
+    o_mel, o_traj = DO.cfm_sample(sd, torch.zeros(1, 143, 100), g["s1_ids"], torch.tensor([143]), lens=torch.tensor([0]),
+                                  y0=y0, method="midpoint", **kw)
+    mel, traj = cfm.sample(torch.zeros(1, 143, 100, device=DEV), g["s1_ids"].to(DEV), torch.tensor([143], device=DEV),
+                           lens=torch.tensor([0], device=DEV), y0=y0, method="midpoint", **kw)
+    assert len(traj) == 4 and torch.equal(traj[0].cpu(), y0)
+    for a, b in zip(traj[1:], o_traj[1:]):
+        assert _rel(a, b) < MEL_TOL
+    assert _rel(mel, o_mel) < MEL_TOL
+    e_mel, _ = DO.cfm_sample(sd, torch.zeros(1, 143, 100), g["s1_ids"], torch.tensor([143]), lens=torch.tensor([0]), y0=y0, **kw)
+    assert _rel(o_mel, e_mel) > 3 * _rel(mel, o_mel)  # the CUDA result follows the midpoint rule, not Euler's
+    with pytest.raises(ValueError, match="method"):
+        cfm.sample(torch.zeros(1, 143, 100, device=DEV), g["s1_ids"].to(DEV), 143, method="rk4")
+
+
 def test_sample_small_config1():
     g = _gold("sample_small.pt")
     cfm = model_for("small").cfm
