@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace oron {
@@ -289,8 +291,14 @@ __device__ __forceinline__ void cta_colsum_atomic(const float2 (&acc)[V2], float
 
 // rows per CTA of the column-reducing kernels (a multiple of 8: one row per warp per pass), chosen by the host so that
 // the grid covers the SMs several times over; fewer rows per CTA = more parallelism, more atomics
-__host__ __device__ inline int tr_rows_for(long long total_rows, int sms) {
-  long long r = total_rows / (4ll * sms);
+inline int tr_rows_for(long long total_rows, int sms) {
+  static int div = 0;
+  if (div == 0) {
+    const char* e = getenv("ORON_TR_DIV");
+    div = e ? atoi(e) : 4;
+    if (div <= 0) div = 4;
+  }
+  long long r = total_rows / ((long long)div * sms);
   r = (r / 8) * 8;
   return int(r < 8 ? 8 : (r > 64 ? 64 : r));
 }
