@@ -642,6 +642,55 @@ class TrainEngine:
             if prm.grad is not None and lo <= prm.grad.data_ptr() < hi:
                 prm.grad = None
 
+    # ---- checkpoint / resume and EMA (trainer.py:98-102, 214-215, 507-526) -----------------------------------------
+    def optimizer_state_dict(self) -> dict:
+        """The Adam moments in ``torch.optim.AdamW.state_dict()`` format (parameter order = ``model.parameters()``), so
+        that ``CheckpointManager.save`` / a later ``torch.optim.AdamW.load_state_dict`` work unchanged."""
+        a = self.arena
+        state, order = {}, []
+        for idx, (name, prm) in enumerate(self.model.named_parameters()):
+            o, n = a.offsets[name], prm.numel()
+            state[idx] = {"step": torch.tensor(float(self.step_count)), "exp_avg": a.m[o:o + n].view(prm.shape).clone(),
+                          "exp_avg_sq": a.v[o:o + n].view(prm.shape).clone()}
+            order.append(idx)
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.wd, amsgrad=False, maximize=False,
+                     foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True, params=order)
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        a = self.arena
+        names = [n for n, _ in self.model.named_parameters()]
+        for idx, st in sd["state"].items():
+            name = names[int(idx)]
+            o, n = a.offsets[name], a.named[name].numel()
+            a.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            a.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            self.step_count = int(float(st["step"]))
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+
+    @torch.no_grad()
+    def enable_ema(self, decay: float = 0.9999) -> None:
+        """Exponential moving average of the parameters with torch_ema's update rule (trainer.py:98-102)."""
+        self.ema, self.ema_decay, self.ema_updates = self.arena.p.clone(), decay, 0
+
+    @torch.no_grad()
+    def ema_update(self) -> None:
+        self.ema_updates += 1
+        d = min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
+        self.ema.lerp_(self.arena.p, 1.0 - d)  # shadow -= (1 - d) * (shadow - param), one pass over the flat arena
+
+    def ema_state_dict(self) -> dict:
+        """``model.state_dict()`` with the EMA weights in place of the parameters: the ``ema_state_dict`` entry that
+        scripts/infer.py prefers (infer.py:20-28, trainer.py:511-514)."""
+        a = self.arena
+        out = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        for name, prm in self.model.named_parameters():
+            o, n = a.offsets[name], prm.numel()
+            out[name] = self.ema[o:o + n].view(prm.shape).clone()
+        return out
+
     def grad_norm(self) -> torch.Tensor:
         """Global L2 norm of the current gradients (trainer.py:171-177), device scalar."""
         s = torch.zeros(1, device=self.arena.g.device, dtype=F32)
@@ -653,6 +702,18 @@ class TrainEngine:
         loss = self.loss_and_grad(mel, text_ids, lens, draws=draws, training=training)
         self.optimizer_step(lr)
         return loss
+
+
+def reference_lr(update: int, *, base_lr: float = 1e-4, warmup_steps: int = 1000, total_steps: int = 100000,
+                 start_factor: float = 1e-4, eta_min: float = 1e-6) -> float:
+    """Learning rate in effect for optimizer update number ``update`` (0-based) under the reference's schedule
+    (trainer.py:88-96): SequentialLR([LinearLR(start_factor -> 1 over warmup_steps), CosineAnnealingLR(T_max =
+    max(total_steps - warmup_steps, 1), eta_min)], milestones=[warmup_steps]), stepped once per update."""
+    if update < warmup_steps:
+        return base_lr * (start_factor + (1.0 - start_factor) * update / max(warmup_steps, 1))
+    t_max = max(total_steps - warmup_steps, 1)
+    e = update - warmup_steps
+    return eta_min + (base_lr - eta_min) * (1.0 + math.cos(math.pi * e / t_max)) / 2.0
 
 
 class OTCFMLoss(torch.autograd.Function):

@@ -139,3 +139,23 @@ def test_gradient_reducer_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_reference_lr_schedule_matches_torch_schedulers():
+    """train.reference_lr against the scheduler stack the reference builds (trainer.py:88-96)."""
+    import torch
+
+    from oron_tts_b200.train import reference_lr
+
+    for warm, total in ((5, 40), (1, 7), (10, 12)):
+        prm = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([prm], lr=1e-4)
+        w = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1e-4, end_factor=1.0, total_iters=warm)
+        c = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=max(total - warm, 1), eta_min=1e-6)
+        sch = torch.optim.lr_scheduler.SequentialLR(opt, schedulers=[w, c], milestones=[warm])
+        for update in range(total):
+            want = opt.param_groups[0]["lr"]
+            got = reference_lr(update, base_lr=1e-4, warmup_steps=warm, total_steps=total)
+            assert abs(got - want) <= 1e-6 * max(want, 1e-12) + 1e-12, (warm, total, update, got, want)
+            opt.step()
+            sch.step()

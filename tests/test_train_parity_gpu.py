@@ -196,3 +196,47 @@ def test_training_mode_dropout_is_applied_and_reproducible():
     assert la != l0 and lc != la and abs(la - l0) < 0.2 * l0
     assert bool(torch.isfinite(ga).all())
     assert abs(l0 - float(g["loss"])) < 2e-2 * float(g["loss"])
+
+
+def test_optimizer_state_round_trip_and_ema():
+    """Checkpoint / resume: the fused optimizer's moments export to torch.optim.AdamW format (a torch optimizer resumed
+    from them takes the same next step) and load back; EMA follows torch_ema's rule."""
+    g = _gold("train_tiny.pt")
+    eng = _engine(lr=1e-3)
+    eng.enable_ema(0.9999)
+    mel, text, lens = g["mel"].to(DEV), g["text"].to(DEV), g["lens"].to(DEV)
+    draws = _to_dev(DO.cfm_eval_draws(g["mel"].transpose(1, 2), g["lens"]))
+    shadow = eng.arena.p.clone()
+    for n in range(1, 3):
+        eng.train_step(mel, text, lens, draws=draws)
+        eng.ema_update()
+        d = min(0.9999, (1 + n) / (10 + n))
+        shadow -= (1 - d) * (shadow - eng.arena.p)
+    assert _rel(eng.ema, shadow) < 1e-6
+    esd = eng.ema_state_dict()
+    assert set(esd) == set(eng.model.state_dict()) and all(v.shape == eng.model.state_dict()[k].shape for k, v in esd.items())
+    osd = eng.optimizer_state_dict()
+    # a torch optimizer resumed from the exported state and fed the same (clipped) gradients lands on the same weights
+    eng.loss_and_grad(mel, text, lens, draws=draws)
+    import copy
+
+    twin = copy.deepcopy({k: p.detach().clone() for k, p in eng.model.named_parameters()})
+    params = [torch.nn.Parameter(v) for v in twin.values()]
+    for prm, src in zip(params, eng.model.parameters()):
+        prm.grad = src.grad.detach().clone()
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01)
+    opt.load_state_dict(osd)
+    torch.nn.utils.clip_grad_norm_(params, 1.0)
+    opt.step()
+    eng.optimizer_step()
+    for prm, src in zip(params, eng.model.parameters()):
+        assert float((prm.detach() - src.detach()).abs().max()) < 2e-6
+    # and back: a fresh engine that loads the state continues identically
+    eng2 = _engine(lr=1e-3)
+    eng2.model.load_state_dict(eng.model.state_dict())
+    eng2.sync_params()
+    eng2.load_optimizer_state_dict(eng.optimizer_state_dict())
+    assert eng2.step_count == eng.step_count and _rel(eng2.arena.m, eng.arena.m) == 0.0 and _rel(eng2.arena.v, eng.arena.v) == 0.0
+    la = eng.train_step(mel, text, lens, draws=draws)
+    lb = eng2.train_step(mel, text, lens, draws=draws)
+    assert abs(float(la) - float(lb)) < 1e-4 * float(la) and _rel(eng2.arena.p, eng.arena.p) < 1e-5
