@@ -319,3 +319,28 @@ def test_vocos_decode_large_batch_tiles():
         assert _rel(wav[b], one[0]) < 2e-3
     ref = AO.vocos_decode(sd, mel[:1])
     assert _rel(wav[:1], ref) < 2e-2
+
+
+def test_gpu_training_batch_vs_reference_dataset_and_collator():
+    """data.GpuBatcher == TTSDataset.__getitem__ + TTSCollator of the live reference (fixture): ids, lengths, masks and
+    padding exact; log-mel within fp32 FFT rounding; and the batch feeds the training engine."""
+    from oron_tts_b200.data import GpuBatcher
+
+    g = _gold("data_batch.pt")
+    out = GpuBatcher(min_duration_s=0.5, device=DEV)(g["waves"], g["texts"], g["langs"], g["attrs"])
+    assert torch.equal(out["text_ids"].cpu(), g["text_ids"]) and torch.equal(out["mel_lengths"].cpu(), g["mel_lengths"])
+    assert torch.equal(out["mask"].cpu(), g["mask"])
+    mel = out["mel"].cpu()
+    assert mel.shape == g["mel"].shape
+    for i, t in enumerate(g["mel_lengths"].tolist()):
+        assert float(mel[i, :, t:].abs().max()) == 0.0 if t < mel.shape[-1] else True
+        assert float((mel[i, :, :t] - g["mel"][i, :, :t]).abs().max()) < 2e-3, i
+    from oron_tts_b200.train import TrainEngine
+
+    m = F5TTS.from_config(GW.CONFIGS["tiny"])
+    m.load_state_dict(ref_state_dict("tiny"), strict=True)
+    eng = TrainEngine(m.to(DEV).train())
+    loss = eng.train_step(out["mel"], out["text_ids"], out["mel_lengths"])
+    assert bool(torch.isfinite(loss)) and int(eng.skipped) == 0
+    with pytest.raises(ValueError, match="too short"):
+        GpuBatcher(min_duration_s=1.0, device=DEV)([g["waves"][0][:1000]], ["a"])

@@ -68,3 +68,19 @@ def test_synthesize_argument_validation():
                dict(max_chars_per_chunk=-1), dict(pause_s=-0.1)):
         with pytest.raises(ValueError):
             model.synthesize("сайн", device="cpu", **kw)
+
+
+def test_dynamic_batch_plan_matches_reference_sampler():
+    """data.dynamic_batches / epoch_order against DynamicBatchSampler (fixture recorded from the live reference)."""
+    import os
+
+    import torch
+
+    from oron_tts_b200.data import dynamic_batches, epoch_order
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data_batch.pt"), weights_only=False)
+    for (thr, mx), ref in g["plans"].items():
+        plan = dynamic_batches(g["durations"], frames_threshold=thr, max_samples=mx)
+        assert plan == ref["batches"], (thr, mx)
+        assert [plan[i] for i in epoch_order(len(plan), 3)] == ref["epoch3"]
+    assert sorted(i for b in dynamic_batches(g["durations"], 3000) for i in b) == list(range(len(g["durations"])))
