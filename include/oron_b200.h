@@ -105,8 +105,10 @@ typedef struct oron_gemm_desc {
   int32_t max_ctas;          /* 0 = one CTA per SM */
   int32_t two_sm;            /* 1: 2-SM (cta_group::2) kernel, 256 x block_n tile per SM pair */
   int32_t f16_from_col;      /* QKV_ROPE: columns >= this (> 0) are stored as IEEE f16, not bf16 (the V operand of attention) */
-  int32_t stream_k;          /* 1 (two_sm + ORON_EPI_GATE_RESID, taps == 1 only): cut the flat (tile, k-block) list into equal shares per SM pair;
-                              * partial sums are added to `out` with f32 vector reductions (sum order, hence the last bit, may vary run to run) */
+  int32_t stream_k;          /* 1 (two_sm + ORON_EPI_GATE_RESID or ORON_EPI_F32, taps == 1 only): cut the flat (tile, k-block) list into equal
+                              * shares per SM pair; partial sums are added to `out` with f32 vector reductions (sum order, hence the last
+                              * bit, may vary run to run). ORON_EPI_F32: out += A W^T (+ bias once), no addend -- the weight-gradient GEMMs,
+                              * whose few output tiles (N_out x K_in / 256^2) would otherwise leave most SM pairs idle */
   void* debug_stamps;        /* NULL, or int64 [grid, 16] device buffer for per-CTA clock64 stamps (profiling aid) */
   /* Backward-pass operand layouts (two_sm = 1, taps = 1, K = w_cols a multiple of 64): the contraction runs over the
    * ROWS of the operand as stored, so no transposed copy is needed (TMA boxes of 64 x 64, MN-major UMMA descriptors):

@@ -188,8 +188,10 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   if (epi == EPI_QKV_ROPE && (!d->bias || !d->rope_cos || !d->rope_sin || d->N % 64 != 0 || d->block_n < 128))
     return fail(ORON_ERR_BAD_ARG, "gemm: QKV_ROPE needs bias, rope tables, N %% 64 == 0, block_n >= 128");
   if (epi == EPI_GATE_RESID && !d->gate) return fail(ORON_ERR_BAD_ARG, "gemm: GATE_RESID needs gate");
-  if (d->stream_k && !(d->two_sm && epi == EPI_GATE_RESID && taps == 1))
-    return fail(ORON_ERR_BAD_ARG, "gemm: stream_k needs two_sm, the GATE_RESID epilogue and taps == 1");
+  if (d->stream_k && !(d->two_sm && (epi == EPI_GATE_RESID || epi == EPI_F32) && taps == 1))
+    return fail(ORON_ERR_BAD_ARG, "gemm: stream_k needs two_sm, the GATE_RESID or F32 epilogue and taps == 1");
+  if (d->stream_k && epi == EPI_F32 && (d->addend != nullptr || d->N % 4 != 0))
+    return fail(ORON_ERR_BAD_ARG, "gemm: stream_k with the F32 epilogue adds into out: no addend, N %% 4 == 0");
   if ((epi == EPI_EMBED_DUAL || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID) && !d->addend)
     return fail(ORON_ERR_BAD_ARG, "gemm: epilogue %d needs addend", epi);
   if (epi == EPI_EMBED_DUAL && !d->out2) return fail(ORON_ERR_BAD_ARG, "gemm: EMBED_DUAL needs out2");
@@ -200,8 +202,8 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   a.a_mn = d->a_mn_major != 0 ? 1 : 0;
   a.b_mn = d->b_mn_major != 0 ? 1 : 0;
   if (a.a_mn || a.b_mn) {
-    if (!two_sm || taps != 1 || d->stream_k || d->w_cols % GEMM_BK != 0 || (a.a_mn && d->nbatch != 1))
-      return fail(ORON_ERR_UNSUPPORTED, "gemm: MN-major operands need two_sm, taps == 1, no stream_k, K %% 64 == 0 (and nbatch == 1 for A)");
+    if (!two_sm || taps != 1 || d->w_cols % GEMM_BK != 0 || (a.a_mn && d->nbatch != 1))
+      return fail(ORON_ERR_UNSUPPORTED, "gemm: MN-major operands need two_sm, taps == 1, K %% 64 == 0 (and nbatch == 1 for A)");
   }
   CUtensorMap ta, tb;
   int rc;

@@ -59,7 +59,8 @@ struct GemmArgs {
   const int* seq_lens;         // [nbatch] valid rows per batch element or nullptr (all valid)
   const unsigned char* row_valid;  // [rows] explicit per-row validity (overrides seq_lens) or nullptr
   int mask_rows;               // EPI_GATE_RESID: skip rows t >= seq_len
-  int stream_k;                // 2-SM EPI_GATE_RESID only: split the K loops evenly over the SM pairs, partial sums land with f32 atomics
+  int stream_k;                // 2-SM EPI_GATE_RESID / EPI_F32: split the K loops evenly over the SM pairs, partial sums land with f32
+                               // vector reductions (EPI_F32: out += A W^T, the caller zeroes or accumulates into out)
   long long* dbg;              // optional [grid, 16] clock64 stamps (tools/kernel_bench.py --trace); nullptr in production
   // 2-SM kernel only: operands whose K dimension runs along the ROWS of the source (the backward-pass GEMMs):
   //   a_mn: A source is [K, M] row-major (D = Asrc^T ...), b_mn: B source is [K, N] row-major (D = ... Bsrc).
@@ -198,8 +199,13 @@ __device__ __forceinline__ void epi_block_fast(const GemmArgs& args, const float
 #pragma unroll
       for (int it = 0; it < 8; ++it) v[it] = add4(v[it], x[it]);
     }
+    if (args.stream_k) {  // this CTA holds part of the K sum: out += partial (the caller zeroed or is accumulating into out)
 #pragma unroll
-    for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = v[it];
+      for (int it = 0; it < 8; ++it) red_add4(o + (long long)it * 4 * args.ldo, v[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = v[it];
+    }
   } else if constexpr (EPI == EPI_GATE_RESID) {
     float* o = reinterpret_cast<float*>(args.out) + grow0 * args.ldo + col;
     if (args.stream_k) {
@@ -275,7 +281,11 @@ __device__ __forceinline__ void epi_block_slow(const GemmArgs& args, const uint3
       st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
     } else if constexpr (EPI == EPI_F32) {
       if (args.addend != nullptr) v = add4(v, ldg4_guard(args.addend + grow * args.ld_add + col, col, N));
-      st_f32x4(reinterpret_cast<float*>(args.out) + grow * args.ldo + col, v, col, N);
+      if (args.stream_k) {
+        if (col < N) red_add4(reinterpret_cast<float*>(args.out) + grow * args.ldo + col, v);  // host guarantees N % 4 == 0
+      } else {
+        st_f32x4(reinterpret_cast<float*>(args.out) + grow * args.ldo + col, v, col, N);
+      }
     } else if constexpr (EPI == EPI_GATE_RESID) {
       if (args.mask_rows && !valid) continue;
       float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col);
@@ -676,7 +686,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int tiles_n = (args.N + BN - 1) / BN;
   const int num_tiles = tiles_mp * tiles_n;
   const int num_kb = args.num_kb;
-  const bool sk = (EPI == EPI_GATE_RESID) && args.stream_k != 0;
+  const bool sk = (EPI == EPI_GATE_RESID || EPI == EPI_F32) && args.stream_k != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);

@@ -328,8 +328,11 @@ class TrainEngine:
         """out[N_out, K_in] (f32, a gradient-arena view) (+)= dy[R, N_out]^T @ x[R, K_in], both operands as stored."""
         nn = x.shape[1]
         bn = 256 if nn % 256 == 0 else 128
-        L.gemm(dy, x, out, epilogue=L.EPI_F32, block_n=bn, a_mn=True, b_mn=True, two_sm=True,
-               addend=out if accumulate else None)
+        # stream-K: the output has few 256 x 256 tiles (16 for a dim x dim weight) but a long reduction (K = rows), so every
+        # SM pair takes an equal share of the (tile, k-block) list and adds its partial sum into the gradient arena, which
+        # the step zeroed (or keeps accumulating into): `accumulate` needs nothing extra
+        L.gemm(dy, x, out, epilogue=L.EPI_F32, block_n=bn, a_mn=True, b_mn=True, two_sm=True, stream_k=True)
+        del accumulate
 
     def _linear_bwd(self, ws, dy, x_saved, w, gw, gb, dx_out, *, acc=False):
         """Backward of y = x W^T + b for [R, .] activations: bias and weight gradients into the arena, data gradient.

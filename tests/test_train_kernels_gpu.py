@@ -367,6 +367,10 @@ def test_gemm_mn_major_operands(R, n_out, k_in, bn):
     dW2 = dW.clone()
     L.gemm(dY, X, dW2, epilogue=L.EPI_F32, a_mn=True, b_mn=True, two_sm=True, block_n=bn, addend=dW2)
     assert _rel(dW2, 2 * ref) < 1e-5
+    if k_in % 4 == 0:  # stream-K: equal (tile, k-block) shares per SM pair, partial sums added into the output
+        dW3 = dW.clone()
+        L.gemm(dY, X, dW3, epilogue=L.EPI_F32, a_mn=True, b_mn=True, two_sm=True, block_n=bn, stream_k=True)
+        assert _rel(dW3, 2 * ref) < 1e-5
     if n_out % 64 == 0 and k_in % 8 == 0:
         W = (torch.randn(n_out, k_in, device=DEV, generator=g) * 0.05).to(BF16)
         dX = torch.zeros(R, k_in, device=DEV, dtype=BF16)
