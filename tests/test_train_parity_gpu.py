@@ -240,3 +240,27 @@ def test_optimizer_state_round_trip_and_ema():
     la = eng.train_step(mel, text, lens, draws=draws)
     lb = eng2.train_step(mel, text, lens, draws=draws)
     assert abs(float(la) - float(lb)) < 1e-4 * float(la) and _rel(eng2.arena.p, eng.arena.p) < 1e-5
+
+
+def test_small_config_gradients_vs_oracle():
+    """BASELINE config-1 architecture (Small: dim 512, depth 12, 8 heads, text_dim 256, conv groups of 32 channels): the
+    other template instantiations of the backward kernels (C = 512 / 256, grouped-conv group width 32), ragged lengths."""
+    sd = _state_dict("small")
+    eng = _engine("small")
+    gen = torch.Generator().manual_seed(41)
+    B, Tn = 3, 300
+    lens = torch.tensor([300, 211, 130])
+    x1 = torch.randn(B, Tn, 100, generator=gen) * 1.5 - 3.0
+    text = torch.randint(4, 65, (B, Tn), generator=gen)
+    for b in range(B):
+        text[b, int(lens[b]):] = -1
+    text[1, 40:52] = -1  # in-sequence fillers
+    pos = torch.arange(Tn)
+    start, ln = torch.tensor([30, 20, 10]), torch.tensor([220, 160, 100])
+    span = (pos[None] >= start[:, None]) & (pos[None] < (start + ln)[:, None]) & (pos[None] < lens[:, None])
+    draws = dict(x1=x1, x0=torch.randn(B, Tn, 100, generator=gen), time=torch.rand(B, generator=gen), span=span,
+                 drop_audio=True, drop_text=False)
+    ref_loss, ref_grads = DO.cfm_loss_and_grads(sd, draws, text, lens)
+    loss = eng.loss_and_grad(x1.transpose(1, 2).to(DEV), text.to(DEV), lens.to(DEV), draws=_to_dev(draws))
+    assert abs(float(loss) - float(ref_loss)) < 2e-2 * float(ref_loss)
+    _check_grads(eng, ref_grads, "small")
