@@ -264,3 +264,25 @@ def test_small_config_gradients_vs_oracle():
     loss = eng.loss_and_grad(x1.transpose(1, 2).to(DEV), text.to(DEV), lens.to(DEV), draws=_to_dev(draws))
     assert abs(float(loss) - float(ref_loss)) < 2e-2 * float(ref_loss)
     _check_grads(eng, ref_grads, "small")
+
+
+def test_base_config_gradients_vs_oracle():
+    """BASELINE config-5 architecture (Base: dim 1024, depth 22, 16 heads, text_dim 512, conv groups of 64 channels,
+    428 M parameters): every gradient of one batch against torch.autograd over the CPU oracle."""
+    sd = _state_dict("base")
+    eng = _engine("base")
+    gen = torch.Generator().manual_seed(43)
+    B, Tn = 2, 384
+    lens = torch.tensor([384, 250])
+    x1 = torch.randn(B, Tn, 100, generator=gen) * 1.5 - 3.0
+    text = torch.randint(4, 65, (B, Tn), generator=gen)
+    text[1, 250:] = -1
+    pos = torch.arange(Tn)
+    start, ln = torch.tensor([40, 25]), torch.tensor([300, 200])
+    span = (pos[None] >= start[:, None]) & (pos[None] < (start + ln)[:, None]) & (pos[None] < lens[:, None])
+    draws = dict(x1=x1, x0=torch.randn(B, Tn, 100, generator=gen), time=torch.tensor([0.37, 0.81]), span=span,
+                 drop_audio=False, drop_text=False)
+    ref_loss, ref_grads = DO.cfm_loss_and_grads(sd, draws, text, lens)
+    loss = eng.loss_and_grad(x1.transpose(1, 2).to(DEV), text.to(DEV), lens.to(DEV), draws=_to_dev(draws))
+    assert abs(float(loss) - float(ref_loss)) < 2e-2 * float(ref_loss)
+    _check_grads(eng, ref_grads, "base")
