@@ -159,6 +159,16 @@ class DiT(nn.Module):
             self.__dict__["_engine_sig"] = sig
         return self.__dict__["_engine"]
 
+    def precise(self):
+        """fp32-mode engine for the current parameters (rebuilt when they change)."""
+        from .precise import PreciseDiT
+
+        sig = self._signature()
+        if self.__dict__.get("_precise") is None or self.__dict__.get("_precise_sig") != sig:
+            self.__dict__["_precise"] = PreciseDiT(self)
+            self.__dict__["_precise_sig"] = sig
+        return self.__dict__["_precise"]
+
     def clear_cache(self) -> None:
         self.text_cond = None
         self.text_uncond = None
@@ -167,13 +177,20 @@ class DiT(nn.Module):
     @torch.no_grad()
     def forward(self, x: torch.Tensor, cond: torch.Tensor, text: torch.Tensor, time: torch.Tensor,
                 mask: torch.Tensor | None = None, drop_audio_cond: bool = False, drop_text: bool = False,
-                cfg_infer: bool = False, cache: bool = False) -> torch.Tensor:
+                cfg_infer: bool = False, cache: bool = False, precision: str = "bf16") -> torch.Tensor:
         """Velocity field [B, N, mel] (or [2B, N, mel] with cfg_infer) — dit.py:165-234.
 
         ``mask`` must be a prefix mask (frames [0, len_b) valid), which is what CFM builds from lengths.
         ``cache`` is accepted for signature parity; text embeddings are recomputed per call here (the
         CFM.sample fast path hoists them out of the ODE loop instead).
         """
+        if precision == "fp32":
+            # parity / debugging mode (extra kwarg): fp32 activations, 3-way bf16-split GEMMs, fp32 attention: within
+            # 1e-6 of the fp32 reference, an order of magnitude slower (oron_tts_b200/precise.py)
+            return self.precise().forward(x, cond, text, time, mask=mask, drop_audio_cond=drop_audio_cond, drop_text=drop_text,
+                                          cfg_infer=cfg_infer)
+        if precision != "bf16":
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("DiT.forward alone builds no autograd graph: train through CFM.forward / F5TTS.forward "
                                       "(an autograd node over the sm_100a training engine) or oron_tts_b200.train.TrainEngine")

@@ -76,13 +76,16 @@ class CFM(nn.Module):
     def sample(self, cond: torch.Tensor, text_ids: torch.Tensor, duration: torch.Tensor | int, *,
                lens: torch.Tensor | None = None, steps: int = 32, cfg_strength: float = 1.0,
                sway_sampling_coef: float | None = None, seed: int | None = None, max_duration: int = 65536,
-               y0: torch.Tensor | None = None, method: str = "euler") -> tuple[torch.Tensor, list[torch.Tensor]]:
+               y0: torch.Tensor | None = None, method: str = "euler",
+               precision: str = "bf16") -> tuple[torch.Tensor, list[torch.Tensor]]:
         """``y0`` (extra, optional): inject the initial noise [B, max_dur, n_mels] instead of drawing it —
         needed for cross-device parity because CPU and CUDA generators produce different streams.
         ``method`` (extra): "euler" (the reference, flow.py:290-299) or "midpoint" (explicit midpoint rule on the same
         schedule: two DiT evaluations per step, second-order accurate)."""
         if method not in ("euler", "midpoint"):
             raise ValueError(f"method must be 'euler' or 'midpoint', got {method!r}")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         evals = 2 if method == "midpoint" else 1
         if steps < 1:
             raise ValueError(f"steps must be >= 1, got {steps}")
@@ -127,6 +130,9 @@ class CFM(nn.Module):
         cond_mask_3d = cond_mask.unsqueeze(-1)
         step_cond = torch.where(cond_mask_3d, cond, torch.zeros_like(cond))
 
+        if precision == "fp32":
+            return self._sample_fp32(cond, cond_mask_3d, step_cond, text_ids, dur_h, max_dur, steps, cfg_strength,
+                                     sway_sampling_coef, seed, y0, method)
         eng = self.backbone.engine()
         w = eng.w
         use_cfg = cfg_strength >= 1e-5
@@ -172,3 +178,39 @@ class CFM(nn.Module):
         trajectory = [tr[i].clone() for i in range(steps + 1)]
         out = torch.where(cond_mask_3d, cond, trajectory[-1])
         return out, trajectory
+
+    def _sample_fp32(self, cond, cond_mask_3d, step_cond, text_ids, dur_h, max_dur, steps, cfg_strength, sway, seed, y0, method):
+        """``sample(precision="fp32")``: the reference loop (flow.py:244-306) around the fp32-mode DiT forward
+        (precise.PreciseDiT). A parity / debugging path: no CUDA graph, text embedding recomputed per evaluation; the
+        three-term state update per step is plain torch on [B, T, n_mels]."""
+        device, batch = cond.device, cond.shape[0]
+        pd = self.backbone.precise()
+        if y0 is None:
+            generator = None if seed is None else torch.Generator(device=device).manual_seed(seed)
+            ys = [torch.randn(d, self.n_mels, device=device, dtype=step_cond.dtype, generator=generator) for d in dur_h]
+            y0 = torch.nn.utils.rnn.pad_sequence(ys, padding_value=0.0, batch_first=True)
+        else:
+            y0 = y0.to(device=device, dtype=torch.float32)
+        t = torch.linspace(0, 1, steps + 1, device=device, dtype=step_cond.dtype)
+        if sway is not None:
+            t = t + sway * (torch.cos(torch.pi / 2 * t) - 1 + t)
+        mask = torch.arange(max_dur, device=device)[None, :] < torch.tensor(dur_h, device=device)[:, None]
+
+        def velocity(x, tt):
+            tb = tt.expand(batch)
+            if cfg_strength < 1e-5:
+                return pd.forward(x, step_cond, text_ids, tb, mask=mask)
+            both = pd.forward(x, step_cond, text_ids, tb, mask=mask, cfg_infer=True)
+            return both[:batch] + (both[:batch] - both[batch:]) * cfg_strength
+
+        x = y0
+        trajectory = [y0]
+        for i in range(steps):
+            dt = t[i + 1] - t[i]
+            v = velocity(x, t[i])
+            if method == "midpoint":
+                v = velocity(x + v * (0.5 * dt), 0.5 * (t[i] + t[i + 1]))
+            x = x + v * dt
+            trajectory.append(x)
+        self.backbone.clear_cache()
+        return torch.where(cond_mask_3d, cond, x), trajectory

@@ -82,3 +82,16 @@ def test_product_path_fails_loudly_without_cuda():
                            torch.tensor([0.5]))
     with pytest.raises(RuntimeError, match="CUDA"):
         AudioProcessor().mel_spectrogram(torch.zeros(24000))
+
+
+def test_precise_header_symbols_exported(built):
+    """include/oron_b200_precise.h (fp32-mode helpers) against the library and its ctypes mirror."""
+    from oron_tts_b200 import precise
+
+    text = open(os.path.join(ROOT, "include", "oron_b200_precise.h")).read()
+    declared = set(re.findall(r"^int (oron_[a-z0-9_]+)\s*\(", text, flags=re.M))
+    assert declared == set(precise.PRECISE_SYMBOLS)
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name, body in re.findall(r"^int (oron_[a-z0-9_]+)\s*\(([^;]*?)\);", text, flags=re.M | re.S):
+        assert hasattr(lib, name), name
+        assert len(body.split(",")) == len(precise._ARGTYPES[name]), name

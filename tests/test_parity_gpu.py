@@ -344,3 +344,37 @@ def test_gpu_training_batch_vs_reference_dataset_and_collator():
     assert bool(torch.isfinite(loss)) and int(eng.skipped) == 0
     with pytest.raises(ValueError, match="too short"):
         GpuBatcher(min_duration_s=1.0, device=DEV)([g["waves"][0][:1000]], ["a"])
+
+
+def test_precise_fp32_mode_velocity_within_1e4():
+    """north_star: per-NFE-step velocity within 1e-4 relative L2 "in fp32 mode". PreciseDiT (fp32 activations, 3-way bf16
+    split GEMMs, fp32 attention / row-wise kernels) against the fixtures recorded from the live fp32 reference: batched
+    CFG forward with ragged lengths and fillers, a forward with the audio condition dropped, and an unmasked one."""
+    from oron_tts_b200.precise import PreciseDiT
+
+    g = _gold("dit_tiny.pt")
+    bb = model_for("tiny").cfm.backbone
+    pd = PreciseDiT(bb)
+    T_ = g["x"].shape[1]
+    mask = (torch.arange(T_)[None, :] < g["lens"][:, None]).to(DEV)
+    args = (g["x"].to(DEV), g["cond"].to(DEV), g["text"].to(DEV), g["time"].to(DEV))
+    valid = torch.cat([mask, mask], 0).cpu()
+    out = pd.forward(*args, mask=mask, cfg_infer=True).cpu()
+    assert _rel(out[valid], g["fwd_cfg"][valid]) < 1e-4, _rel(out[valid], g["fwd_cfg"][valid])
+    out = pd.forward(*args, mask=mask, drop_audio_cond=True).cpu()
+    assert _rel(out[mask.cpu()], g["fwd_drop"][mask.cpu()]) < 1e-4
+    out = pd.forward(g["x"][:1].to(DEV), g["cond"][:1].to(DEV), g["text"][:1].to(DEV), torch.tensor(0.5, device=DEV)).cpu()
+    assert _rel(out, g["fwd_nomask_scalar_t"]) < 1e-4
+    # the bf16 production path on the same inputs, for scale
+    ref = bb(*args, mask=mask, cfg_infer=True).cpu()
+    assert 1e-4 < _rel(ref[valid], g["fwd_cfg"][valid]) < VEL_TOL
+    # the same through the public kwargs: DiT.forward(precision="fp32") and a 4-step CFM.sample(precision="fp32")
+    out = bb(*args, mask=mask, cfg_infer=True, precision="fp32").cpu()
+    assert _rel(out[valid], g["fwd_cfg"][valid]) < 1e-4
+    cfm = model_for("tiny").cfm
+    mel, traj = cfm.sample(torch.zeros(1, 143, 100, device=DEV), g["s1_ids"].to(DEV), torch.tensor([143], device=DEV),
+                           lens=torch.tensor([0], device=DEV), steps=4, cfg_strength=2.0, sway_sampling_coef=-1.0,
+                           y0=g["s1_traj"][0], precision="fp32")
+    assert _rel(torch.stack(traj), g["s1_traj"]) < 1e-4 and _rel(mel, g["s1_mel"]) < 1e-4
+    with pytest.raises(ValueError, match="precision"):
+        bb(*args, mask=mask, precision="fp16")
