@@ -219,6 +219,10 @@ def test_base_config2_velocity_and_mel():
         both = bb(g["y0"].to(DEV), cond, ids, torch.tensor([tv], device=DEV), mask=mask, cfg_infer=True)
         assert both.shape == (2, T, 100)
         assert _rel(both[0], g[name][0]) < VEL_TOL and _rel(both[1], g[name][1]) < VEL_TOL, name
+    # fp32 mode at the BASELINE config-2 size (Base, T = 1406, CFG): 1e-4 on the per-NFE velocity
+    both = bb(g["y0"].to(DEV), cond, ids, torch.tensor([0.5], device=DEV), mask=mask, cfg_infer=True, precision="fp32")
+    assert _rel(both[0], g["v_t05"][0]) < 1e-4 and _rel(both[1], g["v_t05"][1]) < 1e-4
+    bb.__dict__["_precise"] = None
     if "mel" in g:
         mel, traj = m.cfm.sample(g["ref_mel"].to(DEV), ids, torch.tensor([T], device=DEV), lens=torch.tensor([ref_len], device=DEV),
                                  steps=32, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=0, y0=g["y0"])
