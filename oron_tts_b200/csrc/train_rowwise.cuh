@@ -26,7 +26,8 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float k = 0.7978845608028654f, a = 0.044715f;
   const float x2 = x * x;
   const float u = k * x * fmaf(a, x2, 1.0f);
-  const float t = tanhf(u);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));  // same unit as the forward epilogue (max rel. error 2^-11)
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * fmaf(3.0f * a, x2, 1.0f);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
@@ -68,15 +69,17 @@ struct DropCfg {
   unsigned int thresh;  // p * 2^32 (0: dropout off)
   float inv_keep;       // 1 / (1 - p)
 };
-__device__ __forceinline__ float drop_scale(const DropCfg& d, unsigned long long idx) {
-  if (d.thresh == 0u) return 1.0f;
-  unsigned int x = (unsigned int)idx * 0x9E3779B1u + d.key;  // lowbias32 finaliser: two 32-bit multiplies per element
+// one hash decides the element pair (idx, idx + 1), idx even: its two 16-bit halves against p * 2^16
+__device__ __forceinline__ float2 drop_scale2(const DropCfg& d, unsigned long long idx) {
+  if (d.thresh == 0u) return make_float2(1.0f, 1.0f);
+  unsigned int x = (unsigned int)(idx >> 1) * 0x9E3779B1u + d.key;  // lowbias32 finaliser
   x ^= x >> 16;
   x *= 0x7feb352du;
   x ^= x >> 15;
   x *= 0x846ca68bu;
   x ^= x >> 16;
-  return x >= d.thresh ? d.inv_keep : 0.0f;
+  const unsigned int t16 = d.thresh >> 16;
+  return make_float2((x & 0xffffu) >= t16 ? d.inv_keep : 0.0f, (x >> 16) >= t16 ? d.inv_keep : 0.0f);
 }
 
 template <typename T>
@@ -108,9 +111,9 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* in, long long ld
       st_from_f32<TO>(q + 1, 0.f);
       continue;
     }
-    const unsigned long long e = (unsigned long long)r * C + c;
-    st_from_f32<TO>(q, act_apply(act, ld_as_f32<TI>(p)) * drop_scale(dc, e));
-    st_from_f32<TO>(q + 1, act_apply(act, ld_as_f32<TI>(p + 1)) * drop_scale(dc, e + 1));
+    const float2 k = drop_scale2(dc, (unsigned long long)r * C + c);
+    st_from_f32<TO>(q, act_apply(act, ld_as_f32<TI>(p)) * k.x);
+    st_from_f32<TO>(q + 1, act_apply(act, ld_as_f32<TI>(p + 1)) * k.y);
   }
 }
 template <typename TD, typename TP, typename TO>
@@ -130,9 +133,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* dy, long long ld
       st_from_f32<TO>(q + 1, 0.f);
       continue;
     }
-    const unsigned long long e = (unsigned long long)r * C + c;
-    st_from_f32<TO>(q, ld_as_f32<TD>(d) * act_grad(act, ld_as_f32<TP>(p)) * drop_scale(dc, e));
-    st_from_f32<TO>(q + 1, ld_as_f32<TD>(d + 1) * act_grad(act, ld_as_f32<TP>(p + 1)) * drop_scale(dc, e + 1));
+    const float2 k = drop_scale2(dc, (unsigned long long)r * C + c);
+    st_from_f32<TO>(q, ld_as_f32<TD>(d) * act_grad(act, ld_as_f32<TP>(p)) * k.x);
+    st_from_f32<TO>(q + 1, ld_as_f32<TD>(d + 1) * act_grad(act, ld_as_f32<TP>(p + 1)) * k.y);
   }
 }
 
@@ -153,8 +156,8 @@ __global__ void __launch_bounds__(256) act_fwd_bf16x8_kernel(const __nv_bfloat16
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 f = bf2_to_f2(w[k]);
-        const unsigned long long e = (unsigned long long)r * C + c + 2 * k;
-        q[k] = pack_bf16x2(act_apply(act, f.x) * drop_scale(dc, e), act_apply(act, f.y) * drop_scale(dc, e + 1));
+        const float2 ks = drop_scale2(dc, (unsigned long long)r * C + c + 2 * k);
+        q[k] = pack_bf16x2(act_apply(act, f.x) * ks.x, act_apply(act, f.y) * ks.y);
       }
       o = make_uint4(q[0], q[1], q[2], q[3]);
     }
@@ -179,8 +182,8 @@ __global__ void __launch_bounds__(256) act_bwd_bf16x8_kernel(const __nv_bfloat16
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 fd = bf2_to_f2(dw[k]), fp = bf2_to_f2(pw[k]);
-        const unsigned long long e = (unsigned long long)r * C + c + 2 * k;
-        q[k] = pack_bf16x2(fd.x * act_grad(act, fp.x) * drop_scale(dc, e), fd.y * act_grad(act, fp.y) * drop_scale(dc, e + 1));
+        const float2 ks = drop_scale2(dc, (unsigned long long)r * C + c + 2 * k);
+        q[k] = pack_bf16x2(fd.x * act_grad(act, fp.x) * ks.x, fd.y * act_grad(act, fp.y) * ks.y);
       }
       o = make_uint4(q[0], q[1], q[2], q[3]);
     }
@@ -415,9 +418,9 @@ __global__ void __launch_bounds__(256) gate_resid_kernel(const float* x, long lo
     float2 xv = *reinterpret_cast<const float2*>(x + row * ldx + c);
     if (!(mask_rows && seq_lens && int(row - (long long)b * rows_per_batch) >= seq_lens[b])) {
       float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(y + row * ldy + c));
-      const unsigned long long e = (unsigned long long)row * C + c;
-      yv.x *= drop_scale(dc, e);
-      yv.y *= drop_scale(dc, e + 1);
+      const float2 ks = drop_scale2(dc, (unsigned long long)row * C + c);
+      yv.x *= ks.x;
+      yv.y *= ks.y;
       const float2 gv = *reinterpret_cast<const float2*>(gate + (long long)b * gate_ld + c);
       xv.x = fmaf(gv.x, yv.x, xv.x);
       xv.y = fmaf(gv.y, yv.y, xv.y);
@@ -471,8 +474,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
     for (int i = 0; i < V2; ++i) {
       const float2 d = *reinterpret_cast<const float2*>(a.dx + row * a.lddx + 2 * (lane + 32 * i));
       const float2 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(a.y + row * a.ldy + 2 * (lane + 32 * i)));
-      const unsigned long long e = (unsigned long long)row * C + 2 * (lane + 32 * i);
-      const float k0 = drop_scale(a.dc, e), k1 = drop_scale(a.dc, e + 1);
+      const float2 ks = drop_scale2(a.dc, (unsigned long long)row * C + 2 * (lane + 32 * i));
+      const float k0 = ks.x, k1 = ks.y;
       dg[i].x += d.x * yv.x * k0;
       dg[i].y += d.y * yv.y * k1;
       const float o0 = d.x * gv[i].x * k0, o1 = d.y * gv[i].y * k1;
