@@ -74,6 +74,21 @@ extern "C" int oron_ln_bwd(const float* x, int64_t ldx, const void* dy_bf16, int
   const int rpc = tr_rows_for((long long)rows_per_batch * nbatch, num_sms());
   LnBwdArgs a{x, ldx, reinterpret_cast<const __nv_bfloat16*>(dy_bf16), lddy, rows_per_batch, nbatch, eps, scale, mod_ld,
               add_one, seq_lens, dx, lddx, accumulate, dscale, dshift, dmod_ld, rpc};
+  const bool vec4 = C % 128 == 0 && ldx % 4 == 0 && lddx % 4 == 0 && lddy % 4 == 0 && mod_ld % 4 == 0 && dmod_ld % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(scale) |
+                      reinterpret_cast<uintptr_t>(dscale) | reinterpret_cast<uintptr_t>(dshift)) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dy_bf16) & 7) == 0;
+  if (vec4) {
+    dim3 g2(unsigned((rows_per_batch + 4 * TR2_ROWS - 1) / (4 * TR2_ROWS)), unsigned(nbatch));
+    switch (C) {
+      case 128: ln_bwd2_kernel<1><<<g2, 128, 0, ST(stream)>>>(a); break;
+      case 256: ln_bwd2_kernel<2><<<g2, 128, 0, ST(stream)>>>(a); break;
+      case 512: ln_bwd2_kernel<4><<<g2, 128, 0, ST(stream)>>>(a); break;
+      case 1024: ln_bwd2_kernel<8><<<g2, 128, 0, ST(stream)>>>(a); break;
+      default: return fail(ORON_ERR_UNSUPPORTED, "ln_bwd: C = %d", C);
+    }
+    return check_launch("ln_bwd");
+  }
   dim3 grid(unsigned((rows_per_batch + rpc - 1) / rpc), unsigned(nbatch));
   DISPATCH_V2(C, (ln_bwd_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("ln_bwd");
@@ -159,6 +174,21 @@ extern "C" int oron_gate_bwd(const float* dx, int64_t lddx, const void* y_bf16, 
   const int rpc = tr_rows_for((long long)rows_per_batch * nbatch, num_sms());
   GateBwdArgs a{dx, lddx, reinterpret_cast<const __nv_bfloat16*>(y_bf16), ldy, rows_per_batch, nbatch, gate, gate_ld,
                 seq_lens, reinterpret_cast<__nv_bfloat16*>(dy_bf16), lddy, dgate, dgate_ld, rpc, drop_cfg(dropout_p, dropout_seed), dbias};
+  const bool vec4 = C % 128 == 0 && lddx % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && gate_ld % 4 == 0 && dgate_ld % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(dgate) |
+                      reinterpret_cast<uintptr_t>(dbias)) & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(dy_bf16)) & 7) == 0;
+  if (vec4) {
+    dim3 g2(unsigned((rows_per_batch + 4 * TR2_ROWS - 1) / (4 * TR2_ROWS)), unsigned(nbatch));
+    switch (C) {
+      case 128: gate_bwd2_kernel<1><<<g2, 128, 0, ST(stream)>>>(a); break;
+      case 256: gate_bwd2_kernel<2><<<g2, 128, 0, ST(stream)>>>(a); break;
+      case 512: gate_bwd2_kernel<4><<<g2, 128, 0, ST(stream)>>>(a); break;
+      case 1024: gate_bwd2_kernel<8><<<g2, 128, 0, ST(stream)>>>(a); break;
+      default: return fail(ORON_ERR_UNSUPPORTED, "gate_bwd: C = %d", C);
+    }
+    return check_launch("gate_bwd");
+  }
   dim3 grid(unsigned((rows_per_batch + rpc - 1) / rpc), unsigned(nbatch));
   DISPATCH_V2(C, (gate_bwd_kernel<V2><<<grid, 256, 0, ST(stream)>>>(a)));
   return check_launch("gate_bwd");

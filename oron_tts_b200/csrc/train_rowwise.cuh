@@ -488,6 +488,149 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
   if (a.dbias != nullptr) cta_colsum_atomic<V2>(db, red, a.dbias);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Second-generation column-reducing kernels (C a multiple of 128): a warp owns TR2_ROWS consecutive rows, each lane four
+// CONTIGUOUS columns per 128-column group (float4 / 8-byte bf16 accesses), per-lane register accumulators for the column
+// sums, flushed straight to global memory with red.global.add.v4.f32 -- no shared memory, no block barriers. CTAs of 128
+// threads (4 warps) so that several fit an SM.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TR2_ROWS = 8;  // rows per warp
+__device__ __forceinline__ void red_add_v4(float* p, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 bf4_to_f4(const uint2 u) {
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <int V4>
+__global__ void __launch_bounds__(128) gate_bwd2_kernel(const GateBwdArgs a) {
+  constexpr int C = 128 * V4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+  const int t0 = (blockIdx.x * 4 + warp) * TR2_ROWS;
+  if (t0 >= a.rows_per_batch) return;
+  float4 gv[V4], dg[V4], db[V4];
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    gv[i] = *reinterpret_cast<const float4*>(a.gate + (long long)b * a.gate_ld + 4 * (lane + 32 * i));
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int t1 = min(t0 + TR2_ROWS, a.rows_per_batch);
+  for (int t = t0; t < t1; ++t) {
+    const long long row = (long long)b * a.rows_per_batch + t;
+    uint2* out = reinterpret_cast<uint2*>(a.dy + row * a.lddy);
+    if (t >= len) {
+#pragma unroll
+      for (int i = 0; i < V4; ++i) out[lane + 32 * i] = make_uint2(0u, 0u);
+      continue;
+    }
+    float4 d[V4];
+    uint2 yb[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      d[i] = *reinterpret_cast<const float4*>(a.dx + row * a.lddx + 4 * (lane + 32 * i));
+      yb[i] = *reinterpret_cast<const uint2*>(a.y + row * a.ldy + 4 * (lane + 32 * i));
+    }
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const float4 yv = bf4_to_f4(yb[i]);
+      const unsigned long long e = (unsigned long long)row * C + 4 * (lane + 32 * i);
+      const float2 k01 = drop_scale2(a.dc, e), k23 = drop_scale2(a.dc, e + 2);
+      dg[i].x += d[i].x * yv.x * k01.x;
+      dg[i].y += d[i].y * yv.y * k01.y;
+      dg[i].z += d[i].z * yv.z * k23.x;
+      dg[i].w += d[i].w * yv.w * k23.y;
+      const float4 o = make_float4(d[i].x * gv[i].x * k01.x, d[i].y * gv[i].y * k01.y, d[i].z * gv[i].z * k23.x,
+                                   d[i].w * gv[i].w * k23.y);
+      db[i].x += o.x; db[i].y += o.y; db[i].z += o.z; db[i].w += o.w;
+      out[lane + 32 * i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    if (a.dgate) red_add_v4(a.dgate + (long long)b * a.dgate_ld + 4 * (lane + 32 * i), dg[i]);
+    if (a.dbias) red_add_v4(a.dbias + 4 * (lane + 32 * i), db[i]);
+  }
+}
+
+template <int V4>
+__global__ void __launch_bounds__(128) ln_bwd2_kernel(const LnBwdArgs a) {
+  constexpr int C = 128 * V4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int len = a.seq_lens ? min(a.seq_lens[b], a.rows_per_batch) : a.rows_per_batch;
+  const int t0 = (blockIdx.x * 4 + warp) * TR2_ROWS;
+  if (t0 >= a.rows_per_batch) return;
+  const float one = a.add_one ? 1.f : 0.f;
+  const float4* mult = reinterpret_cast<const float4*>(a.scale + (long long)b * a.mod_ld);  // re-read per row (L1 resident)
+  float4 ds[V4], dh[V4];
+#pragma unroll
+  for (int i = 0; i < V4; ++i) ds[i] = dh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int t1 = min(t0 + TR2_ROWS, a.rows_per_batch);
+  for (int t = t0; t < t1; ++t) {
+    const long long row = (long long)b * a.rows_per_batch + t;
+    float4* dxr = reinterpret_cast<float4*>(a.dx + row * a.lddx);
+    if (t >= len) {
+      if (!a.accumulate) {
+#pragma unroll
+        for (int i = 0; i < V4; ++i) dxr[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
+    float4 v[V4];
+    uint2 db[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(a.x + row * a.ldx + 4 * (lane + 32 * i));
+      db[i] = *reinterpret_cast<const uint2*>(a.dy + row * a.lddy + 4 * (lane + 32 * i));
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum_t(s) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    const float rstd = rsqrtf(warp_sum_t(ss) * (1.0f / C) + a.eps);
+    float4 g[V4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const float4 d = bf4_to_f4(db[i]);
+      const float4 m = __ldg(mult + lane + 32 * i);
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xhat
+      ds[i].x += d.x * v[i].x; ds[i].y += d.y * v[i].y; ds[i].z += d.z * v[i].z; ds[i].w += d.w * v[i].w;
+      dh[i].x += d.x; dh[i].y += d.y; dh[i].z += d.z; dh[i].w += d.w;
+      g[i] = make_float4(d.x * (one + m.x), d.y * (one + m.y), d.z * (one + m.z), d.w * (one + m.w));
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+    }
+    const float m1 = warp_sum_t(s1) * (1.0f / C);
+    const float m2 = warp_sum_t(s2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      float4 o = make_float4(rstd * (g[i].x - m1 - v[i].x * m2), rstd * (g[i].y - m1 - v[i].y * m2),
+                             rstd * (g[i].z - m1 - v[i].z * m2), rstd * (g[i].w - m1 - v[i].w * m2));
+      if (a.accumulate) {
+        const float4 old = dxr[lane + 32 * i];
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      dxr[lane + 32 * i] = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    if (a.dscale) red_add_v4(a.dscale + (long long)b * a.dmod_ld + 4 * (lane + 32 * i), ds[i]);
+    if (a.dshift) red_add_v4(a.dshift + (long long)b * a.dmod_ld + 4 * (lane + 32 * i), dh[i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // depthwise conv k=7 (f32), forward / data gradient (flip) and weight gradient
 // ---------------------------------------------------------------------------------------------------------
