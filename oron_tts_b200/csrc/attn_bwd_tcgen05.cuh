@@ -1,7 +1,8 @@
 // Backward of the varlen non-causal attention (head_dim 64) on tcgen05 / TMEM: one CTA per (batch, head, 128-row owner
-// tile). Every 128-row operand tile (TMA, double buffered) is consumed as two 64-column sub-tiles with their own
-// S / dP accumulators in TMEM (2 x (64 + 64) columns), so the tensor core computes S / dP of sub-tile n + 1 and the
-// accumulating MMAs of sub-tile n - 1 while the CUDA cores turn S / dP of sub-tile n into dS (and P^T).
+// tile). The 128-row operand tiles arrive by TMA (double buffered); S and dP are 128 x 128 accumulators in TMEM that the
+// CUDA cores copy to registers and release at once, so the tensor core computes S / dP of tile j + 1 (N = 128 MMAs: the
+// single issuing thread is the bound, wide instructions are cheapest per FLOP) and the accumulating MMAs of tile j while
+// the CUDA cores turn tile j into dS (and P^T).
 //
 //   MODE 0 (dQ):    owner = 128 queries. Pre-pass over the key tiles: S = Q K^T -> log2-domain log-sum-exp per row
 //                   (written to `lse` together with delta = rowsum(dO * O)). Main pass per key tile j:
@@ -36,15 +37,15 @@ struct AttnBwdArgs {
   int have_lse;  // 1: `lse` was written by the forward kernel (oron_attention_fwd_lse): MODE 0 skips its pre-pass
 };
 
-constexpr int AB_THREADS = 288;  // warp 0: TMA + MMA issue (+ TMEM alloc); warps 1..8: two threads per owner row
-                                 // (warp & 3 = TMEM lane quarter, (warp - 1) >> 2 = which 64 of the tile's 128 columns)
+constexpr int AB_THREADS = 544;  // warp 0: TMA + MMA issue (+ TMEM alloc); warps 1..16: four threads per owner row
+                                 // (warp & 3 = TMEM lane quarter, (warp - 1) >> 2 = which 32 of the tile's 128 columns)
 constexpr int AB_TILE = 128;
 constexpr int AB_D = 64;
 constexpr int AB_TILE_BYTES = AB_TILE * AB_D * 2;  // 16 KB
 constexpr int AB_TMEM_COLS = 512;
 // smem: X1 | X2 | Y1[0] Y2[0] | Y1[1] Y2[1] | stageA (2 slabs) | stageB (2 slabs) | barriers + lse/delta staging
 // (the Y tiles of iteration it + 1 are fetched by TMA while iteration it computes)
-constexpr int AB_SMEM_BYTES = 10 * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 4 * 128 * 4 + 1024;
+constexpr int AB_SMEM_BYTES = 10 * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 8 * 128 * 4 + 1024;
 
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
@@ -120,7 +121,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     for (int u = 0; u < 2; ++u) {
       mbar_init(bar_y(u), 1);
       mbar_init(bar_s(u), 1);
-      mbar_init(bar_p(u), 256);
+      mbar_init(bar_p(u), 512);
     }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
@@ -134,23 +135,25 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  // TMEM columns: [S_0 | dP_0 | S_1 | dP_1] 64 each, then the two 64-column accumulators
-  auto tmem_S = [&](int u) { return tmem_base + 128u * uint32_t(u); };
-  auto tmem_dP = [&](int u) { return tmem_base + 128u * uint32_t(u) + 64u; };
+  // TMEM columns: S (128) | dP (128) | two 64-column accumulators
+  auto tmem_S = [&](int u) { return tmem_base + 128u * uint32_t(u); };  // u = 0: S, u = 1: dP
   const uint32_t tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 320;
 
-  // sub-iterations: n = 2 * (tile index) + (which 64 columns); the optional pre-pass (no lse from the forward) walks
-  // the same sub-tiles with S only
-  const int n_pre = (MODE == 0 && !args.have_lse) ? 2 * nt : 0;
-  const int n_sub = n_pre + 2 * nt;
+  // Iterations: one per 128-row operand tile (an optional pre-pass over the same tiles computes the log-sum-exp when the
+  // forward did not supply it). S and dP are single 128-column TMEM tiles: the CUDA cores copy their 64 columns to
+  // registers first and release the tiles at once (bar_free), so the tensor core computes S / dP of tile j + 1 while
+  // tile j is turned into dS / P^T and fed to the accumulating MMAs.
+  const int n_pre = (MODE == 0 && !args.have_lse) ? nt : 0;
+  const int n_it = n_pre + nt;
+  const uint32_t bar_free = bar_p(1);  // the second bar_p slot is unused in this scheme
 
   if (warp == 0) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
       const uint64_t x1desc = make_smem_desc_sw128(sX1, 16, 1024), x2desc = make_smem_desc_sw128(sX2, 16, 1024);
       // every descriptor is base + a small multiple: no arrays (dynamic indexing would put them in local memory and each
-      // tcgen05.mma issue behind a load). Buffer st of the Y tiles is 2 tiles further (>> 4: 2048), staging slab u one
+      // tcgen05.mma issue behind a load). Buffer st of the Y tiles is 2 tiles further (>> 4: 2048), staging slab 1 one
       // tile further (1024).
       const uint64_t y1d = make_smem_desc_sw128(sY1(0), 16, 1024), y2d = make_smem_desc_sw128(sY2(0), 16, 1024);
       const uint64_t y1m = make_smem_desc_sw128(sY1(0), 1024, 1024), y2m = make_smem_desc_sw128(sY2(0), 1024, 1024);
@@ -165,11 +168,10 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         tma_load_3d(sX1, &tmQK, bar_x, HD + h * AB_D, tile * AB_TILE, b);  // K
         tma_load_3d(sX2, &tmV, bar_x, h * AB_D, tile * AB_TILE, b);        // V
       }
-      const int n_tiles = n_sub / 2;  // operand tiles over both passes
-      auto fetch = [&](int ti) {      // the Y tiles of tile-iteration ti into buffer ti & 1
-        const bool pre = 2 * ti < n_pre;
-        const int j = pre ? ti : ti - n_pre / 2;
-        const int st = ti & 1;
+      auto fetch = [&](int it) {  // the Y tiles of iteration `it` into buffer it & 1
+        const bool pre = it < n_pre;
+        const int j = pre ? it : it - n_pre;
+        const int st = it & 1;
         mbar_arrive_expect_tx(bar_y(st), (pre ? 1 : 2) * AB_TILE_BYTES);
         if (MODE == 0) {
           tma_load_3d(sY1(st), &tmQK, bar_y(st), HD + h * AB_D, j * AB_TILE, b);  // K_j
@@ -179,77 +181,68 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           tma_load_3d(sY2(st), &tmDO, bar_y(st), h * AB_D, j * AB_TILE, b);   // dO_i
         }
       };
-      // S_u / dP_u of sub-iteration n (u = n & 1): the 64 rows [64 u, 64 u + 64) of the Y tiles as the N dimension
-      auto issue_sdp = [&](int n) {
-        const int ti = n >> 1, u = n & 1, st = ti & 1;
-        if (u == 0) {
-          mbar_wait(bar_y(st), (ti >> 1) & 1u, 2);
-          tc_fence_after();
-        }
-        const uint64_t roff = uint64_t(u) * (64u * 128u >> 4);  // 64 rows of 128 bytes
-        // accumulating MMAs into one TMEM tile form a dependent chain (~130 cycles per link against ~65 for independent
-        // instructions): the S and dP chains are interleaved
-        const bool with_dp = n >= n_pre;
+      auto issue_sdp = [&](int it) {
+        const int st = it & 1;
+        mbar_wait(bar_y(st), (it >> 1) & 1u, 2);
+        tc_fence_after();
+        const bool with_dp = it >= n_pre;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16_ss(tmem_S(u), x1desc + uint64_t(2 * k), (y1d + kBuf * uint64_t(st)) + roff + uint64_t(2 * k), idesc_s, k != 0);
-          if (with_dp) umma_bf16_ss(tmem_dP(u), x2desc + uint64_t(2 * k), (y2d + kBuf * uint64_t(st)) + roff + uint64_t(2 * k), idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) {  // the S and dP chains interleaved (independent accumulators)
+          umma_bf16_ss(tmem_S(0), x1desc + uint64_t(2 * k), (y1d + kBuf * uint64_t(st)) + uint64_t(2 * k), idesc_s, k != 0);
+          if (with_dp) umma_bf16_ss(tmem_S(1), x2desc + uint64_t(2 * k), (y2d + kBuf * uint64_t(st)) + uint64_t(2 * k), idesc_s, k != 0);
         }
-        umma_commit(bar_s(u));
+        umma_commit(bar_s(0));
       };
+#define AB_CSTAMP(slot) do { if (args.dbg != nullptr && it == n_pre + 3) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
       fetch(0);
       mbar_wait(bar_x, 0, 1);
       issue_sdp(0);
       int n_acc = 0;  // bar_acc phases committed so far (one per main tile)
-#define AB_CSTAMP(slot) do { if (args.dbg != nullptr && n == n_pre + 6) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
-      for (int n = 0; n < n_sub; ++n) {
-        const int ti = n >> 1, u = n & 1, st = ti & 1;
-        const bool pre = n < n_pre;
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const bool pre = it < n_pre;
         AB_CSTAMP(8);
-        // TMEM buffer (n + 1) & 1 was released by the bar_p wait of sub-iteration n - 1 (below, previous turn)
-        AB_CSTAMP(9);
-        if (n + 1 < n_sub) issue_sdp(n + 1);
-        AB_CSTAMP(10);
-        if (u == 0 && ti + 1 < n_tiles) {
-          // buffer (ti + 1) & 1 was last read by the MMAs of tile ti - 1: S / dP (retired: their bar_p waits are behind
-          // us) and, in the main pass, the accumulating MMAs committed to bar_acc
-          if (n_acc > 0) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
-          fetch(ti + 1);
+        if (it + 1 < n_it) {
+          // buffer (it + 1) & 1 was last read by the MMAs of iteration it - 1 (S / dP: retired, their tiles were consumed;
+          // accumulating MMAs: committed to bar_acc)
+          if (n_acc > 0 && it - 1 >= n_pre) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
+          fetch(it + 1);
         }
-        mbar_wait(bar_p(u), (n >> 1) & 1u, 3);  // S_u / dP_u consumed; staging slab u written
+        AB_CSTAMP(9);
+        mbar_wait(bar_free, it & 1u, 8);  // S / dP of this iteration are in registers: the tiles may be overwritten
+        if (it + 1 < n_it) issue_sdp(it + 1);
+        AB_CSTAMP(10);
+        mbar_wait(bar_p(0), it & 1u, 3);  // staging written
         AB_CSTAMP(11);
         if (!pre) {
           tc_fence_after();
-          const int j = ti - n_pre / 2;
-          const uint32_t accf = (j == 0 && u == 0) ? 0u : 1u;
+          const int j = it - n_pre;
+          const uint32_t accf = j == 0 ? 0u : 1u;
           if (MODE == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // dQ += dS[:, 64 u ..] K_j[64 u .., :]; even / odd k-steps into two accumulators
-                                         // (two interleaved dependent chains instead of one), summed in the epilogue
-              umma_bf16_ss((k & 1) ? tmem_acc1 : tmem_acc2, (ad + kSlab * uint64_t(u)) + uint64_t(2 * k),
-                           (y1m + kBuf * uint64_t(st)) + uint64_t(128 * (4 * u + k)), idesc_acc, k >= 2 ? 1u : accf);
+            for (int kk = 0; kk < 8; ++kk)  // dQ += dS K_j; even / odd k-steps into two accumulators, summed in the epilogue
+              umma_bf16_ss((kk & 1) ? tmem_acc1 : tmem_acc2, (ad + kSlab * uint64_t(kk >> 2)) + uint64_t(2 * (kk & 3)),
+                           (y1m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc, kk >= 2 ? 1u : accf);
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // dV += P^T dO_i and dK += dS^T Q_i, interleaved (independent chains)
-              umma_bf16_ss(tmem_acc1, (ad + kSlab * uint64_t(u)) + uint64_t(2 * k), (y2m + kBuf * uint64_t(st)) + uint64_t(128 * (4 * u + k)), idesc_acc,
-                           k != 0 ? 1u : accf);
-              umma_bf16_ss(tmem_acc2, (bd + kSlab * uint64_t(u)) + uint64_t(2 * k), (y1m + kBuf * uint64_t(st)) + uint64_t(128 * (4 * u + k)), idesc_acc,
-                           k != 0 ? 1u : accf);
+            for (int kk = 0; kk < 8; ++kk) {  // dV += P^T dO_i and dK += dS^T Q_i, interleaved
+              umma_bf16_ss(tmem_acc1, (ad + kSlab * uint64_t(kk >> 2)) + uint64_t(2 * (kk & 3)),
+                           (y2m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc, kk != 0 ? 1u : accf);
+              umma_bf16_ss(tmem_acc2, (bd + kSlab * uint64_t(kk >> 2)) + uint64_t(2 * (kk & 3)),
+                           (y1m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc, kk != 0 ? 1u : accf);
             }
           }
-          if (u == 1) {
-            umma_commit(bar_acc);
-            ++n_acc;
-          }
+          umma_commit(bar_acc);
+          ++n_acc;
         }
         AB_CSTAMP(12);
       }
     }
     __syncwarp();
   } else {
-    // ===================== two threads per owner row =====================
+    // ===================== four threads per owner row =====================
     const int q4 = warp & 3;
-    const int half = (warp - 1) >> 2;  // columns [32 * half, 32 * half + 32) of every 64-column sub-tile
+    const int quad = (warp - 1) >> 2;  // columns [32 * quad, 32 * quad + 32) of every 128-column tile
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = uint32_t(q4 * 32) << 16;
     const int t_own = tile * AB_TILE + r;
@@ -266,8 +259,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       {
         const int tid = int(threadIdx.x) - 32;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = i * 256 + tid;
+        for (int i = 0; i < 2; ++i) {
+          const int q = i * 512 + tid;
           const int row = q >> 3, k = q & 7;
           const int t = tile * AB_TILE + row;
           float part = 0.f;
@@ -286,21 +279,20 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           part += __shfl_xor_sync(0xffffffffu, part, 4);
           if (k == 0) s_stat[128 + row] = part;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         delta = s_stat[128 + r];
       }
-      // ---- pre-pass (no lse from the forward): log-sum-exp of the row, log2 domain; each thread covers its 32 columns of
-      // every sub-tile, the two partial (max, sum) pairs of a row are combined through shared memory ----
+      // ---- pre-pass (no lse from the forward): log-sum-exp of the row, log2 domain; each thread covers its 64 columns of
+      // every tile, the two partial (max, sum) pairs of a row are combined through shared memory ----
       float m = -INFINITY, l = 0.f;
-      for (int n = 0; n < n_pre; ++n) {
-        const int u = n & 1;
-        const int nv = min(AB_TILE, len - (n >> 1) * AB_TILE);
-        const int c0 = 64 * u + 32 * half;
-        mbar_wait(bar_s(u), (n >> 1) & 1u, 5);
+      for (int it = 0; it < n_pre; ++it) {
+        const int nv = min(AB_TILE, len - it * AB_TILE);
+        mbar_wait(bar_s(0), it & 1u, 5);
         tc_fence_after();
-        if (c0 < nv) {
+        for (int c0 = 32 * quad; c0 < 32 * quad + 32; c0 += 32) {
+          if (c0 >= nv) break;
           uint32_t v[32];
-          ab_tmem_ld32(tmem_S(u) + lane_off + 32 * half, v);
+          ab_tmem_ld32(tmem_S(0) + lane_off + c0, v);
           tmem_wait_ld();
           float cm = -INFINITY;
 #pragma unroll
@@ -315,21 +307,25 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           m = mn;
         }
         tc_fence_before();
-        mbar_arrive(bar_p(u));
+        mbar_arrive(bar_free);
+        mbar_arrive(bar_p(0));
       }
       if (!args.have_lse) {
-        s_stat[256 + 2 * (128 * half + r)] = m;
-        s_stat[256 + 2 * (128 * half + r) + 1] = l;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float m0 = s_stat[256 + 2 * r], l0 = s_stat[256 + 2 * r + 1];
-        const float m1 = s_stat[256 + 2 * (128 + r)], l1 = s_stat[256 + 2 * (128 + r) + 1];
-        const float mm = fmaxf(m0, m1);
+        s_stat[256 + 2 * (128 * quad + r)] = m;
+        s_stat[256 + 2 * (128 * quad + r) + 1] = l;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float mm = -INFINITY;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) mm = fmaxf(mm, s_stat[256 + 2 * (128 * qq + r)]);
         float ll = 0.f;
-        if (m0 > -INFINITY) ll += l0 * ex2_approx(m0 - mm);
-        if (m1 > -INFINITY) ll += l1 * ex2_approx(m1 - mm);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float mq = s_stat[256 + 2 * (128 * qq + r)];
+          if (mq > -INFINITY) ll += s_stat[256 + 2 * (128 * qq + r) + 1] * ex2_approx(mq - mm);
+        }
         lse2 = mm + log2f(ll);
       }
-      if (half == 0 && t_own < args.rows_per_batch) {
+      if (quad == 0 && t_own < args.rows_per_batch) {
         if (!args.have_lse) args.lse[stat_base + t_own] = lse2;
         args.delta[stat_base + t_own] = delta;
       }
@@ -337,43 +333,48 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     if (MODE == 0) lse2 -= log2f(args.scale);  // ps = scale * P straight out of the exp2
     AB_STAMP(1);
     // ---- main pass ----
-    for (int n = n_pre; n < n_sub; ++n) {
-      const int u = n & 1;
-      const int j = (n - n_pre) >> 1;
+    for (int it = n_pre; it < n_it; ++it) {
+      const int j = it - n_pre;
       const int nv = min(AB_TILE, len - j * AB_TILE);  // valid columns of this tile (keys in MODE 0, queries in MODE 1)
       const float* st = s_stat + (j & 1) * 256;
-      if (MODE == 1 && u == 0) {
+      if (MODE == 1) {
         const int tq = j * AB_TILE + r;
         float* sw_ = s_stat + (j & 1) * 256;
-        const float* src = half == 0 ? args.lse : args.delta;
-        const float sv = tq < args.rows_per_batch ? src[stat_base + tq] : 0.f;
-        sw_[128 * half + r] = half == 0 ? sv : -args.scale * sv;  // (lse, -scale * delta)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (quad < 2) {
+          const float* src = quad == 0 ? args.lse : args.delta;
+          const float sv = tq < args.rows_per_batch ? src[stat_base + tq] : 0.f;
+          sw_[128 * quad + r] = quad == 0 ? sv : -args.scale * sv;  // (lse, -scale * delta)
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
-      if (n == n_pre + 6) AB_STAMP(13);
-      mbar_wait(bar_s(u), (n >> 1) & 1u, 6);
+      if (it == n_pre + 3) AB_STAMP(13);
+      mbar_wait(bar_s(0), it & 1u, 6);
       tc_fence_after();
-      if (n == n_pre) AB_STAMP(2);
-      if (n == n_pre + 2) AB_STAMP(3);
-      if (n == n_pre + 6) AB_STAMP(14);
-      {
-        const int c0 = 64 * u + 32 * half;  // column inside the 128-wide tile
-        uint32_t vs[32], vd[32];
-        ab_tmem_ld32(tmem_S(u) + lane_off + 32 * half, vs);
-        ab_tmem_ld32(tmem_dP(u) + lane_off + 32 * half, vd);
-        tmem_wait_ld();
+      if (it == n_pre) AB_STAMP(2);
+      if (it == n_pre + 1) AB_STAMP(3);
+      if (it == n_pre + 3) AB_STAMP(14);
+      // this thread's 32 columns of S and dP to registers, then the TMEM tiles are free for the next iteration's MMAs
+      uint32_t vs[1][32], vd[1][32];
+      ab_tmem_ld32(tmem_S(0) + lane_off + 32 * quad, vs[0]);
+      ab_tmem_ld32(tmem_S(1) + lane_off + 32 * quad, vd[0]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_free);
+      const bool fast = own_valid && nv == AB_TILE;  // nv is CTA-uniform
+#pragma unroll
+      for (int cc = 0; cc < 1; ++cc) {
+        const int c0 = 32 * quad;  // column inside the 128-wide tile
         uint32_t pp[16], pd[16];
         // MODE 0: the softmax scale is folded into the exponent (lse2 holds lse - log2(scale)): ps = scale * P in one
         // exp2, dS = ps * (dP - delta). MODE 1: the staged column statistics are (lse, -scale * delta), so that
         // dS^T = P^T * fma(dP^T, scale, -scale * delta). Full tiles of valid rows skip the masks.
-        const bool fast = own_valid && nv == AB_TILE;  // nv is CTA-uniform
         if (fast) {
           if (MODE == 0) {
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(vs[k]), c, -lse2));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(vs[k + 1]), c, -lse2));
-              pd[k >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[k]) - delta), p1 * (__uint_as_float(vd[k + 1]) - delta));
+              const float p0 = ex2_approx(fmaf(__uint_as_float(vs[cc][k]), c, -lse2));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(vs[cc][k + 1]), c, -lse2));
+              pd[k >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[cc][k]) - delta), p1 * (__uint_as_float(vd[cc][k + 1]) - delta));
             }
           } else {
             const float4* sl = reinterpret_cast<const float4*>(st + c0);
@@ -385,8 +386,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
               float pv[4], dv[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                pv[e] = ex2_approx(fmaf(__uint_as_float(vs[4 * k4 + e]), c, -ll[e]));
-                dv[e] = pv[e] * fmaf(__uint_as_float(vd[4 * k4 + e]), args.scale, ee[e]);
+                pv[e] = ex2_approx(fmaf(__uint_as_float(vs[cc][4 * k4 + e]), c, -ll[e]));
+                dv[e] = pv[e] * fmaf(__uint_as_float(vd[cc][4 * k4 + e]), args.scale, ee[e]);
               }
               pp[2 * k4] = pack_bf16x2(pv[0], pv[1]);
               pp[2 * k4 + 1] = pack_bf16x2(pv[2], pv[3]);
@@ -401,17 +402,20 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
             const float l0 = MODE == 0 ? lse2 : st[c0 + k], l1 = MODE == 0 ? lse2 : st[c0 + k + 1];
             const float e0 = MODE == 0 ? delta : st[128 + c0 + k], e1 = MODE == 0 ? delta : st[128 + c0 + k + 1];
             if (own_valid && c0 + k < nv) {
-              p0 = ex2_approx(fmaf(__uint_as_float(vs[k]), c, -l0));
-              d0 = MODE == 0 ? p0 * (__uint_as_float(vd[k]) - e0) : p0 * fmaf(__uint_as_float(vd[k]), args.scale, e0);
+              p0 = ex2_approx(fmaf(__uint_as_float(vs[cc][k]), c, -l0));
+              d0 = MODE == 0 ? p0 * (__uint_as_float(vd[cc][k]) - e0) : p0 * fmaf(__uint_as_float(vd[cc][k]), args.scale, e0);
             }
             if (own_valid && c0 + k + 1 < nv) {
-              p1 = ex2_approx(fmaf(__uint_as_float(vs[k + 1]), c, -l1));
-              d1 = MODE == 0 ? p1 * (__uint_as_float(vd[k + 1]) - e1) : p1 * fmaf(__uint_as_float(vd[k + 1]), args.scale, e1);
+              p1 = ex2_approx(fmaf(__uint_as_float(vs[cc][k + 1]), c, -l1));
+              d1 = MODE == 0 ? p1 * (__uint_as_float(vd[cc][k + 1]) - e1) : p1 * fmaf(__uint_as_float(vd[cc][k + 1]), args.scale, e1);
             }
             pp[k >> 1] = pack_bf16x2(p0, p1);
             pd[k >> 1] = pack_bf16x2(d0, d1);
           }
         }
+        // the staging tiles still feed the previous iteration's accumulating MMAs: wait for them only now, with this
+        // iteration's arithmetic already done
+        if (j > 0) mbar_wait(bar_acc, (j - 1) & 1u, 9);
         if (MODE == 0) {
           ab_stage_store(sA, r, c0, pd);
         } else {
@@ -421,8 +425,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p(u));
-      if (n == n_pre + 6) AB_STAMP(15);
+      mbar_arrive(bar_p(0));
+      if (it == n_pre + 3) AB_STAMP(15);
     }
     AB_STAMP(4);
     // ---- read the accumulators ----
@@ -432,31 +436,24 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     // Phase A: the accumulator rows go to shared memory as f32 (row = 256 B, 16-byte chunks XOR-swizzled by row & 15)
     // in the idle staging tiles; phase B: all threads store 16-byte bf16 chunks, 8 lanes per row (coalesced), with the
     // RoPE rotation of dq / dk applied on the way (cos / sin read coalesced too).
-    auto to_smem = [&](uint32_t tm, uint32_t tile_s, uint32_t tm_add) {  // tm_add != 0: a second accumulator to add
-      uint32_t lo[32], hi[32];
-      ab_tmem_ld32(tm + lane_off, lo);
-      ab_tmem_ld32(tm + lane_off + 32, hi);
+    // columns [32 ch, 32 ch + 32) of an accumulator row (ch = 0 / 1), plus optionally the same columns of a second one
+    auto to_smem = [&](uint32_t tm, uint32_t tile_s, uint32_t tm_add, int ch) {
+      uint32_t lo[32];
+      ab_tmem_ld32(tm + lane_off + 32 * ch, lo);
       tmem_wait_ld();
       if (tm_add != 0u) {
-        uint32_t lo2[32], hi2[32];
-        ab_tmem_ld32(tm_add + lane_off, lo2);
-        ab_tmem_ld32(tm_add + lane_off + 32, hi2);
+        uint32_t lo2[32];
+        ab_tmem_ld32(tm_add + lane_off + 32 * ch, lo2);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          lo[i] = __float_as_uint(__uint_as_float(lo[i]) + __uint_as_float(lo2[i]));
-          hi[i] = __float_as_uint(__uint_as_float(hi[i]) + __uint_as_float(hi2[i]));
-        }
+        for (int i = 0; i < 32; ++i) lo[i] = __float_as_uint(__uint_as_float(lo[i]) + __uint_as_float(lo2[i]));
       }
       const uint32_t rowa = tile_s + uint32_t(r) * 256u;
       const uint32_t sw = uint32_t(r & 15);
 #pragma unroll
-      for (int cidx = 0; cidx < 8; ++cidx) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((uint32_t(cidx) ^ sw) << 4)), "r"(lo[4 * cidx]),
+      for (int cidx = 0; cidx < 8; ++cidx)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((uint32_t(cidx + 8 * ch) ^ sw) << 4)), "r"(lo[4 * cidx]),
                      "r"(lo[4 * cidx + 1]), "r"(lo[4 * cidx + 2]), "r"(lo[4 * cidx + 3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((uint32_t(cidx + 8) ^ sw) << 4)), "r"(hi[4 * cidx]),
-                     "r"(hi[4 * cidx + 1]), "r"(hi[4 * cidx + 2]), "r"(hi[4 * cidx + 3]) : "memory");
-      }
     };
     auto ld_chunk = [&](uint32_t tile_s, int row, int cidx, float (&f)[4]) {
       uint32_t a0, a1, a2, a3;
@@ -501,17 +498,17 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     };
     const int tid = int(threadIdx.x) - 32;
     if (MODE == 0) {
-      if (half == 0) to_smem(tmem_acc2, sA, tmem_acc1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (quad < 2) to_smem(tmem_acc2, sA, tmem_acc1, quad);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) store_task(sA, i * 256 + tid, 0, true);
+      for (int i = 0; i < 2; ++i) store_task(sA, i * 512 + tid, 0, true);
     } else {
-      if (half == 0) to_smem(tmem_acc1, sA, 0u); else to_smem(tmem_acc2, sB, 0u);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (quad < 2) to_smem(tmem_acc1, sA, 0u, quad); else to_smem(tmem_acc2, sB, 0u, quad - 2);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
 #pragma unroll 1
-      for (int i = 0; i < 8; ++i) {
-        if (half == 0) store_task(sA, i * 128 + (tid & 127), 2 * HD, false);
-        else store_task(sB, i * 128 + (tid & 127), HD, true);
+      for (int i = 0; i < 4; ++i) {
+        if (quad < 2) store_task(sA, i * 256 + (tid & 255), 2 * HD, false);
+        else store_task(sB, i * 256 + (tid & 255), HD, true);
       }
     }
     AB_STAMP(6);
