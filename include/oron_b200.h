@@ -47,6 +47,10 @@ enum oron_epilogue {
   ORON_EPI_MISH_MASK_BF16 = 5,  /* out_bf16 = valid ? mish(acc + bias) : 0 (modules.py:137-140) */
   ORON_EPI_MISH_MASK_RESID = 6, /* out_f32 = (valid ? mish(acc + bias) : 0) + addend (dit.py:54) */
   ORON_EPI_SCALE_RESID = 7,     /* out_f32 = valid ? addend + colscale * (acc + bias) : 0 (modules.py:185, encoder.py:94) */
+  /* training-step fusions of FeedForward (modules.py:294-297), two_sm only; the dropout mask is the stateless hash of
+   * oron_b200_train.h over element index row * N + col (dropout_p = 0: none) */
+  ORON_EPI_GELU_DROP_DUAL = 8,  /* out2_bf16 = pre = acc + bias ; out_bf16 = dropout(gelu_tanh(pre)) */
+  ORON_EPI_GELU_DROP_BWD = 9,   /* out_bf16 = acc * gelu_tanh'(out2_bf16[row, col]) * mask  (out2 is read: the saved pre-activation) */
 };
 enum oron_act { ORON_ACT_NONE = 0, ORON_ACT_GELU_TANH = 1, ORON_ACT_GELU_ERF = 2, ORON_ACT_SILU = 3 };
 
@@ -117,6 +121,8 @@ typedef struct oron_gemm_desc {
    * weight gradient dW = dY^T X: both; data gradient dX = dY W: b_mn_major only. */
   int32_t a_mn_major;
   int32_t b_mn_major;
+  float dropout_p;       /* ORON_EPI_GELU_DROP_*: dropout probability (0: off) and seed */
+  uint64_t dropout_seed;
 } oron_gemm_desc;
 
 int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);

@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("ORON_LIB_PATH") or os.path.join(_HERE, "liboron_b200.
 # ---- enums (include/oron_b200.h) -------------------------------------------------------------
 EPI_BF16, EPI_F32, EPI_QKV_ROPE, EPI_GATE_RESID = 0, 1, 2, 3
 EPI_EMBED_DUAL, EPI_MISH_MASK_BF16, EPI_MISH_MASK_RESID, EPI_SCALE_RESID = 4, 5, 6, 7
+EPI_GELU_DROP_DUAL, EPI_GELU_DROP_BWD = 8, 9
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = (
@@ -89,6 +90,8 @@ class GemmDesc(ctypes.Structure):
         ("debug_stamps", c_void_p),
         ("a_mn_major", c_int32),
         ("b_mn_major", c_int32),
+        ("dropout_p", c_float),
+        ("dropout_seed", c_uint64),
     ]
 
 
@@ -213,6 +216,8 @@ def gemm(
     a_mn: bool = False,
     b_mn: bool = False,
     k: int | None = None,
+    dropout_p: float = 0.0,
+    dropout_seed: int = 0,
 ) -> None:
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16.
 
@@ -260,6 +265,7 @@ def gemm(
     d.stream_k = int(bool(stream_k))
     d.debug_stamps = _ptr(debug_stamps, torch.int64, "debug_stamps")
     d.a_mn_major, d.b_mn_major = int(bool(a_mn)), int(bool(b_mn))
+    d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
                                          EPI_SCALE_RESID) else torch.bfloat16
     if out.dtype != want:

@@ -183,7 +183,27 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   const int epi = d->epilogue;
   // per-epilogue operand checks (vectorised epilogues assume 32-column granularity)
   const bool vec_epi = epi == EPI_QKV_ROPE || epi == EPI_GATE_RESID || epi == EPI_EMBED_DUAL ||
-                       epi == EPI_MISH_MASK_BF16 || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID;
+                       epi == EPI_MISH_MASK_BF16 || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID ||
+                       epi == EPI_GELU_DROP_DUAL || epi == EPI_GELU_DROP_BWD;
+  if ((epi == EPI_GELU_DROP_DUAL || epi == EPI_GELU_DROP_BWD) && (!d->out2 || d->ldo2 % 8 != 0 || !d->two_sm))
+    return fail(ORON_ERR_BAD_ARG, "gemm: the GELU_DROP epilogues need out2 (pre-activation, ldo2 %% 8 == 0) and two_sm");
+  {
+    float p = d->dropout_p;
+    a.drop.thresh = 0u;
+    a.drop.inv_keep = 1.f;
+    a.drop.key = 0u;
+    if (p > 0.f) {
+      if (p > 0.999f) p = 0.999f;
+      uint64_t z = d->dropout_seed + 0x9E3779B97F4A7C15ull;  // splitmix64, as in train.cu
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      a.drop.key = (unsigned int)(z >> 32) ^ (unsigned int)z;
+      a.drop.thresh = (unsigned int)((double)p * 4294967296.0);
+      if (a.drop.thresh == 0u) a.drop.thresh = 1u;
+      a.drop.inv_keep = 1.0f / (1.0f - p);
+    }
+  }
   if (vec_epi && (d->N % 32 != 0)) return fail(ORON_ERR_BAD_ARG, "gemm: epilogue %d needs N %% 32 == 0", epi);
   if (epi == EPI_QKV_ROPE && (!d->bias || !d->rope_cos || !d->rope_sin || d->N % 64 != 0 || d->block_n < 128))
     return fail(ORON_ERR_BAD_ARG, "gemm: QKV_ROPE needs bias, rope tables, N %% 64 == 0, block_n >= 128");
@@ -227,6 +247,8 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
     if (d->block_n == BN_ && epi == EPI_ && mnm == MNM_) return launch_gemm2<BN_, EPI_, MNM_>(ta, tb, a, d->max_ctas, st);
     ORON_GEMM2_MN_CASE(128, EPI_BF16, 2)
     ORON_GEMM2_MN_CASE(256, EPI_BF16, 2)
+    ORON_GEMM2_MN_CASE(128, EPI_GELU_DROP_BWD, 2)
+    ORON_GEMM2_MN_CASE(256, EPI_GELU_DROP_BWD, 2)
     ORON_GEMM2_MN_CASE(128, EPI_F32, 2)
     ORON_GEMM2_MN_CASE(256, EPI_F32, 2)
     ORON_GEMM2_MN_CASE(128, EPI_F32, 3)
@@ -247,6 +269,8 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM2_CASE(128, EPI_EMBED_DUAL)
   ORON_GEMM2_CASE(128, EPI_SCALE_RESID)
   ORON_GEMM2_CASE(256, EPI_SCALE_RESID)
+  ORON_GEMM2_CASE(128, EPI_GELU_DROP_DUAL)
+  ORON_GEMM2_CASE(256, EPI_GELU_DROP_DUAL)
 #undef ORON_GEMM2_CASE
   if (two_sm) return fail(ORON_ERR_UNSUPPORTED, "gemm: no 2-SM kernel for block_n=%d epilogue=%d", d->block_n, epi);
 #define ORON_GEMM_CASE(BN_, EPI_) \

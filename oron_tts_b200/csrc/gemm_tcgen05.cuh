@@ -23,6 +23,9 @@ enum GemmEpilogue : int {
   EPI_MISH_MASK_BF16 = 5,  // out_bf16 = valid ? mish(acc + bias) : 0
   EPI_MISH_MASK_RESID = 6, // out_f32 = (valid ? mish(acc + bias) : 0) + addend[row, col]
   EPI_SCALE_RESID = 7,     // out_f32 = valid ? addend[row,col] + colscale[col]*(acc+bias) : 0 ; opt. out_bf16
+  // training-step fusions (oron_tts_b200/train.py): FeedForward up-projection forward and its data gradient
+  EPI_GELU_DROP_DUAL = 8,  // out2_bf16 = pre = acc + bias ; out_bf16 = dropout(gelu_tanh(pre))   (modules.py:294-297)
+  EPI_GELU_DROP_BWD = 9,   // out_bf16 = acc * gelu_tanh'(aux_bf16[row, col]) * dropout mask; aux = out2 (read only)
 };
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_SILU = 3 };
@@ -67,6 +70,7 @@ struct GemmArgs {
   // The TMA box is 64 (MN, contiguous) x 64 (K rows); a 128-wide operand tile is two such 8 KB boxes, consumed through
   // MN-major SW128 descriptors (SBO = 1024: next 8 K rows, LBO = 8192: next 64 MN elements).
   int a_mn, b_mn;
+  DropCfg drop;  // EPI_GELU_DROP_*: stateless dropout mask over element index row * N + col (thresh 0: off)
 };
 
 #define ORON_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -189,6 +193,34 @@ __device__ __forceinline__ void epi_block_fast(const GemmArgs& args, const float
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow0 * args.ldo + col;
 #pragma unroll
     for (int it = 0; it < 8; ++it) *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) = pack4(act4<ACT>(v[it]));
+  } else if constexpr (EPI == EPI_GELU_DROP_DUAL) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow0 * args.ldo + col;
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(args.out2) + grow0 * args.ldo2 + col;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const unsigned long long e = (unsigned long long)(grow0 + 4 * it) * args.N + col;
+      const float2 k01 = drop_scale2(args.drop, e), k23 = drop_scale2(args.drop, e + 2);
+      *reinterpret_cast<uint2*>(o2 + (long long)it * 4 * args.ldo2) = pack4(v[it]);
+      const float4 h = map4(v[it], gelu_tanh_f);
+      *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) =
+          pack4(make_float4(h.x * k01.x, h.y * k01.y, h.z * k23.x, h.w * k23.y));
+    }
+  } else if constexpr (EPI == EPI_GELU_DROP_BWD) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow0 * args.ldo + col;
+    const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(args.out2) + grow0 * args.ldo2 + col;
+    uint2 pre[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) pre[it] = __ldg(reinterpret_cast<const uint2*>(ax + (long long)it * 4 * args.ldo2));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const unsigned long long e = (unsigned long long)(grow0 + 4 * it) * args.N + col;
+      const float2 k01 = drop_scale2(args.drop, e), k23 = drop_scale2(args.drop, e + 2);
+      const float p0 = __uint_as_float(pre[it].x << 16), p1 = __uint_as_float(pre[it].x & 0xffff0000u);
+      const float p2 = __uint_as_float(pre[it].y << 16), p3 = __uint_as_float(pre[it].y & 0xffff0000u);
+      *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) =
+          pack4(make_float4(v[it].x * gelu_tanh_grad(p0) * k01.x, v[it].y * gelu_tanh_grad(p1) * k01.y,
+                            v[it].z * gelu_tanh_grad(p2) * k23.x, v[it].w * gelu_tanh_grad(p3) * k23.y));
+    }
   } else if constexpr (EPI == EPI_F32) {
     float* o = reinterpret_cast<float*>(args.out) + grow0 * args.ldo + col;
     if (args.addend != nullptr) {
@@ -279,6 +311,22 @@ __device__ __forceinline__ void epi_block_slow(const GemmArgs& args, const uint3
       else if (args.act == ACT_GELU_ERF) v = map4(v, gelu_erf_f);
       else if (args.act == ACT_SILU) v = map4(v, silu_f);
       st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
+    } else if constexpr (EPI == EPI_GELU_DROP_DUAL || EPI == EPI_GELU_DROP_BWD) {
+      // the host guarantees N % 32 == 0 for these: only ragged ROWS reach this path
+      const unsigned long long e = (unsigned long long)grow * N + col;
+      const float2 k01 = drop_scale2(args.drop, e), k23 = drop_scale2(args.drop, e + 2);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col;
+      if constexpr (EPI == EPI_GELU_DROP_DUAL) {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col) = pack4(v);
+        const float4 h = map4(v, gelu_tanh_f);
+        *reinterpret_cast<uint2*>(o) = pack4(make_float4(h.x * k01.x, h.y * k01.y, h.z * k23.x, h.w * k23.y));
+      } else {
+        const uint2 pre = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(args.out2) + grow * args.ldo2 + col);
+        const float p0 = __uint_as_float(pre.x << 16), p1 = __uint_as_float(pre.x & 0xffff0000u);
+        const float p2 = __uint_as_float(pre.y << 16), p3 = __uint_as_float(pre.y & 0xffff0000u);
+        *reinterpret_cast<uint2*>(o) = pack4(make_float4(v.x * gelu_tanh_grad(p0) * k01.x, v.y * gelu_tanh_grad(p1) * k01.y,
+                                                         v.z * gelu_tanh_grad(p2) * k23.x, v.w * gelu_tanh_grad(p3) * k23.y));
+      }
     } else if constexpr (EPI == EPI_F32) {
       if (args.addend != nullptr) v = add4(v, ldg4_guard(args.addend + grow * args.ld_add + col, col, N));
       if (args.stream_k) {

@@ -22,14 +22,6 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
 // ---------------------------------------------------------------------------------------------------------
 // derivatives of the activations (forward forms are the ones of the fused GEMM epilogues, ptx.cuh)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_tanh_grad(float x) {
-  const float k = 0.7978845608028654f, a = 0.044715f;
-  const float x2 = x * x;
-  const float u = k * x * fmaf(a, x2, 1.0f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));  // same unit as the forward epilogue (max rel. error 2^-11)
-  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k * fmaf(3.0f * a, x2, 1.0f);
-}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
@@ -60,26 +52,6 @@ __device__ __forceinline__ float act_grad(int act, float x) {
     case 4: return mish_grad(x);
     default: return 1.0f;
   }
-}
-
-// Dropout (modules.py:253, 297) as a stateless mask: element `idx` of a tensor survives iff hash(seed, idx) >= p * 2^32,
-// survivors are scaled by 1 / (1 - p). Forward and backward recompute the same mask from (seed, idx): nothing is stored.
-struct DropCfg {
-  unsigned int key;     // host-mixed (splitmix64) 32-bit key of the call's seed
-  unsigned int thresh;  // p * 2^32 (0: dropout off)
-  float inv_keep;       // 1 / (1 - p)
-};
-// one hash decides the element pair (idx, idx + 1), idx even: its two 16-bit halves against p * 2^16
-__device__ __forceinline__ float2 drop_scale2(const DropCfg& d, unsigned long long idx) {
-  if (d.thresh == 0u) return make_float2(1.0f, 1.0f);
-  unsigned int x = (unsigned int)(idx >> 1) * 0x9E3779B1u + d.key;  // lowbias32 finaliser
-  x ^= x >> 16;
-  x *= 0x7feb352du;
-  x ^= x >> 15;
-  x *= 0x846ca68bu;
-  x ^= x >> 16;
-  const unsigned int t16 = d.thresh >> 16;
-  return make_float2((x & 0xffffu) >= t16 ? d.inv_keep : 0.0f, (x >> 16) >= t16 ? d.inv_keep : 0.0f);
 }
 
 template <typename T>

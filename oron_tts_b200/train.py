@@ -412,7 +412,7 @@ class TrainEngine:
     def _forward(self, ws: TrainWorkspace, x: torch.Tensor, cond: torch.Tensor, text: torch.Tensor, time: torch.Tensor,
                  lens: torch.Tensor, drop_audio: bool, drop_text: bool) -> None:
         w = self.w
-        nb, tpad, D, C, M = ws.nb, ws.tpad, w.dim, w.text_dim, w.n_mels
+        nb, tpad, D, C, M, H = ws.nb, ws.tpad, w.dim, w.text_dim, w.n_mels, w.ff_dim
         Tn = x.shape[1]
         ids = (text.to(torch.int64) + 1)[:, :Tn]
         iv = ws.ids.view(nb, tpad)
@@ -481,8 +481,10 @@ class TrainEngine:
             T.gate_resid(ws.xin[i], ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True,
                          dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, out=ws.xmid[i], **common)
             L.ln_modulate(ws.xmid[i], scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], out_bf16=ws.nrm2[i], **mod)
-            L.gemm(ws.nrm2[i], blk["w1"], ws.hpre[i], epilogue=L.EPI_BF16, bias=blk["b1"], block_n=bn_big, two_sm=True, **common)
-            T.act_fwd(ws.hpre[i], ws.hid[i], L.ACT_GELU_TANH, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1)
+            # FFN up-projection: the epilogue keeps the pre-activation (for the backward) and writes dropout(gelu(pre))
+            L.gemm(ws.nrm2[i], blk["w1"], ws.hid[i], epilogue=L.EPI_GELU_DROP_DUAL, bias=blk["b1"], out2=ws.hpre[i],
+                   block_n=256 if H % 256 == 0 else 128, two_sm=True, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1,
+                   **common)
             L.gemm(ws.hid[i], blk["w2"], ws.y2[i], epilogue=L.EPI_BF16, bias=blk["b2"], block_n=bn_big, two_sm=True, **common)
             T.gate_resid(ws.xmid[i], ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=None, mask_rows=False,
                          out=ws.xin[i + 1], **common)
@@ -519,8 +521,10 @@ class TrainEngine:
             # FFN branch: x += gate_mlp * (W2 gelu(W1 n + b1) + b2)
             T.gate_bwd(ws.dx, ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=sl, dy=ws.g_d, dgate=dtab[o + 5 * D:],
                        dgate_ld=an, dbias=a.view(G, p + "ff.ff.3.bias"), **common)
-            self._linear_bwd(ws, ws.g_d, ws.hid[i], blk["w2"], a.view(G, p + "ff.ff.3.weight"), None, ws.g_h, acc=acc)
-            T.act_bwd(ws.g_h, ws.hpre[i], ws.g_h, L.ACT_GELU_TANH, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1)
+            self._wgrad(ws.g_d, ws.hid[i], a.view(G, p + "ff.ff.3.weight"), accumulate=acc)
+            # data gradient with the GELU derivative and the dropout mask applied in the epilogue (reads the saved pre-activation)
+            L.gemm(ws.g_d, blk["w2"], ws.g_h, epilogue=L.EPI_GELU_DROP_BWD, out2=ws.hpre[i], b_mn=True, two_sm=True,
+                   block_n=256 if H % 256 == 0 else 128, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1, **common)
             self._linear_bwd(ws, ws.g_h, ws.nrm2[i], blk["w1"], a.view(G, p + "ff.ff.0.weight"), a.view(G, p + "ff.ff.0.bias"),
                              ws.g_d, acc=acc)
             T.ln_bwd(ws.xmid[i], ws.g_d, scale=tab[o + 4 * D:], accumulate=True, dscale=dtab[o + 4 * D:], dshift=dtab[o + 3 * D:],

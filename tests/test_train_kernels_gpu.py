@@ -420,3 +420,35 @@ def test_dropout_masks():
     mask = k2.float() / (1 - p)
     assert _rel(dyo, (gate[:, None, :] * dx.view(nb, rpb, Cg) * mask).reshape(-1, Cg)) < 5e-3
     assert _rel(dg, (dx.view(nb, rpb, Cg) * y.float().view(nb, rpb, Cg) * mask).sum(1)) < 1e-4
+
+
+def test_gemm_fused_gelu_dropout_epilogues():
+    """FeedForward up-projection with the training epilogues: forward keeps the pre-activation and writes
+    dropout(gelu(pre)); the data-gradient GEMM applies gelu'(pre) and the same mask. Checked against the un-fused
+    kernels (act_fwd / act_bwd), which share the mask definition."""
+    g = torch.Generator(device=DEV).manual_seed(14)
+    R, D, H, p, seed = 1024, 256, 1024, 0.25, 99
+    x = torch.randn(R, D, device=DEV, generator=g).to(BF16)
+    w1 = (torch.randn(H, D, device=DEV, generator=g) / 16).to(BF16)
+    b1 = torch.randn(H, device=DEV, generator=g) * 0.1
+    hid, pre = torch.empty(R, H, device=DEV, dtype=BF16), torch.empty(R, H, device=DEV, dtype=BF16)
+    L.gemm(x, w1, hid, epilogue=L.EPI_GELU_DROP_DUAL, bias=b1, out2=pre, block_n=256, two_sm=True, dropout_p=p, dropout_seed=seed,
+           rows_per_batch=R // 2, nbatch=2)
+    pre_ref = x.float() @ w1.float().t() + b1
+    assert _rel(pre, pre_ref) < 5e-3
+    hid_ref = torch.empty_like(hid)
+    T.act_fwd(pre, hid_ref, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=seed)
+    assert torch.equal(hid.float() != 0, hid_ref.float() != 0) or float(((hid.float() != 0) != (hid_ref.float() != 0)).float().mean()) < 1e-3
+    assert _rel(hid, hid_ref) < 1e-2
+    assert abs(float((hid.float() != 0).float().mean()) - (1 - p)) < 2e-2
+    # backward: dhpre = (dy @ w2) * gelu'(pre) * mask
+    w2 = (torch.randn(D, H, device=DEV, generator=g) / 32).to(BF16)
+    dy = (torch.randn(R, D, device=DEV, generator=g) * 0.1).to(BF16)
+    dpre = torch.empty(R, H, device=DEV, dtype=BF16)
+    L.gemm(dy, w2, dpre, epilogue=L.EPI_GELU_DROP_BWD, out2=pre, b_mn=True, two_sm=True, block_n=256, dropout_p=p, dropout_seed=seed,
+           rows_per_batch=R // 2, nbatch=2)
+    dh = torch.empty(R, H, device=DEV, dtype=BF16)
+    L.gemm(dy, w2, dh, epilogue=L.EPI_BF16, b_mn=True, two_sm=True, block_n=256, rows_per_batch=R // 2, nbatch=2)
+    ref = torch.empty_like(dh)
+    T.act_bwd(dh, pre, ref, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=seed)
+    assert _rel(dpre, ref) < 1e-2
