@@ -51,6 +51,8 @@ enum oron_epilogue {
    * oron_b200_train.h over element index row * N + col (dropout_p = 0: none) */
   ORON_EPI_GELU_DROP_DUAL = 8,  /* out2_bf16 = pre = acc + bias ; out_bf16 = dropout(gelu_tanh(pre)) */
   ORON_EPI_GELU_DROP_BWD = 9,   /* out_bf16 = acc * gelu_tanh'(out2_bf16[row, col]) * mask  (out2 is read: the saved pre-activation) */
+  ORON_EPI_GATE_RESID_DUAL = 10, /* y = acc + bias -> out2_bf16 ; out_f32 = addend + gate[b] * dropout(valid ? y : 0): the gated residuals of
+                                  * DiTBlock (modules.py:338, 343) writing the next saved residual-stream buffer and keeping y for the backward */
 };
 enum oron_act { ORON_ACT_NONE = 0, ORON_ACT_GELU_TANH = 1, ORON_ACT_GELU_ERF = 2, ORON_ACT_SILU = 3 };
 

@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("ORON_LIB_PATH") or os.path.join(_HERE, "liboron_b200.
 # ---- enums (include/oron_b200.h) -------------------------------------------------------------
 EPI_BF16, EPI_F32, EPI_QKV_ROPE, EPI_GATE_RESID = 0, 1, 2, 3
 EPI_EMBED_DUAL, EPI_MISH_MASK_BF16, EPI_MISH_MASK_RESID, EPI_SCALE_RESID = 4, 5, 6, 7
-EPI_GELU_DROP_DUAL, EPI_GELU_DROP_BWD = 8, 9
+EPI_GELU_DROP_DUAL, EPI_GELU_DROP_BWD, EPI_GATE_RESID_DUAL = 8, 9, 10
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = (
@@ -267,7 +267,7 @@ def gemm(
     d.a_mn_major, d.b_mn_major = int(bool(a_mn)), int(bool(b_mn))
     d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
     want = torch.float32 if epilogue in (EPI_F32, EPI_GATE_RESID, EPI_EMBED_DUAL, EPI_MISH_MASK_RESID,
-                                         EPI_SCALE_RESID) else torch.bfloat16
+                                         EPI_SCALE_RESID, EPI_GATE_RESID_DUAL) else torch.bfloat16
     if out.dtype != want:
         raise TypeError(f"gemm epilogue {epilogue}: out must be {want}, got {out.dtype}")
     _check(lib().oron_gemm_bf16(ctypes.byref(d), _stream()), "oron_gemm_bf16")

@@ -184,9 +184,11 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   // per-epilogue operand checks (vectorised epilogues assume 32-column granularity)
   const bool vec_epi = epi == EPI_QKV_ROPE || epi == EPI_GATE_RESID || epi == EPI_EMBED_DUAL ||
                        epi == EPI_MISH_MASK_BF16 || epi == EPI_MISH_MASK_RESID || epi == EPI_SCALE_RESID ||
-                       epi == EPI_GELU_DROP_DUAL || epi == EPI_GELU_DROP_BWD;
-  if ((epi == EPI_GELU_DROP_DUAL || epi == EPI_GELU_DROP_BWD) && (!d->out2 || d->ldo2 % 8 != 0 || !d->two_sm))
-    return fail(ORON_ERR_BAD_ARG, "gemm: the GELU_DROP epilogues need out2 (pre-activation, ldo2 %% 8 == 0) and two_sm");
+                       epi == EPI_GELU_DROP_DUAL || epi == EPI_GELU_DROP_BWD || epi == EPI_GATE_RESID_DUAL;
+  if ((epi == EPI_GELU_DROP_DUAL || epi == EPI_GELU_DROP_BWD || epi == EPI_GATE_RESID_DUAL) &&
+      (!d->out2 || d->ldo2 % 8 != 0 || !d->two_sm))
+    return fail(ORON_ERR_BAD_ARG, "gemm: the training epilogues need out2 (ldo2 %% 8 == 0) and two_sm");
+  if (epi == EPI_GATE_RESID_DUAL && (!d->gate || !d->addend)) return fail(ORON_ERR_BAD_ARG, "gemm: GATE_RESID_DUAL needs gate and addend");
   {
     float p = d->dropout_p;
     a.drop.thresh = 0u;
@@ -271,6 +273,8 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM2_CASE(256, EPI_SCALE_RESID)
   ORON_GEMM2_CASE(128, EPI_GELU_DROP_DUAL)
   ORON_GEMM2_CASE(256, EPI_GELU_DROP_DUAL)
+  ORON_GEMM2_CASE(128, EPI_GATE_RESID_DUAL)
+  ORON_GEMM2_CASE(256, EPI_GATE_RESID_DUAL)
 #undef ORON_GEMM2_CASE
   if (two_sm) return fail(ORON_ERR_UNSUPPORTED, "gemm: no 2-SM kernel for block_n=%d epilogue=%d", d->block_n, epi);
 #define ORON_GEMM_CASE(BN_, EPI_) \

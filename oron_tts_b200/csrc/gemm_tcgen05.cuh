@@ -26,6 +26,7 @@ enum GemmEpilogue : int {
   // training-step fusions (oron_tts_b200/train.py): FeedForward up-projection forward and its data gradient
   EPI_GELU_DROP_DUAL = 8,  // out2_bf16 = pre = acc + bias ; out_bf16 = dropout(gelu_tanh(pre))   (modules.py:294-297)
   EPI_GELU_DROP_BWD = 9,   // out_bf16 = acc * gelu_tanh'(aux_bf16[row, col]) * dropout mask; aux = out2 (read only)
+  EPI_GATE_RESID_DUAL = 10,  // y = acc + bias -> out2_bf16 ; out_f32 = addend + gate[b] * dropout(valid ? y : 0)  (modules.py:338, 343)
 };
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_SILU = 3 };
@@ -205,6 +206,24 @@ __device__ __forceinline__ void epi_block_fast(const GemmArgs& args, const float
       *reinterpret_cast<uint2*>(o + (long long)it * 4 * args.ldo) =
           pack4(make_float4(h.x * k01.x, h.y * k01.y, h.z * k23.x, h.w * k23.y));
     }
+  } else if constexpr (EPI == EPI_GATE_RESID_DUAL) {
+    float* o = reinterpret_cast<float*>(args.out) + grow0 * args.ldo + col;
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(args.out2) + grow0 * args.ldo2 + col;
+    const float* ad = args.addend + grow0 * args.ld_add + col;
+    float4 x[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) x[it] = __ldg(reinterpret_cast<const float4*>(ad + (long long)it * 4 * args.ld_add));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      *reinterpret_cast<uint2*>(o2 + (long long)it * 4 * args.ldo2) = pack4(v[it]);
+      float4 r = x[it];
+      if (!(args.mask_rows && (t0 + 4 * it >= seq_len))) {
+        const unsigned long long e = (unsigned long long)(grow0 + 4 * it) * args.N + col;
+        const float2 k01 = drop_scale2(args.drop, e), k23 = drop_scale2(args.drop, e + 2);
+        r = fma4(g4, make_float4(v[it].x * k01.x, v[it].y * k01.y, v[it].z * k23.x, v[it].w * k23.y), x[it]);
+      }
+      *reinterpret_cast<float4*>(o + (long long)it * 4 * args.ldo) = r;
+    }
   } else if constexpr (EPI == EPI_GELU_DROP_BWD) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + grow0 * args.ldo + col;
     const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(args.out2) + grow0 * args.ldo2 + col;
@@ -311,6 +330,15 @@ __device__ __forceinline__ void epi_block_slow(const GemmArgs& args, const uint3
       else if (args.act == ACT_GELU_ERF) v = map4(v, gelu_erf_f);
       else if (args.act == ACT_SILU) v = map4(v, silu_f);
       st_bf16x4(reinterpret_cast<__nv_bfloat16*>(args.out) + grow * args.ldo + col, v, col, N);
+    } else if constexpr (EPI == EPI_GATE_RESID_DUAL) {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(args.out2) + grow * args.ldo2 + col) = pack4(v);
+      float4 r = *reinterpret_cast<const float4*>(args.addend + grow * args.ld_add + col);
+      if (!(args.mask_rows && !valid)) {
+        const unsigned long long e = (unsigned long long)grow * N + col;
+        const float2 k01 = drop_scale2(args.drop, e), k23 = drop_scale2(args.drop, e + 2);
+        r = fma4(g4, make_float4(v.x * k01.x, v.y * k01.y, v.z * k23.x, v.w * k23.y), r);
+      }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + grow * args.ldo + col) = r;
     } else if constexpr (EPI == EPI_GELU_DROP_DUAL || EPI == EPI_GELU_DROP_BWD) {
       // the host guarantees N % 32 == 0 for these: only ragged ROWS reach this path
       const unsigned long long e = (unsigned long long)grow * N + col;
@@ -382,7 +410,7 @@ __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmArgs& args, con
     pc.g4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
     if (col < args.N) {
       if (with_bias && args.bias != nullptr) pc.b4[j] = ldg4_guard(args.bias + col, col, args.N);
-      if constexpr (EPI == EPI_GATE_RESID) {
+      if constexpr (EPI == EPI_GATE_RESID || EPI == EPI_GATE_RESID_DUAL) {
         const long long step = args.step_ptr ? (long long)__ldg(args.step_ptr) : 0ll;
         pc.g4[j] = __ldg(reinterpret_cast<const float4*>(args.gate + step * args.gate_step_stride +
                                                         (long long)(b % args.gate_nb) * args.gate_ld + col));

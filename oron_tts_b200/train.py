@@ -477,17 +477,18 @@ class TrainEngine:
                    rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
             T.attention_fwd_lse(ws.qkv[i], ws.ao[i], ws.lse[i], nbatch=nb, rows_per_batch=tpad, heads=w.heads,
                                 seq_lens=ws.seq_lens, scale=1.0 / math.sqrt(w.dim_head))
-            L.gemm(ws.ao[i], blk["wo"], ws.y1[i], epilogue=L.EPI_BF16, bias=blk["bo"], block_n=bn_big, two_sm=True, **common)
-            T.gate_resid(ws.xin[i], ws.y1[i], gate=tab[o + 2 * D:], gate_ld=an, seq_lens=ws.seq_lens, mask_rows=True,
-                         dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, out=ws.xmid[i], **common)
+            # out-projection with the gated residual in the epilogue: xmid = xin + gate_msa * dropout(mask(y1)), y1 kept
+            L.gemm(ws.ao[i], blk["wo"], ws.xmid[i], epilogue=L.EPI_GATE_RESID_DUAL, bias=blk["bo"], out2=ws.y1[i], addend=ws.xin[i],
+                   gate=tab[o + 2 * D:], gate_ld=an, gate_nb=nb, seq_lens=ws.seq_lens, mask_rows=True, block_n=bn_big, two_sm=True,
+                   dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i, **common)
             L.ln_modulate(ws.xmid[i], scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], out_bf16=ws.nrm2[i], **mod)
             # FFN up-projection: the epilogue keeps the pre-activation (for the backward) and writes dropout(gelu(pre))
             L.gemm(ws.nrm2[i], blk["w1"], ws.hid[i], epilogue=L.EPI_GELU_DROP_DUAL, bias=blk["b1"], out2=ws.hpre[i],
                    block_n=256 if H % 256 == 0 else 128, two_sm=True, dropout_p=ws.drop_p, dropout_seed=ws.drop_seed + 4 * i + 1,
                    **common)
-            L.gemm(ws.hid[i], blk["w2"], ws.y2[i], epilogue=L.EPI_BF16, bias=blk["b2"], block_n=bn_big, two_sm=True, **common)
-            T.gate_resid(ws.xmid[i], ws.y2[i], gate=tab[o + 5 * D:], gate_ld=an, seq_lens=None, mask_rows=False,
-                         out=ws.xin[i + 1], **common)
+            L.gemm(ws.hid[i], blk["w2"], ws.xin[i + 1], epilogue=L.EPI_GATE_RESID_DUAL, bias=blk["b2"], out2=ws.y2[i],
+                   addend=ws.xmid[i], gate=tab[o + 5 * D:], gate_ld=an, gate_nb=nb, mask_rows=False, block_n=bn_big, two_sm=True,
+                   **common)
         o = w.depth * 6 * D
         L.ln_modulate(ws.xres, scale=tab[o:], shift=tab[o + D:], out_bf16=ws.nrmf, **mod)
         L.gemm(ws.nrmf, w.wp, ws.v, epilogue=L.EPI_F32, bias=w.bp, block_n=128, **common)

@@ -452,3 +452,35 @@ def test_gemm_fused_gelu_dropout_epilogues():
     ref = torch.empty_like(dh)
     T.act_bwd(dh, pre, ref, L.ACT_GELU_TANH, dropout_p=p, dropout_seed=seed)
     assert _rel(dpre, ref) < 1e-2
+
+
+def test_gemm_gate_resid_dual_epilogue():
+    """Out-projection / FFN down-projection of the training forward: y = A W^T + b kept as bf16, and
+    out = addend + gate[b] * dropout(mask(y)) written to a separate residual buffer -- against GEMM + oron_gate_resid."""
+    g = torch.Generator(device=DEV).manual_seed(15)
+    nb, rpb, K, N, p, seed = 2, 384, 512, 256, 0.2, 4242
+    R = nb * rpb
+    lens = [384, 200]
+    sl = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    a = torch.randn(R, K, device=DEV, generator=g).to(BF16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / 22).to(BF16)
+    b = torch.randn(N, device=DEV, generator=g) * 0.1
+    x_in = torch.randn(R, N, device=DEV, generator=g)
+    gate = torch.randn(nb, 3 * N, device=DEV, generator=g)[:, N:2 * N]
+    for mask_rows, pp in ((True, p), (False, 0.0)):
+        y = torch.empty(R, N, device=DEV, dtype=BF16)
+        out = torch.full((R, N), 7.0, device=DEV)
+        L.gemm(a, w, out, epilogue=L.EPI_GATE_RESID_DUAL, bias=b, out2=y, addend=x_in, gate=gate, gate_ld=3 * N, gate_nb=nb,
+               seq_lens=sl, mask_rows=mask_rows, block_n=256, two_sm=True, dropout_p=pp, dropout_seed=seed, rows_per_batch=rpb,
+               nbatch=nb)
+        y_ref = torch.empty(R, N, device=DEV, dtype=BF16)
+        L.gemm(a, w, y_ref, epilogue=L.EPI_BF16, bias=b, block_n=256, two_sm=True, rows_per_batch=rpb, nbatch=nb)
+        assert torch.equal(y, y_ref)
+        ref = torch.empty_like(x_in)
+        T.gate_resid(x_in, y_ref, rows_per_batch=rpb, nbatch=nb, gate=gate, gate_ld=3 * N, seq_lens=sl, mask_rows=mask_rows,
+                     dropout_p=pp, dropout_seed=seed, out=ref)
+        # the fused epilogue gates the fp32 accumulator, the reference path the bf16-rounded y
+        assert _rel(out, ref) < 2e-3, (mask_rows, _rel(out, ref))
+        if mask_rows:
+            m = _mask(nb, rpb, lens)
+            assert torch.equal(out[~m], x_in[~m])
