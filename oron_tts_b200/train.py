@@ -11,8 +11,10 @@ Design:
     copy written by the fused AdamW kernel IS the next step's GEMM operand;
   * the forward pass is the inference engine's kernel sequence with the two fused epilogues that hide a needed
     intermediate (gated residual, activations) un-fused and every activation kept (180 GB HBM: no recomputation);
-  * backward: dgrad / wgrad GEMMs on the same tcgen05 GEMM (operands transposed by ``oron_transpose_bf16``, which
-    also yields the bias gradients), tcgen05 attention backward, row-wise backward kernels (include/oron_b200_train.h);
+  * backward: dgrad / wgrad GEMMs on the same tcgen05 GEMM reading the row-major activations / weights as stored
+    (MN-major operand variants, stream-K for the few-tile weight gradients), bias gradients as column sums, GELU +
+    dropout and the gated residuals fused into GEMM epilogues, tcgen05 attention backward, row-wise backward kernels
+    (include/oron_b200_train.h);
   * gradients of each transformer block are all-reduced (async, NCCL stream) as soon as its backward is enqueued.
 
 Train-mode randomness (t, span, noise, CFG drops) is drawn with torch as the reference does. Dropout (p_dropout,
@@ -324,15 +326,14 @@ class TrainEngine:
         bn = 256 if nn % 256 == 0 else 128
         L.gemm(dy, w, out, epilogue=L.EPI_BF16, rows_per_batch=ws.tpad, nbatch=ws.nb, block_n=bn, b_mn=True, two_sm=True)
 
-    def _wgrad(self, dy, x, out, *, accumulate=False):
-        """out[N_out, K_in] (f32, a gradient-arena view) (+)= dy[R, N_out]^T @ x[R, K_in], both operands as stored."""
+    def _wgrad(self, dy, x, out, *, accumulate=False):  # noqa: ARG002 (accumulation is implicit, see below)
+        """out[N_out, K_in] (f32, a gradient-arena view) += dy[R, N_out]^T @ x[R, K_in], both operands as stored."""
         nn = x.shape[1]
         bn = 256 if nn % 256 == 0 else 128
         # stream-K: the output has few 256 x 256 tiles (16 for a dim x dim weight) but a long reduction (K = rows), so every
         # SM pair takes an equal share of the (tile, k-block) list and adds its partial sum into the gradient arena, which
         # the step zeroed (or keeps accumulating into): `accumulate` needs nothing extra
         L.gemm(dy, x, out, epilogue=L.EPI_F32, block_n=bn, a_mn=True, b_mn=True, two_sm=True, stream_k=True)
-        del accumulate
 
     def _linear_bwd(self, ws, dy, x_saved, w, gw, gb, dx_out, *, acc=False):
         """Backward of y = x W^T + b for [R, .] activations: bias and weight gradients into the arena, data gradient.

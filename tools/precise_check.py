@@ -1,13 +1,15 @@
+"""fp32-mode accuracy check: PreciseDiT vs the live-reference fixture (tiny) and vs the CPU oracle (Small)."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests/golden"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import weights as GW
 from oracle import dit_oracle as DO
 from oron_tts_b200.f5tts import F5TTS
 from oron_tts_b200.precise import PreciseDiT
 DEV = "cuda"
 rel = lambda a, b: float((a.float().cpu() - b.float().cpu()).norm() / b.float().cpu().norm())
-g = torch.load("/root/repo/tests/golden/dit_tiny.pt", weights_only=False)
-keys = torch.load("/root/repo/tests/golden/state_keys.pt", weights_only=False)
+g = torch.load(os.path.join(ROOT, "tests", "golden", "dit_tiny.pt"), weights_only=False)
+keys = torch.load(os.path.join(ROOT, "tests", "golden", "state_keys.pt"), weights_only=False)
 def sd_of(name):
     sd = GW.fill_state_dict({k: torch.empty(s) for k, s in keys[name].items()}, GW.SEEDS[name])
     sd["cfm.backbone.rotary_embed.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
