@@ -82,6 +82,19 @@ def test_product_path_fails_loudly_without_cuda():
                            torch.tensor([0.5]))
     with pytest.raises(RuntimeError, match="CUDA"):
         AudioProcessor().mel_spectrogram(torch.zeros(24000))
+    # the training engine, the fp32 mode and the GPU data path have no CPU fallback either
+    from oron_tts_b200.data import GpuBatcher
+    from oron_tts_b200.precise import PreciseDiT
+    from oron_tts_b200.train import TrainEngine
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        TrainEngine(model)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        PreciseDiT(model.cfm.backbone)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.train()(torch.zeros(1, 100, 60), torch.zeros(1, 60, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GpuBatcher(min_duration_s=0.1, device="cpu")([torch.zeros(24000)], ["сайн"])
 
 
 def test_precise_header_symbols_exported(built):
