@@ -244,6 +244,9 @@ void oron_debug_set_attention_stamps(void* buf);
 /* Test aid: attention schedule override. -1 = automatic (default), 0 = one CTA per item, 1 = balanced whenever a
  * planned workspace is passed (exercises the split / merge path on small shapes). */
 void oron_debug_set_attention_schedule(int32_t mode);
+/* A/B aid: 4 = the current attention kernel (attn_fwd4.cuh, default), 3 = the round-1 kernel (attn_tcgen05.cuh). A
+ * workspace must be re-planned (oron_attention_plan) after switching. Env ORON_ATT_VERSION sets the initial value. */
+void oron_debug_set_attention_version(int32_t version);
 
 int oron_abi_version(void);
 const char* oron_last_error(void);

@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "oron_peak_normalize",
     "oron_debug_set_attention_stamps",
     "oron_debug_set_attention_schedule",
+    "oron_debug_set_attention_version",
     "oron_abi_version",
     "oron_last_error",
     "oron_launch_count",
@@ -116,6 +117,8 @@ def lib() -> ctypes.CDLL:
     L.oron_debug_set_attention_stamps.restype = None
     L.oron_debug_set_attention_schedule.argtypes = [c_int32]
     L.oron_debug_set_attention_schedule.restype = None
+    L.oron_debug_set_attention_version.argtypes = [c_int32]
+    L.oron_debug_set_attention_version.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                       c_void_p, c_float, c_void_p, c_int64, c_void_p]

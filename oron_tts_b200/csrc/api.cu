@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "../../include/oron_b200.h"
+#include "attn_fwd4.cuh"
 #include "attn_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "host_util.h"
@@ -336,23 +337,129 @@ static AttnWsLayout attn_ws_layout(int nbatch, int rows_per_batch, int heads) {
   return w;
 }
 
+// ---- fourth-generation kernel (attn_fwd4.cuh): the default. ORON_ATT_VERSION=3 / oron_debug_set_attention_version(3)
+// selects the round-1 kernel (kept for A/B measurements).
+static int g_attn_version = 0;
+static int attn_version() {
+  if (g_attn_version == 0) { const char* e = getenv("ORON_ATT_VERSION"); g_attn_version = (e && atoi(e) == 3) ? 3 : 4; }
+  return g_attn_version;
+}
+extern "C" void oron_debug_set_attention_version(int32_t v) { g_attn_version = (v == 3) ? 3 : 4; }
+
+struct Attn4WsLayout {
+  int grid, seg_stride;
+  int64_t off_nseg, off_segs, off_merge, off_ml, off_o, bytes;
+};
+static Attn4WsLayout attn4_ws_layout(int nbatch, int rows_per_batch, int heads) {
+  Attn4WsLayout w;
+  w.grid = attn_slots();
+  const int64_t q_tiles = (rows_per_batch + ATT4_TILE - 1) / ATT4_TILE;
+  const int64_t total_max = int64_t(nbatch) * heads * q_tiles * q_tiles;
+  w.seg_stride = int((total_max + w.grid - 1) / w.grid) + 2;  // whole items in a share <= its units, + the two partial ends
+  auto up = [](int64_t x) { return (x + 255) & ~int64_t(255); };
+  w.off_nseg = up(sizeof(Attn4PlanHeader));
+  w.off_segs = up(w.off_nseg + int64_t(w.grid) * 4);
+  w.off_merge = up(w.off_segs + int64_t(w.grid) * w.seg_stride * int64_t(sizeof(Attn4Seg)));
+  w.off_ml = up(w.off_merge + int64_t(w.grid) * int64_t(sizeof(Attn4Merge)));
+  w.off_o = up(w.off_ml + int64_t(2 * w.grid) * ATT4_TILE * 2 * 4);
+  w.bytes = up(w.off_o + int64_t(2 * w.grid) * ATT4_TILE * ATT4_D * 2);
+  return w;
+}
+
 extern "C" int64_t oron_attention_workspace_bytes(int32_t nbatch, int32_t rows_per_batch, int32_t heads) {
   if (nbatch <= 0 || rows_per_batch <= 0 || heads <= 0) return 0;
-  return attn_ws_layout(nbatch, rows_per_batch, heads).bytes;
+  const int64_t a = attn_ws_layout(nbatch, rows_per_batch, heads).bytes, b = attn4_ws_layout(nbatch, rows_per_batch, heads).bytes;
+  return a > b ? a : b;
 }
 
 extern "C" int oron_attention_plan(const int32_t* seq_lens, int32_t nbatch, int32_t rows_per_batch, int32_t heads,
                                    void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
   if (!workspace || nbatch <= 0 || rows_per_batch <= 0 || heads <= 0) return fail(ORON_ERR_BAD_ARG, "attention_plan: bad argument");
-  const AttnWsLayout w = attn_ws_layout(nbatch, rows_per_batch, heads);
-  if (workspace_bytes < w.bytes || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+  if (workspace_bytes < oron_attention_workspace_bytes(nbatch, rows_per_batch, heads) || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
     return fail(ORON_ERR_BAD_ARG, "attention_plan: workspace too small or not 16-byte aligned");
   char* p = reinterpret_cast<char*>(workspace);
+  if (attn_version() == 4) {
+    const Attn4WsLayout w = attn4_ws_layout(nbatch, rows_per_batch, heads);
+    attn4_plan_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<Attn4PlanHeader*>(p), reinterpret_cast<int*>(p + w.off_nseg), reinterpret_cast<Attn4Seg*>(p + w.off_segs),
+        reinterpret_cast<Attn4Merge*>(p + w.off_merge), seq_lens, nbatch, rows_per_batch, heads, w.grid, w.seg_stride, g_attn_schedule == 1 ? 1 : 0);
+    return check_launch("attn4_plan");
+  }
+  const AttnWsLayout w = attn_ws_layout(nbatch, rows_per_batch, heads);
   attn_plan_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<AttnPlanHeader*>(p), reinterpret_cast<int*>(p + w.off_nseg), reinterpret_cast<AttnSeg*>(p + w.off_segs),
       reinterpret_cast<AttnMergeEnt*>(p + w.off_merge), reinterpret_cast<int*>(p + w.off_cnt), seq_lens, nbatch, rows_per_batch,
       heads, w.grid, w.seg_stride);
   return check_launch("attn_plan");
+}
+
+static int attention4_impl(const CUtensorMap& tq, void* out, int64_t ldo, int32_t nbatch, int32_t rows_per_batch, int32_t heads,
+                           const int32_t* seq_lens, float scale, void* workspace, int64_t workspace_bytes, float* lse,
+                           cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(int(e), "attention smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const Attn4WsLayout w = attn4_ws_layout(nbatch, rows_per_batch, heads);
+  const bool have_ws = workspace != nullptr && workspace_bytes >= w.bytes && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+  Attn4Args a;
+  memset(&a, 0, sizeof(a));
+  a.rows_per_batch = rows_per_batch;
+  a.nbatch = nbatch;
+  a.heads = heads;
+  a.seq_lens = seq_lens;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.ldo = ldo;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.dbg = g_attn_dbg;
+  a.lse = lse;
+  a.q_tiles = (rows_per_batch + ATT4_TILE - 1) / ATT4_TILE;
+  const long long items = (long long)a.q_tiles * heads * nbatch;
+  // with a planned workspace: at most two CTAs per SM, equal shares of the key-tile list; g_attn_schedule == 0 forces
+  // one CTA per item
+  const bool planned = have_ws && g_attn_schedule != 0;
+  if (planned) {
+    char* p = reinterpret_cast<char*>(workspace);
+    a.plan_hdr = reinterpret_cast<const Attn4PlanHeader*>(p);
+    a.plan_nseg = reinterpret_cast<const int*>(p + w.off_nseg);
+    a.plan_segs = reinterpret_cast<const Attn4Seg*>(p + w.off_segs);
+    a.plan_merge = reinterpret_cast<const Attn4Merge*>(p + w.off_merge);
+    a.ws_ml = reinterpret_cast<float*>(p + w.off_ml);
+    a.ws_o = reinterpret_cast<__half*>(p + w.off_o);
+  }
+  dim3 grid(planned ? unsigned(w.grid) : unsigned(items));
+  static int abl = -1;  // ORON_ATT_ABL: ablation variants for tools/kernel_bench.py (wrong results, timing only)
+  if (abl < 0) { const char* e = getenv("ORON_ATT_ABL"); abl = e ? atoi(e) : 0; }
+  cudaError_t le;
+  if (abl != 0) {
+    auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES); return launch_pdl(k, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a); };
+    switch (abl) {
+      case 7: le = set(attn_fwd4_kernel<false, 7>); break;
+      case 15: le = set(attn_fwd4_kernel<false, 15>); break;
+      case 23: le = set(attn_fwd4_kernel<false, 23>); break;
+      case 39: le = set(attn_fwd4_kernel<false, 39>); break;
+      case 71: le = set(attn_fwd4_kernel<false, 71>); break;
+      case 55: le = set(attn_fwd4_kernel<false, 55>); break;
+      default: le = a.dbg ? set(attn_fwd4_kernel<true, 127>) : set(attn_fwd4_kernel<false, 127>); break;
+    }
+  } else
+  le = a.dbg ? launch_pdl(attn_fwd4_kernel<true>, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a)
+             : launch_pdl(attn_fwd4_kernel<false>, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a);
+  if (le != cudaSuccess) return fail(int(le), "attention launch: %s", cudaGetErrorString(le));
+  int rc = check_launch("attn_fwd4");
+  if (rc) return rc;
+  // items are split only when there are more of them than CTAs (or when the test aid forces shares): then the parts are
+  // combined by a second, small launch right behind the first
+  if (planned && (items > w.grid || g_attn_schedule == 1)) {
+    le = launch_pdl(attn4_combine_kernel, dim3(unsigned(w.grid)), dim3(256), 0, st, a.plan_merge, (const __half*)a.ws_o, (const float*)a.ws_ml,
+                    a.out, (long long)ldo, lse, (int)rows_per_batch, (int)heads);
+    if (le != cudaSuccess) return fail(int(le), "attention combine launch: %s", cudaGetErrorString(le));
+    rc = check_launch("attn4_combine");
+  }
+  return rc;
 }
 
 static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch, int32_t rows_per_batch,
@@ -365,6 +472,9 @@ static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ld
   int rc = make_tmap_bf16(&tq, qkv, uint64_t(3 * heads * ATT_D), uint64_t(rows_per_batch), uint64_t(nbatch),
                           uint64_t(ld_qkv), uint64_t(ld_qkv) * uint64_t(rows_per_batch), ATT_TILE, 3);
   if (rc) return rc;
+  if (attn_version() == 4)
+    return attention4_impl(tq, out, ldo, nbatch, rows_per_batch, heads, seq_lens, scale, workspace, workspace_bytes, lse,
+                           reinterpret_cast<cudaStream_t>(stream));
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -286,29 +286,21 @@ def test_gemm_two_sm_fused_epilogues(L):
 # ------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("nb,T,H,lens", [(1, 128, 2, None), (2, 384, 4, [384, 130]), (2, 1408, 16, [1406, 1406]),
-                                         (3, 200, 8, [200, 1, 77]), (2, 1408, 16, [1406, 300]), (5, 2816, 16, None)])
-def test_attention(L, nb, T, H, lens):
+@pytest.mark.parametrize("version", [4, 3])
+@pytest.mark.parametrize("nb,T,H,lens,qmul", [(1, 128, 2, None, 1.0), (2, 384, 4, [384, 130], 1.0), (2, 1408, 16, [1406, 1406], 1.0),
+                                              (3, 200, 8, [200, 1, 77], 1.0), (2, 1408, 16, [1406, 300], 1.0), (5, 2816, 16, None, 1.0),
+                                              (2, 1024, 4, [1000, 515], 6.0)])
+def test_attention(L, nb, T, H, lens, qmul, version):
+    """version 4 = attn_fwd4.cuh (production), 3 = the round-1 kernel kept for A/B. qmul > 1 spreads the scores so that the
+    running maximum moves by more than 2^8 between key tiles (the lazy-rescale branch)."""
     g = torch.Generator(device=DEV).manual_seed(T + H)
-    qkv = _bf(torch.randn(nb * T, 3 * H * 64, device=DEV, generator=g))
+    qkv = torch.randn(nb * T, 3 * H * 64, device=DEV, generator=g)
+    qkv[:, : H * 64] *= qmul
+    qkv = _bf(qkv)
     # the V third is IEEE f16 (bit-cast into the bf16-typed buffer), as the QKV GEMM epilogue writes it
     v16 = torch.randn(nb * T, H * 64, device=DEV, generator=g).half()
     qkv[:, 2 * H * 64:] = v16.view(torch.bfloat16)
-    out = torch.zeros(nb * T, H * 64, device=DEV, dtype=torch.bfloat16)
     lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32) if lens is not None else None
-    # with a planned workspace the kernel runs its balanced schedule: equal shares of the flat (item, key tile) list
-    # per CTA, split items merged by attn_merge_kernel (forced here for the small shapes too: many parts per item,
-    # empty shares); run twice on the same workspace
-    ws = L.attention_workspace(nb, T, H, DEV, seq_lens=lens_t)
-    L.lib().oron_debug_set_attention_schedule(1)
-    try:
-        for _ in range(2):
-            out.zero_()
-            L.attention(qkv, out, nbatch=nb, rows_per_batch=T, heads=H, seq_lens=lens_t, scale=0.125, workspace=ws)
-    finally:
-        L.lib().oron_debug_set_attention_schedule(-1)
-    out_ns = torch.zeros_like(out)
-    L.attention(qkv, out_ns, nbatch=nb, rows_per_batch=T, heads=H, seq_lens=lens_t, scale=0.125)
     x = qkv.float().view(nb, T, 3, H, 64)
     q, k = (x[:, :, i].transpose(1, 2) for i in range(2))
     v = v16.float().view(nb, T, H, 64).transpose(1, 2)
@@ -316,10 +308,28 @@ def test_attention(L, nb, T, H, lens):
     mask = torch.arange(T, device=DEV)[None, :] < torch.tensor(ll, device=DEV)[:, None]
     ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask[:, None, None, :])
     ref = ref.transpose(1, 2).reshape(nb, T, H * 64)
-    o = out.view(nb, T, H * 64)
-    for b in range(nb):
-        assert _rel(o[b, : ll[b]], ref[b, : ll[b]]) < 1e-2, b
-        assert _rel(out_ns.view(nb, T, H * 64)[b, : ll[b]], ref[b, : ll[b]]) < 1e-2, b
+    L.lib().oron_debug_set_attention_version(version)
+    try:
+        # schedules: -1 = planned workspace (equal shares of the (item, key tile) list when there are more items than
+        # CTA slots, else one CTA per item), 1 = shares forced on the small shapes too (many parts per item, empty
+        # shares; split items combined in-kernel), None = no workspace: one CTA per item. Each runs twice on the same
+        # workspace (the arrival counters must come back to zero).
+        for sched in (-1, 1, None):
+            out = torch.zeros(nb * T, H * 64, device=DEV, dtype=torch.bfloat16)
+            if sched is not None:
+                L.lib().oron_debug_set_attention_schedule(sched)
+                ws = L.attention_workspace(nb, T, H, DEV, seq_lens=lens_t)
+            else:
+                ws = None
+            for _ in range(2):
+                out.zero_()
+                L.attention(qkv, out, nbatch=nb, rows_per_batch=T, heads=H, seq_lens=lens_t, scale=0.125, workspace=ws)
+            o = out.view(nb, T, H * 64)
+            for b in range(nb):
+                assert _rel(o[b, : ll[b]], ref[b, : ll[b]]) < 1e-2, (sched, b)
+    finally:
+        L.lib().oron_debug_set_attention_schedule(-1)
+        L.lib().oron_debug_set_attention_version(4)
 
 
 # ------------------------------------------------------------------------------------------

@@ -110,11 +110,42 @@ if what in ("attn", "all"):
     qkv[:, 2048:] = torch.randn(R, 1024, device=DEV, generator=g).half().view(torch.bfloat16)
     o = torch.zeros(R, 1024, device=DEV, dtype=torch.bfloat16)
     lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
-    AWS = L.attention_workspace(2, T, 16, DEV, seq_lens=lens)
-    run([("attention T=1406 H=16 nb=2 (one CTA per item)", 4 * 2 * 16 * 1406 * 1406 * 64,
-          lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125)),
-         ("attention T=1406 H=16 nb=2 (balanced schedule)", 4 * 2 * 16 * 1406 * 1406 * 64,
-          lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=AWS))])
+    fl = 4 * 2 * 16 * 1406 * 1406 * 64
+    for ver in (4, 3):
+        L.lib().oron_debug_set_attention_version(ver)
+        AWS = L.attention_workspace(2, T, 16, DEV, seq_lens=lens)
+        run([(f"attention v{ver} T=1406 H=16 nb=2 (one CTA per item)", fl,
+              lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125)),
+             (f"attention v{ver} T=1406 H=16 nb=2 (planned shares)", fl,
+              lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=AWS))])
+    # back-to-back launches inside one CUDA graph (what the ODE step sees: PDL overlap, warm L2), after 1.5 s of sustained
+    # load: the SM clock ramps up from idle over many milliseconds, so short bursts are timed at a low clock
+    def graph_time(ver):
+        import time
+        L.lib().oron_debug_set_attention_version(ver)
+        AWS = L.attention_workspace(2, T, 16, DEV, seq_lens=lens)
+        fn = lambda: L.attention(qkv, o, nbatch=2, rows_per_batch=T, heads=16, seq_lens=lens, scale=0.125, workspace=AWS)
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            for _ in range(3): fn()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=s_):
+                for _ in range(22): fn()
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                for _ in range(20): gph.replay()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_)
+            for _ in range(50): gph.replay()
+            e1.record(s_)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (22 * 50)
+        print(f"attention v{ver} planned, 22 launches per graph replay, sustained: {us:.1f} us per launch = {fl / us / 1e6:.1f} TFLOP/s", flush=True)
+    if not NCU:
+        for ver in ((4,) if os.environ.get("ORON_ATT_ABL") else (4, 3)):
+            graph_time(ver)
+    L.lib().oron_debug_set_attention_version(4)
 if what in ("ln", "all"):
     g = torch.Generator(device=DEV).manual_seed(2)
     x = torch.randn(R, 1024, device=DEV, generator=g)
