@@ -346,9 +346,17 @@ static int attn_version() {
 }
 extern "C" void oron_debug_set_attention_version(int32_t v) { g_attn_version = (v == 3) ? 3 : 4; }
 
+// Split items are merged by attn4_combine_kernel right behind the attention launch (default; measured 37.2 us per call at
+// config 2) or, with ORON_ATT_COMBINE=inline, by the attention kernel's own combine warps (38.1 us: no second launch, but
+// the two extra warps take issue slots from the softmax warps they share schedulers with).
+static bool attn_inline_combine() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ORON_ATT_COMBINE"); v = (e && e[0] == 'i') ? 1 : 0; }
+  return v == 1;
+}
 struct Attn4WsLayout {
   int grid, seg_stride;
-  int64_t off_nseg, off_segs, off_merge, off_ml, off_o, bytes;
+  int64_t off_nseg, off_segs, off_merge, off_cnt, off_ml, off_o, bytes;
 };
 static Attn4WsLayout attn4_ws_layout(int nbatch, int rows_per_batch, int heads) {
   Attn4WsLayout w;
@@ -360,7 +368,8 @@ static Attn4WsLayout attn4_ws_layout(int nbatch, int rows_per_batch, int heads) 
   w.off_nseg = up(sizeof(Attn4PlanHeader));
   w.off_segs = up(w.off_nseg + int64_t(w.grid) * 4);
   w.off_merge = up(w.off_segs + int64_t(w.grid) * w.seg_stride * int64_t(sizeof(Attn4Seg)));
-  w.off_ml = up(w.off_merge + int64_t(w.grid) * int64_t(sizeof(Attn4Merge)));
+  w.off_cnt = up(w.off_merge + int64_t(w.grid) * int64_t(sizeof(Attn4Merge)));
+  w.off_ml = up(w.off_cnt + int64_t(w.grid) * 4);
   w.off_o = up(w.off_ml + int64_t(2 * w.grid) * ATT4_TILE * 2 * 4);
   w.bytes = up(w.off_o + int64_t(2 * w.grid) * ATT4_TILE * ATT4_D * 2);
   return w;
@@ -382,7 +391,7 @@ extern "C" int oron_attention_plan(const int32_t* seq_lens, int32_t nbatch, int3
     const Attn4WsLayout w = attn4_ws_layout(nbatch, rows_per_batch, heads);
     attn4_plan_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<Attn4PlanHeader*>(p), reinterpret_cast<int*>(p + w.off_nseg), reinterpret_cast<Attn4Seg*>(p + w.off_segs),
-        reinterpret_cast<Attn4Merge*>(p + w.off_merge), seq_lens, nbatch, rows_per_batch, heads, w.grid, w.seg_stride, g_attn_schedule == 1 ? 1 : 0);
+        reinterpret_cast<Attn4Merge*>(p + w.off_merge), reinterpret_cast<int*>(p + w.off_cnt), seq_lens, nbatch, rows_per_batch, heads, w.grid, w.seg_stride, g_attn_schedule == 1 ? 1 : 0);
     return check_launch("attn4_plan");
   }
   const AttnWsLayout w = attn_ws_layout(nbatch, rows_per_batch, heads);
@@ -427,6 +436,7 @@ static int attention4_impl(const CUtensorMap& tq, void* out, int64_t ldo, int32_
     a.plan_nseg = reinterpret_cast<const int*>(p + w.off_nseg);
     a.plan_segs = reinterpret_cast<const Attn4Seg*>(p + w.off_segs);
     a.plan_merge = reinterpret_cast<const Attn4Merge*>(p + w.off_merge);
+    a.ws_cnt = attn_inline_combine() ? reinterpret_cast<int*>(p + w.off_cnt) : nullptr;
     a.ws_ml = reinterpret_cast<float*>(p + w.off_ml);
     a.ws_o = reinterpret_cast<__half*>(p + w.off_o);
   }
@@ -453,7 +463,7 @@ static int attention4_impl(const CUtensorMap& tq, void* out, int64_t ldo, int32_
   if (rc) return rc;
   // items are split only when there are more of them than CTAs (or when the test aid forces shares): then the parts are
   // combined by a second, small launch right behind the first
-  if (planned && (items > w.grid || g_attn_schedule == 1)) {
+  if (planned && a.ws_cnt == nullptr && (items > w.grid || g_attn_schedule == 1)) {
     le = launch_pdl(attn4_combine_kernel, dim3(unsigned(w.grid)), dim3(256), 0, st, a.plan_merge, (const __half*)a.ws_o, (const float*)a.ws_ml,
                     a.out, (long long)ldo, lse, (int)rows_per_batch, (int)heads);
     if (le != cudaSuccess) return fail(int(le), "attention combine launch: %s", cudaGetErrorString(le));

@@ -63,6 +63,7 @@ struct Attn4Args {
   const int* plan_nseg;
   const Attn4Seg* plan_segs;
   const Attn4Merge* plan_merge;  // [grid]
+  int* ws_cnt;          // [grid] arrival counters of the split items (zero between launches), or nullptr: attn4_combine_kernel merges
   __half* ws_o;         // [2 * grid][128][64] f16: O_p / l_p of a partial segment
   float* ws_ml;         // [2 * grid][128][2] f32: (running max * c, l_p)
   float* lse;           // optional [nbatch * heads * rows_per_batch] f32: log2-domain log-sum-exp of every query row
@@ -78,6 +79,9 @@ constexpr int ATT4_QS = 2, ATT4_KS = 2, ATT4_VS = 3;
 constexpr int ATT4_BAR_OFF = (ATT4_QS + ATT4_KS + ATT4_VS) * ATT4_TILE_BYTES;
 constexpr int ATT4_SMEM_BYTES = ATT4_BAR_OFF + 256;
 constexpr int ATT4_TMEM_COLS = 256;
+#ifndef ATT4_EX2_POLY
+#define ATT4_EX2_POLY 1  // 1: part of the exponentials on the FMA pipe (ex2_poly2)
+#endif
 constexpr float ATT4_RESCALE_LOG2 = 8.0f;  // raise the running max only when exceeded by > 2^8
 constexpr float ATT4_P_EXP_BIAS = 7.0f;    // probabilities are scaled by 2^7 (<= 2^15 in f16); cancels in O / l
 #define ATT4_STAMP(slot) do { if (DBG) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -133,6 +137,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ float fmax2(float a, float b) {  // opaque to the compiler, which would fuse pairs into FMNMX3
+  float d;
+  asm("max.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -153,6 +162,32 @@ __device__ __forceinline__ void fadd2(float& s0, float& s1, float x0, float x1) 
   asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(x0), "f"(x1));
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(sv), "l"(xv));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(r));
+}
+
+// 2^x for a pair on the FMA / ALU pipes instead of the MUFU unit (one in four exponentials goes this way: the MUFU unit,
+// 16 results per clock per SM, is the softmax's narrowest pipe). x = floor(x) + f by adding 1.5 * 2^23 with round-down,
+// degree-3 polynomial for 2^f on [0, 1) (max relative error 9e-5, f16 resolution is 4.9e-4), floor(x) added into the
+// exponent field. Valid for -127 <= x < 128; smaller x are clamped (result ~0).
+__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
+  uint64_t xv, mg, t, r, f, p, c3, c2, c1, c0;
+  const float y0 = fmaxf(x0, -127.0f), y1 = fmaxf(x1, -127.0f);
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(y0), "f"(y1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(12582912.0f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.07711965f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.22756439f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.69514614f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(1.0f));
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(t) : "l"(xv), "l"(mg));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(t), "l"(mg));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(f) : "l"(xv), "l"(r));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(f), "l"(c3), "l"(c2));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c1));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c0));
+  uint32_t t0, t1, p0, p1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(p));
+  x0 = __uint_as_float(p0 + (t0 << 23));
+  x1 = __uint_as_float(p1 + (t1 << 23));
 }
 
 // Bounded wait without printf (its argument buffer lives in local memory: see below). A stuck pipeline records the tag of
@@ -196,6 +231,78 @@ __device__ __forceinline__ void mbar_wait4(uint32_t bar, uint32_t parity, int ta
 // every local-memory access misses -- that, not the softmax arithmetic, bounded the first versions of this kernel.)
 __device__ __forceinline__ int seg_field(const Attn4Seg* segs, int s, int f) {
   return reinterpret_cast<const int*>(segs + s)[f];  // 0 b, 1 h, 2 qt, 3 j0, 4 j1, 5 slot, 6 owner, 7 nparts
+}
+
+// Combine the parts of one split item (parts live in slots 2 (owner + p) + (p == 0), p = 0 .. nparts - 1): NT threads,
+// 8 threads per row (16 bytes of f16 each), RPT rows per thread per round, four parts per round of loads, all of a round's
+// loads in flight at once; online (running-max) combination.
+template <int NT, int RPT>
+__device__ __forceinline__ void att4_combine_item(int tid, int owner, int nparts, int b, int h, int qt, const __half* ws_o,
+                                                  const float* ws_ml, __nv_bfloat16* out, long long ldo, float* lse,
+                                                  int rows_per_batch, int heads) {
+  constexpr int ROWS = NT / 8;  // rows per sub-pass
+  const int rsub = tid >> 3, c8 = (tid & 7) * 8;
+  auto slot_of = [&](int p) { return (long long)(2 * (owner + p) + (p == 0 ? 1 : 0)); };
+#pragma unroll 1
+  for (int r0 = 0; r0 < ATT4_TILE; r0 += ROWS * RPT) {
+    float acc[RPT][8], m_run[RPT], l_run[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      m_run[j] = -INFINITY;
+      l_run[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+    }
+#pragma unroll 1
+    for (int p0 = 0; p0 < nparts; p0 += 4) {
+      float2 ml[RPT][4];
+      uint4 u[RPT][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long sl = slot_of(min(p0 + i, nparts - 1)) * ATT4_TILE;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const long long rr = sl + r0 + j * ROWS + rsub;
+          ml[j][i] = __ldcg(reinterpret_cast<const float2*>(ws_ml + rr * 2));
+          u[j][i] = __ldcg(reinterpret_cast<const uint4*>(ws_o + rr * ATT4_D + c8));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        float m_new = m_run[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (p0 + i < nparts) m_new = fmaxf(m_new, ml[j][i].x);
+        const float f_old = ex2_approx(m_run[j] - m_new);  // 0 on the first round (m_run = -inf)
+        l_run[j] *= f_old;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j][k] *= f_old;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float wgt = p0 + i < nparts ? ml[j][i].y * ex2_approx(ml[j][i].x - m_new) : 0.f;
+          l_run[j] += wgt;
+          const uint32_t wd[4] = {u[j][i].x, u[j][i].y, u[j][i].z, u[j][i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&wd[k]));
+            acc[j][2 * k] = fmaf(fv.x, wgt, acc[j][2 * k]);
+            acc[j][2 * k + 1] = fmaf(fv.y, wgt, acc[j][2 * k + 1]);
+          }
+        }
+        m_run[j] = m_new;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int t = qt * ATT4_TILE + r0 + j * ROWS + rsub;
+      if (t >= rows_per_batch) continue;
+      const float inv_l = 1.0f / l_run[j];
+      if (lse != nullptr && c8 == 0)
+        lse[((long long)b * heads + h) * rows_per_batch + t] = log2f(l_run[j]) + m_run[j] - ATT4_P_EXP_BIAS;
+      *reinterpret_cast<uint4*>(out + ((long long)b * rows_per_batch + t) * ldo + h * ATT4_D + c8) =
+          make_uint4(pack_bf16x2(acc[j][0] * inv_l, acc[j][1] * inv_l), pack_bf16x2(acc[j][2] * inv_l, acc[j][3] * inv_l),
+                     pack_bf16x2(acc[j][4] * inv_l, acc[j][5] * inv_l), pack_bf16x2(acc[j][6] * inv_l, acc[j][7] * inv_l));
+    }
+  }
 }
 
 // The CTA's segment list: from the plan, or (one CTA per item) the single segment the first thread left in shared memory.
@@ -265,6 +372,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
 #define p_full (bar_base + 8u * 16)     /* softmax -> MMA: P(i) is in TMEM (4 warp arrivals) */
 #define o_full (bar_base + 8u * 17)     /* MMA -> softmax: O includes P(i) V(i); also: the P columns are free */
 #define tmem_slot (bar_base + 8u * 18)
+#define part_ready (bar_base + 8u * 19) /* softmax -> combine warps: a partial result is in the workspace (4 warp arrivals) */
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -275,6 +383,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
     mbar_init(s_free, 4);
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
+    mbar_init(part_ready, 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -406,7 +515,41 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
 #endif
     }
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT4_REGS_AUX));  // warps 2, 3: only there to complete the warpgroup
+    // ===================== combine warps (64 threads): the split items =====================
+    // args.ws_cnt != nullptr: the softmax threads only publish a partial result and move on; here the part is counted and,
+    // if it was the item's last one to arrive, all parts are combined (nobody waits for anybody). The plans run the
+    // partial segments FIRST, so this happens early in the launch, under the softmax of the whole items.
+    // args.ws_cnt == nullptr: attn4_combine_kernel does it after the launch.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT4_REGS_AUX));
+    if (args.ws_cnt != nullptr) {
+      const Attn4Seg* segs;
+      int nseg;
+      att4_segments(args, smem_raw, segs, nseg);
+      const uint32_t bar_base = smem_u32(smem_raw) + ATT4_BAR_OFF;
+      volatile int* merge_flag = reinterpret_cast<volatile int*>(smem_raw + ATT4_BAR_OFF + 184);
+      const int hid = threadIdx.x - 64;
+      int np = 0;
+      for (int sidx = 0; sidx < nseg; ++sidx) {
+        if (seg_field(segs, sidx, 5) < 0) continue;
+        const int owner = seg_field(segs, sidx, 6), nparts = seg_field(segs, sidx, 7);
+        mbar_wait4(part_ready, np & 1u, 22);
+        ++np;
+        if (hid == 0) {
+          __threadfence();  // cumulative: the softmax threads' stores (observed through the barrier) before the count
+          const int old = atomicAdd(args.ws_cnt + owner, 1);
+          const int is_last = old == nparts - 1;
+          if (is_last) args.ws_cnt[owner] = 0;  // ready for the next launch (CUDA-graph replays included)
+          *merge_flag = is_last;
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        const int is_last = *merge_flag;
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (!is_last) continue;
+        __threadfence();
+        att4_combine_item<64, 1>(hid, owner, nparts, seg_field(segs, sidx, 0), seg_field(segs, sidx, 1), seg_field(segs, sidx, 2),
+                                 args.ws_o, args.ws_ml, args.out, args.ldo, args.lse, args.rows_per_batch, args.heads);
+      }
+    }
   } else {
     // ===================== softmax threads =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT4_REGS_SOFTMAX));
@@ -471,17 +614,15 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
           if (k >= n_valid) v[k] = 0xff800000u;  // -inf: exp2 gives probability 0
       }
       // ---- row maximum ----
-      float mm[8];
+      float mm[8];  // plain 2-input FMNMX: the 3-input form issues at a quarter of the rate on this part
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mm[k] = fmax3(__uint_as_float(v[k]), __uint_as_float(v[k + 8]), __uint_as_float(v[k + 16]));
+      for (int k = 0; k < 8; ++k) mm[k] = fmax2(__uint_as_float(v[k]), __uint_as_float(v[k + 8]));
 #pragma unroll
-      for (int k0 = 24; k0 < 120; k0 += 16) {
+      for (int k0 = 16; k0 < 128; k0 += 8) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mm[k] = fmax3(mm[k], __uint_as_float(v[k0 + k]), __uint_as_float(v[k0 + 8 + k]));
+        for (int k = 0; k < 8; ++k) mm[k] = fmax2(mm[k], __uint_as_float(v[k0 + k]));
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) mm[k] = fmaxf(mm[k], __uint_as_float(v[120 + k]));
-      float mxc = fmaxf(fmax3(mm[0], mm[1], mm[2]), fmax3(fmax3(mm[3], mm[4], mm[5]), mm[6], mm[7])) * c;
+      float mxc = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), fmaxf(fmaxf(mm[4], mm[5]), fmaxf(mm[6], mm[7]))) * c;
       if (ABL & 2) mxc = __uint_as_float(v[0]) * c;
       // ---- lazy rescale: only when this tile's max exceeds the running one by more than 2^8 ----
       const bool need = mxc > mc + ATT4_RESCALE_LOG2;
@@ -524,7 +665,11 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
         ffma2(x2, x3, c, nmcb);
         if (!(ABL & 1)) {
           x0 = ex2_approx(x0); x1 = ex2_approx(x1);
-          x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+          if (ATT4_EX2_POLY && (k & 4) && k >= 32 && k < 96) {   // keys 36-39, 44-47, ... of the middle two 32-key groups: 1 in 8 per row
+            ex2_poly2(x2, x3);
+          } else {
+            x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+          }
         }
         fadd2(s0, s1, x0, x1);
         fadd2(s2, s3, x2, x3);
@@ -580,6 +725,10 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
           __stcg(dst + g, make_uint4(hw[0], hw[1], hw[2], hw[3]));
         }
         __stcg(reinterpret_cast<float2*>(args.ws_ml + ((long long)slot * ATT4_TILE + r) * 2), make_float2(mc, l_run));
+        if (args.ws_cnt != nullptr) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(part_ready);
+        }
       } else if (t < args.rows_per_batch) {
         if (args.lse != nullptr)  // log2 sum_k 2^(s_k c)
           args.lse[((long long)sg_b * args.heads + sg_h) * args.rows_per_batch + t] = log2f(l_run) + mc - ATT4_P_EXP_BIAS;
@@ -626,6 +775,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
 #undef p_full
 #undef o_full
 #undef tmem_slot
+#undef part_ready
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -671,7 +821,7 @@ struct Plan4Walk {
   }
 };
 
-__global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg* segs_out, Attn4Merge* merge, const int* seq_lens,
+__global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg* segs_out, Attn4Merge* merge, int* cnt, const int* seq_lens,
                                   int nbatch, int rows, int heads, int grid, int seg_stride, int force_flat) {
   if (threadIdx.x == 0) {
     hdr->nbatch = nbatch; hdr->rows = rows; hdr->heads = heads; hdr->grid = grid; hdr->seg_stride = seg_stride;
@@ -766,6 +916,7 @@ __global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg*
     }
     nseg_out[c] = n;
     merge[c] = me;
+    cnt[c] = 0;
   }
   __syncthreads();
   if (threadIdx.x == 0) { __threadfence(); hdr->magic = ATT4_PLAN_MAGIC; }
@@ -786,55 +937,7 @@ attn4_combine_kernel(const Attn4Merge* __restrict__ merge, const __half* __restr
   // waiting would count as complete and release the NEXT kernel of the stream before the attention results exist
   pdl_wait();
   if (me.nparts == 0) return;
-  const int rsub = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;
-  const int c = blockIdx.x;
-  auto slot_of = [&](int p) { return (long long)(2 * (c + p) + (p == 0 ? 1 : 0)); };
-#pragma unroll 1
-  for (int r0 = 0; r0 < ATT4_TILE; r0 += 32) {
-    const int row = r0 + rsub;
-    float acc[8], m_run = -INFINITY, l_run = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll 1
-    for (int p0 = 0; p0 < me.nparts; p0 += 4) {
-      float2 ml[4];
-      uint4 u[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long rr = slot_of(min(p0 + i, me.nparts - 1)) * ATT4_TILE + row;
-        ml[i] = __ldcg(reinterpret_cast<const float2*>(ws_ml + rr * 2));
-        u[i] = __ldcg(reinterpret_cast<const uint4*>(ws_o + rr * ATT4_D + c8));
-      }
-      float m_new = m_run;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) if (p0 + i < me.nparts) m_new = fmaxf(m_new, ml[i].x);
-      const float f_old = ex2_approx(m_run - m_new);  // 0 on the first round (m_run = -inf)
-      l_run *= f_old;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] *= f_old;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float wgt = p0 + i < me.nparts ? ml[i].y * ex2_approx(ml[i].x - m_new) : 0.f;
-        l_run += wgt;
-        const uint32_t wd[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&wd[k]));
-          acc[2 * k] = fmaf(fv.x, wgt, acc[2 * k]);
-          acc[2 * k + 1] = fmaf(fv.y, wgt, acc[2 * k + 1]);
-        }
-      }
-      m_run = m_new;
-    }
-    const int t = me.qt * ATT4_TILE + row;
-    if (t >= rows_per_batch) continue;
-    const float inv_l = 1.0f / l_run;
-    if (lse != nullptr && c8 == 0)
-      lse[((long long)me.b * heads + me.h) * rows_per_batch + t] = log2f(l_run) + m_run - ATT4_P_EXP_BIAS;
-    *reinterpret_cast<uint4*>(out + ((long long)me.b * rows_per_batch + t) * ldo + me.h * ATT4_D + c8) =
-        make_uint4(pack_bf16x2(acc[0] * inv_l, acc[1] * inv_l), pack_bf16x2(acc[2] * inv_l, acc[3] * inv_l),
-                   pack_bf16x2(acc[4] * inv_l, acc[5] * inv_l), pack_bf16x2(acc[6] * inv_l, acc[7] * inv_l));
-  }
+  att4_combine_item<256, 1>(threadIdx.x, blockIdx.x, me.nparts, me.b, me.h, me.qt, ws_o, ws_ml, out, ldo, lse, rows_per_batch, heads);
 }
 
 }  // namespace oron
