@@ -1,11 +1,13 @@
-"""Checkpoint I/O contract used by scripts/infer.py (src/utils/checkpoint.py:39-59, 62-151, 214-228):
-file names, dict keys, config.json sibling and the ``._orig_mod.`` key adaptation for backbones that were
-wrapped by torch.compile. The Hugging Face upload/download half of the reference class is control plane
-and out of scope here."""
+"""Checkpoint I/O contract used by scripts/infer.py and scripts/train.py (src/utils/checkpoint.py:24-59, 62-228):
+file names, dict keys, config.json sibling, the ``._orig_mod.`` key adaptation for backbones that were wrapped by
+torch.compile, and the shape-filtered pretrained loader (``load_pretrained_f5tts``, pinned by the reference's
+tests/test_checkpoint.py:58-86, mirrored in tests/test_checkpoint_contract.py). The Hugging Face upload/download half of
+the reference class is control plane and out of scope here."""
 
 from __future__ import annotations
 
 import json
+import re
 from collections.abc import Mapping
 from pathlib import Path
 from typing import Any
@@ -23,6 +25,16 @@ def adapt_state_dict_to_model(state_dict: Mapping[str, torch.Tensor], model: tor
     """Rename keys so that eager and torch.compile-wrapped (``_orig_mod``) layouts load into either model."""
     wanted = {_plain(k): k for k in model.state_dict()}
     return {wanted.get(_plain(k), k): v for k, v in state_dict.items()}
+
+
+def _is_step_checkpoint(path: str, model_name: str) -> bool:
+    return re.fullmatch(rf"{re.escape(model_name)}_step_\d+\.pt", Path(path).name) is not None
+
+
+def stale_remote_checkpoint_paths(remote_paths: list[str], local_paths: list[str], model_name: str) -> list[str]:
+    """Step checkpoints present remotely but rotated away locally (src/utils/checkpoint.py:24-36)."""
+    keep = {Path(p).name for p in local_paths if _is_step_checkpoint(p, model_name)}
+    return [p for p in remote_paths if _is_step_checkpoint(p, model_name) and Path(p).name not in keep]
 
 
 class CheckpointManager:
@@ -81,6 +93,34 @@ class CheckpointManager:
             scheduler.load_state_dict(blob["scheduler_state_dict"])
         return {"step": blob.get("step", 0), "loss": blob.get("loss"), "ema_state_dict": blob.get("ema_state_dict"),
                 "epoch": blob.get("epoch", 0), "best_val": blob.get("best_val", float("inf"))}
+
+    def load_pretrained_f5tts(self, model: torch.nn.Module, checkpoint_path: str | Path, device: str = "cpu",
+                              strict: bool = False) -> dict[str, Any]:
+        """Load a pretrained F5-TTS checkpoint (src/utils/checkpoint.py:153-205): ``.safetensors`` or a torch file whose
+        ``ema_state_dict`` / ``ema_model_state_dict`` / ``model_state_dict`` entry is preferred in that order; with
+        ``strict=False`` tensors whose shape differs from the model's (the extended Cyrillic text embedding) are skipped
+        and reported."""
+        path = Path(checkpoint_path)
+        if path.suffix == ".safetensors":
+            try:
+                from safetensors.torch import load_file
+            except ImportError as exc:
+                raise ImportError("Install safetensors: pip install safetensors") from exc
+            state = load_file(str(path), device=device)
+        else:
+            state = torch.load(path, map_location=device, weights_only=True)
+            for key in ("ema_state_dict", "ema_model_state_dict", "model_state_dict"):
+                if key in state:
+                    state = state[key]
+                    break
+        state = adapt_state_dict_to_model(state, model)
+        if strict:
+            missing, unexpected = model.load_state_dict(state, strict=True)
+            return {"missing_keys": missing, "unexpected_keys": unexpected, "skipped_keys": []}
+        have = model.state_dict()
+        skipped = [k for k, v in state.items() if k in have and have[k].shape != v.shape]
+        missing, unexpected = model.load_state_dict({k: v for k, v in state.items() if k not in skipped}, strict=False)
+        return {"missing_keys": missing, "unexpected_keys": unexpected, "skipped_keys": skipped}
 
     def load_config(self) -> dict[str, Any] | None:
         p = self.checkpoint_dir / "config.json"

@@ -145,7 +145,13 @@ class DiT(nn.Module):
 
     # ---- engine / packed weights ---------------------------------------------------------------
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        def ver(p):  # tensors created under torch.inference_mode() have no version counter
+            try:
+                return p._version
+            except RuntimeError:
+                return -1
+
+        return tuple((p.data_ptr(), ver(p)) for p in self.parameters())
 
     def engine(self) -> DiTEngine:
         """Packed-weight engine for the current parameters (rebuilt after load_state_dict / .to())."""

@@ -272,6 +272,9 @@ class DiTEngine:
         """Token ids (+1 shift, crop / 0-pad to seq_len: encoder.py:68-74), drop flags and lengths."""
         nb, tpad = ws.nb, ws.tpad
         ids = (text.to(torch.int64) + 1)[:, :seq_len]
+        vocab1 = self.w.text_table.shape[0]
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= vocab1):  # nn.Embedding raises here too (encoder.py:75)
+            raise IndexError(f"text ids out of range: ids must lie in [-1, {vocab1 - 2}] (index out of range in the text embedding table)")
         ids2 = torch.zeros(nb, tpad, device=self.w.device, dtype=torch.int32)
         ids2[:, : ids.shape[1]] = ids.to(torch.int32)
         ws.ids.view(ws.nbp, tpad).copy_(ids2.repeat(len(branches), 1))

@@ -128,6 +128,11 @@ class GradReducer:
             for lo, hi in self.block_ranges[i]:
                 self._pending.append((dist.all_reduce(self.g[lo:hi], op=dist.ReduceOp.SUM, async_op=True), lo, hi))
 
+    def drain(self) -> None:
+        """Wait for every all-reduce in flight (before the gradient arena is zeroed or rewritten)."""
+        for h, _, _ in self._pending:
+            h.wait()
+
     def finish(self) -> None:
         import torch.distributed as dist
 
@@ -375,9 +380,15 @@ class TrainEngine:
 
     @torch.no_grad()
     def loss_and_grad(self, mel: torch.Tensor, text_ids: torch.Tensor, lens: torch.Tensor | None = None, *,
-                      draws: dict | None = None, training: bool = True, accumulate: bool = False) -> torch.Tensor:
+                      draws: dict | None = None, training: bool = True, accumulate: bool = False,
+                      reduce: bool = True) -> torch.Tensor:
         """CFM.forward + backward: returns the scalar loss (device tensor) with every ``param.grad`` filled
-        (added to, when ``accumulate``). ``draws``: output of ``draw`` to inject the batch's randomness."""
+        (added to, when ``accumulate``). ``draws``: output of ``draw`` to inject the batch's randomness.
+
+        ``reduce``: issue this engine's per-block gradient all-reduces during the backward pass (data-parallel runs).
+        Pass ``False`` for every micro-batch of a gradient-accumulation window except the last one (the ranges are summed
+        in place, so reducing them before the window is complete would count the earlier micro-batches ``world`` times),
+        and whenever something else owns the reduction (the autograd bridge under DDP, trainer.py:70-71)."""
         x1 = mel.transpose(1, 2) if (mel.ndim == 3 and mel.shape[1] == self.cfm.n_mels) else mel
         B, Tn, dev = x1.shape[0], x1.shape[1], x1.device
         if lens is None:
@@ -389,8 +400,14 @@ class TrainEngine:
         cond = torch.where(span[..., None], torch.zeros_like(x1), x1)
         tpad = _rup(Tn, TILE)
         ws = self.workspace(B, tpad)
+        self.reducer.drain()  # nothing may still be reducing the ranges this pass zeroes / adds to
+        if accumulate and self.reducer._pending:
+            raise RuntimeError("loss_and_grad(accumulate=True) after a micro-batch that already reduced its gradients: pass "
+                               "reduce=False for every micro-batch of the window except the last")
         if not accumulate:
+            self.reducer._pending.clear()
             self.arena.g.zero_()
+        self._reduce_in_backward = bool(reduce)
         dseed = d.get("dropout_seed")
         ws.drop_p = self.dropout_p if dseed is not None else 0.0
         ws.drop_seed = int(dseed) if dseed is not None else 0
@@ -407,6 +424,7 @@ class TrainEngine:
         ws.loss_sum.zero_()
         T.cfm_loss(ws.v, ws.flow, ws.span, ws.count, ws.loss_sum, ws.dpred, n_mels=M)
         self._backward(ws, acc=accumulate)
+        self._check_ids_end()
         return (ws.loss_sum / (ws.count.clamp(min=1).float() * M)).reshape(())
 
     # ---- forward (DiT.forward dit.py:165-234 with every intermediate kept) -----------------------------------
@@ -418,8 +436,9 @@ class TrainEngine:
         ids = (text.to(torch.int64) + 1)[:, :Tn]
         iv = ws.ids.view(nb, tpad)
         iv.zero_()
-        iv[:, : ids.shape[1]].copy_(ids)
+        iv[:, : ids.shape[1]].copy_(ids.clamp(0, w.text_table.shape[0] - 1))  # the kernels never index outside the table
         ws.drop.fill_(1 if drop_text else 0)
+        self._check_ids_begin(ids)
         ws.seq_lens.copy_(lens)
         ws.text_lens.fill_(Tn)  # TextEmbedding runs over the whole padded batch (encoder.py:68-96), fillers included
         common = dict(rows_per_batch=tpad, nbatch=nb)
@@ -604,25 +623,47 @@ class TrainEngine:
 
     # ---- data-parallel gradient mean + optimizer ---------------------------------------------------------------
     def _block_done(self, i: int) -> None:
-        self.reducer.block_done(i)
+        if getattr(self, "_reduce_in_backward", True):
+            self.reducer.block_done(i)
+
+    # token ids outside [-1, vocab) (nn.Embedding raises IndexError for them, encoder.py:68-75): the range test runs on the
+    # device at the start of the pass, the kernels see clamped ids, and the verdict is read once the whole pass has been
+    # enqueued -- so the check costs no pipeline bubble. The same read tells whether the PREVIOUS optimizer step was
+    # skipped on the device (non-finite gradients), in which case its Adam step number is given back.
+    def _check_ids_begin(self, ids_shifted: torch.Tensor):
+        vocab1 = self.w.text_table.shape[0]
+        self._id_flags = torch.stack([((ids_shifted < 0) | (ids_shifted >= vocab1)).any().to(I32), self.skipped.reshape(())])
+        return self._id_flags
+
+    def _check_ids_end(self) -> None:
+        bad, skipped_prev = (int(v) for v in self._id_flags.tolist())
+        if skipped_prev and getattr(self, "_step_pending_skip_check", False):
+            self.step_count -= 1
+        self._step_pending_skip_check = False
+        if bad:
+            raise IndexError(f"text_ids out of range: ids must lie in [-1, {self.w.text_table.shape[0] - 2}] "
+                             "(index out of range in the text embedding table)")
 
     def reduce_gradients(self) -> None:
         self.reducer.finish()
 
     @torch.no_grad()
-    def optimizer_step(self, lr: float | None = None) -> None:
+    def optimizer_step(self, lr: float | None = None, accum_steps: int = 1) -> None:
         """clip_grad_norm_(max_grad_norm) + AdamW + bf16 operand refresh (trainer.py:191-216), gradients averaged over
-        the ranks first. Non-finite gradient norm: the update is skipped on the device (``self.skipped`` = 1)."""
+        the ranks -- and over the ``accum_steps`` micro-batches accumulated into them (trainer.py:236 divides each
+        micro-batch loss by grad_accum) -- first. Non-finite gradient norm: the update is skipped on the device
+        (``self.skipped`` = 1) and the Adam step number is given back at the next pass."""
         import torch.distributed as dist
 
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.reduce_gradients()
         a = self.arena
         self.step_count += 1
+        self._step_pending_skip_check = True
         self.sumsq.zero_()
         self.skipped.zero_()
         T.sumsq(a.g, self.sumsq)
-        T.adamw_clip(a.p, a.g, a.m, a.v, a.pb, self.sumsq, grad_scale=1.0 / world, max_norm=self.max_norm,
+        T.adamw_clip(a.p, a.g, a.m, a.v, a.pb, self.sumsq, grad_scale=1.0 / (world * max(int(accum_steps), 1)), max_norm=self.max_norm,
                      lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, wd=self.wd,
                      step=self.step_count, skipped=self.skipped)
         self.w.refresh()
@@ -735,7 +776,7 @@ class OTCFMLoss(torch.autograd.Function):
     def forward(ctx, eng: TrainEngine, mel, text_ids, lens, *params):
         eng.sync_params()
         eng.detach_grads()
-        loss = eng.loss_and_grad(mel, text_ids, lens, training=True)
+        loss = eng.loss_and_grad(mel, text_ids, lens, training=True, reduce=False)  # DDP / the caller owns the reduction
         ctx.eng = eng
         ctx.keys = [k for k in eng.arena.order]
         return loss.clone()

@@ -25,6 +25,15 @@ from . import _lib as L
 BF16, F32 = torch.bfloat16, torch.float32
 
 
+def _version_of(p: torch.Tensor) -> int:
+    """In-place update counter; tensors created under torch.inference_mode() (the vocoder is built inside
+    ``F5TTS.synthesize``) do not have one."""
+    try:
+        return p._version
+    except RuntimeError:
+        return -1
+
+
 class _ConvNeXtBlock(nn.Module):
     def __init__(self, dim: int, intermediate_dim: int, layer_scale_init_value: float):
         super().__init__()
@@ -93,7 +102,7 @@ class Vocos(nn.Module):
         p0 = next(self.parameters())
         if not p0.is_cuda:
             raise RuntimeError("oron_tts_b200.Vocos runs only on a CUDA device (no CPU fallback)")
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        sig = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
         if self.__dict__["_packed"] is not None and self.__dict__["_packed_sig"] == sig:
             return self.__dict__["_packed"]
         dev = p0.device

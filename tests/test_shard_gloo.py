@@ -117,6 +117,33 @@ def _reducer_worker(rank, world, port, q):
             red.block_done(i)
         red.finish()
         ok = ok and torch.equal(arena.g, base * sum(r + 1 for r in range(world)))
+    # gradient accumulation under data parallelism (TrainEngine.loss_and_grad(reduce=...)): the block ranges may only be
+    # reduced with the window's LAST micro-batch -- and not at all when something else owns the reduction (the autograd
+    # bridge under DDP). The engine's gate (_block_done) is exercised on a stand-in that carries the same two attributes.
+    from types import SimpleNamespace
+
+    from oron_tts_b200.train import TrainEngine
+
+    g1, g2 = base * (rank + 1), base.flip(0) * (rank + 2)
+    eng = SimpleNamespace(reducer=GradReducer(arena.g, arena.block_ranges, overlap=True), _reduce_in_backward=False)
+    arena.g.copy_(g1)                       # micro-batch 1: reduce=False
+    for i in reversed(range(3)):
+        TrainEngine._block_done(eng, i)
+    ok = ok and not eng.reducer._pending and torch.equal(arena.g, g1)
+    eng._reduce_in_backward = True          # micro-batch 2 (last of the window): accumulate, then reduce
+    arena.g.add_(g2)
+    for i in reversed(range(3)):
+        TrainEngine._block_done(eng, i)
+    eng.reducer.finish()
+    want = sum(base * (r + 1) + base.flip(0) * (r + 2) for r in range(world))
+    ok = ok and torch.equal(arena.g, want)
+    # bridge mode: nothing is reduced by the engine, the caller (DDP) sees the local gradient
+    eng._reduce_in_backward = False
+    arena.g.copy_(g1)
+    for i in reversed(range(3)):
+        TrainEngine._block_done(eng, i)
+    eng.reducer.drain()
+    ok = ok and torch.equal(arena.g, g1) and not eng.reducer._pending
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

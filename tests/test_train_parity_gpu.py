@@ -286,3 +286,62 @@ def test_base_config_gradients_vs_oracle():
     loss = eng.loss_and_grad(x1.transpose(1, 2).to(DEV), text.to(DEV), lens.to(DEV), draws=_to_dev(draws))
     assert abs(float(loss) - float(ref_loss)) < 2e-2 * float(ref_loss)
     _check_grads(eng, ref_grads, "base")
+
+
+def test_gradient_accumulation_and_accum_steps():
+    """Two micro-batches accumulated (reduce only with the last one) give g1 + g2, and optimizer_step(accum_steps=2) is the
+    update for their mean (trainer.py:236 divides every micro-batch loss by grad_accum)."""
+    g = _to_dev({k: v for k, v in _gold("train_tiny.pt").items() if k in ("mel", "text", "lens")})
+    mel, ids, lens = g["mel"], g["text"], g["lens"]
+    eng = _engine()
+    d1 = eng.draw(mel, lens, training=False)
+    torch.manual_seed(5)
+    d2 = eng.draw(mel, lens, training=True)
+    d2.pop("dropout_seed", None)
+    eng.loss_and_grad(mel, ids, lens, draws=d1)
+    g1 = eng.arena.g.clone()
+    eng.loss_and_grad(mel, ids, lens, draws=d2)
+    g2 = eng.arena.g.clone()
+    eng.loss_and_grad(mel, ids, lens, draws=d1, reduce=False)
+    eng.loss_and_grad(mel, ids, lens, draws=d2, accumulate=True)
+    # stream-K partial sums arrive in any order: compare to fp32 round-off, not bit for bit
+    assert _rel(eng.arena.g, g1 + g2) < 1e-5
+    eng.optimizer_step(lr=1e-3, accum_steps=2)
+    ref = _engine()
+    ref.arena.g.copy_((g1 + g2) * 0.5)
+    ref.optimizer_step(lr=1e-3)
+    assert _rel(eng.arena.p, ref.arena.p) < 1e-6
+
+
+def test_out_of_range_token_ids_raise_like_nn_embedding():
+    g = _to_dev({k: v for k, v in _gold("train_tiny.pt").items() if k in ("mel", "text", "lens")})
+    mel, ids, lens = g["mel"], g["text"].clone(), g["lens"]
+    eng = _engine()
+    before = eng.arena.g.clone()
+    vocab = eng.w.text_table.shape[0] - 1
+    for bad in (vocab, vocab + 40, -2):
+        broken = ids.clone()
+        broken[0, 1] = bad
+        with pytest.raises(IndexError):
+            eng.loss_and_grad(mel, broken, lens, training=False)
+    eng.loss_and_grad(mel, ids, lens, training=False)          # the engine stays usable, in-range ids still work
+    assert torch.isfinite(eng.arena.g).all() and not torch.equal(eng.arena.g, before)
+    m = eng.model
+    with pytest.raises(IndexError):
+        m.cfm.sample(torch.zeros(1, 64, 100, device=DEV), torch.full((1, 8), vocab, device=DEV), 64,
+                     lens=torch.tensor([0], device=DEV), steps=2)
+
+
+def test_skipped_optimizer_step_gives_its_adam_step_back():
+    g = _to_dev({k: v for k, v in _gold("train_tiny.pt").items() if k in ("mel", "text", "lens")})
+    mel, ids, lens = g["mel"], g["text"], g["lens"]
+    eng = _engine()
+    eng.loss_and_grad(mel, ids, lens, training=False)
+    eng.arena.g[0] = float("nan")
+    p0 = eng.arena.p.clone()
+    eng.optimizer_step(lr=1e-3)
+    assert int(eng.skipped) == 1 and torch.equal(eng.arena.p, p0)
+    eng.loss_and_grad(mel, ids, lens, training=False)          # reads the flag: the skipped update does not count
+    assert eng.step_count == 0
+    eng.optimizer_step(lr=1e-3)
+    assert eng.step_count == 1 and int(eng.skipped) == 0 and not torch.equal(eng.arena.p, p0)
