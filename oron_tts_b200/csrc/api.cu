@@ -668,12 +668,10 @@ extern "C" int oron_grn(void* h_bf16, int64_t ldh, int32_t rows_per_batch, int32
                         oron_stream_t stream) {
   if (!h_bf16 || !gamma || !beta || !gx2) return fail(ORON_ERR_BAD_ARG, "grn: null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(gx2, 0, sizeof(float) * size_t(nb) * C, st);
-  if (e != cudaSuccess) return fail(int(e), "grn memset: %s", cudaGetErrorString(e));
   const int rpb = 32;
   dim3 grid((rows_per_batch + rpb - 1) / rpb, nb);
   __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(h_bf16);
-  grn_sumsq_kernel<<<grid, 256, 0, st>>>(h, ldh, rows_per_batch, nb, seq_lens, C, rpb, gx2);
+  grn_sumsq_kernel<<<dim3((C + 31) / 32, nb), 256, 0, st>>>(h, ldh, rows_per_batch, nb, seq_lens, C, gx2);
   int rc = check_launch("grn_sumsq");
   if (rc) return rc;
   grn_apply_kernel<<<grid, 256, 0, st>>>(h, ldh, rows_per_batch, nb, C, rpb, gx2, gamma, beta);

@@ -406,23 +406,33 @@ __global__ void __launch_bounds__(C / 4) dwconv7_ln_run_kernel(const DwLnArgs a,
 // ---------------------------------------------------------------------------
 // GRN (modules.py:153-156): gx[b,c] = ||h[b,:,c]||_2 over the frames of the sequence,
 // nx = gx / (mean_c gx + 1e-6), y = gamma * (h * nx) + beta + h.   Two kernels:
-//   grn_sumsq : partial sums of squares per (b, c) accumulated with atomics into gx2 (pre-zeroed)
+//   grn_sumsq : sums of squares per (b, c) into gx2, fixed summation order
 //   grn_apply : every block re-derives mean_c from gx2 (C <= 2048) and rewrites h in place (bf16)
 // ---------------------------------------------------------------------------
+// One block per (32 channels, batch element): 8 row lanes x 32 channels; every thread sums its rows in order, the eight
+// row lanes are added in a fixed order -- no atomics, so the result (and with it a seeded CFM.sample) is bit-reproducible.
 __global__ void __launch_bounds__(256)
 grn_sumsq_kernel(const __nv_bfloat16* h, long long ldh, int rows_per_batch, int nb, const int* seq_lens,
-                 int C, int rows_per_block, float* gx2) {
+                 int C, float* gx2) {
+  __shared__ float part[8][33];
   const int b = blockIdx.y;
-  const int len = seq_lens ? seq_lens[b] : rows_per_batch;
-  const int t0 = blockIdx.x * rows_per_block;
-  const int t1 = min(t0 + rows_per_block, len);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int t = t0; t < t1; ++t) {
+  const int len = seq_lens ? min(seq_lens[b], rows_per_batch) : rows_per_batch;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < C) {
+    for (int t = ry; t < len; t += 8) {
       const float v = __bfloat162float(h[((long long)b * rows_per_batch + t) * ldh + c]);
       s += v * v;
     }
-    if (t1 > t0) atomicAdd(gx2 + (long long)b * C + c, s);
+  }
+  part[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float tot = part[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) tot += part[k][cx];
+    gx2[(long long)b * C + c] = tot;
   }
 }
 

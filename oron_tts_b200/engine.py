@@ -251,6 +251,9 @@ class DiTEngine:
         self.w = weights
         self._ws: dict = {}
         self.use_graph = True
+        # True: every reduction runs in a fixed order (the stream-K split of the FFN down-projection is switched off), so two
+        # runs from the same noise agree bit for bit; set per call by CFM.sample(deterministic=...), part of the graph key
+        self.deterministic = False
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (not seen by oron_launch_count)
 
     # -------------------------------------------------------------------------------------------
@@ -373,7 +376,7 @@ class DiTEngine:
                    block_n=bn_big, two_sm=True, **common)
             L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                   block_n=bn_big, two_sm=True, stream_k=STREAM_K, **common)
+                   block_n=bn_big, two_sm=True, stream_k=STREAM_K and not self.deterministic, **common)
         o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
         L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o:], shift=tab[o + D:], mod_ld=mld, mod_nb=mod_nb,
                       step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
@@ -396,7 +399,7 @@ class DiTEngine:
             for _ in range(steps):
                 one_step()
             return
-        key = (cfg, has_uncond, method)
+        key = (cfg, has_uncond, method, self.deterministic)
         if ws.graph is None or ws.graph_key != key:
             # warm-up outside capture (sets kernel attributes, builds tables), then rewind the state it touched
             x_save, xb_save = ws.x.clone(), ws.xb.clone()

@@ -382,3 +382,27 @@ def test_precise_fp32_mode_velocity_within_1e4():
     assert _rel(torch.stack(traj), g["s1_traj"]) < 1e-4 and _rel(mel, g["s1_mel"]) < 1e-4
     with pytest.raises(ValueError, match="precision"):
         bb(*args, mask=mask, precision="fp16")
+
+
+def test_seeded_sample_is_bit_reproducible():
+    """The reference's seeded CFM.sample is bit-reproducible run to run. Here the only reduction whose
+    order is not fixed by the program is the stream-K split of the FFN down-projection, whose partial sums are added to
+    the residual stream in contributor order (gemm_tcgen05.cuh: sk_turn_wait): two seeded runs must agree bit for bit,
+    including the whole trajectory, with CFG (batched cond + uncond) and with ragged batches."""
+    import weights as GW
+    from oron_tts_b200.f5tts import F5TTS
+
+    model = F5TTS.from_config(GW.CONFIGS["small"])
+    model.load_state_dict(GW.fill_state_dict(model.state_dict(), GW.SEEDS["small"]), strict=True)
+    model = model.to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    for B, T, lens, durs in ((1, 1406, [469], [1406]), (3, 700, [100, 0, 300], [700, 333, 512])):
+        cond = (torch.randn(B, T, 100, generator=g) * 1.5 - 3.0).to(DEV)
+        ids = torch.randint(4, 65, (B, T), generator=g).to(DEV)
+        kw = dict(lens=torch.tensor(lens, device=DEV), steps=6, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=123)
+        a, ta = model.cfm.sample(cond, ids, torch.tensor(durs, device=DEV), **kw)
+        a, ta = a.clone(), [t.clone() for t in ta]
+        for _ in range(2):
+            b, tb = model.cfm.sample(cond, ids, torch.tensor(durs, device=DEV), **kw)
+            assert torch.equal(a, b)
+            assert all(torch.equal(x, y) for x, y in zip(ta, tb))
