@@ -447,6 +447,9 @@ static int attention4_impl(const CUtensorMap& tq, void* out, int64_t ldo, int32_
   if (abl != 0) {
     auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM_BYTES); return launch_pdl(k, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a); };
     switch (abl) {
+      case 128: le = set(attn_fwd4_kernel<false, 128>); break;
+      case 256: le = set(attn_fwd4_kernel<false, 256>); break;
+      case 384: le = set(attn_fwd4_kernel<false, 384>); break;
       case 7: le = set(attn_fwd4_kernel<false, 7>); break;
       case 15: le = set(attn_fwd4_kernel<false, 15>); break;
       case 23: le = set(attn_fwd4_kernel<false, 23>); break;

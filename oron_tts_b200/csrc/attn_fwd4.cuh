@@ -665,7 +665,12 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
         ffma2(x2, x3, c, nmcb);
         if (!(ABL & 1)) {
           x0 = ex2_approx(x0); x1 = ex2_approx(x1);
-          if (ATT4_EX2_POLY && (k & 4) && k >= 32 && k < 96) {   // keys 36-39, 44-47, ... of the middle two 32-key groups: 1 in 8 per row
+          constexpr int POLYSEL = (ABL >> 7) & 3;  // tuning variants: 0 = 1 in 8 (default), 1 = none, 2 = 1 in 4, 3 = 3 in 8
+          const bool poly = POLYSEL == 1 ? false
+                          : POLYSEL == 0 ? ((k & 4) && k >= 32 && k < 96)
+                          : POLYSEL == 2 ? ((k & 4) && k >= 0 && k < 128)
+                                         : (((k & 4) && k >= 16) || ((k & 8) && !(k & 4) && k >= 32 && k < 96));
+          if (ATT4_EX2_POLY && poly) {
             ex2_poly2(x2, x3);
           } else {
             x2 = ex2_approx(x2); x3 = ex2_approx(x3);
