@@ -219,9 +219,14 @@ int oron_grn(void* h_bf16, int64_t ldh, int32_t rows_per_batch, int32_t nb, int3
  *   wav: f32 [nb, n_samples] (ld_wav elements between clips); fb: f32 [n_fft/2+1, n_mels];
  *   window: f32 [n_fft]; out: f32 [nb, n_mels, n_frames], n_frames = 1 + n_samples / hop.
  * n_fft = 1024, hop = 256 only.
+ *   bands: the non-zero band of every triangular filter, prepared ONCE per filterbank by oron_logmel_bands into a
+ *   caller-owned, 16-byte aligned device buffer of oron_logmel_bands_bytes() bytes (the filterbank is banded: 1-31
+ *   non-zero bins per filter, SURVEY appendix A.1 -- the projection is a short banded sum, not a 513 x 100 GEMM).
  */
+int64_t oron_logmel_bands_bytes(void);
+int oron_logmel_bands(const float* fb, int32_t n_mels, void* bands, oron_stream_t stream);
 int oron_logmel(const float* wav, int64_t ld_wav, int32_t nb, int32_t n_samples, const float* window,
-                const float* fb, int32_t n_mels, float clip, float* out, oron_stream_t stream);
+                const float* fb, const void* bands, int32_t n_mels, float clip, float* out, oron_stream_t stream);
 
 /*
  * Vocos ISTFTHead tail (vocos heads.py ISTFTHead.forward + spectral_ops.py ISTFT "center"):

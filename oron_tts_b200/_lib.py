@@ -35,6 +35,8 @@ EXPORTED_SYMBOLS = (
     "oron_dwconv7_ln",
     "oron_grn",
     "oron_logmel",
+    "oron_logmel_bands",
+    "oron_logmel_bands_bytes",
     "oron_istft_head",
     "oron_peak_normalize",
     "oron_debug_set_attention_stamps",
@@ -138,8 +140,11 @@ def lib() -> ctypes.CDLL:
                                   c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]
     L.oron_grn.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p]
-    L.oron_logmel.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float,
+    L.oron_logmel.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                               c_void_p, c_void_p]
+    L.oron_logmel_bands.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
+    L.oron_logmel_bands_bytes.argtypes = []
+    L.oron_logmel_bands_bytes.restype = c_int64
     L.oron_istft_head.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p,
                                   c_int64, c_void_p]
     L.oron_peak_normalize.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p]
@@ -380,11 +385,24 @@ def grn(h: torch.Tensor, *, rows_per_batch: int, nb: int, seq_lens: torch.Tensor
     )
 
 
-def logmel(wav: torch.Tensor, window: torch.Tensor, fb: torch.Tensor, out: torch.Tensor, *, clip: float) -> None:
-    """wav f32 [nb, S] -> out f32 [nb, n_mels, 1 + S // 256]."""
+def logmel_bands(fb: torch.Tensor) -> torch.Tensor:
+    """The non-zero band of every mel filter of `fb` [513, n_mels], laid out for `logmel` (once per filterbank)."""
+    L = lib()
+    bands = torch.empty(int(L.oron_logmel_bands_bytes()), dtype=torch.uint8, device=fb.device)
+    _check(L.oron_logmel_bands(_ptr(fb, torch.float32, "fb"), fb.shape[1], _ptr(bands, torch.uint8, "bands"), _stream()),
+           "oron_logmel_bands")
+    return bands
+
+
+def logmel(wav: torch.Tensor, window: torch.Tensor, fb: torch.Tensor, out: torch.Tensor, *, clip: float,
+           bands: torch.Tensor | None = None) -> None:
+    """wav f32 [nb, S] -> out f32 [nb, n_mels, 1 + S // 256]. `bands` = logmel_bands(fb) (computed here when omitted)."""
+    if bands is None:
+        bands = logmel_bands(fb)
     _check(
         lib().oron_logmel(_ptr(wav, torch.float32, "wav"), _ld(wav), wav.shape[0], wav.shape[1],
-                          _ptr(window, torch.float32, "window"), _ptr(fb, torch.float32, "fb"), fb.shape[1],
+                          _ptr(window, torch.float32, "window"), _ptr(fb, torch.float32, "fb"),
+                          _ptr(bands, torch.uint8, "bands"), fb.shape[1],
                           float(clip), _ptr(out, torch.float32, "out"), _stream()),
         "oron_logmel",
     )

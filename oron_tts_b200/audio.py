@@ -52,7 +52,10 @@ class AudioProcessor:
     def _tables(self, device: torch.device):
         key = str(device)
         if key not in self._dev_cache:
-            self._dev_cache[key] = (self._win_cpu.to(device), self._fb_cpu.to(device))
+            fb = self._fb_cpu.to(device)
+            with torch.inference_mode(False):
+                bands = L.logmel_bands(fb)  # the banded form of the filterbank, once per device
+            self._dev_cache[key] = (self._win_cpu.to(device), fb, bands)
         return self._dev_cache[key]
 
     # ---- I/O helpers: unchanged behaviour, not on the GPU path ------------------------------------
@@ -103,8 +106,8 @@ class AudioProcessor:
                                "move the waveform to the GPU first, as F5TTS._synthesize_segment does")
         x = audio.unsqueeze(0) if audio.dim() == 1 else audio
         x = x.contiguous().float()
-        window, fb = self._tables(x.device)
+        window, fb, bands = self._tables(x.device)
         frames = 1 + x.shape[1] // self.hop_length
         out = torch.empty(x.shape[0], self.n_mels, frames, device=x.device, dtype=torch.float32)
-        L.logmel(x, window, fb, out, clip=1e-5)
+        L.logmel(x, window, fb, out, clip=1e-5, bands=bands)
         return out.squeeze(0)

@@ -44,14 +44,44 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // ---------------------------------------------------------------------------
 constexpr int MEL_MAXBAND = 32;  // widest triangular filter (bins) kept in smem
 constexpr int MEL_MAXM = 128;
-constexpr int MAG_LD = 544;      // floats between the two magnitude rows inside a warp tile
+// Filter bands (oron_logmel_bands): int lo[128] | int n[128] | float w[32][128]  (w[i][m] = fb[lo[m] + i][m])
+constexpr int MEL_BANDS_BYTES = 2 * MEL_MAXM * 4 + MEL_MAXBAND * MEL_MAXM * 4;
 constexpr int MEL_SMEM = AUD_WARPS * XB_BYTES + NFFT * 8 + NFFT * 4 + MEL_MAXBAND * MEL_MAXM * 4 +
                          AUD_FR * (MEL_MAXM + 1) * 4 + 2 * MEL_MAXM * 4;
 
+// The non-zero band of every triangular mel filter, once per filterbank (it used to be rediscovered by every CTA of
+// every launch: 51 k dependent global loads per CTA, 16 % of the kernel's stall samples).
+__global__ void __launch_bounds__(256)
+logmel_bands_kernel(const float* __restrict__ fb, int n_mels, uint8_t* __restrict__ bands) {
+  __shared__ int lo_s[MEL_MAXM], hi_s[MEL_MAXM];
+  int* lo_g = reinterpret_cast<int*>(bands);
+  int* n_g = lo_g + MEL_MAXM;
+  float* w_g = reinterpret_cast<float*>(n_g + MEL_MAXM);
+  for (int m = threadIdx.x; m < MEL_MAXM; m += blockDim.x) { lo_s[m] = NBIN; hi_s[m] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NBIN * n_mels; i += blockDim.x) {
+    if (fb[i] != 0.f) {
+      const int k = i / n_mels, m = i - k * n_mels;
+      atomicMin(&lo_s[m], k);
+      atomicMax(&hi_s[m], k);
+    }
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < MEL_MAXM; m += blockDim.x) {
+    const bool any = m < n_mels && lo_s[m] <= hi_s[m];
+    const int lo = any ? lo_s[m] : 0;
+    const int n = any ? hi_s[m] - lo_s[m] + 1 : 0;
+    lo_g[m] = lo;
+    n_g[m] = n;  // n > MEL_MAXBAND: the kernel reads this filter from fb directly
+    for (int i = 0; i < MEL_MAXBAND; ++i) w_g[i * MEL_MAXM + m] = (i < n && n <= MEL_MAXBAND) ? fb[(long long)(lo + i) * n_mels + m] : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(AUD_THREADS, 2)
 logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_samples, int n_frames,
-              const float* __restrict__ window, const float* __restrict__ fb, int n_mels, float clip,
-              float* __restrict__ out) {
+              const float* __restrict__ window, const float* __restrict__ fb, const uint8_t* __restrict__ bands, int n_mels,
+              float clip, float* __restrict__ out) {
+  using fw::c64;
   extern __shared__ __align__(16) uint8_t dsm[];
   float2* xb_all = reinterpret_cast<float2*>(dsm);
   float2* tw = xb_all + AUD_WARPS * fw::XB_ELEMS;
@@ -62,48 +92,46 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
   int* band_n = band_lo + MEL_MAXM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* xb = xb_all + warp * fw::XB_ELEMS;
-  float* magA = reinterpret_cast<float*>(xb);
-  float* magB = magA + MAG_LD;
+  c64* mag2 = reinterpret_cast<c64*>(xb);  // after the transform: (|A[k]|, |B[k]|), k = 0..512, of this warp's frame pair
 
-  // ---- once per (persistent) CTA: twiddles, window, and the band of every triangular mel filter ----
+  // ---- once per (persistent) CTA: twiddles, window, filter bands ----
   fw::fill_twiddle_table(tw);
   for (int n = threadIdx.x; n < NFFT; n += blockDim.x) win[n] = window[n];
-  for (int m = threadIdx.x; m < MEL_MAXM; m += blockDim.x) { band_lo[m] = NBIN; band_n[m] = -1; }  // band_n holds "hi" for now
-  __syncthreads();
-  for (int i = threadIdx.x; i < NBIN * n_mels; i += blockDim.x) {
-    if (fb[i] != 0.f) {
-      const int k = i / n_mels, m = i - k * n_mels;
-      atomicMin(&band_lo[m], k);
-      atomicMax(&band_n[m], k);
-    }
-  }
-  __syncthreads();
-  for (int m = threadIdx.x; m < MEL_MAXM; m += blockDim.x) {
-    const bool any = m < n_mels && band_lo[m] <= band_n[m];
-    const int lo = any ? band_lo[m] : 0;
-    const int n = any ? band_n[m] - band_lo[m] + 1 : 0;
-    band_lo[m] = lo;
-    band_n[m] = n;
-    for (int i = 0; i < MEL_MAXBAND; ++i) fbs[i][m] = (i < n && n <= MEL_MAXBAND) ? fb[(long long)(lo + i) * n_mels + m] : 0.f;
+  {
+    const int* bl = reinterpret_cast<const int*>(bands);
+    const float4* bw = reinterpret_cast<const float4*>(bands + 2 * MEL_MAXM * 4);
+    for (int m = threadIdx.x; m < 2 * MEL_MAXM; m += blockDim.x) band_lo[m] = bl[m];  // lo[128] | n[128], contiguous here too
+    float4* dst = reinterpret_cast<float4*>(&fbs[0][0]);
+    for (int i = threadIdx.x; i < MEL_MAXBAND * MEL_MAXM / 4; i += blockDim.x) dst[i] = bw[i];
   }
   __syncthreads();
 
   const int chunks_per_clip = (n_frames + AUD_FR - 1) / AUD_FR;
-  for (int chunk = blockIdx.x; chunk < nb * chunks_per_clip; chunk += gridDim.x) {
+  const int n_chunks = nb * chunks_per_clip;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int b = chunk / chunks_per_clip;
     const int t0 = (chunk - b * chunks_per_clip) * AUD_FR;
     const float* x = wav + (long long)b * ld_wav;
+    {  // the next chunk's samples ((AUD_FR - 1) * HOP + NFFT floats) into L2 while this one is transformed
+      const int nc = chunk + gridDim.x;
+      if (nc < n_chunks) {
+        const int nb_ = nc / chunks_per_clip;
+        const long long s0 = (long long)(nc - nb_ * chunks_per_clip) * AUD_FR * HOP - NFFT / 2 + 32LL * threadIdx.x;
+        if (threadIdx.x < ((AUD_FR - 1) * HOP + NFFT + 31) / 32 && s0 >= 0 && s0 < n_samples)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(wav + (long long)nb_ * ld_wav + s0));
+      }
+    }
     const int fA = t0 + 2 * warp;
     if (fA < n_frames) {  // warp-uniform
       const bool hasB = fA + 1 < n_frames;
       // frame pair (fA, fA+1): reflect-padded (center=True) windowed samples, lane holds n = lane + 32 n1
-      float2 v[32];
+      c64 v[32];
       const int base = fA * HOP - NFFT / 2 + lane;
       if (base - lane >= 0 && base - lane + NFFT + HOP <= n_samples) {  // interior: no reflection
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
           const float w = win[lane + 32 * n1];
-          v[n1] = make_float2(x[base + 32 * n1] * w, x[base + HOP + 32 * n1] * w);
+          v[n1] = fw::cmul2(fw::cpack(x[base + 32 * n1], x[base + HOP + 32 * n1]), fw::cpack(w, w));
         }
       } else {
 #pragma unroll
@@ -119,49 +147,47 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
             if (nB >= n_samples) nB = 2 * (n_samples - 1) - nB;
             vb = x[nB] * w;
           }
-          v[n1] = make_float2(x[nA] * w, vb);
+          v[n1] = fw::cpack(x[nA] * w, vb);
         }
       }
       fw::fft1024_warp<false>(v, xb, tw, lane);
       // split the two real spectra: bin k = lane + 32 k2 needs Z[k] and Z[1024 - k]; the latter sits in lane
-      // (32 - lane) & 31, register 31 - k2 (lane 0: own register (32 - k2) & 31)
+      // (32 - lane) & 31, register 31 - k2 (lane 0: own register (32 - k2) & 31).
+      // A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i: |A| = |p| / 2, |B| = |q| / 2 with
+      // p = (z.x + zp.x, z.y - zp.y), q = (z.x - zp.x, z.y + zp.y)
       const int src = (32 - lane) & 31;
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
-        const float2 z = v[k2];
-        float2 zp;
-        zp.x = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
-        zp.y = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
+        const c64 z = v[k2];
+        c64 zp = __shfl_sync(0xffffffffu, v[31 - k2], src);
         if (lane == 0) zp = v[(32 - k2) & 31];
-        const float ar = 0.5f * (z.x + zp.x), ai = 0.5f * (z.y - zp.y);
-        const float br = 0.5f * (z.y + zp.y), bi = 0.5f * (zp.x - z.x);
-        magA[lane + 32 * k2] = sqrt_approx(ar * ar + ai * ai);
-        magB[lane + 32 * k2] = sqrt_approx(br * br + bi * bi);
+        const c64 pq = fw::cfma2(zp, fw::cpack(1.0f, -1.0f), z), qq = fw::cfma2(zp, fw::cpack(-1.0f, 1.0f), z);
+        const float2 p2 = fw::cunpack(fw::cmul2(pq, pq)), q2 = fw::cunpack(fw::cmul2(qq, qq));
+        mag2[lane + 32 * k2] = fw::cpack(sqrt_approx(0.25f * (p2.x + p2.y)), sqrt_approx(0.25f * (q2.x + q2.y)));
       }
       if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
-        magA[512] = fabsf(v[16].x);
-        magB[512] = fabsf(v[16].y);
+        const float2 ny = fw::cunpack(v[16]);
+        mag2[512] = fw::cpack(fabsf(ny.x), fabsf(ny.y));
       }
       __syncwarp();
-      // banded mel projection: lane -> filters lane, lane+32, ...
+      // banded mel projection, both frames at once: lane -> filters lane, lane+32, ...
       for (int m = lane; m < n_mels; m += 32) {
         const int lo = band_lo[m], n = band_n[m];
-        float accA = 0.f, accB = 0.f;
+        c64 acc = fw::cpack(0.f, 0.f);
         if (n <= MEL_MAXBAND) {
           for (int i = 0; i < n; ++i) {
             const float f = fbs[i][m];
-            accA += f * magA[lo + i];
-            accB += f * magB[lo + i];
+            acc = fw::cfma2(mag2[lo + i], fw::cpack(f, f), acc);
           }
         } else {
           for (int i = 0; i < n; ++i) {
             const float f = fb[(long long)(lo + i) * n_mels + m];
-            accA += f * magA[lo + i];
-            accB += f * magB[lo + i];
+            acc = fw::cfma2(mag2[lo + i], fw::cpack(f, f), acc);
           }
         }
-        mel_s[2 * warp][m] = logf(fmaxf(accA, clip));
-        mel_s[2 * warp + 1][m] = logf(fmaxf(accB, clip));
+        const float2 a2 = fw::cunpack(acc);
+        mel_s[2 * warp][m] = logf(fmaxf(a2.x, clip));
+        mel_s[2 * warp + 1][m] = logf(fmaxf(a2.y, clip));
       }
     }
     __syncthreads();
@@ -358,9 +384,20 @@ peak_scale_kernel(const float* __restrict__ x, long long ldx, int n, const float
 
 }  // namespace
 
+extern "C" int64_t oron_logmel_bands_bytes(void) { return MEL_BANDS_BYTES; }
+
+extern "C" int oron_logmel_bands(const float* fb, int32_t n_mels, void* bands, oron_stream_t stream) {
+  if (!fb || !bands) return fail(ORON_ERR_BAD_ARG, "logmel_bands: null pointer");
+  if (n_mels <= 0 || n_mels > MEL_MAXM) return fail(ORON_ERR_BAD_ARG, "logmel_bands: n_mels must be in [1,128]");
+  if ((reinterpret_cast<uintptr_t>(bands) & 15) != 0) return fail(ORON_ERR_BAD_ARG, "logmel_bands: buffer must be 16-byte aligned");
+  logmel_bands_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(fb, n_mels, reinterpret_cast<uint8_t*>(bands));
+  return check_launch("logmel_bands");
+}
+
 extern "C" int oron_logmel(const float* wav, int64_t ld_wav, int32_t nb, int32_t n_samples, const float* window,
-                           const float* fb, int32_t n_mels, float clip, float* out, oron_stream_t stream) {
-  if (!wav || !window || !fb || !out) return fail(ORON_ERR_BAD_ARG, "logmel: null pointer");
+                           const float* fb, const void* bands, int32_t n_mels, float clip, float* out, oron_stream_t stream) {
+  if (!wav || !window || !fb || !bands || !out) return fail(ORON_ERR_BAD_ARG, "logmel: null pointer");
+  if ((reinterpret_cast<uintptr_t>(bands) & 15) != 0) return fail(ORON_ERR_BAD_ARG, "logmel: bands must be 16-byte aligned");
   if (nb <= 0 || n_mels <= 0 || n_mels > MEL_MAXM) return fail(ORON_ERR_BAD_ARG, "logmel: n_mels must be in [1,128]");
   if (n_samples <= NFFT / 2) return fail(ORON_ERR_BAD_ARG, "logmel: reflect padding needs more than 512 samples");
   const int n_frames = 1 + n_samples / HOP;
@@ -374,7 +411,7 @@ extern "C" int oron_logmel(const float* wav, int64_t ld_wav, int32_t nb, int32_t
     configured = true;
   }
   logmel_kernel<<<grid, AUD_THREADS, MEL_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-      wav, ld_wav, nb, n_samples, n_frames, window, fb, n_mels, clip, out);
+      wav, ld_wav, nb, n_samples, n_frames, window, fb, reinterpret_cast<const uint8_t*>(bands), n_mels, clip, out);
   return check_launch("logmel");
 }
 

@@ -9,8 +9,9 @@
 //   transpose: write row k1 / read row n2 of a 32 x 33 float2 tile (both conflict-free)
 //   pass 2: lane k1 holds n2 = register index, DFT-32 over n2 -> X[k1 + 32 k2] in register k2
 //
-// Instruction budget per lane: 2 x ~460 (butterflies) + 31 x 4 (twiddles) + 64 smem accesses, versus
-// ~850 per thread x 8 warps for the former block-wide radix-4 Stockham transform with five barriers.
+// Instruction budget per lane: 2 x ~260 packed-f32x2 butterfly instructions + 31 x 2 (twiddles) + 64 smem accesses (the
+// scalar version of the same transform: 2 x ~460 + 31 x 4; the block-wide radix-4 Stockham transform before it: ~850 per
+// thread x 8 warps with five barriers).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -44,37 +45,75 @@ __device__ __forceinline__ void static_for(F&& f) {
   }
 }
 
+// ---- packed complex arithmetic: one 64-bit register pair = (re, im), every operation one FADD2 / FMUL2 / FFMA2 (the
+// swap of the two halves and the sign pattern of a complex product are operand modifiers of FFMA2 on sm_100: free).
+// A radix-2 butterfly with twiddle is 4 instructions instead of 10 scalar ones; these kernels are bound by fp32
+// instruction issue ("audio kernels").
+typedef unsigned long long c64;
+__device__ __forceinline__ c64 cpack(float re, float im) {
+  c64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im));
+  return r;
+}
+__device__ __forceinline__ float2 cunpack(c64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ c64 cswap(c64 v) {
+  const float2 t = cunpack(v);
+  return cpack(t.y, t.x);
+}
+__device__ __forceinline__ c64 cadd(c64 a, c64 b) {
+  c64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c64 csub(c64 a, c64 b) {
+  c64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c64 cmul2(c64 a, c64 b) {  // element-wise
+  c64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c64 cfma2(c64 a, c64 b, c64 c) {  // element-wise a * b + c
+  c64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// d * (wr + i wi)
+__device__ __forceinline__ c64 cmul(c64 d, float wr, float wi) {
+  return cfma2(cswap(d), cpack(-wi, wi), cmul2(d, cpack(wr, wr)));
+}
+
 // d * exp(-2 pi i M / 32) (forward) or d * exp(+2 pi i M / 32) (inverse)
 template <int M, bool INV>
-__device__ __forceinline__ float2 mul_w32(float2 d) {
+__device__ __forceinline__ c64 mul_w32(c64 d) {
   if constexpr (M == 0) {
     return d;
-  } else if constexpr (M == 8) {
-    return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-  } else if constexpr (M == 4) {
-    constexpr float r = 0.70710678118655f;
-    return INV ? make_float2(r * (d.x - d.y), r * (d.x + d.y)) : make_float2(r * (d.x + d.y), r * (d.y - d.x));
-  } else if constexpr (M == 12) {
-    constexpr float r = 0.70710678118655f;
-    return INV ? make_float2(-r * (d.x + d.y), r * (d.x - d.y)) : make_float2(r * (d.y - d.x), -r * (d.x + d.y));
+  } else if constexpr (M == 8) {  // -i d = (d.y, -d.x);  +i d = (-d.y, d.x)
+    return cmul2(cswap(d), INV ? cpack(-1.0f, 1.0f) : cpack(1.0f, -1.0f));
   } else {
     constexpr float c = kCos[M], s = kSin[M];
-    return INV ? make_float2(d.x * c - d.y * s, d.y * c + d.x * s) : make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
+    return INV ? cmul(d, c, s) : cmul(d, c, -s);
   }
 }
 
 // In-register 32-point DFT, decimation in frequency: v[brev5(k)] = sum_n v_in[n] W32^{nk} on return.
 template <bool INV>
-__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+__device__ __forceinline__ void dft32(c64 (&v)[32]) {
   static_for<0, 5>([&](auto S) {
     constexpr int half = 16 >> decltype(S)::value;
     static_for<0, 16>([&](auto I) {
       constexpr int i = decltype(I)::value;
       constexpr int i0 = (i / half) * 2 * half + (i % half), i1 = i0 + half;
       constexpr int m = (i % half) * (16 / half);
-      const float2 a = v[i0], c = v[i1];
-      v[i0] = make_float2(a.x + c.x, a.y + c.y);
-      v[i1] = mul_w32<m, INV>(make_float2(a.x - c.x, a.y - c.y));
+      const c64 a = v[i0], c = v[i1];
+      v[i0] = cadd(a, c);
+      v[i1] = mul_w32<m, INV>(csub(a, c));
     });
   });
 }
@@ -92,27 +131,38 @@ __device__ __forceinline__ void fill_twiddle_table(float2* tw) {
 // in:  v[n1] = x[32 n1 + lane];  out: v[k2] = X[lane + 32 k2].  `xb` is this warp's XB_ELEMS tile.
 // Unnormalised in both directions.  Ends with a __syncwarp(): the tile may be reused right away.
 template <bool INV>
-__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* xb, const float2* tw, int lane) {
+__device__ __forceinline__ void fft1024_warp(c64 (&v)[32], float2* xb, const float2* tw, int lane) {
   dft32<INV>(v);
+  c64* xq = reinterpret_cast<c64*>(xb);
+  const c64* twq = reinterpret_cast<const c64*>(tw);
   static_for<0, 32>([&](auto K) {
     constexpr int k1 = decltype(K)::value;
-    float2 y = v[brev5(k1)];
+    c64 y = v[brev5(k1)];
     if constexpr (k1 > 0) {
-      float2 w = tw[k1 * 32 + lane];
-      if (INV) w.y = -w.y;
-      y = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+      const float2 w = cunpack(twq[k1 * 32 + lane]);  // exp(-2 pi i k1 lane / 1024); conjugate for the inverse
+      y = cmul(y, w.x, INV ? -w.y : w.y);
     }
-    xb[k1 * XB_LD + lane] = y;
+    xq[k1 * XB_LD + lane] = y;
   });
   __syncwarp();
 #pragma unroll
-  for (int n2 = 0; n2 < 32; ++n2) v[n2] = xb[lane * XB_LD + n2];
+  for (int n2 = 0; n2 < 32; ++n2) v[n2] = xq[lane * XB_LD + n2];
   __syncwarp();
   dft32<INV>(v);
-  float2 t[32];
+  c64 t[32];
   static_for<0, 32>([&](auto K) { t[decltype(K)::value] = v[brev5(decltype(K)::value)]; });
 #pragma unroll
   for (int k = 0; k < 32; ++k) v[k] = t[k];
+}
+// float2 interface (same contract)
+template <bool INV>
+__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* xb, const float2* tw, int lane) {
+  c64 q[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) q[k] = cpack(v[k].x, v[k].y);
+  fft1024_warp<INV>(q, xb, tw, lane);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = cunpack(q[k]);
 }
 
 }  // namespace fw
