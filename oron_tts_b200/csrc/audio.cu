@@ -106,98 +106,99 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
   }
   __syncthreads();
 
-  const int chunks_per_clip = (n_frames + AUD_FR - 1) / AUD_FR;
-  const int n_chunks = nb * chunks_per_clip;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int b = chunk / chunks_per_clip;
-    const int t0 = (chunk - b * chunks_per_clip) * AUD_FR;
+  // Every warp is on its own from here on: it walks frame pairs (two real frames per complex transform) with no block
+  // barrier -- the transform, the spectra, the projection and the store of a pair all stay inside the warp.
+  const int pairs_per_clip = (n_frames + 1) / 2;
+  const long long n_pairs = (long long)nb * pairs_per_clip;
+  const long long pair_step = (long long)gridDim.x * AUD_WARPS;
+  for (long long pair = (long long)blockIdx.x * AUD_WARPS + warp; pair < n_pairs; pair += pair_step) {
+    const int b = int(pair / pairs_per_clip);
+    const int fA = 2 * int(pair - (long long)b * pairs_per_clip);
     const float* x = wav + (long long)b * ld_wav;
-    {  // the next chunk's samples ((AUD_FR - 1) * HOP + NFFT floats) into L2 while this one is transformed
-      const int nc = chunk + gridDim.x;
-      if (nc < n_chunks) {
-        const int nb_ = nc / chunks_per_clip;
-        const long long s0 = (long long)(nc - nb_ * chunks_per_clip) * AUD_FR * HOP - NFFT / 2 + 32LL * threadIdx.x;
-        if (threadIdx.x < ((AUD_FR - 1) * HOP + NFFT + 31) / 32 && s0 >= 0 && s0 < n_samples)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(wav + (long long)nb_ * ld_wav + s0));
+    {  // the next pair's samples (NFFT + HOP floats = 40 lines of 128 bytes) into L2 while this one is transformed
+      const long long np = pair + pair_step;
+      if (np < n_pairs) {
+        const int nb_ = int(np / pairs_per_clip);
+        const long long s0 = 2LL * (np - (long long)nb_ * pairs_per_clip) * HOP - NFFT / 2;
+        const float* px = wav + (long long)nb_ * ld_wav;
+        const long long o0 = s0 + 32LL * lane, o1 = s0 + 32LL * (lane + 32);
+        if (o0 >= 0 && o0 < n_samples) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o0));
+        if (lane < 8 && o1 >= 0 && o1 < n_samples) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o1));
       }
     }
-    const int fA = t0 + 2 * warp;
-    if (fA < n_frames) {  // warp-uniform
-      const bool hasB = fA + 1 < n_frames;
-      // frame pair (fA, fA+1): reflect-padded (center=True) windowed samples, lane holds n = lane + 32 n1
-      c64 v[32];
-      const int base = fA * HOP - NFFT / 2 + lane;
-      if (base - lane >= 0 && base - lane + NFFT + HOP <= n_samples) {  // interior: no reflection
+    const bool hasB = fA + 1 < n_frames;
+    // frame pair (fA, fA+1): reflect-padded (center=True) windowed samples, lane holds n = lane + 32 n1
+    c64 v[32];
+    const int base = fA * HOP - NFFT / 2 + lane;
+    if (base - lane >= 0 && base - lane + NFFT + HOP <= n_samples) {  // interior: no reflection
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const float w = win[lane + 32 * n1];
-          v[n1] = fw::cmul2(fw::cpack(x[base + 32 * n1], x[base + HOP + 32 * n1]), fw::cpack(w, w));
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const float w = win[lane + 32 * n1];
+        v[n1] = fw::cmul2(fw::cpack(x[base + 32 * n1], x[base + HOP + 32 * n1]), fw::cpack(w, w));
+      }
+    } else {
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const float w = win[lane + 32 * n1];
+        int nA = base + 32 * n1;
+        if (nA < 0) nA = -nA;
+        if (nA >= n_samples) nA = 2 * (n_samples - 1) - nA;
+        float vb = 0.f;
+        if (hasB) {
+          int nB = base + HOP + 32 * n1;
+          if (nB < 0) nB = -nB;
+          if (nB >= n_samples) nB = 2 * (n_samples - 1) - nB;
+          vb = x[nB] * w;
+        }
+        v[n1] = fw::cpack(x[nA] * w, vb);
+      }
+    }
+    fw::fft1024_warp<false>(v, xb, tw, lane);
+    // split the two real spectra: bin k = lane + 32 k2 needs Z[k] and Z[1024 - k]; the latter sits in lane
+    // (32 - lane) & 31, register 31 - k2 (lane 0: own register (32 - k2) & 31).
+    // A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i: |A| = |p| / 2, |B| = |q| / 2 with
+    // p = (z.x + zp.x, z.y - zp.y), q = (z.x - zp.x, z.y + zp.y)
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const c64 z = v[k2];
+      c64 zp = __shfl_sync(0xffffffffu, v[31 - k2], src);
+      if (lane == 0) zp = v[(32 - k2) & 31];
+      const c64 pq = fw::cfma2(zp, fw::cpack(1.0f, -1.0f), z), qq = fw::cfma2(zp, fw::cpack(-1.0f, 1.0f), z);
+      const float2 p2 = fw::cunpack(fw::cmul2(pq, pq)), q2 = fw::cunpack(fw::cmul2(qq, qq));
+      mag2[lane + 32 * k2] = fw::cpack(sqrt_approx(0.25f * (p2.x + p2.y)), sqrt_approx(0.25f * (q2.x + q2.y)));
+    }
+    if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
+      const float2 ny = fw::cunpack(v[16]);
+      mag2[512] = fw::cpack(fabsf(ny.x), fabsf(ny.y));
+    }
+    __syncwarp();
+    // banded mel projection, both frames at once: lane -> filters lane, lane + 32, ...; rows of fbs beyond a filter's
+    // band hold zeros, so the band loop runs in steps of four independent multiply-adds (bins clamped to the last one)
+    for (int m = lane; m < n_mels; m += 32) {
+      const int lo = band_lo[m], n = band_n[m];
+      c64 acc0 = fw::cpack(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+      if (n <= MEL_MAXBAND) {
+        for (int i = 0; i < n; i += 4) {
+          const float f0 = fbs[i][m], f1 = fbs[i + 1][m], f2 = fbs[i + 2][m], f3 = fbs[i + 3][m];
+          const int k = lo + i;
+          acc0 = fw::cfma2(mag2[min(k, 512)], fw::cpack(f0, f0), acc0);
+          acc1 = fw::cfma2(mag2[min(k + 1, 512)], fw::cpack(f1, f1), acc1);
+          acc2 = fw::cfma2(mag2[min(k + 2, 512)], fw::cpack(f2, f2), acc2);
+          acc3 = fw::cfma2(mag2[min(k + 3, 512)], fw::cpack(f3, f3), acc3);
         }
       } else {
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          const float w = win[lane + 32 * n1];
-          int nA = base + 32 * n1;
-          if (nA < 0) nA = -nA;
-          if (nA >= n_samples) nA = 2 * (n_samples - 1) - nA;
-          float vb = 0.f;
-          if (hasB) {
-            int nB = base + HOP + 32 * n1;
-            if (nB < 0) nB = -nB;
-            if (nB >= n_samples) nB = 2 * (n_samples - 1) - nB;
-            vb = x[nB] * w;
-          }
-          v[n1] = fw::cpack(x[nA] * w, vb);
+        for (int i = 0; i < n; ++i) {
+          const float f = fb[(long long)(lo + i) * n_mels + m];
+          acc0 = fw::cfma2(mag2[lo + i], fw::cpack(f, f), acc0);
         }
       }
-      fw::fft1024_warp<false>(v, xb, tw, lane);
-      // split the two real spectra: bin k = lane + 32 k2 needs Z[k] and Z[1024 - k]; the latter sits in lane
-      // (32 - lane) & 31, register 31 - k2 (lane 0: own register (32 - k2) & 31).
-      // A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i: |A| = |p| / 2, |B| = |q| / 2 with
-      // p = (z.x + zp.x, z.y - zp.y), q = (z.x - zp.x, z.y + zp.y)
-      const int src = (32 - lane) & 31;
-#pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        const c64 z = v[k2];
-        c64 zp = __shfl_sync(0xffffffffu, v[31 - k2], src);
-        if (lane == 0) zp = v[(32 - k2) & 31];
-        const c64 pq = fw::cfma2(zp, fw::cpack(1.0f, -1.0f), z), qq = fw::cfma2(zp, fw::cpack(-1.0f, 1.0f), z);
-        const float2 p2 = fw::cunpack(fw::cmul2(pq, pq)), q2 = fw::cunpack(fw::cmul2(qq, qq));
-        mag2[lane + 32 * k2] = fw::cpack(sqrt_approx(0.25f * (p2.x + p2.y)), sqrt_approx(0.25f * (q2.x + q2.y)));
-      }
-      if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
-        const float2 ny = fw::cunpack(v[16]);
-        mag2[512] = fw::cpack(fabsf(ny.x), fabsf(ny.y));
-      }
-      __syncwarp();
-      // banded mel projection, both frames at once: lane -> filters lane, lane+32, ...
-      for (int m = lane; m < n_mels; m += 32) {
-        const int lo = band_lo[m], n = band_n[m];
-        c64 acc = fw::cpack(0.f, 0.f);
-        if (n <= MEL_MAXBAND) {
-          for (int i = 0; i < n; ++i) {
-            const float f = fbs[i][m];
-            acc = fw::cfma2(mag2[lo + i], fw::cpack(f, f), acc);
-          }
-        } else {
-          for (int i = 0; i < n; ++i) {
-            const float f = fb[(long long)(lo + i) * n_mels + m];
-            acc = fw::cfma2(mag2[lo + i], fw::cpack(f, f), acc);
-          }
-        }
-        const float2 a2 = fw::cunpack(acc);
-        mel_s[2 * warp][m] = logf(fmaxf(a2.x, clip));
-        mel_s[2 * warp + 1][m] = logf(fmaxf(a2.y, clip));
-      }
+      const float2 a2 = fw::cunpack(fw::cadd(fw::cadd(acc0, acc1), fw::cadd(acc2, acc3)));
+      float* o = out + ((long long)b * n_mels + m) * n_frames + fA;
+      o[0] = logf(fmaxf(a2.x, clip));
+      if (hasB) o[1] = logf(fmaxf(a2.y, clip));
     }
-    __syncthreads();
-    // out[b, m, t0 + f]: contiguous along frames
-    const int nfr = min(AUD_FR, n_frames - t0);
-    for (int i = threadIdx.x; i < n_mels * AUD_FR; i += blockDim.x) {
-      const int m = i / AUD_FR, f = i % AUD_FR;
-      if (f < nfr) out[((long long)b * n_mels + m) * n_frames + t0 + f] = mel_s[f][m];
-    }
-    __syncthreads();  // mel_s and the warp tiles are reused by the next chunk
+    __syncwarp();  // the tile (magnitudes) is reused by the next pair's transform
   }
 }
 
