@@ -354,6 +354,14 @@ static bool attn_inline_combine() {
   if (v < 0) { const char* e = getenv("ORON_ATT_COMBINE"); v = (e && e[0] == 'i') ? 1 : 0; }
   return v == 1;
 }
+// ORON_ATT_SKEW: share of a CTA's work moved from the second CTA of every SM to the first (attn4_plan_kernel). Default 0:
+// measured at config 2, per call: 0 -> 33.0 us, 0.05 -> 33.4, 0.09 -> 34.5, 0.13 -> 37.0 (the asymmetry between the two CTAs
+// of an SM is real -- 17.9 vs 21.5 us with equal work -- but is not a property of the block index that a static plan can use)
+static float attn_skew() {
+  static float v = -1.f;
+  if (v < 0.f) { const char* e = getenv("ORON_ATT_SKEW"); v = e ? float(atof(e)) : 0.0f; if (v < 0.f) v = 0.f; }
+  return v;
+}
 struct Attn4WsLayout {
   int grid, seg_stride;
   int64_t off_nseg, off_segs, off_merge, off_cnt, off_ml, off_o, bytes;
@@ -391,7 +399,7 @@ extern "C" int oron_attention_plan(const int32_t* seq_lens, int32_t nbatch, int3
     const Attn4WsLayout w = attn4_ws_layout(nbatch, rows_per_batch, heads);
     attn4_plan_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<Attn4PlanHeader*>(p), reinterpret_cast<int*>(p + w.off_nseg), reinterpret_cast<Attn4Seg*>(p + w.off_segs),
-        reinterpret_cast<Attn4Merge*>(p + w.off_merge), reinterpret_cast<int*>(p + w.off_cnt), seq_lens, nbatch, rows_per_batch, heads, w.grid, w.seg_stride, g_attn_schedule == 1 ? 1 : 0);
+        reinterpret_cast<Attn4Merge*>(p + w.off_merge), reinterpret_cast<int*>(p + w.off_cnt), seq_lens, nbatch, rows_per_batch, heads, w.grid, w.seg_stride, g_attn_schedule == 1 ? 1 : 0, attn_skew());
     return check_launch("attn4_plan");
   }
   const AttnWsLayout w = attn_ws_layout(nbatch, rows_per_batch, heads);
@@ -458,16 +466,20 @@ static int attention4_impl(const CUtensorMap& tq, void* out, int64_t ldo, int32_
       case 55: le = set(attn_fwd4_kernel<false, 55>); break;
       default: le = a.dbg ? set(attn_fwd4_kernel<true, 127>) : set(attn_fwd4_kernel<false, 127>); break;
     }
-  } else
-  le = a.dbg ? launch_pdl(attn_fwd4_kernel<true>, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a)
+  } else {
+  // ORON_ATT_TRACE=lite: the production instantiation with start / end wall-clock stamps only
+  static int lite = -1;
+  if (lite < 0) { const char* e = getenv("ORON_ATT_TRACE"); lite = (e && e[0] == 'l') ? 1 : 0; }
+  le = (a.dbg && !lite) ? launch_pdl(attn_fwd4_kernel<true>, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a)
              : launch_pdl(attn_fwd4_kernel<false>, grid, dim3(ATT4_THREADS), ATT4_SMEM_BYTES, st, tq, a);
+  }
   if (le != cudaSuccess) return fail(int(le), "attention launch: %s", cudaGetErrorString(le));
   int rc = check_launch("attn_fwd4");
   if (rc) return rc;
   // items are split only when there are more of them than CTAs (or when the test aid forces shares): then the parts are
   // combined by a second, small launch right behind the first
   if (planned && a.ws_cnt == nullptr && (items > w.grid || g_attn_schedule == 1)) {
-    le = launch_pdl(attn4_combine_kernel, dim3(unsigned(w.grid)), dim3(256), 0, st, a.plan_merge, (const __half*)a.ws_o, (const float*)a.ws_ml,
+    le = launch_pdl(attn4_combine_kernel, dim3(unsigned(4 * w.grid)), dim3(256), 0, st, a.plan_merge, (const __half*)a.ws_o, (const float*)a.ws_ml,
                     a.out, (long long)ldo, lse, (int)rows_per_batch, (int)heads);
     if (le != cudaSuccess) return fail(int(le), "attention combine launch: %s", cudaGetErrorString(le));
     rc = check_launch("attn4_combine");

@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
   return ok;
 }
 #ifndef ATT4_SPIN
-#define ATT4_SPIN 1   // 1: poll with the non-blocking test_wait (the SM never goes to sleep), 0: suspending try_wait
+#define ATT4_SPIN 0   // 1: poll with the non-blocking test_wait, 0: suspending try_wait (measured: no difference for the main roles)
 #endif
 __device__ __forceinline__ void mbar_wait4(uint32_t bar, uint32_t parity, int tag) {
 #if ATT4_SPIN
@@ -236,15 +236,15 @@ __device__ __forceinline__ int seg_field(const Attn4Seg* segs, int s, int f) {
 // Combine the parts of one split item (parts live in slots 2 (owner + p) + (p == 0), p = 0 .. nparts - 1): NT threads,
 // 8 threads per row (16 bytes of f16 each), RPT rows per thread per round, four parts per round of loads, all of a round's
 // loads in flight at once; online (running-max) combination.
-template <int NT, int RPT>
+template <int NT, int RPT, int PPR = 4>
 __device__ __forceinline__ void att4_combine_item(int tid, int owner, int nparts, int b, int h, int qt, const __half* ws_o,
                                                   const float* ws_ml, __nv_bfloat16* out, long long ldo, float* lse,
-                                                  int rows_per_batch, int heads) {
+                                                  int rows_per_batch, int heads, int row_begin = 0, int row_end = ATT4_TILE) {
   constexpr int ROWS = NT / 8;  // rows per sub-pass
   const int rsub = tid >> 3, c8 = (tid & 7) * 8;
   auto slot_of = [&](int p) { return (long long)(2 * (owner + p) + (p == 0 ? 1 : 0)); };
 #pragma unroll 1
-  for (int r0 = 0; r0 < ATT4_TILE; r0 += ROWS * RPT) {
+  for (int r0 = row_begin; r0 < row_end; r0 += ROWS * RPT) {
     float acc[RPT][8], m_run[RPT], l_run[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -254,11 +254,11 @@ __device__ __forceinline__ void att4_combine_item(int tid, int owner, int nparts
       for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
     }
 #pragma unroll 1
-    for (int p0 = 0; p0 < nparts; p0 += 4) {
-      float2 ml[RPT][4];
-      uint4 u[RPT][4];
+    for (int p0 = 0; p0 < nparts; p0 += PPR) {
+      float2 ml[RPT][PPR];
+      uint4 u[RPT][PPR];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < PPR; ++i) {
         const long long sl = slot_of(min(p0 + i, nparts - 1)) * ATT4_TILE;
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
@@ -271,13 +271,13 @@ __device__ __forceinline__ void att4_combine_item(int tid, int owner, int nparts
       for (int j = 0; j < RPT; ++j) {
         float m_new = m_run[j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) if (p0 + i < nparts) m_new = fmaxf(m_new, ml[j][i].x);
+        for (int i = 0; i < PPR; ++i) if (p0 + i < nparts) m_new = fmaxf(m_new, ml[j][i].x);
         const float f_old = ex2_approx(m_run[j] - m_new);  // 0 on the first round (m_run = -inf)
         l_run[j] *= f_old;
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[j][k] *= f_old;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < PPR; ++i) {
           const float wgt = p0 + i < nparts ? ml[j][i].y * ex2_approx(ml[j][i].x - m_new) : 0.f;
           l_run[j] += wgt;
           const uint32_t wd[4] = {u[j][i].x, u[j][i].y, u[j][i].z, u[j][i].w};
@@ -396,7 +396,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
   pdl_wait();  // the QKV activations of the previous kernel are visible from here on
   if (threadIdx.x == 0) {
     ATT4_STAMP(0);
-    if (DBG) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); args.dbg[(long long)blockIdx.x * 16 + 8] = (long long)gt; }
+    if (args.dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); args.dbg[(long long)blockIdx.x * 16 + 8] = (long long)gt; }
   }
 
   if (warp == 0) {
@@ -532,7 +532,8 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
       for (int sidx = 0; sidx < nseg; ++sidx) {
         if (seg_field(segs, sidx, 5) < 0) continue;
         const int owner = seg_field(segs, sidx, 6), nparts = seg_field(segs, sidx, 7);
-        mbar_wait4(part_ready, np & 1u, 22);
+        // a long wait: sleep in the suspending try_wait instead of polling (the softmax warps share these schedulers)
+        { const long long t0w = clock64(); while (!mbar_try_wait(part_ready, np & 1u)) { if (clock64() - t0w > ORON_WATCHDOG_CYCLES) { g_att4_fault = 22000000 + int(blockIdx.x) * 1000; __trap(); } } }
         ++np;
         if (hid == 0) {
           __threadfence();  // cumulative: the softmax threads' stores (observed through the barrier) before the count
@@ -760,7 +761,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
   __syncthreads();
   if (threadIdx.x == 0) {
     ATT4_STAMP(15);
-    if (DBG) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); args.dbg[(long long)blockIdx.x * 16 + 9] = (long long)gt; }
+    if (args.dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); args.dbg[(long long)blockIdx.x * 16 + 9] = (long long)gt; }
   }
   if ((threadIdx.x >> 5) == 1) {
     tc_fence_after();
@@ -827,7 +828,7 @@ struct Plan4Walk {
 };
 
 __global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg* segs_out, Attn4Merge* merge, int* cnt, const int* seq_lens,
-                                  int nbatch, int rows, int heads, int grid, int seg_stride, int force_flat) {
+                                  int nbatch, int rows, int heads, int grid, int seg_stride, int force_flat, float skew) {
   if (threadIdx.x == 0) {
     hdr->nbatch = nbatch; hdr->rows = rows; hdr->heads = heads; hdr->grid = grid; hdr->seg_stride = seg_stride;
   }
@@ -858,9 +859,25 @@ __global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg*
   };
   // two_phase: pieces of the left-over items' flat list [0, RU)
   const long long W = items / grid, R = items - W * grid, RU = R * nt0, Gp = min((long long)grid, RU);
-  auto pstart_of = [&](long long cta) { return (RU * cta) / Gp; };
+  // Skew: the first CTA placed on an SM runs measurably faster than the second one (17.9 vs 21.5 us at config 2 with equal
+  // work: the older CTA's warps win the issue / MUFU arbitration), and an SM whose CTAs finish apart spends the difference
+  // with one CTA alone. Blocks 0 .. grid/2 - 1 (placed first, one per SM) therefore take pieces that are `skew` * share
+  // tiles longer, the others as much shorter, so that the two CTAs of an SM end together.
+  const double share = double(total) / double(grid);
+  const long long half = Gp / 2;
+  double d_units = (Gp == grid && R > 0) ? double(skew) * share : 0.0;
+  const double mean_piece = Gp > 0 ? double(RU) / double(Gp) : 0.0;
+  if (d_units > mean_piece - 0.5) d_units = mean_piece > 0.5 ? mean_piece - 0.5 : 0.0;  // every piece keeps >= half a tile
+  auto pstart_of = [&](long long cta) {
+    if (cta >= Gp) return RU;
+    const double x = cta <= half ? (mean_piece + d_units) * double(cta)
+                                 : (mean_piece + d_units) * double(half) + (mean_piece - d_units) * double(cta - half);
+    long long v = (long long)(x + 1e-6);
+    return v < 0 ? 0LL : (v > RU ? RU : v);
+  };
   auto pcta_of = [&](long long u) {
     long long cc = (u * Gp) / RU;
+    if (cc >= Gp) cc = Gp - 1;
     while (cc + 1 < Gp && pstart_of(cc + 1) <= u) ++cc;
     while (cc > 0 && pstart_of(cc) > u) --cc;
     return cc;
@@ -928,21 +945,24 @@ __global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg*
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// The split items: CTA c combines the parts of the item whose first key tile CTA c of the attention launch held
-// (parts live in slots 2 (c + p) + (p == 0), p = 0 .. nparts - 1). 8 threads per row (16 bytes of f16 each), 32 rows
-// per pass; four parts per round of loads, all of them in flight at once; online (running-max) combination.
-// Launched right behind the attention kernel (programmatic dependent launch): no atomics, no inter-CTA waiting.
+// The split items: CTAs 4c .. 4c+3 combine 32 rows each of the item whose first key tile CTA c of the attention launch
+// held (parts live in slots 2 (c + p) + (p == 0), p = 0 .. nparts - 1). 8 threads per row (16 bytes of f16 each); eight
+// parts per round of loads, all of them in flight at once (one L2 round trip for the usual 5-7 parts); online
+// (running-max) combination. Launched right behind the attention kernel (programmatic dependent launch): no atomics, no
+// inter-CTA waiting. It sits on the critical path between the attention kernel and the out-projection, so its own
+// latency matters: the first version (one CTA per item, four passes of two rounds) cost ~6 us per call.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn4_combine_kernel(const Attn4Merge* __restrict__ merge, const __half* __restrict__ ws_o, const float* __restrict__ ws_ml,
                      __nv_bfloat16* __restrict__ out, long long ldo, float* __restrict__ lse, int rows_per_batch, int heads) {
   pdl_launch_dependents();
-  const Attn4Merge me = merge[blockIdx.x];  // plan data, written long before the attention launch
+  const Attn4Merge me = merge[blockIdx.x >> 2];  // plan data, written long before the attention launch
   // every CTA waits for the attention kernel, also those with nothing to combine: a grid whose CTAs all left without
   // waiting would count as complete and release the NEXT kernel of the stream before the attention results exist
   pdl_wait();
   if (me.nparts == 0) return;
-  att4_combine_item<256, 1>(threadIdx.x, blockIdx.x, me.nparts, me.b, me.h, me.qt, ws_o, ws_ml, out, ldo, lse, rows_per_batch, heads);
+  const int r0 = int(blockIdx.x & 3) * 32;
+  att4_combine_item<256, 1, 8>(threadIdx.x, int(blockIdx.x >> 2), me.nparts, me.b, me.h, me.qt, ws_o, ws_ml, out, ldo, lse, rows_per_batch, heads, r0, r0 + 32);
 }
 
 }  // namespace oron

@@ -22,9 +22,10 @@ L.lib().oron_debug_set_attention_stamps(dbg.data_ptr())
 fn(); torch.cuda.synchronize()
 L.lib().oron_debug_set_attention_stamps(None)
 d = dbg.cpu()
+LITE = os.environ.get("ORON_ATT_TRACE", "") .startswith("l")
 names = {13: "tiles", 1: "sm:wait s_full", 2: "sm:wait P free", 3: "sm:epilogues", 4: "sm:S load", 5: "sm:max", 6: "sm:exp", 7: "sm:P store", 10: "sm:loop misc", 11: "mma:wait p_full+v_full", 12: "sm:loop span", 14: "softmax end", 15: "cta end"}
 NCTA = 352 if PER_ITEM else 296
-for cta in (0, 1, 50, 100, 150, 200, 250, 295):
+for cta in (() if LITE else (0, 1, 50, 100, 150, 200, 250, 295)):
     base = int(d[cta, 0])
     print(f"  cta {cta}: " + ", ".join(f"{names[i]}={int(d[cta, i]) - (base if i in (14, 15) else 0)}" for i in sorted(names)))
 d = d[:NCTA]
@@ -38,3 +39,13 @@ en = (d[:, 9] - g0).double() / 1e3
 print("kernel span (us): %.1f; cta start %.1f..%.1f end %.1f..%.1f" % (float(en.max() - st.min()), st.min(), st.max(), en.min(), en.max()))
 ghz = ((d[:, 15] - d[:, 0]).double() / (d[:, 9] - d[:, 8]).double())
 print("SM clock during the traced launch (clock64 / globaltimer): mean %.3f GHz min %.3f max %.3f" % (float(ghz.mean()), float(ghz.min()), float(ghz.max())))
+if LITE:
+    import torch
+    dur_us = (en - st)
+    order = torch.argsort(dur_us)
+    print("cta duration (us): min %.1f p25 %.1f median %.1f p75 %.1f max %.1f" % tuple(float(torch.quantile(dur_us, q)) for q in (0, .25, .5, .75, 1)))
+    lo, hi = dur_us[:148], dur_us[148:296]
+    print("mean duration of blocks 0..147: %.1f us, of blocks 148..295: %.1f us; correlation of the two halves (same SM if round-robin): %.2f" % (
+        float(lo.mean()), float(hi.mean()), float(torch.corrcoef(torch.stack([lo, hi]))[0, 1])))
+    print("slowest ctas:", [(int(i), round(float(dur_us[i]), 1)) for i in order[-12:].tolist()])
+    print("fastest ctas:", [(int(i), round(float(dur_us[i]), 1)) for i in order[:12].tolist()])
