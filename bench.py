@@ -445,9 +445,12 @@ def secondary_cfg5(model, dev, rank, world, barrier, steps: int = 3) -> dict:
     ls = [float(x) for x in losses]
     assert all(v == v and v < 1e6 for v in ls), ls
     fwd = B * Tn * (563.4e6 + 90112.0 * Tn)
+    comm = ("no collective" if world == 1 else
+            f"sharded optimizer: NCCL reduce-scatter of {eng.arena.numel * 4 / 1e9:.2f} GB fp32 gradients, AdamW on 1/{world} of the arenas, "
+            f"all-gather of the {eng.arena.numel * 2 / 1e9:.2f} GB bf16 operand copy" if eng.sharded is not None else
+            f"NCCL all-reduce of {eng.arena.numel * 4 / 1e9:.2f} GB fp32 gradients per step, per-block buckets overlapped with backward")
     out = {"workload": f"cfg5: Base DiT OT-CFM training step, per-GPU batch {B} x {Tn} frames, bf16 operands / fp32 master+grads, "
-                       f"data-parallel x{world} (NCCL all-reduce of {eng.arena.numel * 4 / 1e9:.2f} GB fp32 gradients per step, "
-                       "per-block buckets overlapped with backward)",
+                       f"data-parallel x{world} ({comm})",
            "ms_per_step": round(ms, 2), "samples_per_s": round(world * B / (ms / 1e3), 2),
            "frames_per_s": round(world * B * Tn / (ms / 1e3), 1),
            "algorithmic_tflops_per_gpu": round(3 * fwd / (ms * 1e-3) / 1e12, 1), "loss_first_last": [round(ls[0], 4), round(ls[-1], 4)],

@@ -28,6 +28,8 @@ from __future__ import annotations
 import math
 from random import random
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -73,6 +75,8 @@ class ParamArena:
         for k in order:
             self.offsets[k] = off
             off += _rup(named[k].numel(), self.ALIGN)
+        self.numel_used = off
+        off = _rup(off, 8 * 1024)  # every arena splits evenly over 1/2/4/8 ranks with 4 KB-aligned shards (sharded optimizer)
         self.numel = off
         for i in range(depth):  # what is final once block i's backward has run: its own tensors + its AdaLN projection
             first = f"{bb}transformer_blocks.{i}.{per_block[0]}"
@@ -147,6 +151,89 @@ class GradReducer:
             if lo > cur:
                 dist.all_reduce(self.g[cur:lo], op=dist.ReduceOp.SUM)
             cur = max(cur, hi)
+
+
+# Parameters the kernels (or TrainWeights.refresh) read in fp32 straight from the master arena: everything except the big
+# GEMM operands, which are consumed through the bf16 copy only.
+_BF16_ONLY = ("attn_norm.linear.weight", "norm_out.linear.weight", "attn.to_q.weight", "attn.to_k.weight", "attn.to_v.weight",
+              "attn.to_out.0.weight", "ff.ff.0.weight", "ff.ff.3.weight", "pwconv1.weight", "pwconv2.weight",
+              "time_embed.time_mlp.0.weight", "time_embed.time_mlp.2.weight")
+
+
+class ShardedOptimizer:
+    """ZeRO-1 style optimizer step for the data-parallel training step (config 5): every rank owns 1 / world of the flat
+    arenas. Per step: reduce-scatter of the fp32 gradients (half the bytes of the all-reduce it replaces), global gradient
+    norm from the shard sums, clip + AdamW on the own shard only (1 / world of the optimizer's HBM traffic), all-gather of
+    the BF16 operand copy (half the bytes of an fp32 all-gather) and a small fp32 exchange for the parameters the kernels
+    read in fp32 (biases, norms, embeddings, conv-position weights: a few MB). Master weights and Adam moments stay fp32,
+    so the arithmetic is the reference's (trainer.py:191-216); on the ranks that do not own them, the fp32 masters of the
+    bf16-only operands go stale between ``consolidate()`` calls (called by the state-dict / EMA exports)."""
+
+    def __init__(self, arena: ParamArena):
+        import torch.distributed as dist
+
+        self.arena = arena
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.nccl = dist.get_backend() == "nccl"
+        n = arena.numel
+        assert n % self.world == 0
+        self.shard = n // self.world
+        self.lo, self.hi = self.rank * self.shard, (self.rank + 1) * self.shard
+        idx = []
+        for k in arena.order:
+            if not k.endswith(_BF16_ONLY):
+                o = arena.offsets[k]
+                idx.append(torch.arange(o, o + arena.named[k].numel(), device=arena.p.device))
+        self.small_idx = torch.cat(idx)
+        mine = (self.small_idx >= self.lo) & (self.small_idx < self.hi)
+        self.small_mine = mine
+        self.small_idx_mine = self.small_idx[mine]
+        self.small_buf = torch.zeros(self.small_idx.numel(), device=arena.p.device, dtype=F32)
+        self.stale = False
+
+    def _reduce_scatter(self, t: torch.Tensor) -> None:
+        """Sum over the ranks, result only in this rank's shard of `t` (in place)."""
+        import torch.distributed as dist
+
+        if self.nccl:
+            dist.reduce_scatter_tensor(t[self.lo:self.hi], t, op=dist.ReduceOp.SUM)
+        else:  # gloo (CPU tests): no reduce-scatter on tensors
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def _all_gather(self, t: torch.Tensor) -> None:
+        """Every rank's shard of `t` to everybody (in place)."""
+        import torch.distributed as dist
+
+        if self.nccl:
+            dist.all_gather_into_tensor(t, t[self.lo:self.hi])
+        else:
+            parts = [torch.empty_like(t[: self.shard]) for _ in range(self.world)]
+            dist.all_gather(parts, t[self.lo:self.hi].contiguous())
+            for r, prt in enumerate(parts):
+                t[r * self.shard:(r + 1) * self.shard].copy_(prt)
+
+    def reduce_gradients(self) -> None:
+        self._reduce_scatter(self.arena.g)
+
+    def exchange_after_step(self) -> None:
+        """bf16 operands of every rank's shard to everybody + the fp32 values of the small parameters."""
+        import torch.distributed as dist
+
+        a = self.arena
+        self._all_gather(a.pb)
+        self.small_buf.zero_()
+        self.small_buf[self.small_mine] = a.p[self.small_idx_mine]
+        dist.all_reduce(self.small_buf, op=dist.ReduceOp.SUM)  # exactly one rank contributes a non-zero value per entry
+        a.p[self.small_idx] = self.small_buf
+        self.stale = True
+
+    def consolidate(self) -> None:
+        """All ranks get the complete fp32 masters and Adam moments (before a state-dict export)."""
+        if self.stale:
+            a = self.arena
+            for t in (a.p, a.m, a.v):
+                self._all_gather(t)
+            self.stale = False
 
 
 class TrainWeights(DiTWeights):
@@ -310,6 +397,11 @@ class TrainEngine:
         self.sumsq = torch.zeros(1, device=p0.device, dtype=F32)
         self.skipped = torch.zeros(1, device=p0.device, dtype=I32)
         self.reducer = GradReducer(self.arena.g, self.arena.block_ranges)
+        # data-parallel runs: sharded optimizer (ZeRO-1) unless ORON_ZERO1=0 (then: all-reduce + replicated AdamW)
+        self.sharded = None
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and os.environ.get("ORON_ZERO1", "1") != "0":
+            self.sharded = ShardedOptimizer(self.arena)
         drops = [m.p for m in self.cfm.backbone.modules() if isinstance(m, torch.nn.Dropout)]
         self.dropout_p = float(drops[0]) if drops else 0.0  # Attention.to_out[1] / FeedForward.ff[2] share p_dropout
 
@@ -623,8 +715,8 @@ class TrainEngine:
 
     # ---- data-parallel gradient mean + optimizer ---------------------------------------------------------------
     def _block_done(self, i: int) -> None:
-        if getattr(self, "_reduce_in_backward", True):
-            self.reducer.block_done(i)
+        if getattr(self, "_reduce_in_backward", True) and getattr(self, "sharded", None) is None:
+            self.reducer.block_done(i)  # sharded optimizer: one reduce-scatter of the whole arena in optimizer_step instead
 
     # token ids outside [-1, vocab) (nn.Embedding raises IndexError for them, encoder.py:68-75): the range test runs on the
     # device at the start of the pass, the kernels see clamped ids, and the verdict is read once the whole pass has been
@@ -656,16 +748,26 @@ class TrainEngine:
         import torch.distributed as dist
 
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        self.reduce_gradients()
         a = self.arena
         self.step_count += 1
         self._step_pending_skip_check = True
         self.sumsq.zero_()
         self.skipped.zero_()
-        T.sumsq(a.g, self.sumsq)
-        T.adamw_clip(a.p, a.g, a.m, a.v, a.pb, self.sumsq, grad_scale=1.0 / (world * max(int(accum_steps), 1)), max_norm=self.max_norm,
-                     lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, wd=self.wd,
-                     step=self.step_count, skipped=self.skipped)
+        kw = dict(grad_scale=1.0 / (world * max(int(accum_steps), 1)), max_norm=self.max_norm,
+                  lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, wd=self.wd,
+                  step=self.step_count, skipped=self.skipped)
+        if self.sharded is not None:
+            so = self.sharded
+            so.reduce_gradients()                       # this rank's shard of g now holds the sum over the ranks
+            lo, hi = so.lo, so.hi
+            T.sumsq(a.g[lo:hi], self.sumsq)
+            dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM)  # global norm: every rank clips (or skips) alike
+            T.adamw_clip(a.p[lo:hi], a.g[lo:hi], a.m[lo:hi], a.v[lo:hi], a.pb[lo:hi], self.sumsq, **kw)
+            so.exchange_after_step()
+        else:
+            self.reduce_gradients()
+            T.sumsq(a.g, self.sumsq)
+            T.adamw_clip(a.p, a.g, a.m, a.v, a.pb, self.sumsq, **kw)
         self.w.refresh()
         self._seen_version = self._versions()
 
@@ -696,6 +798,7 @@ class TrainEngine:
     def optimizer_state_dict(self) -> dict:
         """The Adam moments in ``torch.optim.AdamW.state_dict()`` format (parameter order = ``model.parameters()``), so
         that ``CheckpointManager.save`` / a later ``torch.optim.AdamW.load_state_dict`` work unchanged."""
+        self.consolidate()
         a = self.arena
         state, order = {}, []
         for idx, (name, prm) in enumerate(self.model.named_parameters()):
@@ -721,6 +824,12 @@ class TrainEngine:
         self.lr, self.betas, self.eps, self.wd = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
 
     @torch.no_grad()
+    def consolidate(self) -> None:
+        """Sharded optimizer: complete fp32 master weights / Adam moments on every rank (a collective: call it on all ranks
+        before ``state_dict()`` / ``optimizer_state_dict()`` / an EMA update). No-op otherwise."""
+        if getattr(self, "sharded", None) is not None:
+            self.sharded.consolidate()
+
     def enable_ema(self, decay: float = 0.9999) -> None:
         """Exponential moving average of the parameters with torch_ema's update rule (trainer.py:98-102)."""
         self.ema, self.ema_decay, self.ema_updates = self.arena.p.clone(), decay, 0
@@ -729,6 +838,7 @@ class TrainEngine:
     def ema_update(self) -> None:
         self.ema_updates += 1
         d = min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
+        self.consolidate()
         self.ema.lerp_(self.arena.p, 1.0 - d)  # shadow -= (1 - d) * (shadow - param), one pass over the flat arena
 
     def ema_state_dict(self) -> dict:

@@ -144,6 +144,31 @@ def _reducer_worker(rank, world, port, q):
         TrainEngine._block_done(eng, i)
     eng.reducer.drain()
     ok = ok and torch.equal(arena.g, g1) and not eng.reducer._pending
+    # sharded optimizer (ZeRO-1): reduce-scatter + update of the own shard + bf16 all-gather + small fp32 exchange must leave
+    # every rank with the state a replicated optimizer produces (a plain SGD step stands in for the CUDA AdamW kernel)
+    from oron_tts_b200.train import _BF16_ONLY, ShardedOptimizer
+
+    so = ShardedOptimizer(arena)
+    ok = ok and arena.numel % (8 * 1024) == 0 and so.shard * world == arena.numel
+    p0 = torch.linspace(-1, 1, arena.numel)
+    arena.p.copy_(p0)
+    arena.pb.copy_(arena.p)
+    arena.g.copy_(base * 1e-7 * (rank + 1))
+    so.reduce_gradients()
+    gsum = base * 1e-7 * sum(r + 1 for r in range(world))
+    ok = ok and torch.equal(arena.g[so.lo:so.hi], gsum[so.lo:so.hi])
+    arena.p[so.lo:so.hi] -= 0.5 * arena.g[so.lo:so.hi]
+    arena.pb[so.lo:so.hi] = arena.p[so.lo:so.hi].to(arena.pb.dtype)
+    so.exchange_after_step()
+    want = p0 - 0.5 * gsum
+    ok = ok and torch.equal(arena.pb, want.to(arena.pb.dtype))                 # every GEMM operand, every rank
+    for k in arena.order:                                                      # fp32 values of what the kernels read in fp32
+        o, n = arena.offsets[k], arena.named[k].numel()
+        same = torch.equal(arena.p[o:o + n], want[o:o + n])
+        if not k.endswith(_BF16_ONLY):
+            ok = ok and same
+    so.consolidate()
+    ok = ok and torch.equal(arena.p[: arena.numel_used], want[: arena.numel_used])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
