@@ -135,11 +135,13 @@ int oron_mask_rows_f32(float* x, int64_t ldx, int64_t rows, int32_t C, const uin
 int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, void* out, int64_t ld_out,
                      oron_stream_t stream);
 
-/* oron_attention_bf16 for the training forward: one CTA per (batch, head, query tile) and lse[(b*heads + h)*rows_per_batch
- * + t] = log2(sum_k exp2(s_tk * scale * log2 e)) of every query row, which oron_attention_bwd takes with have_lse = 1. */
+/* oron_attention_bf16 for the training forward: also writes lse[(b*heads + h)*rows_per_batch + t] =
+ * log2(sum_k exp2(s_tk * scale * log2 e)) of every query row, which oron_attention_bwd takes with have_lse = 1.
+ * workspace (optional, as for oron_attention_bf16: oron_attention_workspace_bytes / oron_attention_plan): the planned
+ * schedule (equal shares of the key-tile list per CTA); NULL: one CTA per (batch, head, query tile). */
 int oron_attention_fwd_lse(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                            int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale, float* lse,
-                           oron_stream_t stream);
+                           void* workspace, int64_t workspace_bytes, oron_stream_t stream);
 
 /*
  * Backward of oron_attention_bf16 (F.scaled_dot_product_attention + key-padding mask, modules.py:271-278) with

@@ -42,7 +42,7 @@ _ARGTYPES = {
     "oron_mask_rows_f32": [_P, _L, _L, _I, _P, _P],
     "oron_colsum_bf16": [_P, _L, _L, _I, _P, _P],
     "oron_attention_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _P, _P, _I, _P],
-    "oron_attention_fwd_lse": [_P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P],
+    "oron_attention_fwd_lse": [_P, _L, _P, _L, _I, _I, _I, _P, _F, _P, _P, _L, _P],
 }
 _bound = False
 
@@ -224,7 +224,9 @@ def attention_bwd(qk: torch.Tensor, v: torch.Tensor, o: torch.Tensor, d_o: torch
 
 
 def attention_fwd_lse(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, *, nbatch: int, rows_per_batch: int, heads: int,
-                      seq_lens: torch.Tensor | None, scale: float) -> None:
+                      seq_lens: torch.Tensor | None, scale: float, workspace: torch.Tensor | None = None) -> None:
+    """`workspace`: a planned attention workspace (_lib.attention_workspace / attention_plan for these seq_lens), or None."""
     _check(tlib().oron_attention_fwd_lse(_ptr(qkv, BF16, "qkv"), _ld(qkv), _ptr(out, BF16, "out"), _ld(out), nbatch,
                                          rows_per_batch, heads, _ptr(seq_lens, torch.int32, "seq_lens"), float(scale),
-                                         _ptr(lse, F32, "lse"), _stream()), "oron_attention_fwd_lse")
+                                         _ptr(lse, F32, "lse"), _ptr(workspace, torch.uint8, "workspace"),
+                                         0 if workspace is None else workspace.numel(), _stream()), "oron_attention_fwd_lse")

@@ -553,9 +553,12 @@ extern "C" int oron_attention_bf16(const void* qkv, int64_t ld_qkv, void* out, i
 // Training forward (include/oron_b200_train.h): one CTA per item, and the log-sum-exp of every row is kept.
 extern "C" int oron_attention_fwd_lse(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int32_t nbatch,
                                       int32_t rows_per_batch, int32_t heads, const int32_t* seq_lens, float scale, float* lse,
-                                      oron_stream_t stream) {
+                                      void* workspace, int64_t workspace_bytes, oron_stream_t stream) {
   if (!lse) return fail(ORON_ERR_BAD_ARG, "attention_fwd_lse: lse is NULL");
-  return attention_impl(qkv, ld_qkv, out, ldo, nbatch, rows_per_batch, heads, seq_lens, scale, nullptr, 0, lse, stream);
+  // the round-1 kernel writes lse for whole items only: planned launches need the current one
+  const bool ws_ok = attn_version() == 4;
+  return attention_impl(qkv, ld_qkv, out, ldo, nbatch, rows_per_batch, heads, seq_lens, scale, ws_ok ? workspace : nullptr,
+                        ws_ok ? workspace_bytes : 0, lse, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -331,6 +331,7 @@ class TrainWorkspace:
         self.nb, self.tpad, self.R = nb, tpad, R
         self.ids, self.drop, self.row_valid = z(R, dt=I32), z(nb, dt=torch.uint8), z(R, dt=torch.uint8)
         self.seq_lens, self.text_lens = z(nb, dt=I32), z(nb, dt=I32)
+        self.attn_ws = torch.zeros(int(L.lib().oron_attention_workspace_bytes(nb, tpad, w.heads)), dtype=torch.uint8, device=dev)
         nl = w.conv_layers
         self.xt = [z(R, C) for _ in range(nl + 1)]
         self.conv = [z(R, C) for _ in range(nl)]
@@ -532,6 +533,8 @@ class TrainEngine:
         ws.drop.fill_(1 if drop_text else 0)
         self._check_ids_begin(ids)
         ws.seq_lens.copy_(lens)
+        # the attention kernel's work plan for these lengths (equal shares of the key-tile list per CTA), once per pass
+        L.attention_plan(ws.attn_ws, nbatch=nb, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens)
         ws.text_lens.fill_(Tn)  # TextEmbedding runs over the whole padded batch (encoder.py:68-96), fillers included
         common = dict(rows_per_batch=tpad, nbatch=nb)
         # -- text embedding
@@ -588,7 +591,8 @@ class TrainEngine:
             L.gemm(ws.nrm1[i], blk["wqkv"], ws.qkv[i], epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
                    rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
             T.attention_fwd_lse(ws.qkv[i], ws.ao[i], ws.lse[i], nbatch=nb, rows_per_batch=tpad, heads=w.heads,
-                                seq_lens=ws.seq_lens, scale=1.0 / math.sqrt(w.dim_head))
+                                seq_lens=ws.seq_lens, scale=1.0 / math.sqrt(w.dim_head),
+                                workspace=ws.attn_ws if os.environ.get("ORON_TRAIN_ATT_PLAN", "1") != "0" else None)
             # out-projection with the gated residual in the epilogue: xmid = xin + gate_msa * dropout(mask(y1)), y1 kept
             L.gemm(ws.ao[i], blk["wo"], ws.xmid[i], epilogue=L.EPI_GATE_RESID_DUAL, bias=blk["bo"], out2=ws.y1[i], addend=ws.xin[i],
                    gate=tab[o + 2 * D:], gate_ld=an, gate_nb=nb, seq_lens=ws.seq_lens, mask_rows=True, block_n=bn_big, two_sm=True,
