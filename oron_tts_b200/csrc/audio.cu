@@ -205,14 +205,20 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
 // ---------------------------------------------------------------------------
 // iSTFT head: spectrum from the head activations -> irfft -> window -> overlap-add -> envelope
 // ---------------------------------------------------------------------------
-constexpr int IST_HOPS = AUD_FR - 3;     // output hops finished per CTA pass (3-frame halo recomputed)
-constexpr int IST_SMEM = AUD_WARPS * XB_BYTES + NFFT * 8 + NFFT * 4;
+// Every warp owns a RUN of consecutive output hops of one clip and walks it two frames at a time: stage the two
+// activation rows in its tile (async copies; the next pair's rows are already on their way into L2), build the packed
+// spectrum, one 1024-point transform, window, and overlap-add against a lane-private carry of the three unfinished hops
+// (sample n = lane + 32 k2 always belongs to the same lane, so the carry needs no synchronisation at all). No block
+// barrier after the table setup, no frame is transformed twice except the four halo frames at the head of a run.
+constexpr int IST_CARRY = 3 * HOP;       // floats per warp: the partial sums of the next three hops
+constexpr int IST_SMEM = AUD_WARPS * (XB_BYTES + IST_CARRY * 4) + NFFT * 8 + NFFT * 4 + HOP * 4;
+constexpr int IST_MIN_RUN = 8;
 
 // exp / cos / sin of the head activations (Vocos ISTFTHead): fast-math units after an explicit
 // two-constant range reduction, absolute error ~1e-6 for |phase| < 1e3.
 __device__ __forceinline__ float2 polar_clip(float logmag, float phase) {
   const float mg = fminf(__expf(logmag), 100.0f);
-  const float q = rintf(phase * 0.15915494309189535f);
+  const float q = (fmaf(phase, 0.15915494309189535f, 12582912.0f)) - 12582912.0f;  // round to nearest (|phase| < 2^22)
   float r = fmaf(q, -6.2831854820251465f, phase);   // hi part of 2 pi (fp32)
   r = fmaf(q, 1.7484555e-7f, r);                    // 2 pi - hi
   float s, c;
@@ -220,140 +226,169 @@ __device__ __forceinline__ float2 polar_clip(float logmag, float phase) {
   return make_float2(mg * c, mg * s);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __global__ void __launch_bounds__(AUD_THREADS, 2)
 istft_head_kernel(const float* __restrict__ h, long long ldh, int rows_per_batch, int nb, int n_frames,
-                  const float* __restrict__ window, int mode, float* __restrict__ out, long long ld_out) {
+                  const float* __restrict__ window, int mode, float* __restrict__ out, long long ld_out, int run,
+                  int runs_per_clip) {
   extern __shared__ __align__(16) uint8_t dsm[];
   float2* xb_all = reinterpret_cast<float2*>(dsm);
-  float2* tw = xb_all + AUD_WARPS * fw::XB_ELEMS;
-  float* win = reinterpret_cast<float*>(tw + NFFT);
+  float* carry_all = reinterpret_cast<float*>(xb_all + AUD_WARPS * fw::XB_ELEMS);
+  float2* tw = reinterpret_cast<float2*>(carry_all + AUD_WARPS * IST_CARRY);
+  float* wins = reinterpret_cast<float*>(tw + NFFT);  // window * transform scale
+  float* ienv = wins + NFFT;                          // 1 / sum_q window[i + 256 q]^2: the envelope of an interior hop
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* xb = xb_all + warp * fw::XB_ELEMS;
-  float* frames = reinterpret_cast<float*>(xb_all);  // after the FFT: tile w holds frames 2w (floats [0,1024)) and 2w+1
-  constexpr int TILE_F = fw::XB_ELEMS * 2;           // floats per warp tile
-  constexpr int RAW_LD = TILE_F / 2;                 // second raw activation row inside the tile
+  float* cw = carry_all + warp * IST_CARRY + lane;    // carry[hop 0..2][j 0..7][lane]
+  constexpr int RAW_LD = fw::XB_ELEMS;                // second raw activation row inside the tile (floats)
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(h) & 15) == 0) && ((ldh & 3) == 0);
-  const bool out_vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((ld_out & 3) == 0);
-
-  fw::fill_twiddle_table(tw);
-  for (int n = threadIdx.x; n < NFFT; n += blockDim.x) win[n] = window[n];
-  __syncthreads();
 
   const float scale = (mode == 1) ? (32.0f / NFFT) : (1.0f / NFFT);  // normalized=True: * sqrt(N)
-  const long long out_len = (long long)HOP * (n_frames - 1);
-  const int chunks_per_clip = (n_frames + 3 + IST_HOPS - 1) / IST_HOPS;
-  for (int chunk = blockIdx.x; chunk < nb * chunks_per_clip; chunk += gridDim.x) {
-    const int b = chunk / chunks_per_clip;
-    const int hop0 = (chunk - b * chunks_per_clip) * IST_HOPS;  // first padded-domain hop finished by this pass
-    const int hop1 = min(hop0 + IST_HOPS, n_frames + 3);
-    const int fr_lo = max(hop0 - 3, 0);
-    const int fr_hi = min(hop1 - 1, n_frames - 1);  // inclusive
-    const int f = fr_lo + 2 * warp;
-    if (f <= fr_hi) {  // warp-uniform
-      const bool hasB = f + 1 <= fr_hi;
-      const float* ha = h + ((long long)b * rows_per_batch + f) * ldh;
-      const float* hb = hasB ? ha + ldh : ha;
-      // stage the two activation rows (1026 floats each) in this warp's tile with one batch of async copies:
-      // every byte of the pass is in flight at once instead of trickling through the register file
-      float* rawA = reinterpret_cast<float*>(xb);
-      float* rawB = rawA + RAW_LD;
-      if (vec_ok) {
+  fw::fill_twiddle_table(tw);
+  for (int n = threadIdx.x; n < NFFT; n += blockDim.x) wins[n] = window[n] * scale;
+  for (int i = threadIdx.x; i < HOP; i += blockDim.x) {
+    float e = 0.f;
 #pragma unroll
-        for (int c = lane; c < 256; c += 32) {
-          cp_async16(rawA + 4 * c, ha + 4 * c);
-          cp_async16(rawB + 4 * c, hb + 4 * c);
+    for (int q = 0; q < 4; ++q) e = fmaf(window[i + HOP * q], window[i + HOP * q], e);
+    ienv[i] = 1.0f / e;
+  }
+  __syncthreads();
+
+  const int gw = blockIdx.x * AUD_WARPS + warp, nw = gridDim.x * AUD_WARPS;
+  for (int item = gw; item < nb * runs_per_clip; item += nw) {
+    const int b = item / runs_per_clip;
+    // padded-domain hop hh receives frames hh-3..hh and holds output samples [256 hh - 512, +256): hops 2..n_frames
+    const int h0 = 2 + (item - b * runs_per_clip) * run;
+    const int h1 = min(h0 + run, n_frames + 1);
+    if (h0 >= h1) continue;
+    const float* hb = h + (long long)b * rows_per_batch * ldh;
+    float* ob = out + (long long)b * ld_out - NFFT / 2 + lane;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) cw[32 * j] = 0.f;
+
+    for (int A = h0 - 4; A < h1; A += 2) {  // frames A (real part) and A + 1 (imaginary part); A is even
+      const bool hasA = A >= 0 && A < n_frames, hasB = A >= 0 && A + 1 < n_frames;
+      fw::c64 v[32];
+      if (hasA) {  // warp-uniform
+        const float* ha = hb + (long long)A * ldh;
+        const float* hbp = hasB ? ha + ldh : ha;
+        float* rawA = reinterpret_cast<float*>(xb);
+        float* rawB = rawA + RAW_LD;
+        if (vec_ok) {
+#pragma unroll
+          for (int c = lane; c < 256; c += 32) {
+            cp_async16(rawA + 4 * c, ha + 4 * c);
+            cp_async16(rawB + 4 * c, hbp + 4 * c);
+          }
+          if (lane < 2) {
+            cp_async4(rawA + 1024 + lane, ha + 1024 + lane);
+            cp_async4(rawB + 1024 + lane, hbp + 1024 + lane);
+          }
+        } else {
+          for (int c = lane; c < 2 * NBIN; c += 32) {
+            cp_async4(rawA + c, ha + c);
+            cp_async4(rawB + c, hbp + c);
+          }
         }
-        if (lane < 2) {
-          cp_async4(rawA + 1024 + lane, ha + 1024 + lane);
-          cp_async4(rawB + 1024 + lane, hb + 1024 + lane);
+        if (A + 2 < h1 && A + 2 < n_frames) {  // the next pair's rows: pull them into L2 while this pair is transformed
+          const char* nx = reinterpret_cast<const char*>(ha + 2 * ldh);
+          prefetch_l2(nx + 128 * lane);
+          if (lane == 0) prefetch_l2(nx + 4096);
+          if (A + 3 < n_frames) {
+            const char* ny = reinterpret_cast<const char*>(ha + 3 * ldh);
+            prefetch_l2(ny + 128 * lane);
+            if (lane == 0) prefetch_l2(ny + 4096);
+          }
         }
+        cp_async_wait_all();
+        __syncwarp();
+        // lower half of Z = A + iB in registers (bin k = lane + 32 n1), mirrored half Z[N-k] = conj(A) + i conj(B)
+        float2 zc[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+          const int k = lane + 32 * n1;
+          float2 P, Q;
+          if (mode == 0) {
+            P = polar_clip(rawA[k], rawA[NBIN + k]);
+            Q = polar_clip(rawB[k], rawB[NBIN + k]);
+          } else {
+            P = *reinterpret_cast<const float2*>(rawA + 2 * k);
+            Q = *reinterpret_cast<const float2*>(rawB + 2 * k);
+          }
+          if (!hasB) Q = make_float2(0.f, 0.f);
+          if (k == 0) { P.y = 0.f; Q.y = 0.f; }  // C2R ignores the imaginary part of DC
+          v[n1] = fw::cpack(P.x - Q.y, P.y + Q.x);
+          zc[n1] = make_float2(P.x + Q.y, Q.x - P.y);
+        }
+        // Nyquist bin (k = 512): real parts only, lives in lane 0 register 16
+        float2 nyq = make_float2(0.f, 0.f);
+        if (lane == 0) {
+          if (mode == 0) {
+            nyq.x = polar_clip(rawA[512], rawA[NBIN + 512]).x;
+            nyq.y = hasB ? polar_clip(rawB[512], rawB[NBIN + 512]).x : 0.f;
+          } else {
+            nyq.x = rawA[1024];
+            nyq.y = hasB ? rawB[1024] : 0.f;
+          }
+        }
+        __syncwarp();  // the raw rows are consumed: the tile now belongs to the FFT
+        // upper half: register r in [16,32) of lane L is Z[32 r + L] = mirrored value of bin 1024 - 32 r - L, which
+        // lane (32 - L) & 31 computed as zc[31 - r] (L = 0: own zc[32 - r]; r = 16: the Nyquist bin)
+        const int src = (32 - lane) & 31;
+#pragma unroll
+        for (int r = 16; r < 32; ++r) {
+          float2 g;
+          g.x = __shfl_sync(0xffffffffu, zc[31 - r].x, src);
+          g.y = __shfl_sync(0xffffffffu, zc[31 - r].y, src);
+          if (lane == 0) g = (r == 16) ? nyq : zc[(32 - r) & 15];
+          v[r] = fw::cpack(g.x, g.y);
+        }
+        fw::fft1024_warp<true>(v, xb, tw, lane);  // real = frame A, imag = frame B, time index n = lane + 32 k2
       } else {
-        for (int c = lane; c < 2 * NBIN; c += 32) {
-          cp_async4(rawA + c, ha + c);
-          cp_async4(rawB + c, hb + c);
-        }
-      }
-      cp_async_wait_all();
-      __syncwarp();
-      // lower half of Z = A + iB in registers (bin k = lane + 32 n1), mirrored half Z[N-k] = conj(A) + i conj(B)
-      float2 v[32], zc[16];
 #pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) {
-        const int k = lane + 32 * n1;
-        float2 A, B;
-        if (mode == 0) {
-          A = polar_clip(rawA[k], rawA[NBIN + k]);
-          B = polar_clip(rawB[k], rawB[NBIN + k]);
-        } else {
-          A = *reinterpret_cast<const float2*>(rawA + 2 * k);
-          B = *reinterpret_cast<const float2*>(rawB + 2 * k);
-        }
-        if (!hasB) B = make_float2(0.f, 0.f);
-        if (k == 0) { A.y = 0.f; B.y = 0.f; }  // C2R ignores the imaginary part of DC
-        v[n1] = make_float2(A.x - B.y, A.y + B.x);
-        zc[n1] = make_float2(A.x + B.y, B.x - A.y);
+        for (int r = 0; r < 32; ++r) v[r] = 0ull;
       }
-      // Nyquist bin (k = 512): real parts only, lives in lane 0 register 16
-      float2 nyq = make_float2(0.f, 0.f);
-      if (lane == 0) {
-        if (mode == 0) {
-          nyq.x = polar_clip(rawA[512], rawA[NBIN + 512]).x;
-          nyq.y = hasB ? polar_clip(rawB[512], rawB[NBIN + 512]).x : 0.f;
-        } else {
-          nyq.x = rawA[1024];
-          nyq.y = hasB ? rawB[1024] : 0.f;
-        }
-      }
-      __syncwarp();  // the raw rows are consumed: the tile now belongs to the FFT
-      // upper half: register r in [16,32) of lane L is Z[32 r + L] = mirrored value of bin 1024 - 32 r - L, which
-      // lane (32 - L) & 31 computed as zc[31 - r] (L = 0: own zc[32 - r]; r = 16: the Nyquist bin)
-      const int src = (32 - lane) & 31;
+      // window, overlap-add: hop A = carry0 + A[0:256); hop A+1 = carry1 + A[256:512) + B[0:256); the rest is carried
+      float o0[8], o1[8];
 #pragma unroll
-      for (int r = 16; r < 32; ++r) {
-        float2 g;
-        g.x = __shfl_sync(0xffffffffu, zc[31 - r].x, src);
-        g.y = __shfl_sync(0xffffffffu, zc[31 - r].y, src);
-        if (lane == 0) g = (r == 16) ? nyq : zc[(32 - r) & 15];
-        v[r] = g;
+      for (int j = 0; j < 8; ++j) {
+        const int n = lane + 32 * j;
+        const float w0 = wins[n], w1 = wins[HOP + n], w2 = wins[2 * HOP + n], w3 = wins[3 * HOP + n];
+        const float2 p0 = fw::cunpack(fw::cmul2(v[j], fw::cpack(w0, w0)));
+        const float2 p1 = fw::cunpack(fw::cmul2(v[8 + j], fw::cpack(w1, w1)));
+        const float2 p2 = fw::cunpack(fw::cmul2(v[16 + j], fw::cpack(w2, w2)));
+        const float2 p3 = fw::cunpack(fw::cmul2(v[24 + j], fw::cpack(w3, w3)));
+        const float c0 = cw[32 * j], c1 = cw[32 * (8 + j)], c2 = cw[32 * (16 + j)];
+        o0[j] = c0 + p0.x;
+        o1[j] = c1 + p1.x + p0.y;
+        cw[32 * j] = c2 + p2.x + p1.y;
+        cw[32 * (8 + j)] = p3.x + p2.y;
+        cw[32 * (16 + j)] = p3.y;
       }
-      fw::fft1024_warp<true>(v, xb, tw, lane);  // real = frame A, imag = frame B, time index n = lane + 32 k2
-      float* fa = reinterpret_cast<float*>(xb);
 #pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) {
-        const float w = win[lane + 32 * k2] * scale;
-        fa[lane + 32 * k2] = v[k2].x * w;
-        fa[NFFT + lane + 32 * k2] = v[k2].y * w;
+      for (int e = 0; e < 2; ++e) {
+        const int hh = A + e;
+        if (hh < h0 || hh >= h1) continue;  // halo pair, or the odd tail of the run
+        float* dst = ob + (long long)hh * HOP;
+        if (hh >= 3 && hh <= n_frames - 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[32 * j] = (e == 0 ? o0[j] : o1[j]) * ienv[lane + 32 * j];
+        } else {  // first / last hop of the clip: fewer than four frames overlap
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float env = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int t = hh - 3 + q;
+              const float w = window[lane + 32 * j + HOP * (3 - q)];
+              if (t >= 0 && t < n_frames) env = fmaf(w, w, env);
+            }
+            dst[32 * j] = (e == 0 ? o0[j] : o1[j]) / env;
+          }
+        }
       }
     }
-    __syncthreads();
-    // overlap-add in ascending frame order, envelope-normalise and write; o = n - 512 in [0, 256*(n_frames-1)).
-    // Four consecutive samples per thread: hop h = hop0 + hrel receives samples [r + 256 (3 - q), +4) of frame h - 3 + q.
-    for (int i4 = threadIdx.x; i4 < (hop1 - hop0) * (HOP / 4); i4 += blockDim.x) {
-      const int hop = hop0 + (i4 >> 6);
-      const int r = (i4 & 63) * 4;
-      const long long o = (long long)hop * HOP + r - NFFT / 2;
-      if (o < 0 || o >= out_len) continue;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), env = acc;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int t = hop - 3 + q;
-        if (t >= fr_lo && t <= fr_hi) {
-          const int slot = t - fr_lo, j = r + HOP * (3 - q);
-          const float4 fv = *reinterpret_cast<const float4*>(&frames[(slot >> 1) * TILE_F + (slot & 1) * NFFT + j]);
-          const float4 w = *reinterpret_cast<const float4*>(&win[j]);
-          acc.x += fv.x; acc.y += fv.y; acc.z += fv.z; acc.w += fv.w;
-          env.x += w.x * w.x; env.y += w.y * w.y; env.z += w.z * w.z; env.w += w.w * w.w;
-        }
-      }
-      float* dst = out + (long long)b * ld_out + o;
-      const float4 res = make_float4(acc.x / env.x, acc.y / env.y, acc.z / env.z, acc.w / env.w);
-      if (out_vec_ok) {
-        *reinterpret_cast<float4*>(dst) = res;
-      } else {
-        dst[0] = res.x; dst[1] = res.y; dst[2] = res.z; dst[3] = res.w;
-      }
-    }
-    __syncthreads();  // warp tiles are reused by the next chunk
   }
 }
 
@@ -421,9 +456,19 @@ extern "C" int oron_istft_head(const float* h, int64_t ldh, int32_t rows_per_bat
   if (!h || !window || !out) return fail(ORON_ERR_BAD_ARG, "istft_head: null pointer");
   if (n_frames < 2 || n_frames > rows_per_batch || nb <= 0) return fail(ORON_ERR_BAD_ARG, "istft_head: bad frame count");
   if (ldh < 2 * NBIN) return fail(ORON_ERR_BAD_ARG, "istft_head: ldh must be >= 1026");
-  const long long chunks = (long long)((n_frames + 3 + IST_HOPS - 1) / IST_HOPS) * nb;
+  // runs of output hops, one warp each: as long as possible (four halo frames per run) while every warp of the
+  // persistent grid (two 8-warp CTAs per SM) still gets the same number of runs
+  const long long hops = n_frames - 1;
+  const long long slots = 2LL * num_sms() * AUD_WARPS;
+  long long rpc = slots / nb;
+  if (rpc < 1) rpc = 1;
+  long long run = (hops + rpc - 1) / rpc;
+  if (run < IST_MIN_RUN) run = IST_MIN_RUN;
+  run = (run + 1) & ~1LL;
+  rpc = (hops + run - 1) / run;
+  const long long ctas = (rpc * nb + AUD_WARPS - 1) / AUD_WARPS;
   const long long cap = 2LL * num_sms();
-  dim3 grid((unsigned)(chunks < cap ? chunks : cap));
+  dim3 grid((unsigned)(ctas < cap ? ctas : cap));
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(istft_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IST_SMEM);
@@ -431,7 +476,7 @@ extern "C" int oron_istft_head(const float* h, int64_t ldh, int32_t rows_per_bat
     configured = true;
   }
   istft_head_kernel<<<grid, AUD_THREADS, IST_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-      h, ldh, rows_per_batch, nb, n_frames, window, mode, out, ld_out);
+      h, ldh, rows_per_batch, nb, n_frames, window, mode, out, ld_out, int(run), int(rpc));
   return check_launch("istft_head");
 }
 

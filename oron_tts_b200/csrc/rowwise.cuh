@@ -287,26 +287,59 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const DwLnArgs a) {
 // channels in registers, so every input row is read from HBM once (+6 halo rows per run) and nothing is
 // re-fetched through L1. Rows arrive through a shared-memory ring filled by 16-byte cp.async copies issued
 // DW_AHEAD rows ahead (each thread copies exactly the 16 bytes it later reads, so the ring needs no barrier):
-// ~24 KB in flight per CTA is what covers HBM latency at four CTAs per SM. Two frames per iteration; the
-// LayerNorm statistics cross the C/128 warps through shared memory (mean, then centred variance: the same
-// two-pass arithmetic as the warp-per-row kernel).
+// ~24 KB in flight per CTA is what covers HBM latency at four or five CTAs per SM.
+//
+// The kernel is bound by instruction issue, not by HBM (ncu: issue 71 % at 44 % of HBM before this version), so the
+// arithmetic is packed: channel pairs live in 64-bit registers and the taps, the statistics and the affine are
+// FFMA2 / FMUL2 / FADD2; the 8-row window is a circular buffer addressed statically (the frame loop is unrolled over
+// one full rotation: no register moves); the four LayerNorm sums of a frame pair (sum and sum of squares of both
+// frames) are reduced together by one 6-shuffle butterfly and cross the C/128 warps through ONE barrier per pair
+// (double-buffered slots). Variance is E[y^2] - mean^2 in fp32, clamped at 0 (the two-pass form costs a second
+// butterfly and barrier; the difference is below the bf16 rounding of the output: tests/test_kernels_gpu.py).
 constexpr int DW_AHEAD = 12;            // rows in flight per CTA (even)
 constexpr int DW_RING = DW_AHEAD + 2;   // + the pair consumed in the previous iteration (write-after-read safety)
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+typedef unsigned long long dw_f2;  // two packed floats
+__device__ __forceinline__ dw_f2 dw_pack(float lo, float hi) {
+  dw_f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 dw_unpack(dw_f2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ dw_f2 dw_fma(dw_f2 a, dw_f2 b, dw_f2 c) {
+  dw_f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ dw_f2 dw_mul(dw_f2 a, dw_f2 b) {
+  dw_f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ dw_f2 dw_add(dw_f2 a, dw_f2 b) {
+  dw_f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 template <int C>
 __global__ void __launch_bounds__(C / 4) dwconv7_ln_run_kernel(const DwLnArgs a, int run) {
   constexpr int NW = C / 128;
-  __shared__ float red[2][NW][2];
+  __shared__ __align__(16) float4 red[2][NW];  // (sum0, sum1, sumsq0, sumsq1) of a frame pair per warp
   __shared__ __align__(16) float4 ring[DW_RING][C / 4];
   const int c = 4 * threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int runs_per_seq = (a.rows_per_batch + run - 1) / run;
 
-  // taps of channels c..c+3: 28 consecutive floats of w[C,7]
-  float wt[4][7];
+  // taps of channels c..c+3: 28 consecutive floats of w[C,7], repacked as (c, c+1) and (c+2, c+3) pairs per tap
+  dw_f2 wlo[7], whi[7];
   {
     const float4* wp = reinterpret_cast<const float4*>(a.w + (long long)c * 7);
     float raw[28];
@@ -316,90 +349,121 @@ __global__ void __launch_bounds__(C / 4) dwconv7_ln_run_kernel(const DwLnArgs a,
       raw[4 * i] = q.x; raw[4 * i + 1] = q.y; raw[4 * i + 2] = q.z; raw[4 * i + 3] = q.w;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < 7; ++k) wt[j][k] = raw[7 * j + k];
+    for (int k = 0; k < 7; ++k) {
+      wlo[k] = dw_pack(raw[k], raw[7 + k]);
+      whi[k] = dw_pack(raw[14 + k], raw[21 + k]);
+    }
   }
-  const float4 bias = __ldg(reinterpret_cast<const float4*>(a.wb + c));
-  const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_w + c));
-  const float4 be = __ldg(reinterpret_cast<const float4*>(a.ln_b + c));
+  const float4 bias4 = __ldg(reinterpret_cast<const float4*>(a.wb + c));
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_w + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + c));
+  const dw_f2 bias_lo = dw_pack(bias4.x, bias4.y), bias_hi = dw_pack(bias4.z, bias4.w);
+  const dw_f2 g_lo = dw_pack(g4.x, g4.y), g_hi = dw_pack(g4.z, g4.w);
+  const dw_f2 be_lo = dw_pack(be4.x, be4.y), be_hi = dw_pack(be4.z, be4.w);
+  const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
 
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   // persistent over (sequence, run) items: grid is sized to the resident CTA slots, so there is no partial last wave
   for (int item = blockIdx.x; item < runs_per_seq * a.nbatch; item += gridDim.x) {
-  const int b = item / runs_per_seq;
-  const int t0 = (item - b * runs_per_seq) * run;
-  const int t1 = min(t0 + run, a.rows_per_batch);
-  const int len = a.seq_lens ? a.seq_lens[b] : a.rows_per_batch;
-  const float* xb = a.x + (long long)b * a.rows_per_batch * a.ldx + c;
-  __nv_bfloat16* ob = a.out + (long long)b * a.rows_per_batch * a.ldo + c;
-  const int t_last = min(len - 1, t1 + 3);  // last row anyone in this run reads
-  auto issue_pair = [&](int q) {  // rows t0 + 2q + 3, +4 -> ring pair slot q % (DW_RING / 2)
-    const int ts = t0 + 2 * q + 3;
-    const int sl = 2 * (q % (DW_RING / 2));
-    if (ts >= 0 && ts <= t_last) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&ring[sl][threadIdx.x])),
-                   "l"(xb + (long long)ts * a.ldx) : "memory");
-    }
-    if (ts + 1 >= 0 && ts + 1 <= t_last) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&ring[sl + 1][threadIdx.x])),
-                   "l"(xb + (long long)(ts + 1) * a.ldx) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
+    const int b = item / runs_per_seq;
+    const int t0 = (item - b * runs_per_seq) * run;
+    const int t1 = min(t0 + run, a.rows_per_batch);
+    const int len = a.seq_lens ? a.seq_lens[b] : a.rows_per_batch;
+    const float* xb = a.x + (long long)b * a.rows_per_batch * a.ldx + c;
+    __nv_bfloat16* ob = a.out + (long long)b * a.rows_per_batch * a.ldo + c;
+    const int t_last = min(len - 1, t1 + 3);  // last row anyone in this run reads
+    // next ring pair slot to fill, the first of its two rows and that row's address; rows past t_last are zero-filled
+    // by the copy itself (source size 0), so the consumer reads the ring unconditionally
+    int issue_sl = 0, issue_t = t0 + 3;
+    const float* issue_p = xb + (long long)issue_t * a.ldx;
+    const long long ldx2 = 2 * a.ldx;
+    auto issue_pair = [&]() {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[issue_sl][threadIdx.x]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(issue_p), "r"(issue_t <= t_last ? 16 : 0) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)sizeof(float4) * (C / 4)),
+                   "l"(issue_p + a.ldx), "r"(issue_t + 1 <= t_last ? 16 : 0) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      issue_t += 2;
+      issue_p += ldx2;
+      issue_sl = issue_sl + 2 == DW_RING ? 0 : issue_sl + 2;
+    };
 #pragma unroll
-  for (int q = 0; q < DW_AHEAD / 2; ++q) issue_pair(q);
-  float4 win[8];  // rows t-3 .. t+4 of the current frame pair; the first six come straight from global memory
+    for (int q = 0; q < DW_AHEAD / 2; ++q) issue_pair();
+    // circular 8-row window: slot (2j + k) % 8 holds row t - 3 + k of the j-th frame pair of a rotation
+    dw_f2 wl[8], wh[8];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int tt = t0 - 3 + k;
-    win[k] = (tt >= 0 && tt < len) ? *reinterpret_cast<const float4*>(xb + (long long)tt * a.ldx) : zero4;
-  }
+    for (int k = 0; k < 6; ++k) {
+      const int tt = t0 - 3 + k;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tt >= 0 && tt < len) v = *reinterpret_cast<const float4*>(xb + (long long)tt * a.ldx);
+      wl[k] = dw_pack(v.x, v.y);
+      wh[k] = dw_pack(v.z, v.w);
+    }
 
-  int p = 0;
-  for (int t = t0; t < t1; t += 2, ++p) {
-    cp_async_wait_group<DW_AHEAD / 2 - 1>();
-    {
-      const int sl = 2 * (p % (DW_RING / 2));
-      win[6] = (t + 3 <= t_last) ? ring[sl][threadIdx.x] : zero4;
-      win[7] = (t + 4 <= t_last) ? ring[sl + 1][threadIdx.x] : zero4;
+    int read_sl = 0, par = 0;
+    __nv_bfloat16* op = ob + (long long)t0 * a.ldo;
+    for (int tb = t0; tb < t1; tb += 8) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = tb + 2 * j;
+        if (t >= t1) break;  // uniform over the CTA
+        cp_async_wait_group<DW_AHEAD / 2 - 1>();
+        {
+          const float4 v6 = ring[read_sl][threadIdx.x], v7 = ring[read_sl + 1][threadIdx.x];
+          wl[(2 * j + 6) & 7] = dw_pack(v6.x, v6.y); wh[(2 * j + 6) & 7] = dw_pack(v6.z, v6.w);
+          wl[(2 * j + 7) & 7] = dw_pack(v7.x, v7.y); wh[(2 * j + 7) & 7] = dw_pack(v7.z, v7.w);
+          read_sl = read_sl + 2 == DW_RING ? 0 : read_sl + 2;
+        }
+        issue_pair();  // overwrites the pair read one iteration ago
+        dw_f2 y0l = bias_lo, y0h = bias_hi, y1l = bias_lo, y1h = bias_hi;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          y0l = dw_fma(wlo[k], wl[(2 * j + k) & 7], y0l);
+          y0h = dw_fma(whi[k], wh[(2 * j + k) & 7], y0h);
+          y1l = dw_fma(wlo[k], wl[(2 * j + k + 1) & 7], y1l);
+          y1h = dw_fma(whi[k], wh[(2 * j + k + 1) & 7], y1h);
+        }
+        // (sum0, sum1, sumsq0, sumsq1) over the warp: exchange halves at lane bit 4, then bit 3, then a plain butterfly
+        const float2 sa = dw_unpack(dw_add(y0l, y0h)), sb = dw_unpack(dw_add(y1l, y1h));
+        const float2 qa = dw_unpack(dw_fma(y0l, y0l, dw_mul(y0h, y0h))), qb = dw_unpack(dw_fma(y1l, y1l, dw_mul(y1h, y1h)));
+        const float s0 = sa.x + sa.y, s1 = sb.x + sb.y, q0 = qa.x + qa.y, q1 = qb.x + qb.y;
+        float k0 = up16 ? q0 : s0, k1 = up16 ? q1 : s1;
+        k0 += __shfl_xor_sync(0xffffffffu, up16 ? s0 : q0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, up16 ? s1 : q1, 16);
+        float kk = up8 ? k1 : k0;
+        kk += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        if ((lane & 7) == 0) reinterpret_cast<float*>(&red[par][warp])[lane >> 3] = kk;
+        __syncthreads();
+        const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(&red[par][0]);
+        ulonglong2 acc = rp[0];
+#pragma unroll
+        for (int i = 1; i < NW; ++i) {
+          const ulonglong2 r = rp[i];
+          acc.x = dw_add(acc.x, r.x);
+          acc.y = dw_add(acc.y, r.y);
+        }
+        const float2 ts = dw_unpack(acc.x), tq = dw_unpack(acc.y);
+        const float4 tot = make_float4(ts.x, ts.y, tq.x, tq.y);
+        par ^= 1;
+        const float m0 = tot.x * (1.0f / C), m1 = tot.y * (1.0f / C);
+        const float r0 = rsqrtf(fmaxf(tot.z * (1.0f / C) - m0 * m0, 0.f) + a.eps);
+        const float r1 = rsqrtf(fmaxf(tot.w * (1.0f / C) - m1 * m1, 0.f) + a.eps);
+        // (y - m) * r * g + be = y * (r g) + (be - m r g)
+        const dw_f2 a0l = dw_mul(dw_pack(r0, r0), g_lo), a0h = dw_mul(dw_pack(r0, r0), g_hi);
+        const dw_f2 a1l = dw_mul(dw_pack(r1, r1), g_lo), a1h = dw_mul(dw_pack(r1, r1), g_hi);
+        const float2 o0l = dw_unpack(dw_fma(y0l, a0l, dw_fma(dw_pack(-m0, -m0), a0l, be_lo)));
+        const float2 o0h = dw_unpack(dw_fma(y0h, a0h, dw_fma(dw_pack(-m0, -m0), a0h, be_hi)));
+        const float2 o1l = dw_unpack(dw_fma(y1l, a1l, dw_fma(dw_pack(-m1, -m1), a1l, be_lo)));
+        const float2 o1h = dw_unpack(dw_fma(y1h, a1h, dw_fma(dw_pack(-m1, -m1), a1h, be_hi)));
+        *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(o0l.x, o0l.y), pack_bf16x2(o0h.x, o0h.y));
+        if (t + 1 < t1)
+          *reinterpret_cast<uint2*>(op + a.ldo) = make_uint2(pack_bf16x2(o1l.x, o1l.y), pack_bf16x2(o1h.x, o1h.y));
+        op += 2 * a.ldo;
+      }
     }
-    issue_pair(p + DW_AHEAD / 2);  // overwrites the pair read one iteration ago
-    float4 y0 = bias, y1 = bias;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      y0.x += wt[0][k] * win[k].x; y0.y += wt[1][k] * win[k].y; y0.z += wt[2][k] * win[k].z; y0.w += wt[3][k] * win[k].w;
-      y1.x += wt[0][k] * win[k + 1].x; y1.y += wt[1][k] * win[k + 1].y; y1.z += wt[2][k] * win[k + 1].z; y1.w += wt[3][k] * win[k + 1].w;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) win[k] = win[k + 2];
-
-    float s0 = warp_sum(y0.x + y0.y + y0.z + y0.w), s1 = warp_sum(y1.x + y1.y + y1.z + y1.w);
-    if (lane == 0) { red[0][warp][0] = s0; red[0][warp][1] = s1; }
-    __syncthreads();
-    s0 = 0.f; s1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) { s0 += red[0][i][0]; s1 += red[0][i][1]; }
-    const float m0 = s0 * (1.0f / C), m1 = s1 * (1.0f / C);
-    y0.x -= m0; y0.y -= m0; y0.z -= m0; y0.w -= m0;
-    y1.x -= m1; y1.y -= m1; y1.z -= m1; y1.w -= m1;
-    float q0 = warp_sum(y0.x * y0.x + y0.y * y0.y + y0.z * y0.z + y0.w * y0.w);
-    float q1 = warp_sum(y1.x * y1.x + y1.y * y1.y + y1.z * y1.z + y1.w * y1.w);
-    if (lane == 0) { red[1][warp][0] = q0; red[1][warp][1] = q1; }
-    __syncthreads();
-    q0 = 0.f; q1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) { q0 += red[1][i][0]; q1 += red[1][i][1]; }
-    const float r0 = rsqrtf(q0 * (1.0f / C) + a.eps), r1 = rsqrtf(q1 * (1.0f / C) + a.eps);
-    uint2 o0, o1;
-    o0.x = pack_bf16x2(y0.x * r0 * g.x + be.x, y0.y * r0 * g.y + be.y);
-    o0.y = pack_bf16x2(y0.z * r0 * g.z + be.z, y0.w * r0 * g.w + be.w);
-    o1.x = pack_bf16x2(y1.x * r1 * g.x + be.x, y1.y * r1 * g.y + be.y);
-    o1.y = pack_bf16x2(y1.z * r1 * g.z + be.z, y1.w * r1 * g.w + be.w);
-    *reinterpret_cast<uint2*>(ob + (long long)t * a.ldo) = o0;
-    if (t + 1 < t1) *reinterpret_cast<uint2*>(ob + (long long)(t + 1) * a.ldo) = o1;
-  }
-  cp_async_wait_group<0>();
+    cp_async_wait_group<0>();
   }
 }
 

@@ -24,3 +24,13 @@ for _ in range(2):
     L.istft_head(hs, win, wv, rows_per_batch=T, nb=nb, n_frames=T, mode=0)
 torch.cuda.synchronize()
 print("ok", float(mel.mean()), float(wv.abs().mean()))
+# dwconv7 + LayerNorm at the same size (C = 512)
+R, D = nb * T, 512
+x = torch.randn(R, D, device=dev)
+n = torch.empty(R, D, device=dev, dtype=torch.bfloat16)
+w, wb = torch.randn(D, 7, device=dev), torch.randn(D, device=dev)
+lw, lb = torch.randn(D, device=dev), torch.randn(D, device=dev)
+for _ in range(2):
+    L.dwconv7_ln(x, rows_per_batch=T, nbatch=nb, seq_lens=None, w=w, wb=wb, ln_w=lw, ln_b=lb, eps=1e-6, out=n)
+torch.cuda.synchronize()
+print("ok dwconv", float(n.float().abs().mean()))
