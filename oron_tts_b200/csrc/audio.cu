@@ -102,7 +102,10 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
     const float4* bw = reinterpret_cast<const float4*>(bands + 2 * MEL_MAXM * 4);
     for (int m = threadIdx.x; m < 2 * MEL_MAXM; m += blockDim.x) band_lo[m] = bl[m];  // lo[128] | n[128], contiguous here too
     float4* dst = reinterpret_cast<float4*>(&fbs[0][0]);
-    for (int i = threadIdx.x; i < MEL_MAXBAND * MEL_MAXM / 4; i += blockDim.x) dst[i] = bw[i];
+    for (int i = threadIdx.x; i < MEL_MAXBAND * MEL_MAXM / 4; i += blockDim.x) {  // * 1/2: |A| = |p| / 2 (below)
+      const float4 q = bw[i];
+      dst[i] = make_float4(0.5f * q.x, 0.5f * q.y, 0.5f * q.z, 0.5f * q.w);
+    }
   }
   __syncthreads();
 
@@ -157,7 +160,8 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
     // split the two real spectra: bin k = lane + 32 k2 needs Z[k] and Z[1024 - k]; the latter sits in lane
     // (32 - lane) & 31, register 31 - k2 (lane 0: own register (32 - k2) & 31).
     // A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i: |A| = |p| / 2, |B| = |q| / 2 with
-    // p = (z.x + zp.x, z.y - zp.y), q = (z.x - zp.x, z.y + zp.y)
+    // p = (z.x + zp.x, z.y - zp.y), q = (z.x - zp.x, z.y + zp.y); the tile holds |p|, |q| and the filter weights in
+    // shared memory carry the factor 1/2
     const int src = (32 - lane) & 31;
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
@@ -166,11 +170,11 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
       if (lane == 0) zp = v[(32 - k2) & 31];
       const c64 pq = fw::cfma2(zp, fw::cpack(1.0f, -1.0f), z), qq = fw::cfma2(zp, fw::cpack(-1.0f, 1.0f), z);
       const float2 p2 = fw::cunpack(fw::cmul2(pq, pq)), q2 = fw::cunpack(fw::cmul2(qq, qq));
-      mag2[lane + 32 * k2] = fw::cpack(sqrt_approx(0.25f * (p2.x + p2.y)), sqrt_approx(0.25f * (q2.x + q2.y)));
+      mag2[lane + 32 * k2] = fw::cpack(sqrt_approx(p2.x + p2.y), sqrt_approx(q2.x + q2.y));
     }
     if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
       const float2 ny = fw::cunpack(v[16]);
-      mag2[512] = fw::cpack(fabsf(ny.x), fabsf(ny.y));
+      mag2[512] = fw::cpack(2.0f * fabsf(ny.x), 2.0f * fabsf(ny.y));
     }
     __syncwarp();
     // banded mel projection, both frames at once: lane -> filters lane, lane + 32, ...; rows of fbs beyond a filter's
@@ -189,14 +193,14 @@ logmel_kernel(const float* __restrict__ wav, long long ld_wav, int nb, int n_sam
         }
       } else {
         for (int i = 0; i < n; ++i) {
-          const float f = fb[(long long)(lo + i) * n_mels + m];
+          const float f = 0.5f * fb[(long long)(lo + i) * n_mels + m];
           acc0 = fw::cfma2(mag2[lo + i], fw::cpack(f, f), acc0);
         }
       }
       const float2 a2 = fw::cunpack(fw::cadd(fw::cadd(acc0, acc1), fw::cadd(acc2, acc3)));
       float* o = out + ((long long)b * n_mels + m) * n_frames + fA;
-      o[0] = logf(fmaxf(a2.x, clip));
-      if (hasB) o[1] = logf(fmaxf(a2.y, clip));
+      o[0] = __logf(fmaxf(a2.x, clip));  // lg2.approx * ln 2: absolute error < 1e-6 on these magnitudes
+      if (hasB) o[1] = __logf(fmaxf(a2.y, clip));
     }
     __syncwarp();  // the tile (magnitudes) is reused by the next pair's transform
   }
@@ -217,20 +221,23 @@ constexpr int IST_MIN_RUN = 8;
 // exp / cos / sin of the head activations (Vocos ISTFTHead): fast-math units after an explicit
 // two-constant range reduction, absolute error ~1e-6 for |phase| < 1e3.
 __device__ __forceinline__ float2 polar_clip(float logmag, float phase) {
-  const float mg = fminf(__expf(logmag), 100.0f);
+  float mg, s, c;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(mg) : "f"(logmag * 1.4426950408889634f));  // < 2^-126 flushes to 0
+  mg = fminf(mg, 100.0f);
   const float q = (fmaf(phase, 0.15915494309189535f, 12582912.0f)) - 12582912.0f;  // round to nearest (|phase| < 2^22)
   float r = fmaf(q, -6.2831854820251465f, phase);   // hi part of 2 pi (fp32)
   r = fmaf(q, 1.7484555e-7f, r);                    // 2 pi - hi
-  float s, c;
-  __sincosf(r, &s, &c);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(r));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(r));
   return make_float2(mg * c, mg * s);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+template <int mode>
 __global__ void __launch_bounds__(AUD_THREADS, 2)
 istft_head_kernel(const float* __restrict__ h, long long ldh, int rows_per_batch, int nb, int n_frames,
-                  const float* __restrict__ window, int mode, float* __restrict__ out, long long ld_out, int run,
+                  const float* __restrict__ window, float* __restrict__ out, long long ld_out, int run,
                   int runs_per_clip) {
   extern __shared__ __align__(16) uint8_t dsm[];
   float2* xb_all = reinterpret_cast<float2*>(dsm);
@@ -317,7 +324,7 @@ istft_head_kernel(const float* __restrict__ h, long long ldh, int rows_per_batch
             Q = *reinterpret_cast<const float2*>(rawB + 2 * k);
           }
           if (!hasB) Q = make_float2(0.f, 0.f);
-          if (k == 0) { P.y = 0.f; Q.y = 0.f; }  // C2R ignores the imaginary part of DC
+          if (n1 == 0 && lane == 0) { P.y = 0.f; Q.y = 0.f; }  // C2R ignores the imaginary part of DC
           v[n1] = fw::cpack(P.x - Q.y, P.y + Q.x);
           zc[n1] = make_float2(P.x + Q.y, Q.x - P.y);
         }
@@ -471,12 +478,16 @@ extern "C" int oron_istft_head(const float* h, int64_t ldh, int32_t rows_per_bat
   dim3 grid((unsigned)(ctas < cap ? ctas : cap));
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(istft_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IST_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(istft_head_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, IST_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(istft_head_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IST_SMEM);
     if (e != cudaSuccess) return fail(int(e), "istft smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  istft_head_kernel<<<grid, AUD_THREADS, IST_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
-      h, ldh, rows_per_batch, nb, n_frames, window, mode, out, ld_out, int(run), int(rpc));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mode == 0)
+    istft_head_kernel<0><<<grid, AUD_THREADS, IST_SMEM, st>>>(h, ldh, rows_per_batch, nb, n_frames, window, out, ld_out, int(run), int(rpc));
+  else
+    istft_head_kernel<1><<<grid, AUD_THREADS, IST_SMEM, st>>>(h, ldh, rows_per_batch, nb, n_frames, window, out, ld_out, int(run), int(rpc));
   return check_launch("istft_head");
 }
 

@@ -139,8 +139,12 @@ __device__ __forceinline__ void fft1024_warp(c64 (&v)[32], float2* xb, const flo
     constexpr int k1 = decltype(K)::value;
     c64 y = v[brev5(k1)];
     if constexpr (k1 > 0) {
+      // y * (wr + i wi) with a run-time twiddle: one FMUL2 (wr broadcast) and two scalar FFMAs on the halves (the packed
+      // form needs the pair (-wi, wi) built from a register: two more instructions)
       const float2 w = cunpack(twq[k1 * 32 + lane]);  // exp(-2 pi i k1 lane / 1024); conjugate for the inverse
-      y = cmul(y, w.x, INV ? -w.y : w.y);
+      const float wi = INV ? -w.y : w.y;
+      const float2 d = cunpack(y), t = cunpack(cmul2(y, cpack(w.x, w.x)));
+      y = cpack(fmaf(-d.y, wi, t.x), fmaf(d.x, wi, t.y));
     }
     xq[k1 * XB_LD + lane] = y;
   });
