@@ -346,12 +346,14 @@ static int attn_version() {
 }
 extern "C" void oron_debug_set_attention_version(int32_t v) { g_attn_version = (v == 3) ? 3 : 4; }
 
-// Split items are merged by attn4_combine_kernel right behind the attention launch (default; measured 37.2 us per call at
-// config 2) or, with ORON_ATT_COMBINE=inline, by the attention kernel's own combine warps (38.1 us: no second launch, but
-// the two extra warps take issue slots from the softmax warps they share schedulers with).
+// Split items are merged inside the attention launch by its two combine warps, every CTA that holds a part of an item
+// combining its share of the item's rows once all parts have arrived (default: 30.2 us per call at config 2), or, with
+// ORON_ATT_COMBINE=kernel, by attn4_combine_kernel right behind the attention launch (33.1 us: a second launch on the
+// critical path between the attention kernel and the out-projection). The first in-kernel version, where the last part
+// to arrive merged the whole item alone, cost 38.1 us.
 static bool attn_inline_combine() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ORON_ATT_COMBINE"); v = (e && e[0] == 'i') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("ORON_ATT_COMBINE"); v = (e && e[0] == 'k') ? 0 : 1; }
   return v == 1;
 }
 // ORON_ATT_SKEW: share of a CTA's work moved from the second CTA of every SM to the first (attn4_plan_kernel). Default 0:
@@ -377,7 +379,7 @@ static Attn4WsLayout attn4_ws_layout(int nbatch, int rows_per_batch, int heads) 
   w.off_segs = up(w.off_nseg + int64_t(w.grid) * 4);
   w.off_merge = up(w.off_segs + int64_t(w.grid) * w.seg_stride * int64_t(sizeof(Attn4Seg)));
   w.off_cnt = up(w.off_merge + int64_t(w.grid) * int64_t(sizeof(Attn4Merge)));
-  w.off_ml = up(w.off_cnt + int64_t(w.grid) * 4);
+  w.off_ml = up(w.off_cnt + int64_t(w.grid) * 8);
   w.off_o = up(w.off_ml + int64_t(2 * w.grid) * ATT4_TILE * 2 * 4);
   w.bytes = up(w.off_o + int64_t(2 * w.grid) * ATT4_TILE * ATT4_D * 2);
   return w;

@@ -63,7 +63,7 @@ struct Attn4Args {
   const int* plan_nseg;
   const Attn4Seg* plan_segs;
   const Attn4Merge* plan_merge;  // [grid]
-  int* ws_cnt;          // [grid] arrival counters of the split items (zero between launches), or nullptr: attn4_combine_kernel merges
+  int* ws_cnt;          // [2 grid] arrival / departure counters of the split items (zero between launches), or nullptr: attn4_combine_kernel merges
   __half* ws_o;         // [2 * grid][128][64] f16: O_p / l_p of a partial segment
   float* ws_ml;         // [2 * grid][128][2] f32: (running max * c, l_p)
   float* lse;           // optional [nbatch * heads * rows_per_batch] f32: log2-domain log-sum-exp of every query row
@@ -516,9 +516,14 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
     }
   } else if (warp < 4) {
     // ===================== combine warps (64 threads): the split items =====================
-    // args.ws_cnt != nullptr: the softmax threads only publish a partial result and move on; here the part is counted and,
-    // if it was the item's last one to arrive, all parts are combined (nobody waits for anybody). The plans run the
-    // partial segments FIRST, so this happens early in the launch, under the softmax of the whole items.
+    // args.ws_cnt != nullptr: the softmax threads only publish a partial result and move on. These two warps count the
+    // CTA's parts as they are published (arrival counter of the item, cnt[2 owner]); then, for every split item the CTA
+    // has a part of, they wait until all of its parts have arrived and combine THEIR SHARE of the item's 128 rows (part p
+    // of n takes row groups [16 p / n, 16 (p + 1) / n) of eight rows): the combination of an item is spread over the CTAs
+    // that hold its parts, eight rows per round of loads, and nobody merges a whole item alone. With the two-phase plan
+    // (a CFG pair) the parts are the FIRST thing every CTA runs, so all of this happens under the softmax of the whole
+    // item that follows. Arrivals are counted for all parts before the first wait: a wait never delays another CTA.
+    // The last part to leave (cnt[2 owner + 1]) zeroes both counters for the next launch (graph replays included).
     // args.ws_cnt == nullptr: attn4_combine_kernel does it after the launch.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT4_REGS_AUX));
     if (args.ws_cnt != nullptr) {
@@ -526,29 +531,42 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn4Args args
       int nseg;
       att4_segments(args, smem_raw, segs, nseg);
       const uint32_t bar_base = smem_u32(smem_raw) + ATT4_BAR_OFF;
-      volatile int* merge_flag = reinterpret_cast<volatile int*>(smem_raw + ATT4_BAR_OFF + 184);
       const int hid = threadIdx.x - 64;
       int np = 0;
       for (int sidx = 0; sidx < nseg; ++sidx) {
         if (seg_field(segs, sidx, 5) < 0) continue;
-        const int owner = seg_field(segs, sidx, 6), nparts = seg_field(segs, sidx, 7);
         // a long wait: sleep in the suspending try_wait instead of polling (the softmax warps share these schedulers)
         { const long long t0w = clock64(); while (!mbar_try_wait(part_ready, np & 1u)) { if (clock64() - t0w > ORON_WATCHDOG_CYCLES) { g_att4_fault = 22000000 + int(blockIdx.x) * 1000; __trap(); } } }
         ++np;
         if (hid == 0) {
           __threadfence();  // cumulative: the softmax threads' stores (observed through the barrier) before the count
-          const int old = atomicAdd(args.ws_cnt + owner, 1);
-          const int is_last = old == nparts - 1;
-          if (is_last) args.ws_cnt[owner] = 0;  // ready for the next launch (CUDA-graph replays included)
-          *merge_flag = is_last;
+          atomicAdd(args.ws_cnt + 2 * seg_field(segs, sidx, 6), 1);
+        }
+      }
+      for (int sidx = 0; sidx < nseg; ++sidx) {
+        if (seg_field(segs, sidx, 5) < 0) continue;
+        const int owner = seg_field(segs, sidx, 6), nparts = seg_field(segs, sidx, 7);
+        if (hid == 0) {
+          const long long t0w = clock64();
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(args.ws_cnt + 2 * owner) : "memory");
+            if (seen >= nparts) break;
+            __nanosleep(64);
+            if (clock64() - t0w > ORON_WATCHDOG_CYCLES) { g_att4_fault = 23000000 + int(blockIdx.x) * 1000; __trap(); }
+          } while (true);
         }
         asm volatile("bar.sync 1, 64;" ::: "memory");
-        const int is_last = *merge_flag;
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        if (!is_last) continue;
         __threadfence();
-        att4_combine_item<64, 1>(hid, owner, nparts, seg_field(segs, sidx, 0), seg_field(segs, sidx, 1), seg_field(segs, sidx, 2),
-                                 args.ws_o, args.ws_ml, args.out, args.ldo, args.lse, args.rows_per_batch, args.heads);
+        const int p = int(blockIdx.x) - owner;
+        att4_combine_item<64, 1, 4>(hid, owner, nparts, seg_field(segs, sidx, 0), seg_field(segs, sidx, 1), seg_field(segs, sidx, 2),
+                                    args.ws_o, args.ws_ml, args.out, args.ldo, args.lse, args.rows_per_batch, args.heads,
+                                    8 * ((16 * p) / nparts), 8 * ((16 * (p + 1)) / nparts));
+        asm volatile("bar.sync 1, 64;" ::: "memory");  // every read of the parts is done
+        if (hid == 0) {
+          const int old = atomicAdd(args.ws_cnt + 2 * owner + 1, 1);
+          if (old == nparts - 1) { args.ws_cnt[2 * owner] = 0; args.ws_cnt[2 * owner + 1] = 0; }
+        }
       }
     }
   } else {
@@ -938,7 +956,8 @@ __global__ void attn4_plan_kernel(Attn4PlanHeader* hdr, int* nseg_out, Attn4Seg*
     }
     nseg_out[c] = n;
     merge[c] = me;
-    cnt[c] = 0;
+    cnt[2 * c] = 0;
+    cnt[2 * c + 1] = 0;
   }
   __syncthreads();
   if (threadIdx.x == 0) { __threadfence(); hdr->magic = ATT4_PLAN_MAGIC; }
