@@ -533,12 +533,14 @@ def secondary_cfg1(voc, dev) -> dict:
     ids = torch.tensor([[4, 30, 11, 21, 25, 53, 12, 11, 21, 25, 11, 53, 32, 32]], device=dev)
     cond, lens = torch.zeros(1, 143, 100, device=dev), torch.tensor([0], device=dev)
 
+    # unseeded, like the headline legs: a seeded call selects the bit-reproducible mode (no stream-K in the FFN
+    # down-projection), which costs ~16 % at this launch-bound size and is reported for config 2 under "deterministic"
     def dev_step(seed):
-        mel, _ = m.cfm.sample(cond, ids, 143, lens=lens, steps=32, cfg_strength=1.5, sway_sampling_coef=SWAY, seed=seed)
+        mel, _ = m.cfm.sample(cond, ids, 143, lens=lens, steps=32, cfg_strength=1.5, sway_sampling_coef=SWAY)
         return voc.decode(mel.transpose(1, 2))
 
     def e2e_step(seed):
-        return m.synthesize("Сайн байна уу", lang="mn", n_steps=32, cfg_strength=1.5, sway_sampling_coef=SWAY, seed=seed, device=str(dev))
+        return m.synthesize("Сайн байна уу", lang="mn", n_steps=32, cfg_strength=1.5, sway_sampling_coef=SWAY, device=str(dev))
 
     res = {}
     for name, fn in (("device", dev_step), ("e2e", e2e_step)):
