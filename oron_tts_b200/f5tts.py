@@ -97,6 +97,17 @@ def estimate_target_len(*, target_duration_s: float | None, sample_rate: int, ho
     return max(50, int(chars * 13 / speed))
 
 
+def _to_device(module: nn.Module, device: str | torch.device) -> nn.Module:
+    """``module.to(device)``, skipped when the module already lives there (judged by its first parameter)."""
+    want = torch.device(device)
+    if want.type == "cuda" and want.index is None and torch.cuda.is_available():
+        want = torch.device("cuda", torch.cuda.current_device())
+    first = next(module.parameters(), None)
+    if first is not None and first.device == want:
+        return module
+    return module.to(device)
+
+
 class F5TTS(nn.Module):
     def __init__(self, n_mels: int = 100, vocab_size: int = 65, dim: int = 1024, depth: int = 22, heads: int = 16,
                  dim_head: int = 64, ff_mult: int = 4, text_dim: int = 512, conv_layers: int = 4, p_dropout: float = 0.1,
@@ -120,6 +131,13 @@ class F5TTS(nn.Module):
             lens = lens.sum(dim=-1).long()
         return self.cfm(mel, text_ids, lens=lens)
 
+    def _ready(self, device: str) -> None:
+        """``self.eval(); self.to(device)`` (f5tts.py:243-244) without the two sweeps over ~2 k submodules when nothing
+        would change: they cost ~4 ms of host time per call during which the GPU has nothing to do."""
+        if self.training:
+            self.eval()
+        _to_device(self, device)
+
     # ---- vocoder: cached outside the parameter tree (f5tts.py:190-202) ---------------------------------
     def _get_vocos(self, device: str) -> Any:
         vocos = self.__dict__.get("_vocos_cache")
@@ -128,7 +146,7 @@ class F5TTS(nn.Module):
 
             vocos = Vocos.from_pretrained("charactr/vocos-mel-24khz").eval()
             object.__setattr__(self, "_vocos_cache", vocos)
-        return vocos.to(device)
+        return _to_device(vocos, device)
 
     def set_vocoder(self, vocos: Any) -> None:
         """Install a vocoder instance explicitly (offline boxes: random-init or locally stored weights)."""
@@ -163,8 +181,7 @@ class F5TTS(nn.Module):
             raise ValueError(f"max_chars_per_chunk must be >= 0, got {max_chars_per_chunk}")
         if pause_s < 0:
             raise ValueError(f"pause_s must be >= 0, got {pause_s}")
-        self.eval()
-        self.to(device)
+        self._ready(device)
         self._warn_lang_contamination(text, lang)
         if ref_text:
             self._warn_lang_contamination(ref_text, lang)
@@ -222,8 +239,7 @@ class F5TTS(nn.Module):
             raise ValueError("target_duration_s must be > 0")
         from .shard import plan_batches
 
-        self.eval()
-        self.to(device)
+        self._ready(device)
         ap = self._audio_processor
         ref_mel_raw = None
         if ref_audio_path is not None:

@@ -97,7 +97,8 @@ class CFM(nn.Module):
             raise ValueError(f"steps must be >= 1, got {steps}")
         if cfg_strength < 0:
             raise ValueError(f"cfg_strength must be >= 0, got {cfg_strength}")
-        self.eval()
+        if self.training:  # eval() is a sweep over every submodule (host milliseconds per call with the GPU idle)
+            self.eval()
         batch, cond_seq_len, device = cond.shape[0], cond.shape[1], cond.device
         if not cond.is_cuda:
             raise RuntimeError("CFM.sample runs only on a CUDA device (oron_tts_b200 has no CPU fallback)")
