@@ -723,16 +723,33 @@ class TrainEngine:
             self.reducer.block_done(i)  # sharded optimizer: one reduce-scatter of the whole arena in optimizer_step instead
 
     # token ids outside [-1, vocab) (nn.Embedding raises IndexError for them, encoder.py:68-75): the range test runs on the
-    # device at the start of the pass, the kernels see clamped ids, and the verdict is read once the whole pass has been
-    # enqueued -- so the check costs no pipeline bubble. The same read tells whether the PREVIOUS optimizer step was
-    # skipped on the device (non-finite gradients), in which case its Adam step number is given back.
+    # device at the start of the pass, the kernels see clamped ids, and the verdict travels to pinned host memory on a SIDE
+    # stream right away (a copy on the compute stream would be ordered behind the whole pass and make the host wait for
+    # the backward: no run-ahead into the next step). It is read once the pass has been enqueued, by which time the copy
+    # has long finished. The same read tells whether the PREVIOUS optimizer step was skipped on the device (non-finite
+    # gradients), in which case its Adam step number is given back.
     def _check_ids_begin(self, ids_shifted: torch.Tensor):
         vocab1 = self.w.text_table.shape[0]
         self._id_flags = torch.stack([((ids_shifted < 0) | (ids_shifted >= vocab1)).any().to(I32), self.skipped.reshape(())])
+        if self._id_flags.is_cuda:
+            if getattr(self, "_flag_stream", None) is None:
+                self._flag_stream = torch.cuda.Stream(device=self._id_flags.device)
+                self._flag_host = torch.zeros(2, dtype=I32).pin_memory()
+                self._flag_event = torch.cuda.Event()
+            main = torch.cuda.current_stream(self._id_flags.device)
+            self._flag_stream.wait_stream(main)
+            with torch.cuda.stream(self._flag_stream):
+                self._flag_host.copy_(self._id_flags, non_blocking=True)
+                self._flag_event.record(self._flag_stream)
+            self._id_flags.record_stream(self._flag_stream)
         return self._id_flags
 
     def _check_ids_end(self) -> None:
-        bad, skipped_prev = (int(v) for v in self._id_flags.tolist())
+        if self._id_flags.is_cuda:
+            self._flag_event.synchronize()
+            bad, skipped_prev = (int(v) for v in self._flag_host.tolist())
+        else:
+            bad, skipped_prev = (int(v) for v in self._id_flags.tolist())
         if skipped_prev and getattr(self, "_step_pending_skip_check", False):
             self.step_count -= 1
         self._step_pending_skip_check = False
