@@ -130,6 +130,21 @@ typedef struct oron_gemm_desc {
 int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);
 
 /*
+ * FeedForward of a DiTBlock in ONE launch (modules.py:294-299 and the gated residual modules.py:343; replaces the two
+ * oron_gemm_bf16 calls `up` then `down`):   H = act(A W1^T + b1) ; resid += gate * (H W2^T + b2).
+ *   up:   ORON_EPI_BF16 (act ORON_ACT_GELU_TANH or NONE), two_sm = 1, block_n = 256, N % 256 == 0; writes H (bf16) to up->out
+ *   down: ORON_EPI_GATE_RESID, two_sm = 1, block_n = 256, A == up->out, w_cols == up->N
+ * Every SM pair runs its share of up-projection tiles and then an equal share of the down-projection's (tile, k-block)
+ * list; a down-projection k-block is fetched as soon as the H tile it reads is complete (global flags in `workspace`),
+ * partial K sums are added to resid with f32 vector reductions (like stream_k: the last bit may vary run to run).
+ * workspace: oron_ffn_workspace_bytes() bytes, 16-byte aligned, zeroed ONCE by the caller; the kernel leaves it zeroed.
+ * One workspace must not be used by two launches that may run concurrently.
+ */
+int64_t oron_ffn_workspace_bytes(int32_t rows_per_batch, int32_t nbatch, int32_t ff_dim);
+int oron_ffn_bf16(const oron_gemm_desc* up, const oron_gemm_desc* down, void* workspace, int64_t workspace_bytes,
+                  oron_stream_t stream);
+
+/*
  * softmax(Q K^T * scale + key_padding_mask) V over the fused QKV activation; head_dim 64.
  * Replaces F.scaled_dot_product_attention + mask (modules.py:271-278). RoPE is already applied
  * by the QKV GEMM epilogue.

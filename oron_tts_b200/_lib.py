@@ -24,6 +24,8 @@ ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
 
 EXPORTED_SYMBOLS = (
     "oron_gemm_bf16",
+    "oron_ffn_bf16",
+    "oron_ffn_workspace_bytes",
     "oron_attention_bf16",
     "oron_attention_workspace_bytes",
     "oron_attention_plan",
@@ -122,6 +124,9 @@ def lib() -> ctypes.CDLL:
     L.oron_debug_set_attention_version.argtypes = [c_int32]
     L.oron_debug_set_attention_version.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
+    L.oron_ffn_bf16.argtypes = [POINTER(GemmDesc), POINTER(GemmDesc), c_void_p, c_int64, c_void_p]
+    L.oron_ffn_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
+    L.oron_ffn_workspace_bytes.restype = c_int64
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
                                       c_void_p, c_float, c_void_p, c_int64, c_void_p]
     L.oron_attention_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
@@ -226,8 +231,10 @@ def gemm(
     k: int | None = None,
     dropout_p: float = 0.0,
     dropout_seed: int = 0,
-) -> None:
+    desc_only: bool = False,
+):
     """out = epilogue(A @ W.T) on the tcgen05 GEMM. A [rows, lda] bf16, W [N, ldw] bf16.
+    ``desc_only``: build and return the descriptor without launching (operand of `ffn`).
 
     ``a_mn`` / ``b_mn`` (2-SM kernel): the operand is given as stored for the backward pass, with the contraction over
     its ROWS -- A as [K, M] (out = A.T @ ...), W as [K, N] (out = ... @ W); pass ``rows_per_batch`` = M and ``n`` = N."""
@@ -278,7 +285,22 @@ def gemm(
                                          EPI_SCALE_RESID, EPI_GATE_RESID_DUAL) else torch.bfloat16
     if out.dtype != want:
         raise TypeError(f"gemm epilogue {epilogue}: out must be {want}, got {out.dtype}")
+    if desc_only:
+        return d
     _check(lib().oron_gemm_bf16(ctypes.byref(d), _stream()), "oron_gemm_bf16")
+
+
+def ffn_workspace(rows_per_batch: int, nbatch: int, ff_dim: int, device) -> torch.Tensor:
+    """Zeroed flag buffer of `ffn` (the kernel leaves it zeroed; one buffer serves any number of launches in stream order)."""
+    n = int(lib().oron_ffn_workspace_bytes(rows_per_batch, nbatch, ff_dim))
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def ffn(up, down, workspace: torch.Tensor) -> None:
+    """FeedForward up-projection + activation + down-projection + gated residual in one launch (oron_ffn_bf16);
+    `up` / `down` are descriptors from `gemm(..., desc_only=True)`."""
+    _check(lib().oron_ffn_bf16(ctypes.byref(up), ctypes.byref(down), _ptr(workspace, torch.uint8, "workspace"),
+                               workspace.numel(), _stream()), "oron_ffn_bf16")
 
 
 def attention_workspace(nbatch: int, rows_per_batch: int, heads: int, device, seq_lens: torch.Tensor | None = None) -> torch.Tensor:

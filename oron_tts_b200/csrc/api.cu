@@ -10,6 +10,7 @@
 #include "../../include/oron_b200.h"
 #include "attn_fwd4.cuh"
 #include "attn_tcgen05.cuh"
+#include "ffn_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "host_util.h"
 #include "rowwise.cuh"
@@ -133,12 +134,12 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   return check_launch("gemm2_bf16_tcgen05");
 }
 
-extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
+// descriptor checks + kernel arguments + TMA maps of one GEMM (shared by oron_gemm_bf16 and oron_ffn_bf16)
+static int gemm_prepare(const oron_gemm_desc* d, GemmArgs& a, CUtensorMap& ta, CUtensorMap& tb) {
   if (!d || !d->A || !d->W || !d->out) return fail(ORON_ERR_BAD_ARG, "gemm: null pointer");
   if (d->rows_per_batch <= 0 || d->nbatch <= 0 || d->N <= 0 || d->w_cols <= 0)
     return fail(ORON_ERR_BAD_ARG, "gemm: bad shape");
   const int taps = d->taps > 0 ? d->taps : 1;
-  GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.rows_per_batch = d->rows_per_batch;
   a.nbatch = d->nbatch;
@@ -228,7 +229,6 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
     if (!two_sm || taps != 1 || d->w_cols % GEMM_BK != 0 || (a.a_mn && d->nbatch != 1))
       return fail(ORON_ERR_UNSUPPORTED, "gemm: MN-major operands need two_sm, taps == 1, K %% 64 == 0 (and nbatch == 1 for A)");
   }
-  CUtensorMap ta, tb;
   int rc;
   if (a.a_mn)  // source [K, lda], columns [0, M): box = 64 MN x 64 K rows
     rc = make_tmap_bf16(&ta, d->A, uint64_t(d->rows_per_batch), uint64_t(d->w_cols), 1, uint64_t(d->lda), 0, 64, 2);
@@ -241,7 +241,15 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   else
     rc = make_tmap_bf16(&tb, d->W, uint64_t(d->w_cols), uint64_t(d->N), 1, uint64_t(d->ldw), 0,
                         uint32_t(two_sm ? d->block_n / 2 : d->block_n), 2);
-  if (rc) return rc;
+  return rc;
+}
+
+extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
+  GemmArgs a;
+  CUtensorMap ta, tb;
+  if (int rc = gemm_prepare(d, a, ta, tb)) return rc;
+  const int epi = d->epilogue;
+  const bool two_sm = d->two_sm != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   if (a.a_mn || a.b_mn) {  // backward-pass layouts: compile-time variants of the 2-SM kernel
@@ -299,6 +307,92 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM_CASE(64, EPI_SCALE_RESID)
 #undef ORON_GEMM_CASE
   return fail(ORON_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d epilogue=%d", d->block_n, epi);
+}
+
+// ---------------------------------------------------------------------------
+// FeedForward in one launch (ffn_tcgen05.cuh)
+// ---------------------------------------------------------------------------
+static int ffn_flag_count(int rows_per_batch, int nbatch, int ff_dim) {
+  const int tiles_m = ((rows_per_batch + GEMM_BM - 1) / GEMM_BM) * nbatch;
+  return 2 * ((tiles_m + 1) / 2) * ((ff_dim + 255) / 256);
+}
+extern "C" int64_t oron_ffn_workspace_bytes(int32_t rows_per_batch, int32_t nbatch, int32_t ff_dim) {
+  if (rows_per_batch <= 0 || nbatch <= 0 || ff_dim <= 0) return 0;
+  return 64 + 4ll * ffn_flag_count(rows_per_batch, nbatch, ff_dim);
+}
+
+extern "C" int oron_ffn_bf16(const oron_gemm_desc* up, const oron_gemm_desc* down, void* workspace, int64_t workspace_bytes,
+                             oron_stream_t stream) {
+  GemmArgs a1, a2;
+  CUtensorMap ta1, tb1, ta2, tb2;
+  if (int rc = gemm_prepare(up, a1, ta1, tb1)) return rc;
+  if (int rc = gemm_prepare(down, a2, ta2, tb2)) return rc;
+  const int taps1 = up->taps > 0 ? up->taps : 1, taps2 = down->taps > 0 ? down->taps : 1;
+  if (!up->two_sm || !down->two_sm || up->block_n != 256 || down->block_n != 256 || taps1 != 1 || taps2 != 1 || a1.a_mn || a1.b_mn ||
+      a2.a_mn || a2.b_mn)
+    return fail(ORON_ERR_UNSUPPORTED, "ffn: both GEMMs must be plain K-major 2-SM GEMMs with block_n 256");
+  if (up->epilogue != EPI_BF16 || down->epilogue != EPI_GATE_RESID)
+    return fail(ORON_ERR_UNSUPPORTED, "ffn: epilogues must be BF16 (up) and GATE_RESID (down)");
+  if (up->act != ACT_GELU_TANH && up->act != ACT_NONE) return fail(ORON_ERR_UNSUPPORTED, "ffn: activation must be GELU_TANH or NONE");
+  if (down->A != up->out || down->lda != up->ldo || up->N != down->w_cols || up->N % 256 != 0 || up->w_cols % GEMM_BK != 0 ||
+      up->rows_per_batch != down->rows_per_batch || up->nbatch != down->nbatch)
+    return fail(ORON_ERR_BAD_ARG, "ffn: the down-projection must read the up-projection's output (same rows; ff_dim %% 256 == 0)");
+  if (down->N % 4 != 0) return fail(ORON_ERR_BAD_ARG, "ffn: N %% 4 == 0");
+  const int nflags = ffn_flag_count(up->rows_per_batch, up->nbatch, up->N);
+  if (!workspace || workspace_bytes < 64 + 4ll * nflags || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0)
+    return fail(ORON_ERR_BAD_ARG, "ffn: workspace of oron_ffn_workspace_bytes() bytes (zero-initialised, 16-byte aligned) required");
+  a2.stream_k = 1;
+  FfnSync sy;
+  sy.done = reinterpret_cast<int*>(workspace);
+  sy.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 64);
+  sy.nflags = nflags;
+  {  // k interleave of the down-projection shares: stride ~ num_kb / golden ratio, coprime with num_kb, and its inverse
+    const int n = a2.num_kb;
+    auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
+    int ks = int(n * 0.6180339887 + 0.5);
+    if (ks < 1) ks = 1;
+    while (gcd(ks, n) != 1) ++ks;
+    ks %= n;
+    if (n == 1) ks = 0;
+    int inv = 0;
+    for (int i = 0; i < n; ++i) if ((long long)i * ks % n == 1 % n) { inv = i; break; }
+    const char* e = getenv("ORON_FFN_KSTRIDE");  // 1: contiguous k ranges (the first version)
+    if (e && atoi(e) == 1) { ks = 1 % n; inv = 1 % n; }
+    sy.kstride = ks;
+    sy.kstride_inv = inv;
+  }
+
+  using Cfg = Gemm2Cfg<256>;
+  const int tiles_m = ((a1.rows_per_batch + GEMM_BM - 1) / GEMM_BM) * a1.nbatch;
+  const long long units = (long long)((tiles_m + 1) / 2) * ((a1.N / 256) * (long long)a1.num_kb + ((a2.N + 255) / 256) * (long long)a2.num_kb);
+  long long pairs = units;
+  const int cap = (up->max_ctas > 0 ? up->max_ctas : num_sms()) / 2;  // co-residency: never more CTAs than SMs
+  if (pairs > cap) pairs = cap;
+  if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+  if (pairs <= 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t le;
+  if (up->act == ACT_GELU_TANH) {
+    auto kern = ffn2_bf16_tcgen05_kernel<ACT_GELU_TANH>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+      if (e != cudaSuccess) return fail(int(e), "ffn smem attribute: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    le = launch_pdl(kern, dim3(unsigned(2 * pairs)), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta1, tb1, ta2, tb2, a1, a2, sy);
+  } else {
+    auto kern = ffn2_bf16_tcgen05_kernel<ACT_NONE>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+      if (e != cudaSuccess) return fail(int(e), "ffn smem attribute: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    le = launch_pdl(kern, dim3(unsigned(2 * pairs)), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta1, tb1, ta2, tb2, a1, a2, sy);
+  }
+  if (le != cudaSuccess) return fail(int(le), "ffn launch: %s", cudaGetErrorString(le));
+  return check_launch("ffn2_bf16_tcgen05");
 }
 
 // ---------------------------------------------------------------------------

@@ -75,6 +75,12 @@ struct GemmArgs {
 };
 
 #define ORON_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ORON_STAMP_NS(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = global_ns(); } while (0)
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -422,7 +428,8 @@ __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmArgs& args, con
   }
 }
 
-template <int BN, int EPI, int HN>
+// FACT >= 0 (EPI_BF16 only): the activation is a compile-time choice, so only that body is instantiated (ffn_tcgen05.cuh)
+template <int BN, int EPI, int HN, int FACT = -1>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const uint32_t trow, const int b,
                                                    const int t_base, const int n0, const int cbeg,
                                                    const uint32_t stage, const int lane, const EpiCols<HN>& pc) {
@@ -513,7 +520,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
       __syncwarp();
       const int col = n0 + c0 + c4;
       if (rows_full && (n0 + c0 + 32 <= N)) {
-        if constexpr (EPI == EPI_BF16) {
+        if constexpr (EPI == EPI_BF16 && FACT >= 0) {
+          epi_block_fast<EPI, FACT>(args, sp, row0 + rsub, col, b4, g4, t_base + rsub, seq_len);
+        } else if constexpr (EPI == EPI_BF16) {
           switch (args.act) {  // hoisted out of the row loop: one straight-line body per activation
             case ACT_GELU_TANH: epi_block_fast<EPI, ACT_GELU_TANH>(args, sp, row0 + rsub, col, b4, g4, t_base + rsub, seq_len); break;
             case ACT_GELU_ERF: epi_block_fast<EPI, ACT_GELU_ERF>(args, sp, row0 + rsub, col, b4, g4, t_base + rsub, seq_len); break;

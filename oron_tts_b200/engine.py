@@ -27,6 +27,12 @@ from . import _lib as L
 # of a run depends on arrival order): 39.8 -> 33.8 us per call. The out-projection (K = dim) is too short to gain
 # (21.5 -> 23.6 us). ORON_STREAM_K=0 restores whole tiles.
 STREAM_K = os.environ.get("ORON_STREAM_K", "1") != "0"
+# FeedForward up + down projection as one persistent launch (csrc/ffn_tcgen05.cuh, oron_ffn_bf16): both phases share one
+# equal split of k-block units over the SM pairs and the down-projection starts per H tile. Measured at config 2
+# (tools/kernel_bench.py ffn, sustained): 50.9-62 us per block against 55.0-55.6 us for the two launches, run-to-run
+# unstable (the main loop is bound by the 64 B/clk per-SM TMA ingest and by the power cap, not by the
+# launch boundary), so it stays opt-in: ORON_FFN_FUSED=1.
+FFN_FUSED = os.environ.get("ORON_FFN_FUSED", "0") == "1"
 BF16 = torch.bfloat16
 F32 = torch.float32
 TILE = 128
@@ -223,6 +229,8 @@ class Workspace:
         with torch.inference_mode(False):
             self.attn_ws = torch.zeros(int(L.lib().oron_attention_workspace_bytes(nbp, tpad, w.heads)), dtype=torch.uint8, device=dev)
         self.hid = z(R, w.ff_dim, dt=BF16)
+        with torch.inference_mode(False):
+            self.ffn_ws = L.ffn_workspace(tpad, nbp, w.ff_dim, dev)
         self.v = z(R, M)
         self.vg = z(Rb, M)
         self.step = z(1, dt=torch.int32)
@@ -372,11 +380,14 @@ class DiTEngine:
                    mask_rows=True, block_n=bn_big, two_sm=True, **common)  # K = dim: too short for stream-K to pay
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
-            L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
-                   block_n=bn_big, two_sm=True, **common)
-            L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
-                   gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                   block_n=bn_big, two_sm=True, stream_k=STREAM_K and not self.deterministic, **common)
+            fused = FFN_FUSED and STREAM_K and not self.deterministic and bn_big == 256 and w.ff_dim % 256 == 0
+            up = L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
+                        block_n=bn_big, two_sm=True, desc_only=fused, **common)
+            down = L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
+                          gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
+                          block_n=bn_big, two_sm=True, stream_k=STREAM_K and not self.deterministic, desc_only=fused, **common)
+            if fused:
+                L.ffn(up, down, ws.ffn_ws)
         o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
         L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o:], shift=tab[o + D:], mod_ld=mld, mod_nb=mod_nb,
                       step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)

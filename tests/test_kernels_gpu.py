@@ -556,3 +556,41 @@ def test_gemm_stream_k(L, nb, T, N, K, bn):
                mask_rows=True, block_n=bn, two_sm=True, stream_k=True)
         assert _rel(x, ref) < 2e-3
         assert torch.equal(x[~mask.squeeze(1)], x0[~mask.squeeze(1)])
+
+
+@pytest.mark.parametrize("nb,T,D,F", [(2, 1408, 1024, 4096), (1, 130, 512, 1024), (3, 640, 1024, 2048), (1, 1408, 256, 512)])
+def test_ffn_fused(L, nb, T, D, F):
+    """FeedForward in one launch (oron_ffn_bf16) against fp32 torch and against the two separate launches: config-2 shape,
+    an odd m-tile count (phantom tile), more phase-1 tiles than three waves, and fewer units than SM pairs. Replayed three
+    times on one workspace: the kernel must leave its flags zeroed."""
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(M + D + F)
+    A = _bf(torch.randn(M, D, device=DEV, generator=g))
+    W1 = _bf(torch.randn(F, D, device=DEV, generator=g) / math.sqrt(D))
+    W2 = _bf(torch.randn(D, F, device=DEV, generator=g) / math.sqrt(F))
+    b1 = torch.randn(F, device=DEV, generator=g) * 0.1
+    b2 = torch.randn(D, device=DEV, generator=g) * 0.1
+    gate = torch.randn(D, device=DEV, generator=g)
+    x0 = torch.randn(M, D, device=DEV, generator=g)
+    h_ref = _bf(torch.nn.functional.gelu(A.float() @ W1.float().t() + b1, approximate="tanh"))
+    ref = x0 + gate * (h_ref.float() @ W2.float().t() + b2)
+    ws = L.ffn_workspace(T, nb, F, DEV)
+    hid = torch.empty(M, F, device=DEV, dtype=torch.bfloat16)
+    for _ in range(3):
+        x = x0.clone()
+        hid.zero_()
+        up = L.gemm(A, W1, hid, epilogue=L.EPI_BF16, bias=b1, act=L.ACT_GELU_TANH, rows_per_batch=T, nbatch=nb, block_n=256,
+                    two_sm=True, desc_only=True)
+        dn = L.gemm(hid, W2, x, epilogue=L.EPI_GATE_RESID, bias=b2, gate=gate, rows_per_batch=T, nbatch=nb, block_n=256,
+                    two_sm=True, desc_only=True)
+        L.ffn(up, dn, ws)
+        torch.cuda.synchronize()
+        assert _rel(hid.float(), h_ref.float()) < 6e-3
+        assert _rel(x, ref) < 3e-3
+        assert int(ws.view(torch.int32).abs().sum()) == 0
+    # the two-launch path computes the same thing
+    x2, hid2 = x0.clone(), torch.empty_like(hid)
+    L.gemm(A, W1, hid2, epilogue=L.EPI_BF16, bias=b1, act=L.ACT_GELU_TANH, rows_per_batch=T, nbatch=nb, block_n=256, two_sm=True)
+    L.gemm(hid2, W2, x2, epilogue=L.EPI_GATE_RESID, bias=b2, gate=gate, rows_per_batch=T, nbatch=nb, block_n=256, two_sm=True)
+    assert torch.equal(hid, hid2)
+    assert _rel(x, x2) < 1e-5

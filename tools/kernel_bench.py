@@ -155,3 +155,77 @@ if what in ("ln", "all"):
     w, c = timeit(fn), timeit(fn, cold=True)
     byt = R * 1024 * 6
     print(f"ln_modulate R=2816 C=1024: warm {w:.1f} us ({byt / w / 1e3:.0f} GB/s) cold {c:.1f} us ({byt / c / 1e3:.0f} GB/s)")
+if what in ("ffn",):
+    # FeedForward of one DiTBlock at config 2: two launches (up-projection + stream-K down-projection) against the fused launch,
+    # 22 per CUDA-graph replay with 22 distinct weight sets (as in the ODE step: weights stream from HBM), sustained clocks
+    import time
+    g = torch.Generator(device=DEV).manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    A1 = rnd(R, 1024).bfloat16()
+    hid = torch.empty(R, 4096, device=DEV, dtype=torch.bfloat16)
+    xres = rnd(R, 1024)
+    gate = rnd(1024) * 0.01
+    W1 = [(rnd(4096, 1024) / 32).bfloat16() for _ in range(22)]
+    W2 = [(rnd(1024, 4096) / 64).bfloat16() for _ in range(22)]
+    b1, b2 = rnd(4096), rnd(1024)
+    fws = L.ffn_workspace(T, 2, 4096, DEV)
+    stamps = None
+    def layer(i, fused, sk=True):
+        up = L.gemm(A1, W1[i], hid, epilogue=L.EPI_BF16, bias=b1, act=L.ACT_GELU_TANH, rows_per_batch=T, nbatch=2, block_n=256,
+                    two_sm=True, desc_only=fused, debug_stamps=stamps if fused else None)
+        dn = L.gemm(hid, W2[i], xres, epilogue=L.EPI_GATE_RESID, bias=b2, gate=gate, rows_per_batch=T, nbatch=2, block_n=256,
+                    two_sm=True, stream_k=sk, desc_only=fused)
+        if fused:
+            L.ffn(up, dn, fws)
+    fl = 2 * R * 1024 * 4096 * 2
+    if NCU:
+        for i in range(2):
+            layer(i, False, True)
+            layer(i, True, True)
+        torch.cuda.synchronize()
+        sys.exit(0)
+    same = "--same-weights" in sys.argv  # every layer reads the same (L2-resident) weights: is the main loop slowed by HBM-cold operands?
+    for name, fused, sk in (("two launches (stream-K down)", False, True), ("two launches (whole tiles)", False, False), ("fused launch", True, True)):
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            for i in range(3): layer(i, fused, sk)
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=s_):
+                for i in range(22): layer(0 if same else i, fused, sk)
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                for _ in range(20): gph.replay()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_)
+            for _ in range(50): gph.replay()
+            e1.record(s_)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (22 * 50)
+        print(f"FFN {name}: {us:.1f} us per block = {fl / us / 1e6:.1f} TFLOP/s", flush=True)
+    if "--trace" in sys.argv:
+        # per-CTA stamps of three launches inside a sustained run (clock64 deltas per CTA, globaltimer across CTAs)
+        stamps_all = torch.zeros(22, 148, 16, device=DEV, dtype=torch.int64)
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=s_):
+                for i in range(22):
+                    stamps = stamps_all[i]
+                    layer(i, True)
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                for _ in range(20): gph.replay()
+                torch.cuda.synchronize()
+        st_all = stamps_all.cpu()
+        for li in (10, 11):
+            st = st_all[li]
+            ns0 = int(st[:, 11].min())
+            print(f"launch {li}: start spread {int(st[:,11].max())-ns0} ns, phase-2 first load {int(st[:,13].min())-ns0}..{int(st[:,13].max())-ns0} ns, "
+                  f"end {int(st[:,12].min())-ns0}..{int(st[:,12].max())-ns0} ns; next launch starts {int(st_all[li+1][:,11].min())-ns0} ns")
+            cyc = (st[:, 10] - st[:, 0]).float()
+            print(f"  cycles per CTA start->end: mean {cyc.mean():.0f} max {cyc.max():.0f}; clock = {float(cyc.max()) / (int(st[:,12].max())-ns0) :.3f} GHz")
+            for c in (0, 2, 54, 56, 100, 146):
+                r = st[c]
+                print(f"  cta {c:3d}: p2-first-load {int(r[2]-r[0]):6d} loads-done {int(r[3]-r[0]):6d} mma-p2-start {int(r[14]-r[0]):6d} mma-done {int(r[4]-r[0]):6d} end {int(r[10]-r[0]):6d} | "
+                      f"producer waits: empty p1 {int(r[1]):6d} p2 {int(r[9]):6d} flags {int(r[8]):6d} | mma waits: full p1 {int(r[5]):6d} p2 {int(r[6]):6d} tempty {int(r[7]):6d}")
