@@ -346,6 +346,7 @@ extern "C" int oron_ffn_bf16(const oron_gemm_desc* up, const oron_gemm_desc* dow
   sy.done = reinterpret_cast<int*>(workspace);
   sy.flags = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 64);
   sy.nflags = nflags;
+  { const char* e = getenv("ORON_FFN_MODE"); sy.mode = e ? atoi(e) : 0; }
   {  // k interleave of the down-projection shares: stride ~ num_kb / golden ratio, coprime with num_kb, and its inverse
     const int n = a2.num_kb;
     auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };

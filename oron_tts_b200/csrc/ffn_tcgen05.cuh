@@ -25,6 +25,7 @@ struct FfnSync {
   int* done;    // [1] CTAs that have left
   int* flags;   // [tiles_m_padded * tiles_n1]
   int nflags;
+  int mode;                  // experiment knob (ORON_FFN_MODE): bit 0 = no fence.proxy.async, bit 1 = no fence.acq_rel.gpu after the polls
   int kstride, kstride_inv;  // phase-2 k interleave: position j of a tile's unit list holds k-block (j * kstride) % num_kb2
 };
 
@@ -194,8 +195,8 @@ ffn2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
 #pragma unroll
             for (int i = 0; i < 8; ++i) m |= (v[i] >= GEMM_EPI_WARPS ? 1u : 0u) << (f0 + i);
           }
-          fence_acq_rel_gpu();
-          fence_proxy_async_all();
+          if (!(sync.mode & 2)) fence_acq_rel_gpu();
+          if (!(sync.mode & 1)) fence_proxy_async_all();
           return m;
         };
         if (w.phase) {
@@ -213,7 +214,7 @@ ffn2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
               const long long c0 = tr ? clock64() : 0;
               flag_wait(frow + f, GEMM_EPI_WARPS);
               ready = f < 32 ? (snapshot() | (1u << f)) : 0u;  // (the snapshot also crosses to the async proxy)
-              if (f >= 32) fence_proxy_async_all();
+              if (f >= 32 && !(sync.mode & 1)) fence_proxy_async_all();
               if (tr) w_flag += clock64() - c0;
             }
           }

@@ -97,13 +97,35 @@ class DiTWeights:
         self.depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("transformer_blocks."))
         tb = [int(k.split(".")[2]) for k in sd if k.startswith("text_embed.text_blocks.")]
         self.conv_layers = (1 + max(tb)) if tb else 0
-        self.dim_head = 2 * sd["rotary_embed.inv_freq"].shape[0]
-        self.heads = D // self.dim_head
-        if self.dim_head != 64:
-            raise NotImplementedError("the sm_100a attention kernel is specialised for head_dim 64")
-        if D % 128 or C % 32:
-            raise NotImplementedError("dim must be a multiple of 128 and text_dim a multiple of 32")
-        self.inv_freq = f32(sd["rotary_embed.inv_freq"])
+        self.dim_head = dh = 2 * sd["rotary_embed.inv_freq"].shape[0]
+        self.heads = H = sd["transformer_blocks.0.attn.to_q.weight"].shape[0] // dh
+        # The attention kernel and the RoPE epilogue work on 64-wide heads (pairs (i, i + 32)). Narrower heads (the
+        # reference's own test configuration has 2 heads of 32, tests/test_checkpoint.py:9-24) are zero-padded to 64 when the
+        # weights are packed: channel c of a head goes to slot c (c < dh/2) or 32 + c - dh/2, so the rotate-half partner
+        # (c, c + dh/2) of modules.py:92-104 sits 32 slots away, q and k are permuted alike (q.k unchanged), the padded q / k /
+        # v channels are exact zeros and the out-projection reads zero columns for them. The softmax scale stays 1/sqrt(dh).
+        if dh > 64 or dh % 2:
+            raise NotImplementedError("the sm_100a attention kernel handles head_dim <= 64 (even)")
+        if D % 32 or C % 32:
+            raise NotImplementedError("dim and text_dim must be multiples of 32")
+        self.inner = H * 64  # padded attention width
+        half = dh // 2
+        slot = torch.cat([torch.arange(half), 32 + torch.arange(half)])  # slot of channel c inside its 64-wide head
+        self._head_rows = (torch.arange(H)[:, None] * 64 + slot[None, :]).reshape(-1).to(device)  # [H * dh] -> padded row
+
+        def pad_rows(t):  # [H * dh, ...] -> [H * 64, ...]
+            if dh == 64:
+                return t
+            out = torch.zeros(self.inner, *t.shape[1:], device=t.device, dtype=t.dtype)
+            out[self._head_rows.to(t.device)] = t
+            return out
+
+        def pad_cols(t):  # [n, H * dh] -> [n, H * 64]
+            return t if dh == 64 else pad_rows(t.t()).t()
+
+        inv = torch.zeros(32)
+        inv[:half] = sd["rotary_embed.inv_freq"].detach().float().cpu()
+        self.inv_freq = inv.to(device)
 
         # timestep MLP (modules.py:54-58)
         self.t0_w, self.t0_b = bf(sd["time_embed.time_mlp.0.weight"]), f32(sd["time_embed.time_mlp.0.bias"])
@@ -157,9 +179,11 @@ class DiTWeights:
         for i in range(self.depth):
             p = f"transformer_blocks.{i}."
             self.blocks.append(dict(
-                wqkv=bf(torch.cat([sd[p + "attn.to_q.weight"], sd[p + "attn.to_k.weight"], sd[p + "attn.to_v.weight"]], 0)),
-                bqkv=f32(torch.cat([sd[p + "attn.to_q.bias"], sd[p + "attn.to_k.bias"], sd[p + "attn.to_v.bias"]], 0)),
-                wo=bf(sd[p + "attn.to_out.0.weight"]), bo=f32(sd[p + "attn.to_out.0.bias"]),
+                wqkv=bf(torch.cat([pad_rows(sd[p + "attn.to_q.weight"]), pad_rows(sd[p + "attn.to_k.weight"]),
+                                   pad_rows(sd[p + "attn.to_v.weight"])], 0)),
+                bqkv=f32(torch.cat([pad_rows(sd[p + "attn.to_q.bias"]), pad_rows(sd[p + "attn.to_k.bias"]),
+                                    pad_rows(sd[p + "attn.to_v.bias"])], 0)),
+                wo=bf(pad_cols(sd[p + "attn.to_out.0.weight"])), bo=f32(sd[p + "attn.to_out.0.bias"]),
                 w1=bf(sd[p + "ff.ff.0.weight"]), b1=f32(sd[p + "ff.ff.0.bias"]),
                 w2=bf(sd[p + "ff.ff.3.weight"]), b2=f32(sd[p + "ff.ff.3.bias"]),
             ))
@@ -222,8 +246,8 @@ class Workspace:
         self.c1 = z(R, D, dt=BF16)
         self.xres = z(R, D)
         self.nrm = z(R, D, dt=BF16)
-        self.qkv = z(R, 3 * D, dt=BF16)
-        self.ao = z(R, D, dt=BF16)
+        self.qkv = z(R, 3 * w.inner, dt=BF16)
+        self.ao = z(R, w.inner, dt=BF16)
         # Workspace of the balanced attention schedule (plan + partial results of the items split between two CTAs);
         # planned in `DiTEngine` once the sequence lengths of the call are known (attention_plan).
         with torch.inference_mode(False):
@@ -372,7 +396,7 @@ class DiTEngine:
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
-                   rope_cols=2 * D, f16_from_col=2 * D, block_n=bn_big, two_sm=True, **common)
+                   rope_cols=2 * w.inner, f16_from_col=2 * w.inner, block_n=bn_big, two_sm=True, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
                         scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],

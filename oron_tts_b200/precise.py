@@ -77,6 +77,8 @@ class PreciseDiT:
         self.depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("transformer_blocks."))
         tb = [int(k.split(".")[2]) for k in sd if k.startswith("text_embed.text_blocks.")]
         self.conv_layers = (1 + max(tb)) if tb else 0
+        if 2 * sd["rotary_embed.inv_freq"].shape[0] != 64:
+            raise NotImplementedError("the fp32 mode handles head_dim 64 only")
         self.heads = D // 64
         self.inv_freq = sd["rotary_embed.inv_freq"].contiguous()
         f = lambda k: sd[k].contiguous()  # noqa: E731

@@ -10,6 +10,7 @@ Outputs (all torch.save files, fp32 / int64):
     mel.pt         log-mel of seeded waveforms through AudioProcessor.mel_spectrogram
     istft.pt       in-repo VocosDecoder (src/models/decoder.py) head activations -> waveform
     dit_tiny.pt    tiny DiT: single forward (cfg_infer), eval loss, 4-step sample with trajectory
+    dit_micro.pt   (--micro) the reference's own test configuration (head_dim 32, dim 64): CFG forward + 3-step sample
     sample_small.pt  BASELINE config 1 (Small, "Сайн байна уу", 32 NFE, CFG 1.5, seed 0)
     sample_base.pt   BASELINE config 2 (Base, 469 + 937 frames, CFG 2.0): teacher-forced velocities and,
                      with --base-full, the free-running final mel
@@ -195,6 +196,31 @@ def gen_dit_tiny() -> dict:
     return out
 
 
+def gen_dit_micro() -> dict:
+    """The reference's own test configuration (tests/test_checkpoint.py:9-24: dim 64, 2 heads of 32, text_dim 32, ff_mult 2):
+    batched CFG forward with ragged lengths and a 3-step CFG sample."""
+    model = build("micro")
+    gen = torch.Generator().manual_seed(11)
+    B, T = 2, 140
+    lens = torch.tensor([140, 77])
+    x = torch.randn(B, T, 100, generator=gen)
+    cond = torch.randn(B, T, 100, generator=gen) * (torch.arange(T)[None, :, None] < 30)
+    text = torch.randint(4, 65, (B, T), generator=gen)
+    text[0, 100:] = -1
+    text[1, 77:] = -1
+    time = torch.tensor([0.2, 0.7])
+    mask = torch.arange(T)[None, :] < lens[:, None]
+    bb = model.cfm.backbone
+    out = dict(x=x, cond=cond, text=text, time=time, lens=lens)
+    out["fwd_cfg"] = bb(x, cond, text, time, mask=mask, cfg_infer=True)
+    ids = torch.randint(4, 65, (1, 120), generator=gen)
+    refmel = torch.randn(1, 40, 100, generator=gen) * 1.5 - 3
+    mel, traj = model.cfm.sample(refmel, ids, torch.tensor([120]), lens=torch.tensor([40]), steps=3, cfg_strength=2.0,
+                                 sway_sampling_coef=-1.0, seed=7)
+    out["s_ref"], out["s_ids"], out["s_traj"], out["s_mel"] = refmel, ids, torch.stack(traj), mel
+    return out
+
+
 def gen_sample_small() -> dict:
     model = build("small")
     tc = TextCleaner()
@@ -248,6 +274,10 @@ def gen_state_keys() -> dict:
 
 
 if __name__ == "__main__":
+    if "--micro" in sys.argv:
+        torch.save(gen_dit_micro(), os.path.join(HERE, "dit_micro.pt"))
+        print("dit_micro written")
+        sys.exit(0)
     if "--keys" in sys.argv:
         torch.save(gen_state_keys(), os.path.join(HERE, "state_keys.pt"))
         print("state_keys written")

@@ -48,7 +48,9 @@ def fill_state_dict(reference_sd: dict, seed: int) -> dict:
 
 CONFIGS = {
     "tiny": {"model": dict(dim=128, depth=2, heads=2, text_dim=64, conv_layers=2)},
+    # the reference's own test configuration (tests/test_checkpoint.py:9-24): head_dim 32, dim 64, text_dim 32
+    "micro": {"model": dict(vocab_size=65, dim=64, depth=1, heads=2, ff_mult=2, text_dim=32, conv_layers=1)},
     "small": {"model": dict(dim=512, depth=12, heads=8, text_dim=256, conv_layers=4)},
     "base": {"model": dict(dim=1024, depth=22, heads=16, text_dim=512, conv_layers=4)},
 }
-SEEDS = {"tiny": 1234, "small": 1234, "base": 1234}
+SEEDS = {"tiny": 1234, "micro": 1234, "small": 1234, "base": 1234}

@@ -33,14 +33,16 @@ def ref_state_dict(name: str) -> dict:
         proto[k] = torch.empty(shape)
     # inv_freq is a buffer that keeps its constructor value (modules.py:73)
     sd = GW.fill_state_dict(proto, GW.SEEDS[name])
-    sd["cfm.backbone.rotary_embed.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
+    mc = GW.CONFIGS[name]["model"]
+    dh = mc["dim"] // mc["heads"]
+    sd["cfm.backbone.rotary_embed.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, dh, 2).float() / dh))
     return sd
 
 
 def test_state_dict_layout_matches_reference():
     """Checkpoint contract: identical keys and shapes for every BASELINE config."""
     keys = _gold("state_keys.pt")
-    for name in ("tiny", "small"):
+    for name in ("tiny", "micro", "small"):
         mine = {k: tuple(v.shape) for k, v in F5TTS.from_config(GW.CONFIGS[name]).state_dict().items()}
         assert mine == keys[name], name
     with torch.device("meta"):
@@ -60,6 +62,19 @@ def test_oracle_dit_forward_and_loss():
     assert _rel(out, g["fwd_drop"]) < 2e-5
     out = DO.dit_forward(sd, g["x"][:1], g["cond"][:1], g["text"][:1], torch.tensor(0.5))
     assert _rel(out, g["fwd_nomask_scalar_t"]) < 2e-5
+
+
+def test_oracle_micro_reference_test_config():
+    """The reference's own test configuration (tests/test_checkpoint.py:9-24): 2 heads of 32, dim 64, text_dim 32, ff_mult 2."""
+    g = _gold("dit_micro.pt")
+    sd = ref_state_dict("micro")
+    T = g["x"].shape[1]
+    mask = torch.arange(T)[None, :] < g["lens"][:, None]
+    out = DO.dit_forward(sd, g["x"], g["cond"], g["text"], g["time"], mask, cfg_infer=True)
+    assert _rel(out, g["fwd_cfg"]) < 2e-5
+    mel, traj = DO.cfm_sample(sd, g["s_ref"], g["s_ids"], torch.tensor([120]), lens=torch.tensor([40]), steps=3,
+                              cfg_strength=2.0, sway_sampling_coef=-1.0, seed=7)
+    assert _rel(torch.stack(traj), g["s_traj"]) < 2e-5 and _rel(mel, g["s_mel"]) < 2e-5
 
 
 def test_oracle_sample_tiny():

@@ -43,7 +43,9 @@ def _rel(a, b):
 def ref_state_dict(name):
     keys = _gold("state_keys.pt")[name]
     sd = GW.fill_state_dict({k: torch.empty(s) for k, s in keys.items()}, GW.SEEDS[name])
-    sd["cfm.backbone.rotary_embed.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
+    mc = GW.CONFIGS[name]["model"]
+    dh = mc["dim"] // mc["heads"]
+    sd["cfm.backbone.rotary_embed.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, dh, 2).float() / dh))
     return sd
 
 
@@ -81,6 +83,28 @@ def test_dit_forward_tiny_vs_golden():
         assert _rel(out[i, : lens[i]], g["fwd_drop"][i, : lens[i]]) < VEL_TOL
     out = bb(args[0][:1], args[1][:1], args[2][:1], torch.tensor(0.5, device=DEV))
     assert _rel(out, g["fwd_nomask_scalar_t"]) < VEL_TOL
+
+
+def test_reference_test_config_head_dim_32():
+    """The reference's own test configuration (tests/test_checkpoint.py:9-24: dim 64, 2 heads of 32, text_dim 32, ff_mult 2):
+    heads are zero-padded to the kernels' 64-wide layout when the weights are packed (engine.DiTWeights). Batched CFG forward
+    with ragged lengths and a 3-step CFG sample against fixtures recorded from the live reference (dit_micro.pt)."""
+    g = _gold("dit_micro.pt")
+    m = model_for("micro")
+    bb = m.cfm.backbone
+    T = g["x"].shape[1]
+    mask = (torch.arange(T)[None, :] < g["lens"][:, None]).to(DEV)
+    out = bb(*[g[k].to(DEV) for k in ("x", "cond", "text", "time")], mask=mask, cfg_infer=True)
+    assert out.shape == g["fwd_cfg"].shape
+    lens = g["lens"].tolist()
+    for i in range(4):
+        n = lens[i % 2]
+        assert _rel(out[i, :n], g["fwd_cfg"][i, :n]) < VEL_TOL, i
+    mel, traj = m.cfm.sample(g["s_ref"].to(DEV), g["s_ids"].to(DEV), torch.tensor([120], device=DEV),
+                             lens=torch.tensor([40], device=DEV), steps=3, cfg_strength=2.0, sway_sampling_coef=-1.0,
+                             y0=g["s_traj"][0])
+    assert _rel(mel, g["s_mel"]) < MEL_TOL
+    assert torch.equal(mel[:, :40].cpu(), g["s_ref"])
 
 
 def test_eval_loss_tiny():

@@ -14,6 +14,8 @@ DEV = "cuda"
 NCU = "--ncu" in sys.argv
 what = next((a for a in sys.argv[1:] if not a.startswith("--")), "all")
 R, D, T = 2816, 1024, 1408
+if "--short" in sys.argv:  # a 1.5 s utterance with CFG: 2 x 256 padded rows
+    R, T = 512, 256
 flush = torch.empty(256 * 1024 * 1024, device=DEV, dtype=torch.uint8)
 
 
