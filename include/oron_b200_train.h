@@ -109,6 +109,12 @@ int oron_skinny_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx
 int oron_gconv_wgrad(const void* x_bf16, int64_t ldx, const void* dy_bf16, int64_t lddy, int32_t rows_per_batch,
                      int32_t nbatch, int32_t C, int32_t cg, int32_t taps, const int32_t* seq_lens, float* dw,
                      float* db, oron_stream_t stream);
+/* Same gradient on the tensor core (tcgen05, operands read MN-major as stored; csrc/gconv_wgrad_tcgen05.cuh): dw += ...
+ * Needs C % 128 == 0, cg dividing 64, rows_per_batch % 64 == 0, and rows t >= seq_len of x and dy already ZERO (no seq_lens
+ * argument: the forward masks x, oron_act_bwd zeroes dy). No bias gradient: use oron_colsum_bf16 on dy. */
+int oron_gconv_wgrad_tc(const void* x_bf16, int64_t ldx, const void* dy_bf16, int64_t lddy, int32_t rows_per_batch,
+                        int32_t nbatch, int32_t C, int32_t cg, int32_t taps, float* dw, oron_stream_t stream);
+
 
 /* Masked MSE of CFM.forward (flow.py:156-159) and its gradient:
  *   loss_sum += sum_{rows with span[r]} sum_c (pred - flow)^2 ;  dpred[r, c] = span[r] ? 2 (pred - flow) / (count * n_mels) : 0

@@ -14,7 +14,7 @@ BF16, F32 = torch.bfloat16, torch.float32
 TRAIN_SYMBOLS = (
     "oron_transpose_bf16", "oron_ln_bwd", "oron_act_fwd", "oron_act_bwd", "oron_gate_resid", "oron_gate_bwd",
     "oron_dwconv7", "oron_dwconv7_wgrad", "oron_grn_bwd_reduce", "oron_grn_bwd_coef", "oron_grn_bwd_apply",
-    "oron_text_embed_bwd", "oron_skinny_dgrad", "oron_skinny_wgrad", "oron_gconv_wgrad", "oron_cfm_loss", "oron_sumsq",
+    "oron_text_embed_bwd", "oron_skinny_dgrad", "oron_skinny_wgrad", "oron_gconv_wgrad", "oron_gconv_wgrad_tc", "oron_cfm_loss", "oron_sumsq",
     "oron_adamw_clip", "oron_f16_to_bf16", "oron_attention_bwd", "oron_mask_rows_f32", "oron_attention_fwd_lse", "oron_colsum_bf16",
 )
 
@@ -35,6 +35,7 @@ _ARGTYPES = {
     "oron_skinny_dgrad": [_P, _L, _I, _I, _P, _L, _I, _P, _L, _P],
     "oron_skinny_wgrad": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _I, _P],
     "oron_gconv_wgrad": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "oron_gconv_wgrad_tc": [_P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P],
     "oron_cfm_loss": [_P, _L, _P, _P, _P, _L, _I, _P, _P, _L, _P],
     "oron_sumsq": [_P, _L, _P, _P],
     "oron_adamw_clip": [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P],
@@ -173,6 +174,12 @@ def gconv_wgrad(x: torch.Tensor, dy: torch.Tensor, *, rows_per_batch: int, nbatc
     _check(tlib().oron_gconv_wgrad(_ptr(x, BF16, "x"), _ld(x), _ptr(dy, BF16, "dy"), _ld(dy), rows_per_batch, nbatch,
                                    x.shape[1], cg, taps, _ptr(seq_lens, torch.int32, "seq_lens"), _ptr(dw, F32, "dw"),
                                    _ptr(db, F32, "db"), _stream()), "oron_gconv_wgrad")
+
+
+def gconv_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, *, rows_per_batch: int, nbatch: int, cg: int, taps: int, dw: torch.Tensor) -> None:
+    """Tensor-core variant: dw += ...; rows beyond each sequence's length must already be zero in x and dy; no bias gradient."""
+    _check(tlib().oron_gconv_wgrad_tc(_ptr(x, BF16, "x"), _ld(x), _ptr(dy, BF16, "dy"), _ld(dy), rows_per_batch, nbatch,
+                                      x.shape[1], cg, taps, _ptr(dw, F32, "dw"), _stream()), "oron_gconv_wgrad_tc")
 
 
 def cfm_loss(pred: torch.Tensor, flow: torch.Tensor, span: torch.Tensor, count: torch.Tensor, loss_sum: torch.Tensor,

@@ -5,6 +5,7 @@
 
 #include "../../include/oron_b200_train.h"
 #include "attn_bwd_tcgen05.cuh"
+#include "gconv_wgrad_tcgen05.cuh"
 #include "host_util.h"
 #include "train_rowwise.cuh"
 
@@ -301,6 +302,40 @@ extern "C" int oron_gconv_wgrad(const void* x_bf16, int64_t ldx, const void* dy_
   dim3 grid(unsigned(((C + 63) / 64) * taps), unsigned(nbatch));
   gconv_wgrad_kernel<<<grid, 256, 0, ST(stream)>>>(a);
   return check_launch("gconv_wgrad");
+}
+
+// tensor-core variant (gconv_wgrad_tcgen05.cuh): dw += ..., no bias gradient (use oron_colsum_bf16), rows beyond each
+// sequence's length must already be zero in x and dy
+extern "C" int oron_gconv_wgrad_tc(const void* x_bf16, int64_t ldx, const void* dy_bf16, int64_t lddy, int32_t rows_per_batch,
+                                   int32_t nbatch, int32_t C, int32_t cg, int32_t taps, float* dw, oron_stream_t stream) {
+  if (!x_bf16 || !dy_bf16 || !dw) return fail(ORON_ERR_BAD_ARG, "gconv_wgrad_tc: null pointer");
+  if (cg <= 0 || 64 % cg != 0 || C % 128 != 0 || taps <= 0 || rows_per_batch <= 0 || rows_per_batch % 64 != 0 || nbatch <= 0)
+    return fail(ORON_ERR_UNSUPPORTED, "gconv_wgrad_tc: needs C %% 128 == 0, a group width dividing 64 and rows_per_batch %% 64 == 0");
+  CUtensorMap tx, tdy;
+  int rc = make_tmap_bf16(&tx, x_bf16, uint64_t(C), uint64_t(rows_per_batch), uint64_t(nbatch), uint64_t(ldx),
+                          uint64_t(ldx) * uint64_t(rows_per_batch), 64, 3);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tdy, dy_bf16, uint64_t(C), uint64_t(rows_per_batch), uint64_t(nbatch), uint64_t(lddy),
+                      uint64_t(lddy) * uint64_t(rows_per_batch), 64, 3);
+  if (rc) return rc;
+  GconvTcArgs a;
+  a.C = C; a.cg = cg; a.taps = taps; a.pad = taps / 2;
+  a.kb_per_batch = rows_per_batch / 64;
+  a.kb_total = a.kb_per_batch * nbatch;
+  const int gx = C / 128, gy = (taps + GCW_TAPS - 1) / GCW_TAPS;
+  int nchunk = (2 * num_sms() + gx * gy - 1) / (gx * gy);  // about two CTAs' worth of work per SM
+  if (nchunk > a.kb_total) nchunk = a.kb_total;
+  if (nchunk < 1) nchunk = 1;
+  a.nchunk = nchunk;
+  a.dw = dw;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gconv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GCW_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(int(e), "gconv_wgrad_tc smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  gconv_wgrad_tc_kernel<<<dim3(gx, gy, nchunk), GCW_THREADS, GCW_SMEM_BYTES, ST(stream)>>>(tx, tdy, a);
+  return check_launch("gconv_wgrad_tc");
 }
 
 extern "C" int oron_cfm_loss(const float* pred, int64_t ldp, const float* flow, const uint8_t* span, const int32_t* count,

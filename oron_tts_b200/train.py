@@ -433,6 +433,17 @@ class TrainEngine:
         # the step zeroed (or keeps accumulating into): `accumulate` needs nothing extra
         L.gemm(dy, x, out, epilogue=L.EPI_F32, block_n=bn, a_mn=True, b_mn=True, two_sm=True, stream_k=True)
 
+    def _gconv_wgrad(self, x, dy, cp, sl, gw, gb, common):
+        """Weight + bias gradient of one ConvPositionEmbedding conv. Tensor-core kernel when the shape allows (dim % 128 == 0;
+        rows beyond each length are zero in x and dy here: the forward masks x, act_bwd zeroes dy); ORON_GCONV_TC=0 keeps the
+        CUDA-core kernel (0.95 ms per conv at config 5)."""
+        C = x.shape[1]
+        if C % 128 == 0 and 64 % cp["cg"] == 0 and common["rows_per_batch"] % 64 == 0 and os.environ.get("ORON_GCONV_TC", "1") != "0":
+            T.gconv_wgrad_tc(x, dy, cg=cp["cg"], taps=cp["taps"], dw=gw, **common)
+            T.colsum(dy, gb)
+        else:
+            T.gconv_wgrad(x, dy, cg=cp["cg"], taps=cp["taps"], seq_lens=sl, dw=gw, db=gb, **common)
+
     def _linear_bwd(self, ws, dy, x_saved, w, gw, gb, dx_out, *, acc=False):
         """Backward of y = x W^T + b for [R, .] activations: bias and weight gradients into the arena, data gradient.
         No transposed copies: the tcgen05 GEMM reads the row-major operands MN-major (oron_gemm_desc.a/b_mn_major)."""
@@ -669,12 +680,10 @@ class TrainEngine:
                                block_n=64, **common)
         gkey = "input_embed.conv_pos_embed.conv1d."
         T.act_bwd(ws.dx, ws.z2, ws.g_d, T.ACT_MISH, rows_per_batch=tpad, seq_lens=sl)
-        T.gconv_wgrad(ws.c1, ws.g_d, cg=c2["cg"], taps=c2["taps"], seq_lens=sl, dw=a.view(G, gkey + "2.weight"),
-                      db=a.view(G, gkey + "2.bias"), **common)
+        self._gconv_wgrad(ws.c1, ws.g_d, c2, sl, a.view(G, gkey + "2.weight"), a.view(G, gkey + "2.bias"), common)
         L.gemm(ws.g_d, t2["w"], ws.g_ao, epilogue=L.EPI_BF16, **conv(t2))
         T.act_bwd(ws.g_ao, ws.z1, ws.g_ao, T.ACT_MISH, rows_per_batch=tpad, seq_lens=sl)
-        T.gconv_wgrad(ws.h0b, ws.g_ao, cg=c1["cg"], taps=c1["taps"], seq_lens=sl, dw=a.view(G, gkey + "0.weight"),
-                      db=a.view(G, gkey + "0.bias"), **common)
+        self._gconv_wgrad(ws.h0b, ws.g_ao, c1, sl, a.view(G, gkey + "0.weight"), a.view(G, gkey + "0.bias"), common)
         L.gemm(ws.g_ao, t1["w"], ws.dx, epilogue=L.EPI_SCALE_RESID, addend=ws.dx, seq_lens=sl, out2=ws.g_d, **conv(t1))
         # -- InputEmbedding.proj (dit.py:53): h0 = [x | cond | text] W^T + b
         Gw = a.view(G, "input_embed.proj.weight")

@@ -246,6 +246,29 @@ def test_gconv_wgrad(C, cg):
     assert _rel(dw, w.grad) < 1e-4 and _rel(db, b.grad) < 1e-4
 
 
+@pytest.mark.parametrize("C,cg,nb,rpb", [(128, 8, 2, 128), (1024, 64, 2, 128), (512, 32, 3, 320), (1024, 64, 8, 1024)])
+def test_gconv_wgrad_tensor_core(C, cg, nb, rpb):
+    """tcgen05 weight gradient of the grouped k = 31 conv against autograd (fp32 conv on the bf16-rounded operands) and the
+    CUDA-core kernel; ragged lengths (rows beyond the length are zero in both operands, as the training step guarantees),
+    accumulation into a non-zero dw, and the config-5 size."""
+    g = torch.Generator(device=DEV).manual_seed(C + nb)
+    taps = 31
+    lens = [rpb if b % 2 == 0 else max(1, rpb - 68) for b in range(nb)]
+    m = _mask(nb, rpb, lens).view(nb, rpb, 1)
+    x = (torch.randn(nb, rpb, C, device=DEV, generator=g) * m).to(BF16)
+    dy = (torch.randn(nb, rpb, C, device=DEV, generator=g) * 0.1 * m).to(BF16)
+    w = torch.zeros(C, cg, taps, device=DEV, requires_grad=True)
+    y = F.conv1d(x.float().transpose(1, 2), w, None, padding=taps // 2, groups=C // cg).transpose(1, 2)
+    (y * dy.float()).sum().backward()
+    dw = torch.full((C, cg, taps), 0.25, device=DEV)
+    T.gconv_wgrad_tc(x.view(-1, C), dy.view(-1, C), rows_per_batch=rpb, nbatch=nb, cg=cg, taps=taps, dw=dw)
+    assert _rel(dw - 0.25, w.grad) < 1e-4
+    dw2 = torch.zeros(C, cg, taps, device=DEV)
+    T.gconv_wgrad(x.view(-1, C), dy.view(-1, C), rows_per_batch=rpb, nbatch=nb, cg=cg, taps=taps,
+                  seq_lens=torch.tensor(lens, device=DEV, dtype=torch.int32), dw=dw2, db=None)
+    assert _rel(dw - 0.25, dw2) < 1e-4
+
+
 def test_cfm_loss():
     g = torch.Generator(device=DEV).manual_seed(9)
     rows, M = 512, 100
