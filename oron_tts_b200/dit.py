@@ -212,7 +212,7 @@ class DiT(nn.Module):
             durations = [int(v) for v in mask.sum(dim=-1).tolist()]
         tpad = _rup(T, TILE)
         ws = eng.workspace(B, B * len(branches), tpad, max(B, 1), False)
-        eng.load_sequences(ws, text=text, durations=durations, seq_len=T, branches=branches)
+        eng.load_sequences(ws, text=text, durations=durations, seq_len=T, branches=branches, text_len=T)
         eng.text_embed(ws)
         cond_in = cond.to(torch.float32)
         eng.static_embed(ws, cond_in, branches)

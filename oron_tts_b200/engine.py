@@ -232,6 +232,7 @@ class Workspace:
         self.drop = z(nbp, dt=torch.uint8)
         self.row_valid = z(R, dt=torch.uint8)
         self.seq_lens = z(nbp, dt=torch.int32)
+        self.text_lens = z(nbp, dt=torch.int32)  # frames the TextEmbedding ConvNeXt blocks / GRN run over (load_sequences)
         self.xt = z(R, C)
         self.xt_n = z(R, C, dt=BF16)
         self.xt_h = z(R, 2 * C, dt=BF16)
@@ -303,8 +304,14 @@ class DiTEngine:
 
     # -------------------------------------------------------------------------------------------
     def load_sequences(self, ws: Workspace, *, text: torch.Tensor, durations: list[int], seq_len: int,
-                       branches: list[Branch]) -> None:
-        """Token ids (+1 shift, crop / 0-pad to seq_len: encoder.py:68-74), drop flags and lengths."""
+                       branches: list[Branch], text_len: int | None = None) -> None:
+        """Token ids (+1 shift, crop / 0-pad to seq_len: encoder.py:68-74), drop flags and lengths.
+
+        ``text_len``: frames the text ConvNeXt blocks / GRN statistics cover. The reference's TextEmbedding runs over the whole
+        padded length of the batch (encoder.py:68-96), so filler rows of shorter sequences enter the GRN norm: DiT.forward and
+        the eval-mode CFM.forward pass ``text_len = seq_len`` and reproduce that. CFM.sample leaves it None = each sequence's
+        own duration, which makes a batched sample equal to the per-utterance calls the reference's synthesize makes (B = 1
+        there, f5tts.py:301-320) whatever the batch composition."""
         nb, tpad = ws.nb, ws.tpad
         ids = (text.to(torch.int64) + 1)[:, :seq_len]
         vocab1 = self.w.text_table.shape[0]
@@ -316,6 +323,7 @@ class DiTEngine:
         drop = [int(br.drop_text) for br in branches for _ in range(nb)]
         ws.drop.copy_(torch.tensor(drop, dtype=torch.uint8), non_blocking=False)
         ws.seq_lens.copy_(torch.tensor(durations * len(branches), dtype=torch.int32))
+        ws.text_lens.copy_(torch.tensor((durations if text_len is None else [int(text_len)] * nb) * len(branches), dtype=torch.int32))
         # schedule of the attention kernel for these lengths (once per call, outside the per-NFE graph)
         L.attention_plan(ws.attn_ws, nbatch=ws.nbp, rows_per_batch=tpad, heads=self.w.heads, seq_lens=ws.seq_lens)
 
@@ -325,11 +333,11 @@ class DiTEngine:
         L.text_embed_front(ws.ids, ws.drop, w.text_table, w.pos_table(ws.tpad), rows_per_batch=ws.tpad, nb=ws.nbp,
                            x=ws.xt, row_valid=ws.row_valid)
         for blk in w.text_blocks:
-            L.dwconv7_ln(ws.xt, rows_per_batch=ws.tpad, nbatch=ws.nbp, seq_lens=ws.seq_lens, w=blk["dw_w"],
+            L.dwconv7_ln(ws.xt, rows_per_batch=ws.tpad, nbatch=ws.nbp, seq_lens=ws.text_lens, w=blk["dw_w"],
                          wb=blk["dw_b"], ln_w=blk["ln_w"], ln_b=blk["ln_b"], eps=1e-6, out=ws.xt_n)
             L.gemm(ws.xt_n, blk["w1"], ws.xt_h, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_ERF,
                    rows_per_batch=ws.tpad, nbatch=ws.nbp, block_n=128)
-            L.grn(ws.xt_h, rows_per_batch=ws.tpad, nb=ws.nbp, seq_lens=ws.seq_lens, gamma=blk["gamma"],
+            L.grn(ws.xt_h, rows_per_batch=ws.tpad, nb=ws.nbp, seq_lens=ws.text_lens, gamma=blk["gamma"],
                   beta=blk["beta"], gx2=ws.gx2)
             L.gemm(ws.xt_h, blk["w2"], ws.xt, epilogue=L.EPI_SCALE_RESID, bias=blk["b2"], rows_per_batch=ws.tpad,
                    nbatch=ws.nbp, addend=ws.xt, row_valid=ws.row_valid,
