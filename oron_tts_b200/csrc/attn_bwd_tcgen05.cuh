@@ -43,9 +43,12 @@ constexpr int AB_TILE = 128;
 constexpr int AB_D = 64;
 constexpr int AB_TILE_BYTES = AB_TILE * AB_D * 2;  // 16 KB
 constexpr int AB_TMEM_COLS = 512;
-// smem: X1 | X2 | Y1[0] Y2[0] | Y1[1] Y2[1] | stageA (2 slabs) | stageB (2 slabs) | barriers + lse/delta staging
-// (the Y tiles of iteration it + 1 are fetched by TMA while iteration it computes)
-constexpr int AB_SMEM_BYTES = 10 * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 8 * 128 * 4 + 1024;
+// smem: X1 | X2 | Y1[0] Y2[0] | Y1[1] Y2[1] | Y1[2] Y2[2] | stageA (2 slabs) | stageB (2 slabs) | barriers + lse/delta staging
+// Three Y buffers: the tiles of iteration it + 2 are fetched at the top of iteration it. With two buffers the fetch of
+// it + 1 could only be issued once the accumulating MMAs of it - 1 had retired, i.e. right before S / dP of it + 1 needed
+// it: the MMA thread sat ~1.2 k cycles per tile in the TMA latency (trace: "issue S/dP(n+1)" 1766 cycles for 8 MMAs).
+constexpr int AB_YBUF = 3;
+constexpr int AB_SMEM_BYTES = (6 + 2 * AB_YBUF) * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 8 * 128 * 4 + 1024;
 
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
 
@@ -104,20 +107,21 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   const uint32_t sX1 = smem_base, sX2 = smem_base + AB_TILE_BYTES;
   auto sY1 = [&](int st) { return smem_base + (2 + 2 * st) * AB_TILE_BYTES; };
   auto sY2 = [&](int st) { return smem_base + (3 + 2 * st) * AB_TILE_BYTES; };
-  const uint32_t sA = smem_base + 6 * AB_TILE_BYTES, sB = smem_base + 8 * AB_TILE_BYTES;
-  const uint32_t bar_base = smem_base + 10 * AB_TILE_BYTES;
+  const uint32_t sA = smem_base + (2 + 2 * AB_YBUF) * AB_TILE_BYTES, sB = smem_base + (4 + 2 * AB_YBUF) * AB_TILE_BYTES;
+  const uint32_t bar_base = smem_base + (6 + 2 * AB_YBUF) * AB_TILE_BYTES;
   // barriers (8 bytes each): x | y0 y1 | s0 s1 | p0 p1 | acc ; then the TMEM slot
-  const uint32_t bar_x = bar_base, bar_acc = bar_base + 56, tmem_slot = bar_base + 64;
-  auto bar_y = [&](int st) { return bar_base + 8u + 8u * uint32_t(st); };
+  const uint32_t bar_x = bar_base, bar_acc = bar_base + 56, tmem_slot = bar_base + 80;
+  auto bar_y = [&](int st) { return st < 2 ? bar_base + 8u + 8u * uint32_t(st) : bar_base + 72u; };
   auto bar_s = [&](int u) { return bar_base + 24u + 8u * uint32_t(u); };   // MMA -> CUDA cores: S_u / dP_u are in TMEM
   auto bar_p = [&](int u) { return bar_base + 40u + 8u * uint32_t(u); };   // CUDA cores -> MMA: S_u / dP_u read, slab u written
-  float* s_stat = reinterpret_cast<float*>(smem_gen + 10 * AB_TILE_BYTES + 128);  // [2][2][128]: buffer, {lse, delta}
+  float* s_stat = reinterpret_cast<float*>(smem_gen + (6 + 2 * AB_YBUF) * AB_TILE_BYTES + 128);  // [2][2][128]: buffer, {lse, delta}
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init(bar_x, 1);
+    mbar_init(bar_y(2), 1);
     for (int u = 0; u < 2; ++u) {
       mbar_init(bar_y(u), 1);
       mbar_init(bar_s(u), 1);
@@ -168,10 +172,10 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         tma_load_3d(sX1, &tmQK, bar_x, HD + h * AB_D, tile * AB_TILE, b);  // K
         tma_load_3d(sX2, &tmV, bar_x, h * AB_D, tile * AB_TILE, b);        // V
       }
-      auto fetch = [&](int it) {  // the Y tiles of iteration `it` into buffer it & 1
+      auto fetch = [&](int it) {  // the Y tiles of iteration `it` into buffer it % 3
         const bool pre = it < n_pre;
         const int j = pre ? it : it - n_pre;
-        const int st = it & 1;
+        const int st = it % AB_YBUF;
         mbar_arrive_expect_tx(bar_y(st), (pre ? 1 : 2) * AB_TILE_BYTES);
         if (MODE == 0) {
           tma_load_3d(sY1(st), &tmQK, bar_y(st), HD + h * AB_D, j * AB_TILE, b);  // K_j
@@ -182,8 +186,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         }
       };
       auto issue_sdp = [&](int it) {
-        const int st = it & 1;
-        mbar_wait(bar_y(st), (it >> 1) & 1u, 2);
+        const int st = it % AB_YBUF;
+        mbar_wait(bar_y(st), uint32_t(it / AB_YBUF) & 1u, 2);
         tc_fence_after();
         const bool with_dp = it >= n_pre;
 #pragma unroll
@@ -195,22 +199,23 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       };
 #define AB_CSTAMP(slot) do { if (args.dbg != nullptr && it == n_pre + 3) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
       fetch(0);
+      if (n_it > 1) fetch(1);
       mbar_wait(bar_x, 0, 1);
       issue_sdp(0);
       int n_acc = 0;  // bar_acc phases committed so far (one per main tile)
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
+        const int st = it % AB_YBUF;
         const bool pre = it < n_pre;
         AB_CSTAMP(8);
-        if (it + 1 < n_it) {
-          // buffer (it + 1) & 1 was last read by the MMAs of iteration it - 1 (S / dP: retired, their tiles were consumed;
-          // accumulating MMAs: committed to bar_acc)
-          if (n_acc > 0 && it - 1 >= n_pre) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
-          fetch(it + 1);
-        }
         AB_CSTAMP(9);
         mbar_wait(bar_free, it & 1u, 8);  // S / dP of this iteration are in registers: the tiles may be overwritten
-        if (it + 1 < n_it) issue_sdp(it + 1);
+        if (it + 1 < n_it) issue_sdp(it + 1);  // its tiles were fetched one iteration ago
+        if (it + 2 < n_it) {
+          // buffer (it + 2) % 3 was last read by the MMAs of iteration it - 1 (S / dP: retired, their tiles were consumed;
+          // accumulating MMAs: committed to bar_acc, and by now they have had the whole S / dP issue to retire)
+          if (n_acc > 0 && it - 1 >= n_pre) mbar_wait(bar_acc, (n_acc - 1) & 1u, 4);
+          fetch(it + 2);
+        }
         AB_CSTAMP(10);
         mbar_wait(bar_p(0), it & 1u, 3);  // staging written
         AB_CSTAMP(11);
@@ -333,17 +338,21 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
     if (MODE == 0) lse2 -= log2f(args.scale);  // ps = scale * P straight out of the exp2
     AB_STAMP(1);
     // ---- main pass ----
+    // MODE 1: the column statistics (lse, delta of the query tile) are read one iteration ahead: the load of tile j + 1 is in
+    // flight under the arithmetic of tile j (it used to sit, ~800 cycles of L2 latency, at the top of every iteration)
+    float sv_next = 0.f;
+    const float* stat_src = quad == 0 ? args.lse : args.delta;
+    if (MODE == 1 && quad < 2 && r < args.rows_per_batch) sv_next = stat_src[stat_base + r];
     for (int it = n_pre; it < n_it; ++it) {
       const int j = it - n_pre;
       const int nv = min(AB_TILE, len - j * AB_TILE);  // valid columns of this tile (keys in MODE 0, queries in MODE 1)
       const float* st = s_stat + (j & 1) * 256;
       if (MODE == 1) {
-        const int tq = j * AB_TILE + r;
         float* sw_ = s_stat + (j & 1) * 256;
         if (quad < 2) {
-          const float* src = quad == 0 ? args.lse : args.delta;
-          const float sv = tq < args.rows_per_batch ? src[stat_base + tq] : 0.f;
-          sw_[128 * quad + r] = quad == 0 ? sv : -args.scale * sv;  // (lse, -scale * delta)
+          sw_[128 * quad + r] = quad == 0 ? sv_next : -args.scale * sv_next;  // (lse, -scale * delta)
+          const int tqn = (j + 1) * AB_TILE + r;
+          sv_next = (it + 1 < n_it && tqn < args.rows_per_batch) ? stat_src[stat_base + tqn] : 0.f;
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
       }

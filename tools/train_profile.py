@@ -69,3 +69,18 @@ if __name__ == "__main__":
     e1.record()
     torch.cuda.synchronize()
     print(f"{name}: {e0.elapsed_time(e1) / steps:.2f} ms per training step, loss {float(loss):.4f}")
+    if "--kineto" in sys.argv:  # in-situ kernel durations (CUPTI activity records: no replay, warm caches, real clocks)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                eng.train_step(mel, text, lens)
+            torch.cuda.synchronize()
+        tot, cnt = defaultdict(float), defaultdict(int)
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                tot[ev.name.split("(")[0]] += ev.device_time
+                cnt[ev.name.split("(")[0]] += 1
+        total = sum(tot.values())
+        print(f"kineto: {total / 2e3:.2f} ms of kernel time per step")
+        for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:24]:
+            print(f"{v / 2e3:9.3f} ms {100 * v / total:5.1f} %  x{cnt[k] // 2:5d}  avg {v / cnt[k]:8.1f} us  {k[:90]}")
