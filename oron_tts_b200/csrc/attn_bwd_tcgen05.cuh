@@ -48,6 +48,9 @@ constexpr int AB_TMEM_COLS = 512;
 // it + 1 could only be issued once the accumulating MMAs of it - 1 had retired, i.e. right before S / dP of it + 1 needed
 // it: the MMA thread sat ~1.2 k cycles per tile in the TMA latency (trace: "issue S/dP(n+1)" 1766 cycles for 8 MMAs).
 constexpr int AB_YBUF = 3;
+#ifndef AB_POLY
+#define AB_POLY 4  // of every 16 pairs of exponentials, this many are evaluated on the FMA pipe (ex2_poly2) instead of the MUFU unit
+#endif
 constexpr int AB_SMEM_BYTES = (6 + 2 * AB_YBUF) * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 8 * 128 * 4 + 1024;
 
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
@@ -381,8 +384,15 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           if (MODE == 0) {
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
-              const float p0 = ex2_approx(fmaf(__uint_as_float(vs[cc][k]), c, -lse2));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(vs[cc][k + 1]), c, -lse2));
+              float p0 = fmaf(__uint_as_float(vs[cc][k]), c, -lse2), p1 = fmaf(__uint_as_float(vs[cc][k + 1]), c, -lse2);
+              // the MUFU unit (16 exp2 per clock per SM) is the narrowest pipe of this loop (ncu: a quarter of all stall
+              // samples sit on MUFU.EX2 with the MIO queue full): AB_POLY pairs of 16 go through the FMA-pipe polynomial
+              if ((k >> 1) % 16 < AB_POLY) {
+                ex2_poly2(p0, p1);
+              } else {
+                p0 = ex2_approx(p0);
+                p1 = ex2_approx(p1);
+              }
               pd[k >> 1] = pack_bf16x2(p0 * (__uint_as_float(vd[cc][k]) - delta), p1 * (__uint_as_float(vd[cc][k + 1]) - delta));
             }
           } else {
@@ -394,10 +404,11 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
               const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
               float pv[4], dv[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                pv[e] = ex2_approx(fmaf(__uint_as_float(vs[cc][4 * k4 + e]), c, -ll[e]));
-                dv[e] = pv[e] * fmaf(__uint_as_float(vd[cc][4 * k4 + e]), args.scale, ee[e]);
-              }
+              for (int e = 0; e < 4; ++e) pv[e] = fmaf(__uint_as_float(vs[cc][4 * k4 + e]), c, -ll[e]);
+              if ((2 * k4) % 16 < AB_POLY) ex2_poly2(pv[0], pv[1]); else { pv[0] = ex2_approx(pv[0]); pv[1] = ex2_approx(pv[1]); }
+              if ((2 * k4 + 1) % 16 < AB_POLY) ex2_poly2(pv[2], pv[3]); else { pv[2] = ex2_approx(pv[2]); pv[3] = ex2_approx(pv[3]); }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) dv[e] = pv[e] * fmaf(__uint_as_float(vd[cc][4 * k4 + e]), args.scale, ee[e]);
               pp[2 * k4] = pack_bf16x2(pv[0], pv[1]);
               pp[2 * k4 + 1] = pack_bf16x2(pv[2], pv[3]);
               pd[2 * k4] = pack_bf16x2(dv[0], dv[1]);

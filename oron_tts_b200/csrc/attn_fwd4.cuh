@@ -164,32 +164,6 @@ __device__ __forceinline__ void fadd2(float& s0, float& s1, float x0, float x1) 
   asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(r));
 }
 
-// 2^x for a pair on the FMA / ALU pipes instead of the MUFU unit (one in four exponentials goes this way: the MUFU unit,
-// 16 results per clock per SM, is the softmax's narrowest pipe). x = floor(x) + f by adding 1.5 * 2^23 with round-down,
-// degree-3 polynomial for 2^f on [0, 1) (max relative error 9e-5, f16 resolution is 4.9e-4), floor(x) added into the
-// exponent field. Valid for -127 <= x < 128; smaller x are clamped (result ~0).
-__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
-  uint64_t xv, mg, t, r, f, p, c3, c2, c1, c0;
-  const float y0 = fmaxf(x0, -127.0f), y1 = fmaxf(x1, -127.0f);
-  asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(y0), "f"(y1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(12582912.0f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.07711965f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.22756439f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.69514614f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(1.0f));
-  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(t) : "l"(xv), "l"(mg));
-  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(t), "l"(mg));
-  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(f) : "l"(xv), "l"(r));
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(f), "l"(c3), "l"(c2));
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c1));
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c0));
-  uint32_t t0, t1, p0, p1;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(p));
-  x0 = __uint_as_float(p0 + (t0 << 23));
-  x1 = __uint_as_float(p1 + (t1 << 23));
-}
-
 // Bounded wait without printf (its argument buffer lives in local memory: see below). A stuck pipeline records the tag of
 // the barrier in g_att4_fault (read back by the host wrapper after a failed launch) and traps.
 __device__ int g_att4_fault = 0;

@@ -317,6 +317,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair on the FMA / ALU pipes instead of the MUFU unit (one in four exponentials goes this way: the MUFU unit,
+// 16 results per clock per SM, is the softmax's narrowest pipe). x = floor(x) + f by adding 1.5 * 2^23 with round-down,
+// degree-3 polynomial for 2^f on [0, 1) (max relative error 9e-5, f16 resolution is 4.9e-4), floor(x) added into the
+// exponent field. Valid for -127 <= x < 128; smaller x are clamped (result ~0).
+__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
+  uint64_t xv, mg, t, r, f, p, c3, c2, c1, c0;
+  const float y0 = fmaxf(x0, -127.0f), y1 = fmaxf(x1, -127.0f);
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(y0), "f"(y1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(12582912.0f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.07711965f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.22756439f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.69514614f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(1.0f));
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(t) : "l"(xv), "l"(mg));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(t), "l"(mg));
+  asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(f) : "l"(xv), "l"(r));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(f), "l"(c3), "l"(c2));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c1));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c0));
+  uint32_t t0, t1, p0, p1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(p));
+  x0 = __uint_as_float(p0 + (t0 << 23));
+  x1 = __uint_as_float(p1 + (t1 << 23));
+}
+
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with the hardware tanh (one MUFU op, max rel. error 2^-11:
   // below the bf16 rounding of the result). The epilogue that uses it is instruction-bound.
