@@ -33,6 +33,7 @@ STREAM_K = os.environ.get("ORON_STREAM_K", "1") != "0"
 # unstable (the main loop is bound by the 64 B/clk per-SM TMA ingest and by the power cap, not by the
 # launch boundary), so it stays opt-in: ORON_FFN_FUSED=1.
 FFN_FUSED = os.environ.get("ORON_FFN_FUSED", "0") == "1"
+SMALL_ROWS = int(os.environ.get("ORON_SMALL_ROWS", "600"))
 BF16 = torch.bfloat16
 F32 = torch.float32
 TILE = 128
@@ -388,6 +389,13 @@ class DiTEngine:
         common = dict(rows_per_batch=tpad, nbatch=nbp)
         # transformer GEMMs run on the 2-SM kernel: 256 x 256 tile per SM pair (256 x 128 for narrow models)
         bn_big = 256 if D % 256 == 0 else 128
+        # few rows (utterances up to ~3 s with CFG): launch-latency bound, one wave either way; the 1-SM kernel has no cluster
+        # launch / cluster barriers in its prologue and epilogue. tools/short_utt_bench.py, T = 143: Small 724 -> 687 us per NFE,
+        # Base 1595 -> 1565; at 1024 rows Small gains (811 -> 715) but Base loses (1725 -> 1894), so the switch stays at 600 rows
+        # (ORON_SMALL_ROWS; 0 = always the 2-SM kernel)
+        two = R > SMALL_ROWS
+        if not two:
+            bn_big = 128
 
         L.gemm(ws.xb, w.wx, ws.h0, epilogue=L.EPI_EMBED_DUAL, addend=ws.c0, seq_lens=ws.seq_lens, out2=ws.h0b,
                block_n=128, **common)
@@ -404,20 +412,20 @@ class DiTEngine:
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
-                   rope_cols=2 * w.inner, f16_from_col=2 * w.inner, block_n=bn_big, two_sm=True, **common)
+                   rope_cols=2 * w.inner, f16_from_col=2 * w.inner, block_n=bn_big, two_sm=two, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
                         scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
-                   mask_rows=True, block_n=bn_big, two_sm=True, **common)  # K = dim: too short for stream-K to pay
+                   mask_rows=True, block_n=bn_big, two_sm=two, **common)  # K = dim: too short for stream-K to pay
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
-            fused = FFN_FUSED and STREAM_K and not self.deterministic and bn_big == 256 and w.ff_dim % 256 == 0
+            fused = FFN_FUSED and STREAM_K and two and not self.deterministic and bn_big == 256 and w.ff_dim % 256 == 0
             up = L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
-                        block_n=bn_big, two_sm=True, desc_only=fused, **common)
+                        block_n=bn_big, two_sm=two, desc_only=fused, **common)
             down = L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                           gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                          block_n=bn_big, two_sm=True, stream_k=STREAM_K and not self.deterministic, desc_only=fused, **common)
+                          block_n=bn_big, two_sm=two, stream_k=STREAM_K and two and not self.deterministic, desc_only=fused, **common)
             if fused:
                 L.ffn(up, down, ws.ffn_ws)
         o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
