@@ -52,6 +52,11 @@ extern "C" int oron_transpose_bf16(const void* in, int64_t ld_in, int32_t rows_p
 
 extern "C" int oron_colsum_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, float* out, oron_stream_t stream) {
   if (!in || !out || rows <= 0 || C <= 0 || (C & 1) || (ld_in & 1)) return fail(ORON_ERR_BAD_ARG, "colsum: bad argument");
+  if ((C & 7) == 0 && (ld_in & 7) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    dim3 grid8(unsigned((C + 127) / 128), unsigned((rows + 255) / 256));
+    colsum_bf16x8_kernel<<<grid8, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, rows, C, out);
+    return check_launch("colsum_bf16");
+  }
   dim3 grid(unsigned((C + 63) / 64), unsigned((rows + 511) / 512));
   colsum_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, rows, C, out);
   return check_launch("colsum_bf16");

@@ -242,6 +242,55 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* i
   }
 }
 
+// Same, 16-byte loads: 256 threads = 16 column groups of 8 x 16 row lanes, four rows in flight per thread; grid
+// (ceil(C / 128), row chunks of 256). The 4-byte version above keeps one load in flight per thread (15.7 us for 8192 x 1024,
+// i.e. ~1 TB/s on operands that mostly sit in L2); used when C % 8 == 0 and the rows are 16-byte aligned.
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const __nv_bfloat16* in, long long ld, long long rows, int C, float* out) {
+  __shared__ float red[16][128 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c = blockIdx.x * 128 + 8 * tx;
+  const long long r0 = (long long)blockIdx.y * 256, r1 = min(r0 + 256, rows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    long long r = r0 + ty;
+    for (; r + 48 < r1; r += 64) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(in + (r + 16 * u) * ld + c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += __uint_as_float(w[k] << 16);
+          acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+        }
+      }
+    }
+    for (; r < r1; r += 16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + r * ld + c));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += __uint_as_float(w[k] << 16);
+        acc[2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[ty][8 * tx + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += red[i][threadIdx.x];
+      atomicAdd(out + cc, s);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // column sums of per-warp register partials: lane owns columns {2*(lane + 32 i), +1}, i < V2 (C = 64 V2);
 // reduce over the 8 warps of the CTA through shared memory, then one atomicAdd per column.

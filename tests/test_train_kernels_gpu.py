@@ -269,6 +269,18 @@ def test_gconv_wgrad_tensor_core(C, cg, nb, rpb):
     assert _rel(dw - 0.25, dw2) < 1e-4
 
 
+@pytest.mark.parametrize("rows,C,ld,off", [(8192, 1024, 1024, 0), (1000, 1024, 3072, 1024), (333, 200, 200, 0), (70, 64, 72, 8), (300, 72, 80, 4)])
+def test_colsum_bf16(rows, C, ld, off):
+    """Bias gradients: out += column sums, through the 16-byte-load kernel (aligned views) and the 4-byte fallback."""
+    g = torch.Generator(device=DEV).manual_seed(rows + C)
+    buf = torch.randn(rows, ld, device=DEV, generator=g).to(BF16)
+    x = buf[:, off:off + C]
+    out = torch.full((C,), 0.5, device=DEV)
+    T.colsum(x, out)
+    ref = 0.5 + x.float().sum(0)
+    assert float((out - ref).abs().max()) < 1e-3 * float(ref.abs().max() + 1)
+
+
 def test_cfm_loss():
     g = torch.Generator(device=DEV).manual_seed(9)
     rows, M = 512, 100
