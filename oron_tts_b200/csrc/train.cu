@@ -380,8 +380,12 @@ extern "C" int oron_mask_rows_f32(float* x, int64_t ldx, int64_t rows, int32_t C
 extern "C" int oron_f16_to_bf16(const void* in, int64_t ld_in, int64_t rows, int32_t C, void* out, int64_t ld_out,
                                 oron_stream_t stream) {
   if (!in || !out || (C & 1) || (ld_in & 1) || (ld_out & 1)) return fail(ORON_ERR_BAD_ARG, "f16_to_bf16: bad argument");
-  f16_to_bf16_kernel<<<ew_blocks(rows * (C / 2)), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), ld_in, rows, C,
-                                                                        reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  if ((C & 7) == 0 && (ld_in & 7) == 0 && (ld_out & 7) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    f16_to_bf16x8_kernel<<<ew_blocks(rows * (C / 8)), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), ld_in, rows, C,
+                                                                            reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  else
+    f16_to_bf16_kernel<<<ew_blocks(rows * (C / 2)), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(in), ld_in, rows, C,
+                                                                          reinterpret_cast<__nv_bfloat16*>(out), ld_out);
   return check_launch("f16_to_bf16");
 }
 

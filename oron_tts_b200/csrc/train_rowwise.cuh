@@ -1097,5 +1097,24 @@ __global__ void __launch_bounds__(256) f16_to_bf16_kernel(const __half* in, long
     *reinterpret_cast<uint32_t*>(out + r * ld_out + c) = pack_bf16x2(v.x, v.y);
   }
 }
+// 16 bytes per thread (C % 8 == 0, rows 16-byte aligned): the 4-byte version runs at ~2.3 TB/s
+__global__ void __launch_bounds__(256) f16_to_bf16x8_kernel(const __half* in, long long ld_in, long long rows, int C,
+                                                            __nv_bfloat16* out, long long ld_out) {
+  const long long per = C / 8;
+  const long long total = rows * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per;
+    const int c = int(i - r * per) * 8;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + r * ld_in + c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      q[k] = pack_bf16x2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = make_uint4(q[0], q[1], q[2], q[3]);
+  }
+}
 
 }  // namespace oron

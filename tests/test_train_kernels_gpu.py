@@ -281,6 +281,17 @@ def test_colsum_bf16(rows, C, ld, off):
     assert float((out - ref).abs().max()) < 1e-3 * float(ref.abs().max() + 1)
 
 
+@pytest.mark.parametrize("rows,C,ld,off", [(8192, 1024, 3072, 2048), (100, 66, 70, 2)])
+def test_f16_to_bf16(rows, C, ld, off):
+    """V of the forward (IEEE f16 bit patterns inside the fused qkv buffer) -> bf16 operand of the backward."""
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    buf = torch.randn(rows, ld, device=DEV, generator=g).half()
+    x = buf[:, off:off + C]
+    out = torch.zeros(rows, C, device=DEV, dtype=BF16)
+    T.f16_to_bf16(x.view(torch.bfloat16) if False else x, out)
+    assert torch.equal(out, x.float().to(BF16))
+
+
 def test_cfm_loss():
     g = torch.Generator(device=DEV).manual_seed(9)
     rows, M = 512, 100
