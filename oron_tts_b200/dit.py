@@ -151,7 +151,28 @@ class DiT(nn.Module):
             except RuntimeError:
                 return -1
 
-        return tuple((p.data_ptr(), ver(p)) for p in self.parameters())
+        # nn.Module.parameters() walks the module tree (2 ms per call for the Base model, with the GPU idle at the start of
+        # every synthesize): keep the (owner module, name) slots and re-read the Parameter objects from them, so replaced
+        # parameters (load_state_dict(assign=True), .to()) are still seen; the slot list is rebuilt after _apply /
+        # load_state_dict / a sub-module assignment on this module
+        slots = self.__dict__.get("_param_slots")
+        if slots is None:
+            slots = [(m, n) for m in self.modules() for n in m._parameters if m._parameters[n] is not None]
+            self.__dict__["_param_slots"] = slots
+        return tuple((p.data_ptr(), ver(p)) for p in (m._parameters[n] for m, n in slots))
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_param_slots"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_param_slots"] = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def __setattr__(self, name, value):
+        if isinstance(value, nn.Module):
+            self.__dict__["_param_slots"] = None
+        super().__setattr__(name, value)
 
     def engine(self) -> DiTEngine:
         """Packed-weight engine for the current parameters (rebuilt after load_state_dict / .to())."""

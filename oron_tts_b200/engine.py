@@ -316,15 +316,27 @@ class DiTEngine:
         nb, tpad = ws.nb, ws.tpad
         ids = (text.to(torch.int64) + 1)[:, :seq_len]
         vocab1 = self.w.text_table.shape[0]
+        # the range check reads the ids on the host: free for a CPU tensor (what F5TTS.synthesize passes), a host sync that
+        # waits for everything enqueued so far for a CUDA tensor
         if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= vocab1):  # nn.Embedding raises here too (encoder.py:75)
             raise IndexError(f"text ids out of range: ids must lie in [-1, {vocab1 - 2}] (index out of range in the text embedding table)")
-        ids2 = torch.zeros(nb, tpad, device=self.w.device, dtype=torch.int32)
-        ids2[:, : ids.shape[1]] = ids.to(torch.int32)
-        ws.ids.view(ws.nbp, tpad).copy_(ids2.repeat(len(branches), 1))
-        drop = [int(br.drop_text) for br in branches for _ in range(nb)]
-        ws.drop.copy_(torch.tensor(drop, dtype=torch.uint8), non_blocking=False)
-        ws.seq_lens.copy_(torch.tensor(durations * len(branches), dtype=torch.int32))
-        ws.text_lens.copy_(torch.tensor((durations if text_len is None else [int(text_len)] * nb) * len(branches), dtype=torch.int32))
+        dev = self.w.device
+
+        def h2d(dst, src):  # host values through pinned memory: an async copy instead of copy_'s stream synchronisation
+            dst.copy_(src.pin_memory(), non_blocking=True)
+
+        nbr = len(branches)
+        if ids.is_cuda:
+            ids2 = torch.zeros(nb, tpad, device=dev, dtype=torch.int32)
+            ids2[:, : ids.shape[1]] = ids.to(torch.int32)
+            ws.ids.view(ws.nbp, tpad).copy_(ids2.repeat(nbr, 1))
+        else:
+            ids2 = torch.zeros(nb, tpad, dtype=torch.int32)
+            ids2[:, : ids.shape[1]] = ids.to(torch.int32)
+            h2d(ws.ids.view(ws.nbp, tpad), ids2.repeat(nbr, 1))
+        h2d(ws.drop, torch.tensor([int(br.drop_text) for br in branches for _ in range(nb)], dtype=torch.uint8))
+        h2d(ws.seq_lens, torch.tensor(durations * nbr, dtype=torch.int32))
+        h2d(ws.text_lens, torch.tensor((durations if text_len is None else [int(text_len)] * nb) * nbr, dtype=torch.int32))
         # schedule of the attention kernel for these lengths (once per call, outside the per-NFE graph)
         L.attention_plan(ws.attn_ws, nbatch=ws.nbp, rows_per_batch=tpad, heads=self.w.heads, seq_lens=ws.seq_lens)
 

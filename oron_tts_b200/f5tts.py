@@ -292,9 +292,10 @@ class F5TTS(nn.Module):
                 if segs[i]["seed"] is not None:
                     g = torch.Generator(device=device).manual_seed(segs[i]["seed"])
                 y0[j, : frames[i]] = torch.randn(frames[i], self.n_mels, device=device, generator=g)
-            mel, _ = self.cfm.sample(cond=cond, text_ids=ids.to(device),
-                                     duration=torch.tensor([frames[i] for i in batch], device=device, dtype=torch.long),
-                                     lens=torch.full((B,), ref_len, device=device, dtype=torch.long), steps=n_steps,
+            # ids / duration / lens stay on the host: CFM.sample validates them without a device read-back (no host sync)
+            mel, _ = self.cfm.sample(cond=cond, text_ids=ids,
+                                     duration=torch.tensor([frames[i] for i in batch], dtype=torch.long),
+                                     lens=torch.full((B,), ref_len, dtype=torch.long), steps=n_steps,
                                      cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, y0=y0)
             for j, i in enumerate(batch):
                 target_mel = mel[j:j + 1, ref_len:frames[i], :].transpose(1, 2)
@@ -342,14 +343,14 @@ class F5TTS(nn.Module):
         plan = self.prepare_segment(text, lang, ref_mel_raw, ref_text, speed, target_duration_s)
         ref_len, total = plan["ref_len"], plan["T_total"]
 
-        ids = torch.tensor([plan["full_ids"]], dtype=torch.long, device=device)
+        ids = torch.tensor([plan["full_ids"]], dtype=torch.long)  # host side: validated without a device read-back
         if ref_mel_raw is not None:
             cond = F.pad(ref_mel_raw.unsqueeze(0).transpose(1, 2), (0, 0, 0, total - ref_len), value=0.0)
         else:
             cond = torch.zeros(1, total, self.n_mels, device=device)
         mel, _ = self.cfm.sample(cond=cond, text_ids=ids,
-                                 duration=torch.tensor([total], device=device, dtype=torch.long),
-                                 lens=torch.tensor([ref_len], device=device, dtype=torch.long),
+                                 duration=torch.tensor([total], dtype=torch.long),
+                                 lens=torch.tensor([ref_len], dtype=torch.long),
                                  steps=n_steps, cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, seed=seed)
         target_mel = mel[:, ref_len:, :].transpose(1, 2)  # [1, n_mels, target_len]
         return self._get_vocos(device).decode(target_mel).squeeze(0).cpu()

@@ -103,21 +103,28 @@ class CFM(nn.Module):
         if not cond.is_cuda:
             raise RuntimeError("CFM.sample runs only on a CUDA device (oron_tts_b200 has no CPU fallback)")
 
-        if lens is None:
-            lens = torch.full((batch,), cond_seq_len, device=device, dtype=torch.long)
-        else:
-            lens = lens.to(device=device, dtype=torch.long)
-        if lens.numel() != batch:
+        # Host copies of duration / lens for the reference's checks (flow.py:219-230) and the workspace shape. Reading a CUDA
+        # tensor back is a host sync that waits for everything already enqueued (the previous utterance's whole ODE loop when
+        # calls are pipelined): ints and CPU tensors (what F5TTS.synthesize passes) need none, CUDA tensors cost one.
+        if lens is not None and lens.numel() != batch:
             raise ValueError(f"lens must have {batch} values, got {lens.numel()}")
-        if isinstance(duration, int):
-            duration = torch.full((batch,), duration, device=device, dtype=torch.long)
-        else:
-            duration = duration.to(device=device, dtype=torch.long)
-        if duration.numel() != batch:
+        if not isinstance(duration, int) and duration.numel() != batch:
             raise ValueError(f"duration must have {batch} values, got {duration.numel()}")
-        # one host sync for all the reference's checks (flow.py:219-230)
-        host = torch.stack([duration, lens]).tolist()
-        dur_h, lens_h = host[0], host[1]
+        dur_h = [int(duration)] * batch if isinstance(duration, int) else None
+        lens_h = [cond_seq_len] * batch if lens is None else None
+        if dur_h is None and not duration.is_cuda:
+            dur_h = [int(v) for v in duration.reshape(-1).tolist()]
+        if lens_h is None and not lens.is_cuda:
+            lens_h = [int(v) for v in lens.reshape(-1).tolist()]
+        if dur_h is None or lens_h is None:  # at least one CUDA tensor: one read-back for both
+            dev_vals = [v.to(device=device, dtype=torch.long).reshape(-1) for v, h in ((duration, dur_h), (lens, lens_h)) if h is None]
+            host = torch.stack(dev_vals).tolist()
+            if dur_h is None:
+                dur_h = host.pop(0)
+            if lens_h is None:
+                lens_h = host.pop(0)
+        lens = torch.tensor(lens_h, dtype=torch.long).to(device, non_blocking=True) if lens is None or not lens.is_cuda \
+            else lens.to(device=device, dtype=torch.long)
         if any(d <= 0 for d in dur_h):
             raise ValueError("duration values must be > 0")
         if any(v < 0 for v in lens_h):
@@ -138,7 +145,7 @@ class CFM(nn.Module):
         step_cond = torch.where(cond_mask_3d, cond, torch.zeros_like(cond))
 
         if precision == "fp32":
-            return self._sample_fp32(cond, cond_mask_3d, step_cond, text_ids, dur_h, max_dur, steps, cfg_strength,
+            return self._sample_fp32(cond, cond_mask_3d, step_cond, text_ids.to(device), dur_h, max_dur, steps, cfg_strength,
                                      sway_sampling_coef, seed, y0, method)
         eng = self.backbone.engine()
         w = eng.w

@@ -97,12 +97,24 @@ class Vocos(nn.Module):
         model.load_state_dict(sd, strict=True)
         return model.eval()
 
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_param_slots"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__["_param_slots"] = None
+        return super().load_state_dict(*args, **kwargs)
+
     # ---- packed weights ------------------------------------------------------------------------------
     def _pack(self):
         p0 = next(self.parameters())
         if not p0.is_cuda:
             raise RuntimeError("oron_tts_b200.Vocos runs only on a CUDA device (no CPU fallback)")
-        sig = tuple((p.data_ptr(), _version_of(p)) for p in self.parameters())
+        slots = self.__dict__.get("_param_slots")  # see DiT._signature: parameters() walks the module tree on every decode
+        if slots is None:
+            slots = [(m, n) for m in self.modules() for n in m._parameters if m._parameters[n] is not None]
+            self.__dict__["_param_slots"] = slots
+        sig = tuple((p.data_ptr(), _version_of(p)) for p in (m._parameters[n] for m, n in slots))
         if self.__dict__["_packed"] is not None and self.__dict__["_packed_sig"] == sig:
             return self.__dict__["_packed"]
         dev = p0.device
