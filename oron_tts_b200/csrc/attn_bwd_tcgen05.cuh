@@ -48,12 +48,40 @@ constexpr int AB_TMEM_COLS = 512;
 // it + 1 could only be issued once the accumulating MMAs of it - 1 had retired, i.e. right before S / dP of it + 1 needed
 // it: the MMA thread sat ~1.2 k cycles per tile in the TMA latency (trace: "issue S/dP(n+1)" 1766 cycles for 8 MMAs).
 constexpr int AB_YBUF = 3;
+#ifndef AB_TS
+#define AB_TS 1  // 1: dS / P^T reach the accumulating MMAs through TMEM (TS-form tcgen05.mma, A operand = 64 TMEM columns of packed
+                 // bf16 per 128 x 128 tile) instead of a swizzled shared-memory staging tile: no staging stores, no cross-proxy
+                 // fence, and a third less shared-memory operand traffic for the tensor pipe
+#endif
 #ifndef AB_POLY
 #define AB_POLY 4  // of every 16 pairs of exponentials, this many are evaluated on the FMA pipe (ex2_poly2) instead of the MUFU unit
 #endif
 constexpr int AB_SMEM_BYTES = (6 + 2 * AB_YBUF) * AB_TILE_BYTES + 128 + 4 * 128 * 4 + 8 * 128 * 4 + 1024;
 
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+// 16 packed bf16x2 words of one row -> 16 TMEM columns (the A operand layout of a TS-form MMA: two K elements per column)
+__device__ __forceinline__ void ab_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void ab_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = 128 lanes x 16 K elements (bf16, two per 32-bit column)
+__device__ __forceinline__ void ab_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // 32 consecutive columns of one staging row (bf16, SW128 K-major tile of 128 rows x 128 columns in two 64-column slabs)
 __device__ __forceinline__ void ab_stage_store(uint32_t stage, int r, int c0, const uint32_t (&pk)[16]) {
@@ -145,6 +173,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
   // TMEM columns: S (128) | dP (128) | two 64-column accumulators
   auto tmem_S = [&](int u) { return tmem_base + 128u * uint32_t(u); };  // u = 0: S, u = 1: dP
   const uint32_t tmem_acc1 = tmem_base + 256, tmem_acc2 = tmem_base + 320;
+  // TS form: packed bf16 A operands, 64 columns each -- MODE 0: dS | MODE 1: P^T, dS^T
+  const uint32_t tmem_a1 = tmem_base + 384, tmem_a2 = tmem_base + 448;
 
   // Iterations: one per 128-row operand tile (an optional pre-pass over the same tiles computes the log-sum-exp when the
   // forward did not supply it). S and dP are single 128-column TMEM tiles: the CUDA cores copy their 64 columns to
@@ -226,6 +256,23 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
           tc_fence_after();
           const int j = it - n_pre;
           const uint32_t accf = j == 0 ? 0u : 1u;
+#if AB_TS
+          (void)ad; (void)bd; (void)kSlab;
+          if (MODE == 0) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)  // dQ += dS K_j; even / odd k-steps into two accumulators, summed in the epilogue
+              ab_umma_ts((kk & 1) ? tmem_acc1 : tmem_acc2, tmem_a1 + 8u * uint32_t(kk),
+                         (y1m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc, kk >= 2 ? 1u : accf);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {  // dV += P^T dO_i and dK += dS^T Q_i, interleaved
+              ab_umma_ts(tmem_acc1, tmem_a1 + 8u * uint32_t(kk), (y2m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc,
+                         kk != 0 ? 1u : accf);
+              ab_umma_ts(tmem_acc2, tmem_a2 + 8u * uint32_t(kk), (y1m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc,
+                         kk != 0 ? 1u : accf);
+            }
+          }
+#else
           if (MODE == 0) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)  // dQ += dS K_j; even / odd k-steps into two accumulators, summed in the epilogue
@@ -240,6 +287,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
                            (y1m + kBuf * uint64_t(st)) + uint64_t(128 * kk), idesc_acc, kk != 0 ? 1u : accf);
             }
           }
+#endif
           umma_commit(bar_acc);
           ++n_acc;
         }
@@ -436,14 +484,28 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
         // the staging tiles still feed the previous iteration's accumulating MMAs: wait for them only now, with this
         // iteration's arithmetic already done
         if (j > 0) mbar_wait(bar_acc, (j - 1) & 1u, 9);
+#if AB_TS
+        // this thread's 32 columns = 16 packed words of its row, at columns [16 quad, 16 quad + 16) of the operand tile
+        tc_fence_after();
+        if (MODE == 0) {
+          ab_tmem_st16(tmem_a1 + lane_off + 16u * uint32_t(quad), pd);
+        } else {
+          ab_tmem_st16(tmem_a1 + lane_off + 16u * uint32_t(quad), pp);
+          ab_tmem_st16(tmem_a2 + lane_off + 16u * uint32_t(quad), pd);
+        }
+        ab_tmem_wait_st();
+#else
         if (MODE == 0) {
           ab_stage_store(sA, r, c0, pd);
         } else {
           ab_stage_store(sA, r, c0, pp);
           ab_stage_store(sB, r, c0, pd);
         }
+#endif
       }
+#if !AB_TS
       fence_proxy_async_smem();
+#endif
       tc_fence_before();
       mbar_arrive(bar_p(0));
       if (it == n_pre + 3) AB_STAMP(15);
