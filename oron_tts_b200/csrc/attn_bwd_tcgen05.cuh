@@ -314,21 +314,31 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_c
       // delta[row] = sum_d dO * O, cooperatively: 8 lanes per row read one 16-byte chunk each (coalesced), shuffle-reduce
       {
         const int tid = int(threadIdx.x) - 32;
+        // all four 16-byte loads first: the two rounds used to run back to back (load - reduce - store, twice: two exposed
+        // memory latencies at the head of every CTA, with S / dP of the first tile already waiting in TMEM)
+        uint4 av[2], dv[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int q = i * 512 + tid;
           const int row = q >> 3, k = q & 7;
           const int t = tile * AB_TILE + row;
-          float part = 0.f;
+          av[i] = make_uint4(0u, 0u, 0u, 0u);
+          dv[i] = make_uint4(0u, 0u, 0u, 0u);
           if (t < len) {
-            const uint4 a = *reinterpret_cast<const uint4*>(args.o + (row_base + t) * args.ld_o + h * AB_D + 8 * k);
-            const uint4 d = *reinterpret_cast<const uint4*>(args.d_o + (row_base + t) * args.ld_do + h * AB_D + 8 * k);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+            av[i] = __ldg(reinterpret_cast<const uint4*>(args.o + (row_base + t) * args.ld_o + h * AB_D + 8 * k));
+            dv[i] = __ldg(reinterpret_cast<const uint4*>(args.d_o + (row_base + t) * args.ld_do + h * AB_D + 8 * k));
+          }
+        }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              part = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(dw[e] << 16), part);
-              part = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(dw[e] & 0xffff0000u), part);
-            }
+        for (int i = 0; i < 2; ++i) {
+          const int q = i * 512 + tid;
+          const int row = q >> 3, k = q & 7;
+          float part = 0.f;
+          const uint32_t aw[4] = {av[i].x, av[i].y, av[i].z, av[i].w}, dw[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            part = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(dw[e] << 16), part);
+            part = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(dw[e] & 0xffff0000u), part);
           }
           part += __shfl_xor_sync(0xffffffffu, part, 1);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
