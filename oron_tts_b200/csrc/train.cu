@@ -283,6 +283,14 @@ extern "C" int oron_skinny_dgrad(const float* dY, int64_t lddy, int32_t nb, int3
                                  int32_t K, float* dX, int64_t lddx, oron_stream_t stream) {
   if (!dY || !W_bf16 || !dX || nb <= 0 || N <= 0 || K <= 0 || (K & 1) || (ldw & 1))
     return fail(ORON_ERR_BAD_ARG, "skinny_dgrad: bad argument");
+  if (nb <= 8 && (K & 7) == 0 && (ldw & 7) == 0 && (reinterpret_cast<uintptr_t>(W_bf16) & 15) == 0) {
+    const int gy = (K + 511) / 512, chunks = (N + 255) / 256;
+    int gx = (2 * num_sms() + gy - 1) / gy;
+    if (gx > chunks) gx = chunks;
+    dim3 grid8((unsigned)gx, (unsigned)gy);
+    skinny_dgrad8_kernel<<<grid8, 256, 0, ST(stream)>>>(dY, lddy, nb, N, reinterpret_cast<const __nv_bfloat16*>(W_bf16), ldw, K, dX, lddx);
+    return check_launch("skinny_dgrad");
+  }
   dim3 grid(unsigned((N + 1023) / 1024), unsigned((K + 511) / 512));
   skinny_dgrad_kernel<<<grid, 256, 0, ST(stream)>>>(dY, lddy, nb, N, reinterpret_cast<const __nv_bfloat16*>(W_bf16), ldw, K,
                                                     dX, lddx);

@@ -210,9 +210,11 @@ def test_text_embed_bwd():
     assert _rel(dt, ref) < 1e-5
 
 
-def test_skinny_dgrad_wgrad():
+@pytest.mark.parametrize("nb,N,K", [(5, 2300, 384), (8, 22 * 6144 + 2048, 1024), (3, 700, 250), (12, 515, 512)])
+def test_skinny_dgrad_wgrad(nb, N, K):
+    """(5, 2300, 384) and the stacked AdaLN matrix of the Base model go through the 16-byte-load kernel, K % 8 != 0 and
+    nb > 8 through the 4-byte one."""
     g = torch.Generator(device=DEV).manual_seed(7)
-    nb, N, K = 5, 2300, 384
     dY = torch.randn(nb, N, device=DEV, generator=g)
     W = torch.randn(N, K, device=DEV, generator=g).to(BF16)
     X = torch.randn(nb, K, device=DEV, generator=g)
