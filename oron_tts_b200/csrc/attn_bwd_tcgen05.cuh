@@ -97,6 +97,8 @@ __device__ __forceinline__ void ab_stage_store(uint32_t stage, int r, int c0, co
   }
 }
 
+// 17 warps: one SM sub-partition holds five of them, so the register budget is 16384 / (5 * 32) -> 96 per thread (ptxas picks
+// it from the launch bounds; __maxnreg__(120), which the whole register file could hold, fails to launch)
 template <int MODE>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
