@@ -190,7 +190,7 @@ class CFM(nn.Module):
             self.backbone.clear_cache()
 
         tr = ws.traj.view(steps * evals + 1, batch, tpad, self.n_mels)[: steps + 1, :, :max_dur]
-        trajectory = [tr[i].clone() for i in range(steps + 1)]
+        trajectory = list(tr.clone().unbind(0))  # one copy out of the (reused) workspace instead of steps + 1
         out = torch.where(cond_mask_3d, cond, trajectory[-1])
         return out, trajectory
 
