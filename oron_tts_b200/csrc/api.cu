@@ -11,6 +11,7 @@
 #include "attn_fwd4.cuh"
 #include "attn_tcgen05.cuh"
 #include "ffn_tcgen05.cuh"
+#include "gconv_res_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "host_util.h"
 #include "rowwise.cuh"
@@ -244,6 +245,31 @@ static int gemm_prepare(const oron_gemm_desc* d, GemmArgs& a, CUtensorMap& ta, C
   return rc;
 }
 
+// grouped conv with the activation window resident in shared memory (gconv_res_tcgen05.cuh)
+template <int EPI>
+static int launch_gconv_res(const oron_gemm_desc* d, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t st) {
+  using Cfg = GconvResCfg;
+  auto kern = gconv_res_tcgen05_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(int(e), "gconv_res smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  CUtensorMap ta;  // same tensor as the generic kernel's A map, but one box = the whole (128 + taps - 1)-row window
+  if (int rc = make_tmap_bf16(&ta, d->A, uint64_t(d->a_cols), uint64_t(d->rows_per_batch), uint64_t(d->nbatch), uint64_t(d->lda),
+                              uint64_t(d->lda) * uint64_t(d->rows_per_batch), Cfg::kWinRows, 3))
+    return rc;
+  const int tiles_m = ((a.rows_per_batch + GEMM_BM - 1) / GEMM_BM) * a.nbatch;
+  int grid = tiles_m * (a.N / Cfg::BN);
+  const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
+  if (grid > cap) grid = cap;
+  if (grid <= 0) return 0;
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta, tb, a);
+  if (le != cudaSuccess) return fail(int(le), "gconv_res launch: %s", cudaGetErrorString(le));
+  return check_launch("gconv_res_tcgen05");
+}
+
 extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   GemmArgs a;
   CUtensorMap ta, tb;
@@ -251,6 +277,22 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   const int epi = d->epilogue;
   const bool two_sm = d->two_sm != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  {  // 64-channel grouped conv: resident-window kernel (ORON_GCONV_RES=0 keeps the generic per-tap fetch for A/B runs)
+    const char* e = getenv("ORON_GCONV_RES");  // read per call (cheap): tests flip it inside one process
+    const int res = (e && atoi(e) == 0) ? 0 : 1;
+    const int taps = d->taps > 0 ? d->taps : 1;
+    if (res && !two_sm && taps > 1 && taps <= GconvResCfg::kMaxTaps && d->grouped == GEMM_BK && d->cin_blocks == 1 &&
+        d->block_n == GconvResCfg::BN && d->N % GconvResCfg::BN == 0 && d->pad >= 0 && d->pad < taps) {
+#define ORON_GCONV_RES_CASE(EPI_) if (epi == EPI_) return launch_gconv_res<EPI_>(d, tb, a, st);
+      ORON_GCONV_RES_CASE(EPI_BF16)
+      ORON_GCONV_RES_CASE(EPI_F32)
+      ORON_GCONV_RES_CASE(EPI_MISH_MASK_BF16)
+      ORON_GCONV_RES_CASE(EPI_MISH_MASK_RESID)
+      ORON_GCONV_RES_CASE(EPI_SCALE_RESID)
+#undef ORON_GCONV_RES_CASE
+    }
+  }
 
   if (a.a_mn || a.b_mn) {  // backward-pass layouts: compile-time variants of the 2-SM kernel
     const int mnm = a.a_mn | (a.b_mn << 1);

