@@ -319,6 +319,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM2_CASE(256, EPI_QKV_ROPE)
   ORON_GEMM2_CASE(128, EPI_GATE_RESID)
   ORON_GEMM2_CASE(256, EPI_GATE_RESID)
+  ORON_GEMM2_CASE(192, EPI_GATE_RESID)  // N = 1024 out-projection: 6 x 11 tiles = one wave of narrower (cheaper) tiles
   ORON_GEMM2_CASE(128, EPI_EMBED_DUAL)
   ORON_GEMM2_CASE(128, EPI_SCALE_RESID)
   ORON_GEMM2_CASE(256, EPI_SCALE_RESID)

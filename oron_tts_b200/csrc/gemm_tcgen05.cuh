@@ -736,8 +736,8 @@ struct Gemm2Cfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : 7;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kStages = (BN == 256) ? 5 : (BN == 192 ? 6 : 7);
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator; allocations are powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + EPI_STAGE_BYTES;
 };
 

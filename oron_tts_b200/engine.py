@@ -34,6 +34,24 @@ STREAM_K = os.environ.get("ORON_STREAM_K", "1") != "0"
 # launch boundary), so it stays opt-in: ORON_FFN_FUSED=1.
 FFN_FUSED = os.environ.get("ORON_FFN_FUSED", "0") == "1"
 SMALL_ROWS = int(os.environ.get("ORON_SMALL_ROWS", "600"))
+# Whole-tile N = dim GEMMs with a residual epilogue (attention out-projection; FFN down-projection without stream-K) may use
+# 192-wide tiles of the 2-SM kernel: at config 2 the out-projection is 44 tiles of 256 columns on 74 SM pairs -- one wave either
+# way, but a 192-wide k-block is 28 KB of TMA ingest per SM instead of 32 KB and the exposed epilogue is a quarter shorter:
+# 13.8 -> 12.6 us per launch (tools/kernel_bench.py outproj), bit-identical results. ORON_BN192=0 keeps 256 everywhere.
+BN192 = os.environ.get("ORON_BN192", "1") != "0"
+
+
+def resid_tile_width(rows_per_batch: int, nbatch: int, n: int, bn_big: int, pairs: int) -> int:
+    """Tile width (256 or 192) of a whole-tile 2-SM GEMM with N = n: waves x per-k-block TMA ingest of one SM (the bound of the
+    main loop, DESIGN 5.9: 16 KB of A rows + bn / 2 weight rows of 128 bytes), the narrower tile only when strictly cheaper."""
+    if not BN192 or bn_big != 256 or pairs <= 0:
+        return bn_big
+    tiles_mp = (((rows_per_batch + 127) // 128) * nbatch + 1) // 2
+    cost = {}
+    for bn in (256, 192):
+        waves = -(-(tiles_mp * -(-n // bn)) // pairs)
+        cost[bn] = waves * (16384 + bn * 64)
+    return 192 if cost[192] < cost[256] else 256
 BF16 = torch.bfloat16
 F32 = torch.float32
 TILE = 128
@@ -289,6 +307,8 @@ class DiTEngine:
         # runs from the same noise agree bit for bit; set per call by CFM.sample(deterministic=...), part of the graph key
         self.deterministic = False
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (not seen by oron_launch_count)
+        dev = weights.device
+        self.sm_pairs = torch.cuda.get_device_properties(dev).multi_processor_count // 2 if dev.type == "cuda" else 0
 
     # -------------------------------------------------------------------------------------------
     def workspace(self, nb: int, nbp: int, tpad: int, steps: int, keep_traj: bool) -> Workspace:
@@ -408,6 +428,7 @@ class DiTEngine:
         two = R > SMALL_ROWS
         if not two:
             bn_big = 128
+        bn_res = resid_tile_width(tpad, nbp, D, bn_big, self.sm_pairs) if two else bn_big
 
         L.gemm(ws.xb, w.wx, ws.h0, epilogue=L.EPI_EMBED_DUAL, addend=ws.c0, seq_lens=ws.seq_lens, out2=ws.h0b,
                block_n=128, **common)
@@ -429,15 +450,16 @@ class DiTEngine:
                         scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
             L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
                    gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
-                   mask_rows=True, block_n=bn_big, two_sm=two, **common)  # K = dim: too short for stream-K to pay
+                   mask_rows=True, block_n=bn_res, two_sm=two, **common)  # K = dim: too short for stream-K to pay
             L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
                           step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
             fused = FFN_FUSED and STREAM_K and two and not self.deterministic and bn_big == 256 and w.ff_dim % 256 == 0
+            sk_down = STREAM_K and two and not self.deterministic
             up = L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
                         block_n=bn_big, two_sm=two, desc_only=fused, **common)
             down = L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                           gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                          block_n=bn_big, two_sm=two, stream_k=STREAM_K and two and not self.deterministic, desc_only=fused, **common)
+                          block_n=bn_big if sk_down else bn_res, two_sm=two, stream_k=sk_down, desc_only=fused, **common)
             if fused:
                 L.ffn(up, down, ws.ffn_ws)
         o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233

@@ -144,6 +144,35 @@ def test_gemm_gate_residual_masked(L):
     assert torch.equal(x[~mask.squeeze(1)], x0[~mask.squeeze(1)])
 
 
+@pytest.mark.parametrize("N,K,T,lens", [(1024, 1024, 300, [300, 131]), (768, 768, 1408, [1406, 900]), (992, 256, 129, [129, 128]),
+                                        (1024, 4096, 256, [256, 256])])
+def test_gemm_gate_residual_tile_width_192(L, N, K, T, lens):
+    """192-wide tiles of the 2-SM kernel (engine.resid_tile_width: out-projection / whole-tile down-projection, modules.py:279,
+    299, 338, 343): same result as the 256-wide tiles bit for bit (same k order per output), incl. a last tile that is mostly
+    (N = 1024: 64 of 192 columns) or raggedly (N = 992) out of range, and against an fp32 reference."""
+    nb = len(lens)
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(19)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    gate = torch.randn(N, device=DEV, generator=g)
+    lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    x0 = torch.randn(M, N, device=DEV, generator=g)
+    outs = {}
+    for bn in (256, 192):
+        x = x0.clone()
+        L.gemm(A, W, x, epilogue=L.EPI_GATE_RESID, bias=bias, rows_per_batch=T, nbatch=nb, gate=gate, seq_lens=lens_t,
+               mask_rows=True, block_n=bn, two_sm=True)
+        outs[bn] = x
+    assert torch.equal(outs[192], outs[256])
+    mask = (torch.arange(T, device=DEV)[None, :] < lens_t[:, None]).reshape(M, 1)
+    upd = gate * (A.float() @ W.float().t() + bias)
+    ref = x0 + torch.where(mask, upd, torch.zeros_like(upd))
+    assert _rel(outs[192], ref) < 2e-3
+    assert torch.equal(outs[192][~mask.squeeze(1)], x0[~mask.squeeze(1)])
+
+
 def test_conv_gemm_grouped_k31_mish(L):
     """ConvPositionEmbedding conv (modules.py:120-141) as implicit GEMM, both epilogues."""
     nb, T, D, G, KS = 2, 256, 1024, 16, 31

@@ -192,6 +192,43 @@ if what in ("conv",):
         us = e0.elapsed_time(e1) * 1e3 / (20 * 50)
         print(f"  in a CUDA graph, sustained: {us:.1f} us per launch = {fl / us / 1e6:.1f} TFLOP/s", flush=True)
     os.environ.pop("ORON_GCONV_RES")
+if what in ("outproj",):
+    # attention out-projection (N = K = 1024, gated residual) at config 2: tile widths of the 2-SM kernel, sustained graph replay
+    import time
+    g = torch.Generator(device=DEV).manual_seed(7)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    A = rnd(R, 1024).bfloat16()
+    Ws = [(rnd(1024, 1024) / 32).bfloat16() for _ in range(22)]
+    b, gate = rnd(1024), rnd(1024) * 0.01
+    lens = torch.tensor([1406, 1406], device=DEV, dtype=torch.int32)
+    fl = 2 * R * 1024 * 1024
+    ref = None
+    for bn, sk in ((256, False), (192, False), (128, False), (256, True)):
+        xres = torch.zeros(R, 1024, device=DEV)
+        fn = lambda i: L.gemm(A, Ws[i], xres, epilogue=L.EPI_GATE_RESID, bias=b, gate=gate, rows_per_batch=T, nbatch=2, block_n=bn,
+                              two_sm=True, stream_k=sk, seq_lens=lens, mask_rows=True)
+        fn(0)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = xres.clone()
+        print(f"bn={bn} sk={sk}: max |diff| vs bn=256 = {float((xres - ref).abs().max()):.3e}", flush=True)
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            for i in range(3): fn(i)
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=s_):
+                for i in range(22): fn(i)
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                for _ in range(20): gph.replay()
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_)
+            for _ in range(50): gph.replay()
+            e1.record(s_)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (22 * 50)
+        print(f"  out-projection bn={bn} stream_k={sk}: {us:.2f} us per launch = {fl / us / 1e6:.1f} TFLOP/s", flush=True)
 if what in ("ffn",):
     # FeedForward of one DiTBlock at config 2: two launches (up-projection + stream-K down-projection) against the fused launch,
     # 22 per CUDA-graph replay with 22 distinct weight sets (as in the ODE step: weights stream from HBM), sustained clocks
