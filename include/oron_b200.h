@@ -130,6 +130,35 @@ typedef struct oron_gemm_desc {
 int oron_gemm_bf16(const oron_gemm_desc* desc, oron_stream_t stream);
 
 /*
+ * oron_gemm_bf16 (two_sm = 1, ORON_EPI_GATE_RESID, block_n 256 or 192, K-major operands, taps == 1; stream_k allowed) followed,
+ * INSIDE the launch, by the LayerNorm + AdaLN modulation of the updated residual rows: the attention out-projection + gated
+ * residual + the block's second norm (modules.py:279, 338-341), and the FeedForward down-projection + gated residual + the next
+ * block's first norm / AdaLayerNormFinal (modules.py:299, 343; 218, 234). Replaces the oron_ln_modulate launch that would follow:
+ *   out_bf16[r, :] = LN(desc->out[r, :], eps) * (add_one + scale) + shift      for every row r, N = C in {128, 256, 512, 768, 1024},
+ * scale / shift addressed like oron_ln_modulate with desc->step_ptr as the step counter. Rows are normalised as soon as the
+ * tiles of their 256-row block have landed (per-block arrival counters), by all SMs of the launch.
+ * counters: int32 [oron_gemm_ln_counters(rows_per_batch, nbatch)], zeroed ONCE by the caller; every launch leaves them zeroed.
+ * One counter buffer must not be used by two launches that may run concurrently. Same arithmetic as oron_ln_modulate: with
+ * stream_k = 0 the result is bit-identical to the two separate launches.
+ */
+typedef struct oron_ln_tail {
+  const float* scale;
+  const float* shift;  /* or NULL */
+  int64_t mod_ld;
+  int32_t mod_nb;
+  int64_t step_stride;
+  float eps;
+  int32_t add_one;
+  void* out_bf16;
+  int64_t ldo;
+  int32_t* counters;
+  int32_t n_counters;
+} oron_ln_tail;
+
+int32_t oron_gemm_ln_counters(int32_t rows_per_batch, int32_t nbatch);
+int oron_gemm_ln_bf16(const oron_gemm_desc* desc, const oron_ln_tail* ln, oron_stream_t stream);
+
+/*
  * FeedForward of a DiTBlock in ONE launch (modules.py:294-299 and the gated residual modules.py:343; replaces the two
  * oron_gemm_bf16 calls `up` then `down`):   H = act(A W1^T + b1) ; resid += gate * (H W2^T + b2).
  *   up:   ORON_EPI_BF16 (act ORON_ACT_GELU_TANH or NONE), two_sm = 1, block_n = 256, N % 256 == 0; writes H (bf16) to up->out

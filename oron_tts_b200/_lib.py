@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "oron_gemm_bf16",
     "oron_ffn_bf16",
     "oron_ffn_workspace_bytes",
+    "oron_gemm_ln_bf16",
+    "oron_gemm_ln_counters",
     "oron_attention_bf16",
     "oron_attention_workspace_bytes",
     "oron_attention_plan",
@@ -100,6 +102,24 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+class LnTail(ctypes.Structure):
+    """Mirror of ``struct oron_ln_tail``."""
+
+    _fields_ = [
+        ("scale", c_void_p),
+        ("shift", c_void_p),
+        ("mod_ld", c_int64),
+        ("mod_nb", c_int32),
+        ("step_stride", c_int64),
+        ("eps", c_float),
+        ("add_one", c_int32),
+        ("out_bf16", c_void_p),
+        ("ldo", c_int64),
+        ("counters", c_void_p),
+        ("n_counters", c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -125,6 +145,9 @@ def lib() -> ctypes.CDLL:
     L.oron_debug_set_attention_version.restype = None
     L.oron_gemm_bf16.argtypes = [POINTER(GemmDesc), c_void_p]
     L.oron_ffn_bf16.argtypes = [POINTER(GemmDesc), POINTER(GemmDesc), c_void_p, c_int64, c_void_p]
+    L.oron_gemm_ln_bf16.argtypes = [POINTER(GemmDesc), POINTER(LnTail), c_void_p]
+    L.oron_gemm_ln_counters.argtypes = [c_int32, c_int32]
+    L.oron_gemm_ln_counters.restype = c_int32
     L.oron_ffn_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     L.oron_ffn_workspace_bytes.restype = c_int64
     L.oron_attention_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
@@ -288,6 +311,27 @@ def gemm(
     if desc_only:
         return d
     _check(lib().oron_gemm_bf16(ctypes.byref(d), _stream()), "oron_gemm_bf16")
+
+
+def gemm_ln_counters(rows_per_batch: int, nbatch: int, device) -> torch.Tensor:
+    """Zeroed arrival counters of `gemm_ln` (every launch leaves them zeroed; one buffer serves launches in stream order)."""
+    return torch.zeros(int(lib().oron_gemm_ln_counters(rows_per_batch, nbatch)), dtype=torch.int32, device=device)
+
+
+def gemm_ln(desc, counters: torch.Tensor, *, eps: float, scale: torch.Tensor, shift: torch.Tensor | None, out_bf16: torch.Tensor,
+            mod_ld: int = 0, mod_nb: int = 1, step_stride: int = 0, add_one: bool = True) -> None:
+    """`desc` (from ``gemm(..., epilogue=EPI_GATE_RESID, two_sm=True, desc_only=True)``) + LayerNorm / modulation of the updated
+    residual rows into ``out_bf16`` inside the same launch (oron_gemm_ln_bf16); the step counter is the descriptor's."""
+    t = LnTail()
+    t.scale = _ptr(scale, torch.float32, "scale")
+    t.shift = _ptr(shift, torch.float32, "shift")
+    t.mod_ld, t.mod_nb, t.step_stride = int(mod_ld), int(mod_nb), int(step_stride)
+    t.eps, t.add_one = float(eps), int(bool(add_one))
+    t.out_bf16 = _ptr(out_bf16, torch.bfloat16, "out_bf16")
+    t.ldo = _ld(out_bf16)
+    t.counters = _ptr(counters, torch.int32, "counters")
+    t.n_counters = counters.numel()
+    _check(lib().oron_gemm_ln_bf16(ctypes.byref(desc), ctypes.byref(t), _stream()), "oron_gemm_ln_bf16")
 
 
 def ffn_workspace(rows_per_batch: int, nbatch: int, ff_dim: int, device) -> torch.Tensor:

@@ -114,20 +114,36 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 }
 
 
-template <int BN, int EPI, int MNM = 0>
+template <int BN, int EPI, int MNM = 0, int LNT = 0>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int max_ctas, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm2_bf16_tcgen05_kernel<BN, EPI, MNM>;
+  auto kern = gemm2_bf16_tcgen05_kernel<BN, EPI, MNM, LNT>;
   static bool configured = false;
+  static int resident_pairs = 0;  // LNT: the tail waits on other SM pairs, so every cluster of the grid must be resident at once
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(int(e), "gemm2 smem attribute: %s", cudaGetErrorString(e));
+    if (LNT) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(unsigned(num_sms() & ~1));
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return fail(ORON_ERR_UNSUPPORTED, "gemm+ln: cluster occupancy query failed"); }
+      resident_pairs = n;
+    }
     configured = true;
   }
   const int tiles_m = ((a.rows_per_batch + GEMM_BM - 1) / GEMM_BM) * a.nbatch;
   const int tiles = ((tiles_m + 1) / 2) * ((a.N + BN - 1) / BN);
   long long pairs = a.stream_k ? (long long)tiles * a.num_kb : tiles;  // stream-K: every pair takes an equal share of k-blocks
-  const int cap = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
+  int cap = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
+  if (LNT && cap > resident_pairs) cap = resident_pairs;
   if (pairs > cap) pairs = cap;
   if (pairs <= 0) return 0;
   cudaError_t le = launch_pdl(kern, dim3(unsigned(2 * pairs)), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ta, tb, a);
@@ -350,6 +366,42 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   ORON_GEMM_CASE(64, EPI_SCALE_RESID)
 #undef ORON_GEMM_CASE
   return fail(ORON_ERR_UNSUPPORTED, "gemm: no kernel for block_n=%d epilogue=%d", d->block_n, epi);
+}
+
+// ---------------------------------------------------------------------------
+// GEMM + gated residual + LayerNorm / modulation of the updated rows in one launch
+// ---------------------------------------------------------------------------
+extern "C" int32_t oron_gemm_ln_counters(int32_t rows_per_batch, int32_t nbatch) {
+  if (rows_per_batch <= 0 || nbatch <= 0) return 0;
+  const int tiles_m = ((rows_per_batch + GEMM_BM - 1) / GEMM_BM) * nbatch;
+  return ((tiles_m + 1) / 2 + 1) * LN_CNT_STRIDE;
+}
+
+extern "C" int oron_gemm_ln_bf16(const oron_gemm_desc* d, const oron_ln_tail* ln, oron_stream_t stream) {
+  GemmArgs a;
+  CUtensorMap ta, tb;
+  if (int rc = gemm_prepare(d, a, ta, tb)) return rc;
+  if (!ln || !ln->scale || !ln->out_bf16 || !ln->counters) return fail(ORON_ERR_BAD_ARG, "gemm+ln: null pointer");
+  const int taps = d->taps > 0 ? d->taps : 1;
+  if (!d->two_sm || d->epilogue != EPI_GATE_RESID || taps != 1 || a.a_mn || a.b_mn || (d->block_n != 256 && d->block_n != 192))
+    return fail(ORON_ERR_UNSUPPORTED, "gemm+ln: needs two_sm, the GATE_RESID epilogue, K-major operands, taps == 1, block_n 256 or 192");
+  if ((d->N != 1024 && d->N != 768 && d->N != 512 && d->N != 256 && d->N != 128) || d->ldo % 4 != 0 || ln->ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(ln->out_bf16) & 7) != 0)
+    return fail(ORON_ERR_BAD_ARG, "gemm+ln: N in {128, 256, 512, 768, 1024}, 16-byte aligned f32 rows, 8-byte aligned bf16 rows");
+  if (ln->n_counters < oron_gemm_ln_counters(d->rows_per_batch, d->nbatch))
+    return fail(ORON_ERR_BAD_ARG, "gemm+ln: counters buffer of oron_gemm_ln_counters() int32 (zero-initialised) required");
+  a.ln.counters = ln->counters;
+  a.ln.scale = ln->scale;
+  a.ln.shift = ln->shift;
+  a.ln.mod_ld = ln->mod_ld;
+  a.ln.mod_nb = ln->mod_nb > 0 ? ln->mod_nb : 1;
+  a.ln.step_stride = ln->step_stride;
+  a.ln.eps = ln->eps;
+  a.ln.add_one = ln->add_one;
+  a.ln.out = reinterpret_cast<__nv_bfloat16*>(ln->out_bf16);
+  a.ln.ldo = ln->ldo;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d->block_n == 256) return launch_gemm2<256, EPI_GATE_RESID, 0, 1>(ta, tb, a, d->max_ctas, st);
+  return launch_gemm2<192, EPI_GATE_RESID, 0, 1>(ta, tb, a, d->max_ctas, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -75,11 +75,7 @@ struct FfnWalk {
   __device__ int advance(int pos) const { pos += ksinv; return pos >= nkb2 ? pos - nkb2 : pos; }
 };
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
+// ld_acquire_gpu: gemm_tcgen05.cuh
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

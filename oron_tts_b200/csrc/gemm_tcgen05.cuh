@@ -31,6 +31,22 @@ enum GemmEpilogue : int {
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_SILU = 3 };
 
+// LayerNorm + modulation of the UPDATED residual rows as the tail of a 2-SM EPI_GATE_RESID launch (gemm2 kernel, LNT = 1):
+// replaces the ln_modulate launch that follows the attention out-projection / FeedForward down-projection of a DiTBlock
+// (modules.py:338-343). counters: int32 [(ceil(m_tiles / 2) + 1) * 32] (one 128-byte line each), zero on entry; the launch leaves them zero.
+struct LnTail {
+  int* counters;
+  const float* scale;        // (1 + scale) and shift rows of the modulation table: ptr + step * step_stride + (b % mod_nb) * mod_ld
+  const float* shift;
+  long long mod_ld;
+  int mod_nb;
+  long long step_stride;
+  float eps;
+  int add_one;
+  __nv_bfloat16* out;        // [rows, ldo]
+  long long ldo;
+};
+
 struct GemmArgs {
   // problem
   int rows_per_batch;  // rows of A / D per batch element (M when nbatch == 1)
@@ -72,6 +88,7 @@ struct GemmArgs {
   // MN-major SW128 descriptors (SBO = 1024: next 8 K rows, LBO = 8192: next 64 MN elements).
   int a_mn, b_mn;
   DropCfg drop;  // EPI_GELU_DROP_*: stateless dropout mask over element index row * N + col (thresh 0: off)
+  LnTail ln;     // gemm2 kernel with LNT = 1 only
 };
 
 #define ORON_STAMP(slot) do { if (args.dbg) args.dbg[(long long)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
@@ -731,6 +748,107 @@ struct SegWalk {
   }
 };
 
+// ---- LayerNorm tail of the 2-SM kernel (LNT = 1) ----
+// Every epilogue warp publishes the k-blocks it has folded into the residual rows of its m-tile pair (fence, then one
+// relaxed add per warp); once all n-tiles x k-blocks x 16 warps of a pair have arrived its 256 rows are final. The rows
+// are dealt round-robin to all epilogue warps of the grid (every CTA is resident: grid <= SM count, one CTA per SM, and
+// nobody waits before its own GEMM work is done, so the waits cannot deadlock; they are bounded all the same).
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// counters sit LN_CNT_STRIDE ints (one 128-byte line) apart; ONE lane per warp polls (37 k threads polling a dozen words would
+// queue up in front of the L2 slices that also have to take the arrivals), the warp barrier hands the acquire to the rest
+constexpr int LN_CNT_STRIDE = 32;
+__device__ __forceinline__ void ln_tail_wait(const int* cnt, int target, int lane) {
+  if (lane == 0 && ld_acquire_gpu(cnt) < target) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(cnt) < target) {
+      __nanosleep(100);
+      if (clock64() - t0 > ORON_WATCHDOG_CYCLES) __trap();
+    }
+  }
+  __syncwarp();
+}
+// One warp, up to LN_TAIL_NR rows at a time: with eight warps per SM the tail is bound by memory LATENCY, so the rows of a batch
+// are fetched together -- with 16-byte cp.async.cg copies (L2, past L1: other SMs wrote x during this launch) into the warp's
+// slice of the operand ring, which is idle once the CTA's last accumulator has been drained (the register file has no room
+// for a second row: 168 registers per thread with ten warps per CTA). Every lane copies exactly the 16-byte pieces it later
+// reads, so its own wait_group is all the synchronisation needed. Per row the arithmetic of ln_modulate_kernel<C>
+// (rowwise.cuh), statement for statement: the tail and the separate launch agree bit for bit. C = 128 * V4 <= 1024.
+constexpr int LN_TAIL_NR = 4;
+constexpr int LN_TAIL_WARP_BYTES = LN_TAIL_NR * 4096;
+template <int V4>
+__device__ __forceinline__ void ln_tail_rows_t(const GemmArgs& a, const long long (&gr)[LN_TAIL_NR], const long long (&moff)[LN_TAIL_NR],
+                                               const int nr, const int lane, const uint32_t buf) {
+  constexpr int C = 128 * V4, NR = LN_TAIL_NR;
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+    if (r < nr) {
+      const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.out) + gr[r] * a.ldo);
+#pragma unroll
+      for (int i = 0; i < V4; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(buf + uint32_t(r * 4096 + (lane + 32 * i) * 16)), "l"(xr + lane + 32 * i)
+                     : "memory");
+    }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const float one = a.ln.add_one ? 1.f : 0.f;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    if (r >= nr) break;
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                   : "r"(buf + uint32_t(r * 4096 + (lane + 32 * i) * 16))
+                   : "memory");
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.0f / C) + a.ln.eps);
+    const float4* sc = reinterpret_cast<const float4*>(a.ln.scale + moff[r]);
+    const float4* sh = a.ln.shift ? reinterpret_cast<const float4*>(a.ln.shift + moff[r]) : nullptr;
+    uint2* orow = reinterpret_cast<uint2*>(a.ln.out + gr[r] * a.ln.ldo);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const float4 g = __ldg(sc + lane + 32 * i);
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sh) h = __ldg(sh + lane + 32 * i);
+      float4 y;
+      y.x = v[i].x * rstd * (one + g.x) + h.x;
+      y.y = v[i].y * rstd * (one + g.y) + h.y;
+      y.z = v[i].z * rstd * (one + g.z) + h.z;
+      y.w = v[i].w * rstd * (one + g.w) + h.w;
+      orow[lane + 32 * i] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    }
+  }
+}
+__device__ __forceinline__ void ln_tail_rows(const GemmArgs& a, const long long (&gr)[LN_TAIL_NR], const long long (&moff)[LN_TAIL_NR],
+                                             const int nr, const int lane, const uint32_t buf) {
+  switch (a.N >> 7) {  // warp-uniform
+    case 8: ln_tail_rows_t<8>(a, gr, moff, nr, lane, buf); break;
+    case 6: ln_tail_rows_t<6>(a, gr, moff, nr, lane, buf); break;
+    case 4: ln_tail_rows_t<4>(a, gr, moff, nr, lane, buf); break;
+    case 2: ln_tail_rows_t<2>(a, gr, moff, nr, lane, buf); break;
+    case 1: ln_tail_rows_t<1>(a, gr, moff, nr, lane, buf); break;
+    default: break;  // the host admits only these widths (the ones ln_modulate has kernels for)
+  }
+}
+
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
@@ -743,12 +861,13 @@ struct Gemm2Cfg {
 
 // MNM: bit 0 = A is MN-major, bit 1 = B is MN-major (compile-time: the K-major instantiations used by the inference path keep
 // constant descriptors / instruction descriptor in the single-thread MMA issue loop)
-template <int BN, int EPI, int MNM = 0>
+template <int BN, int EPI, int MNM = 0, int LNT = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int kStages = Cfg::kStages;
+  static_assert(LNT == 0 || kStages * Cfg::kStageBytes >= GEMM_EPI_WARPS * LN_TAIL_WARP_BYTES, "LN tail row buffers live in the operand ring");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
@@ -897,6 +1016,40 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));
       if (threadIdx.x == 64 && it < 2) ORON_STAMP(7 + 2 * it);
+      if constexpr (LNT != 0) {  // this warp's share of k-blocks [kb0, kb1) of the tile is in the residual rows
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(args.ln.counters + (tile % tiles_mp) * LN_CNT_STRIDE, w.kb1 - w.kb0);
+      }
+    }
+    if constexpr (LNT != 0) {
+      const long long rows = (long long)args.rows_per_batch * args.nbatch;
+      const int total_warps = int(gridDim.x) * GEMM_EPI_WARPS;
+      const int target = tiles_n * num_kb * 2 * GEMM_EPI_WARPS;
+      const long long step = args.step_ptr ? (long long)__ldg(args.step_ptr) : 0ll;
+      for (long long g0 = (long long)blockIdx.x * GEMM_EPI_WARPS + (warp - 2); g0 < rows; g0 += (long long)LN_TAIL_NR * total_warps) {
+        long long gr[LN_TAIL_NR], moff[LN_TAIL_NR];
+        int nr = 0;
+#pragma unroll
+        for (int r = 0; r < LN_TAIL_NR; ++r) {
+          gr[r] = g0 + (long long)r * total_warps;
+          moff[r] = 0;
+          if (gr[r] < rows) {
+            nr = r + 1;
+            const int b = int(gr[r] / args.rows_per_batch);
+            const int t = int(gr[r] - (long long)b * args.rows_per_batch);
+            moff[r] = step * args.ln.step_stride + (long long)(b % args.ln.mod_nb) * args.ln.mod_ld;
+            ln_tail_wait(args.ln.counters + ((b * tiles_m_pb + t / GEMM_BM) >> 1) * LN_CNT_STRIDE, target, lane);
+          }
+        }
+        ln_tail_rows(args, gr, moff, nr, lane, smem_base + uint32_t(warp - 2) * LN_TAIL_WARP_BYTES);
+      }
+      __syncwarp();
+      if (lane == 0) {  // the last warp out of the whole grid re-arms the counters for the next launch
+        if (atomicAdd(args.ln.counters + tiles_mp * LN_CNT_STRIDE, 1) == total_warps - 1) {
+          for (int j = 0; j <= tiles_mp; ++j) args.ln.counters[j * LN_CNT_STRIDE] = 0;
+        }
+      }
     }
   }
 

@@ -39,6 +39,14 @@ SMALL_ROWS = int(os.environ.get("ORON_SMALL_ROWS", "600"))
 # way, but a 192-wide k-block is 28 KB of TMA ingest per SM instead of 32 KB and the exposed epilogue is a quarter shorter:
 # 13.8 -> 12.6 us per launch (tools/kernel_bench.py outproj), bit-identical results. ORON_BN192=0 keeps 256 everywhere.
 BN192 = os.environ.get("ORON_BN192", "1") != "0"
+# Opt-in (ORON_LN_TAIL=1), a measured NEGATIVE result: the LayerNorm + modulation that follows each gated-residual GEMM (a
+# block's second norm after the out-projection; the next block's first norm / AdaLayerNormFinal after the down-projection) run
+# as the TAIL of that GEMM's launch (oron_gemm_ln_bf16: rows are normalised by all SMs as soon as the tiles of their 256-row
+# block have landed; 44 of the 45 ln_modulate launches of a Base NFE disappear; bit-identical without stream-K). Same-box A/B at
+# config 2: 2.905 -> 3.01 ms per NFE. The separate ln_modulate launch needs no shared memory, so it is resident next to the
+# GEMM's CTAs before they finish and -- more important -- the NEXT GEMM's CTAs move in and run their prologue (barriers, TMEM,
+# cluster sync) while it executes; a tail keeps the SM's shared memory until the norm is done.
+LN_TAIL = os.environ.get("ORON_LN_TAIL", "0") == "1"
 
 
 def resid_tile_width(rows_per_batch: int, nbatch: int, n: int, bn_big: int, pairs: int) -> int:
@@ -275,6 +283,7 @@ class Workspace:
         self.hid = z(R, w.ff_dim, dt=BF16)
         with torch.inference_mode(False):
             self.ffn_ws = L.ffn_workspace(tpad, nbp, w.ff_dim, dev)
+            self.ln_cnt = L.gemm_ln_counters(tpad, nbp, dev)  # arrival counters of the GEMM + LayerNorm launches (self-resetting)
         self.v = z(R, M)
         self.vg = z(Rb, M)
         self.step = z(1, dt=torch.int32)
@@ -440,31 +449,40 @@ class DiTEngine:
                cin_blocks=c2["gsz"] // 64, pad=c2["taps"] // 2, grouped=c2["gsz"], block_n=64, seq_lens=ws.seq_lens,
                addend=ws.h0, **common)
 
+        ln = dict(eps=1e-6, mod_ld=mld, mod_nb=mod_nb, step_stride=sstride, add_one=True, out_bf16=ws.nrm)
+        # norm that follows a gated-residual GEMM: inside its launch (tail) when the 2-SM kernel runs and N = dim fits
+        tail = LN_TAIL and two and not FFN_FUSED and D in (128, 256, 512, 768, 1024) and bn_big == 256
+        of = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
+        L.ln_modulate(ws.xres, scale=tab[D:], shift=tab, step_ptr=step_ptr, **ln, **common)  # block 0, first norm
         for i, blk in enumerate(w.blocks):
             o = i * 6 * D  # (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp) — modules.py:215-217
-            L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + D:], shift=tab[o:], mod_ld=mld, mod_nb=mod_nb,
-                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
+            last = i == w.depth - 1
             L.gemm(ws.nrm, blk["wqkv"], ws.qkv, epilogue=L.EPI_QKV_ROPE, bias=blk["bqkv"], rope_cos=cos, rope_sin=sin,
                    rope_cols=2 * w.inner, f16_from_col=2 * w.inner, block_n=bn_big, two_sm=two, **common)
             L.attention(ws.qkv, ws.ao, nbatch=nbp, rows_per_batch=tpad, heads=w.heads, seq_lens=ws.seq_lens,
                         scale=1.0 / math.sqrt(w.dim_head), workspace=ws.attn_ws)
-            L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
-                   gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
-                   mask_rows=True, block_n=bn_res, two_sm=two, **common)  # K = dim: too short for stream-K to pay
-            L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], mod_ld=mld, mod_nb=mod_nb,
-                          step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
+            d = L.gemm(ws.ao, blk["wo"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["bo"], gate=tab[o + 2 * D:],
+                       gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, seq_lens=ws.seq_lens,
+                       mask_rows=True, block_n=bn_res, two_sm=two, desc_only=tail, **common)  # K = dim: too short for stream-K to pay
+            if tail:
+                L.gemm_ln(d, ws.ln_cnt, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], **ln)
+            else:
+                L.ln_modulate(ws.xres, scale=tab[o + 4 * D:], shift=tab[o + 3 * D:], step_ptr=step_ptr, **ln, **common)
             fused = FFN_FUSED and STREAM_K and two and not self.deterministic and bn_big == 256 and w.ff_dim % 256 == 0
             sk_down = STREAM_K and two and not self.deterministic
             up = L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
                         block_n=bn_big, two_sm=two, desc_only=fused, **common)
             down = L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                           gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
-                          block_n=bn_big if sk_down else bn_res, two_sm=two, stream_k=sk_down, desc_only=fused, **common)
+                          block_n=bn_big if sk_down else bn_res, two_sm=two, stream_k=sk_down, desc_only=fused or tail, **common)
             if fused:
                 L.ffn(up, down, ws.ffn_ws)
-        o = w.depth * 6 * D  # AdaLayerNormFinal: (scale, shift) — modules.py:233
-        L.ln_modulate(ws.xres, eps=1e-6, scale=tab[o:], shift=tab[o + D:], mod_ld=mld, mod_nb=mod_nb,
-                      step_stride=sstride, step_ptr=step_ptr, add_one=True, out_bf16=ws.nrm, **common)
+            # next block's first norm (shift, scale at o + 6D) or the final norm (scale, shift)
+            nsc, nsh = (tab[of:], tab[of + D:]) if last else (tab[o + 7 * D:], tab[o + 6 * D:])
+            if tail:
+                L.gemm_ln(down, ws.ln_cnt, scale=nsc, shift=nsh, **ln)
+            else:
+                L.ln_modulate(ws.xres, scale=nsc, shift=nsh, step_ptr=step_ptr, **ln, **common)
         L.gemm(ws.nrm, w.wp, ws.v, epilogue=L.EPI_F32, bias=w.bp, block_n=128, **common)
 
     def euler(self, ws: Workspace, *, cfg: float, has_uncond: bool, method: int = 0) -> None:

@@ -173,6 +173,50 @@ def test_gemm_gate_residual_tile_width_192(L, N, K, T, lens):
     assert torch.equal(outs[192][~mask.squeeze(1)], x0[~mask.squeeze(1)])
 
 
+@pytest.mark.parametrize("N,K,T,lens,bn,sk", [(1024, 1024, 1408, [1406, 1406], 192, False), (1024, 4096, 1408, [1406, 1000], 256, True),
+                                              (1024, 1024, 300, [300, 131, 7], 256, False), (768, 3072, 700, [700], 256, True),
+                                              (768, 768, 129, [129, 77], 192, False), (1024, 4096, 1024, [1024] * 8, 256, True)])
+def test_gemm_ln_tail(L, N, K, T, lens, bn, sk):
+    """Gated-residual GEMM with the LayerNorm + modulation of the updated rows as the tail of the launch (oron_gemm_ln_bf16;
+    modules.py:338-343 followed by :218 / :341 / :234) against the two separate launches: bit-identical without stream-K,
+    within rounding of the sum order with it; odd m-tile counts (a phantom tile in the last pair), several batch elements,
+    masked rows, a per-step modulation table, and three launches on ONE counter buffer (the launch re-arms it)."""
+    nb = len(lens)
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(29)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    steps = 3
+    table = torch.randn(steps, 6 * N, device=DEV, generator=g) * 0.3
+    tab = table.view(-1)
+    step = torch.tensor([1], device=DEV, dtype=torch.int32)
+    lens_t = torch.tensor(lens, device=DEV, dtype=torch.int32)
+    x0 = torch.randn(M, N, device=DEV, generator=g)
+    kw = dict(epilogue=L.EPI_GATE_RESID, bias=bias, rows_per_batch=T, nbatch=nb, gate=tab[2 * N:], gate_step_stride=6 * N,
+              step_ptr=step, seq_lens=lens_t, mask_rows=True, block_n=bn, two_sm=True, stream_k=sk)
+    lnkw = dict(eps=1e-6, scale=tab[4 * N:], shift=tab[3 * N:], step_stride=6 * N, add_one=True)
+    x_ref = x0.clone()
+    L.gemm(A, W, x_ref, **kw)
+    n_ref = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    L.ln_modulate(x_ref, rows_per_batch=T, nbatch=nb, step_ptr=step, out_bf16=n_ref, **lnkw)
+    cnt = L.gemm_ln_counters(T, nb, DEV)
+    for rep in range(3):
+        x = x0.clone()
+        n_out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        d = L.gemm(A, W, x, desc_only=True, **kw)
+        L.gemm_ln(d, cnt, out_bf16=n_out, **lnkw)
+        torch.cuda.synchronize()
+        assert int(cnt.abs().sum()) == 0, rep
+        if sk:
+            assert _rel(x, x_ref) < 1e-6
+            assert _rel(n_out, n_ref) < 4e-3
+            assert torch.isfinite(n_out.float()).all()
+        else:
+            assert torch.equal(x, x_ref)
+            assert torch.equal(n_out, n_ref)
+
+
 def test_conv_gemm_grouped_k31_mish(L):
     """ConvPositionEmbedding conv (modules.py:120-141) as implicit GEMM, both epilogues."""
     nb, T, D, G, KS = 2, 256, 1024, 16, 31
