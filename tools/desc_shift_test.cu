@@ -62,6 +62,30 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
     tc_fence_before();
     __syncthreads();
   }
+  // timing: REP x 64 back-to-back MMAs (M128 N64 K16) through the A descriptor at row shift s, one commit per 64; cycles per MMA
+  // land in out[NSHIFT * 128 * 64 + s] (does an operand that straddles the 1024-byte swizzle atoms cost extra shared-memory reads?)
+  if (use_base_offset == 0) {
+    uint32_t ph = NSHIFT & 1u;
+    for (int shift = 0; shift < 16; ++shift) {
+      long long t0 = 0;
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+        const uint64_t adesc = make_smem_desc_sw128(sA + uint32_t(shift) * 128u, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(sB, 16, 1024);
+        t0 = clock64();
+        for (int rep = 0; rep < 16; ++rep)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, 1u);
+        umma_commit(bar2);
+      }
+      mbar_wait(bar2, ph, 3);
+      ph ^= 1u;
+      if (threadIdx.x == 0) out[(long long)NSHIFT * 128 * 64 + shift] = float(clock64() - t0) / 64.f;
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 64); }
 }
 
@@ -89,13 +113,13 @@ int main() {
   for (int i = 0; i < 64 * 64; ++i) { fB[i] = float(rand() % 5 - 2); hB[i] = __float2bfloat16(fB[i]); }
   void *dA, *dB;
   float* dO;
-  cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dO, NSHIFT * 128 * 64 * 4);
+  cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dO, (NSHIFT * 128 * 64 + 64) * 4);
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
   CUtensorMap ta = make_map(dA, 64, 256, 128), tb = make_map(dB, 64, 64, 64);
   const int smem = 32768 + 8192 + 1024 + 64;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  std::vector<float> hO(NSHIFT * 128 * 64);
+  std::vector<float> hO(NSHIFT * 128 * 64 + 64);
   for (int ubo = 0; ubo < 2; ++ubo) {
     cudaMemset(dO, 0, hO.size() * 4);
     probe_kernel<<<1, 128, smem>>>(ta, tb, dO, ubo);
@@ -113,6 +137,11 @@ int main() {
       if (ok) printf(" %d", s);
     }
     printf("\n");
+    if (ubo == 0) {
+      printf("cycles per M128 N64 K16 MMA (64 back to back) by row shift of the A descriptor:");
+      for (int s2 = 0; s2 < 16; ++s2) printf(" %d:%.1f", s2, hO[NSHIFT * 128 * 64 + s2]);
+      printf("\n");
+    }
   }
   return 0;
 }
