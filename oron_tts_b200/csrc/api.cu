@@ -329,6 +329,7 @@ extern "C" int oron_gemm_bf16(const oron_gemm_desc* d, oron_stream_t stream) {
   if (two_sm && d->block_n == BN_ && epi == EPI_) return launch_gemm2<BN_, EPI_>(ta, tb, a, d->max_ctas, st);
   ORON_GEMM2_CASE(128, EPI_BF16)
   ORON_GEMM2_CASE(256, EPI_BF16)
+  ORON_GEMM2_CASE(224, EPI_BF16)  // FFN up-projection at config 2: 19 x 11 = 209 tiles fill three waves of 74 SM pairs with cheaper k-blocks
   ORON_GEMM2_CASE(128, EPI_F32)
   ORON_GEMM2_CASE(256, EPI_F32)
   ORON_GEMM2_CASE(128, EPI_QKV_ROPE)

@@ -446,10 +446,12 @@ __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmArgs& args, con
 }
 
 // FACT >= 0 (EPI_BF16 only): the activation is a compile-time choice, so only that body is instantiated (ffn_tcgen05.cuh)
+// nch: 32-column chunks this warp drains (HN / 32, fewer for the upper half of an uneven split: BN = 224 is 128 + 96)
 template <int BN, int EPI, int HN, int FACT = -1>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const uint32_t trow, const int b,
                                                    const int t_base, const int n0, const int cbeg,
-                                                   const uint32_t stage, const int lane, const EpiCols<HN>& pc) {
+                                                   const uint32_t stage, const int lane, const EpiCols<HN>& pc,
+                                                   const int nch = HN / 32) {
   const int rsub = lane >> 3;        // row inside a 4-row group
   const int c4 = (lane & 7) * 4;     // first of the 4 columns this lane owns inside a 32-column chunk
   const int seq_len = args.seq_lens ? args.seq_lens[b] : args.rows_per_batch;
@@ -523,7 +525,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, const u
     // 74 % icc hit rate, stall_no_instruction second only to the accumulator wait). The prefetched per-column
     // operands are picked out of their registers with selects.
 #pragma unroll 1
-    for (int j = 0; j < HN / 32; ++j) {
+    for (int j = 0; j < nch; ++j) {
       const int c0 = cbeg + 32 * j;
       float4 b4 = pc.b4[0], g4 = pc.g4[0];
 #pragma unroll
@@ -854,7 +856,7 @@ struct Gemm2Cfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : (BN == 192 ? 6 : 7);
+  static constexpr int kStages = (BN == 256 || BN == 224) ? 5 : (BN == 192 ? 6 : 7);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;  // double-buffered accumulator; allocations are powers of two
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + EPI_STAGE_BYTES;
 };
@@ -992,8 +994,11 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else {
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;
-    constexpr int HN = BN / 2;
+    // the tile's columns are split between the two warps of a lane quarter in 32-column chunks: evenly, except BN = 224 = 128 + 96
+    constexpr int HN = (BN == 224) ? 128 : BN / 2;
+    static_assert(EPI != EPI_QKV_ROPE || BN != 224, "the RoPE epilogue walks whole 64-wide heads per half");
     const int cbeg = chalf * HN;
+    const int nch = (BN == 224 && chalf == 1) ? 3 : HN / 32;
     int it = 0;
     for (SegWalk w(sk, pair_id, num_pairs, num_tiles, num_kb); w.next(); ++it) {
       const int tile = w.tile;
@@ -1011,7 +1016,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int t_base = m_tile < tiles_m ? (m_tile % tiles_m_pb) * GEMM_BM + q * 32 : args.rows_per_batch;
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
       gemm_epilogue_tile<BN, EPI, HN>(args, trow, b, t_base, n_tile * BN, cbeg,
-                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane, pc);
+                                      bar_base + 256u + uint32_t(warp - 2) * EPI_STAGE_BYTES_PER_WARP, lane, pc, nch);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));

@@ -39,6 +39,9 @@ SMALL_ROWS = int(os.environ.get("ORON_SMALL_ROWS", "600"))
 # way, but a 192-wide k-block is 28 KB of TMA ingest per SM instead of 32 KB and the exposed epilogue is a quarter shorter:
 # 13.8 -> 12.6 us per launch (tools/kernel_bench.py outproj), bit-identical results. ORON_BN192=0 keeps 256 everywhere.
 BN192 = os.environ.get("ORON_BN192", "1") != "0"
+# 224-wide tiles for the FeedForward up-projection where the same cost model prefers them (up_tile_width): opt-in, measured no
+# gain at config 2 (same-box A/B 2.878 vs 2.889 ms per NFE: the 19th column tile carries 64 useful columns at the full k-loop)
+BN224 = os.environ.get("ORON_BN224", "0") == "1"
 # Opt-in (ORON_LN_TAIL=1), a measured NEGATIVE result: the LayerNorm + modulation that follows each gated-residual GEMM (a
 # block's second norm after the out-projection; the next block's first norm / AdaLayerNormFinal after the down-projection) run
 # as the TAIL of that GEMM's launch (oron_gemm_ln_bf16: rows are normalised by all SMs as soon as the tiles of their 256-row
@@ -49,17 +52,30 @@ BN192 = os.environ.get("ORON_BN192", "1") != "0"
 LN_TAIL = os.environ.get("ORON_LN_TAIL", "0") == "1"
 
 
-def resid_tile_width(rows_per_batch: int, nbatch: int, n: int, bn_big: int, pairs: int) -> int:
-    """Tile width (256 or 192) of a whole-tile 2-SM GEMM with N = n: waves x per-k-block TMA ingest of one SM (the bound of the
-    main loop, DESIGN 5.9: 16 KB of A rows + bn / 2 weight rows of 128 bytes), the narrower tile only when strictly cheaper."""
+def tile_width(rows_per_batch: int, nbatch: int, n: int, bn_big: int, pairs: int, narrow: int) -> int:
+    """Tile width (256 or `narrow`) of a whole-tile 2-SM GEMM with N = n: waves x per-k-block TMA ingest of one SM (the bound of
+    the main loop, DESIGN 5.9: 16 KB of A rows + bn / 2 weight rows of 128 bytes), the narrower tile only when strictly cheaper."""
     if not BN192 or bn_big != 256 or pairs <= 0:
         return bn_big
     tiles_mp = (((rows_per_batch + 127) // 128) * nbatch + 1) // 2
     cost = {}
-    for bn in (256, 192):
+    for bn in (256, narrow):
         waves = -(-(tiles_mp * -(-n // bn)) // pairs)
         cost[bn] = waves * (16384 + bn * 64)
-    return 192 if cost[192] < cost[256] else 256
+    return narrow if cost[narrow] < cost[256] else 256
+
+
+def resid_tile_width(rows_per_batch: int, nbatch: int, n: int, bn_big: int, pairs: int) -> int:
+    """Gated-residual GEMMs (out-projection, whole-tile down-projection): 256 or 192 columns."""
+    return tile_width(rows_per_batch, nbatch, n, bn_big, pairs, 192)
+
+
+def up_tile_width(rows_per_batch: int, nbatch: int, n: int, bn_big: int, pairs: int) -> int:
+    """FeedForward up-projection: 256 or 224 columns (config 2: 16 x 11 = 176 tiles of 256 are 2.38 waves on 74 SM pairs, i.e.
+    three; 19 x 11 = 209 tiles of 224 are three waves as well, of k-blocks that cost 30 KB of ingest instead of 32)."""
+    return tile_width(rows_per_batch, nbatch, n, bn_big, pairs, 224) if BN224 else bn_big
+
+
 BF16 = torch.bfloat16
 F32 = torch.float32
 TILE = 128
@@ -438,6 +454,7 @@ class DiTEngine:
         if not two:
             bn_big = 128
         bn_res = resid_tile_width(tpad, nbp, D, bn_big, self.sm_pairs) if two else bn_big
+        bn_up = up_tile_width(tpad, nbp, w.ff_dim, bn_big, self.sm_pairs) if two and not FFN_FUSED else bn_big
 
         L.gemm(ws.xb, w.wx, ws.h0, epilogue=L.EPI_EMBED_DUAL, addend=ws.c0, seq_lens=ws.seq_lens, out2=ws.h0b,
                block_n=128, **common)
@@ -471,7 +488,7 @@ class DiTEngine:
             fused = FFN_FUSED and STREAM_K and two and not self.deterministic and bn_big == 256 and w.ff_dim % 256 == 0
             sk_down = STREAM_K and two and not self.deterministic
             up = L.gemm(ws.nrm, blk["w1"], ws.hid, epilogue=L.EPI_BF16, bias=blk["b1"], act=L.ACT_GELU_TANH,
-                        block_n=bn_big, two_sm=two, desc_only=fused, **common)
+                        block_n=bn_up, two_sm=two, desc_only=fused, **common)
             down = L.gemm(ws.hid, blk["w2"], ws.xres, epilogue=L.EPI_GATE_RESID, bias=blk["b2"], gate=tab[o + 5 * D:],
                           gate_ld=mld, gate_nb=mod_nb, gate_step_stride=sstride, step_ptr=step_ptr, mask_rows=False,
                           block_n=bn_big if sk_down else bn_res, two_sm=two, stream_k=sk_down, desc_only=fused or tail, **common)

@@ -217,6 +217,26 @@ def test_gemm_ln_tail(L, N, K, T, lens, bn, sk):
             assert torch.equal(n_out, n_ref)
 
 
+@pytest.mark.parametrize("N,K,T,nb", [(4096, 1024, 1408, 2), (3072, 768, 300, 3), (4000, 256, 129, 1)])
+def test_gemm_tile_width_224(L, N, K, T, nb):
+    """224-wide tiles of the 2-SM kernel (engine.up_tile_width: the FeedForward up-projection, modules.py:294-297; the tile's
+    columns are drained as 128 + 96 by the two warps of a lane quarter): bit-identical to the 256-wide tiles (same k order per
+    output) incl. a last tile that is mostly (N = 4096: 64 of 224 columns) or raggedly (N = 4000) out of range; fp32 reference."""
+    M = nb * T
+    g = torch.Generator(device=DEV).manual_seed(37)
+    A = _bf(torch.randn(M, K, device=DEV, generator=g))
+    W = _bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    outs = {}
+    for bn in (256, 224):
+        o = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        L.gemm(A, W, o, epilogue=L.EPI_BF16, bias=bias, act=L.ACT_GELU_TANH, rows_per_batch=T, nbatch=nb, block_n=bn, two_sm=True)
+        outs[bn] = o
+    assert torch.equal(outs[224], outs[256])
+    ref = F.gelu(A.float() @ W.float().t() + bias, approximate="tanh")
+    assert _rel(outs[224], ref) < 6e-3
+
+
 def test_conv_gemm_grouped_k31_mish(L):
     """ConvPositionEmbedding conv (modules.py:120-141) as implicit GEMM, both epilogues."""
     nb, T, D, G, KS = 2, 256, 1024, 16, 31
